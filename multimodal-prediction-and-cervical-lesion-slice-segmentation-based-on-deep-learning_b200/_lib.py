@@ -1,0 +1,103 @@
+"""ctypes binding of the C ABI declared in include/cervix_b200.h.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a) as
+``csrc/libcervix_b200.so``.  There is no fallback: if the library is missing the import of any
+compute path fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcervix_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+EUNSUPPORTED = -3
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "pad", "dil",
+                                          "ho", "wo", "dtype")]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_D = C.POINTER(ConvDesc)
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+PROTOTYPES = {
+    "cvx_abi_version": [],
+    "cvx_last_error": [],
+    "cvx_device_is_sm100": [],
+    "cvx_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "cvx_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "cvx_pack_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _P],
+    "cvx_pack_dw_weight": [_P, _P, _I, _P],
+    "cvx_unpack_dw_wgrad": [_P, _P, _I, _P],
+    "cvx_copy_channels": [_P, _I, _I, _P, _I, _I, _L, _I, _I, _P],
+    "cvx_conv_fwd": [_D, _P, _P, _P, _P, _P],
+    "cvx_conv_dgrad": [_D, _P, _P, _P, _P],
+    "cvx_conv_wgrad": [_D, _P, _P, _P, _P],
+    "cvx_bias_grad": [_P, _P, _P, _L, _I, _I, _P],
+    "cvx_conv_fwd_tc": [_D, _P, _P, _P, _P, _P],
+    "cvx_conv_dgrad_tc": [_D, _P, _P, _P, _P],
+    "cvx_conv_wgrad_tc": [_D, _P, _P, _P, _P],
+    "cvx_subsample": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_subsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_dwconv_fwd": [_D, _P, _P, _P, _I, _P],
+    "cvx_dwconv_bwd_data": [_D, _P, _P, _P, _P, _I, _P],
+    "cvx_dwconv_bwd_weight": [_D, _P, _P, _P, _P, _I, _P],
+    "cvx_bn_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _P],
+    "cvx_bn_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "cvx_relu_fwd": [_P, _P, _L, _I, _P],
+    "cvx_relu_bwd": [_P, _P, _P, _L, _I, _P],
+    "cvx_add": [_P, _P, _P, _L, _I, _P],
+    "cvx_spatial_reduce": [_P, _P, _I, _I, _I, _F, _I, _P],
+    "cvx_spatial_broadcast": [_P, _P, _I, _I, _I, _F, _I, _P],
+    "cvx_upsample_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_upsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_upsample_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_upsample_to_nchw_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_dropout_fwd": [_P, _P, _P, _L, _F, C.c_uint64, _I, _P],
+    "cvx_dropout_bwd": [_P, _P, _P, _L, _F, _I, _P],
+    "cvx_seg_loss_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
+    "cvx_seg_loss_finalize": [_P, _P, _I, _F, _F, _P],
+    "cvx_seg_loss_grad": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P],
+    "cvx_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],
+}
+_RESTYPES = {"cvx_last_error": C.c_char_p}
+
+_lib = None
+
+
+class CervixError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcervix_b200.so and bind every symbol of include/cervix_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CervixError(
+            "cervix_b200: %s not found - build the CUDA extension first "
+            "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.cvx_abi_version() != 1:
+        raise CervixError("cervix_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = _lib.cvx_last_error().decode("utf-8", "replace") if _lib is not None else ""
+        raise CervixError("%s failed (rc=%d): %s" % (what, rc, msg))

@@ -1,0 +1,380 @@
+"""Tensor-level wrapper over the C ABI (include/cervix_b200.h).
+
+Every method takes/returns torch tensors that live on a CUDA device, hands their
+``data_ptr()`` to the library together with the current torch stream, and returns freshly
+allocated outputs (torch's caching allocator owns all memory - the library allocates
+nothing).  Activations are NHWC (``[n, h, w, c]`` contiguous), fp32 or bf16.
+
+This is the ONLY compute backend of the product: it raises when the shared library is
+missing or a tensor is not on a CUDA device.  (tests/emu_backend.py implements the same
+method set with plain torch ops, as the per-kernel specification the CUDA results are
+checked against, and lets the host-side graph logic be exercised on CPU-only CI.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise TypeError("cervix_b200 activations must be float32 or bfloat16, got %s" % t.dtype)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class ConvGeom:
+    """Geometry of one nn.Conv2d call on an NHWC input."""
+    __slots__ = ("n", "h", "w", "cin", "cout", "kh", "kw", "stride", "pad", "dil", "ho", "wo")
+
+    def __init__(self, n, h, w, cin, cout, kh, kw, stride, pad, dil):
+        self.n, self.h, self.w, self.cin, self.cout = n, h, w, cin, cout
+        self.kh, self.kw, self.stride, self.pad, self.dil = kh, kw, stride, pad, dil
+        self.ho = (h + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        self.wo = (w + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+
+    def desc(self, dtype: int) -> ConvDesc:
+        return ConvDesc(self.n, self.h, self.w, self.cin, self.cout, self.kh, self.kw, self.stride, self.pad,
+                        self.dil, self.ho, self.wo, dtype)
+
+
+class CudaBackend:
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.CervixError("cervix_b200 needs a CUDA device; there is no CPU fallback")
+        self._sm100 = None
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _chk(*tensors):
+        for t in tensors:
+            if t is None:
+                continue
+            if not t.is_cuda:
+                raise _lib.CervixError("cervix_b200: tensor on %s - the CUDA path has no CPU fallback" % t.device)
+            if not t.is_contiguous():
+                raise _lib.CervixError("cervix_b200: non-contiguous tensor passed to the C ABI")
+
+    def is_sm100(self) -> bool:
+        if self._sm100 is None:
+            self._sm100 = bool(self.lib.cvx_device_is_sm100())
+        return self._sm100
+
+    # ------------------------------------------------------------------ layout
+    def to_nhwc(self, x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        self._chk(x)
+        n, c, h, w = x.shape
+        y = torch.empty((n, h, w, c), dtype=dtype, device=x.device)
+        check(self.lib.cvx_nchw_to_nhwc(_p(x), _p(y), n, c, h, w, _dt(y), self._stream()), "cvx_nchw_to_nhwc")
+        return y
+
+    def to_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        self._chk(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_nhwc_to_nchw(_p(x), _p(y), n, c, h, w, _dt(x), self._stream()), "cvx_nhwc_to_nchw")
+        return y
+
+    def pack_weight(self, w: torch.Tensor, dtype: torch.dtype, transpose_flip: bool) -> torch.Tensor:
+        self._chk(w)
+        cout, cin, kh, kw = w.shape
+        shape = (kh * kw, cin, cout) if transpose_flip else (kh * kw, cout, cin)
+        out = torch.empty(shape, dtype=dtype, device=w.device)
+        check(self.lib.cvx_pack_weight(_p(w), _p(out), cout, cin, kh, kw, _dt(out), int(transpose_flip), self._stream()),
+              "cvx_pack_weight")
+        return out
+
+    def unpack_wgrad(self, g: torch.Tensor, cout, cin, kh, kw) -> torch.Tensor:
+        self._chk(g)
+        out = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=g.device)
+        check(self.lib.cvx_unpack_wgrad(_p(g), _p(out), cout, cin, kh, kw, self._stream()), "cvx_unpack_wgrad")
+        return out
+
+    def pack_dw_weight(self, w: torch.Tensor) -> torch.Tensor:
+        self._chk(w)
+        c = w.shape[0]
+        out = torch.empty((9, c), dtype=torch.float32, device=w.device)
+        check(self.lib.cvx_pack_dw_weight(_p(w), _p(out), c, self._stream()), "cvx_pack_dw_weight")
+        return out
+
+    def unpack_dw_wgrad(self, g: torch.Tensor) -> torch.Tensor:
+        self._chk(g)
+        c = g.shape[1]
+        out = torch.empty((c, 1, 3, 3), dtype=torch.float32, device=g.device)
+        check(self.lib.cvx_unpack_dw_wgrad(_p(g), _p(out), c, self._stream()), "cvx_unpack_dw_wgrad")
+        return out
+
+    def cat_channels(self, xs: Sequence[torch.Tensor]) -> torch.Tensor:
+        self._chk(*xs)
+        n, h, w, _ = xs[0].shape
+        ctot = sum(int(x.shape[3]) for x in xs)
+        y = torch.empty((n, h, w, ctot), dtype=xs[0].dtype, device=xs[0].device)
+        off = 0
+        for x in xs:
+            c = int(x.shape[3])
+            check(self.lib.cvx_copy_channels(_p(x), c, 0, _p(y), ctot, off, n * h * w, c, _dt(x), self._stream()),
+                  "cvx_copy_channels")
+            off += c
+        return y
+
+    def slice_channels(self, x: torch.Tensor, off: int, c: int) -> torch.Tensor:
+        self._chk(x)
+        n, h, w, ctot = x.shape
+        y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+        check(self.lib.cvx_copy_channels(_p(x), ctot, off, _p(y), c, 0, n * h * w, c, _dt(x), self._stream()),
+              "cvx_copy_channels")
+        return y
+
+    # ------------------------------------------------------------------ dense conv
+    def conv_fwd(self, x, wp, bias, g: ConvGeom, tc: bool) -> torch.Tensor:
+        self._chk(x, wp, bias)
+        y = torch.empty((g.n, g.ho, g.wo, g.cout), dtype=x.dtype, device=x.device)
+        d = g.desc(_dt(x))
+        fn = self.lib.cvx_conv_fwd_tc if tc else self.lib.cvx_conv_fwd
+        check(fn(C.byref(d), _p(x), _p(wp), _p(bias), _p(y), self._stream()), "cvx_conv_fwd" + ("_tc" if tc else ""))
+        return y
+
+    def conv_dgrad(self, dy, wpt, g: ConvGeom, tc: bool) -> torch.Tensor:
+        self._chk(dy, wpt)
+        dx = torch.empty((g.n, g.h, g.w, g.cin), dtype=dy.dtype, device=dy.device)
+        d = g.desc(_dt(dy))
+        fn = self.lib.cvx_conv_dgrad_tc if tc else self.lib.cvx_conv_dgrad
+        check(fn(C.byref(d), _p(dy), _p(wpt), _p(dx), self._stream()), "cvx_conv_dgrad" + ("_tc" if tc else ""))
+        return dx
+
+    def conv_wgrad(self, x, dy, g: ConvGeom, tc: bool) -> torch.Tensor:
+        self._chk(x, dy)
+        dwp = torch.zeros((g.kh * g.kw, g.cout, g.cin), dtype=torch.float32, device=x.device)
+        d = g.desc(_dt(x))
+        fn = self.lib.cvx_conv_wgrad_tc if tc else self.lib.cvx_conv_wgrad
+        check(fn(C.byref(d), _p(x), _p(dy), _p(dwp), self._stream()), "cvx_conv_wgrad" + ("_tc" if tc else ""))
+        return dwp
+
+    def bias_grad(self, dy) -> torch.Tensor:
+        self._chk(dy)
+        c = int(dy.shape[-1])
+        rows = dy.numel() // c
+        out = torch.empty((c,), dtype=torch.float32, device=dy.device)
+        ws = torch.empty((c,), dtype=torch.float64, device=dy.device)
+        check(self.lib.cvx_bias_grad(_p(dy), _p(out), _p(ws), rows, c, _dt(dy), self._stream()), "cvx_bias_grad")
+        return out
+
+    def subsample(self, x, s: int) -> torch.Tensor:
+        self._chk(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, (h - 1) // s + 1, (w - 1) // s + 1, c), dtype=x.dtype, device=x.device)
+        check(self.lib.cvx_subsample(_p(x), _p(y), n, h, w, c, s, _dt(x), self._stream()), "cvx_subsample")
+        return y
+
+    def subsample_bwd(self, dy, h: int, w: int, s: int) -> torch.Tensor:
+        self._chk(dy)
+        n, _, _, c = dy.shape
+        dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+        check(self.lib.cvx_subsample_bwd(_p(dy), _p(dx), n, h, w, c, s, _dt(dy), self._stream()), "cvx_subsample_bwd")
+        return dx
+
+    # ------------------------------------------------------------------ depthwise
+    def dw_fwd(self, x, w9c, g: ConvGeom, relu_in: bool) -> torch.Tensor:
+        self._chk(x, w9c)
+        y = torch.empty((g.n, g.ho, g.wo, g.cin), dtype=x.dtype, device=x.device)
+        d = g.desc(_dt(x))
+        check(self.lib.cvx_dwconv_fwd(C.byref(d), _p(x), _p(w9c), _p(y), int(relu_in), self._stream()), "cvx_dwconv_fwd")
+        return y
+
+    def dw_bwd_data(self, dy, w9c, x, g: ConvGeom, relu_in: bool) -> torch.Tensor:
+        self._chk(dy, w9c, x)
+        dx = torch.empty((g.n, g.h, g.w, g.cin), dtype=dy.dtype, device=dy.device)
+        d = g.desc(_dt(dy))
+        check(self.lib.cvx_dwconv_bwd_data(C.byref(d), _p(dy), _p(w9c), _p(x), _p(dx), int(relu_in), self._stream()),
+              "cvx_dwconv_bwd_data")
+        return dx
+
+    def dw_bwd_weight(self, x, dy, g: ConvGeom, relu_in: bool) -> torch.Tensor:
+        self._chk(x, dy)
+        out = torch.empty((9, g.cin), dtype=torch.float32, device=x.device)
+        ws = torch.empty((9 * g.cin,), dtype=torch.float64, device=x.device)
+        d = g.desc(_dt(x))
+        check(self.lib.cvx_dwconv_bwd_weight(C.byref(d), _p(x), _p(dy), _p(out), _p(ws), int(relu_in), self._stream()),
+              "cvx_dwconv_bwd_weight")
+        return out
+
+    # ------------------------------------------------------------------ batch norm
+    def bn_forward(self, x, residual, gamma, beta, rmean, rvar, act: int, training: bool, momentum: float, eps: float):
+        self._chk(x, residual, gamma, beta, rmean, rvar)
+        c = int(x.shape[-1])
+        rows = x.numel() // c
+        y = torch.empty_like(x)
+        mean = torch.empty((c,), dtype=torch.float32, device=x.device)
+        invstd = torch.empty((c,), dtype=torch.float32, device=x.device)
+        ws = torch.empty((2 * c,), dtype=torch.float64, device=x.device)
+        check(self.lib.cvx_bn_forward(_p(x), _p(residual), _p(y), _p(gamma), _p(beta), _p(rmean), _p(rvar), _p(mean),
+                                      _p(invstd), _p(ws), rows, c, _dt(x), act, int(training), float(momentum),
+                                      float(eps), self._stream()), "cvx_bn_forward")
+        return y, mean, invstd
+
+    def bn_backward(self, dy, x, y, gamma, mean, invstd, act: int, training: bool, want_dres: bool):
+        self._chk(dy, x, y, gamma, mean, invstd)
+        c = int(x.shape[-1])
+        rows = x.numel() // c
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if want_dres else None
+        dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
+        dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
+        ws = torch.empty((2 * c,), dtype=torch.float64, device=x.device)
+        check(self.lib.cvx_bn_backward(_p(dy), _p(x), _p(y), _p(gamma), _p(mean), _p(invstd), _p(dx), _p(dres),
+                                       _p(dgamma), _p(dbeta), _p(ws), rows, c, _dt(x), act, int(training),
+                                       self._stream()), "cvx_bn_backward")
+        return dx, dres, dgamma, dbeta
+
+    # ------------------------------------------------------------------ small ops
+    def relu_fwd(self, x):
+        self._chk(x)
+        y = torch.empty_like(x)
+        check(self.lib.cvx_relu_fwd(_p(x), _p(y), x.numel(), _dt(x), self._stream()), "cvx_relu_fwd")
+        return y
+
+    def relu_bwd(self, dy, y):
+        self._chk(dy, y)
+        dx = torch.empty_like(dy)
+        check(self.lib.cvx_relu_bwd(_p(dy), _p(y), _p(dx), dy.numel(), _dt(dy), self._stream()), "cvx_relu_bwd")
+        return dx
+
+    def add(self, a, b):
+        self._chk(a, b)
+        out = torch.empty_like(a)
+        check(self.lib.cvx_add(_p(a), _p(b), _p(out), a.numel(), _dt(a), self._stream()), "cvx_add")
+        return out
+
+    def spatial_reduce(self, x, scale: float):
+        self._chk(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, 1, 1, c), dtype=x.dtype, device=x.device)
+        check(self.lib.cvx_spatial_reduce(_p(x), _p(y), n, h * w, c, float(scale), _dt(x), self._stream()),
+              "cvx_spatial_reduce")
+        return y
+
+    def spatial_broadcast(self, x, h: int, w: int, scale: float):
+        self._chk(x)
+        n, _, _, c = x.shape
+        y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+        check(self.lib.cvx_spatial_broadcast(_p(x), _p(y), n, h * w, c, float(scale), _dt(x), self._stream()),
+              "cvx_spatial_broadcast")
+        return y
+
+    def upsample_fwd(self, x, ho: int, wo: int):
+        self._chk(x)
+        n, hi, wi, c = x.shape
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        check(self.lib.cvx_upsample_fwd(_p(x), _p(y), n, hi, wi, ho, wo, c, _dt(x), self._stream()), "cvx_upsample_fwd")
+        return y
+
+    def upsample_bwd(self, dy, hi: int, wi: int):
+        self._chk(dy)
+        n, ho, wo, c = dy.shape
+        dx = torch.empty((n, hi, wi, c), dtype=dy.dtype, device=dy.device)
+        check(self.lib.cvx_upsample_bwd(_p(dy), _p(dx), n, hi, wi, ho, wo, c, _dt(dy), self._stream()), "cvx_upsample_bwd")
+        return dx
+
+    def upsample_to_nchw_fwd(self, x, ho: int, wo: int):
+        self._chk(x)
+        n, hi, wi, c = x.shape
+        y = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_upsample_to_nchw_fwd(_p(x), _p(y), n, hi, wi, ho, wo, c, _dt(x), self._stream()),
+              "cvx_upsample_to_nchw_fwd")
+        return y
+
+    def upsample_to_nchw_bwd(self, dy, hi: int, wi: int, dtype: torch.dtype):
+        self._chk(dy)
+        n, c, ho, wo = dy.shape
+        dx = torch.empty((n, hi, wi, c), dtype=dtype, device=dy.device)
+        check(self.lib.cvx_upsample_to_nchw_bwd(_p(dy), _p(dx), n, hi, wi, ho, wo, c, _dt(dx), self._stream()),
+              "cvx_upsample_to_nchw_bwd")
+        return dx
+
+    def dropout_fwd(self, x, p: float, seed: int):
+        self._chk(x)
+        y = torch.empty_like(x)
+        mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        check(self.lib.cvx_dropout_fwd(_p(x), _p(y), _p(mask), x.numel(), float(p), int(seed) & (2 ** 64 - 1), _dt(x),
+                                       self._stream()), "cvx_dropout_fwd")
+        return y, mask
+
+    def dropout_bwd(self, dy, mask, p: float):
+        self._chk(dy, mask)
+        dx = torch.empty_like(dy)
+        check(self.lib.cvx_dropout_bwd(_p(dy), _p(mask), _p(dx), dy.numel(), float(p), _dt(dy), self._stream()),
+              "cvx_dropout_bwd")
+        return dx
+
+    # ------------------------------------------------------------------ loss
+    def seg_loss_stats(self, logits, target, onehot, cls_w, alpha: float, gamma: float, thr: float):
+        self._chk(logits, target, onehot, cls_w)
+        n, c, h, w = logits.shape
+        stats = torch.empty((4 + 6 * c,), dtype=torch.float64, device=logits.device)
+        check(self.lib.cvx_seg_loss_stats(_p(logits), _p(target), _p(onehot), _p(cls_w), _p(stats), n, c, h, w,
+                                          float(alpha), float(gamma), float(thr), self._stream()), "cvx_seg_loss_stats")
+        return stats
+
+    def seg_loss_finalize(self, stats, c: int, beta: float, smooth: float):
+        self._chk(stats)
+        res = torch.empty((4,), dtype=torch.float32, device=stats.device)
+        check(self.lib.cvx_seg_loss_finalize(_p(stats), _p(res), c, float(beta), float(smooth), self._stream()),
+              "cvx_seg_loss_finalize")
+        return res
+
+    def seg_loss_grad(self, logits, target, onehot, cls_w, stats, g, alpha, gamma, beta, smooth):
+        self._chk(logits, target, onehot, cls_w, stats, g)
+        n, c, h, w = logits.shape
+        d = torch.empty_like(logits)
+        check(self.lib.cvx_seg_loss_grad(_p(logits), _p(target), _p(onehot), _p(cls_w), _p(stats), _p(g), _p(d), n, c,
+                                         h, w, float(alpha), float(gamma), float(beta), float(smooth), self._stream()),
+              "cvx_seg_loss_grad")
+        return d
+
+    # ------------------------------------------------------------------ optimizer
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, wd, step_t, grad_scale=1.0):
+        self._chk(p, g, m, v)
+        check(self.lib.cvx_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
+                                     float(eps), float(wd), int(step_t), float(grad_scale), self._stream()),
+              "cvx_adam_step")
+
+    def sgd_step(self, p, g, buf, lr, momentum, wd, nesterov, first_step, grad_scale=1.0):
+        self._chk(p, g, buf)
+        check(self.lib.cvx_sgd_step(_p(p), _p(g), _p(buf), p.numel(), float(lr), float(momentum), float(wd),
+                                    int(nesterov), int(first_step), float(grad_scale), self._stream()), "cvx_sgd_step")
+
+
+_BACKEND = None
+
+
+def get_backend():
+    """The process-wide compute backend (the CUDA library).  Raises if it cannot be loaded."""
+    global _BACKEND
+    if _BACKEND is None:
+        _BACKEND = CudaBackend()
+    return _BACKEND
+
+
+def set_backend(b):
+    """Test hook: install a different implementation of the backend method set."""
+    global _BACKEND
+    prev = _BACKEND
+    _BACKEND = b
+    return prev

@@ -1,0 +1,87 @@
+// Per-channel (column) reductions over an NHWC tensor viewed as [rows][C].
+//
+// Bandwidth-bound: every thread owns one 16-byte channel vector and walks down the rows, so
+// a warp always reads whole contiguous 512-byte spans; partial sums are combined through
+// shared-memory atomics per block and fp64 global atomics per channel (one per block).
+#pragma once
+
+#include "common.cuh"
+
+namespace cvx {
+
+// F must provide:  static constexpr int NACC;
+//   __device__ void operator()(int64_t row, int c0, float (&acc)[NACC][VEC]) const;
+template <typename T, typename F>
+__global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, int colchunk_vecs,
+                                                        int rows_per_block, double* __restrict__ out) {
+  constexpr int VEC = Elem<T>::kVec;
+  constexpr int NACC = F::NACC;
+  extern __shared__ float sm_acc[];  // [NACC][colchunk_vecs*VEC]
+  const int chunk_elems = colchunk_vecs * VEC;
+  for (int i = threadIdx.x; i < NACC * chunk_elems; i += blockDim.x) sm_acc[i] = 0.f;
+  __syncthreads();
+
+  const int lanes = (blockDim.x / colchunk_vecs);  // row lanes per block
+  const int cv = threadIdx.x % colchunk_vecs;
+  const int lane = threadIdx.x / colchunk_vecs;
+  const int cvec = blockIdx.y * colchunk_vecs + cv;
+  const bool active = lane < lanes && cvec * VEC < C;
+
+  float acc[NACC][VEC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[a][i] = 0.f;
+
+  if (active) {
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    int64_t r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    for (int64_t r = r0 + lane; r < r1; r += lanes) f(r, cvec * VEC, acc);
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) atomicAdd(&sm_acc[a * chunk_elems + cv * VEC + i], acc[a][i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NACC * chunk_elems; i += blockDim.x) {
+    const int a = i / chunk_elems, e = i % chunk_elems;
+    const int c = blockIdx.y * chunk_elems + e;
+    if (c < C) atomicAdd(out + (size_t)a * C + c, (double)sm_acc[i]);
+  }
+}
+
+// Launch helper.  `out` ([NACC][C] doubles) must be zeroed by the caller.
+template <typename T, typename F>
+static int colreduce_launch(const F& f, int64_t rows, int C, double* out, cudaStream_t stream) {
+  constexpr int VEC = Elem<T>::kVec;
+  if (C % VEC != 0) {
+    set_error("channel count %d is not a multiple of the %d-element vector width", C, VEC);
+    return CVX_EINVAL;
+  }
+  const int cvn = C / VEC;
+  int maxchunk = (12288 / F::NACC) / VEC;  // keep the block's partial-sum tile within 48 KB
+  if (maxchunk > 256) maxchunk = 256;
+  const int colchunk = cvn < maxchunk ? cvn : maxchunk;
+  const int lanes = 256 / colchunk;
+  const int ychunks = (cvn + colchunk - 1) / colchunk;
+  // enough blocks to fill the machine, each walking >= 8 rows per lane
+  int64_t want_blocks = (int64_t)kNumSMs * 8 / ychunks;
+  if (want_blocks < 1) want_blocks = 1;
+  int64_t rpb = ceil_div64(rows, want_blocks);
+  const int64_t min_rpb = (int64_t)lanes * 8;
+  if (rpb < min_rpb) rpb = min_rpb;
+  rpb = ceil_div64(rpb, lanes) * lanes;
+  const int64_t gx = ceil_div64(rows, rpb);
+  dim3 grid((unsigned)gx, ychunks);
+  const size_t smem = sizeof(float) * F::NACC * colchunk * VEC;
+  colreduce_kernel<T, F><<<grid, 256, smem, stream>>>(f, rows, C, colchunk, (int)rpb, out);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("colreduce launch failed: %s", cudaGetErrorString(e));
+    return CVX_ECUDA;
+  }
+  return CVX_OK;
+}
+
+}  // namespace cvx

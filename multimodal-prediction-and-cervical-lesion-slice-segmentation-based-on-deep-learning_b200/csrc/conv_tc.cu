@@ -1,0 +1,560 @@
+// Dense convolution as a tcgen05 / TMEM / TMA implicit GEMM (bf16 in, fp32 accumulate), sm_100a.
+//
+//   forward / dgrad : D[128 pixels][BN out-ch] += A[128 px][64 ch] * W[BN][64 ch]^T  per (tap, 64-ch block)
+//       A is a 4-D TMA box (64 ch, BW, BH, 1 image) of the NHWC activation whose start
+//       coordinate is shifted by the tap offset (kh*dil - pad, kw*dil - pad); TMA zero-fills
+//       out-of-bounds elements, which IS the convolution's zero padding and also pads the
+//       channel tails (728 = 11*64 + 24).  Both operands are K-major, SWIZZLE_128B.
+//   wgrad           : D[128 co][BN ci] += dY[64 px][128 co]^T * X[64 px][BN ci]  per pixel tile
+//       both operands are MN-major (pixel = K is the slow smem axis), split over pixel tiles,
+//       accumulated into fp32 with red.global.add.
+//
+// One CTA = one accumulator tile; 4 warps: warp0 lane0 = TMA producer, warp1 lane0 = MMA
+// issuer, warp2 = TMEM allocator, then all 4 warps drain TMEM (warp w owns lanes 32w..32w+31).
+// Two CTAs are co-resident per SM (3 x 32 KB stages each) so one CTA's epilogue overlaps the
+// other's main loop.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace cvx {
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must not hang the (shared) GPU - trap after ~seconds instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("cervix_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B, sm_100 version field = 1
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------ fwd / dgrad
+constexpr int kStages = 3;
+constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct TcFwdParams {
+  int n, ho, wo, cout;       // output geometry (rows of the GEMM)
+  int cin;                   // reduction channels
+  int kh, kw, pad, dil;      // taps; input coordinate = out - pad + k*dil  (stride 1)
+  int bw, bh;                // pixel tile (bw*bh == 128)
+  int tiles_x, tiles_y;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(128) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                          const __grid_constant__ CUtensorMap tmap_w,
+                                                          const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ y, TcFwdParams p) {
+  constexpr int kBBytes = BN * 128;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kStages, tfull = full0 + 16 * kStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+  const int ty = tile % p.tiles_y;
+  const int img = tile / p.tiles_y;
+  const int ox0 = tx * p.bw, oy0 = ty * p.bh;
+  const int n0 = blockIdx.y * BN;
+  const int kcb = (p.cin + 63) / 64;
+  const int num_kb = p.kh * p.kw * kcb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const int tap = kb / kcb, cb = kb - tap * kcb;
+        const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+        const uint32_t sa = smem_base + s * kStageBytes;
+        mbar_expect_tx(full0 + 8 * s, kStageBytes);
+        tma_load_4d(sa, &tmap_x, full0 + 8 * s, cb * 64, ox0 - p.pad + kwi * p.dil, oy0 - p.pad + khi * p.dil, img);
+        tma_load_3d(sa + kABytes, &tmap_w, full0 + 8 * s, cb * 64, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * kStageBytes;
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
+          const uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * s);  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tfull);
+    }
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> (bias) -> bf16 -> global ---------------------------
+  mbar_wait(tfull, 0);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  const int oy = oy0 + row / p.bw, ox = ox0 + row % p.bw;
+  const bool row_ok = oy < p.ho && ox < p.wo;
+  __nv_bfloat16* yrow = y + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (n0 + c0 >= p.cout) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = c0 + g * 8;
+        if (n0 + c < p.cout) {  // cout % 8 == 0: whole 8-column groups are in or out
+          uint32_t packed[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
+            if (bias) { v0 += __ldg(bias + n0 + c + 2 * j); v1 += __ldg(bias + n0 + c + 2 * j + 1); }
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(yrow + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------ wgrad
+constexpr int kWStages = 4;
+constexpr int kWBox = 64 * 128;  // 64 pixels x 64 bf16 channels
+
+struct TcWgradParams {
+  int n, ho, wo, cout, cin;
+  int kh, kw, pad, dil;
+  int bw, bh;                // pixel tile (bw*bh == 64)
+  int tiles_x, tiles_y;
+  int splits;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(128) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dy,
+                                                            const __grid_constant__ CUtensorMap tmap_x,
+                                                            float* __restrict__ dw, TcWgradParams p) {
+  constexpr int kABytesW = 2 * kWBox;          // 128 co
+  constexpr int kBBytesW = (BN / 64) * kWBox;  // BN ci
+  constexpr int kStageBytes = kABytesW + kBBytesW;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kWStages, tfull = full0 + 16 * kWStages;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 128, ci0 = blockIdx.y * BN;
+  const int tap = blockIdx.z / p.splits, split = blockIdx.z - tap * p.splits;
+  const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+  const int ptiles = p.n * p.tiles_y * p.tiles_x;
+  const int per = (ptiles + p.splits - 1) / p.splits;
+  const int t_begin = split * per;
+  const int t_end = min(t_begin + per, ptiles);
+  const int num_kb = max(t_end - t_begin, 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_x);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(smem_u32(tmem_slot), BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = kb % kWStages;
+          const uint32_t ph = (kb / kWStages) & 1;
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          int t = t_begin + kb;
+          const int tx = t % p.tiles_x; t /= p.tiles_x;
+          const int ty = t % p.tiles_y;
+          const int img = t / p.tiles_y;
+          const int ox0 = tx * p.bw, oy0 = ty * p.bh;
+          const uint32_t sa = smem_base + s * kStageBytes;
+          mbar_expect_tx(full0 + 8 * s, kStageBytes);
+          tma_load_4d(sa, &tmap_dy, full0 + 8 * s, co0, ox0, oy0, img);
+          tma_load_4d(sa + kWBox, &tmap_dy, full0 + 8 * s, co0 + 64, ox0, oy0, img);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_4d(sa + kABytesW + j * kWBox, &tmap_x, full0 + 8 * s, ci0 + j * 64,
+                        ox0 - p.pad + kwi * p.dil, oy0 - p.pad + khi * p.dil, img);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);  // both operands MN-major
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = kb % kWStages;
+          const uint32_t ph = (kb / kWStages) & 1;
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * kStageBytes;
+          const uint32_t sb = sa + kABytesW;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 pixels per MMA = 16 smem rows of 128 B
+            const uint64_t ad = make_smem_desc(sa + k * 2048, kWBox, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * 2048, kWBox, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull);
+      }
+    }
+    __syncwarp();
+
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int co = co0 + warp * 32 + lane;
+    float* drow = dw + ((size_t)tap * p.cout + co) * p.cin + ci0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (ci0 + c0 >= p.cin) break;
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (co < p.cout) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ci0 + c0 + j < p.cin) atomicAdd(drow + c0 + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [n][h][w][c] with a (64, bw, bh, 1) box
+static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int bw, int bh) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CVX_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %dx%d) failed: %d", n, h, w, c, bw, bh, (int)r); return CVX_ECUDA; }
+  return CVX_OK;
+}
+
+// packed weights [taps][rows][k] bf16 with a (64, bn, 1) box
+static int make_weight_map(CUtensorMap* m, const void* base, int taps, int rows, int k, int bn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CVX_ECUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)taps};
+  cuuint64_t strides[2] = {(cuuint64_t)k * 2, (cuuint64_t)rows * k * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)bn, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights %dx%dx%d box %d) failed: %d", taps, rows, k, bn, (int)r); return CVX_ECUDA; }
+  return CVX_OK;
+}
+
+// choose the pixel tile (bw x bh == pixels) that wastes the fewest rows on an ho x wo map
+static void pick_tile(int ho, int wo, int pixels, int* bw, int* bh) {
+  int best_bw = pixels, best_cost = INT32_MAX;
+  for (int w = 8; w <= pixels && w <= 256; w *= 2) {
+    const int h = pixels / w;
+    if (h > 256) continue;
+    const int cost = ((wo + w - 1) / w) * ((ho + h - 1) / h);
+    if (cost < best_cost || (cost == best_cost && w > best_bw)) { best_cost = cost; best_bw = w; }
+  }
+  *bw = best_bw;
+  *bh = pixels / best_bw;
+}
+
+static int tc_supported(const cvx_conv_desc* d, const char* who) {
+  CVX_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
+  if (d->dtype != CVX_BF16 || d->stride != 1 || d->cin % 8 != 0 || d->cout % 8 != 0) {
+    set_error("%s: tensor-core path needs bf16, stride 1, C_in %% 8 == 0 and C_out %% 8 == 0 (got dtype=%d stride=%d cin=%d cout=%d)",
+              who, d->dtype, d->stride, d->cin, d->cout);
+    return CVX_EUNSUPPORTED;
+  }
+  const int ho = d->h + 2 * d->pad - d->dil * (d->kh - 1);
+  const int wo = d->w + 2 * d->pad - d->dil * (d->kw - 1);
+  CVX_CHECK_ARG(ho == d->ho && wo == d->wo && ho > 0 && wo > 0, "%s: inconsistent output size", who);
+  return CVX_OK;
+}
+
+template <int BN>
+static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, void* y, const TcFwdParams& p,
+                      cudaStream_t st) {
+  constexpr int smem = kStages * (kABytes + BN * 128) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(p.n * p.tiles_y * p.tiles_x, (p.cout + BN - 1) / BN);
+  conv_tc_fwd_kernel<BN><<<grid, 128, smem, st>>>(mx, mw, bias, (__nv_bfloat16*)y, p);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+// rows = output pixels [n,ho,wo] ; src = [n,hs,ws,cred] ; wp = [taps][ncol][cred]
+static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, int kh, int kw, int pad, int dil,
+                     const void* src, const void* wp, const float* bias, void* dst, cudaStream_t st) {
+  TcFwdParams p;
+  p.n = n; p.ho = ho; p.wo = wo; p.cout = ncol; p.cin = cred; p.kh = kh; p.kw = kw; p.pad = pad; p.dil = dil;
+  pick_tile(ho, wo, 128, &p.bw, &p.bh);
+  p.tiles_x = (wo + p.bw - 1) / p.bw;
+  p.tiles_y = (ho + p.bh - 1) / p.bh;
+  const int bn = ncol <= 64 ? 64 : 128;
+  CUtensorMap mx, mw;
+  if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
+  if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, bn)) return rc;
+  return bn == 64 ? launch_fwd<64>(mx, mw, bias, dst, p, st) : launch_fwd<128>(mx, mw, bias, dst, p, st);
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dw, const TcWgradParams& p,
+                        cudaStream_t st) {
+  constexpr int smem = kWStages * (2 * kWBox + (BN / 64) * kWBox) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid((p.cout + 127) / 128, (p.cin + BN - 1) / BN, p.kh * p.kw * p.splits);
+  conv_tc_wgrad_kernel<BN><<<grid, 128, smem, st>>>(mdy, mx, dw, p);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+}  // namespace cvx
+
+using namespace cvx;
+
+extern "C" {
+
+int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
+                    void* stream) {
+  if (int rc = tc_supported(d, "conv_fwd_tc")) return rc;
+  CVX_CHECK_ARG(x && w_packed && y, "conv_fwd_tc: null pointer");
+  return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, bias, y,
+                   as_stream(stream));
+}
+
+int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream) {
+  if (int rc = tc_supported(d, "conv_dgrad_tc")) return rc;
+  CVX_CHECK_ARG(dy && w_packed_t && dx, "conv_dgrad_tc: null pointer");
+  // stride-1 data gradient == forward conv of dy with the flipped/transposed filter and
+  // padding dil*(k-1) - pad
+  const int pad_t = d->dil * (d->kh - 1) - d->pad;
+  CVX_CHECK_ARG(pad_t >= 0 && d->kh == d->kw, "conv_dgrad_tc: unsupported padding/filter");
+  return run_igemm(d->n, d->ho, d->wo, d->cout, d->h, d->w, d->cin, d->kh, d->kw, pad_t, d->dil, dy, w_packed_t,
+                   nullptr, dx, as_stream(stream));
+}
+
+int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream) {
+  if (int rc = tc_supported(d, "conv_wgrad_tc")) return rc;
+  CVX_CHECK_ARG(x && dy && dw_packed, "conv_wgrad_tc: null pointer");
+  TcWgradParams p;
+  p.n = d->n; p.ho = d->ho; p.wo = d->wo; p.cout = d->cout; p.cin = d->cin;
+  p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.dil = d->dil;
+  pick_tile(d->ho, d->wo, 64, &p.bw, &p.bh);
+  p.tiles_x = (d->wo + p.bw - 1) / p.bw;
+  p.tiles_y = (d->ho + p.bh - 1) / p.bh;
+  const int bn = d->cin <= 64 ? 64 : 128;
+  const int ptiles = p.n * p.tiles_y * p.tiles_x;
+  const int out_tiles = ((d->cout + 127) / 128) * ((d->cin + bn - 1) / bn) * d->kh * d->kw;
+  int splits = (2 * kNumSMs + out_tiles - 1) / out_tiles;
+  if (splits > ptiles / 4) splits = ptiles / 4;  // keep >= 4 pixel tiles per CTA
+  if (splits < 1) splits = 1;
+  CVX_CHECK_ARG((int64_t)d->kh * d->kw * splits <= 65535, "conv_wgrad_tc: grid.z too large");
+  p.splits = splits;
+  CUtensorMap mdy, mx;
+  if (int rc = make_act_map(&mdy, dy, d->n, d->ho, d->wo, d->cout, p.bw, p.bh)) return rc;
+  if (int rc = make_act_map(&mx, x, d->n, d->h, d->w, d->cin, p.bw, p.bh)) return rc;
+  return bn == 64 ? launch_wgrad<64>(mdy, mx, dw_packed, p, as_stream(stream))
+                  : launch_wgrad<128>(mdy, mx, dw_packed, p, as_stream(stream));
+}
+
+}  // extern "C"

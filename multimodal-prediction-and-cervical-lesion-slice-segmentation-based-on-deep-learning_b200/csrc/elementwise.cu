@@ -1,0 +1,366 @@
+// Small bandwidth-bound ops: ReLU, add, ASPP global pooling / broadcast, bilinear
+// (align_corners=True) upsampling forward/backward, dropout.
+#include "common.cuh"
+
+namespace cvx {
+
+static inline int ew_grid(int64_t total, int block = 256) {
+  int64_t b = ceil_div64(total, block);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+#define CVX_GRID_STRIDE(i, total) \
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (total); i += (int64_t)gridDim.x * blockDim.x)
+
+template <typename T>
+__global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t nvec, int64_t n) {
+  constexpr int VEC = Elem<T>::kVec;
+  CVX_GRID_STRIDE(i, nvec) {
+    Vec<T> v;
+    v.load(x + i * VEC);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v.v[k] = fmaxf(v.v[k], 0.f);
+    v.store(y + i * VEC);
+  }
+  // tail
+  const int64_t t0 = nvec * VEC + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t0 < n) Elem<T>::st(y + t0, fmaxf(Elem<T>::ld(x + t0), 0.f));
+}
+
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t nvec,
+                                int64_t n) {
+  constexpr int VEC = Elem<T>::kVec;
+  CVX_GRID_STRIDE(i, nvec) {
+    Vec<T> g, v;
+    g.load(dy + i * VEC);
+    v.load(y + i * VEC);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) g.v[k] = v.v[k] > 0.f ? g.v[k] : 0.f;
+    g.store(dx + i * VEC);
+  }
+  const int64_t t0 = nvec * VEC + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t0 < n) Elem<T>::st(dx + t0, Elem<T>::ld(y + t0) > 0.f ? Elem<T>::ld(dy + t0) : 0.f);
+}
+
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int64_t nvec,
+                           int64_t n) {
+  constexpr int VEC = Elem<T>::kVec;
+  CVX_GRID_STRIDE(i, nvec) {
+    Vec<T> u, v;
+    u.load(a + i * VEC);
+    v.load(b + i * VEC);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) u.v[k] += v.v[k];
+    u.store(o + i * VEC);
+  }
+  const int64_t t0 = nvec * VEC + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t0 < n) Elem<T>::st(o + t0, Elem<T>::ld(a + t0) + Elem<T>::ld(b + t0));
+}
+
+// y[n,c] = scale * sum_p x[n,p,c] ; grid (ceil(c/256), n)
+template <typename T>
+__global__ void spatial_reduce_kernel(const T* __restrict__ x, T* __restrict__ y, int hw, int c, float scale) {
+  const int cc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cc >= c) return;
+  const T* p = x + (size_t)blockIdx.y * hw * c + cc;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int i = 0;
+  for (; i + 3 < hw; i += 4) {
+    s0 += Elem<T>::ld(p + (size_t)i * c);
+    s1 += Elem<T>::ld(p + (size_t)(i + 1) * c);
+    s2 += Elem<T>::ld(p + (size_t)(i + 2) * c);
+    s3 += Elem<T>::ld(p + (size_t)(i + 3) * c);
+  }
+  for (; i < hw; ++i) s0 += Elem<T>::ld(p + (size_t)i * c);
+  Elem<T>::st(y + (size_t)blockIdx.y * c + cc, (s0 + s1 + s2 + s3) * scale);
+}
+
+template <typename T>
+__global__ void spatial_broadcast_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total, int hw, int c,
+                                         float scale) {
+  CVX_GRID_STRIDE(i, total) {
+    const int cc = (int)(i % c);
+    const int64_t nn = i / ((int64_t)hw * c);
+    Elem<T>::st(y + i, Elem<T>::ld(x + nn * c + cc) * scale);
+  }
+}
+
+// ---- bilinear, align_corners=True (same index arithmetic as ATen's upsample_bilinear2d) -----
+struct Lerp {
+  int i0, i1;
+  float w0, w1;
+};
+__device__ __forceinline__ Lerp lerp_of(int o, float scale, int in_size) {
+  const float r = scale * (float)o;
+  Lerp l;
+  l.i0 = (int)r;
+  if (l.i0 > in_size - 1) l.i0 = in_size - 1;
+  l.i1 = l.i0 + (l.i0 < in_size - 1 ? 1 : 0);
+  l.w1 = r - (float)l.i0;
+  l.w0 = 1.f - l.w1;
+  return l;
+}
+static inline float lerp_scale(int in_size, int out_size) {
+  return out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+}
+// total weight with which input index `i` contributes to output index `o`
+__device__ __forceinline__ float lerp_weight(int i, int o, float scale, int in_size) {
+  const Lerp l = lerp_of(o, scale, in_size);
+  return (l.i0 == i ? l.w0 : 0.f) + (l.i1 == i ? l.w1 : 0.f);
+}
+// candidate output range that can touch input index i
+__device__ __forceinline__ void lerp_range(int i, float scale, int out_size, int* lo, int* hi) {
+  if (scale <= 0.f) { *lo = 0; *hi = out_size - 1; return; }
+  int a = (int)floorf((float)(i - 1) / scale) - 1;
+  int b = (int)ceilf((float)(i + 1) / scale) + 1;
+  *lo = a < 0 ? 0 : a;
+  *hi = b > out_size - 1 ? out_size - 1 : b;
+}
+
+template <typename T>
+__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int hi, int wi, int ho,
+                                    int wo, int c, float sh, float sw) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int cvn = c / VEC;
+  const int64_t total = (int64_t)n * ho * wo * cvn;
+  CVX_GRID_STRIDE(e, total) {
+    const int c0 = (int)(e % cvn) * VEC;
+    int64_t p = e / cvn;
+    const int ox = (int)(p % wo), oy = (int)((p / wo) % ho), nn = (int)(p / ((int64_t)wo * ho));
+    const Lerp ly = lerp_of(oy, sh, hi), lx = lerp_of(ox, sw, wi);
+    const T* base = x + (size_t)nn * hi * wi * c + c0;
+    Vec<T> a, b, cc, d, o;
+    a.load(base + ((size_t)ly.i0 * wi + lx.i0) * c);
+    b.load(base + ((size_t)ly.i0 * wi + lx.i1) * c);
+    cc.load(base + ((size_t)ly.i1 * wi + lx.i0) * c);
+    d.load(base + ((size_t)ly.i1 * wi + lx.i1) * c);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      o.v[i] = ly.w0 * (lx.w0 * a.v[i] + lx.w1 * b.v[i]) + ly.w1 * (lx.w0 * cc.v[i] + lx.w1 * d.v[i]);
+    o.store(y + e * VEC);
+  }
+}
+
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int hi, int wi, int ho,
+                                    int wo, int c, float sh, float sw) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int cvn = c / VEC;
+  const int64_t total = (int64_t)n * hi * wi * cvn;
+  CVX_GRID_STRIDE(e, total) {
+    const int c0 = (int)(e % cvn) * VEC;
+    int64_t p = e / cvn;
+    const int ix = (int)(p % wi), iy = (int)((p / wi) % hi), nn = (int)(p / ((int64_t)wi * hi));
+    int ylo, yhi, xlo, xhi;
+    lerp_range(iy, sh, ho, &ylo, &yhi);
+    lerp_range(ix, sw, wo, &xlo, &xhi);
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    for (int oy = ylo; oy <= yhi; ++oy) {
+      const float wy = lerp_weight(iy, oy, sh, hi);
+      if (wy == 0.f) continue;
+      for (int ox = xlo; ox <= xhi; ++ox) {
+        const float wgt = wy * lerp_weight(ix, ox, sw, wi);
+        if (wgt == 0.f) continue;
+        Vec<T> g;
+        g.load(dy + (((size_t)nn * ho + oy) * wo + ox) * c + c0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(wgt, g.v[i], acc[i]);
+      }
+    }
+    Vec<T> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.store(dx + e * VEC);
+  }
+}
+
+// low-res NHWC (any small C) -> full-res NCHW fp32
+template <typename T>
+__global__ void upsample_to_nchw_fwd_kernel(const T* __restrict__ x, float* __restrict__ y, int n, int hi, int wi,
+                                            int ho, int wo, int c, float sh, float sw) {
+  const int64_t total = (int64_t)n * ho * wo;
+  CVX_GRID_STRIDE(p, total) {
+    const int ox = (int)(p % wo), oy = (int)((p / wo) % ho), nn = (int)(p / ((int64_t)wo * ho));
+    const Lerp ly = lerp_of(oy, sh, hi), lx = lerp_of(ox, sw, wi);
+    const T* base = x + (size_t)nn * hi * wi * c;
+    const T* p00 = base + ((size_t)ly.i0 * wi + lx.i0) * c;
+    const T* p01 = base + ((size_t)ly.i0 * wi + lx.i1) * c;
+    const T* p10 = base + ((size_t)ly.i1 * wi + lx.i0) * c;
+    const T* p11 = base + ((size_t)ly.i1 * wi + lx.i1) * c;
+    for (int cc = 0; cc < c; ++cc) {
+      const float v = ly.w0 * (lx.w0 * Elem<T>::ld(p00 + cc) + lx.w1 * Elem<T>::ld(p01 + cc)) +
+                      ly.w1 * (lx.w0 * Elem<T>::ld(p10 + cc) + lx.w1 * Elem<T>::ld(p11 + cc));
+      y[(((size_t)nn * c + cc) * ho + oy) * wo + ox] = v;
+    }
+  }
+}
+
+template <typename T>
+__global__ void upsample_to_nchw_bwd_kernel(const float* __restrict__ dy, T* __restrict__ dx, int n, int hi, int wi,
+                                            int ho, int wo, int c, float sh, float sw) {
+  const int64_t total = (int64_t)n * hi * wi * c;
+  CVX_GRID_STRIDE(e, total) {
+    const int cc = (int)(e % c);
+    int64_t p = e / c;
+    const int ix = (int)(p % wi), iy = (int)((p / wi) % hi), nn = (int)(p / ((int64_t)wi * hi));
+    int ylo, yhi, xlo, xhi;
+    lerp_range(iy, sh, ho, &ylo, &yhi);
+    lerp_range(ix, sw, wo, &xlo, &xhi);
+    const float* plane = dy + ((size_t)nn * c + cc) * ho * wo;
+    float acc = 0.f;
+    for (int oy = ylo; oy <= yhi; ++oy) {
+      const float wy = lerp_weight(iy, oy, sh, hi);
+      if (wy == 0.f) continue;
+      for (int ox = xlo; ox <= xhi; ++ox) {
+        const float wgt = wy * lerp_weight(ix, ox, sw, wi);
+        if (wgt != 0.f) acc = fmaf(wgt, plane[(size_t)oy * wo + ox], acc);
+      }
+    }
+    Elem<T>::st(dx + e, acc);
+  }
+}
+
+// ---- dropout -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+template <typename T>
+__global__ void dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
+                                   float p, uint64_t seed) {
+  const float keep_scale = 1.f / (1.f - p);
+  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)p * 4294967296.0);
+  CVX_GRID_STRIDE(i, n) {
+    const uint32_t r = mix64(seed * 0x100000001b3ull + (uint64_t)i);
+    const uint8_t keep = r >= thresh ? 1 : 0;
+    mask[i] = keep;
+    Elem<T>::st(y + i, keep ? Elem<T>::ld(x + i) * keep_scale : 0.f);
+  }
+}
+
+template <typename T>
+__global__ void dropout_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ mask, T* __restrict__ dx,
+                                   int64_t n, float p) {
+  const float keep_scale = 1.f / (1.f - p);
+  CVX_GRID_STRIDE(i, n) { Elem<T>::st(dx + i, mask[i] ? Elem<T>::ld(dy + i) * keep_scale : 0.f); }
+}
+
+}  // namespace cvx
+
+using namespace cvx;
+
+extern "C" {
+
+int cvx_relu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) {
+  CVX_CHECK_ARG(x && y && n > 0, "relu_fwd: bad arguments");
+  CVX_CHECK_ARG((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0, "relu_fwd: pointers must be 16-byte aligned");
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  const int64_t nvec = n / vec;
+  CVX_DISPATCH_DTYPE(dtype, T, (relu_fwd_kernel<T><<<ew_grid(nvec), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, nvec, n)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, void* stream) {
+  CVX_CHECK_ARG(dy && y && dx && n > 0, "relu_bwd: bad arguments");
+  CVX_CHECK_ARG((uintptr_t)dy % 16 == 0 && (uintptr_t)y % 16 == 0 && (uintptr_t)dx % 16 == 0,
+                "relu_bwd: pointers must be 16-byte aligned");
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  const int64_t nvec = n / vec;
+  CVX_DISPATCH_DTYPE(dtype, T, (relu_bwd_kernel<T><<<ew_grid(nvec), 256, 0, as_stream(stream)>>>((const T*)dy, (const T*)y, (T*)dx, nvec, n)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
+  CVX_CHECK_ARG(a && b && out && n > 0, "add: bad arguments");
+  CVX_CHECK_ARG((uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0 && (uintptr_t)out % 16 == 0,
+                "add: pointers must be 16-byte aligned");
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  const int64_t nvec = n / vec;
+  CVX_DISPATCH_DTYPE(dtype, T, (add_kernel<T><<<ew_grid(nvec), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out, nvec, n)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_spatial_reduce(const void* x, void* y, int n, int hw, int c, float scale, int dtype, void* stream) {
+  CVX_CHECK_ARG(x && y && n > 0 && hw > 0 && c > 0 && n <= 65535, "spatial_reduce: bad arguments");
+  dim3 grid((c + 255) / 256, n);
+  CVX_DISPATCH_DTYPE(dtype, T, (spatial_reduce_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, hw, c, scale)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_spatial_broadcast(const void* x, void* y, int n, int hw, int c, float scale, int dtype, void* stream) {
+  CVX_CHECK_ARG(x && y && n > 0 && hw > 0 && c > 0, "spatial_broadcast: bad arguments");
+  const int64_t total = (int64_t)n * hw * c;
+  CVX_DISPATCH_DTYPE(dtype, T, (spatial_broadcast_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, total, hw, c, scale)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_upsample_fwd(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream) {
+  CVX_CHECK_ARG(x && y && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_fwd: bad arguments");
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  CVX_CHECK_ARG(c % vec == 0, "upsample_fwd: C=%d not a multiple of %d", c, vec);
+  const int64_t total = (int64_t)n * ho * wo * (c / vec);
+  CVX_DISPATCH_DTYPE(dtype, T, (upsample_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (T*)y, n, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream) {
+  CVX_CHECK_ARG(dy && dx && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_bwd: bad arguments");
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  CVX_CHECK_ARG(c % vec == 0, "upsample_bwd: C=%d not a multiple of %d", c, vec);
+  const int64_t total = (int64_t)n * hi * wi * (c / vec);
+  CVX_DISPATCH_DTYPE(dtype, T, (upsample_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                                   (const T*)dy, (T*)dx, n, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_upsample_to_nchw_fwd(const void* x, float* y, int n, int hi, int wi, int ho, int wo, int c, int dtype,
+                             void* stream) {
+  CVX_CHECK_ARG(x && y && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_to_nchw_fwd: bad arguments");
+  const int64_t total = (int64_t)n * ho * wo;
+  CVX_DISPATCH_DTYPE(dtype, T, (upsample_to_nchw_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, y, n, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_upsample_to_nchw_bwd(const float* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype,
+                             void* stream) {
+  CVX_CHECK_ARG(dy && dx && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_to_nchw_bwd: bad arguments");
+  const int64_t total = (int64_t)n * hi * wi * c;
+  CVX_DISPATCH_DTYPE(dtype, T, (upsample_to_nchw_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                                   dy, (T*)dx, n, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, int dtype, void* stream) {
+  CVX_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments");
+  CVX_DISPATCH_DTYPE(dtype, T, (dropout_fwd_kernel<T><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, mask, n, p, seed)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream) {
+  CVX_CHECK_ARG(dy && dx && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_bwd: bad arguments");
+  CVX_DISPATCH_DTYPE(dtype, T, (dropout_bwd_kernel<T><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const T*)dy, mask, (T*)dx, n, p)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Fused optimizer steps (train.py:472-476: Adam(betas=(momentum,0.999)) / SGD(nesterov)).
+#include "common.cuh"
+
+namespace cvx {
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt, float gscale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n,
+                           float lr, float mom, float wd, int nesterov, int first, float gscale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    if (mom != 0.f) {
+      const float b = first ? gi : mom * buf[i] + gi;
+      buf[i] = b;
+      gi = nesterov ? gi + mom * b : b;
+    }
+    p[i] = pi - lr * gi;
+  }
+}
+
+}  // namespace cvx
+
+using namespace cvx;
+
+extern "C" {
+
+int cvx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step_t, float grad_scale, void* stream) {
+  CVX_CHECK_ARG(p && g && m && v && n > 0 && step_t >= 1, "adam_step: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step_t);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step_t);
+  int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
+  adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                     (float)sqrt(bc2), grad_scale);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum, float weight_decay,
+                 int nesterov, int first_step, float grad_scale, void* stream) {
+  CVX_CHECK_ARG(p && g && n > 0 && (momentum == 0.f || buf), "sgd_step: bad arguments");
+  int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
+  sgd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, buf, n, lr, momentum, weight_decay, nesterov, first_step,
+                                                    grad_scale);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,362 @@
+"""Autograd operators of the B200 DeepLabv3+ path.
+
+Each ``torch.autograd.Function`` below is a thin host-side shell: forward and backward call
+the CUDA kernels through the C ABI (backend.py) and nothing else.  Activations flowing between
+operators are NHWC tensors in the engine's compute dtype (bf16 for training, fp32 for the
+exact-parity mode); parameters stay in the reference's fp32 OIHW/`nn.BatchNorm2d` layout so the
+reference's ``state_dict``/optimizers/DDP see ordinary ``nn.Parameter``s.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .backend import ConvGeom, get_backend
+
+ACT_NONE, ACT_RELU, ACT_RELU6 = _lib.ACT_NONE, _lib.ACT_RELU, _lib.ACT_RELU6
+
+
+def _tc_ok(x: torch.Tensor, cin: int, cout: int) -> bool:
+    """Tensor-core (tcgen05) eligibility of a dense conv: bf16 storage, 16-byte rows."""
+    if os.environ.get("CERVIX_DISABLE_TC") == "1":
+        return False
+    B = get_backend()
+    return (x.dtype == torch.bfloat16 and cin % 8 == 0 and cout % 8 == 0 and getattr(B, "is_sm100", lambda: False)())
+
+
+class ToNHWC(Function):
+    """NCHW fp32 image batch -> NHWC compute dtype (entry of DeepLab.forward)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return get_backend().to_nhwc(x.contiguous().float(), dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return get_backend().to_nchw(dy.contiguous()), None
+
+
+class ToNCHW(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.dtype = x.dtype
+        return get_backend().to_nchw(x.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return get_backend().to_nhwc(dy.contiguous(), ctx.dtype)
+
+
+class Conv2d(Function):
+    """Dense nn.Conv2d (groups=1) on NHWC.  weight: fp32 OIHW parameter; bias: fp32 or None."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, dil):
+        B = get_backend()
+        x = x.contiguous()
+        n, h, w, cin = x.shape
+        cout, cin_w, kh, kw = weight.shape
+        assert cin_w == cin, "conv: channel mismatch %d vs %d" % (cin_w, cin)
+        tc = _tc_ok(x, cin, cout)
+        sub = 1
+        if tc and stride != 1:
+            if kh == 1 and kw == 1 and pad == 0:
+                # 1x1 stride-s conv == 1x1 stride-1 conv of the subsampled input
+                x = B.subsample(x, stride)
+                sub, stride = stride, 1
+                n, h2, w2, _ = x.shape
+            else:
+                tc = False
+        g = ConvGeom(n, x.shape[1], x.shape[2], cin, cout, kh, kw, stride, pad, dil)
+        wp = B.pack_weight(weight.detach(), x.dtype, False)
+        y = B.conv_fwd(x, wp, None if bias is None else bias.detach(), g, tc)
+        ctx.save_for_backward(x, weight)
+        ctx.g, ctx.tc, ctx.sub, ctx.in_hw, ctx.has_bias = g, tc, sub, (h, w), bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B = get_backend()
+        x, weight = ctx.saved_tensors
+        g, tc = ctx.g, ctx.tc
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wpt = B.pack_weight(weight.detach(), dy.dtype, True)
+            dx = B.conv_dgrad(dy, wpt, g, tc)
+            if ctx.sub != 1:
+                dx = B.subsample_bwd(dx, ctx.in_hw[0], ctx.in_hw[1], ctx.sub)
+        if ctx.needs_input_grad[1]:
+            dwp = B.conv_wgrad(x, dy, g, tc)
+            dw = B.unpack_wgrad(dwp, g.cout, g.cin, g.kh, g.kw)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = B.bias_grad(dy)
+        return dx, dw, db, None, None, None
+
+
+class DepthwiseConv3x3(Function):
+    """nn.Conv2d(C, C, 3, groups=C, bias=False) on NHWC with an optional fused input ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad, dil, relu_in):
+        B = get_backend()
+        x = x.contiguous()
+        n, h, w, c = x.shape
+        assert tuple(weight.shape) == (c, 1, 3, 3)
+        g = ConvGeom(n, h, w, c, c, 3, 3, stride, pad, dil)
+        w9c = B.pack_dw_weight(weight.detach())
+        y = B.dw_fwd(x, w9c, g, relu_in)
+        ctx.save_for_backward(x, w9c)
+        ctx.g, ctx.relu_in = g, relu_in
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B = get_backend()
+        x, w9c = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = B.dw_bwd_data(dy, w9c, x, ctx.g, ctx.relu_in)
+        if ctx.needs_input_grad[1]:
+            dw = B.unpack_dw_wgrad(B.dw_bwd_weight(x, dy, ctx.g, ctx.relu_in))
+        return dx, dw, None, None, None, None
+
+
+class BatchNormAct(Function):
+    """y = act(BatchNorm2d(x) + residual) with nn.BatchNorm2d training/eval semantics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, training, momentum, eps, act):
+        B = get_backend()
+        x = x.contiguous()
+        if residual is not None:
+            residual = residual.contiguous()
+        y, mean, invstd = B.bn_forward(x, residual, gamma.detach(), beta.detach(), running_mean, running_var, act,
+                                       training, momentum, eps)
+        ctx.save_for_backward(x, y if act != ACT_NONE else None, gamma, mean, invstd)
+        ctx.act, ctx.training, ctx.has_res = act, training, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B = get_backend()
+        x, y, gamma, mean, invstd = ctx.saved_tensors
+        dx, dres, dgamma, dbeta = B.bn_backward(dy.contiguous(), x, y, gamma.detach(), mean, invstd, ctx.act,
+                                                ctx.training, ctx.has_res and ctx.needs_input_grad[5])
+        if not ctx.needs_input_grad[1]:
+            dgamma = None
+        if not ctx.needs_input_grad[2]:
+            dbeta = None
+        return dx, dgamma, dbeta, None, None, dres, None, None, None, None
+
+
+class ReLU(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = get_backend().relu_fwd(x.contiguous())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return get_backend().relu_bwd(dy.contiguous(), y)
+
+
+class Add(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return get_backend().add(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+class CatChannels(Function):
+    """torch.cat(dim=1) of the reference == channel concat on NHWC."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        ctx.widths = [int(x.shape[3]) for x in xs]
+        return get_backend().cat_channels([x.contiguous() for x in xs])
+
+    @staticmethod
+    def backward(ctx, dy):
+        B = get_backend()
+        dy = dy.contiguous()
+        outs, off = [], 0
+        for i, c in enumerate(ctx.widths):
+            outs.append(B.slice_channels(dy, off, c) if ctx.needs_input_grad[i] else None)
+            off += c
+        return tuple(outs)
+
+
+class GlobalAvgPool(Function):
+    """torch.mean over H then W with keepdim (ASPP branch 5)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, h, w, c = x.shape
+        ctx.hw = (h, w)
+        return get_backend().spatial_reduce(x.contiguous(), 1.0 / (h * w))
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, w = ctx.hw
+        return get_backend().spatial_broadcast(dy.contiguous(), h, w, 1.0 / (h * w))
+
+
+class BroadcastHW(Function):
+    """F.interpolate(1x1 -> HxW, bilinear, align_corners=True) == broadcast."""
+
+    @staticmethod
+    def forward(ctx, x, h, w):
+        return get_backend().spatial_broadcast(x.contiguous(), h, w, 1.0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return get_backend().spatial_reduce(dy.contiguous(), 1.0), None, None
+
+
+class UpsampleBilinear(Function):
+    """F.interpolate(mode='bilinear', align_corners=True) on NHWC."""
+
+    @staticmethod
+    def forward(ctx, x, ho, wo):
+        ctx.in_hw = (int(x.shape[1]), int(x.shape[2]))
+        return get_backend().upsample_fwd(x.contiguous(), ho, wo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return get_backend().upsample_bwd(dy.contiguous(), *ctx.in_hw), None, None
+
+
+class UpsampleToNCHW(Function):
+    """Final F.interpolate of the logits fused with the NHWC -> NCHW fp32 conversion."""
+
+    @staticmethod
+    def forward(ctx, x, ho, wo):
+        ctx.in_hw, ctx.dtype = (int(x.shape[1]), int(x.shape[2])), x.dtype
+        return get_backend().upsample_to_nchw_fwd(x.contiguous(), ho, wo)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return get_backend().upsample_to_nchw_bwd(dy.contiguous().float(), ctx.in_hw[0], ctx.in_hw[1], ctx.dtype), None, None
+
+
+class Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        y, mask = get_backend().dropout_fwd(x.contiguous(), p, seed)
+        ctx.save_for_backward(mask)
+        ctx.p = p
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        return get_backend().dropout_bwd(dy.contiguous(), mask, ctx.p), None, None
+
+
+class SegLoss(Function):
+    """Weighted sum of the reference's CE / focal / dice losses plus the f_score metric, from
+    one statistics pass over fp32 NCHW logits.  Returns a 4-vector (ce, focal, dice, f_score);
+    gradients flow from the first three."""
+
+    @staticmethod
+    def forward(ctx, logits, target, onehot, cls_w, alpha, gamma, beta, smooth, thr):
+        B = get_backend()
+        logits = logits.contiguous()
+        target = target.contiguous()
+        if onehot is not None:
+            onehot = onehot.contiguous().float()
+        if cls_w is not None:
+            cls_w = cls_w.contiguous().float()
+        c = int(logits.shape[1])
+        stats = B.seg_loss_stats(logits, target, onehot, cls_w, alpha, gamma, thr)
+        res = B.seg_loss_finalize(stats, c, beta, smooth)
+        ctx.save_for_backward(logits, target, onehot, cls_w, stats)
+        ctx.cfg = (alpha, gamma, beta, smooth)
+        return res
+
+    @staticmethod
+    def backward(ctx, dres):
+        logits, target, onehot, cls_w, stats = ctx.saved_tensors
+        alpha, gamma, beta, smooth = ctx.cfg
+        g = dres.contiguous().float()[:3].contiguous()
+        d = get_backend().seg_loss_grad(logits, target, onehot, cls_w, stats, g, alpha, gamma, beta, smooth)
+        return d, None, None, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------- functional API
+def to_nhwc(x, dtype):
+    return ToNHWC.apply(x, dtype)
+
+
+def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1):
+    return Conv2d.apply(x, weight, bias, stride, pad, dil)
+
+
+def dwconv3x3(x, weight, stride=1, pad=1, dil=1, relu_in=False):
+    return DepthwiseConv3x3.apply(x, weight, stride, pad, dil, relu_in)
+
+
+def batchnorm_act(x, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None):
+    """Apply an ``nn.BatchNorm2d`` parameter holder to an NHWC tensor (never calls bn.forward)."""
+    training = bn.training or (bn.running_mean is None)
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    return BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training, momentum,
+                              bn.eps, act)
+
+
+def relu(x):
+    return ReLU.apply(x)
+
+
+def cat_channels(xs):
+    return CatChannels.apply(*xs)
+
+
+def global_avg_pool(x):
+    return GlobalAvgPool.apply(x)
+
+
+def broadcast_hw(x, h, w):
+    return BroadcastHW.apply(x, h, w)
+
+
+def upsample_bilinear(x, ho, wo):
+    if x.shape[1] == ho and x.shape[2] == wo:
+        return x
+    return UpsampleBilinear.apply(x, ho, wo)
+
+
+def upsample_to_nchw(x, ho, wo):
+    return UpsampleToNCHW.apply(x, ho, wo)
+
+
+_dropout_counter = [0]
+
+
+def dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    # seed derived from torch's generator so torch.manual_seed governs it (host-side only)
+    _dropout_counter[0] += 1
+    seed = (torch.initial_seed() * 1000003 + _dropout_counter[0]) & (2 ** 63 - 1)
+    return Dropout.apply(x, float(p), seed)
+
+
+def seg_losses(logits, target, onehot=None, cls_weights=None, alpha=0.5, gamma=2.0, beta=1.0, smooth=1e-5,
+               threshold=0.5):
+    """(ce, focal, dice, f_score) as a 4-element fp32 tensor."""
+    a = 1.0 if alpha is None else float(alpha)
+    return SegLoss.apply(logits, target, onehot, cls_weights, a, float(gamma), float(beta), float(smooth),
+                         float(threshold))

@@ -1,0 +1,291 @@
+"""Plain-torch emulation of the backend method set (TEST INFRASTRUCTURE ONLY).
+
+``EmuBackend`` restates, op by op, what each C-ABI entry point of include/cervix_b200.h must
+compute, using stock torch ops in fp32.  It is used two ways:
+  * on CPU-only CI it is installed in place of the CUDA backend so the host-side graph logic
+    (module wiring, autograd shells, weight packing conventions) is checked against the oracle;
+  * on the GPU box every CUDA kernel is compared with the corresponding method here.
+The product never imports this file.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def _nchw(x):  # NHWC -> NCHW fp32
+    return x.permute(0, 3, 1, 2).float()
+
+
+def _nhwc(x, dtype):
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+class EmuBackend:
+    name = "emu"
+
+    def is_sm100(self):
+        return False
+
+    # ---- layout
+    def to_nhwc(self, x, dtype):
+        return _nhwc(x.float(), dtype)
+
+    def to_nchw(self, x):
+        return _nchw(x).contiguous()
+
+    def pack_weight(self, w, dtype, transpose_flip):
+        cout, cin, kh, kw = w.shape
+        if not transpose_flip:
+            return w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).contiguous().to(dtype)
+        wf = torch.flip(w, dims=(2, 3))
+        return wf.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout).contiguous().to(dtype)
+
+    def unpack_wgrad(self, g, cout, cin, kh, kw):
+        return g.reshape(kh, kw, cout, cin).permute(2, 3, 0, 1).contiguous().float()
+
+    def pack_dw_weight(self, w):
+        return w.reshape(w.shape[0], 9).t().contiguous().float()
+
+    def unpack_dw_wgrad(self, g):
+        return g.t().reshape(g.shape[1], 1, 3, 3).contiguous().float()
+
+    def cat_channels(self, xs):
+        return torch.cat(list(xs), dim=3).contiguous()
+
+    def slice_channels(self, x, off, c):
+        return x[..., off:off + c].contiguous()
+
+    # ---- dense conv (weights arrive PACKED, exactly as the C ABI receives them)
+    @staticmethod
+    def _unpack(wp, g):
+        return wp.float().reshape(g.kh, g.kw, g.cout, g.cin).permute(2, 3, 0, 1).contiguous()
+
+    @staticmethod
+    def _unpack_t(wpt, g):
+        w = wpt.float().reshape(g.kh, g.kw, g.cin, g.cout).permute(3, 2, 0, 1)
+        return torch.flip(w, dims=(2, 3)).contiguous()
+
+    def conv_fwd(self, x, wp, bias, g, tc):
+        y = F.conv2d(_nchw(x), self._unpack(wp, g), None if bias is None else bias.float(), g.stride, g.pad, g.dil)
+        assert y.shape[2] == g.ho and y.shape[3] == g.wo
+        return _nhwc(y, x.dtype)
+
+    def conv_dgrad(self, dy, wpt, g, tc):
+        w = self._unpack_t(wpt, g)
+        dx = torch.nn.grad.conv2d_input((g.n, g.cin, g.h, g.w), w, _nchw(dy), g.stride, g.pad, g.dil)
+        return _nhwc(dx, dy.dtype)
+
+    def conv_wgrad(self, x, dy, g, tc):
+        dw = torch.nn.grad.conv2d_weight(_nchw(x), (g.cout, g.cin, g.kh, g.kw), _nchw(dy), g.stride, g.pad, g.dil)
+        return dw.permute(2, 3, 0, 1).reshape(g.kh * g.kw, g.cout, g.cin).contiguous()
+
+    def bias_grad(self, dy):
+        return dy.float().reshape(-1, dy.shape[-1]).sum(0)
+
+    def subsample(self, x, s):
+        return x[:, ::s, ::s, :].contiguous()
+
+    def subsample_bwd(self, dy, h, w, s):
+        dx = torch.zeros((dy.shape[0], h, w, dy.shape[3]), dtype=dy.dtype, device=dy.device)
+        dx[:, ::s, ::s, :] = dy
+        return dx
+
+    # ---- depthwise
+    @staticmethod
+    def _dw_w(w9c):
+        return w9c.t().reshape(w9c.shape[1], 1, 3, 3).contiguous()
+
+    def dw_fwd(self, x, w9c, g, relu_in):
+        xi = _nchw(x)
+        if relu_in:
+            xi = F.relu(xi)
+        return _nhwc(F.conv2d(xi, self._dw_w(w9c), None, g.stride, g.pad, g.dil, groups=g.cin), x.dtype)
+
+    def dw_bwd_data(self, dy, w9c, x, g, relu_in):
+        dx = torch.nn.grad.conv2d_input((g.n, g.cin, g.h, g.w), self._dw_w(w9c), _nchw(dy), g.stride, g.pad, g.dil,
+                                        groups=g.cin)
+        if relu_in:
+            dx = dx * (_nchw(x) > 0)
+        return _nhwc(dx, dy.dtype)
+
+    def dw_bwd_weight(self, x, dy, g, relu_in):
+        xi = _nchw(x)
+        if relu_in:
+            xi = F.relu(xi)
+        dw = torch.nn.grad.conv2d_weight(xi, (g.cin, 1, 3, 3), _nchw(dy), g.stride, g.pad, g.dil, groups=g.cin)
+        return dw.reshape(g.cin, 9).t().contiguous()
+
+    # ---- batch norm
+    @staticmethod
+    def _act(v, act):
+        return F.relu(v) if act == 1 else (F.relu6(v) if act == 2 else v)
+
+    @staticmethod
+    def _mask(y, act):
+        if act == 1:
+            return (y > 0).float()
+        if act == 2:
+            return ((y > 0) & (y < 6)).float()
+        return torch.ones_like(y, dtype=torch.float32)
+
+    def bn_forward(self, x, residual, gamma, beta, rmean, rvar, act, training, momentum, eps):
+        c = x.shape[-1]
+        xf = x.float().reshape(-1, c)
+        if training:
+            mean = xf.double().mean(0)
+            var = xf.double().var(0, unbiased=False)
+            n = xf.shape[0]
+            if rmean is not None:
+                rmean.mul_(1 - momentum).add_(momentum * mean.float())
+                rvar.mul_(1 - momentum).add_(momentum * (var * n / max(n - 1, 1)).float())
+            mean, invstd = mean.float(), (1.0 / torch.sqrt(var + eps)).float()
+        else:
+            mean, invstd = rmean.clone().float(), 1.0 / torch.sqrt(rvar.float() + eps)
+        y = (xf - mean) * (invstd * gamma.float()) + beta.float()
+        if residual is not None:
+            y = y + residual.float().reshape(-1, c)
+        return self._act(y, act).reshape(x.shape).to(x.dtype), mean, invstd
+
+    def bn_backward(self, dy, x, y, gamma, mean, invstd, act, training, want_dres):
+        c = x.shape[-1]
+        dz = dy.float().reshape(-1, c)
+        if act != 0:
+            dz = dz * self._mask(y.float().reshape(-1, c), act)
+        xhat = (x.float().reshape(-1, c) - mean) * invstd
+        dbeta = dz.double().sum(0).float()
+        dgamma = (dz * xhat).double().sum(0).float()
+        k = gamma.float() * invstd
+        if training:
+            n = dz.shape[0]
+            dx = k * (dz - dbeta / n - xhat * dgamma / n)
+        else:
+            dx = k * dz
+        dres = dz.reshape(x.shape).to(x.dtype) if want_dres else None
+        return dx.reshape(x.shape).to(x.dtype), dres, dgamma, dbeta
+
+    # ---- small ops
+    def relu_fwd(self, x):
+        return F.relu(x)
+
+    def relu_bwd(self, dy, y):
+        return dy * (y > 0)
+
+    def add(self, a, b):
+        return (a.float() + b.float()).to(a.dtype)
+
+    def spatial_reduce(self, x, scale):
+        return (x.float().sum(dim=(1, 2), keepdim=True) * scale).to(x.dtype)
+
+    def spatial_broadcast(self, x, h, w, scale):
+        return (x.float() * scale).expand(x.shape[0], h, w, x.shape[3]).contiguous().to(x.dtype)
+
+    def upsample_fwd(self, x, ho, wo):
+        return _nhwc(F.interpolate(_nchw(x), size=(ho, wo), mode="bilinear", align_corners=True), x.dtype)
+
+    def upsample_bwd(self, dy, hi, wi):
+        n, ho, wo, c = dy.shape
+        with torch.enable_grad():
+            x = torch.zeros((n, c, hi, wi), dtype=torch.float32, device=dy.device, requires_grad=True)
+            F.interpolate(x, size=(ho, wo), mode="bilinear", align_corners=True).backward(_nchw(dy))
+        return _nhwc(x.grad, dy.dtype)
+
+    def upsample_to_nchw_fwd(self, x, ho, wo):
+        return F.interpolate(_nchw(x), size=(ho, wo), mode="bilinear", align_corners=True).contiguous()
+
+    def upsample_to_nchw_bwd(self, dy, hi, wi, dtype):
+        n, c, ho, wo = dy.shape
+        with torch.enable_grad():
+            x = torch.zeros((n, c, hi, wi), dtype=torch.float32, device=dy.device, requires_grad=True)
+            F.interpolate(x, size=(ho, wo), mode="bilinear", align_corners=True).backward(dy.float())
+        return _nhwc(x.grad, dtype)
+
+    def dropout_fwd(self, x, p, seed):
+        g = torch.Generator(device="cpu").manual_seed(seed % (2 ** 63))
+        mask = (torch.rand(x.shape, generator=g) >= p).to(torch.uint8).to(x.device)
+        return (x.float() * mask / (1 - p)).to(x.dtype), mask
+
+    def dropout_bwd(self, dy, mask, p):
+        return (dy.float() * mask / (1 - p)).to(dy.dtype)
+
+    # ---- loss
+    def seg_loss_stats(self, logits, target, onehot, cls_w, alpha, gamma, thr):
+        n, c, h, w = logits.shape
+        z = logits.double().permute(0, 2, 3, 1).reshape(-1, c)
+        t = target.reshape(-1)
+        valid = (t >= 0) & (t < c)
+        ts = torch.where(valid, t, torch.zeros_like(t))
+        logp = torch.log_softmax(z, -1)
+        p = logp.exp()
+        wt = (cls_w.double()[ts] if cls_w is not None else torch.ones_like(ts, dtype=torch.float64)) * valid
+        u = wt * logp.gather(1, ts[:, None])[:, 0]
+        pt = u.exp()
+        focal = -((1 - pt) ** gamma) * alpha * u
+        oh = onehot.double().reshape(-1, c + 1)[:, :c] if onehot is not None else \
+            F.one_hot(torch.where(valid, t, torch.full_like(t, c)), c + 1)[:, :c].double()
+        hard = (p.float() > thr).double()
+        stats = torch.cat([torch.stack([-(u.sum()), wt.sum(), focal.sum(), torch.tensor(float(z.shape[0]), dtype=torch.float64, device=z.device)]),
+                           (oh * p).sum(0), p.sum(0), oh.sum(0), (oh * hard).sum(0), hard.sum(0), oh.sum(0)])
+        return stats
+
+    @staticmethod
+    def _dice(tp, sp, st, beta, smooth):
+        b2 = beta * beta
+        fp, fn = sp - tp, st - tp
+        return (((1 + b2) * tp + smooth) / ((1 + b2) * tp + b2 * fn + fp + smooth)).mean()
+
+    def seg_loss_finalize(self, stats, c, beta, smooth):
+        s = stats
+        ce = s[0] / s[1]
+        focal = s[2] / s[3]
+        dice = 1 - self._dice(s[4:4 + c], s[4 + c:4 + 2 * c], s[4 + 2 * c:4 + 3 * c], beta, smooth)
+        fsc = self._dice(s[4 + 3 * c:4 + 4 * c], s[4 + 4 * c:4 + 5 * c], s[4 + 5 * c:4 + 6 * c], beta, smooth)
+        return torch.stack([ce, focal, dice, fsc]).float()
+
+    def seg_loss_grad(self, logits, target, onehot, cls_w, stats, g, alpha, gamma, beta, smooth):
+        # autograd through an independent fp64 restatement of the three losses
+        with torch.enable_grad():
+            return self._seg_loss_grad(logits, target, onehot, cls_w, g, alpha, gamma, beta, smooth)
+
+    def _seg_loss_grad(self, logits, target, onehot, cls_w, g, alpha, gamma, beta, smooth):
+        n, c, h, w = logits.shape
+        z = logits.double().detach().requires_grad_(True)
+        flat = z.permute(0, 2, 3, 1).reshape(-1, c)
+        t = target.reshape(-1)
+        valid = (t >= 0) & (t < c)
+        ts = torch.where(valid, t, torch.zeros_like(t))
+        logp = torch.log_softmax(flat, -1)
+        wt = (cls_w.double()[ts] if cls_w is not None else torch.ones_like(ts, dtype=torch.float64)) * valid
+        u = wt * logp.gather(1, ts[:, None])[:, 0]
+        ce = -(u.sum()) / wt.sum()
+        focal = (-((1 - u.exp()) ** gamma) * alpha * u).mean()
+        p = logp.exp()
+        oh = onehot.double().reshape(-1, c + 1)[:, :c] if onehot is not None else \
+            F.one_hot(torch.where(valid, t, torch.full_like(t, c)), c + 1)[:, :c].double()
+        dice = 1 - self._dice((oh * p).sum(0), p.sum(0), oh.sum(0), beta, smooth)
+        gd = g.double()
+        (gd[0] * ce + gd[1] * focal + gd[2] * dice).backward()
+        return z.grad.float()
+
+    # ---- optimizer
+    def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, wd, step_t, grad_scale=1.0):
+        gi = g * grad_scale
+        if wd != 0:
+            gi = gi + wd * p
+        m.mul_(beta1).add_((1 - beta1) * gi)
+        v.mul_(beta2).add_((1 - beta2) * gi * gi)
+        bc1 = 1 - beta1 ** step_t
+        bc2 = 1 - beta2 ** step_t
+        p.sub_((lr / bc1) * m / (v.sqrt() / (bc2 ** 0.5) + eps))
+
+    def sgd_step(self, p, g, buf, lr, momentum, wd, nesterov, first_step, grad_scale=1.0):
+        gi = g * grad_scale
+        if wd != 0:
+            gi = gi + wd * p
+        if momentum != 0:
+            if first_step:
+                buf.copy_(gi)
+            else:
+                buf.mul_(momentum).add_(gi)
+            gi = gi + momentum * buf if nesterov else buf
+        p.sub_(lr * gi)
