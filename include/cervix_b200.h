@@ -30,6 +30,11 @@ extern "C" {
 #endif
 
 #define CVX_ABI_VERSION 1
+#if defined(__GNUC__)
+#define CVX_API __attribute__((visibility("default")))
+#else
+#define CVX_API
+#endif
 
 enum { CVX_F32 = 0, CVX_BF16 = 1 };
 enum { CVX_ACT_NONE = 0, CVX_ACT_RELU = 1, CVX_ACT_RELU6 = 2 };
@@ -44,94 +49,96 @@ typedef struct cvx_conv_desc {
   int32_t dtype;             /* CVX_F32 | CVX_BF16 : storage of x, packed w and y */
 } cvx_conv_desc;
 
-int         cvx_abi_version(void);
-const char* cvx_last_error(void);
+CVX_API int         cvx_abi_version(void);
+CVX_API const char* cvx_last_error(void);
+/* number of kernels this library has launched so far in this process */
+CVX_API int64_t     cvx_launch_count(void);
 /* 1 if the running device is sm_100 (tcgen05/TMA kernels usable), 0 otherwise */
-int         cvx_device_is_sm100(void);
+CVX_API int         cvx_device_is_sm100(void);
 
 /* ---- layout plumbing -------------------------------------------------------------- */
 /* NCHW fp32 -> NHWC dtype : entry of DeepLab.forward (nets/deeplabv3_plus.py:169). */
-int cvx_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dtype, void* stream);
-int cvx_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int dtype, void* stream);
+CVX_API int cvx_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dtype, void* stream);
+CVX_API int cvx_nhwc_to_nchw(const void* src, float* dst, int n, int c, int h, int w, int dtype, void* stream);
 /* nn.Conv2d.weight OIHW fp32 -> packed [tap][cout][cin] dtype.  transpose_flip=1 gives the
  * data-gradient operand [flipped tap][cin][cout]. */
-int cvx_pack_weight(const float* w_oihw, void* dst, int cout, int cin, int kh, int kw, int dtype,
+CVX_API int cvx_pack_weight(const float* w_oihw, void* dst, int cout, int cin, int kh, int kw, int dtype,
                     int transpose_flip, void* stream);
 /* packed fp32 weight gradient [tap][cout][cin] -> OIHW fp32 (.grad layout) */
-int cvx_unpack_wgrad(const float* g_packed, float* g_oihw, int cout, int cin, int kh, int kw, void* stream);
+CVX_API int cvx_unpack_wgrad(const float* g_packed, float* g_oihw, int cout, int cin, int kh, int kw, void* stream);
 /* depthwise nn.Conv2d.weight [C,1,3,3] <-> fp32 [9][C] */
-int cvx_pack_dw_weight(const float* w_c133, float* dst, int c, void* stream);
-int cvx_unpack_dw_wgrad(const float* g_9c, float* g_c133, int c, void* stream);
+CVX_API int cvx_pack_dw_weight(const float* w_c133, float* dst, int c, void* stream);
+CVX_API int cvx_unpack_dw_wgrad(const float* g_9c, float* g_c133, int c, void* stream);
 /* channel-slice copy: dst[row, dst_coff : dst_coff+c] = src[row, src_coff : src_coff+c]
  * (torch.cat / its backward on NHWC; nets/deeplabv3_plus.py:110,185) */
-int cvx_copy_channels(const void* src, int src_ld, int src_coff, void* dst, int dst_ld, int dst_coff,
+CVX_API int cvx_copy_channels(const void* src, int src_ld, int src_coff, void* dst, int dst_ld, int dst_coff,
                       int64_t rows, int c, int dtype, void* stream);
 
 /* ---- dense convolution, generic SIMT path (any shape; the fp32 parity path) ----------- */
 /* nn.Conv2d forward (xception.py:95,99,44,16; deeplabv3_plus.py:59-87,149-167) */
-int cvx_conv_fwd(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+CVX_API int cvx_conv_fwd(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                  void* y, void* stream);
 /* data gradient; w_packed_t is the transpose_flip=1 packing */
-int cvx_conv_dgrad(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
+CVX_API int cvx_conv_dgrad(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
 /* weight gradient, ACCUMULATED into fp32 dw_packed[tap][cout][cin] (caller zeroes it) */
-int cvx_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
+CVX_API int cvx_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
 /* bias gradient: dbias[c] = sum over rows of dy (overwrites) */
-int cvx_bias_grad(const void* dy, float* dbias, double* ws, int64_t rows, int c, int dtype, void* stream);
+CVX_API int cvx_bias_grad(const void* dy, float* dbias, double* ws, int64_t rows, int c, int dtype, void* stream);
 
 /* ---- dense convolution, tcgen05/TMEM/TMA implicit GEMM (bf16, sm_100a) ---------------- */
 /* Same contracts as the three calls above; stride must be 1 (stride-2 1x1 convs are fed a
  * pre-subsampled input by the host).  Returns CVX_EUNSUPPORTED for shapes the tensor-core
  * path does not take (C_in or C_out not a multiple of 8, dtype != bf16). */
-int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+CVX_API int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                     void* y, void* stream);
-int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
-int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
+CVX_API int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
+CVX_API int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
 /* spatial subsample x[:, ::s, ::s, :] and its scatter-back (1x1 stride-2 skip convs,
  * xception.py:44) */
-int cvx_subsample(const void* x, void* y, int n, int h, int w, int c, int s, int dtype, void* stream);
-int cvx_subsample_bwd(const void* dy, void* dx, int n, int h, int w, int c, int s, int dtype, void* stream);
+CVX_API int cvx_subsample(const void* x, void* y, int n, int h, int w, int c, int s, int dtype, void* stream);
+CVX_API int cvx_subsample_bwd(const void* dy, void* dx, int n, int h, int w, int c, int s, int dtype, void* stream);
 
 /* ---- depthwise 3x3 (xception.py:13, mobilenetv2.py:39,58) --------------------------- */
 /* relu_in=1 applies ReLU to x on load (SeparableConv2d.relu0, xception.py:22-23) */
-int cvx_dwconv_fwd(const cvx_conv_desc* d, const void* x, const float* w9c, void* y, int relu_in, void* stream);
-int cvx_dwconv_bwd_data(const cvx_conv_desc* d, const void* dy, const float* w9c, const void* x,
+CVX_API int cvx_dwconv_fwd(const cvx_conv_desc* d, const void* x, const float* w9c, void* y, int relu_in, void* stream);
+CVX_API int cvx_dwconv_bwd_data(const cvx_conv_desc* d, const void* dy, const float* w9c, const void* x,
                         void* dx, int relu_in, void* stream);
 /* dw9c (fp32 [9][C]) is overwritten; ws needs 9*C doubles */
-int cvx_dwconv_bwd_weight(const cvx_conv_desc* d, const void* x, const void* dy, float* dw9c,
+CVX_API int cvx_dwconv_bwd_weight(const cvx_conv_desc* d, const void* x, const void* dy, float* dw9c,
                           double* ws, int relu_in, void* stream);
 
 /* ---- BatchNorm2d (+ residual add + activation) -------------------------------------- */
 /* y = act(bn(x) + residual).  training=1: batch statistics, running buffers updated with
  * `momentum` (unbiased variance), save_mean/save_invstd written for backward.
  * training=0: running statistics.  ws: 2*C doubles of scratch. */
-int cvx_bn_forward(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
+CVX_API int cvx_bn_forward(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                    double* ws, int64_t rows, int c, int dtype, int act, int training,
                    float momentum, float eps, void* stream);
 /* dx (and dres = d(act) if non-null), dgamma, dbeta (overwritten).  y is required when
  * act != NONE (activation mask).  training=0 treats mean/invstd as constants. */
-int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* gamma,
+CVX_API int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* gamma,
                     const float* save_mean, const float* save_invstd, void* dx, void* dres,
                     float* dgamma, float* dbeta, double* ws, int64_t rows, int c, int dtype,
                     int act, int training, void* stream);
 
 /* ---- small bandwidth ops ------------------------------------------------------------ */
-int cvx_relu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
-int cvx_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, void* stream);
-int cvx_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+CVX_API int cvx_relu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream);
+CVX_API int cvx_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, void* stream);
+CVX_API int cvx_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 /* y[n,c] = scale * sum_hw x[n,hw,c]  (ASPP global pooling, deeplabv3_plus.py:101-102) */
-int cvx_spatial_reduce(const void* x, void* y, int n, int hw, int c, float scale, int dtype, void* stream);
+CVX_API int cvx_spatial_reduce(const void* x, void* y, int n, int hw, int c, float scale, int dtype, void* stream);
 /* y[n,hw,c] = scale * x[n,c]  (1x1 -> HxW "bilinear" broadcast, deeplabv3_plus.py:106) */
-int cvx_spatial_broadcast(const void* x, void* y, int n, int hw, int c, float scale, int dtype, void* stream);
+CVX_API int cvx_spatial_broadcast(const void* x, void* y, int n, int hw, int c, float scale, int dtype, void* stream);
 /* F.interpolate(mode='bilinear', align_corners=True) on NHWC (deeplabv3_plus.py:184) */
-int cvx_upsample_fwd(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
-int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
+CVX_API int cvx_upsample_fwd(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
+CVX_API int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
 /* final upsample fused with the NHWC->NCHW fp32 conversion (deeplabv3_plus.py:187) */
-int cvx_upsample_to_nchw_fwd(const void* x, float* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
-int cvx_upsample_to_nchw_bwd(const float* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
+CVX_API int cvx_upsample_to_nchw_fwd(const void* x, float* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
+CVX_API int cvx_upsample_to_nchw_bwd(const float* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
 /* nn.Dropout: mask byte per element, y = x * mask / (1-p) (deeplabv3_plus.py:159,165) */
-int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, int dtype, void* stream);
-int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream);
+CVX_API int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, int dtype, void* stream);
+CVX_API int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream);
 
 /* ---- segmentation objective (nets/deeplabv3_training.py:9-56, utils/utils_metrics.py:13-35) */
 /* One pass over fp32 NCHW logits [n,c,h,w] and int64 targets [n,h,w] (value c = ignore).
@@ -139,13 +146,13 @@ int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, fl
  * stats (double, 4 + 6*c entries, zeroed by the call):
  *   [0] sum w_t*nll  [1] sum w_t (valid)  [2] sum focal_i  [3] pixel count
  *   [4..4+c) tp  [4+c..) sum p  [4+2c..) sum t   then the same three for the hard mask. */
-int cvx_seg_loss_stats(const float* logits, const int64_t* target, const float* onehot,
+CVX_API int cvx_seg_loss_stats(const float* logits, const int64_t* target, const float* onehot,
                        const float* cls_weights, double* stats, int n, int c, int h, int w,
                        float focal_alpha, float focal_gamma, float threshold, void* stream);
 /* results[0..3] = CE, focal, dice, f_score from stats (device -> device, fp32) */
-int cvx_seg_loss_finalize(const double* stats, float* results, int c, float beta, float smooth, void* stream);
+CVX_API int cvx_seg_loss_finalize(const double* stats, float* results, int c, float beta, float smooth, void* stream);
 /* dlogits = g[0]*dCE + g[1]*dFocal + g[2]*dDice, g = 3 device floats (upstream grads) */
-int cvx_seg_loss_grad(const float* logits, const int64_t* target, const float* onehot,
+CVX_API int cvx_seg_loss_grad(const float* logits, const int64_t* target, const float* onehot,
                       const float* cls_weights, const double* stats, const float* g, float* dlogits,
                       int n, int c, int h, int w, float focal_alpha, float focal_gamma,
                       float beta, float smooth, void* stream);
@@ -153,10 +160,10 @@ int cvx_seg_loss_grad(const float* logits, const int64_t* target, const float* o
 /* ---- optimizer (train.py:472-476) ---------------------------------------------------- */
 /* torch.optim.Adam semantics (L2 weight decay added to the gradient), fp32 state.
  * step_t is the 1-based step count; grad_scale multiplies the gradient first. */
-int cvx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+CVX_API int cvx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step_t, float grad_scale, void* stream);
 /* torch.optim.SGD(momentum, nesterov) semantics */
-int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,
+CVX_API int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 
 #ifdef __cplusplus

@@ -29,6 +29,7 @@ _D = C.POINTER(ConvDesc)
 PROTOTYPES = {
     "cvx_abi_version": [],
     "cvx_last_error": [],
+    "cvx_launch_count": [],
     "cvx_device_is_sm100": [],
     "cvx_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _P],
     "cvx_nhwc_to_nchw": [_P, _P, _I, _I, _I, _I, _I, _P],
@@ -68,7 +69,7 @@ PROTOTYPES = {
     "cvx_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],
 }
-_RESTYPES = {"cvx_last_error": C.c_char_p}
+_RESTYPES = {"cvx_last_error": C.c_char_p, "cvx_launch_count": C.c_int64}
 
 _lib = None
 

@@ -76,6 +76,7 @@ static int colreduce_launch(const F& f, int64_t rows, int C, double* out, cudaSt
   dim3 grid((unsigned)gx, ychunks);
   const size_t smem = sizeof(float) * F::NACC * colchunk * VEC;
   colreduce_kernel<T, F><<<grid, 256, smem, stream>>>(f, rows, C, colchunk, (int)rpb, out);
+  ++g_kernel_launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     set_error("colreduce launch failed: %s", cudaGetErrorString(e));

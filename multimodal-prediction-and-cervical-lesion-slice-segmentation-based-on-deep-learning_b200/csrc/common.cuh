@@ -11,6 +11,7 @@
 namespace cvx {
 
 void set_error(const char* fmt, ...);
+extern unsigned long long g_kernel_launches;  // kernels launched by this library (bench.py's gpu_launches)
 
 #define CVX_CHECK_ARG(cond, ...)                 \
   do {                                           \
@@ -31,6 +32,7 @@ void set_error(const char* fmt, ...);
 
 #define CVX_LAUNCH_OK()                                                              \
   do {                                                                               \
+    ++cvx::g_kernel_launches;                                                        \
     cudaError_t _e = cudaPeekAtLastError();                                          \
     if (_e != cudaSuccess) {                                                         \
       cvx::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

@@ -1,0 +1,141 @@
+"""Training-step engine for the DeepLabv3+ path: flat parameter/gradient storage, one fused
+optimizer launch, and bucketed NCCL gradient all-reduce overlapped with backward.
+
+Replaces, for callers that want the fast path, the reference's per-step sequence
+``optimizer.zero_grad(); outputs = model_train(imgs); loss = focal + dice; loss.backward();
+optimizer.step()`` (utils/utils_fit.py:60-121) and its ``DistributedDataParallel`` wrapper
+(train.py:386).  Semantics kept: torch.optim.Adam / SGD(nesterov) math, mean-reduced gradients
+across ranks, per-rank BatchNorm statistics (the reference's default ``sync_bn=False``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .backend import get_backend
+from .nets.deeplabv3_training import seg_objective
+
+
+class FlatParams:
+    """All trainable parameters of a module re-homed into ONE contiguous fp32 buffer (and their
+    ``.grad`` into a second one), so the optimizer and the all-reduce see a single tensor."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.offsets, off = [], 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4  # keep every tensor 16-byte aligned
+        self.numel = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            self.data[o:o + p.numel()].copy_(p.data.reshape(-1))
+            p.data = self.data[o:o + p.numel()].view(p.shape)
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+class SegTrainer:
+    """One data-parallel training step of DeepLab with the reference's default objective
+    (focal + dice, train.py:259-265) on the CUDA engine."""
+
+    def __init__(self, model: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, optimizer: str = "adam", momentum: float = 0.9,
+                 cls_weights=None, num_classes: int = 5, dice: bool = True, focal: bool = True,
+                 bucket_mb: float = 32.0, world_size: int = 1):
+        self.model = model
+        self.flat = FlatParams(model)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.optimizer, self.momentum = optimizer, momentum
+        self.num_classes, self.dice, self.focal = num_classes, dice, focal
+        dev = self.flat.data.device
+        self.cls_weights = None if cls_weights is None else torch.as_tensor(cls_weights, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.flat.data)
+        self.v = torch.zeros_like(self.flat.data) if optimizer == "adam" else None
+        self.t = 0
+        self.world = world_size
+        self.last = None
+        if world_size > 1:
+            self._setup_buckets(bucket_mb)
+
+    # ------------------------------------------------------------------ data parallel
+    def _setup_buckets(self, bucket_mb: float):
+        """Buckets are contiguous slices of the flat gradient, filled from the END (backward
+        produces decoder gradients first).  A bucket is all-reduced on a side stream as soon as
+        its last gradient has been accumulated."""
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        n = len(self.flat.params)
+        self.bucket_of = [0] * n
+        self.buckets: List[List[int]] = []  # [start, end, pending, total]
+        end = self.flat.numel
+        start_idx = n
+        cur = 0
+        for i in range(n - 1, -1, -1):
+            size = (self.flat.params[i].numel() + 3) // 4 * 4
+            cur += size
+            self.bucket_of[i] = len(self.buckets)
+            if cur >= cap or i == 0:
+                self.buckets.append([self.flat.offsets[i], end, 0, start_idx - i])
+                end, start_idx, cur = self.flat.offsets[i], i, 0
+        # (gloo / CPU tensors are only used by the host-logic tests: no streams there)
+        self.comm_stream = torch.cuda.Stream() if self.flat.grad.is_cuda else None
+        self.works = []
+        for i, p in enumerate(self.flat.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(_p):
+            b = self.buckets[self.bucket_of[i]]
+            b[2] += 1
+            if b[2] == b[3]:
+                self._launch_bucket(b)
+        return hook
+
+    def _launch_bucket(self, b):
+        if self.comm_stream is None:
+            self.works.append(dist.all_reduce(self.flat.grad[b[0]:b[1]], op=dist.ReduceOp.SUM, async_op=True))
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            self.works.append(dist.all_reduce(self.flat.grad[b[0]:b[1]], op=dist.ReduceOp.SUM, async_op=True))
+
+    def _finish_allreduce(self):
+        for b in self.buckets:          # frozen / unused parameters never fire their hook
+            if b[2] != b[3]:
+                self._launch_bucket(b)
+            b[2] = 0
+        for w in self.works:
+            w.wait()
+        self.works = []
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    # ------------------------------------------------------------------ step
+    def step(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None):
+        """imgs: fp32 NCHW in [0,1]; pngs: int64 class map (num_classes = ignore); labels: the
+        reference's fp32 one-hot [B,H,W,C+1] (optional).  Returns the 4-vector
+        (ce, focal, dice, f_score) as a device tensor (no host sync)."""
+        B = get_backend()
+        self.flat.grad.zero_()
+        out = self.model(imgs)
+        ce, focal, dice, fs = seg_objective(out, pngs, labels, self.cls_weights, self.num_classes)
+        loss = (focal if self.focal else ce) + (dice if self.dice else 0.0)
+        loss.backward()
+        gscale = 1.0
+        if self.world > 1:
+            self._finish_allreduce()
+            gscale = 1.0 / self.world
+        self.t += 1
+        if self.optimizer == "adam":
+            B.adam_step(self.flat.data, self.flat.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1],
+                        self.eps, self.wd, self.t, gscale)
+        else:
+            B.sgd_step(self.flat.data, self.flat.grad, self.m, self.lr, self.momentum, self.wd, True, self.t == 1,
+                       gscale)
+        self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
+        return self.last
