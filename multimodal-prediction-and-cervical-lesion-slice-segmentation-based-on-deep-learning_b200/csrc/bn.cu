@@ -245,7 +245,7 @@ int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* g
   CVX_CHECK_ARG(c % vec == 0, "bn_backward: C=%d not a multiple of %d", c, vec);
   CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
   int rc = CVX_OK;
-  CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, BnBwdF<T>>(
+  CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, BnBwdF<T>, 256, 3>(
                                    BnBwdF<T>{(const T*)dy, (const T*)x, (const T*)y, save_mean, save_invstd, c, act},
                                    rows, c, ws, st)));
   if (rc) return rc;

@@ -1,8 +1,9 @@
 // Per-channel (column) reductions over an NHWC tensor viewed as [rows][C].
 //
 // Bandwidth-bound: every thread owns one 16-byte channel vector and walks down the rows, so
-// a warp always reads whole contiguous 512-byte spans; partial sums are combined through
-// shared-memory atomics per block and fp64 global atomics per channel (one per block).
+// a warp always reads whole contiguous 512-byte spans (4 independent rows in flight per
+// thread); partial sums are combined through shared-memory atomics once per block and fp64
+// global atomics per channel.  Few, long-lived blocks keep that epilogue negligible.
 #pragma once
 
 #include "common.cuh"
@@ -11,17 +12,17 @@ namespace cvx {
 
 // F must provide:  static constexpr int NACC;
 //   __device__ void operator()(int64_t row, int c0, float (&acc)[NACC][VEC]) const;
-template <typename T, typename F>
-__global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C, int colchunk_vecs,
-                                                        int rows_per_block, double* __restrict__ out) {
+template <typename T, typename F, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) colreduce_kernel(F f, int64_t rows, int C, int colchunk_vecs,
+                                                             int64_t rows_per_block, double* __restrict__ out) {
   constexpr int VEC = Elem<T>::kVec;
   constexpr int NACC = F::NACC;
   extern __shared__ float sm_acc[];  // [NACC][colchunk_vecs*VEC]
   const int chunk_elems = colchunk_vecs * VEC;
-  for (int i = threadIdx.x; i < NACC * chunk_elems; i += blockDim.x) sm_acc[i] = 0.f;
+  for (int i = threadIdx.x; i < NACC * chunk_elems; i += NT) sm_acc[i] = 0.f;
   __syncthreads();
 
-  const int lanes = (blockDim.x / colchunk_vecs);  // row lanes per block
+  const int lanes = NT / colchunk_vecs;  // row lanes per block
   const int cv = threadIdx.x % colchunk_vecs;
   const int lane = threadIdx.x / colchunk_vecs;
   const int cvec = blockIdx.y * colchunk_vecs + cv;
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > rows) r1 = rows;
+#pragma unroll 4
     for (int64_t r = r0 + lane; r < r1; r += lanes) f(r, cvec * VEC, acc);
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
       for (int i = 0; i < VEC; ++i) atomicAdd(&sm_acc[a * chunk_elems + cv * VEC + i], acc[a][i]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NACC * chunk_elems; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NACC * chunk_elems; i += NT) {
     const int a = i / chunk_elems, e = i % chunk_elems;
     const int c = blockIdx.y * chunk_elems + e;
     if (c < C) atomicAdd(out + (size_t)a * C + c, (double)sm_acc[i]);
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(F f, int64_t rows, int C
 }
 
 // Launch helper.  `out` ([NACC][C] doubles) must be zeroed by the caller.
-template <typename T, typename F>
+template <typename T, typename F, int NT = 256, int MINB = 4>
 static int colreduce_launch(const F& f, int64_t rows, int C, double* out, cudaStream_t stream) {
   constexpr int VEC = Elem<T>::kVec;
   if (C % VEC != 0) {
@@ -61,21 +63,21 @@ static int colreduce_launch(const F& f, int64_t rows, int C, double* out, cudaSt
   }
   const int cvn = C / VEC;
   int maxchunk = (12288 / F::NACC) / VEC;  // keep the block's partial-sum tile within 48 KB
-  if (maxchunk > 256) maxchunk = 256;
+  if (maxchunk > NT) maxchunk = NT;
   const int colchunk = cvn < maxchunk ? cvn : maxchunk;
-  const int lanes = 256 / colchunk;
+  const int lanes = NT / colchunk;
   const int ychunks = (cvn + colchunk - 1) / colchunk;
-  // enough blocks to fill the machine, each walking >= 8 rows per lane
-  int64_t want_blocks = (int64_t)kNumSMs * 8 / ychunks;
+  // one wave of resident blocks, each walking >= 16 rows per lane
+  int64_t want_blocks = (int64_t)kNumSMs * MINB / ychunks;
   if (want_blocks < 1) want_blocks = 1;
   int64_t rpb = ceil_div64(rows, want_blocks);
-  const int64_t min_rpb = (int64_t)lanes * 8;
+  const int64_t min_rpb = (int64_t)lanes * 16;
   if (rpb < min_rpb) rpb = min_rpb;
   rpb = ceil_div64(rpb, lanes) * lanes;
   const int64_t gx = ceil_div64(rows, rpb);
   dim3 grid((unsigned)gx, ychunks);
   const size_t smem = sizeof(float) * F::NACC * colchunk * VEC;
-  colreduce_kernel<T, F><<<grid, 256, smem, stream>>>(f, rows, C, colchunk, (int)rpb, out);
+  colreduce_kernel<T, F, NT, MINB><<<grid, NT, smem, stream>>>(f, rows, C, colchunk, rpb, out);
   ++g_kernel_launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -1,0 +1,292 @@
+// Convolutions with a very narrow channel dimension, where an implicit GEMM tile would be
+// almost empty and the op is bandwidth-bound:
+//   * "narrow in"  : the stem conv 3 -> 32, 3x3 stride 2 (xception.py:95, mobilenetv2.py:94)
+//                    forward + weight gradient (the image needs no data gradient);
+//   * "narrow out" : the classifier 1x1 conv 256 -> num_classes (deeplabv3_plus.py:167)
+//                    forward + data gradient + weight gradient.
+#include "colreduce.cuh"
+#include "conv_narrow.cuh"
+
+namespace cvx {
+
+struct NGeom {
+  int n, h, w, cin, cout, kh, kw, stride, pad, dil, ho, wo;
+};
+
+constexpr int kStemCout = 32;
+constexpr int kStemMaxK = 36;  // taps * cin
+
+// ---------------------------------------------------------------- narrow in: forward
+template <typename T>
+__global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wp,
+                                                       T* __restrict__ y, NGeom g) {
+  __shared__ float ws[kStemMaxK][kStemCout];  // [tap*cin + ci][co]
+  const int K = g.kh * g.kw * g.cin;
+  for (int i = threadIdx.x; i < K * kStemCout; i += blockDim.x) {
+    const int k = i / kStemCout, co = i % kStemCout;
+    const int tap = k / g.cin, ci = k % g.cin;
+    ws[k][co] = Elem<T>::ld(wp + ((size_t)tap * kStemCout + co) * g.cin + ci);
+  }
+  __syncthreads();
+  const int64_t npix = (int64_t)g.n * g.ho * g.wo;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % g.wo), oy = (int)((p / g.wo) % g.ho), nn = (int)(p / ((int64_t)g.wo * g.ho));
+    float acc[kStemCout];
+#pragma unroll
+    for (int c = 0; c < kStemCout; ++c) acc[c] = 0.f;
+    for (int kh = 0; kh < g.kh; ++kh) {
+      const int iy = oy * g.stride - g.pad + kh * g.dil;
+      if (iy < 0 || iy >= g.h) continue;
+      for (int kw = 0; kw < g.kw; ++kw) {
+        const int ix = ox * g.stride - g.pad + kw * g.dil;
+        if (ix < 0 || ix >= g.w) continue;
+        const T* px = x + (((size_t)nn * g.h + iy) * g.w + ix) * g.cin;
+        const int kbase = (kh * g.kw + kw) * g.cin;
+        for (int ci = 0; ci < g.cin; ++ci) {
+          const float xv = Elem<T>::ld(px + ci);
+          const float4* wrow = reinterpret_cast<const float4*>(ws[kbase + ci]);
+#pragma unroll
+          for (int j = 0; j < kStemCout / 4; ++j) {
+            const float4 w4 = wrow[j];
+            acc[4 * j] = fmaf(xv, w4.x, acc[4 * j]);
+            acc[4 * j + 1] = fmaf(xv, w4.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(xv, w4.z, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(xv, w4.w, acc[4 * j + 3]);
+          }
+        }
+      }
+    }
+    T* out = y + p * kStemCout;
+    constexpr int V = Elem<T>::kVec;
+#pragma unroll
+    for (int j = 0; j < kStemCout / V; ++j) {
+      Vec<T> o;
+#pragma unroll
+      for (int i = 0; i < V; ++i) o.v[i] = acc[j * V + i];
+      o.store(out + j * V);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- narrow in: weight gradient
+// block = 256 threads; thread (k, cg) owns dW[k][4*cg .. 4*cg+3]; pixels staged 64 at a time
+template <typename T>
+__global__ void __launch_bounds__(288) stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                         float* __restrict__ dw, NGeom g) {
+  constexpr int P = 64;
+  __shared__ float xs[P][kStemMaxK + 1];
+  __shared__ __align__(16) float dys[P][kStemCout];
+  const int K = g.kh * g.kw * g.cin;
+  const int k = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const bool owner = k < K;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t npix = (int64_t)g.n * g.ho * g.wo;
+  for (int64_t p0 = (int64_t)blockIdx.x * P; p0 < npix; p0 += (int64_t)gridDim.x * P) {
+    for (int i = threadIdx.x; i < P * kStemCout; i += blockDim.x) {
+      const int pp = i / kStemCout, co = i % kStemCout;
+      dys[pp][co] = (p0 + pp < npix) ? Elem<T>::ld(dy + (p0 + pp) * kStemCout + co) : 0.f;
+    }
+    for (int i = threadIdx.x; i < P * K; i += blockDim.x) {
+      const int pp = i / K, kk = i % K;
+      const int64_t p = p0 + pp;
+      float v = 0.f;
+      if (p < npix) {
+        const int ox = (int)(p % g.wo), oy = (int)((p / g.wo) % g.ho), nn = (int)(p / ((int64_t)g.wo * g.ho));
+        const int tap = kk / g.cin, ci = kk % g.cin;
+        const int iy = oy * g.stride - g.pad + (tap / g.kw) * g.dil;
+        const int ix = ox * g.stride - g.pad + (tap % g.kw) * g.dil;
+        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) v = Elem<T>::ld(x + (((size_t)nn * g.h + iy) * g.w + ix) * g.cin + ci);
+      }
+      xs[pp][kk] = v;
+    }
+    __syncthreads();
+    if (owner) {
+#pragma unroll 8
+      for (int pp = 0; pp < P; ++pp) {
+        const float a = xs[pp][k];
+        const float4 d = *reinterpret_cast<const float4*>(&dys[pp][cg * 4]);
+        acc.x = fmaf(a, d.x, acc.x); acc.y = fmaf(a, d.y, acc.y);
+        acc.z = fmaf(a, d.z, acc.z); acc.w = fmaf(a, d.w, acc.w);
+      }
+    }
+    __syncthreads();
+  }
+  if (owner) {
+    const int tap = k / g.cin, ci = k % g.cin;
+    const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(dw + ((size_t)tap * kStemCout + cg * 4 + j) * g.cin + ci, v[j]);
+  }
+}
+
+// ---------------------------------------------------------------- narrow out (1x1, C_out <= 8)
+constexpr int kMaxNarrowOut = 8;
+constexpr int kMaxNarrowCin = 1024;
+
+// one warp per pixel: lanes split the channel vectors, shuffle-reduce the C_out dot products
+template <typename T>
+__global__ void __launch_bounds__(256) narrow_out_fwd_kernel(const T* __restrict__ x, const T* __restrict__ wp,
+                                                             const float* __restrict__ bias, T* __restrict__ y,
+                                                             int64_t npix, int cin, int cout) {
+  constexpr int V = Elem<T>::kVec;
+  extern __shared__ float wsm[];  // [cout][cin]
+  for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) wsm[i] = Elem<T>::ld(wp + i);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int cvn = cin / V;
+  for (int64_t p = warp0; p < npix; p += nwarps) {
+    float acc[kMaxNarrowOut];
+#pragma unroll
+    for (int c = 0; c < kMaxNarrowOut; ++c) acc[c] = 0.f;
+    for (int cv = lane; cv < cvn; cv += 32) {
+      Vec<T> v;
+      v.load(x + p * cin + cv * V);
+#pragma unroll
+      for (int c = 0; c < kMaxNarrowOut; ++c) {
+        if (c < cout) {
+          const float* wr = wsm + c * cin + cv * V;
+#pragma unroll
+          for (int i = 0; i < V; ++i) acc[c] = fmaf(v.v[i], wr[i], acc[c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxNarrowOut; ++c)
+      if (c < cout) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < kMaxNarrowOut; ++c)
+        if (c < cout) Elem<T>::st(y + p * cout + c, acc[c] + (bias ? bias[c] : 0.f));
+    }
+  }
+}
+
+// dx[p][ci] = sum_co dy[p][co] * Wt[ci][co]  (packed_t layout [1][cin][cout])
+template <typename T>
+__global__ void __launch_bounds__(256) narrow_out_dgrad_kernel(const T* __restrict__ dy, const T* __restrict__ wpt,
+                                                               T* __restrict__ dx, int64_t npix, int cin, int cout) {
+  constexpr int V = Elem<T>::kVec;
+  extern __shared__ float wsm[];  // [cin][cout]
+  for (int i = threadIdx.x; i < cout * cin; i += blockDim.x) wsm[i] = Elem<T>::ld(wpt + i);
+  __syncthreads();
+  const int cvn = cin / V;
+  const int64_t total = npix * cvn;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = e / cvn;
+    const int c0 = (int)(e - p * cvn) * V;
+    float g[kMaxNarrowOut];
+#pragma unroll
+    for (int c = 0; c < kMaxNarrowOut; ++c) g[c] = c < cout ? Elem<T>::ld(dy + p * cout + c) : 0.f;
+    Vec<T> o;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < kMaxNarrowOut; ++c)
+        if (c < cout) s = fmaf(g[c], wsm[(c0 + i) * cout + c], s);
+      o.v[i] = s;
+    }
+    o.store(dx + e * V);
+  }
+}
+
+template <typename T>
+struct NarrowWgradF {
+  static constexpr int NACC = kMaxNarrowOut;
+  const T* x;
+  const T* dy;
+  int cin, cout;
+  __device__ __forceinline__ void operator()(int64_t row, int c0, float (&acc)[kMaxNarrowOut][Elem<T>::kVec]) const {
+    Vec<T> v;
+    v.load(x + row * cin + c0);
+#pragma unroll
+    for (int c = 0; c < kMaxNarrowOut; ++c) {
+      if (c < cout) {
+        const float g = Elem<T>::ld(dy + row * cout + c);
+#pragma unroll
+        for (int i = 0; i < Vec<T>::N; ++i) acc[c][i] = fmaf(g, v.v[i], acc[c][i]);
+      }
+    }
+  }
+};
+
+__global__ void narrow_wgrad_finish_kernel(const double* __restrict__ acc, float* __restrict__ dw, int cin, int cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cin * cout) dw[i] += (float)acc[i];  // acc is [co][cin] == packed [1][cout][cin]
+}
+
+static bool is_stem(const cvx_conv_desc* d) {
+  return d->cin <= 4 && d->cout == kStemCout && d->kh * d->kw * d->cin <= kStemMaxK;
+}
+static bool is_narrow_out(const cvx_conv_desc* d) {
+  const int vec = d->dtype == CVX_F32 ? 4 : 8;
+  return d->cout <= kMaxNarrowOut && d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0 && d->cin % vec == 0 &&
+         d->cin <= kMaxNarrowCin;
+}
+static NGeom ngeom(const cvx_conv_desc* d) {
+  return NGeom{d->n, d->h, d->w, d->cin, d->cout, d->kh, d->kw, d->stride, d->pad, d->dil, d->ho, d->wo};
+}
+static inline int cap_blocks(int64_t want, int per_sm) {
+  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  return (int)(want > cap ? cap : (want < 1 ? 1 : want));
+}
+
+int narrow_conv_fwd(const cvx_conv_desc* d, const void* x, const void* wp, const float* bias, void* y, cudaStream_t st) {
+  const int64_t npix = (int64_t)d->n * d->ho * d->wo;
+  if (is_stem(d) && bias == nullptr) {
+    const NGeom g = ngeom(d);
+    CVX_DISPATCH_DTYPE(d->dtype, T, (stem_fwd_kernel<T><<<cap_blocks(ceil_div64(npix, 256), 8), 256, 0, st>>>(
+                                        (const T*)x, (const T*)wp, (T*)y, g)));
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
+  if (is_narrow_out(d)) {
+    const size_t smem = sizeof(float) * d->cin * d->cout;
+    CVX_DISPATCH_DTYPE(d->dtype, T, (narrow_out_fwd_kernel<T><<<cap_blocks(ceil_div64(npix, 8), 8), 256, smem, st>>>(
+                                        (const T*)x, (const T*)wp, bias, (T*)y, npix, d->cin, d->cout)));
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
+  return CVX_EUNSUPPORTED;
+}
+
+int narrow_conv_dgrad(const cvx_conv_desc* d, const void* dy, const void* wpt, void* dx, cudaStream_t st) {
+  if (!is_narrow_out(d)) return CVX_EUNSUPPORTED;
+  const int64_t npix = (int64_t)d->n * d->h * d->w;
+  const int vec = d->dtype == CVX_F32 ? 4 : 8;
+  const size_t smem = sizeof(float) * d->cin * d->cout;
+  CVX_DISPATCH_DTYPE(d->dtype, T, (narrow_out_dgrad_kernel<T><<<cap_blocks(ceil_div64(npix * (d->cin / vec), 256), 8), 256, smem, st>>>(
+                                      (const T*)dy, (const T*)wpt, (T*)dx, npix, d->cin, d->cout)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+// scratch for the narrow-out weight gradient lives in a small static device buffer per process
+int narrow_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, float* dwp, cudaStream_t st) {
+  if (is_stem(d)) {
+    const NGeom g = ngeom(d);
+    const int64_t npix = (int64_t)d->n * d->ho * d->wo;
+    CVX_DISPATCH_DTYPE(d->dtype, T, (stem_wgrad_kernel<T><<<cap_blocks(ceil_div64(npix, 64), 4), 288, 0, st>>>(
+                                        (const T*)x, (const T*)dy, dwp, g)));
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
+  if (is_narrow_out(d)) {
+    static double* scratch = nullptr;
+    if (!scratch) CVX_CUDA_OK(cudaMalloc(&scratch, sizeof(double) * kMaxNarrowOut * kMaxNarrowCin));
+    CVX_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * kMaxNarrowOut * d->cin, st));
+    const int64_t rows = (int64_t)d->n * d->ho * d->wo;
+    int rc = CVX_OK;
+    CVX_DISPATCH_DTYPE(d->dtype, T, rc = (colreduce_launch<T, NarrowWgradF<T>, 256, 2>(
+                                        NarrowWgradF<T>{(const T*)x, (const T*)dy, d->cin, d->cout}, rows, d->cin, scratch, st)));
+    if (rc) return rc;
+    narrow_wgrad_finish_kernel<<<(d->cin * d->cout + 255) / 256, 256, 0, st>>>(scratch, dwp, d->cin, d->cout);
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
+  return CVX_EUNSUPPORTED;
+}
+
+}  // namespace cvx

@@ -7,6 +7,7 @@
 //   dgrad   : M = N*H*W   pixels, N = C_in,  K = taps*C_out   (weights packed transposed+flipped)
 //   wgrad   : M = C_out, N = C_in, K = N*Ho*Wo pixels, one GEMM per tap, split over pixels
 #include "common.cuh"
+#include "conv_narrow.cuh"
 
 namespace cvx {
 
@@ -186,27 +187,47 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const T* __restrict__ x
   }
 }
 
-template <typename T>
+// fwd: y[n,oy,ox,:] = x[n,oy*s,ox*s,:]   bwd: dx[n,iy,ix,:] = (iy%s==0 && ix%s==0) ? dy[n,iy/s,ix/s,:] : 0
+// VW = elements moved per thread (a 16-byte vector when the channel count allows, else 1)
+template <typename T, int VW>
 __global__ void subsample_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c, int s,
                                  int ho, int wo, int bwd) {
-  // fwd: y[n,oy,ox,:] = x[n,oy*s,ox*s,:]   bwd: dx[n,iy,ix,:] = (iy%s==0 && ix%s==0) ? dy[n,iy/s,ix/s,:] : 0
-  const int64_t total = bwd ? (int64_t)n * h * w * c : (int64_t)n * ho * wo * c;
+  const int cv = c / VW;
+  const int64_t total = (bwd ? (int64_t)n * h * w : (int64_t)n * ho * wo) * cv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int cc = (int)(i % c);
-    int64_t p = i / c;
+    const int cc = (int)(i % cv) * VW;
+    const int64_t p = i / cv;
+    const T* src = nullptr;
     if (!bwd) {
       const int ox = (int)(p % wo), oy = (int)((p / wo) % ho), nn = (int)(p / ((int64_t)wo * ho));
-      y[i] = x[(((int64_t)nn * h + oy * s) * w + ox * s) * c + cc];
+      src = x + (((int64_t)nn * h + oy * s) * w + ox * s) * c + cc;
     } else {
       const int ix = (int)(p % w), iy = (int)((p / w) % h), nn = (int)(p / ((int64_t)w * h));
+      if (iy % s == 0 && ix % s == 0 && iy / s < ho && ix / s < wo)
+        src = x + (((int64_t)nn * ho + iy / s) * wo + ix / s) * c + cc;
+    }
+    T* dst = y + p * c + cc;
+    if (VW == 1) {
       T v;
       Elem<T>::st(&v, 0.f);
-      if (iy % s == 0 && ix % s == 0 && iy / s < ho && ix / s < wo)
-        v = x[(((int64_t)nn * ho + iy / s) * wo + ix / s) * c + cc];
-      y[i] = v;
+      *dst = src ? *src : v;
+    } else {
+      *reinterpret_cast<uint4*>(dst) = src ? *reinterpret_cast<const uint4*>(src) : make_uint4(0, 0, 0, 0);
     }
   }
+}
+
+template <typename T>
+static void subsample_launch(const T* x, T* y, int n, int h, int w, int c, int s, int ho, int wo, int bwd,
+                             cudaStream_t st) {
+  constexpr int V = Elem<T>::kVec;
+  const bool vec = (c % V == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0);
+  const int64_t total = (bwd ? (int64_t)n * h * w : (int64_t)n * ho * wo) * (vec ? c / V : c);
+  const int64_t b = ceil_div64(total, 256);
+  const int grid = (int)(b > (int64_t)kNumSMs * 16 ? (int64_t)kNumSMs * 16 : (b < 1 ? 1 : b));
+  if (vec) subsample_kernel<T, V><<<grid, 256, 0, st>>>(x, y, n, h, w, c, s, ho, wo, bwd);
+  else subsample_kernel<T, 1><<<grid, 256, 0, st>>>(x, y, n, h, w, c, s, ho, wo, bwd);
 }
 
 static int check_desc(const cvx_conv_desc* d, const char* who) {
@@ -231,6 +252,7 @@ int cvx_conv_fwd(const cvx_conv_desc* d, const void* x, const void* w_packed, co
                  void* stream) {
   if (int rc = check_desc(d, "conv_fwd")) return rc;
   CVX_CHECK_ARG(x && w_packed && y, "conv_fwd: null pointer");
+  if (int rc = narrow_conv_fwd(d, x, w_packed, bias, y, as_stream(stream)); rc != CVX_EUNSUPPORTED) return rc;
   const ConvGeom g = geom_of(d);
   const int64_t M = (int64_t)g.n * g.ho * g.wo;
   dim3 grid((unsigned)ceil_div64(M, BM), (g.cout + BN - 1) / BN);
@@ -243,6 +265,7 @@ int cvx_conv_fwd(const cvx_conv_desc* d, const void* x, const void* w_packed, co
 int cvx_conv_dgrad(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream) {
   if (int rc = check_desc(d, "conv_dgrad")) return rc;
   CVX_CHECK_ARG(dy && w_packed_t && dx, "conv_dgrad: null pointer");
+  if (int rc = narrow_conv_dgrad(d, dy, w_packed_t, dx, as_stream(stream)); rc != CVX_EUNSUPPORTED) return rc;
   const ConvGeom g = geom_of(d);
   const int64_t M = (int64_t)g.n * g.h * g.w;
   dim3 grid((unsigned)ceil_div64(M, BM), (g.cin + BN - 1) / BN);
@@ -255,6 +278,7 @@ int cvx_conv_dgrad(const cvx_conv_desc* d, const void* dy, const void* w_packed_
 int cvx_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream) {
   if (int rc = check_desc(d, "conv_wgrad")) return rc;
   CVX_CHECK_ARG(x && dy && dw_packed, "conv_wgrad: null pointer");
+  if (int rc = narrow_conv_wgrad(d, x, dy, dw_packed, as_stream(stream)); rc != CVX_EUNSUPPORTED) return rc;
   const ConvGeom g = geom_of(d);
   const int64_t M = (int64_t)g.n * g.ho * g.wo;
   const int taps = g.kh * g.kw;
@@ -274,9 +298,7 @@ int cvx_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, float*
 int cvx_subsample(const void* x, void* y, int n, int h, int w, int c, int s, int dtype, void* stream) {
   CVX_CHECK_ARG(x && y && n > 0 && h > 0 && w > 0 && c > 0 && s > 0, "subsample: bad arguments");
   const int ho = (h - 1) / s + 1, wo = (w - 1) / s + 1;
-  const int64_t total = (int64_t)n * ho * wo * c;
-  int grid = (int)(ceil_div64(total, 256) > kNumSMs * 16 ? kNumSMs * 16 : ceil_div64(total, 256));
-  CVX_DISPATCH_DTYPE(dtype, T, (subsample_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, n, h, w, c, s, ho, wo, 0)));
+  CVX_DISPATCH_DTYPE(dtype, T, (subsample_launch<T>((const T*)x, (T*)y, n, h, w, c, s, ho, wo, 0, as_stream(stream))));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -284,9 +306,7 @@ int cvx_subsample(const void* x, void* y, int n, int h, int w, int c, int s, int
 int cvx_subsample_bwd(const void* dy, void* dx, int n, int h, int w, int c, int s, int dtype, void* stream) {
   CVX_CHECK_ARG(dy && dx && n > 0 && h > 0 && w > 0 && c > 0 && s > 0, "subsample_bwd: bad arguments");
   const int ho = (h - 1) / s + 1, wo = (w - 1) / s + 1;
-  const int64_t total = (int64_t)n * h * w * c;
-  int grid = (int)(ceil_div64(total, 256) > kNumSMs * 16 ? kNumSMs * 16 : ceil_div64(total, 256));
-  CVX_DISPATCH_DTYPE(dtype, T, (subsample_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)dy, (T*)dx, n, h, w, c, s, ho, wo, 1)));
+  CVX_DISPATCH_DTYPE(dtype, T, (subsample_launch<T>((const T*)dy, (T*)dx, n, h, w, c, s, ho, wo, 1, as_stream(stream))));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

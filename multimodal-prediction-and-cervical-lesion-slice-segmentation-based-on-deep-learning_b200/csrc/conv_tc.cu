@@ -14,62 +14,13 @@
 // Two CTAs are co-resident per SM (3 x 32 KB stages each) so one CTA's epilogue overlaps the
 // other's main loop.
 #include <cuda.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "tma_utils.cuh"
 
 namespace cvx {
 
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline bug must not hang the (shared) GPU - trap after ~seconds instead.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("cervix_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
+// ------------------------------------------------------------------------------ PTX wrappers (tcgen05)
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
 }
@@ -266,6 +217,165 @@ __global__ void __launch_bounds__(128) conv_tc_fwd_kernel(const __grid_constant_
   if (warp == 2) tmem_dealloc(tmem_base, BN);
 }
 
+
+// ------------------------------------------------------------------------------ fwd / dgrad, persistent
+// One CTA per SM loops over output tiles (n-tile fastest, so the CTAs that run concurrently share
+// the same activation tile through L2).  Warp roles: 0 = TMA producer, 1 = TMEM owner + MMA issuer,
+// 2..5 = epilogue.  The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of
+// tile i overlaps the main loop of tile i+1, and the per-CTA prologue (barrier init, TMEM alloc,
+// descriptor fetch, pipeline fill) is paid once per launch instead of once per tile.  BN = 256
+// halves the shared-memory traffic per MMA relative to BN = 128 (A is re-read once per 256 columns).
+constexpr int kPStages = 4;
+constexpr int kPBN = 256;
+constexpr int kPBBytes = kPBN * 128;
+constexpr int kPStageBytes = kABytes + kPBBytes;
+
+
+__global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x,
+                                                                        const __grid_constant__ CUtensorMap tmap_w,
+                                                                        const float* __restrict__ bias,
+                                                                        __nv_bfloat16* __restrict__ y, TcFwdParams p,
+                                                                        int n_tiles, int total_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kPStages * kPStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPStages + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kPStages;
+  const uint32_t tfull0 = empty0 + 8 * kPStages, tempty0 = tfull0 + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kcb = (p.cin + 63) / 64;
+  const int num_kb = p.kh * p.kw * kcb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < kPStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 2 * kPBN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        int mt = tile / n_tiles;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int img = mt / p.tiles_y;
+        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * kPBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages;
+          mbar_wait(empty0 + 8 * s, ((it / kPStages) & 1) ^ 1);
+          const int tap = kb / kcb, cb = kb - tap * kcb;
+          const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+          const uint32_t sa = smem_base + s * kPStageBytes;
+          mbar_expect_tx(full0 + 8 * s, kPStageBytes);
+          tma_load_4d(sa, &tmap_x, full0 + 8 * s, cb * 64, ox0 - p.pad + kwi * p.dil, oy0 - p.pad + khi * p.dil, img);
+          tma_load_3d(sa + kABytes, &tmap_w, full0 + 8 * s, cb * 64, n0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        const int nt = tile % n_tiles;
+        const int n0 = nt * kPBN;
+        int n_eff = p.cout - n0;
+        n_eff = n_eff > kPBN ? kPBN : ((n_eff + 15) & ~15);
+        const uint32_t idesc = make_idesc(128, n_eff, 0, 0);
+        const int acc = tcount & 1;
+        mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kPBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % kPStages;
+          mbar_wait(full0 + 8 * s, (it / kPStages) & 1);
+          tc_fence_after();
+          const int cb = kb % kcb;
+          const int crem = p.cin - cb * 64;
+          const int ksteps = crem >= 64 ? 4 : (crem + 15) / 16;
+          const uint32_t sa = smem_base + s * kPStageBytes;
+          const uint32_t sb = sa + kABytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int lg = warp & 3;  // TMEM lane group this warp may access
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % n_tiles;
+      int mt = tile / n_tiles;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int n0 = nt * kPBN;
+      const int row = lg * 32 + lane;
+      const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
+      const bool row_ok = oy < p.ho && ox < p.wo;
+      __nv_bfloat16* yrow = y + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
+      const int acc = tcount & 1;
+      mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kPBN; c0 += 32) {
+        if (n0 + c0 >= p.cout) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = c0 + g * 8;
+            if (n0 + c < p.cout) {
+              uint32_t packed[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
+                if (bias) { v0 += __ldg(bias + n0 + c + 2 * j); v1 += __ldg(bias + n0 + c + 2 * j + 1); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                packed[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(yrow + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * kPBN);
+}
+
 // ------------------------------------------------------------------------------ wgrad
 constexpr int kWStages = 4;
 constexpr int kWBox = 64 * 128;  // 64 pixels x 64 bf16 channels
@@ -391,37 +501,6 @@ __global__ void __launch_bounds__(128) conv_tc_wgrad_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
-// NHWC bf16 activation [n][h][w][c] with a (64, bw, bh, 1) box
-static int make_act_map(CUtensorMap* m, const void* base, int n, int h, int w, int c, int bw, int bh) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return CVX_ECUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d box %dx%d) failed: %d", n, h, w, c, bw, bh, (int)r); return CVX_ECUDA; }
-  return CVX_OK;
-}
-
 // packed weights [taps][rows][k] bf16 with a (64, bn, 1) box
 static int make_weight_map(CUtensorMap* m, const void* base, int taps, int rows, int k, int bn) {
   EncodeTiledFn fn = get_encode_fn();
@@ -486,6 +565,24 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
   pick_tile(ho, wo, 128, &p.bw, &p.bh);
   p.tiles_x = (wo + p.bw - 1) / p.bw;
   p.tiles_y = (ho + p.bh - 1) / p.bh;
+  static const bool use_v1 = getenv("CERVIX_TC_V1") != nullptr;
+  if (!use_v1) {
+    CUtensorMap mx, mw;
+    if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
+    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, kPBN)) return rc;
+    constexpr int smem = kPStages * kPStageBytes + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    const int n_tiles = (ncol + kPBN - 1) / kPBN;
+    const int total = n * p.tiles_y * p.tiles_x * n_tiles;
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    conv_tc_fwd_persistent_kernel<<<grid, 192, smem, st>>>(mx, mw, bias, (__nv_bfloat16*)dst, p, n_tiles, total);
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
   const int bn = ncol <= 64 ? 64 : 128;
   CUtensorMap mx, mw;
   if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;

@@ -116,6 +116,20 @@ def test_depthwise(B, dtype, c, stride, dil, relu_in):
     check(B.dw_bwd_weight(x, dy, g, relu_in), EMU.dw_bwd_weight(x, dy, g, relu_in), 1e-3, "bwd_weight")
 
 
+@pytest.mark.parametrize("n,h,w,c", [(4, 128, 128, 64), (3, 40, 70, 136), (2, 32, 32, 728)])
+def test_depthwise_tiled_pipeline(B, n, h, w, c):
+    """bf16 stride-1 path (TMA-staged tiles): many tiles per CTA, ragged image and channel tails."""
+    dtype = torch.bfloat16
+    g = ConvGeom(n, h, w, c, c, 3, 3, 1, 1, 1)
+    x = rnd((n, h, w, c), dtype, 1)
+    w9c = B.pack_dw_weight(rnd((c, 1, 3, 3), torch.float32, 2, 0.3))
+    dy = rnd((n, h, w, c), dtype, 3)
+    for relu_in in (True, False):
+        check(B.dw_fwd(x, w9c, g, relu_in), EMU.dw_fwd(x, w9c, g, relu_in), tol(dtype), "fwd")
+        check(B.dw_bwd_data(dy, w9c, x, g, relu_in), EMU.dw_bwd_data(dy, w9c, x, g, relu_in), tol(dtype), "bwd_data")
+        check(B.dw_bwd_weight(x, dy, g, relu_in), EMU.dw_bwd_weight(x, dy, g, relu_in), 2e-3, "bwd_weight")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("c,act,res", [(64, 0, False), (728, 1, True), (48, 2, False), (2048, 1, False), (304, 0, True)])
