@@ -238,20 +238,32 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     losses = [float(v) for v in res.cpu()]
 
-    # ---- end to end: pinned host batch -> device every step, loss read back every step ---------
-    for _ in range(2):
-        trainer.step(imgs_h.cuda(non_blocking=True), pngs_h.cuda(non_blocking=True), labels_h.cuda(non_blocking=True)).cpu()
+    # ---- end to end: every step's batch comes from pinned HOST memory (imgs fp32 + int64 class map,
+    # the one-hot labels are derived on the device), prefetched one step ahead on a copy stream;
+    # the 4 loss/metric scalars are read back to the host every step.
+    from cervix_b200.engine import BatchPrefetcher
+
+    def host_batches(k):
+        for _ in range(k):
+            yield (imgs_h, pngs_h)
+
+    for bi, bp in BatchPrefetcher(host_batches(2)):
+        trainer.step(bi, bp, None).cpu()
     sync_all()
-    t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e2.record()
-    for _ in range(args.steps):
-        r = trainer.step(imgs_h.cuda(non_blocking=True), pngs_h.cuda(non_blocking=True),
-                         labels_h.cuda(non_blocking=True))
-        r.cpu()
+    pf = BatchPrefetcher(host_batches(args.steps))   # first copy is inside the timed region
+    prev = None
+    for bi, bp in pf:
+        r = trainer.step(bi, bp, None)
+        if prev is not None:
+            prev.cpu()                                # result of the previous step (keeps 1 step in flight)
+        prev = r
+    prev.cpu()
     e3.record()
     sync_all()
-    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3 * 0.0)
+    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -273,7 +285,7 @@ def run_ours(args):
         cpu_ips, cpu_steps, cores, cpu_sec = cpu_train_throughput(3, 1, budget_s=45.0)
         cpu_baseline = {"value": cpu_ips, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d timed steps of the oracle port's train step, batch 2 at 512x512 (%.1f s/step)" % (cpu_steps, cpu_sec)}
-    h2d = imgs_h.numel() * 4 + pngs_h.numel() * 8 + labels_h.numel() * 4
+    h2d = imgs_h.numel() * 4 + pngs_h.numel() * 8
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -93,6 +93,10 @@ CVX_API int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w
                     void* y, void* stream);
 CVX_API int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
 CVX_API int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
+/* im2col of a narrow-channel input (C_in <= 4): patches[n,ho,wo,kpad], k = tap*C_in + ci, zero padded
+ * to kpad (a multiple of 8).  Turns the ResNet-101 7x7/2 stem of the classifier's patch encoder
+ * (MM/Graph_Structure(data_augmentation).py:136) into a 1x1 tensor-core GEMM. */
+CVX_API int cvx_im2col_narrow(const cvx_conv_desc* d, const void* x, void* patches, int kpad, void* stream);
 /* spatial subsample x[:, ::s, ::s, :] and its scatter-back (1x1 stride-2 skip convs,
  * xception.py:44) */
 CVX_API int cvx_subsample(const void* x, void* y, int n, int h, int w, int c, int s, int dtype, void* stream);
@@ -136,6 +140,11 @@ CVX_API int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, in
 /* final upsample fused with the NHWC->NCHW fp32 conversion (deeplabv3_plus.py:187) */
 CVX_API int cvx_upsample_to_nchw_fwd(const void* x, float* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
 CVX_API int cvx_upsample_to_nchw_bwd(const float* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
+/* nn.MaxPool2d(3, stride 2, padding 1) of the torchvision ResNet-101 patch encoder
+ * (MM/Graph_Structure(data_augmentation).py:136); the gradient goes to the first maximum. */
+CVX_API int cvx_maxpool3x3s2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream);
+CVX_API int cvx_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int c,
+                         int dtype, void* stream);
 /* nn.Dropout: mask byte per element, y = x * mask / (1-p) (deeplabv3_plus.py:159,165) */
 CVX_API int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, int dtype, void* stream);
 CVX_API int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream);

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "cvx_conv_fwd_tc": [_D, _P, _P, _P, _P, _P],
     "cvx_conv_dgrad_tc": [_D, _P, _P, _P, _P],
     "cvx_conv_wgrad_tc": [_D, _P, _P, _P, _P],
+    "cvx_im2col_narrow": [_D, _P, _P, _I, _P],
     "cvx_subsample": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cvx_subsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cvx_dwconv_fwd": [_D, _P, _P, _P, _I, _P],
@@ -61,6 +62,8 @@ PROTOTYPES = {
     "cvx_upsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cvx_upsample_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cvx_upsample_to_nchw_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_maxpool3x3s2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "cvx_maxpool3x3s2_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cvx_dropout_fwd": [_P, _P, _P, _L, _F, C.c_uint64, _I, _P],
     "cvx_dropout_bwd": [_P, _P, _P, _L, _F, _I, _P],
     "cvx_seg_loss_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],

@@ -190,6 +190,28 @@ class CudaBackend:
         check(self.lib.cvx_subsample_bwd(_p(dy), _p(dx), n, h, w, c, s, _dt(dy), self._stream()), "cvx_subsample_bwd")
         return dx
 
+    def im2col_narrow(self, x, g: ConvGeom, kpad: int) -> torch.Tensor:
+        self._chk(x)
+        y = torch.empty((g.n, g.ho, g.wo, kpad), dtype=x.dtype, device=x.device)
+        d = g.desc(_dt(x))
+        check(self.lib.cvx_im2col_narrow(C.byref(d), _p(x), _p(y), kpad, self._stream()), "cvx_im2col_narrow")
+        return y
+
+    def maxpool_fwd(self, x) -> torch.Tensor:
+        self._chk(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, (h - 1) // 2 + 1, (w - 1) // 2 + 1, c), dtype=x.dtype, device=x.device)
+        check(self.lib.cvx_maxpool3x3s2_fwd(_p(x), _p(y), n, h, w, c, _dt(x), self._stream()), "cvx_maxpool3x3s2_fwd")
+        return y
+
+    def maxpool_bwd(self, x, y, dy) -> torch.Tensor:
+        self._chk(x, y, dy)
+        n, h, w, c = x.shape
+        dx = torch.empty_like(x)
+        check(self.lib.cvx_maxpool3x3s2_bwd(_p(x), _p(y), _p(dy), _p(dx), n, h, w, c, _dt(x), self._stream()),
+              "cvx_maxpool3x3s2_bwd")
+        return dx
+
     # ------------------------------------------------------------------ depthwise
     def dw_fwd(self, x, w9c, g: ConvGeom, relu_in: bool) -> torch.Tensor:
         self._chk(x, w9c)

@@ -217,6 +217,37 @@ __global__ void narrow_wgrad_finish_kernel(const double* __restrict__ acc, float
   if (i < cin * cout) dw[i] += (float)acc[i];  // acc is [co][cin] == packed [1][cout][cin]
 }
 
+// ---------------------------------------------------------------- narrow in: im2col for large filters
+// patches[p][k], k = tap*cin + ci (zero beyond taps*cin up to kpad): turns the 7x7 stride-2 3->64
+// ResNet stem (Graph_Structure(data_augmentation).py:136, torchvision resnet101.conv1) into a 1x1
+// tensor-core GEMM with K = kpad.
+template <typename T>
+__global__ void im2col_narrow_kernel(const T* __restrict__ x, T* __restrict__ y, NGeom g, int kpad) {
+  constexpr int V = Elem<T>::kVec;
+  const int kv = kpad / V;
+  const int K = g.kh * g.kw * g.cin;
+  const int64_t total = (int64_t)g.n * g.ho * g.wo * kv;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int k0 = (int)(e % kv) * V;
+    const int64_t p = e / kv;
+    const int ox = (int)(p % g.wo), oy = (int)((p / g.wo) % g.ho), nn = (int)(p / ((int64_t)g.wo * g.ho));
+    Vec<T> o;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int k = k0 + i;
+      float v = 0.f;
+      if (k < K) {
+        const int tap = k / g.cin, ci = k - tap * g.cin;
+        const int iy = oy * g.stride - g.pad + (tap / g.kw) * g.dil;
+        const int ix = ox * g.stride - g.pad + (tap % g.kw) * g.dil;
+        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) v = Elem<T>::ld(x + (((size_t)nn * g.h + iy) * g.w + ix) * g.cin + ci);
+      }
+      o.v[i] = v;
+    }
+    o.store(y + e * V);
+  }
+}
+
 static bool is_stem(const cvx_conv_desc* d) {
   return d->cin <= 4 && d->cout == kStemCout && d->kh * d->kw * d->cin <= kStemMaxK;
 }
@@ -290,3 +321,16 @@ int narrow_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, flo
 }
 
 }  // namespace cvx
+
+extern "C" int cvx_im2col_narrow(const cvx_conv_desc* d, const void* x, void* patches, int kpad, void* stream) {
+  using namespace cvx;
+  CVX_CHECK_ARG(d && x && patches, "im2col_narrow: null pointer");
+  const int vec = d->dtype == CVX_F32 ? 4 : 8;
+  CVX_CHECK_ARG(d->cin <= 4 && kpad % vec == 0 && kpad >= d->kh * d->kw * d->cin, "im2col_narrow: bad geometry");
+  const NGeom g = ngeom(d);
+  const int64_t total = (int64_t)d->n * d->ho * d->wo * (kpad / vec);
+  CVX_DISPATCH_DTYPE(d->dtype, T, (im2col_narrow_kernel<T><<<cap_blocks(ceil_div64(total, 256), 16), 256, 0, as_stream(stream)>>>(
+                                      (const T*)x, (T*)patches, g, kpad)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}

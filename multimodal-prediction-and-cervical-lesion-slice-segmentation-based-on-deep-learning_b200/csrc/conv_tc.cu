@@ -93,9 +93,10 @@ constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16
 struct TcFwdParams {
   int n, ho, wo, cout;       // output geometry (rows of the GEMM)
   int cin;                   // reduction channels
-  int kh, kw, pad, dil;      // taps; input coordinate = out - pad + k*dil  (stride 1)
+  int kh, kw, pad, dil;      // taps; input coordinate = out*stride - pad + k*dil
   int bw, bh;                // pixel tile (bw*bh == 128)
   int tiles_x, tiles_y;
+  int stride;                // 1, or 2 (persistent forward kernel only: TMA element strides)
 };
 
 template <int BN>
@@ -287,7 +288,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
           const int khi = tap / p.kw, kwi = tap - khi * p.kw;
           const uint32_t sa = smem_base + s * kPStageBytes;
           mbar_expect_tx(full0 + 8 * s, kPStageBytes);
-          tma_load_4d(sa, &tmap_x, full0 + 8 * s, cb * 64, ox0 - p.pad + kwi * p.dil, oy0 - p.pad + khi * p.dil, img);
+          tma_load_4d(sa, &tmap_x, full0 + 8 * s, cb * 64, ox0 * p.stride - p.pad + kwi * p.dil,
+                      oy0 * p.stride - p.pad + khi * p.dil, img);
           tma_load_3d(sa + kABytes, &tmap_w, full0 + 8 * s, cb * 64, n0, tap);
         }
       }
@@ -376,6 +378,235 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
   if (warp == 1) tmem_dealloc(tmem_base, 2 * kPBN);
 }
 
+
+// ------------------------------------------------------------------------------ fwd / dgrad, CTA pair (cta_group::2)
+// Two CTAs of a cluster (same TPC) form one 256-pixel x 256-channel tile: each CTA stages its own
+// 128 pixels of A and HALF of the weight tile (128 rows), and the leader issues
+// tcgen05.mma.cta_group::2 (M = 256).  Per SM and per MMA the shared-memory traffic is half of the
+// single-CTA kernel's (A: 4 KB + B: 4 KB per 128x256x16 half-MMA), which lifts the smem-bandwidth
+// ceiling that bounds the 1-CTA kernel at ~70 % of the tensor peak, and every weight tile is
+// fetched from L2 once per pair instead of once per CTA.
+constexpr int k2Stages = 6;
+constexpr int k2BBytes = 128 * 128;                 // half of a 256-row weight tile
+constexpr int k2StageBytes = kABytes + k2BBytes;    // 32 KB
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default (.release.cta) semantics on purpose: a .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR
+  // on every call, which serialised the peer's producer loop (seen in the ncu source view)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit -> arrive on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(bar), "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, TcFwdParams p, int n_tiles,
+                        int m_tiles, int total_pair_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * k2Stages + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * k2Stages;
+  const uint32_t tfull0 = empty0 + 8 * k2Stages, tempty0 = tfull0 + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int kcb = (p.cin + 63) / 64;
+  const int num_kb = p.kh * p.kw * kcb;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(full0 + 8 * s, 2);   // leader's expect_tx arrival + the peer producer's arrival
+      mbar_init(empty0 + 8 * s, 1);  // leader's multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one used)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), 2 * kPBN);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pt = pair; pt < total_pair_tiles; pt += npairs) {
+        const int nt = pt % n_tiles;
+        const int mtile = 2 * (pt / n_tiles) + (int)rank;
+        int tx = 0, ty = 0, img = p.n;  // img == n -> every TMA coordinate is out of bounds (zero fill)
+        if (mtile < m_tiles) {
+          int mt = mtile;
+          tx = mt % p.tiles_x; mt /= p.tiles_x;
+          ty = mt % p.tiles_y;
+          img = mt / p.tiles_y;
+        }
+        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * kPBN;
+        int n_eff = p.cout - n0;
+        n_eff = n_eff > kPBN ? kPBN : ((n_eff + 15) & ~15);
+        const int brow0 = n0 + (int)rank * (n_eff >> 1);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % k2Stages;
+          mbar_wait(empty0 + 8 * s, ((it / k2Stages) & 1) ^ 1);
+          const int tap = kb / kcb, cb = kb - tap * kcb;
+          const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+          const uint32_t sa = smem_base + s * k2StageBytes;
+          const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;  // the leader CTA's barrier (peer bit cleared)
+          if (leader) mbar_expect_tx(full0 + 8 * s, 2 * k2StageBytes);
+          else mbar_arrive_cluster(map_to_cta(full0 + 8 * s, 0));
+          tma_load_4d_2sm(sa, &tmap_x, lead_full, cb * 64, ox0 - p.pad + kwi * p.dil, oy0 - p.pad + khi * p.dil, img);
+          tma_load_3d_2sm(sa + kABytes, &tmap_w, lead_full, cb * 64, brow0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      uint32_t it = 0, tcount = 0;
+      for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
+        const int nt = pt % n_tiles;
+        const int n0 = nt * kPBN;
+        int n_eff = p.cout - n0;
+        n_eff = n_eff > kPBN ? kPBN : ((n_eff + 15) & ~15);
+        const uint32_t idesc = make_idesc(256, n_eff, 0, 0);
+        const int acc = tcount & 1;
+        mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kPBN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % k2Stages;
+          mbar_wait(full0 + 8 * s, (it / k2Stages) & 1);
+          tc_fence_after();
+          const int cb = kb % kcb;
+          const int crem = p.cin - cb * 64;
+          const int ksteps = crem >= 64 ? 4 : (crem + 15) / 16;
+          const uint32_t sa = smem_base + s * k2StageBytes;
+          const uint32_t sb = sa + kABytes;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(empty0 + 8 * s);
+        }
+        umma_commit_2sm(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const uint32_t lead_tempty0 = map_to_cta(tempty0, 0);
+    uint32_t tcount = 0;
+    for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
+      const int nt = pt % n_tiles;
+      const int mtile = 2 * (pt / n_tiles) + (int)rank;
+      const bool tile_ok = mtile < m_tiles;
+      int mt = tile_ok ? mtile : 0;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int n0 = nt * kPBN;
+      const int row = lg * 32 + lane;
+      const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
+      const bool row_ok = tile_ok && oy < p.ho && ox < p.wo;
+      __nv_bfloat16* yrow = y + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
+      const int acc = tcount & 1;
+      mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < kPBN; c0 += 32) {
+        if (n0 + c0 >= p.cout) break;
+        uint32_t r[32];
+        tmem_ld32(t_addr + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = c0 + g * 8;
+            if (n0 + c < p.cout) {
+              uint32_t packed[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
+                if (bias) { v0 += __ldg(bias + n0 + c + 2 * j); v1 += __ldg(bias + n0 + c + 2 * j + 1); }
+                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+                packed[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(yrow + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 2 * kPBN);
+}
+
 // ------------------------------------------------------------------------------ wgrad
 constexpr int kWStages = 4;
 constexpr int kWBox = 64 * 128;  // 64 pixels x 64 bf16 channels
@@ -404,7 +635,8 @@ __global__ void __launch_bounds__(128) conv_tc_wgrad_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.x * 128, ci0 = blockIdx.y * BN;
-  const int tap = blockIdx.z / p.splits, split = blockIdx.z - tap * p.splits;
+  const int taps = p.kh * p.kw;
+  const int split = blockIdx.z / taps, tap = blockIdx.z - split * taps;  // split slowest: taps of a split share X/dY in L2
   const int khi = tap / p.kw, kwi = tap - khi * p.kw;
   const int ptiles = p.n * p.tiles_y * p.tiles_x;
   const int per = (ptiles + p.splits - 1) / p.splits;
@@ -500,6 +732,175 @@ __global__ void __launch_bounds__(128) conv_tc_wgrad_kernel(const __grid_constan
   if (warp == 2) tmem_dealloc(tmem_base, BN);
 }
 
+
+// ------------------------------------------------------------------------------ wgrad, persistent (BN = 256)
+// Work item = (128 output channels) x (256 input channels) x tap x pixel split.  Items are ordered
+// with the pixel split slowest, so the CTAs that run at the same time read the same slice of dY / X
+// and share it through L2; a CTA loops over items with a double-buffered TMEM accumulator so the
+// red.global.add epilogue of one item overlaps the main loop of the next.  N = 256 halves the
+// shared-memory operand traffic per MMA relative to the 128 x 128 kernel.
+constexpr int kWPStages = 4;
+constexpr int kWPABytes = 2 * kWBox;              // 128 co
+constexpr int kWPBBytes = 4 * kWBox;              // 256 ci
+constexpr int kWPStageBytes = kWPABytes + kWPBBytes;  // 48 KB per 64 pixels
+
+struct TcWgradPParams {
+  int n, ho, wo, cout, cin;
+  int kh, kw, pad, dil;
+  int bw, bh, tiles_x, tiles_y;
+  int co_tiles, ci_tiles, splits, total_items;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy,
+                                                                          const __grid_constant__ CUtensorMap tmap_x,
+                                                                          float* __restrict__ dw, TcWgradPParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWPStages * kWPStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWPStages + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kWPStages;
+  const uint32_t tfull0 = empty0 + 8 * kWPStages, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int taps = p.kh * p.kw;
+  const int ptiles = p.n * p.tiles_y * p.tiles_x;
+  const int per = (ptiles + p.splits - 1) / p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < kWPStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (co tile fastest, ci tile, tap, split slowest)
+  auto decode = [&](int item, int& cot, int& cit, int& tap, int& t_begin, int& t_end) {
+    cot = item % p.co_tiles; item /= p.co_tiles;
+    cit = item % p.ci_tiles; item /= p.ci_tiles;
+    tap = item % taps;
+    const int split = item / taps;
+    t_begin = split * per;
+    t_end = min(t_begin + per, ptiles);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int cot, cit, tap, t_begin, t_end;
+        decode(item, cot, cit, tap, t_begin, t_end);
+        const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+        const int co0 = cot * 128, ci0 = cit * 256;
+        int ci_boxes = (p.cin - ci0 + 63) / 64;
+        ci_boxes = ci_boxes > 4 ? 4 : ci_boxes;
+        for (int t = t_begin; t < t_end; ++t, ++it) {
+          const int s = it % kWPStages;
+          mbar_wait(empty0 + 8 * s, ((it / kWPStages) & 1) ^ 1);
+          int tt = t;
+          const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+          const int ty = tt % p.tiles_y;
+          const int img = tt / p.tiles_y;
+          const int ox0 = tx * p.bw, oy0 = ty * p.bh;
+          const uint32_t sa = smem_base + s * kWPStageBytes;
+          mbar_expect_tx(full0 + 8 * s, kWPABytes + ci_boxes * kWBox);
+          tma_load_4d(sa, &tmap_dy, full0 + 8 * s, co0, ox0, oy0, img);
+          tma_load_4d(sa + kWBox, &tmap_dy, full0 + 8 * s, co0 + 64, ox0, oy0, img);
+          for (int j = 0; j < ci_boxes; ++j)
+            tma_load_4d(sa + kWPABytes + j * kWBox, &tmap_x, full0 + 8 * s, ci0 + j * 64, ox0 - p.pad + kwi * p.dil,
+                        oy0 - p.pad + khi * p.dil, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, icount = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++icount) {
+        int cot, cit, tap, t_begin, t_end;
+        decode(item, cot, cit, tap, t_begin, t_end);
+        const int ci0 = cit * 256;
+        int ci_boxes = (p.cin - ci0 + 63) / 64;
+        ci_boxes = ci_boxes > 4 ? 4 : ci_boxes;
+        const uint32_t idesc = make_idesc(128, ci_boxes * 64, 1, 1);  // both operands MN-major
+        const int acc = icount & 1;
+        mbar_wait(tempty0 + 8 * acc, ((icount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int t = t_begin; t < t_end; ++t, ++it) {
+          const int s = it % kWPStages;
+          mbar_wait(full0 + 8 * s, (it / kWPStages) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * kWPStageBytes;
+          const uint32_t sb = sa + kWPABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * 2048, kWBox, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * 2048, kWBox, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (t > t_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);
+        }
+        umma_commit(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    uint32_t icount = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++icount) {
+      int cot, cit, tap, t_begin, t_end;
+      decode(item, cot, cit, tap, t_begin, t_end);
+      const int ci0 = cit * 256;
+      const int co = cot * 128 + lg * 32 + lane;
+      const int acc = icount & 1;
+      mbar_wait(tfull0 + 8 * acc, (icount >> 1) & 1);
+      tc_fence_after();
+      if (t_end > t_begin) {
+        float* drow = dw + ((size_t)tap * p.cout + co) * p.cin + ci0;
+        const uint32_t t_addr = tmem_base + acc * 256 + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          if (ci0 + c0 >= p.cin) break;
+          uint32_t r[32];
+          tmem_ld32(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (co < p.cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (ci0 + c0 + j < p.cin)  // cin % 8 == 0: whole groups of 4 are in or out
+                red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                           __uint_as_float(r[j + 3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------ host side
 // packed weights [taps][rows][k] bf16 with a (64, bn, 1) box
 static int make_weight_map(CUtensorMap* m, const void* base, int taps, int rows, int k, int bn) {
@@ -529,15 +930,16 @@ static void pick_tile(int ho, int wo, int pixels, int* bw, int* bh) {
   *bh = pixels / best_bw;
 }
 
-static int tc_supported(const cvx_conv_desc* d, const char* who) {
+static int tc_supported(const cvx_conv_desc* d, const char* who, bool allow_stride2 = false) {
   CVX_CHECK_ARG(d != nullptr, "%s: null descriptor", who);
-  if (d->dtype != CVX_BF16 || d->stride != 1 || d->cin % 8 != 0 || d->cout % 8 != 0) {
+  const bool stride_ok = d->stride == 1 || (allow_stride2 && d->stride == 2);
+  if (d->dtype != CVX_BF16 || !stride_ok || d->cin % 8 != 0 || d->cout % 8 != 0) {
     set_error("%s: tensor-core path needs bf16, stride 1, C_in %% 8 == 0 and C_out %% 8 == 0 (got dtype=%d stride=%d cin=%d cout=%d)",
               who, d->dtype, d->stride, d->cin, d->cout);
     return CVX_EUNSUPPORTED;
   }
-  const int ho = d->h + 2 * d->pad - d->dil * (d->kh - 1);
-  const int wo = d->w + 2 * d->pad - d->dil * (d->kw - 1);
+  const int ho = (d->h + 2 * d->pad - d->dil * (d->kh - 1) - 1) / d->stride + 1;
+  const int wo = (d->w + 2 * d->pad - d->dil * (d->kw - 1) - 1) / d->stride + 1;
   CVX_CHECK_ARG(ho == d->ho && wo == d->wo && ho > 0 && wo > 0, "%s: inconsistent output size", who);
   return CVX_OK;
 }
@@ -559,16 +961,39 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const float*
 
 // rows = output pixels [n,ho,wo] ; src = [n,hs,ws,cred] ; wp = [taps][ncol][cred]
 static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, int kh, int kw, int pad, int dil,
-                     const void* src, const void* wp, const float* bias, void* dst, cudaStream_t st) {
+                     const void* src, const void* wp, const float* bias, void* dst, cudaStream_t st, int stride = 1) {
   TcFwdParams p;
   p.n = n; p.ho = ho; p.wo = wo; p.cout = ncol; p.cin = cred; p.kh = kh; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.stride = stride;
   pick_tile(ho, wo, 128, &p.bw, &p.bh);
   p.tiles_x = (wo + p.bw - 1) / p.bw;
   p.tiles_y = (ho + p.bh - 1) / p.bh;
   static const bool use_v1 = getenv("CERVIX_TC_V1") != nullptr;
-  if (!use_v1) {
+  static const bool use_2cta = getenv("CERVIX_TC_1CTA") == nullptr;  // CTA-pair kernel by default
+  if (stride != 1) {
+    CVX_CHECK_ARG(stride == 2 && p.bw * 2 <= 256 && p.bh * 2 <= 256 && !use_v1, "conv_tc: unsupported stride %d", stride);
+  }
+  if (use_2cta && stride == 1) {
     CUtensorMap mx, mw;
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
+    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, 128)) return rc;
+    constexpr int smem = k2Stages * k2StageBytes + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    const int n_tiles = (ncol + kPBN - 1) / kPBN;
+    const int m_tiles = n * p.tiles_y * p.tiles_x;
+    const int total = ((m_tiles + 1) / 2) * n_tiles;
+    const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
+    conv_tc_fwd_2cta_kernel<<<2 * pairs, 192, smem, st>>>(mx, mw, bias, (__nv_bfloat16*)dst, p, n_tiles, m_tiles, total);
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
+  if (!use_v1) {
+    CUtensorMap mx, mw;
+    if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh, CU_TENSOR_MAP_SWIZZLE_128B, stride)) return rc;
     if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, kPBN)) return rc;
     constexpr int smem = kPStages * kPStageBytes + 1024 + 256;
     static bool configured = false;
@@ -613,10 +1038,10 @@ extern "C" {
 
 int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
                     void* stream) {
-  if (int rc = tc_supported(d, "conv_fwd_tc")) return rc;
+  if (int rc = tc_supported(d, "conv_fwd_tc", true)) return rc;
   CVX_CHECK_ARG(x && w_packed && y, "conv_fwd_tc: null pointer");
   return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, bias, y,
-                   as_stream(stream));
+                   as_stream(stream), d->stride);
 }
 
 int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream) {
@@ -633,6 +1058,37 @@ int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_pack
 int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream) {
   if (int rc = tc_supported(d, "conv_wgrad_tc")) return rc;
   CVX_CHECK_ARG(x && dy && dw_packed, "conv_wgrad_tc: null pointer");
+  static const bool wgrad_v1 = getenv("CERVIX_TC_WGRAD_V1") != nullptr;
+  if (!wgrad_v1) {
+    TcWgradPParams q;
+    q.n = d->n; q.ho = d->ho; q.wo = d->wo; q.cout = d->cout; q.cin = d->cin;
+    q.kh = d->kh; q.kw = d->kw; q.pad = d->pad; q.dil = d->dil;
+    pick_tile(d->ho, d->wo, 64, &q.bw, &q.bh);
+    q.tiles_x = (d->wo + q.bw - 1) / q.bw;
+    q.tiles_y = (d->ho + q.bh - 1) / q.bh;
+    q.co_tiles = (d->cout + 127) / 128;
+    q.ci_tiles = (d->cin + 255) / 256;
+    const int ptiles = q.n * q.tiles_y * q.tiles_x;
+    const int out_tiles = q.co_tiles * q.ci_tiles * d->kh * d->kw;
+    int splits = (2 * kNumSMs + out_tiles - 1) / out_tiles;
+    if (splits > ptiles / 8) splits = ptiles / 8;  // keep >= 8 pixel tiles (512 pixels) per item
+    if (splits < 1) splits = 1;
+    q.splits = splits;
+    q.total_items = out_tiles * splits;
+    CUtensorMap mdy, mx;
+    if (int rc = make_act_map(&mdy, dy, d->n, d->ho, d->wo, d->cout, q.bw, q.bh)) return rc;
+    if (int rc = make_act_map(&mx, x, d->n, d->h, d->w, d->cin, q.bw, q.bh)) return rc;
+    constexpr int smem = kWPStages * kWPStageBytes + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = true;
+    }
+    const int grid = q.total_items < kNumSMs ? q.total_items : kNumSMs;
+    conv_tc_wgrad_persistent_kernel<<<grid, 192, smem, as_stream(stream)>>>(mdy, mx, dw_packed, q);
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
   TcWgradParams p;
   p.n = d->n; p.ho = d->ho; p.wo = d->wo; p.cout = d->cout; p.cin = d->cin;
   p.kh = d->kh; p.kw = d->kw; p.pad = d->pad; p.dil = d->dil;

@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(128, 4) dw_stream_kernel(const T* __restrict__
 
   const int rows_h = MODE == 0 ? g.ho : g.h, rows_w = MODE == 0 ? g.wo : g.w;
   const int src_h = MODE == 0 ? g.h : g.ho, src_w = MODE == 0 ? g.w : g.wo;
+  const int sshift = g.stride == 2 ? 1 : 0, smask = g.stride - 1;  // stride is 1 or 2 (checked on the host)
   const int npix = g.n * rows_h * rows_w;  // < 2^31 (checked by the launcher)
   const int pstep = (int)(stride_items / cvn);
   for (int p = (int)(e0 / cvn); p < npix; p += pstep) {
@@ -70,8 +71,8 @@ __global__ void __launch_bounds__(128, 4) dw_stream_kernel(const T* __restrict__
         oky = sy >= 0 && sy < src_h;
       } else {
         const int ny = py + g.pad - kh * g.dil;
-        oky = ny >= 0 && (ny % g.stride == 0);
-        sy = ny / g.stride;
+        oky = ny >= 0 && ((ny & smask) == 0);
+        sy = ny >> sshift;
         oky = oky && sy < src_h;
       }
 #pragma unroll
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(128, 4) dw_stream_kernel(const T* __restrict__
           okx = sx >= 0 && sx < src_w;
         } else {
           const int nx = px + g.pad - kw * g.dil;
-          okx = nx >= 0 && (nx % g.stride == 0);
-          sx = nx / g.stride;
+          okx = nx >= 0 && ((nx & smask) == 0);
+          sx = nx >> sshift;
           okx = okx && sx < src_w;
         }
         const int t = kh * 3 + kw;
@@ -297,6 +298,7 @@ static int dw_check(const cvx_conv_desc* d, const char* who, DwGeom* g) {
   const int ho = (d->h + 2 * d->pad - d->dil * 2 - 1) / d->stride + 1;
   const int wo = (d->w + 2 * d->pad - d->dil * 2 - 1) / d->stride + 1;
   CVX_CHECK_ARG(ho == d->ho && wo == d->wo, "%s: inconsistent output size", who);
+  CVX_CHECK_ARG(d->stride == 1 || d->stride == 2, "%s: stride must be 1 or 2", who);
   const int vec = d->dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(d->cin % vec == 0, "%s: C=%d not a multiple of %d", who, d->cin, vec);
   *g = DwGeom{d->n, d->h, d->w, d->cin, d->stride, d->pad, d->dil, d->ho, d->wo};

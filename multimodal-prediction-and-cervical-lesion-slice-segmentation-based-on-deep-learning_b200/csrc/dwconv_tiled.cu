@@ -168,10 +168,16 @@ __global__ void __launch_bounds__(128, MODE == 2 ? 2 : 3) dw_tiled_kernel(const 
     float* red = reinterpret_cast<float*>(smem);  // [9][64]
     for (int i = t; i < 9 * 64; i += 128) red[i] = 0.f;
     __syncthreads();
+    // lanes l, l^8, l^16, l^24 of a warp share the channel vector: fold them first
 #pragma unroll
     for (int k = 0; k < 9; ++k)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&red[k * 64 + cv * 8 + e], wreg[k][e]);
+      for (int e = 0; e < 8; ++e) {
+        float v = wreg[k][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if ((t & 31) < 8) atomicAdd(&red[k * 64 + cv * 8 + e], v);
+      }
     __syncthreads();
     for (int i = t; i < 9 * 64; i += 128) {
       const int k = i / 64, cc = cchunk * 64 + (i % 64);
@@ -194,7 +200,7 @@ int dw_tiled_launch(int mode, const cvx_conv_desc* d, const void* src, const flo
   CUtensorMap map;
   if (int rc = make_act_map(&map, src, d->n, d->h, d->w, d->cin, kTX + 2, kTY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   const int chunks = (d->cin + 63) / 64;
-  int gx = (kNumSMs * 3 + chunks - 1) / chunks;
+  int gx = (kNumSMs * (mode == 2 ? 2 : 3) + chunks - 1) / chunks;
   if (gx > p.ntiles) gx = p.ntiles;
   dim3 grid(gx, chunks);
   constexpr int smem = kDwStages * kTileBytes + 128 + 64;

@@ -225,6 +225,91 @@ __global__ void upsample_to_nchw_bwd_kernel(const float* __restrict__ dy, T* __r
   }
 }
 
+// ---- max pooling 3x3 stride 2 pad 1 (torchvision ResNet stem) ----------------------------
+template <typename T>
+__global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c, int ho,
+                                        int wo) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int cvn = c / VEC;
+  const int64_t total = (int64_t)n * ho * wo * cvn;
+  CVX_GRID_STRIDE(e, total) {
+    const int c0 = (int)(e % cvn) * VEC;
+    int64_t p = e / cvn;
+    const int ox = (int)(p % wo), oy = (int)((p / wo) % ho), nn = (int)(p / ((int64_t)wo * ho));
+    float m[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) m[i] = -INFINITY;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = oy * 2 - 1 + kh;
+      if (iy < 0 || iy >= h) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix = ox * 2 - 1 + kw;
+        if (ix < 0 || ix >= w) continue;
+        Vec<T> v;
+        v.load(x + (((size_t)nn * h + iy) * w + ix) * c + c0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) m[i] = fmaxf(m[i], v.v[i]);
+      }
+    }
+    Vec<T> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = m[i];
+    o.store(y + e * VEC);
+  }
+}
+
+// gradient goes to the FIRST maximal element of each window (ATen's tie rule, row-major scan)
+template <typename T>
+__global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ dy,
+                                        T* __restrict__ dx, int n, int h, int w, int c, int ho, int wo) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int cvn = c / VEC;
+  const int64_t total = (int64_t)n * h * w * cvn;
+  CVX_GRID_STRIDE(e, total) {
+    const int c0 = (int)(e % cvn) * VEC;
+    int64_t p = e / cvn;
+    const int ix = (int)(p % w), iy = (int)((p / w) % h), nn = (int)(p / ((int64_t)w * h));
+    Vec<T> xv;
+    xv.load(x + e * VEC);
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    for (int oy = (iy + 1) / 2 - 1; oy <= (iy + 1) / 2; ++oy) {
+      if (oy < 0 || oy >= ho || iy < oy * 2 - 1 || iy > oy * 2 + 1) continue;
+      for (int ox = (ix + 1) / 2 - 1; ox <= (ix + 1) / 2; ++ox) {
+        if (ox < 0 || ox >= wo || ix < ox * 2 - 1 || ix > ox * 2 + 1) continue;
+        const size_t o = (((size_t)nn * ho + oy) * wo + ox) * c + c0;
+        Vec<T> yv, gv;
+        yv.load(y + o);
+        gv.load(dy + o);
+        // is (iy,ix) the first position of this window that attains the max?
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          if (xv.v[i] != yv.v[i]) continue;
+          bool first = true;
+          for (int kh = 0; kh < 3 && first; ++kh) {
+            const int yy = oy * 2 - 1 + kh;
+            if (yy < 0 || yy >= h) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+              const int xx = ox * 2 - 1 + kw;
+              if (xx < 0 || xx >= w) continue;
+              if (yy == iy && xx == ix) { kh = 3; break; }
+              if (Elem<T>::ld(x + (((size_t)nn * h + yy) * w + xx) * c + c0 + i) == yv.v[i]) { first = false; break; }
+            }
+          }
+          if (first) acc[i] += gv.v[i];
+        }
+      }
+    }
+    Vec<T> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
+    o.store(dx + e * VEC);
+  }
+}
+
 // ---- dropout -------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mix64(uint64_t z) {
   z += 0x9e3779b97f4a7c15ull;
@@ -345,6 +430,31 @@ int cvx_upsample_to_nchw_bwd(const float* dy, void* dx, int n, int hi, int wi, i
   const int64_t total = (int64_t)n * hi * wi * c;
   CVX_DISPATCH_DTYPE(dtype, T, (upsample_to_nchw_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
                                    dy, (T*)dx, n, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_maxpool3x3s2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream) {
+  CVX_CHECK_ARG(x && y && n > 0 && h > 0 && w > 0 && c > 0, "maxpool_fwd: bad arguments");
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  CVX_CHECK_ARG(c % vec == 0, "maxpool_fwd: C=%d not a multiple of %d", c, vec);
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)n * ho * wo * (c / vec);
+  CVX_DISPATCH_DTYPE(dtype, T, (maxpool3x3s2_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (T*)y, n, h, w, c, ho, wo)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int c, int dtype,
+                         void* stream) {
+  CVX_CHECK_ARG(x && y && dy && dx && n > 0 && h > 0 && w > 0 && c > 0, "maxpool_bwd: bad arguments");
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  CVX_CHECK_ARG(c % vec == 0, "maxpool_bwd: C=%d not a multiple of %d", c, vec);
+  const int ho = (h + 2 - 3) / 2 + 1, wo = (w + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)n * h * w * (c / vec);
+  CVX_DISPATCH_DTYPE(dtype, T, (maxpool3x3s2_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (const T*)y, (const T*)dy, (T*)dx, n, h, w, c, ho, wo)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -14,6 +14,7 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .backend import get_backend
 from .nets.deeplabv3_training import seg_objective
 
@@ -58,6 +59,8 @@ class SegTrainer:
         self.t = 0
         self.world = world_size
         self.last = None
+        self._nbt = [m.num_batches_tracked for m in model.modules()
+                     if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
         if world_size > 1:
             self._setup_buckets(bucket_mb)
 
@@ -122,7 +125,10 @@ class SegTrainer:
         (ce, focal, dice, f_score) as a device tensor (no host sync)."""
         B = get_backend()
         self.flat.grad.zero_()
-        out = self.model(imgs)
+        with ops.defer_batch_counters():
+            out = self.model(imgs)
+        if self.model.training and self._nbt:
+            torch._foreach_add_(self._nbt, 1)
         ce, focal, dice, fs = seg_objective(out, pngs, labels, self.cls_weights, self.num_classes)
         loss = (focal if self.focal else ce) + (dice if self.dice else 0.0)
         loss.backward()
@@ -139,3 +145,39 @@ class SegTrainer:
                        gscale)
         self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
         return self.last
+
+
+class BatchPrefetcher:
+    """Moves pinned host batches to the device one step ahead on a side stream, so the
+    host->device copy of step i+1 overlaps the compute of step i (replaces the synchronous
+    ``imgs.cuda(local_rank)`` calls of utils/utils_fit.py:52-58)."""
+
+    def __init__(self, batches, device=None):
+        self.it = iter(batches)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.stream = torch.cuda.Stream(self.device)
+        self.next = None
+        self._fetch()
+
+    def _fetch(self):
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self.next = None
+            return
+        with torch.cuda.stream(self.stream):
+            self.next = tuple(None if t is None else t.to(self.device, non_blocking=True) for t in host)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.next is None:
+            raise StopIteration
+        torch.cuda.current_stream().wait_stream(self.stream)
+        cur = self.next
+        for t in cur:
+            if t is not None:
+                t.record_stream(torch.cuda.current_stream())
+        self._fetch()
+        return cur

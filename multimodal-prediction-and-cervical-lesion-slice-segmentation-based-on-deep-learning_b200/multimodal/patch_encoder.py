@@ -1,0 +1,122 @@
+"""ResNet-101 patch encoder of the classifier's image branches on the B200 NHWC engine.
+
+Reference: ``MultiModal Prediction/Graph_Structure(data_augmentation).py`` :136-168 -
+``models.resnet101(pretrained=True)`` with ``fc = Linear(2048, 1024)``, ``eval()``, applied to 16
+patches (256x256, cut x-major from the image resized to 1024x1024) of each modality, one patch per
+call.  Here the same network (identical ``state_dict`` keys/shapes as torchvision's ``resnet101``, so
+ImageNet checkpoints load unchanged) runs all patches of all modalities as ONE batch through the
+tcgen05 implicit-GEMM convolutions; BatchNorm uses its running statistics (the reference never
+trains or un-freezes this network).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)   # torchvision v1.5: stride on the 3x3
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        identity = x
+        if self.downsample is not None:
+            d = self.downsample[0]
+            identity = ops.conv2d(x, d.weight, None, d.stride[0], 0, 1)
+            identity = ops.batchnorm_act(identity, self.downsample[1], ops.ACT_NONE)
+        y = ops.conv2d(x, self.conv1.weight, None, 1, 0, 1)
+        y = ops.batchnorm_act(y, self.bn1, ops.ACT_RELU)
+        y = ops.conv2d(y, self.conv2.weight, None, self.conv2.stride[0], 1, 1)
+        y = ops.batchnorm_act(y, self.bn2, ops.ACT_RELU)
+        y = ops.conv2d(y, self.conv3.weight, None, 1, 0, 1)
+        return ops.batchnorm_act(y, self.bn3, ops.ACT_RELU, identity)   # relu(bn3(.) + identity)
+
+
+class ResNet101Encoder(nn.Module):
+    """torchvision ``resnet101`` with ``fc -> Linear(2048, out_features)``; NCHW fp32 in, [N, out] fp32 out."""
+
+    def __init__(self, out_features: int = 1024, layers=(3, 4, 23, 3)):
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.layer1 = self._make_layer(64, layers[0], 1)
+        self.layer2 = self._make_layer(128, layers[1], 2)
+        self.layer3 = self._make_layer(256, layers[2], 2)
+        self.layer4 = self._make_layer(512, layers[3], 2)
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(2048, out_features)
+        self._cervix_dtype = torch.bfloat16
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def _make_layer(self, planes, blocks, stride):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * 4:
+            downsample = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride, bias=False),
+                                       nn.BatchNorm2d(planes * 4))
+        layers = [Bottleneck(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * 4
+        layers += [Bottleneck(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def set_compute_dtype(self, dtype: torch.dtype):
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("compute dtype must be float32 or bfloat16")
+        self._cervix_dtype = dtype
+        return self
+
+    def forward(self, x):
+        x = ops.to_nhwc(x, self._cervix_dtype)
+        c1 = self.conv1
+        x = ops.conv2d_narrow_in(x, c1.weight, c1.stride[0], c1.padding[0])
+        x = ops.batchnorm_act(x, self.bn1, ops.ACT_RELU)
+        x = ops.maxpool3x3s2(x)
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                x = blk(x)
+        x = ops.global_avg_pool(x)                                        # [N,1,1,2048]
+        w = self.fc.weight.reshape(self.fc.out_features, self.fc.in_features, 1, 1)
+        y = ops.conv2d(x.float() if self._cervix_dtype == torch.float32 else x, w, self.fc.bias, 1, 0, 1)
+        return y.reshape(y.shape[0], -1).float()
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def split_patches(images: torch.Tensor, new_size: int = 1024, patch_size: int = 256) -> torch.Tensor:
+    """Tensor form of ``resize_and_split_image`` (:151-161) + the ImageNet normalisation (:145-148):
+    [B,3,H,W] in [0,1] -> [B*16, 3, 256, 256], patches enumerated x-major (outer loop over columns)."""
+    x = torch.nn.functional.interpolate(images, size=(new_size, new_size), mode="bilinear", align_corners=False)
+    mean = torch.tensor(IMAGENET_MEAN, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, device=x.device).view(1, 3, 1, 1)
+    x = (x - mean) / std
+    k = new_size // patch_size
+    b = x.shape[0]
+    x = x.reshape(b, 3, k, patch_size, k, patch_size)          # [b, c, iy, py, ix, px]
+    x = x.permute(0, 4, 2, 1, 3, 5)                             # [b, ix, iy, c, py, px]  (x-major patch order)
+    return x.reshape(b * k * k, 3, patch_size, patch_size).contiguous()
+
+
+@torch.no_grad()
+def extract_features(patches: torch.Tensor, model: ResNet101Encoder) -> torch.Tensor:
+    """``extract_features`` (:164-168) for a whole batch of patches at once: [P,3,256,256] -> [P,1024]."""
+    model.eval()
+    return model(patches)

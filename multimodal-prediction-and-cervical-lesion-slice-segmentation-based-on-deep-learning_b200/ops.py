@@ -62,17 +62,18 @@ class Conv2d(Function):
         assert cin_w == cin, "conv: channel mismatch %d vs %d" % (cin_w, cin)
         tc = _tc_ok(x, cin, cout)
         sub = 1
-        if tc and stride != 1:
-            if kh == 1 and kw == 1 and pad == 0:
-                # 1x1 stride-s conv == 1x1 stride-1 conv of the subsampled input
-                x = B.subsample(x, stride)
-                sub, stride = stride, 1
-                n, h2, w2, _ = x.shape
-            else:
-                tc = False
-        g = ConvGeom(n, x.shape[1], x.shape[2], cin, cout, kh, kw, stride, pad, dil)
+        if tc and stride != 1 and kh == 1 and kw == 1 and pad == 0:
+            # 1x1 stride-s conv == 1x1 stride-1 conv of the subsampled input
+            x = B.subsample(x, stride)
+            sub, stride = stride, 1
+        g = ConvGeom(x.shape[0], x.shape[1], x.shape[2], cin, cout, kh, kw, stride, pad, dil)
+        # strided kxk convs: the tensor-core forward takes stride 2 (TMA element strides); their
+        # gradients use the generic kernels
+        tc_fwd = tc and stride in (1, 2)
+        tc_bwd = tc and stride == 1
         wp = B.pack_weight(weight.detach(), x.dtype, False)
-        y = B.conv_fwd(x, wp, None if bias is None else bias.detach(), g, tc)
+        y = B.conv_fwd(x, wp, None if bias is None else bias.detach(), g, tc_fwd)
+        tc = tc_bwd
         ctx.save_for_backward(x, weight)
         ctx.g, ctx.tc, ctx.sub, ctx.in_hw, ctx.has_bias = g, tc, sub, (h, w), bias is not None
         return y
@@ -95,6 +96,42 @@ class Conv2d(Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = B.bias_grad(dy)
         return dx, dw, db, None, None, None
+
+
+class MaxPool3x3S2(Function):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = get_backend().maxpool_fwd(x)
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        return get_backend().maxpool_bwd(x, y, dy.contiguous())
+
+
+def conv2d_narrow_in(x, weight, stride, pad):
+    """Inference-only dense conv for C_in <= 4 and a large filter (the 7x7/2 ResNet stem): im2col into a
+    K-padded patch tensor, then a 1x1 conv on the tensor cores.  Falls back to ``conv2d`` when a gradient
+    is needed or the engine runs in fp32."""
+    cout, cin, kh, kw = weight.shape
+    if (torch.is_grad_enabled() and (weight.requires_grad or x.requires_grad)) or not _tc_ok(x, 8, cout):
+        return conv2d(x, weight, None, stride, pad, 1)
+    B = get_backend()
+    x = x.contiguous()
+    n, h, w, _ = x.shape
+    g = ConvGeom(n, h, w, cin, cout, kh, kw, stride, pad, 1)
+    k = kh * kw * cin
+    kpad = (k + 7) // 8 * 8
+    patches = B.im2col_narrow(x, g, kpad)
+    # [cout, cin, kh, kw] -> [cout, (tap, ci)] zero-padded to kpad, as a 1x1 filter
+    w2 = weight.detach().permute(0, 2, 3, 1).reshape(cout, k)
+    w2 = torch.nn.functional.pad(w2, (0, kpad - k)).reshape(cout, kpad, 1, 1).contiguous()
+    return conv2d(patches, w2, None, 1, 0, 1)
 
 
 class DepthwiseConv3x3(Function):
@@ -306,10 +343,24 @@ def dwconv3x3(x, weight, stride=1, pad=1, dil=1, relu_in=False):
     return DepthwiseConv3x3.apply(x, weight, stride, pad, dil, relu_in)
 
 
+# When a trainer owns the step it bumps every ``num_batches_tracked`` with ONE foreach launch
+# (engine.SegTrainer) instead of 141 one-element kernels; see defer_batch_counters().
+_DEFER_NBT = [False]
+
+
+class defer_batch_counters:
+    def __enter__(self):
+        self.prev = _DEFER_NBT[0]
+        _DEFER_NBT[0] = True
+
+    def __exit__(self, *exc):
+        _DEFER_NBT[0] = self.prev
+
+
 def batchnorm_act(x, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None):
     """Apply an ``nn.BatchNorm2d`` parameter holder to an NHWC tensor (never calls bn.forward)."""
     training = bn.training or (bn.running_mean is None)
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None and not _DEFER_NBT[0]:
         bn.num_batches_tracked.add_(1)
     momentum = 0.0 if bn.momentum is None else bn.momentum
     return BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training, momentum,
@@ -318,6 +369,10 @@ def batchnorm_act(x, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None):
 
 def relu(x):
     return ReLU.apply(x)
+
+
+def maxpool3x3s2(x):
+    return MaxPool3x3S2.apply(x)
 
 
 def cat_channels(xs):

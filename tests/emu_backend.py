@@ -91,6 +91,21 @@ class EmuBackend:
         dx[:, ::s, ::s, :] = dy
         return dx
 
+    def im2col_narrow(self, x, g, kpad):
+        cols = F.unfold(_nchw(x), (g.kh, g.kw), dilation=g.dil, padding=g.pad, stride=g.stride)  # [n, cin*taps, L]
+        n = x.shape[0]
+        cols = cols.reshape(n, g.cin, g.kh * g.kw, g.ho, g.wo).permute(0, 3, 4, 2, 1).reshape(n, g.ho, g.wo, -1)
+        return F.pad(cols, (0, kpad - cols.shape[-1])).contiguous().to(x.dtype)
+
+    def maxpool_fwd(self, x):
+        return _nhwc(F.max_pool2d(_nchw(x), 3, 2, 1), x.dtype)
+
+    def maxpool_bwd(self, x, y, dy):
+        with torch.enable_grad():
+            xi = _nchw(x).detach().requires_grad_(True)
+            F.max_pool2d(xi, 3, 2, 1).backward(_nchw(dy))
+        return _nhwc(xi.grad, x.dtype)
+
     # ---- depthwise
     @staticmethod
     def _dw_w(w9c):

@@ -186,6 +186,18 @@ def test_small_ops(B, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+def test_maxpool_and_im2col(B, dtype):
+    x = rnd((2, 13, 18, 64), dtype, 1)
+    y = B.maxpool_fwd(x)
+    check(y, EMU.maxpool_fwd(x), 0, "maxpool fwd")
+    dy = rnd(tuple(y.shape), dtype, 2)
+    check(B.maxpool_bwd(x, y, dy), EMU.maxpool_bwd(x, y, dy), 1e-6 if dtype == torch.float32 else 8e-3, "maxpool bwd")
+    img = rnd((2, 21, 30, 3), dtype, 3)
+    g = ConvGeom(2, 21, 30, 3, 64, 7, 7, 2, 3, 1)
+    check(B.im2col_narrow(img, g, 152), EMU.im2col_narrow(img, g, 152), 0, "im2col")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_dropout(B, dtype):
     x = rnd((4, 32, 32, 64), dtype, 1) + 3
     y, mask = B.dropout_fwd(x, 0.5, 1234)

@@ -1,0 +1,74 @@
+"""ResNet-101 patch encoder (classifier image branches) against torchvision's
+resnet101 - the architecture the reference instantiates - on identical random weights and inputs.
+CPU: host graph on the emulation backend.  GPU: the CUDA engine in fp32 (1e-3) and bf16 (cosine)."""
+import pytest
+import torch
+import torchvision
+
+import cervix_b200.backend as backend
+from cervix_b200.multimodal.patch_encoder import ResNet101Encoder, extract_features, split_patches
+from tests.emu_backend import EmuBackend
+
+
+def _pair(seed=0):
+    torch.manual_seed(seed)
+    ref = torchvision.models.resnet101(weights=None)
+    ref.fc = torch.nn.Linear(2048, 1024)
+    for m in ref.modules():   # non-trivial running statistics, damped residual branches (keeps activations O(1))
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.3, 0.6); m.bias.data.normal_(0, 0.05)
+    ref.eval()
+    enc = ResNet101Encoder()
+    assert list(enc.state_dict().keys()) == list(ref.state_dict().keys())
+    enc.load_state_dict(ref.state_dict(), strict=True)
+    return ref, enc.eval()
+
+
+def test_cpu_host_graph_matches_torchvision():
+    prev = backend.set_backend(EmuBackend())
+    try:
+        ref, enc = _pair()
+        enc.set_compute_dtype(torch.float32)
+        x = torch.rand(2, 3, 64, 96)
+        with torch.no_grad():
+            a, b = enc(x), ref(x)
+        assert float((a - b).abs().max()) < 1e-4 * float(b.abs().max())
+    finally:
+        backend.set_backend(prev)
+
+
+def test_split_patches_order_and_normalisation():
+    img = torch.rand(1, 3, 1024, 1024)
+    p = split_patches(img)
+    assert p.shape == (16, 3, 256, 256)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1); std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    # reference loop order: for i in x-blocks: for j in y-blocks -> patch index = i*4 + j
+    for i, j in ((0, 0), (1, 0), (0, 3), (2, 1)):
+        want = (img[0, :, j * 256:(j + 1) * 256, i * 256:(i + 1) * 256] - mean) / std
+        assert torch.allclose(p[i * 4 + j], want, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_gpu_fp32_matches_torchvision():
+    ref, enc = _pair(1)
+    enc.set_compute_dtype(torch.float32).cuda()
+    x = split_patches(torch.rand(1, 3, 300, 280))[:6]
+    with torch.no_grad():
+        b = ref(x)
+        a = extract_features(x.cuda(), enc).cpu()
+    assert a.shape == (6, 1024)
+    assert float((a - b).abs().max()) < 1e-3 * float(b.abs().max())
+
+
+@pytest.mark.gpu
+def test_gpu_bf16_tracks_torchvision():
+    ref, enc = _pair(2)
+    enc.set_compute_dtype(torch.bfloat16).cuda()
+    x = split_patches(torch.rand(1, 3, 256, 256))
+    with torch.no_grad():
+        b = ref(x)
+        a = extract_features(x.cuda(), enc).cpu()
+    cos = torch.nn.functional.cosine_similarity(a, b, dim=1)
+    assert float(cos.min()) > 0.995, float(cos.min())
+    assert float((a - b).abs().max()) < 0.08 * float(b.abs().max())

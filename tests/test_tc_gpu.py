@@ -18,13 +18,13 @@ def test_tc_conv_case(idx):
     torch.backends.cudnn.allow_tf32 = False
     kind, n, h, w, cin, cout, k, pad, dil, bias = CASES[idx]
     B = get_backend()
-    g = ConvGeom(n, h, w, cin, cout, k, k, 1, pad, dil)
+    g = ConvGeom(n, h, w, cin, cout, k, k, 2 if kind == "fwd_s2" else 1, pad, dil)
     gen = torch.Generator(device="cuda").manual_seed(idx)
     x = torch.randn((n, h, w, cin), generator=gen, device="cuda").bfloat16()
     wt = torch.randn((cout, cin, k, k), generator=gen, device="cuda") * (2.0 / (cin * k * k)) ** 0.5
     b = torch.randn((cout,), generator=gen, device="cuda") if bias else None
     dy = torch.randn((n, g.ho, g.wo, cout), generator=gen, device="cuda").bfloat16()
-    if kind == "fwd":
+    if kind in ("fwd", "fwd_s2"):
         wp = B.pack_weight(wt, torch.bfloat16, False)
         got, ref, tol = B.conv_fwd(x, wp, b, g, True), EMU.conv_fwd(x, wp, b, g, False), 1.2e-2
     elif kind == "dgrad":

@@ -22,6 +22,8 @@ CASES = [
     ("fwd", 2, 24, 40, 304, 256, 3, 1, 1, True),
     ("fwd", 2, 32, 32, 256, 48, 1, 0, 1, True),
     ("fwd", 3, 6, 6, 2048, 256, 3, 12, 12, True),
+    ("fwd_s2", 2, 32, 32, 128, 128, 3, 1, 1, False),
+    ("fwd_s2", 3, 28, 20, 256, 256, 3, 1, 1, True),
     ("dgrad", 2, 16, 16, 64, 128, 1, 0, 1, False),
     ("dgrad", 2, 32, 32, 728, 728, 1, 0, 1, False),
     ("dgrad", 1, 32, 32, 128, 256, 3, 6, 6, False),
@@ -55,13 +57,13 @@ def run_one(idx):
     torch.backends.cuda.matmul.allow_tf32 = False
     kind, n, h, w, cin, cout, k, pad, dil, bias = CASES[idx]
     B, E = get_backend(), EmuBackend()
-    g = ConvGeom(n, h, w, cin, cout, k, k, 1, pad, dil)
+    g = ConvGeom(n, h, w, cin, cout, k, k, 2 if kind == "fwd_s2" else 1, pad, dil)
     gen = torch.Generator(device="cuda").manual_seed(idx)
     x = torch.randn((n, h, w, cin), generator=gen, device="cuda").bfloat16()
     wt = torch.randn((cout, cin, k, k), generator=gen, device="cuda") * (2.0 / (cin * k * k)) ** 0.5
     b = torch.randn((cout,), generator=gen, device="cuda") if bias else None
     dy = torch.randn((n, g.ho, g.wo, cout), generator=gen, device="cuda").bfloat16()
-    if kind == "fwd":
+    if kind in ("fwd", "fwd_s2"):
         wp = B.pack_weight(wt, torch.bfloat16, False)
         got, ref = B.conv_fwd(x, wp, b, g, True), E.conv_fwd(x, wp, b, g, False)
         simt = B.conv_fwd(x, wp, b, g, False)
@@ -99,7 +101,12 @@ def main():
         ok = run_one(int(sys.argv[sys.argv.index("--one") + 1]))
         sys.exit(0 if ok else 1)
     fails = 0
+    only = None
+    if "--kinds" in sys.argv:
+        only = sys.argv[sys.argv.index("--kinds") + 1].split(",")
     for i in range(len(CASES)):
+        if only and CASES[i][0] not in only:
+            continue
         try:
             p = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", str(i)], capture_output=True,
                                text=True, timeout=180)
