@@ -219,9 +219,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_graph = world == 1 and not args.no_graph
+    if use_graph:
+        trainer.capture(imgs, pngs, None)
+        step_fn = lambda a, b, c=None: trainer.step_graphed(a, b)   # noqa: E731
+    else:
+        step_fn = lambda a, b, c=None: trainer.step(a, b, c)        # noqa: E731
+
     # ---- device-resident throughput ------------------------------------------------------
     for _ in range(args.warmup):
-        trainer.step(imgs, pngs, labels)
+        step_fn(imgs, pngs, labels)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -230,10 +237,14 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        res = trainer.step(imgs, pngs, labels)
+        res = step_fn(imgs, pngs, labels)
     e1.record()
     sync_all()
     launches = B.lib.cvx_launch_count() - launches0
+    if use_graph:   # replays do not pass through the library's launch counter: count one eager step instead
+        c0 = B.lib.cvx_launch_count()
+        trainer.step(imgs, pngs, None)
+        launches = (B.lib.cvx_launch_count() - c0) * args.steps
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     losses = [float(v) for v in res.cpu()]
@@ -248,7 +259,7 @@ def run_ours(args):
             yield (imgs_h, pngs_h)
 
     for bi, bp in BatchPrefetcher(host_batches(2)):
-        trainer.step(bi, bp, None).cpu()
+        step_fn(bi, bp, None).cpu()
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -256,7 +267,9 @@ def run_ours(args):
     pf = BatchPrefetcher(host_batches(args.steps))   # first copy is inside the timed region
     prev = None
     for bi, bp in pf:
-        r = trainer.step(bi, bp, None)
+        r = step_fn(bi, bp, None)
+        if use_graph:
+            r = r.clone()                             # the graph's output buffer is overwritten by the next replay
         if prev is not None:
             prev.cpu()                                # result of the previous step (keeps 1 step in flight)
         prev = r
@@ -293,6 +306,7 @@ def run_ours(args):
         "config": {"workload": "DeepLabv3+ Xception ds=16 bf16 training (fwd + focal+dice + bwd + Adam), "
                                "batch %d per GPU at %dx%d, 5 classes (BASELINE configs[2]/[3])" % (bsz, size, size),
                    "global_batch": world * bsz, "per_gpu_batch": bsz, "parallelism": "dp%d" % world,
+                   "cuda_graph": bool(use_graph),
                    "l2": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2"},
         "roofline": roof,
         "step_tensor": {"achieved_tflops_per_gpu": step_tf, "peak": peaks["tf_sustained"],
@@ -319,6 +333,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the single-GPU step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -114,7 +114,7 @@ CVX_API int cvx_dwconv_bwd_weight(const cvx_conv_desc* d, const void* x, const v
 /* ---- BatchNorm2d (+ residual add + activation) -------------------------------------- */
 /* y = act(bn(x) + residual).  training=1: batch statistics, running buffers updated with
  * `momentum` (unbiased variance), save_mean/save_invstd written for backward.
- * training=0: running statistics.  ws: 2*C doubles of scratch. */
+ * training=0: running statistics.  ws: 2*C + 2 doubles of scratch (sums + grid-barrier counter). */
 CVX_API int cvx_bn_forward(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                    double* ws, int64_t rows, int c, int dtype, int act, int training,
@@ -146,7 +146,9 @@ CVX_API int cvx_maxpool3x3s2_fwd(const void* x, void* y, int n, int h, int w, in
 CVX_API int cvx_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int c,
                          int dtype, void* stream);
 /* nn.Dropout: mask byte per element, y = x * mask / (1-p) (deeplabv3_plus.py:159,165) */
-CVX_API int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, int dtype, void* stream);
+/* step_dev (nullable device int): mixed into the seed so that a CUDA-graph replay draws a new mask every step */
+CVX_API int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, const int* step_dev,
+                    int dtype, void* stream);
 CVX_API int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream);
 
 /* ---- segmentation objective (nets/deeplabv3_training.py:9-56, utils/utils_metrics.py:13-35) */
@@ -171,6 +173,10 @@ CVX_API int cvx_seg_loss_grad(const float* logits, const int64_t* target, const 
  * step_t is the 1-based step count; grad_scale multiplies the gradient first. */
 CVX_API int cvx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int step_t, float grad_scale, void* stream);
+/* same update with hyper = device float[6] {lr, beta1, beta2, eps, weight_decay, grad_scale} and the 1-based step
+ * count in device memory: safe to capture in a CUDA graph and replay */
+CVX_API int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, const int* step,
+                      void* stream);
 /* torch.optim.SGD(momentum, nesterov) semantics */
 CVX_API int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);

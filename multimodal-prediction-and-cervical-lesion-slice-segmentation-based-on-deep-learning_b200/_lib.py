@@ -64,12 +64,13 @@ PROTOTYPES = {
     "cvx_upsample_to_nchw_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cvx_maxpool3x3s2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "cvx_maxpool3x3s2_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "cvx_dropout_fwd": [_P, _P, _P, _L, _F, C.c_uint64, _I, _P],
+    "cvx_dropout_fwd": [_P, _P, _P, _L, _F, C.c_uint64, _P, _I, _P],
     "cvx_dropout_bwd": [_P, _P, _P, _L, _F, _I, _P],
     "cvx_seg_loss_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
     "cvx_seg_loss_finalize": [_P, _P, _I, _F, _F, _P],
     "cvx_seg_loss_grad": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P],
     "cvx_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "cvx_adam_step_dev": [_P, _P, _P, _P, _L, _P, _P, _P],
     "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],
 }
 _RESTYPES = {"cvx_last_error": C.c_char_p, "cvx_launch_count": C.c_int64}

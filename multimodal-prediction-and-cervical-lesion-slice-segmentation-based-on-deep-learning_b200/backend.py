@@ -245,7 +245,7 @@ class CudaBackend:
         y = torch.empty_like(x)
         mean = torch.empty((c,), dtype=torch.float32, device=x.device)
         invstd = torch.empty((c,), dtype=torch.float32, device=x.device)
-        ws = torch.empty((2 * c,), dtype=torch.float64, device=x.device)
+        ws = torch.empty((2 * c + 2,), dtype=torch.float64, device=x.device)
         check(self.lib.cvx_bn_forward(_p(x), _p(residual), _p(y), _p(gamma), _p(beta), _p(rmean), _p(rvar), _p(mean),
                                       _p(invstd), _p(ws), rows, c, _dt(x), act, int(training), float(momentum),
                                       float(eps), self._stream()), "cvx_bn_forward")
@@ -259,7 +259,7 @@ class CudaBackend:
         dres = torch.empty_like(x) if want_dres else None
         dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
-        ws = torch.empty((2 * c,), dtype=torch.float64, device=x.device)
+        ws = torch.empty((2 * c + 2,), dtype=torch.float64, device=x.device)
         check(self.lib.cvx_bn_backward(_p(dy), _p(x), _p(y), _p(gamma), _p(mean), _p(invstd), _p(dx), _p(dres),
                                        _p(dgamma), _p(dbeta), _p(ws), rows, c, _dt(x), act, int(training),
                                        self._stream()), "cvx_bn_backward")
@@ -330,12 +330,12 @@ class CudaBackend:
               "cvx_upsample_to_nchw_bwd")
         return dx
 
-    def dropout_fwd(self, x, p: float, seed: int):
-        self._chk(x)
+    def dropout_fwd(self, x, p: float, seed: int, step_dev=None):
+        self._chk(x, step_dev)
         y = torch.empty_like(x)
         mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
-        check(self.lib.cvx_dropout_fwd(_p(x), _p(y), _p(mask), x.numel(), float(p), int(seed) & (2 ** 64 - 1), _dt(x),
-                                       self._stream()), "cvx_dropout_fwd")
+        check(self.lib.cvx_dropout_fwd(_p(x), _p(y), _p(mask), x.numel(), float(p), int(seed) & (2 ** 64 - 1),
+                                       _p(step_dev), _dt(x), self._stream()), "cvx_dropout_fwd")
         return y, mask
 
     def dropout_bwd(self, dy, mask, p: float):
@@ -376,6 +376,11 @@ class CudaBackend:
         check(self.lib.cvx_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2),
                                      float(eps), float(wd), int(step_t), float(grad_scale), self._stream()),
               "cvx_adam_step")
+
+    def adam_step_dev(self, p, g, m, v, hyper, step_dev):
+        self._chk(p, g, m, v, hyper, step_dev)
+        check(self.lib.cvx_adam_step_dev(_p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), _p(step_dev), self._stream()),
+              "cvx_adam_step_dev")
 
     def sgd_step(self, p, g, buf, lr, momentum, wd, nesterov, first_step, grad_scale=1.0):
         self._chk(p, g, buf)

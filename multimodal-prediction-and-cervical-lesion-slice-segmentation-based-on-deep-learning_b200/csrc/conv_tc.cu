@@ -97,6 +97,7 @@ struct TcFwdParams {
   int bw, bh;                // pixel tile (bw*bh == 128)
   int tiles_x, tiles_y;
   int stride;                // 1, or 2 (persistent forward kernel only: TMA element strides)
+  int tile_n;                // output-channel tile (multiple of 16, <= 256), balanced over n_tiles
 };
 
 template <int BN>
@@ -280,14 +281,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
         const int tx = mt % p.tiles_x; mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
         const int img = mt / p.tiles_y;
-        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * kPBN;
+        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * p.tile_n;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % kPStages;
           mbar_wait(empty0 + 8 * s, ((it / kPStages) & 1) ^ 1);
           const int tap = kb / kcb, cb = kb - tap * kcb;
           const int khi = tap / p.kw, kwi = tap - khi * p.kw;
           const uint32_t sa = smem_base + s * kPStageBytes;
-          mbar_expect_tx(full0 + 8 * s, kPStageBytes);
+          mbar_expect_tx(full0 + 8 * s, kABytes + p.tile_n * 128);
           tma_load_4d(sa, &tmap_x, full0 + 8 * s, cb * 64, ox0 * p.stride - p.pad + kwi * p.dil,
                       oy0 * p.stride - p.pad + khi * p.dil, img);
           tma_load_3d(sa + kABytes, &tmap_w, full0 + 8 * s, cb * 64, n0, tap);
@@ -299,9 +300,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
       uint32_t it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
         const int nt = tile % n_tiles;
-        const int n0 = nt * kPBN;
+        const int n0 = nt * p.tile_n;
         int n_eff = p.cout - n0;
-        n_eff = n_eff > kPBN ? kPBN : ((n_eff + 15) & ~15);
+        n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
         const uint32_t idesc = make_idesc(128, n_eff, 0, 0);
         const int acc = tcount & 1;
         mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
       const int img = mt / p.tiles_y;
-      const int n0 = nt * kPBN;
+      const int n0 = nt * p.tile_n;
       const int row = lg * 32 + lane;
       const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
       const bool row_ok = oy < p.ho && ox < p.wo;
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kPBN; c0 += 32) {
+      for (int c0 = 0; c0 < p.tile_n; c0 += 32) {
         if (n0 + c0 >= p.cout) break;  // warp-uniform
         uint32_t r[32];
         tmem_ld32(t_addr + (uint32_t)c0, r);
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int c = c0 + g * 8;
-            if (n0 + c < p.cout) {
+            if (n0 + c < p.cout && c < p.tile_n) {
               uint32_t packed[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -502,9 +503,9 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           ty = mt % p.tiles_y;
           img = mt / p.tiles_y;
         }
-        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * kPBN;
+        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * p.tile_n;
         int n_eff = p.cout - n0;
-        n_eff = n_eff > kPBN ? kPBN : ((n_eff + 15) & ~15);
+        n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
         const int brow0 = n0 + (int)rank * (n_eff >> 1);
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % k2Stages;
@@ -513,7 +514,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           const int khi = tap / p.kw, kwi = tap - khi * p.kw;
           const uint32_t sa = smem_base + s * k2StageBytes;
           const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;  // the leader CTA's barrier (peer bit cleared)
-          if (leader) mbar_expect_tx(full0 + 8 * s, 2 * k2StageBytes);
+          if (leader) mbar_expect_tx(full0 + 8 * s, 2 * (kABytes + (p.tile_n >> 1) * 128));
           else mbar_arrive_cluster(map_to_cta(full0 + 8 * s, 0));
           tma_load_4d_2sm(sa, &tmap_x, lead_full, cb * 64, ox0 - p.pad + kwi * p.dil, oy0 - p.pad + khi * p.dil, img);
           tma_load_3d_2sm(sa + kABytes, &tmap_w, lead_full, cb * 64, brow0, tap);
@@ -525,9 +526,9 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       uint32_t it = 0, tcount = 0;
       for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
         const int nt = pt % n_tiles;
-        const int n0 = nt * kPBN;
+        const int n0 = nt * p.tile_n;
         int n_eff = p.cout - n0;
-        n_eff = n_eff > kPBN ? kPBN : ((n_eff + 15) & ~15);
+        n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
         const uint32_t idesc = make_idesc(256, n_eff, 0, 0);
         const int acc = tcount & 1;
         mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
@@ -564,7 +565,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
       const int img = mt / p.tiles_y;
-      const int n0 = nt * kPBN;
+      const int n0 = nt * p.tile_n;
       const int row = lg * 32 + lane;
       const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
       const bool row_ok = tile_ok && oy < p.ho && ox < p.wo;
@@ -574,7 +575,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < kPBN; c0 += 32) {
+      for (int c0 = 0; c0 < p.tile_n; c0 += 32) {
         if (n0 + c0 >= p.cout) break;
         uint32_t r[32];
         tmem_ld32(t_addr + (uint32_t)c0, r);
@@ -583,7 +584,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int c = c0 + g * 8;
-            if (n0 + c < p.cout) {
+            if (n0 + c < p.cout && c < p.tile_n) {
               uint32_t packed[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -749,6 +750,7 @@ struct TcWgradPParams {
   int kh, kw, pad, dil;
   int bw, bh, tiles_x, tiles_y;
   int co_tiles, ci_tiles, splits, total_items;
+  int ci_tile;               // input-channel tile (multiple of 16, <= 256), balanced over ci_tiles
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -809,9 +811,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
         int cot, cit, tap, t_begin, t_end;
         decode(item, cot, cit, tap, t_begin, t_end);
         const int khi = tap / p.kw, kwi = tap - khi * p.kw;
-        const int co0 = cot * 128, ci0 = cit * 256;
-        int ci_boxes = (p.cin - ci0 + 63) / 64;
-        ci_boxes = ci_boxes > 4 ? 4 : ci_boxes;
+        const int co0 = cot * 128, ci0 = cit * p.ci_tile;
+        int ci_n = p.cin - ci0;
+        ci_n = ci_n > p.ci_tile ? p.ci_tile : ci_n;
+        const int ci_boxes = (ci_n + 63) / 64;
         for (int t = t_begin; t < t_end; ++t, ++it) {
           const int s = it % kWPStages;
           mbar_wait(empty0 + 8 * s, ((it / kWPStages) & 1) ^ 1);
@@ -836,10 +839,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++icount) {
         int cot, cit, tap, t_begin, t_end;
         decode(item, cot, cit, tap, t_begin, t_end);
-        const int ci0 = cit * 256;
-        int ci_boxes = (p.cin - ci0 + 63) / 64;
-        ci_boxes = ci_boxes > 4 ? 4 : ci_boxes;
-        const uint32_t idesc = make_idesc(128, ci_boxes * 64, 1, 1);  // both operands MN-major
+        const int ci0 = cit * p.ci_tile;
+        int ci_n = p.cin - ci0;
+        ci_n = ci_n > p.ci_tile ? p.ci_tile : ((ci_n + 15) & ~15);
+        const uint32_t idesc = make_idesc(128, ci_n, 1, 1);  // both operands MN-major
         const int acc = icount & 1;
         mbar_wait(tempty0 + 8 * acc, ((icount >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -867,7 +870,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++icount) {
       int cot, cit, tap, t_begin, t_end;
       decode(item, cot, cit, tap, t_begin, t_end);
-      const int ci0 = cit * 256;
+      const int ci0 = cit * p.ci_tile;
       const int co = cot * 128 + lg * 32 + lane;
       const int acc = icount & 1;
       mbar_wait(tfull0 + 8 * acc, (icount >> 1) & 1);
@@ -876,7 +879,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
         float* drow = dw + ((size_t)tap * p.cout + co) * p.cin + ci0;
         const uint32_t t_addr = tmem_base + acc * 256 + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = 0; c0 < p.ci_tile; c0 += 32) {
           if (ci0 + c0 >= p.cin) break;
           uint32_t r[32];
           tmem_ld32(t_addr + (uint32_t)c0, r);
@@ -884,7 +887,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
           if (co < p.cout) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              if (ci0 + c0 + j < p.cin)  // cin % 8 == 0: whole groups of 4 are in or out
+              if (ci0 + c0 + j < p.cin && c0 + j < p.ci_tile)  // cin % 8 == 0: whole groups of 4 are in or out
                 red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                            __uint_as_float(r[j + 3]));
             }
@@ -965,6 +968,11 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
   TcFwdParams p;
   p.n = n; p.ho = ho; p.wo = wo; p.cout = ncol; p.cin = cred; p.kh = kh; p.kw = kw; p.pad = pad; p.dil = dil;
   p.stride = stride;
+  {
+    const int nt = (ncol + kPBN - 1) / kPBN;
+    p.tile_n = ((ncol + nt - 1) / nt + 15) & ~15;   // balanced tiles: 304 -> 2 x 160 instead of 256 + 48
+    if (p.tile_n > kPBN) p.tile_n = kPBN;
+  }
   pick_tile(ho, wo, 128, &p.bw, &p.bh);
   p.tiles_x = (wo + p.bw - 1) / p.bw;
   p.tiles_y = (ho + p.bh - 1) / p.bh;
@@ -976,14 +984,14 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
   if (use_2cta && stride == 1) {
     CUtensorMap mx, mw;
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
-    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, 128)) return rc;
+    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n >> 1)) return rc;
     constexpr int smem = k2Stages * k2StageBytes + 1024 + 256;
     static bool configured = false;
     if (!configured) {
       CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured = true;
     }
-    const int n_tiles = (ncol + kPBN - 1) / kPBN;
+    const int n_tiles = (ncol + p.tile_n - 1) / p.tile_n;
     const int m_tiles = n * p.tiles_y * p.tiles_x;
     const int total = ((m_tiles + 1) / 2) * n_tiles;
     const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
@@ -994,14 +1002,14 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
   if (!use_v1) {
     CUtensorMap mx, mw;
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh, CU_TENSOR_MAP_SWIZZLE_128B, stride)) return rc;
-    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, kPBN)) return rc;
+    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n)) return rc;
     constexpr int smem = kPStages * kPStageBytes + 1024 + 256;
     static bool configured = false;
     if (!configured) {
       CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured = true;
     }
-    const int n_tiles = (ncol + kPBN - 1) / kPBN;
+    const int n_tiles = (ncol + p.tile_n - 1) / p.tile_n;
     const int total = n * p.tiles_y * p.tiles_x * n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
     conv_tc_fwd_persistent_kernel<<<grid, 192, smem, st>>>(mx, mw, bias, (__nv_bfloat16*)dst, p, n_tiles, total);
@@ -1068,6 +1076,9 @@ int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, flo
     q.tiles_y = (d->ho + q.bh - 1) / q.bh;
     q.co_tiles = (d->cout + 127) / 128;
     q.ci_tiles = (d->cin + 255) / 256;
+    q.ci_tile = ((d->cin + q.ci_tiles - 1) / q.ci_tiles + 15) & ~15;
+    if (q.ci_tile > 256) q.ci_tile = 256;
+    q.ci_tiles = (d->cin + q.ci_tile - 1) / q.ci_tile;
     const int ptiles = q.n * q.tiles_y * q.tiles_x;
     const int out_tiles = q.co_tiles * q.ci_tiles * d->kh * d->kw;
     int splits = (2 * kNumSMs + out_tiles - 1) / out_tiles;

@@ -320,7 +320,8 @@ __device__ __forceinline__ uint32_t mix64(uint64_t z) {
 
 template <typename T>
 __global__ void dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
-                                   float p, uint64_t seed) {
+                                   float p, uint64_t seed, const int* __restrict__ step_dev) {
+  if (step_dev) seed += 0x9e3779b97f4a7c15ull * (uint64_t)(*step_dev);  // per-step stream under CUDA-graph replay
   const float keep_scale = 1.f / (1.f - p);
   const uint32_t thresh = (uint32_t)((double)p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)p * 4294967296.0);
   CVX_GRID_STRIDE(i, n) {
@@ -459,9 +460,10 @@ int cvx_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, void* dx,
   return CVX_OK;
 }
 
-int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, int dtype, void* stream) {
+int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, const int* step_dev,
+                    int dtype, void* stream) {
   CVX_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments");
-  CVX_DISPATCH_DTYPE(dtype, T, (dropout_fwd_kernel<T><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, mask, n, p, seed)));
+  CVX_DISPATCH_DTYPE(dtype, T, (dropout_fwd_kernel<T><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, mask, n, p, seed, step_dev)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -19,6 +19,27 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// graph-capturable variant: the step count and the hyper-parameters live in device memory, so a captured
+// launch stays correct on every replay
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const float* __restrict__ hyper,
+                                const int* __restrict__ step) {
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gscale = hyper[5];
+  const float t = (float)(*step);
+  const float bc1 = 1.f - powf(b1, t);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = pi - (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  }
+}
+
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n,
                            float lr, float mom, float wd, int nesterov, int first, float gscale) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -48,6 +69,15 @@ int cvx_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float
   int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
   adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
                                                      (float)sqrt(bc2), grad_scale);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, const int* step,
+                      void* stream) {
+  CVX_CHECK_ARG(p && g && m && v && hyper && step && n > 0, "adam_step_dev: bad arguments");
+  int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
+  adam_dev_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, hyper, step);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -59,6 +59,11 @@ class SegTrainer:
         self.t = 0
         self.world = world_size
         self.last = None
+        # device-side step counter + hyper-parameters: what a captured CUDA graph reads on every replay
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hyper_dev = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0 / max(world_size, 1)],
+                                      dtype=torch.float32, device=dev)
+        self.graph = None
         self._nbt = [m.num_batches_tracked for m in model.modules()
                      if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
         if world_size > 1:
@@ -125,6 +130,8 @@ class SegTrainer:
         (ce, focal, dice, f_score) as a device tensor (no host sync)."""
         B = get_backend()
         self.flat.grad.zero_()
+        self.step_dev.add_(1)
+        ops.set_step_counter(self.step_dev)
         with ops.defer_batch_counters():
             out = self.model(imgs)
         if self.model.training and self._nbt:
@@ -138,13 +145,46 @@ class SegTrainer:
             gscale = 1.0 / self.world
         self.t += 1
         if self.optimizer == "adam":
-            B.adam_step(self.flat.data, self.flat.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1],
-                        self.eps, self.wd, self.t, gscale)
+            # step count and hyper-parameters are read from device memory (graph-replay safe)
+            B.adam_step_dev(self.flat.data, self.flat.grad, self.m, self.v, self.hyper_dev, self.step_dev)
         else:
             B.sgd_step(self.flat.data, self.flat.grad, self.m, self.lr, self.momentum, self.wd, True, self.t == 1,
                        gscale)
         self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
         return self.last
+
+    def set_lr(self, lr: float):
+        self.lr = lr
+        self.hyper_dev[0] = lr
+
+    # ------------------------------------------------------------------ CUDA graph
+    def capture(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None, warmup: int = 3):
+        """Capture one whole training step (forward, loss, backward, optimizer: ~1 800 kernel launches) into a
+        CUDA graph over static input buffers.  Single-GPU only; the data-parallel path stays eager so that
+        the bucketed all-reduce keeps overlapping backward."""
+        if self.world > 1:
+            raise RuntimeError("graph capture is implemented for the single-GPU step")
+        self.s_imgs, self.s_pngs = imgs.clone(), pngs.clone()
+        self.s_labels = None if labels is None else labels.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self.s_imgs, self.s_pngs, self.s_labels)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.s_out = self.step(self.s_imgs, self.s_pngs, self.s_labels)
+        return self
+
+    def step_graphed(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None):
+        self.s_imgs.copy_(imgs, non_blocking=True)
+        self.s_pngs.copy_(pngs, non_blocking=True)
+        if self.s_labels is not None and labels is not None:
+            self.s_labels.copy_(labels, non_blocking=True)
+        self.graph.replay()
+        self.t += 1
+        return self.s_out
 
 
 class BatchPrefetcher:

@@ -289,7 +289,7 @@ class UpsampleToNCHW(Function):
 class Dropout(Function):
     @staticmethod
     def forward(ctx, x, p, seed):
-        y, mask = get_backend().dropout_fwd(x.contiguous(), p, seed)
+        y, mask = get_backend().dropout_fwd(x.contiguous(), p, seed, _STEP_DEV[0])
         ctx.save_for_backward(mask)
         ctx.p = p
         return y
@@ -398,6 +398,14 @@ def upsample_to_nchw(x, ho, wo):
 
 
 _dropout_counter = [0]
+# device int32 step counter installed by a trainer that replays a captured CUDA graph: mixed into every
+# dropout seed on the device so each replay draws fresh masks (host-side seeds are frozen in the graph)
+_STEP_DEV = [None]
+
+
+def set_step_counter(t):
+    _STEP_DEV[0] = t
+
 
 
 def dropout(x, p, training):

@@ -215,7 +215,9 @@ class EmuBackend:
             F.interpolate(x, size=(ho, wo), mode="bilinear", align_corners=True).backward(dy.float())
         return _nhwc(x.grad, dtype)
 
-    def dropout_fwd(self, x, p, seed):
+    def dropout_fwd(self, x, p, seed, step_dev=None):
+        if step_dev is not None:
+            seed = seed + 7919 * int(step_dev)
         g = torch.Generator(device="cpu").manual_seed(seed % (2 ** 63))
         mask = (torch.rand(x.shape, generator=g) >= p).to(torch.uint8).to(x.device)
         return (x.float() * mask / (1 - p)).to(x.dtype), mask
@@ -292,6 +294,10 @@ class EmuBackend:
         bc1 = 1 - beta1 ** step_t
         bc2 = 1 - beta2 ** step_t
         p.sub_((lr / bc1) * m / (v.sqrt() / (bc2 ** 0.5) + eps))
+
+    def adam_step_dev(self, p, g, m, v, hyper, step_dev):
+        lr, b1, b2, eps, wd, gs = [float(t) for t in hyper]
+        self.adam_step(p, g, m, v, lr, b1, b2, eps, wd, int(step_dev), gs)
 
     def sgd_step(self, p, g, buf, lr, momentum, wd, nesterov, first_step, grad_scale=1.0):
         gi = g * grad_scale
