@@ -219,7 +219,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     if use_graph:
         trainer.capture(imgs, pngs, None)
         step_fn = lambda a, b, c=None: trainer.step_graphed(a, b)   # noqa: E731

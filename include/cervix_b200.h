@@ -168,6 +168,45 @@ CVX_API int cvx_seg_loss_grad(const float* logits, const int64_t* target, const 
                       int n, int c, int h, int w, float focal_alpha, float focal_gamma,
                       float beta, float smooth, void* stream);
 
+/* ---- multimodal fusion head: fp32 row operators on [groups*seg, C] matrices ----------------------
+ * (MultiModal Prediction/Four_Modal/my_mae_model.py:500-793; a "group" is one patient graph).
+ * Linear layers use cvx_conv_fwd/dgrad/wgrad with a 1x1 geometry. */
+/* mode 0 = torch_geometric LayerNorm(mode='graph') (my_mae_model.py:350,396,471-478): statistics over
+ * all seg*C elements of a group, eps added to the std; mode 1 = nn.LayerNorm (mae_utils.py:112,118), seg = 1.
+ * stats: 3 floats per group (mean, multiplier, std), kept for the backward. */
+CVX_API int cvx_seg_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int groups,
+                          int seg, int c, float eps, int mode, void* stream);
+CVX_API int cvx_seg_layernorm_bwd(const float* dy, const float* x, const float* w, const float* stats, float* dx,
+                          float* dw, float* db, int groups, int seg, int c, float eps, int mode, void* stream);
+/* nn.GELU (erf form; mae_utils.py:38-55, my_mae_model.py:338-343) */
+CVX_API int cvx_gelu_fwd(const float* x, float* y, int64_t n, void* stream);
+CVX_API int cvx_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, void* stream);
+/* SAGEConv mean aggregation over a fixed topology shared by all groups (CSR rowptr/col + per-edge weight):
+ * out[g,i,:] = sum_e w[e] * x[g,col[e],:]  (my_mae_model.py:404-416,544; the transposed CSR gives the gradient) */
+CVX_API int cvx_graph_gather(const float* x, float* out, int groups, int nodes, int c, const int* rowptr, const int* col,
+                     const float* w, void* stream);
+/* my_GlobalAttention (my_mae_model.py:35-63): att = softmax over the seg nodes of a group (+1e-16), pooled = sum att*x */
+CVX_API int cvx_gate_pool_fwd(const float* x, const float* gate, float* pooled, float* att, int groups, int seg, int c,
+                      void* stream);
+CVX_API int cvx_gate_pool_bwd(const float* dpooled, const float* x, const float* att, float* dx, float* dgate, int groups,
+                      int seg, int c, void* stream);
+/* multi-head attention over <= 8 tokens (mae_utils.py:58-102): qkv [b,n,3,h,d] -> out [b,n,h*d], probs [b,h,n,n] */
+CVX_API int cvx_attn_small_fwd(const float* qkv, float* out, float* probs, int b, int n, int h, int d, float scale,
+                       float drop_p, uint64_t seed, void* stream);
+CVX_API int cvx_attn_small_bwd(const float* dout, const float* qkv, const float* probs, float* dqkv, int b, int n, int h,
+                       int d, float scale, float drop_p, uint64_t seed, void* stream);
+/* F.normalize(dim=1) (my_mae_model.py:679) */
+CVX_API int cvx_l2norm_fwd(const float* x, float* y, float* norms, int rows, int c, void* stream);
+CVX_API int cvx_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int rows, int c, void* stream);
+/* token (un)shuffling of the masked auto-encoder (my_mae_model.py:143,318-335): y[i] = idx[i] >= 0 ? x[idx[i]] : fill */
+CVX_API int cvx_rows_gather(const float* x, const int* idx, const float* fill, float* y, int rows, int c, void* stream);
+CVX_API int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int c, void* stream);
+/* classifier objective (my_train(full).py:309-347): loss += weight * mean CE ; masked-row MSE */
+CVX_API int cvx_softmax_ce(const float* logits, const int64_t* labels, float* loss, float* dlogits, int b, int k,
+                   float weight, void* stream);
+CVX_API int cvx_masked_mse(const float* a, const float* b, const uint8_t* sel, float* loss, float* da, float* db, int rows,
+                   int c, float weight, float inv_count, void* stream);
+
 /* ---- optimizer (train.py:472-476) ---------------------------------------------------- */
 /* torch.optim.Adam semantics (L2 weight decay added to the gradient), fp32 state.
  * step_t is the 1-based step count; grad_scale multiplies the gradient first. */

@@ -69,6 +69,21 @@ PROTOTYPES = {
     "cvx_seg_loss_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
     "cvx_seg_loss_finalize": [_P, _P, _I, _F, _F, _P],
     "cvx_seg_loss_grad": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P],
+    "cvx_seg_layernorm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    "cvx_seg_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
+    "cvx_gelu_fwd": [_P, _P, _L, _P],
+    "cvx_gelu_bwd": [_P, _P, _P, _L, _P],
+    "cvx_graph_gather": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
+    "cvx_gate_pool_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "cvx_gate_pool_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "cvx_attn_small_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, _P],
+    "cvx_attn_small_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, _P],
+    "cvx_l2norm_fwd": [_P, _P, _P, _I, _I, _P],
+    "cvx_l2norm_bwd": [_P, _P, _P, _P, _I, _I, _P],
+    "cvx_rows_gather": [_P, _P, _P, _P, _I, _I, _P],
+    "cvx_rows_scatter_add": [_P, _P, _P, _P, _I, _I, _P],
+    "cvx_softmax_ce": [_P, _P, _P, _P, _I, _I, _F, _P],
+    "cvx_masked_mse": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P],
     "cvx_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "cvx_adam_step_dev": [_P, _P, _P, _P, _L, _P, _P, _P],
     "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],

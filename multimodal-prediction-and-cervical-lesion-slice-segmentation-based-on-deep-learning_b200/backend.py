@@ -370,6 +370,127 @@ class CudaBackend:
               "cvx_seg_loss_grad")
         return d
 
+    # ------------------------------------------------------------------ fusion-head row operators (fp32)
+    def seg_layernorm_fwd(self, x, w, b, groups: int, seg: int, eps: float, mode: int):
+        self._chk(x, w, b)
+        c = int(x.shape[-1])
+        y = torch.empty_like(x)
+        stats = torch.empty((groups, 3), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_seg_layernorm_fwd(_p(x), _p(w), _p(b), _p(y), _p(stats), groups, seg, c, float(eps), mode,
+                                             self._stream()), "cvx_seg_layernorm_fwd")
+        return y, stats
+
+    def seg_layernorm_bwd(self, dy, x, w, stats, groups: int, seg: int, eps: float, mode: int):
+        self._chk(dy, x, w, stats)
+        c = int(x.shape[-1])
+        dx = torch.empty_like(x)
+        dw = torch.empty((c,), dtype=torch.float32, device=x.device)
+        db = torch.empty((c,), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_seg_layernorm_bwd(_p(dy), _p(x), _p(w), _p(stats), _p(dx), _p(dw), _p(db), groups, seg, c,
+                                             float(eps), mode, self._stream()), "cvx_seg_layernorm_bwd")
+        return dx, dw, db
+
+    def gelu_fwd(self, x):
+        self._chk(x)
+        y = torch.empty_like(x)
+        check(self.lib.cvx_gelu_fwd(_p(x), _p(y), x.numel(), self._stream()), "cvx_gelu_fwd")
+        return y
+
+    def gelu_bwd(self, dy, x):
+        self._chk(dy, x)
+        dx = torch.empty_like(x)
+        check(self.lib.cvx_gelu_bwd(_p(dy), _p(x), _p(dx), x.numel(), self._stream()), "cvx_gelu_bwd")
+        return dx
+
+    def graph_gather(self, x, groups: int, nodes: int, rowptr, col, w):
+        self._chk(x, rowptr, col, w)
+        c = int(x.shape[-1])
+        out = torch.empty_like(x)
+        check(self.lib.cvx_graph_gather(_p(x), _p(out), groups, nodes, c, _p(rowptr), _p(col), _p(w), self._stream()),
+              "cvx_graph_gather")
+        return out
+
+    def gate_pool_fwd(self, x, gate, groups: int, seg: int):
+        self._chk(x, gate)
+        c = int(x.shape[-1])
+        pooled = torch.empty((groups, c), dtype=torch.float32, device=x.device)
+        att = torch.empty((groups * seg,), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_gate_pool_fwd(_p(x), _p(gate), _p(pooled), _p(att), groups, seg, c, self._stream()),
+              "cvx_gate_pool_fwd")
+        return pooled, att
+
+    def gate_pool_bwd(self, dpooled, x, att, groups: int, seg: int):
+        self._chk(dpooled, x, att)
+        c = int(x.shape[-1])
+        dx = torch.empty_like(x)
+        dgate = torch.empty((groups * seg,), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_gate_pool_bwd(_p(dpooled), _p(x), _p(att), _p(dx), _p(dgate), groups, seg, c, self._stream()),
+              "cvx_gate_pool_bwd")
+        return dx, dgate
+
+    def attn_small_fwd(self, qkv, b: int, n: int, h: int, d: int, scale: float, drop_p: float, seed: int):
+        self._chk(qkv)
+        out = torch.empty((b, n, h * d), dtype=torch.float32, device=qkv.device)
+        probs = torch.empty((b, h, n, n), dtype=torch.float32, device=qkv.device)
+        check(self.lib.cvx_attn_small_fwd(_p(qkv), _p(out), _p(probs), b, n, h, d, float(scale), float(drop_p),
+                                          int(seed) & (2 ** 64 - 1), self._stream()), "cvx_attn_small_fwd")
+        return out, probs
+
+    def attn_small_bwd(self, dout, qkv, probs, b, n, h, d, scale, drop_p, seed):
+        self._chk(dout, qkv, probs)
+        dqkv = torch.empty_like(qkv)
+        check(self.lib.cvx_attn_small_bwd(_p(dout), _p(qkv), _p(probs), _p(dqkv), b, n, h, d, float(scale), float(drop_p),
+                                          int(seed) & (2 ** 64 - 1), self._stream()), "cvx_attn_small_bwd")
+        return dqkv
+
+    def l2norm_fwd(self, x):
+        self._chk(x)
+        rows, c = x.shape
+        y = torch.empty_like(x)
+        norms = torch.empty((rows,), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_l2norm_fwd(_p(x), _p(y), _p(norms), rows, c, self._stream()), "cvx_l2norm_fwd")
+        return y, norms
+
+    def l2norm_bwd(self, dy, y, norms):
+        self._chk(dy, y, norms)
+        rows, c = y.shape
+        dx = torch.empty_like(y)
+        check(self.lib.cvx_l2norm_bwd(_p(dy), _p(y), _p(norms), _p(dx), rows, c, self._stream()), "cvx_l2norm_bwd")
+        return dx
+
+    def rows_gather(self, x, idx, fill):
+        self._chk(x, idx, fill)
+        rows, c = int(idx.shape[0]), int(x.shape[-1])
+        y = torch.empty((rows, c), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_rows_gather(_p(x), _p(idx), _p(fill), _p(y), rows, c, self._stream()), "cvx_rows_gather")
+        return y
+
+    def rows_scatter_add(self, dy, idx, src_rows: int, want_fill: bool):
+        self._chk(dy, idx)
+        rows, c = dy.shape
+        dx = torch.zeros((src_rows, c), dtype=torch.float32, device=dy.device)
+        dfill = torch.zeros((c,), dtype=torch.float32, device=dy.device) if want_fill else None
+        check(self.lib.cvx_rows_scatter_add(_p(dy), _p(idx), _p(dx), _p(dfill), rows, c, self._stream()),
+              "cvx_rows_scatter_add")
+        return dx, dfill
+
+    def softmax_ce(self, logits, labels, loss, weight: float, want_grad: bool):
+        self._chk(logits, labels, loss)
+        b, k = logits.shape
+        d = torch.empty_like(logits) if want_grad else None
+        check(self.lib.cvx_softmax_ce(_p(logits), _p(labels), _p(loss), _p(d), b, k, float(weight), self._stream()),
+              "cvx_softmax_ce")
+        return d
+
+    def masked_mse(self, a, b, sel, loss, weight: float, inv_count: float, want_grad: bool):
+        self._chk(a, b, sel, loss)
+        rows, c = a.shape
+        da = torch.empty_like(a) if want_grad else None
+        db = torch.empty_like(a) if want_grad else None
+        check(self.lib.cvx_masked_mse(_p(a), _p(b), _p(sel), _p(loss), _p(da), _p(db), rows, c, float(weight),
+                                      float(inv_count), self._stream()), "cvx_masked_mse")
+        return da, db
+
     # ------------------------------------------------------------------ optimizer
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, wd, step_t, grad_scale=1.0):
         self._chk(p, g, m, v)

@@ -64,6 +64,7 @@ class SegTrainer:
         self.hyper_dev = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0 / max(world_size, 1)],
                                       dtype=torch.float32, device=dev)
         self.graph = None
+        self._hooks_off = False
         self._nbt = [m.num_batches_tracked for m in model.modules()
                      if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
         if world_size > 1:
@@ -96,6 +97,8 @@ class SegTrainer:
 
     def _make_hook(self, i):
         def hook(_p):
+            if self._hooks_off:
+                return
             b = self.buckets[self.bucket_of[i]]
             b[2] += 1
             if b[2] == b[3]:
@@ -128,7 +131,11 @@ class SegTrainer:
         """imgs: fp32 NCHW in [0,1]; pngs: int64 class map (num_classes = ignore); labels: the
         reference's fp32 one-hot [B,H,W,C+1] (optional).  Returns the 4-vector
         (ce, focal, dice, f_score) as a device tensor (no host sync)."""
-        B = get_backend()
+        losses = self._forward_backward(imgs, pngs, labels)
+        self._reduce_and_update()
+        return losses
+
+    def _forward_backward(self, imgs, pngs, labels):
         self.flat.grad.zero_()
         self.step_dev.add_(1)
         ops.set_step_counter(self.step_dev)
@@ -139,9 +146,17 @@ class SegTrainer:
         ce, focal, dice, fs = seg_objective(out, pngs, labels, self.cls_weights, self.num_classes)
         loss = (focal if self.focal else ce) + (dice if self.dice else 0.0)
         loss.backward()
+        self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
+        return self.last
+
+    def _reduce_and_update(self):
+        B = get_backend()
         gscale = 1.0
         if self.world > 1:
-            self._finish_allreduce()
+            if self._hooks_off:     # graph-replayed backward: one all-reduce of the whole flat gradient
+                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
+            else:
+                self._finish_allreduce()
             gscale = 1.0 / self.world
         self.t += 1
         if self.optimizer == "adam":
@@ -150,8 +165,6 @@ class SegTrainer:
         else:
             B.sgd_step(self.flat.data, self.flat.grad, self.m, self.lr, self.momentum, self.wd, True, self.t == 1,
                        gscale)
-        self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
-        return self.last
 
     def set_lr(self, lr: float):
         self.lr = lr
@@ -159,11 +172,11 @@ class SegTrainer:
 
     # ------------------------------------------------------------------ CUDA graph
     def capture(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None, warmup: int = 3):
-        """Capture one whole training step (forward, loss, backward, optimizer: ~1 800 kernel launches) into a
-        CUDA graph over static input buffers.  Single-GPU only; the data-parallel path stays eager so that
-        the bucketed all-reduce keeps overlapping backward."""
-        if self.world > 1:
-            raise RuntimeError("graph capture is implemented for the single-GPU step")
+        """Capture one training step (~1 800 kernel launches) into a CUDA graph over static input buffers.
+        Single GPU: forward, loss, backward and the optimizer are all inside the graph.  Data parallel:
+        forward + loss + backward are captured; the gradient all-reduce (one NCCL call on the flat 219 MB
+        gradient, ~0.5 ms on NVLink 5) and the fused Adam run right after each replay."""
+        self._hooks_off = self.world > 1
         self.s_imgs, self.s_pngs = imgs.clone(), pngs.clone()
         self.s_labels = None if labels is None else labels.clone()
         side = torch.cuda.Stream()
@@ -174,7 +187,10 @@ class SegTrainer:
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.s_out = self.step(self.s_imgs, self.s_pngs, self.s_labels)
+            if self.world > 1:
+                self.s_out = self._forward_backward(self.s_imgs, self.s_pngs, self.s_labels)
+            else:
+                self.s_out = self.step(self.s_imgs, self.s_pngs, self.s_labels)
         return self
 
     def step_graphed(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None):
@@ -183,7 +199,10 @@ class SegTrainer:
         if self.s_labels is not None and labels is not None:
             self.s_labels.copy_(labels, non_blocking=True)
         self.graph.replay()
-        self.t += 1
+        if self.world > 1:
+            self._reduce_and_update()
+        else:
+            self.t += 1
         return self.s_out
 
 

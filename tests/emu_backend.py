@@ -284,6 +284,121 @@ class EmuBackend:
         (gd[0] * ce + gd[1] * focal + gd[2] * dice).backward()
         return z.grad.float()
 
+    # ---- fusion-head row operators
+    @staticmethod
+    def _ln(x, w, b, groups, seg, eps, mode):
+        c = x.shape[-1]
+        xs = x.reshape(groups, seg * c)
+        mean = xs.mean(1, keepdim=True)
+        xc = xs - mean
+        sd = xc.pow(2).mean(1, keepdim=True).sqrt()
+        r = 1 / (sd + eps) if mode == 0 else 1 / torch.sqrt(sd * sd + eps)
+        y = (xc * r).reshape(-1, c) * w + b
+        return y.reshape(x.shape), torch.cat([mean, r, sd], 1)
+
+    def seg_layernorm_fwd(self, x, w, b, groups, seg, eps, mode):
+        return self._ln(x, w, b, groups, seg, eps, mode)
+
+    def seg_layernorm_bwd(self, dy, x, w, stats, groups, seg, eps, mode):
+        with torch.enable_grad():
+            xi = x.detach().requires_grad_(True); wi = w.detach().requires_grad_(True)
+            bi = torch.zeros_like(w).requires_grad_(True)
+            y, _ = self._ln(xi, wi, bi, groups, seg, eps, mode)
+            y.backward(dy)
+        return xi.grad, wi.grad, bi.grad
+
+    def gelu_fwd(self, x):
+        return F.gelu(x)
+
+    def gelu_bwd(self, dy, x):
+        with torch.enable_grad():
+            xi = x.detach().requires_grad_(True)
+            F.gelu(xi).backward(dy)
+        return xi.grad
+
+    def graph_gather(self, x, groups, nodes, rowptr, col, w):
+        c = x.shape[-1]
+        xs = x.reshape(groups, nodes, c)
+        out = torch.zeros_like(xs)
+        rp = rowptr.tolist(); cl = col.tolist(); ww = w.tolist()
+        for i in range(nodes):
+            for e in range(rp[i], rp[i + 1]):
+                out[:, i] += ww[e] * xs[:, cl[e]]
+        return out.reshape(x.shape)
+
+    @staticmethod
+    def _pool(x, gate, groups, seg):
+        c = x.shape[-1]
+        g = gate.reshape(groups, seg)
+        e = (g - g.max(1, keepdim=True).values).exp()
+        att = e / (e.sum(1, keepdim=True) + 1e-16)
+        pooled = (att.unsqueeze(-1) * x.reshape(groups, seg, c)).sum(1)
+        return pooled, att.reshape(-1)
+
+    def gate_pool_fwd(self, x, gate, groups, seg):
+        return self._pool(x, gate, groups, seg)
+
+    def gate_pool_bwd(self, dpooled, x, att, groups, seg):
+        c = x.shape[-1]
+        xs = x.reshape(groups, seg, c); a = att.reshape(groups, seg)
+        dx = (a.unsqueeze(-1) * dpooled.unsqueeze(1)).reshape(x.shape)
+        datt = (dpooled.unsqueeze(1) * xs).sum(-1)
+        dgate = a * (datt - (a * datt).sum(1, keepdim=True))
+        return dx, dgate.reshape(-1)
+
+    @staticmethod
+    def _attn(qkv, b, n, h, d, scale):
+        q, k, v = qkv.reshape(b, n, 3, h, d).permute(2, 0, 3, 1, 4)
+        p = ((q * scale) @ k.transpose(-2, -1)).softmax(-1)
+        return (p @ v).transpose(1, 2).reshape(b, n, h * d), p
+
+    def attn_small_fwd(self, qkv, b, n, h, d, scale, drop_p, seed):
+        assert drop_p == 0.0, "the emulation backend covers the deterministic (eval) attention only"
+        return self._attn(qkv, b, n, h, d, scale)
+
+    def attn_small_bwd(self, dout, qkv, probs, b, n, h, d, scale, drop_p, seed):
+        with torch.enable_grad():
+            qi = qkv.detach().requires_grad_(True)
+            self._attn(qi, b, n, h, d, scale)[0].backward(dout)
+        return qi.grad
+
+    def l2norm_fwd(self, x):
+        n = x.norm(dim=1).clamp_min(1e-12)
+        return x / n.unsqueeze(1), n
+
+    def l2norm_bwd(self, dy, y, norms):
+        return (dy - y * (dy * y).sum(1, keepdim=True)) / norms.unsqueeze(1)
+
+    def rows_gather(self, x, idx, fill):
+        y = x[idx.clamp_min(0).long()]
+        if fill is not None:
+            y = torch.where((idx < 0).unsqueeze(1), fill.unsqueeze(0).expand_as(y), y)
+        else:
+            y = y * (idx >= 0).unsqueeze(1)
+        return y.contiguous()
+
+    def rows_scatter_add(self, dy, idx, src_rows, want_fill):
+        dx = torch.zeros((src_rows, dy.shape[1]), dtype=dy.dtype, device=dy.device)
+        ok = idx >= 0
+        dx.index_add_(0, idx[ok].long(), dy[ok])
+        dfill = dy[~ok].sum(0) if want_fill else None
+        return dx, dfill
+
+    def softmax_ce(self, logits, labels, loss, weight, want_grad):
+        b = logits.shape[0]
+        lse = torch.logsumexp(logits, 1)
+        loss += weight * (lse - logits.gather(1, labels[:, None])[:, 0]).sum() / b
+        if not want_grad:
+            return None
+        return weight * (torch.softmax(logits, 1) - F.one_hot(labels, logits.shape[1]).float()) / b
+
+    def masked_mse(self, a, b, sel, loss, weight, inv_count, want_grad):
+        d = (a - b) * sel.bool().unsqueeze(1)
+        loss += weight * (d * d).sum() * inv_count
+        if not want_grad:
+            return None, None
+        return 2 * d * weight * inv_count, -2 * d * weight * inv_count
+
     # ---- optimizer
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, wd, step_t, grad_scale=1.0):
         gi = g * grad_scale
