@@ -1,0 +1,436 @@
+"""B200 path of the multimodal fusion classifier.
+
+Drop-in for ``MultiModal Prediction/{Four,Three,Two}_Modal/my_mae_model*.py``: the class
+``fusion_model_mae_2`` keeps the reference's constructor (my_mae_model.py:400), its 148-entry
+``state_dict`` schema and the 9-tuple ``forward`` (my_mae_model.py:500-793), so the reference's train scripts
+(my_train(full).py:79-81,246-248) run unchanged.  One parametrised implementation covers the 2-, 3- and
+4-modal variants (they differ only in ``train_type_num`` and in which modality branches are visited).
+
+The reference processes ONE patient graph per forward through hundreds of tiny ATen / PyG launches.  Here
+``forward_batch`` lays G patients out as ``[G * nodes, C]`` row matrices and every graph-level operator
+(SAGE mean aggregation, PyG graph-mode LayerNorm, gated attention pooling, the <= 4-token MAE attention,
+MLP-Mixer) is one CUDA launch over the whole batch (csrc/rowops.cu); linear layers go through the 1x1
+convolution kernels.  ``forward`` is the G = 1 case.  No torch compute op is on the path: the modules below
+are parameter holders and are never called.
+
+torch_geometric / torch_scatter / timm are not needed: their published algorithms are
+restated by the kernels and pinned by tests/golden/fusion_*.npz.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+from . import rowops as R
+
+MODALITIES = ("imgN", "imgA", "imgL", "cli")
+_EDGE_ATTR = {"imgN": "edge_index_imageN", "imgA": "edge_index_imageA", "imgL": "edge_index_imageL",
+              "cli": "edge_index_cli"}
+
+
+# ----------------------------------------------------------------------------- parameter holders
+class SAGEConv(nn.Module):
+    """torch_geometric.nn.SAGEConv(aggr='mean', root_weight=True): lin_l(mean_j x_j) + lin_r(x_i)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.lin_l = nn.Linear(in_channels, out_channels, bias=True)
+        self.lin_r = nn.Linear(in_channels, out_channels, bias=False)
+
+
+class LayerNorm(nn.Module):
+    """torch_geometric.nn.LayerNorm(mode='graph') parameter holder (eps is added to the std)."""
+
+    def __init__(self, in_channels, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(in_channels))
+        self.bias = nn.Parameter(torch.zeros(in_channels))
+
+
+class my_GlobalAttention(nn.Module):
+    def __init__(self, gate_nn, nn=None):
+        super().__init__()
+        self.gate_nn = gate_nn
+        self.nn = nn
+
+
+def _xavier(module):
+    for m in module.modules():
+        if isinstance(m, nn.Linear):
+            nn.init.xavier_uniform_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class Attention(nn.Module):
+    """mae_utils.py:58-102: head_dim = dim // heads (512 // 12 = 42 -> qkv 512 -> 1512, proj 504 -> 512)."""
+
+    def __init__(self, dim, num_heads, attn_drop):
+        super().__init__()
+        self.num_heads = num_heads
+        self.head_dim = dim // num_heads
+        self.scale = self.head_dim ** -0.5
+        self.qkv = nn.Linear(dim, self.head_dim * num_heads * 3, bias=False)
+        self.proj = nn.Linear(self.head_dim * num_heads, dim)
+        self.attn_drop = attn_drop
+
+
+class Block(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio=4.0, attn_drop=0.0):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = Attention(dim, num_heads, attn_drop)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+
+class _Encoder(nn.Module):
+    def __init__(self, dim, heads, attn_drop):
+        super().__init__()
+        self.patch_embed = nn.Linear(dim, dim)
+        self.blocks = nn.ModuleList([Block(dim, heads, 4.0, attn_drop)])
+        self.norm = nn.LayerNorm(dim)
+        _xavier(self)
+
+
+class _Decoder(nn.Module):
+    def __init__(self, dim, heads, attn_drop):
+        super().__init__()
+        self.blocks = nn.ModuleList([Block(dim, heads, 4.0, attn_drop)])
+        self.norm = nn.LayerNorm(dim)
+        self.head = nn.Linear(dim, dim)
+        _xavier(self)
+
+
+def get_sinusoid_encoding_table(n_position, d_hid):
+    pos = np.arange(n_position, dtype=np.float64)[:, None]
+    j = np.arange(d_hid)[None, :]
+    table = pos / np.power(10000, 2 * (j // 2) / d_hid)
+    table[:, 0::2] = np.sin(table[:, 0::2])
+    table[:, 1::2] = np.cos(table[:, 1::2])
+    return torch.tensor(table, dtype=torch.float32).unsqueeze(0)
+
+
+class PretrainVisionTransformer(nn.Module):
+    """my_mae_model.py:216-335 with encoder_depth = decoder_depth = 1, 12 / 8 heads, attn_drop 0.3
+    (drop_path resolves to 0 at depth 1, init_values = 0 -> no layer scale)."""
+
+    def __init__(self, dim=512, train_type_num=4, attn_drop_rate=0.3):
+        super().__init__()
+        self.encoder = _Encoder(dim, 12, attn_drop_rate)
+        self.decoder = _Decoder(dim, 8, attn_drop_rate)
+        self.encoder_to_decoder = nn.Linear(dim, dim, bias=False)
+        self.mask_token = nn.Parameter(torch.zeros(1, 1, dim))
+        self.pos_embed = get_sinusoid_encoding_table(train_type_num, dim)      # plain tensor, as in the reference
+        nn.init.trunc_normal_(self.mask_token, std=0.02, a=-0.02, b=0.02)
+
+
+def Mix_mlp(dim1):
+    return nn.Sequential(nn.Linear(dim1, dim1), nn.GELU(), nn.Linear(dim1, dim1))
+
+
+class MixerBlock(nn.Module):
+    def __init__(self, dim1, dim2):
+        super().__init__()
+        self.norm = LayerNorm(dim2)
+        self.mix_mip_1 = Mix_mlp(dim1)
+        self.mix_mip_2 = Mix_mlp(dim2)
+
+
+def GNN_relu_Block(dim2, dropout=0.3):
+    return nn.Sequential(nn.ReLU(), LayerNorm(dim2), nn.Dropout(p=dropout))
+
+
+def _gate(dim):
+    return nn.Sequential(nn.Linear(dim, dim // 4), nn.ReLU(), nn.Linear(dim // 4, 1))
+
+
+# ----------------------------------------------------------------------------- the model
+class fusion_model_mae_2(nn.Module):
+    def __init__(self, in_feats, n_hidden, out_classes, dropout=0.3, train_type_num=4):
+        super().__init__()
+        C = out_classes
+        for m in MODALITIES:
+            setattr(self, m + "_gnn_2", SAGEConv(in_feats, C))
+            setattr(self, m + "_relu_2", GNN_relu_Block(C))
+        self.fc_cli_1 = nn.Linear(1024, C)      # present in the reference's state_dict, never used in forward
+        self.fc_cli_2 = nn.Linear(C, C)
+        for m in MODALITIES:
+            setattr(self, "mpool_" + m, my_GlobalAttention(_gate(C)))
+        for m in MODALITIES:
+            setattr(self, "mpool_" + m + "_2", my_GlobalAttention(_gate(C)))
+        self.mae = PretrainVisionTransformer(C, train_type_num)
+        self.mix = MixerBlock(train_type_num, C)
+        for m in MODALITIES:
+            setattr(self, "lin1_" + m, nn.Linear(C, C // 4))
+            setattr(self, "lin2_" + m, nn.Linear(C // 4, C // 16))
+            setattr(self, "lin3_" + m, nn.Linear(C // 16, C // 64))
+        for m in MODALITIES:
+            setattr(self, "norm1_" + m, LayerNorm(C // 4))
+        for m in MODALITIES:
+            setattr(self, "norm2_" + m, LayerNorm(C // 16))
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(p=dropout)
+        self.classifier = nn.Linear(C // 64, 4)
+        for m in MODALITIES:
+            setattr(self, "classifier_" + m, nn.Linear(C // 64, 4))
+        self.hidden = C
+        self.train_type_num = train_type_num
+        self._topo: Dict[tuple, R.GraphTopology] = {}
+        self._const: Dict[tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _topology(self, edge_index, nodes: int, device) -> R.GraphTopology:
+        ei = torch.as_tensor(edge_index).detach().cpu().to(torch.int64)
+        key = (nodes, str(device), ei.numpy().tobytes())
+        t = self._topo.get(key)
+        if t is None:
+            t = self._topo[key] = R.GraphTopology(ei, nodes, device)
+        return t
+
+    def _idx(self, values: Sequence[int], device) -> torch.Tensor:
+        key = ("idx", str(device), tuple(values))
+        t = self._const.get(key)
+        if t is None:
+            t = self._const[key] = torch.tensor(list(values), dtype=torch.int32, device=device)
+        return t
+
+    def _pos_rows(self, order: Sequence[int], device) -> torch.Tensor:
+        """Sinusoid table rows in the given token order, as a [len(order), C] device constant."""
+        key = ("pos", str(device), tuple(order))
+        t = self._const.get(key)
+        if t is None:
+            t = self._const[key] = self.mae.pos_embed[0][list(order)].contiguous().to(device)
+        return t
+
+    def _drop(self, x, p):
+        return ops.dropout(x, p, self.training)
+
+    def _block(self, x, blk: Block, b: int, n: int):
+        a = blk.attn
+        h = R.linear(R.layernorm(x, blk.norm1), a.qkv)
+        p = a.attn_drop if self.training else 0.0
+        seed = 0
+        if p > 0.0:
+            ops._dropout_counter[0] += 1
+            seed = (torch.initial_seed() * 1000003 + ops._dropout_counter[0]) & (2 ** 63 - 1)
+        h = R.AttnSmall.apply(h, b, n, a.num_heads, a.head_dim, a.scale, p, seed).reshape(b * n, a.num_heads * a.head_dim)
+        x = ops.Add.apply(x, R.linear(h, a.proj))
+        h = R.linear(R.gelu(R.linear(R.layernorm(x, blk.norm2), blk.mlp.fc1)), blk.mlp.fc2)
+        return ops.Add.apply(x, h)
+
+    def _mae(self, tokens, masks: np.ndarray):
+        """tokens [G*T, C] (modality order); masks [G, T] bool, True = masked.  Every patient of the batch must
+        have the same number of visible tokens (the training mask has exactly one, generate_mask mae_utils.py:11-21).
+        Returns the reconstructed tokens [G*T, C] in modality order (my_mae_model.py:305-335)."""
+        G, T = masks.shape
+        dev = tokens.device
+        n_vis = int((~masks[0]).sum())
+        if any(int((~m).sum()) != n_vis for m in masks):
+            raise ValueError("all patients of a batch must have the same number of visible modalities")
+        mae = self.mae
+        vis_idx, vis_pos, dec_idx, dec_pos, unshuffle = [], [], [], [], []
+        for g in range(G):
+            vis = [t for t in range(T) if not masks[g, t]]
+            msk = [t for t in range(T) if masks[g, t]]
+            vis_idx += [g * T + t for t in vis]
+            dec_idx += [g * n_vis + j for j in range(n_vis)] + [-1] * len(msk)
+            dec_pos += vis + msk
+            slot = {t: j for j, t in enumerate(vis + msk)}
+            unshuffle += [g * T + slot[t] for t in range(T)]
+        x = R.linear(tokens, mae.encoder.patch_embed)
+        x = ops.Add.apply(x, self._pos_rows(list(range(T)) * G, dev))
+        x = R.RowsGather.apply(x, self._idx(vis_idx, dev), None)                       # x[~mask]
+        x = self._block(x, mae.encoder.blocks[0], G, n_vis)
+        x = R.linear(R.layernorm(x, mae.encoder.norm), mae.encoder_to_decoder)
+        # decoder input: visible tokens first, then mask tokens, each plus its own position row
+        x = R.RowsGather.apply(x, self._idx(dec_idx, dev), mae.mask_token if n_vis < T else None)
+        x = ops.Add.apply(x, self._pos_rows(dec_pos, dev))
+        x = self._block(x, mae.decoder.blocks[0], G, T)
+        x = R.linear(R.layernorm(x, mae.decoder.norm), mae.decoder.head)
+        return R.RowsGather.apply(x, self._idx(unshuffle, dev), None)
+
+    def _mixer(self, x, G: int, T: int):
+        """MixerBlock (my_mae_model.py:345-369) on [G*T, C]: the same graph-mode LayerNorm twice, token mixing on
+        the per-patient transpose, channel mixing."""
+        C = x.shape[1]
+        mix = self.mix
+        y = R.graph_layernorm(x, mix.norm, G, T)
+        y = ops.ToNCHW.apply(y.reshape(G, T, 1, C)).reshape(G * C, T)                  # per-patient transpose
+        y = R.linear(R.gelu(R.linear(y, mix.mix_mip_1[0])), mix.mix_mip_1[2])
+        y = ops.ToNHWC.apply(y.reshape(G, C, T, 1), torch.float32).reshape(G * T, C)
+        x = ops.Add.apply(x, y)
+        y = R.graph_layernorm(x, mix.norm, G, T)
+        y = R.linear(R.gelu(R.linear(y, mix.mix_mip_2[0])), mix.mix_mip_2[2])
+        return ops.Add.apply(x, y)
+
+    def _pool(self, x, pool: my_GlobalAttention, G: int, seg: int):
+        gate = R.linear(ops.relu(R.linear(x, pool.gate_nn[0])), pool.gate_nn[2])
+        return R.GatePool.apply(x, gate, G, seg)
+
+    # ------------------------------------------------------------------ batched forward
+    def forward_batch(self, feats: Dict[str, torch.Tensor], edges: Dict[str, torch.Tensor],
+                      train_use_type: Sequence[str], use_type: Optional[Sequence[str]] = None,
+                      masks: Optional[np.ndarray] = None, mix: bool = True) -> Dict[str, torch.Tensor]:
+        """feats[m]: fp32 ``[G, nodes_m, in_feats]`` on the device; edges[m]: ``[2, E]`` topology shared by all
+        patients; masks: bool ``[G, T]`` over ``train_use_type`` (True = masked), None = nothing masked.
+        Returns a dict of batched tensors: logits_all / logits_<m> ``[G, 4]``, one_x ``[G, 8]``, multi_x
+        ``[G, T', 8]``, fea ``[G, T', 512]``, mae_out / mae_labels, att_2 / att_3 (lists of ``[G, nodes]``)."""
+        train_use_type = list(train_use_type)
+        use_type = list(train_use_type if use_type is None else use_type)
+        Tt = len(train_use_type)
+        present = [m for m in MODALITIES if m in use_type]
+        G = int(feats[present[0]].shape[0])
+        dev = feats[present[0]].device
+        C = self.hidden
+        nodes, seg, pooled, att_2 = {}, {}, [], []
+        for m in present:
+            x = feats[m].contiguous().float()
+            seg[m] = int(x.shape[1])
+            x = x.reshape(G * seg[m], x.shape[2])
+            conv = getattr(self, m + "_gnn_2")
+            agg = R.GraphMean.apply(x, self._topology(edges[m], seg[m], dev), G)
+            x = ops.Add.apply(R.linear(agg, conv.lin_l), R.linear(x, conv.lin_r))
+            x = R.graph_layernorm(ops.relu(x), getattr(self, m + "_relu_2")[1], G, seg[m])
+            x = self._drop(x, getattr(self, m + "_relu_2")[2].p)
+            nodes[m] = x
+            px, att = self._pool(x, getattr(self, "mpool_" + m), G, seg[m])
+            pooled.append(px.reshape(G, 1, 1, C)); att_2.append(att.reshape(G, seg[m]))
+        pool_x = (ops.cat_channels(pooled) if len(pooled) > 1 else pooled[0]).reshape(G * len(present), C)
+        out = {"mae_labels": pool_x.reshape(G, len(present), C), "att_2": att_2}
+        if Tt > 1:
+            if use_type == train_use_type:
+                mk = np.zeros((G, Tt), dtype=bool) if masks is None else np.asarray(masks, dtype=bool).reshape(G, Tt)
+                tokens = pool_x
+            else:
+                # inference with missing modalities (my_mae_model.py:597-612): absent tokens are zero and masked
+                slot, k = [], 0
+                mk = np.ones((G, Tt), dtype=bool)
+                for i, m in enumerate(train_use_type):
+                    if m in use_type:
+                        slot.append(k); k += 1; mk[:, i] = False
+                    else:
+                        slot.append(-1)
+                if k == 0:
+                    mk[:] = False
+                idx = [(-1 if s < 0 else g * len(present) + s) for g in range(G) for s in slot]
+                tokens = R.RowsGather.apply(pool_x, self._idx(idx, dev), None)
+            mae_x = self._mae(tokens, mk)
+            out["mae_out"] = mae_x.reshape(G, Tt, C)
+            out["after_mae"] = mae_x.reshape(G, Tt, C)
+            if mix:
+                mae_x = self._mixer(mae_x, G, Tt)
+                out["after_mix"] = mae_x.reshape(G, Tt, C)
+            for m in present:
+                if m in train_use_type:
+                    i = train_use_type.index(m)
+                    row = R.RowsGather.apply(mae_x, self._idx([g * Tt + i for g in range(G)], dev), None)
+                    nodes[m] = ops.Add.apply(nodes[m], ops.broadcast_hw(row.reshape(G, 1, 1, C), seg[m], 1)
+                                             .reshape(G * seg[m], C))
+        att_3, heads, feas, logits = [], [], [], {}
+        for m in present:
+            px, att = self._pool(nodes[m], getattr(self, "mpool_" + m + "_2"), G, seg[m])
+            att_3.append(att.reshape(G, seg[m]))
+            f = R.L2Norm.apply(px)                                                     # F.normalize(dim=1) is row-wise
+            feas.append(f.reshape(G, 1, 1, C))
+            v = R.graph_layernorm(ops.relu(R.linear(f, getattr(self, "lin1_" + m))), getattr(self, "norm1_" + m), G, 1)
+            v = self._drop(v, self.dropout.p)
+            v = R.graph_layernorm(ops.relu(R.linear(v, getattr(self, "lin2_" + m))), getattr(self, "norm2_" + m), G, 1)
+            v = self._drop(v, self.dropout.p)
+            v = R.linear(v, getattr(self, "lin3_" + m))
+            logits[m] = R.linear(v, getattr(self, "classifier_" + m))
+            heads.append(v.reshape(G, 1, 1, v.shape[1]))
+        K = heads[0].shape[3]
+        P = len(present)
+        multi_x = (ops.cat_channels(heads) if P > 1 else heads[0]).reshape(G, P, 1, K)
+        one_x = ops.global_avg_pool(multi_x).reshape(G, K) if P > 1 else multi_x.reshape(G, K)
+        out.update(one_x=one_x, multi_x=multi_x.reshape(G, P, K), logits_all=R.linear(one_x, self.classifier),
+                   att_3=att_3, fea=(ops.cat_channels(feas) if P > 1 else feas[0]).reshape(G, P, C), present=present)
+        for m in present:
+            out["logits_" + m] = logits[m]
+        return out
+
+    # ------------------------------------------------------------------ reference signature (one patient)
+    def forward(self, all_thing, train_use_type=None, use_type=None, in_mask=[], mix=True):
+        get = (lambda k: all_thing[k]) if isinstance(all_thing, dict) else (lambda k: getattr(all_thing, k))
+        train_use_type = list(train_use_type)
+        use_type = list(train_use_type if use_type is None else use_type)
+        dev = self.classifier.weight.device
+        feats = {m: torch.as_tensor(get("x_" + m)).to(dev).unsqueeze(0) for m in MODALITIES if m in use_type}
+        edges = {m: get(_EDGE_ATTR[m]) for m in MODALITIES if m in use_type}
+        masks = None if len(in_mask) == 0 else np.asarray(in_mask, dtype=bool).reshape(1, -1)
+        o = self.forward_batch(feats, edges, train_use_type, use_type, masks, mix)
+        save_fea, fea_dict = {}, {"mae_labels": o["mae_labels"][0]}
+        if "mae_out" in o:
+            fea_dict["mae_out"] = o["mae_out"][0]
+            save_fea["after_mae"] = o["after_mae"][0].detach().cpu().numpy()
+            if "after_mix" in o:
+                save_fea["after_mix"] = o["after_mix"][0].detach().cpu().numpy()
+        for k, m in enumerate(o["present"]):
+            fea_dict[m] = o["fea"][0, k]
+        lg = {m: (o["logits_" + m][0] if m in o["present"] else None) for m in MODALITIES}
+        att_2 = [a.reshape(-1, 1) for a in o["att_2"]]
+        att_3 = [a.reshape(-1, 1) for a in o["att_3"]]
+        return ((o["one_x"][0], o["multi_x"][0]), save_fea, (att_2, att_3), fea_dict, o["logits_all"][0],
+                lg["imgN"], lg["imgA"], lg["imgL"], lg["cli"])
+
+
+# ----------------------------------------------------------------------------- objective + train step
+MODALITY_LOSS_WEIGHT = {"imgN": 0.3, "imgA": 0.3, "imgL": 0.3, "cli": 0.2}
+
+
+def fusion_objective(out: Dict[str, torch.Tensor], labels: torch.Tensor, masks: np.ndarray, mse_factor: float = 5.0):
+    """my_train(full).py:309-347 for a batch of G patients: CE(all) + 0.3 CE(img*) + 0.2 CE(cli) on the stacked
+    ``[G, 4]`` logits + sum_g mse_factor * MSE(mae_out[g][masked], pool_x[g][masked]) / G / 5."""
+    present = out["present"]
+    G, T, C = out["mae_out"].shape
+    masks = np.asarray(masks, dtype=bool).reshape(G, T)
+    n_masked = int(masks[0].sum())
+    sel = torch.from_numpy(masks.reshape(-1).astype(np.uint8)).to(labels.device)
+    logits = [out["logits_all"]] + [out["logits_" + m] for m in present]
+    weights = [1.0] + [MODALITY_LOSS_WEIGHT[m] for m in present]
+    inv_count = 1.0 / max(n_masked * C, 1)
+    return R.FusionObjective.apply(labels, sel, weights, mse_factor / G / 5.0, inv_count,
+                                   out["mae_out"].reshape(G * T, C), out["mae_labels"].reshape(G * T, C), *logits)
+
+
+def generate_mask(num=3):
+    """mae_utils.py:11-21: exactly one visible modality; shape [1,1,num] bool (True = masked)."""
+    mask = np.hstack([np.zeros(1, dtype=bool), np.ones(num - 1, dtype=bool)])
+    np.random.shuffle(mask)
+    return mask[None, None, :]
+
+
+def get_edge_index_image():
+    """4x4 patch grid, 8-neighbourhood, both directions (Graph_Structure(data_augmentation).py:338-355) -> [2, 84]."""
+    start, end = [], []
+    for pos in range(16):
+        r, c = divmod(pos, 4)
+        for rr in range(max(r - 1, 0), min(r + 2, 4)):
+            for cc in range(max(c - 1, 0), min(c + 2, 4)):
+                if (rr, cc) != (r, c):
+                    start.append(pos); end.append(rr * 4 + cc)
+    return torch.tensor([start, end], dtype=torch.long)
+
+
+def get_edge_index_full(n=4):
+    """complete digraph on the clinical nodes (util.py:69-77, Graph_Structure...py:367-376) -> [2, n(n-1)]."""
+    start, end = [], []
+    for i in range(n):
+        for j in range(n):
+            if i != j:
+                start.append(j); end.append(i)
+    return torch.tensor([start, end], dtype=torch.long)

@@ -149,13 +149,14 @@ class RowsGather(Function):
     def forward(ctx, x, idx, fill):
         ctx.save_for_backward(idx)
         ctx.src_rows, ctx.has_fill = x.shape[0], fill is not None
+        ctx.fill_shape = None if fill is None else fill.shape
         return get_backend().rows_gather(x.contiguous(), idx, None if fill is None else fill.detach().contiguous().reshape(-1))
 
     @staticmethod
     def backward(ctx, dy):
         (idx,) = ctx.saved_tensors
         dx, dfill = get_backend().rows_scatter_add(dy.contiguous(), idx, ctx.src_rows, ctx.has_fill)
-        return dx, None, dfill
+        return dx, None, (None if dfill is None else dfill.reshape(ctx.fill_shape))
 
 
 class FusionObjective(Function):

@@ -1,0 +1,195 @@
+"""GPU parity tests of the multimodal fusion head through the C ABI:
+  * every row operator of csrc/rowops.cu against its plain-torch specification (tests/emu_backend.py);
+  * the whole head (forward, objective, gradients) against the golden vectors of the reference's unmodified model;
+  * size-independent properties: a batch of G patients equals G single-patient calls; permuting the patients
+    permutes the outputs; dropout in training mode keeps the expectation."""
+import numpy as np
+import pytest
+import torch
+
+from cervix_b200.backend import get_backend
+from cervix_b200.multimodal import rowops as R
+from cervix_b200.multimodal.my_mae_model import (fusion_model_mae_2, fusion_objective, generate_mask,
+                                                 get_edge_index_full, get_edge_index_image)
+from oracle import fusion_ref as FR
+from tests import fusion_cases as FC
+from tests.emu_backend import EmuBackend
+
+pytestmark = pytest.mark.gpu
+EMU = EmuBackend()
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(shape, generator=g, device="cuda") * scale
+
+
+def close(a, b, tol=1e-5):
+    err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+    assert err < tol, err
+
+
+@pytest.mark.parametrize("groups,seg,c,mode", [(5, 16, 512, 0), (7, 4, 512, 0), (9, 1, 128, 0), (3, 1, 32, 0),
+                                               (11, 1, 512, 1), (1, 4, 512, 0)])
+def test_seg_layernorm(groups, seg, c, mode):
+    B = get_backend()
+    x, w, b, dy = rnd(groups * seg, c, seed=1), rnd(c, seed=2) + 1, rnd(c, seed=3), rnd(groups * seg, c, seed=4)
+    y, stats = B.seg_layernorm_fwd(x, w, b, groups, seg, 1e-5, mode)
+    yr, _ = EMU.seg_layernorm_fwd(x, w, b, groups, seg, 1e-5, mode)
+    close(y, yr)
+    dx, dw, db = B.seg_layernorm_bwd(dy, x, w, stats, groups, seg, 1e-5, mode)
+    dxr, dwr, dbr = EMU.seg_layernorm_bwd(dy, x, w, None, groups, seg, 1e-5, mode)
+    close(dx, dxr, 2e-5); close(dw, dwr, 2e-5); close(db, dbr, 2e-5)
+
+
+def test_gelu():
+    B = get_backend()
+    x, dy = rnd(37, 2048, seed=5, scale=2.0), rnd(37, 2048, seed=6)
+    close(B.gelu_fwd(x), EMU.gelu_fwd(x)); close(B.gelu_bwd(dy, x), EMU.gelu_bwd(dy, x))
+
+
+@pytest.mark.parametrize("nodes,edges", [(16, "image"), (4, "full")])
+def test_graph_mean_aggregation(nodes, edges):
+    ei = get_edge_index_image() if edges == "image" else get_edge_index_full(4)
+    assert torch.equal(ei, FR.image_edge_index() if edges == "image" else FR.cli_edge_index())
+    topo = R.GraphTopology(ei, nodes, torch.device("cuda"))
+    G, C = 6, 1024
+    x = rnd(G * nodes, C, seed=7).requires_grad_(True)
+    y = R.GraphMean.apply(x, topo, G)
+    dy = rnd(G * nodes, C, seed=8)
+    y.backward(dy)
+    # specification: SAGEConv's mean over in-neighbours (oracle/fusion_ref.py: sage_conv)
+    xr = x.detach().cpu().reshape(G, nodes, C).clone().requires_grad_(True)
+    outs = []
+    for g in range(G):
+        agg = torch.zeros(nodes, C).index_add(0, ei[1], xr[g][ei[0]])
+        deg = torch.zeros(nodes).index_add(0, ei[1], torch.ones(ei.shape[1]))
+        outs.append(agg / deg.clamp_min(1)[:, None])
+    yr = torch.stack(outs).reshape(G * nodes, C)
+    yr.backward(dy.cpu())
+    close(y.detach().cpu(), yr.detach()); close(x.grad.cpu(), xr.grad.reshape(G * nodes, C))
+
+
+@pytest.mark.parametrize("groups,seg", [(8, 16), (5, 4), (3, 1)])
+def test_gate_pool(groups, seg):
+    B = get_backend()
+    x, gate, dp = rnd(groups * seg, 512, seed=9), rnd(groups * seg, seed=10, scale=3.0), rnd(groups, 512, seed=11)
+    p, a = B.gate_pool_fwd(x, gate, groups, seg)
+    pr, ar = EMU.gate_pool_fwd(x, gate, groups, seg)
+    close(p, pr); close(a, ar)
+    dx, dg = B.gate_pool_bwd(dp, x, a, groups, seg)
+    dxr, dgr = EMU.gate_pool_bwd(dp, x, ar, groups, seg)
+    close(dx, dxr); close(dg, dgr, 5e-5)
+
+
+@pytest.mark.parametrize("b,n,h,d", [(6, 1, 12, 42), (6, 4, 8, 64), (3, 3, 12, 42), (2, 2, 8, 64), (1, 8, 4, 16)])
+def test_attention_small(b, n, h, d):
+    B = get_backend()
+    qkv, do = rnd(b * n, 3 * h * d, seed=12), rnd(b, n, h * d, seed=13)
+    out, probs = B.attn_small_fwd(qkv, b, n, h, d, d ** -0.5, 0.0, 0)
+    outr, probsr = EMU.attn_small_fwd(qkv, b, n, h, d, d ** -0.5, 0.0, 0)
+    close(out, outr); close(probs, probsr)
+    close(B.attn_small_bwd(do, qkv, probs, b, n, h, d, d ** -0.5, 0.0, 0),
+          EMU.attn_small_bwd(do, qkv, probsr, b, n, h, d, d ** -0.5, 0.0, 0).reshape(b * n, -1), 5e-5)
+
+
+def test_attention_dropout_statistics():
+    """attn-drop 0.3 (my_mae_model.py:236): dropped probabilities are exactly zero, kept ones scaled by 1/(1-p), the
+    backward uses the same mask (gradient of a dropped entry is zero => d(out)/d(v) matches probs)."""
+    B = get_backend()
+    b, n, h, d = 64, 4, 8, 64
+    qkv = rnd(b * n, 3 * h * d, seed=14)
+    _, clean = B.attn_small_fwd(qkv, b, n, h, d, d ** -0.5, 0.0, 0)
+    out, probs = B.attn_small_fwd(qkv, b, n, h, d, d ** -0.5, 0.3, 1234)
+    kept = probs != 0
+    frac = float(kept.float().mean())
+    assert abs(frac - 0.7) < 0.03, frac
+    close(probs[kept], clean[kept] / 0.7)
+    _, probs2 = B.attn_small_fwd(qkv, b, n, h, d, d ** -0.5, 0.3, 1234)
+    assert torch.equal(probs, probs2)                        # same seed -> same mask
+    v = qkv.reshape(b, n, 3, h, d)[:, :, 2].permute(0, 2, 1, 3)
+    close(out, (probs @ v).transpose(1, 2).reshape(b, n, h * d))
+
+
+def test_l2norm_rows_losses():
+    B = get_backend()
+    x, dy = rnd(9, 512, seed=15), rnd(9, 512, seed=16)
+    y, nrm = B.l2norm_fwd(x)
+    yr, nr = EMU.l2norm_fwd(x)
+    close(y, yr); close(nrm, nr); close(B.l2norm_bwd(dy, y, nrm), EMU.l2norm_bwd(dy, yr, nr))
+    idx = torch.tensor([3, -1, 0, 8, -1, 3, 2], dtype=torch.int32, device="cuda")
+    fill = rnd(512, seed=17)
+    assert torch.equal(B.rows_gather(x, idx, fill), EMU.rows_gather(x, idx, fill))
+    assert torch.equal(B.rows_gather(x, idx, None), EMU.rows_gather(x, idx, None))
+    d7 = rnd(7, 512, seed=18)
+    dx, dfill = B.rows_scatter_add(d7, idx, 9, True)
+    dxr, dfr = EMU.rows_scatter_add(d7, idx, 9, True)
+    close(dx, dxr); close(dfill, dfr)
+    logits = rnd(13, 4, seed=19, scale=2.0)
+    labels = torch.randint(0, 4, (13,), device="cuda")
+    l1, l2 = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    close(B.softmax_ce(logits, labels, l1, 0.3, True), EMU.softmax_ce(logits, labels, l2, 0.3, True)); close(l1, l2)
+    a, b = rnd(12, 512, seed=20), rnd(12, 512, seed=21)
+    sel = torch.tensor([1, 1, 1, 0] * 3, dtype=torch.uint8, device="cuda")
+    da, db = B.masked_mse(a, b, sel, l1, 0.125, 1.0 / (3 * 512), True)
+    dar, dbr = EMU.masked_mse(a, b, sel, l2, 0.125, 1.0 / (3 * 512), True)
+    close(da, dar); close(db, dbr); close(l1, l2)
+
+
+@pytest.mark.parametrize("tag", ["4modal", "3modal"])
+def test_head_matches_reference_golden(tag):
+    FC.check_batched(tag, torch.device("cuda"))
+    FC.check_single(tag, torch.device("cuda"))
+
+
+def test_missing_modality_inference():
+    FC.check_missing_modality(torch.device("cuda"))
+
+
+def _batch(G, seed0=100):
+    patients = [FR.synthetic_patient(seed0 + i) for i in range(G)]
+    return patients, FC.batch_of(patients, list(FR.MODALITIES), torch.device("cuda"))
+
+
+def test_batch_equals_single_patient_calls_and_is_permutation_equivariant():
+    """BASELINE configs[1] size (16 patients): patients are independent graphs, so the batched launch must equal
+    16 one-patient launches (PyG graph-mode LayerNorm keeps per-patient statistics) and commute with a shuffle."""
+    _, types, model = FC.build("4modal", torch.device("cuda"))
+    G = 16
+    patients, (feats, edges) = _batch(G)
+    np.random.seed(0)
+    masks = np.concatenate([generate_mask(4)[0] for _ in range(G)])
+    with torch.no_grad():
+        out = model.forward_batch(feats, edges, types, types, masks, True)
+        for g in (0, 5, 15):
+            one = model.forward_batch({m: v[g:g + 1] for m, v in feats.items()}, edges, types, types, masks[g:g + 1], True)
+            for k in ("logits_all", "one_x", "mae_out", "fea"):
+                close(out[k][g], one[k][0], 2e-5)
+        perm = torch.randperm(G, generator=torch.Generator().manual_seed(1))
+        outp = model.forward_batch({m: v[perm.cuda()].contiguous() for m, v in feats.items()}, edges, types, types,
+                                   masks[perm.numpy()], True)
+        close(outp["logits_all"], out["logits_all"][perm.cuda()], 2e-5)
+
+
+def test_train_step_with_dropout_decreases_loss():
+    """configs[1]: fp32 forward/backward of 16 patients with dropout + attention dropout on, Adam as in
+    my_train(full).py (lr 1e-4, wd 5e-4): the objective is finite and falls when the same batch is revisited."""
+    torch.manual_seed(0)
+    _, types, model = FC.build("4modal", torch.device("cuda"))
+    model.train()
+    G = 16
+    _, (feats, edges) = _batch(G, 300)
+    labels = torch.randint(0, 4, (G,), generator=torch.Generator().manual_seed(2)).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=5e-4)
+    np.random.seed(1)
+    losses = []
+    for _ in range(12):
+        masks = np.concatenate([generate_mask(4)[0] for _ in range(G)])
+        out = model.forward_batch(feats, edges, types, types, masks, True)
+        loss = fusion_objective(out, labels, masks)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses)), losses
+    assert np.mean(losses[-3:]) < np.mean(losses[:3]), losses
