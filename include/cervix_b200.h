@@ -168,6 +168,55 @@ CVX_API int cvx_seg_loss_grad(const float* logits, const int64_t* target, const 
                       int n, int c, int h, int w, float focal_alpha, float focal_gamma,
                       float beta, float smooth, void* stream);
 
+/* ---- fused Xception separable-conv chain (bf16, training mode; xception.py:9-31,33-73) -----------------
+ * relu -> depthwise 3x3 -> bn1 -> pointwise 1x1 -> bn2 with NEITHER BatchNorm output materialised: bn1 is folded
+ * into the pointwise weights, bn2 is applied on load by its consumer (csrc/sepconv.cu has the algebra).
+ * All statistics buffers are fp64 [2][C] and are zeroed by the call that fills them. */
+/* cvx_conv_fwd_tc with epilogue extras: y = conv + bias[c] + side_scale[c]*side[row][c]; stats += (sum y, sum y^2) */
+CVX_API int cvx_conv_fwd_tc_ex(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                       const void* side, const float* side_scale, double* stats, void* y, void* stream);
+/* cvx_conv_dgrad_tc with the same epilogue (side has the shape of dx) */
+CVX_API int cvx_conv_dgrad_tc_ex(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, const float* bias,
+                         const void* side, const float* side_scale, void* dx, void* stream);
+/* d = dw3x3(act(in_scale*x + in_shift)) (in_scale/in_shift nullable = identity; zero padding applies AFTER the
+ * affine), stats (nullable) += (sum d, sum d^2) */
+CVX_API int cvx_dwf_fwd(const cvx_conv_desc* d, const void* x, const float* w9c, const float* in_scale,
+                const float* in_shift, int relu_in, void* y, double* stats, void* stream);
+/* both gradients of that layer in one pass over (dd, x): g = dwT(dd') * 1[in_scale*x+in_shift > 0] (+ addend),
+ * dw9c fp32 [9][C] (ws: 9*C doubles), sums (nullable) += (sum g, sum g*x).  The incoming gradient is
+ * dd' = dd + negk*dside + kmean inside the image when dside/negk/kmean are given (bn1's backward applied on load:
+ * dd = the pointwise conv's data gradient, dside = this layer's forward output), else dd itself. */
+CVX_API int cvx_dwf_bwd(const cvx_conv_desc* d, const void* dd, const void* dside, const float* negk, const float* kmean,
+                const void* x, const float* w9c, const float* in_scale, const float* in_shift, int relu_in,
+                const void* addend, void* g, float* dw9c, double* ws, double* sums, void* stream);
+/* stats = (sum x, sum x^2) over the rows of a [rows][c] bf16 tensor */
+CVX_API int cvx_bn_stats(const void* x, double* stats, int64_t rows, int c, int dtype, void* stream);
+/* batch statistics -> mean, invstd, scale = gamma*invstd, shift = beta - mean*scale; running buffers (nullable)
+ * updated like nn.BatchNorm2d in training mode.  mean_offset (nullable): per-channel constant that was left out of
+ * the measured tensor (it only moves the running mean). */
+CVX_API int cvx_bn_affine(const double* stats, int64_t rows, const float* gamma, const float* beta, const float* mean_offset,
+                  float* running_mean, float* running_var, float* mean, float* invstd, float* scale, float* shift, int c,
+                  float momentum, float eps, void* stream);
+/* wp[o][i] = bf16(W[o][i]*scale[i]), wpt = wp^T, bias[o] = sum_i W[o][i]*shift[i]  (1x1 conv weight W fp32 [cout][cin]) */
+CVX_API int cvx_pw_fold(const float* w, const float* scale, const float* shift, void* wp, void* wpt, float* bias, int cout,
+                int cin, void* stream);
+/* y = act(scale*p + shift + res)  (res nullable) */
+CVX_API int cvx_affine_act(const void* p, const void* res, void* y, const float* scale, const float* shift, int64_t rows,
+                   int c, int act, void* stream);
+/* sums = (sum g, sum g*p) with g = dy * act'(y)  (y nullable when act == NONE) */
+CVX_API int cvx_bn_bwd_sums(const void* dy, const void* y, const void* p, double* sums, int64_t rows, int c, int act,
+                    void* stream);
+/* from those raw sums: dp = a*g + b*p + cc (BatchNorm backward as an affine map), dgamma, dbeta */
+CVX_API int cvx_bn_bwd_coef(const double* sums, int64_t rows, const float* mean, const float* invstd, const float* gamma,
+                    float* a, float* b, float* cc, float* dgamma, float* dbeta, int c, void* stream);
+CVX_API int cvx_bn_bwd_affine(const void* dy, const void* y, const void* p, const float* a, const float* b, const float* cc,
+                      void* dp, void* gout, int64_t rows, int c, int act, void* stream);
+/* bn1's backward from the pointwise weight gradient G [cout][cin] w.r.t. the un-normalised input: dw = G*scale,
+ * dgamma, dbeta (= 0), and the data-gradient epilogue vectors negk (side_scale) / kmean (bias).  colsum: cin floats. */
+CVX_API int cvx_pw_bwd_coef(const float* g_packed, const float* w, const float* scale, const float* invstd,
+                    const float* mean, int64_t rows, float* dw, float* colsum, float* dgamma, float* dbeta,
+                    float* negk, float* kmean, int cout, int cin, void* stream);
+
 /* ---- multimodal fusion head: fp32 row operators on [groups*seg, C] matrices ----------------------
  * (MultiModal Prediction/Four_Modal/my_mae_model.py:500-793; a "group" is one patient graph).
  * Linear layers use cvx_conv_fwd/dgrad/wgrad with a 1x1 geometry. */

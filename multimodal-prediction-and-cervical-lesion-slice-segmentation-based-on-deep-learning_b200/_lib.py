@@ -69,6 +69,18 @@ PROTOTYPES = {
     "cvx_seg_loss_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
     "cvx_seg_loss_finalize": [_P, _P, _I, _F, _F, _P],
     "cvx_seg_loss_grad": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P],
+    "cvx_conv_fwd_tc_ex": [_D, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cvx_conv_dgrad_tc_ex": [_D, _P, _P, _P, _P, _P, _P, _P],
+    "cvx_dwf_fwd": [_D, _P, _P, _P, _P, _I, _P, _P, _P],
+    "cvx_dwf_bwd": [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],
+    "cvx_bn_stats": [_P, _P, _L, _I, _I, _P],
+    "cvx_bn_affine": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _P],
+    "cvx_pw_fold": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "cvx_affine_act": [_P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "cvx_bn_bwd_sums": [_P, _P, _P, _P, _L, _I, _I, _P],
+    "cvx_bn_bwd_coef": [_P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "cvx_bn_bwd_affine": [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "cvx_pw_bwd_coef": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "cvx_seg_layernorm_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     "cvx_seg_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P],
     "cvx_gelu_fwd": [_P, _P, _L, _P],

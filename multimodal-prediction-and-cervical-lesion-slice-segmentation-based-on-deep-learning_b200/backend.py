@@ -491,6 +491,123 @@ class CudaBackend:
                                       float(inv_count), self._stream()), "cvx_masked_mse")
         return da, db
 
+    # ------------------------------------------------------------------ fused separable-conv chain (csrc/sepconv.cu)
+    def sepconv_fused_ok(self, x: torch.Tensor, cin: int, cout: int, stride: int, dil: int, pad: int) -> bool:
+        """The fused chain takes bf16 NHWC tensors, 3x3/stride 1/dilation 1/pad 1 depthwise, channel counts % 8."""
+        return (x.dtype == torch.bfloat16 and self.is_sm100() and stride == 1 and dil == 1 and pad == 1
+                and cin % 8 == 0 and cout % 8 == 0 and cout <= 2048)
+
+    @staticmethod
+    def _f32(n, dev):
+        return torch.empty((n,), dtype=torch.float32, device=dev)
+
+    def dwf_fwd(self, x, w9c, in_scale, in_shift, relu_in: bool, g: ConvGeom, want_stats: bool):
+        self._chk(x, w9c, in_scale, in_shift)
+        y = torch.empty_like(x)
+        stats = torch.empty((2, g.cin), dtype=torch.float64, device=x.device) if want_stats else None
+        d = g.desc(_dt(x))
+        check(self.lib.cvx_dwf_fwd(C.byref(d), _p(x), _p(w9c), _p(in_scale), _p(in_shift), int(relu_in), _p(y), _p(stats),
+                                   self._stream()), "cvx_dwf_fwd")
+        return y, stats
+
+    def dwf_bwd(self, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in: bool, addend, g: ConvGeom, want_sums: bool):
+        self._chk(dd, dside, negk, kmean, x, w9c, in_scale, in_shift, addend)
+        gout = torch.empty_like(x)
+        dw9c = torch.empty((9, g.cin), dtype=torch.float32, device=x.device)
+        ws = torch.empty((9, g.cin), dtype=torch.float64, device=x.device)
+        sums = torch.empty((2, g.cin), dtype=torch.float64, device=x.device) if want_sums else None
+        d = g.desc(_dt(x))
+        check(self.lib.cvx_dwf_bwd(C.byref(d), _p(dd), _p(dside), _p(negk), _p(kmean), _p(x), _p(w9c), _p(in_scale),
+                                   _p(in_shift), int(relu_in), _p(addend), _p(gout), _p(dw9c), _p(ws), _p(sums),
+                                   self._stream()), "cvx_dwf_bwd")
+        return gout, dw9c, sums
+
+    def bn_stats(self, x):
+        self._chk(x)
+        c = int(x.shape[-1])
+        stats = torch.empty((2, c), dtype=torch.float64, device=x.device)
+        check(self.lib.cvx_bn_stats(_p(x), _p(stats), x.numel() // c, c, _dt(x), self._stream()), "cvx_bn_stats")
+        return stats
+
+    def bn_affine(self, stats, rows: int, gamma, beta, rmean, rvar, momentum: float, eps: float, mean_offset=None):
+        self._chk(stats, gamma, beta, rmean, rvar, mean_offset)
+        c = int(gamma.shape[0])
+        out = torch.empty((4, c), dtype=torch.float32, device=gamma.device)      # mean, invstd, scale, shift
+        check(self.lib.cvx_bn_affine(_p(stats), rows, _p(gamma), _p(beta), _p(mean_offset), _p(rmean), _p(rvar), out[0].data_ptr(),
+                                     out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), c, float(momentum), float(eps),
+                                     self._stream()), "cvx_bn_affine")
+        return out[0], out[1], out[2], out[3]
+
+    def pw_fold(self, weight, scale, shift, dtype):
+        self._chk(weight, scale, shift)
+        cout, cin = int(weight.shape[0]), int(weight.shape[1])
+        wp = torch.empty((1, cout, cin), dtype=dtype, device=weight.device)
+        wpt = torch.empty((1, cin, cout), dtype=dtype, device=weight.device)
+        bias = self._f32(cout, weight.device)
+        check(self.lib.cvx_pw_fold(_p(weight), _p(scale), _p(shift), _p(wp), _p(wpt), _p(bias), cout, cin, self._stream()),
+              "cvx_pw_fold")
+        return wp, wpt, bias
+
+    def conv_fwd_ex(self, x, wp, bias, g: ConvGeom, side=None, side_scale=None, want_stats=False):
+        self._chk(x, wp, bias, side, side_scale)
+        y = torch.empty((g.n, g.ho, g.wo, g.cout), dtype=x.dtype, device=x.device)
+        stats = torch.empty((2, g.cout), dtype=torch.float64, device=x.device) if want_stats else None
+        d = g.desc(_dt(x))
+        check(self.lib.cvx_conv_fwd_tc_ex(C.byref(d), _p(x), _p(wp), _p(bias), _p(side), _p(side_scale), _p(stats), _p(y),
+                                          self._stream()), "cvx_conv_fwd_tc_ex")
+        return y, stats
+
+    def conv_dgrad_ex(self, dy, wpt, g: ConvGeom, bias=None, side=None, side_scale=None):
+        self._chk(dy, wpt, bias, side, side_scale)
+        dx = torch.empty((g.n, g.h, g.w, g.cin), dtype=dy.dtype, device=dy.device)
+        d = g.desc(_dt(dy))
+        check(self.lib.cvx_conv_dgrad_tc_ex(C.byref(d), _p(dy), _p(wpt), _p(bias), _p(side), _p(side_scale), _p(dx),
+                                            self._stream()), "cvx_conv_dgrad_tc_ex")
+        return dx
+
+    def affine_act(self, p, scale, shift, res, act: int):
+        self._chk(p, scale, shift, res)
+        c = int(p.shape[-1])
+        y = torch.empty_like(p)
+        check(self.lib.cvx_affine_act(_p(p), _p(res), _p(y), _p(scale), _p(shift), p.numel() // c, c, act, self._stream()),
+              "cvx_affine_act")
+        return y
+
+    def bn_bwd_sums(self, dy, y, p, act: int):
+        self._chk(dy, y, p)
+        c = int(p.shape[-1])
+        sums = torch.empty((2, c), dtype=torch.float64, device=p.device)
+        check(self.lib.cvx_bn_bwd_sums(_p(dy), _p(y), _p(p), _p(sums), p.numel() // c, c, act, self._stream()), "cvx_bn_bwd_sums")
+        return sums
+
+    def bn_bwd_coef(self, sums, rows: int, mean, invstd, gamma):
+        self._chk(sums, mean, invstd, gamma)
+        c = int(gamma.shape[0])
+        out = torch.empty((5, c), dtype=torch.float32, device=gamma.device)      # a, b, cc, dgamma, dbeta
+        check(self.lib.cvx_bn_bwd_coef(_p(sums), rows, _p(mean), _p(invstd), _p(gamma), out[0].data_ptr(), out[1].data_ptr(),
+                                       out[2].data_ptr(), out[3].data_ptr(), out[4].data_ptr(), c, self._stream()),
+              "cvx_bn_bwd_coef")
+        return out[0], out[1], out[2], out[3], out[4]
+
+    def bn_bwd_affine(self, dy, y, p, a, b, cc, act: int, want_g: bool):
+        self._chk(dy, y, p, a, b, cc)
+        c = int(p.shape[-1])
+        dp = torch.empty_like(p)
+        gout = torch.empty_like(p) if want_g else None
+        check(self.lib.cvx_bn_bwd_affine(_p(dy), _p(y), _p(p), _p(a), _p(b), _p(cc), _p(dp), _p(gout), p.numel() // c, c, act,
+                                         self._stream()), "cvx_bn_bwd_affine")
+        return dp, gout
+
+    def pw_bwd_coef(self, gp, weight, scale, invstd, mean, rows: int):
+        self._chk(gp, weight, scale, invstd, mean)
+        cout, cin = int(weight.shape[0]), int(weight.shape[1])
+        dw = torch.empty_like(weight)
+        out = torch.empty((5, cin), dtype=torch.float32, device=weight.device)   # colsum, dgamma, dbeta, negk, kmean
+        check(self.lib.cvx_pw_bwd_coef(_p(gp), _p(weight), _p(scale), _p(invstd), _p(mean), rows, _p(dw), out[0].data_ptr(),
+                                       out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), out[4].data_ptr(), cout, cin,
+                                       self._stream()), "cvx_pw_bwd_coef")
+        return dw, out[1], out[2], out[3], out[4]
+
     # ------------------------------------------------------------------ optimizer
     def adam_step(self, p, g, m, v, lr, beta1, beta2, eps, wd, step_t, grad_scale=1.0):
         self._chk(p, g, m, v)

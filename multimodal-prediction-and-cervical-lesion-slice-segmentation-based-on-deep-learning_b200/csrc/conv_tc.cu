@@ -100,6 +100,147 @@ struct TcFwdParams {
   int tile_n;                // output-channel tile (multiple of 16, <= 256), balanced over n_tiles
 };
 
+// Optional epilogue work of the forward / data-gradient kernels (persistent variants):
+//   y[row][c] = acc + bias[c] + side_scale[c] * side[row][c]          (bias, side nullable)
+//   stats[0][c] += sum_rows y ; stats[1][c] += sum_rows y^2           (of the bf16-rounded stored values; nullable)
+// The side term turns the data gradient of a pointwise conv into the gradient through the BatchNorm that preceded
+// it (sepconv.cu); the statistics feed the BatchNorm that follows the conv, saving one full read of y.
+struct TcEpi {
+  const float* bias;
+  const __nv_bfloat16* side;
+  const float* side_scale;
+  double* stats;
+};
+constexpr int kEpiMaxNTiles = 8;
+constexpr int kEpiStatsBytes = kEpiMaxNTiles * 256 * 2 * 4;  // per-CTA fp32 staging [n_tile][2][256]
+
+// transpose-reduce over a warp: on return v[0] of lane L holds sum_{lanes} v[L]
+__device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float a = v[i], b = v[i + off];
+      const float send = up ? a : b, keep = up ? b : a;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Drain this warp's 32 rows x tile_n columns of one accumulator: TMEM -> (+bias, +side) -> bf16 -> global.
+__device__ __forceinline__ void tc_epilogue_tile(const TcEpi& ep, uint32_t t_addr, int tile_n, int n0, int cout,
+                                                 bool row_ok, __nv_bfloat16* yrow, const __nv_bfloat16* srow,
+                                                 float* stats_sm, int lane) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < tile_n; c0 += 32) {
+    if (n0 + c0 >= cout) break;  // warp-uniform
+    uint4 sv[4];
+    if (ep.side) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = c0 + g * 8;
+        sv[g] = (row_ok && n0 + c < cout && c < tile_n) ? __ldg(reinterpret_cast<const uint4*>(srow + c))
+                                                        : make_uint4(0, 0, 0, 0);
+      }
+    }
+    uint32_t r[32];
+    tmem_ld32(t_addr + (uint32_t)c0, r);
+    tmem_ld_wait();
+    float vals[32];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int c = c0 + g * 8;
+      const bool ok = row_ok && n0 + c < cout && c < tile_n;
+      const uint32_t su[4] = {sv[g].x, sv[g].y, sv[g].z, sv[g].w};
+      uint32_t packed[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
+        if (ok) {
+          if (ep.bias) { v0 += __ldg(ep.bias + n0 + c + 2 * j); v1 += __ldg(ep.bias + n0 + c + 2 * j + 1); }
+          if (ep.side) {
+            v0 = fmaf(__ldg(ep.side_scale + n0 + c + 2 * j), __uint_as_float(su[j] << 16), v0);
+            v1 = fmaf(__ldg(ep.side_scale + n0 + c + 2 * j + 1), __uint_as_float(su[j] & 0xffff0000u), v1);
+          }
+        }
+        __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+        vals[g * 8 + 2 * j] = ok ? __uint_as_float(packed[j] << 16) : 0.f;
+        vals[g * 8 + 2 * j + 1] = ok ? __uint_as_float(packed[j] & 0xffff0000u) : 0.f;
+      }
+      if (ok) *reinterpret_cast<uint4*>(yrow + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    if (ep.stats) {
+      float sq[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sq[i] = vals[i] * vals[i];
+      warp_colsum32(vals, lane);
+      warp_colsum32(sq, lane);
+      const int c = c0 + lane;
+      if (n0 + c < cout && c < tile_n) {
+        atomicAdd(&stats_sm[c], vals[0]);
+        atomicAdd(&stats_sm[256 + c], sq[0]);
+      }
+    }
+  }
+}
+
+// lean epilogue of the plain (bias-only) kernels
+__device__ __forceinline__ void tc_epilogue_tile_plain(const float* __restrict__ bias, uint32_t t_addr, int tile_n, int n0,
+                                                       int cout, bool row_ok, __nv_bfloat16* yrow) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < tile_n; c0 += 32) {
+    if (n0 + c0 >= cout) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld32(t_addr + (uint32_t)c0, r);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = c0 + g * 8;
+        if (n0 + c < cout && c < tile_n) {
+          float bv[8];
+          if (bias) {
+            if ((reinterpret_cast<uintptr_t>(bias) & 15) == 0) {  // parameter views of a flat buffer may be unaligned
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + 4));
+              bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) bv[j] = __ldg(bias + n0 + c + j);
+            }
+          }
+          uint32_t packed[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
+            if (bias) { v0 += bv[2 * j]; v1 += bv[2 * j + 1]; }
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(yrow + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+      }
+    }
+  }
+}
+
+// flush the per-CTA statistics staging to the fp64 accumulators (called by the 128 epilogue threads)
+__device__ __forceinline__ void tc_epilogue_flush_stats(const TcEpi& ep, const float* stats_sm, int n_tiles, int tile_n,
+                                                        int cout, int epi_tid) {
+  epi_bar_sync();
+  for (int i = epi_tid; i < n_tiles * 512; i += 128) {
+    const float v = stats_sm[i];
+    if (v == 0.f) continue;
+    const int nt = i >> 9, which = (i >> 8) & 1, c = i & 255;
+    const int col = nt * tile_n + c;
+    if (c < tile_n && col < cout) atomicAdd(ep.stats + (size_t)which * cout + col, (double)v);
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(128) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                           const __grid_constant__ CUtensorMap tmap_w,
@@ -233,9 +374,10 @@ constexpr int kPBBytes = kPBN * 128;
 constexpr int kPStageBytes = kABytes + kPBBytes;
 
 
+template <bool EXTRA>
 __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __grid_constant__ CUtensorMap tmap_x,
                                                                         const __grid_constant__ CUtensorMap tmap_w,
-                                                                        const float* __restrict__ bias,
+                                                                        const TcEpi ep,
                                                                         __nv_bfloat16* __restrict__ y, TcFwdParams p,
                                                                         int n_tiles, int total_tiles) {
   extern __shared__ uint8_t smem_raw[];
@@ -329,6 +471,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
     }
   } else {
     const int lg = warp & 3;  // TMEM lane group this warp may access
+    const int epi_tid = threadIdx.x - 64;
+    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    if (EXTRA && ep.stats) {
+      for (int i = epi_tid; i < n_tiles * 512; i += 128) stats_sm[i] = 0.f;
+      epi_bar_sync();
+    }
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
       const int nt = tile % n_tiles;
@@ -340,39 +488,21 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
       const int row = lg * 32 + lane;
       const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
       const bool row_ok = oy < p.ho && ox < p.wo;
-      __nv_bfloat16* yrow = y + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
+      const size_t roff = (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
       const int acc = tcount & 1;
       mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.tile_n; c0 += 32) {
-        if (n0 + c0 >= p.cout) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_addr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = c0 + g * 8;
-            if (n0 + c < p.cout && c < p.tile_n) {
-              uint32_t packed[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
-                if (bias) { v0 += __ldg(bias + n0 + c + 2 * j); v1 += __ldg(bias + n0 + c + 2 * j + 1); }
-                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                packed[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(yrow + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
-          }
-        }
-      }
+      if (EXTRA)
+        tc_epilogue_tile(ep, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff, ep.side ? ep.side + roff : nullptr,
+                         stats_sm + nt * 512, lane);
+      else
+        tc_epilogue_tile_plain(ep.bias, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
     }
+    if (EXTRA && ep.stats) tc_epilogue_flush_stats(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
   }
   tc_fence_before();
   __syncthreads();
@@ -449,9 +579,10 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       : "memory");
 }
 
+template <bool EXTRA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, TcFwdParams p, int n_tiles,
+                        const TcEpi ep, __nv_bfloat16* __restrict__ y, TcFwdParams p, int n_tiles,
                         int m_tiles, int total_pair_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -556,6 +687,12 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   } else {
     const int lg = warp & 3;
     const uint32_t lead_tempty0 = map_to_cta(tempty0, 0);
+    const int epi_tid = threadIdx.x - 64;
+    float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+    if (EXTRA && ep.stats) {
+      for (int i = epi_tid; i < n_tiles * 512; i += 128) stats_sm[i] = 0.f;
+      epi_bar_sync();
+    }
     uint32_t tcount = 0;
     for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
       const int nt = pt % n_tiles;
@@ -569,39 +706,21 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int row = lg * 32 + lane;
       const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
       const bool row_ok = tile_ok && oy < p.ho && ox < p.wo;
-      __nv_bfloat16* yrow = y + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
+      const size_t roff = (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
       const int acc = tcount & 1;
       mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.tile_n; c0 += 32) {
-        if (n0 + c0 >= p.cout) break;
-        uint32_t r[32];
-        tmem_ld32(t_addr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = c0 + g * 8;
-            if (n0 + c < p.cout && c < p.tile_n) {
-              uint32_t packed[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
-                if (bias) { v0 += __ldg(bias + n0 + c + 2 * j); v1 += __ldg(bias + n0 + c + 2 * j + 1); }
-                __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-                packed[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(yrow + c) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-            }
-          }
-        }
-      }
+      if (EXTRA)
+        tc_epilogue_tile(ep, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff, ep.side ? ep.side + roff : nullptr,
+                         stats_sm + nt * 512, lane);
+      else
+        tc_epilogue_tile_plain(ep.bias, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8 * acc);
     }
+    if (EXTRA && ep.stats) tc_epilogue_flush_stats(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -964,7 +1083,8 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const float*
 
 // rows = output pixels [n,ho,wo] ; src = [n,hs,ws,cred] ; wp = [taps][ncol][cred]
 static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, int kh, int kw, int pad, int dil,
-                     const void* src, const void* wp, const float* bias, void* dst, cudaStream_t st, int stride = 1) {
+                     const void* src, const void* wp, const TcEpi& ep, void* dst, cudaStream_t st, int stride = 1) {
+  const float* bias = ep.bias;
   TcFwdParams p;
   p.n = n; p.ho = ho; p.wo = wo; p.cout = ncol; p.cin = cred; p.kh = kh; p.kw = kw; p.pad = pad; p.dil = dil;
   p.stride = stride;
@@ -985,17 +1105,22 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     CUtensorMap mx, mw;
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
     if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n >> 1)) return rc;
-    constexpr int smem = k2Stages * k2StageBytes + 1024 + 256;
+    constexpr int smem = k2Stages * k2StageBytes + 1024 + 256 + kEpiStatsBytes;
     static bool configured = false;
     if (!configured) {
-      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured = true;
     }
     const int n_tiles = (ncol + p.tile_n - 1) / p.tile_n;
     const int m_tiles = n * p.tiles_y * p.tiles_x;
     const int total = ((m_tiles + 1) / 2) * n_tiles;
     const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
-    conv_tc_fwd_2cta_kernel<<<2 * pairs, 192, smem, st>>>(mx, mw, bias, (__nv_bfloat16*)dst, p, n_tiles, m_tiles, total);
+    CVX_CHECK_ARG(!ep.stats || n_tiles <= kEpiMaxNTiles, "conv_tc: fused statistics need C_out <= %d", kEpiMaxNTiles * kPBN);
+    if (ep.side || ep.stats)
+      conv_tc_fwd_2cta_kernel<true><<<2 * pairs, 192, smem, st>>>(mx, mw, ep, (__nv_bfloat16*)dst, p, n_tiles, m_tiles, total);
+    else
+      conv_tc_fwd_2cta_kernel<false><<<2 * pairs, 192, smem, st>>>(mx, mw, ep, (__nv_bfloat16*)dst, p, n_tiles, m_tiles, total);
     CVX_LAUNCH_OK();
     return CVX_OK;
   }
@@ -1003,19 +1128,25 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     CUtensorMap mx, mw;
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh, CU_TENSOR_MAP_SWIZZLE_128B, stride)) return rc;
     if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n)) return rc;
-    constexpr int smem = kPStages * kPStageBytes + 1024 + 256;
+    constexpr int smem = kPStages * kPStageBytes + 1024 + 256 + kEpiStatsBytes;
     static bool configured = false;
     if (!configured) {
-      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured = true;
     }
     const int n_tiles = (ncol + p.tile_n - 1) / p.tile_n;
     const int total = n * p.tiles_y * p.tiles_x * n_tiles;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    conv_tc_fwd_persistent_kernel<<<grid, 192, smem, st>>>(mx, mw, bias, (__nv_bfloat16*)dst, p, n_tiles, total);
+    CVX_CHECK_ARG(!ep.stats || n_tiles <= kEpiMaxNTiles, "conv_tc: fused statistics need C_out <= %d", kEpiMaxNTiles * kPBN);
+    if (ep.side || ep.stats)
+      conv_tc_fwd_persistent_kernel<true><<<grid, 192, smem, st>>>(mx, mw, ep, (__nv_bfloat16*)dst, p, n_tiles, total);
+    else
+      conv_tc_fwd_persistent_kernel<false><<<grid, 192, smem, st>>>(mx, mw, ep, (__nv_bfloat16*)dst, p, n_tiles, total);
     CVX_LAUNCH_OK();
     return CVX_OK;
   }
+  CVX_CHECK_ARG(!ep.side && !ep.stats, "conv_tc: the legacy kernel (CERVIX_TC_V1) has no fused epilogue");
   const int bn = ncol <= 64 ? 64 : 128;
   CUtensorMap mx, mw;
   if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
@@ -1048,8 +1179,30 @@ int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w_packed,
                     void* stream) {
   if (int rc = tc_supported(d, "conv_fwd_tc", true)) return rc;
   CVX_CHECK_ARG(x && w_packed && y, "conv_fwd_tc: null pointer");
-  return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, bias, y,
+  const TcEpi ep{bias, nullptr, nullptr, nullptr};
+  return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, ep, y,
                    as_stream(stream), d->stride);
+}
+
+int cvx_conv_fwd_tc_ex(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* side,
+                       const float* side_scale, double* stats, void* y, void* stream) {
+  if (int rc = tc_supported(d, "conv_fwd_tc_ex", true)) return rc;
+  CVX_CHECK_ARG(x && w_packed && y && (!side || side_scale), "conv_fwd_tc_ex: null pointer");
+  if (stats) CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, as_stream(stream)));
+  const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, stats};
+  return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, ep, y,
+                   as_stream(stream), d->stride);
+}
+
+int cvx_conv_dgrad_tc_ex(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, const float* bias,
+                         const void* side, const float* side_scale, void* dx, void* stream) {
+  if (int rc = tc_supported(d, "conv_dgrad_tc_ex")) return rc;
+  CVX_CHECK_ARG(dy && w_packed_t && dx && (!side || side_scale), "conv_dgrad_tc_ex: null pointer");
+  const int pad_t = d->dil * (d->kh - 1) - d->pad;
+  CVX_CHECK_ARG(pad_t >= 0 && d->kh == d->kw, "conv_dgrad_tc_ex: unsupported padding/filter");
+  const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, nullptr};
+  return run_igemm(d->n, d->ho, d->wo, d->cout, d->h, d->w, d->cin, d->kh, d->kw, pad_t, d->dil, dy, w_packed_t, ep, dx,
+                   as_stream(stream));
 }
 
 int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream) {
@@ -1059,8 +1212,9 @@ int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_pack
   // padding dil*(k-1) - pad
   const int pad_t = d->dil * (d->kh - 1) - d->pad;
   CVX_CHECK_ARG(pad_t >= 0 && d->kh == d->kw, "conv_dgrad_tc: unsupported padding/filter");
-  return run_igemm(d->n, d->ho, d->wo, d->cout, d->h, d->w, d->cin, d->kh, d->kw, pad_t, d->dil, dy, w_packed_t,
-                   nullptr, dx, as_stream(stream));
+  const TcEpi ep{nullptr, nullptr, nullptr, nullptr};
+  return run_igemm(d->n, d->ho, d->wo, d->cout, d->h, d->w, d->cin, d->kh, d->kw, pad_t, d->dil, dy, w_packed_t, ep, dx,
+                   as_stream(stream));
 }
 
 int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream) {

@@ -18,7 +18,7 @@ import os
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import ops, ops_fused
 
 bn_mom = 0.0003
 
@@ -84,10 +84,26 @@ class Block(nn.Module):
         """inp: NHWC.  ``inp_is_relu`` says the producer already applied the ReLU that an
         identity-skip block performs in place on its input; ``relu_out`` asks this block to
         emit relu(out) because its only consumer is such an identity-skip block."""
+        fuse = os.environ.get("CERVIX_NO_FUSED_BLOCK") != "1"
+        seps = (self.sepconv1, self.sepconv2, self.sepconv3)
+        out_act = ops.ACT_RELU if relu_out else ops.ACT_NONE
+        if fuse and self.skip is None and inp_is_relu and ops_fused.chain_fusable(seps, inp):
+            # training-mode fast path: the whole block as one hand-scheduled chain of fused kernels
+            self.hook_layer = None
+            return ops_fused.sep_chain(seps, inp, None, True, out_act)
         if self.skip is not None:
             s = self.skip
             skip = ops.conv2d(inp, s.weight, None, s.stride[0], 0, 1)
             skip = ops.batchnorm_act(skip, self.skipbn, ops.ACT_NONE)
+            if fuse and ops_fused.chain_fusable(seps, inp):
+                self.hook_layer = None          # stride-1 block with a 1x1 skip (block20): all three fused
+                return ops_fused.sep_chain(seps, inp, skip, False, out_act)
+            if fuse and ops_fused.chain_fusable(seps[:2], inp):
+                # entry-flow blocks: the first two (full-resolution) separable convs fused, their pre-ReLU output
+                # materialised once (it is block2's low-level feature), the strided third one on the operator path
+                x = ops_fused.sep_chain(seps[:2], inp, None, False, ops.ACT_NONE)
+                self.hook_layer = x
+                return self.sepconv3(x, residual=skip, out_act=out_act)
         else:
             if not inp_is_relu:
                 inp = ops.relu(inp)

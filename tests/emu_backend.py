@@ -284,6 +284,116 @@ class EmuBackend:
         (gd[0] * ce + gd[1] * focal + gd[2] * dice).backward()
         return z.grad.float()
 
+    # ---- fused separable-conv chain (specification of csrc/sepconv.cu, dwconv_fused.cu, conv_tc.cu's TcEpi)
+    def sepconv_fused_ok(self, x, cin, cout, stride, dil, pad):
+        return stride == 1 and dil == 1 and pad == 1
+
+    @staticmethod
+    def _virt(x, in_scale, in_shift, relu_in):
+        v = _nchw(x)
+        if in_scale is not None:
+            v = v * in_scale.view(1, -1, 1, 1) + in_shift.view(1, -1, 1, 1)
+        return F.relu(v) if relu_in else v
+
+    @staticmethod
+    def _stats(y):
+        v = y.float().reshape(-1, y.shape[-1]).double()
+        return torch.stack([v.sum(0), (v * v).sum(0)])
+
+    def dwf_fwd(self, x, w9c, in_scale, in_shift, relu_in, g, want_stats):
+        v = self._virt(x, in_scale, in_shift, relu_in)
+        y = _nhwc(F.conv2d(v, self._dw_w(w9c), None, 1, 1, 1, groups=g.cin), x.dtype)
+        return y, (self._stats(y) if want_stats else None)
+
+    def dwf_bwd(self, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, want_sums):
+        v = self._virt(x, in_scale, in_shift, relu_in)
+        if dside is not None:     # bn1's backward applied on load (zero padding applies to the assembled gradient)
+            dd = (dd.float() + negk * dside.float() + kmean).to(torch.float32)
+        gx = torch.nn.grad.conv2d_input((g.n, g.cin, g.h, g.w), self._dw_w(w9c), _nchw(dd), 1, 1, 1, groups=g.cin)
+        if relu_in:
+            gx = gx * (v > 0)
+        gq = _nhwc(gx, x.dtype)
+        sums = None
+        if want_sums:
+            a = gq.float().reshape(-1, g.cin).double(); b = x.float().reshape(-1, g.cin).double()
+            sums = torch.stack([a.sum(0), (a * b).sum(0)])
+        dw = torch.nn.grad.conv2d_weight(v, (g.cin, 1, 3, 3), _nchw(dd), 1, 1, 1, groups=g.cin)
+        out = gq if addend is None else (gx + _nchw(addend)).permute(0, 2, 3, 1).contiguous().to(x.dtype)
+        return out, dw.reshape(g.cin, 9).t().contiguous(), sums
+
+    def bn_stats(self, x):
+        return self._stats(x)
+
+    def bn_affine(self, stats, rows, gamma, beta, rmean, rvar, momentum, eps, mean_offset=None):
+        mean = stats[0] / rows
+        var = (stats[1] / rows - mean * mean).clamp_min(0)
+        invstd = 1.0 / torch.sqrt(var + eps)
+        if rmean is not None:
+            unbiased = var * rows / (rows - 1) if rows > 1 else var
+            true_mean = mean if mean_offset is None else mean + mean_offset.double()
+            rmean.copy_(((1 - momentum) * rmean.double() + momentum * true_mean).float())
+            rvar.copy_(((1 - momentum) * rvar.double() + momentum * unbiased).float())
+        mean, invstd = mean.float(), invstd.float()
+        scale = gamma.float() * invstd
+        return mean, invstd, scale, beta.float() - mean * scale
+
+    def pw_fold(self, weight, scale, shift, dtype):
+        w = weight.float().reshape(weight.shape[0], weight.shape[1])
+        wp = (w * scale.view(1, -1)).to(dtype)
+        return wp.unsqueeze(0).contiguous(), wp.t().unsqueeze(0).contiguous(), w @ shift
+
+    def conv_fwd_ex(self, x, wp, bias, g, side=None, side_scale=None, want_stats=False):
+        y = F.conv2d(_nchw(x), self._unpack(wp, g), None if bias is None else bias.float(), g.stride, g.pad, g.dil)
+        if side is not None:
+            y = y + _nchw(side) * side_scale.view(1, -1, 1, 1)
+        y = _nhwc(y, x.dtype)
+        return y, (self._stats(y) if want_stats else None)
+
+    def conv_dgrad_ex(self, dy, wpt, g, bias=None, side=None, side_scale=None):
+        w = self._unpack_t(wpt, g)
+        dx = torch.nn.grad.conv2d_input((g.n, g.cin, g.h, g.w), w, _nchw(dy), g.stride, g.pad, g.dil)
+        if bias is not None:
+            dx = dx + bias.view(1, -1, 1, 1)
+        if side is not None:
+            dx = dx + _nchw(side) * side_scale.view(1, -1, 1, 1)
+        return _nhwc(dx, dy.dtype)
+
+    def affine_act(self, p, scale, shift, res, act):
+        v = p.float() * scale + shift
+        if res is not None:
+            v = v + res.float()
+        return self._act(v, act).to(p.dtype)
+
+    def _g(self, dy, y, act):
+        g = dy.float()
+        return g if act == 0 else g * self._mask(y.float(), act)
+
+    def bn_bwd_sums(self, dy, y, p, act):
+        g = self._g(dy, y, act).reshape(-1, p.shape[-1]).double()
+        return torch.stack([g.sum(0), (g * p.float().reshape(-1, p.shape[-1]).double()).sum(0)])
+
+    def bn_bwd_coef(self, sums, rows, mean, invstd, gamma):
+        sg, sgp = sums[0], sums[1]
+        mu, is_ = mean.double(), invstd.double()
+        dgam = is_ * (sgp - mu * sg)
+        sc = gamma.double() * is_
+        b = -sc * is_ * dgam / rows
+        return sc.float(), b.float(), (-sc * sg / rows - b * mu).float(), dgam.float(), sg.float()
+
+    def bn_bwd_affine(self, dy, y, p, a, b, cc, act, want_g):
+        g = self._g(dy, y, act)
+        dp = (a * g + b * p.float() + cc).to(p.dtype)
+        return dp, (g.to(p.dtype) if want_g else None)
+
+    def pw_bwd_coef(self, gp, weight, scale, invstd, mean, rows):
+        cout, cin = weight.shape[0], weight.shape[1]
+        G = gp.reshape(cout, cin).float()
+        w = weight.float().reshape(cout, cin)
+        colsum = (w * G).sum(0)
+        dgam = invstd * colsum
+        k = scale * invstd * dgam / rows
+        return (G * scale.view(1, -1)).reshape(weight.shape), dgam, torch.zeros_like(dgam), -k, k * mean
+
     # ---- fusion-head row operators
     @staticmethod
     def _ln(x, w, b, groups, seg, eps, mode):
