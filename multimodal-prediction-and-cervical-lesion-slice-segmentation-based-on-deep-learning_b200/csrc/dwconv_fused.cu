@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__
     load_row(1, 1);
 #pragma unroll 1
     for (int r3 = 0; r3 < kFY; r3 += 3) {
+      if (oy0 + r3 >= p.h) break;  // the rest of this tile lies below the image
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int r = r3 + j;
@@ -290,30 +291,61 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) cvalid[kw] = (ox - 1 + kw) >= 0 && (ox - 1 + kw) < p.w;
 
-    // the incoming gradient dd at halo-tile position (rr, cc)
-    auto load_dd = [&](int rr, int cc, bool valid, float (&out)[8]) {
-      unpack8f(*reinterpret_cast<const uint4*>(dd_s + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
-      if (SIDE) {
-        float dv[8];
-        unpack8f(*reinterpret_cast<const uint4*>(d_s + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), dv);
+    if (SIDE) {
+      // ---- pre-pass, all 256 threads: assemble each halo element ONCE instead of once per tap and per role:
+      //   dd  = e + negk*d + kmean  (bn1's backward)          -> written over the e tile
+      //   xin = act(in_scale*x + in_shift)  (virtual input)   -> written over the d tile
+      // both zero outside the image; thread t always handles channel vector t & 7 (= cv).
+      uint8_t* e_w = smem + s * kStage;
+      uint8_t* d_w = e_w + 2 * kFTile;
+      const int ox0 = tx * kFX;
+      for (int v = t; v < (kFY + 2) * (kFX + 2) * 8; v += 256) {
+        const int pix = v >> 3;
+        const int rr = pix / (kFX + 2), cc = pix - rr * (kFX + 2);
+        const int iy = oy0 - 1 + rr, ix = ox0 - 1 + cc;
+        if (iy > p.h) break;  // rows below the image feed nothing (warp-uniform up to the last partial row)
+        const bool valid = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+        const int off = (pix * 64 + cv * 8) * 2;
+        float ev[8], dv[8], xv[8];
+        unpack8f(*reinterpret_cast<const uint4*>(e_w + off), ev);
+        unpack8f(*reinterpret_cast<const uint4*>(d_w + off), dv);
+        unpack8f(*reinterpret_cast<const uint4*>(x_s + off), xv);
+        uint32_t pd[4], px[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) out[e] = valid ? fmaf(nk[e], dv[e], out[e] + km[e]) : 0.f;
+        for (int e2 = 0; e2 < 4; ++e2) {
+          float a0 = fmaf(nk[2 * e2], dv[2 * e2], ev[2 * e2] + km[2 * e2]);
+          float a1 = fmaf(nk[2 * e2 + 1], dv[2 * e2 + 1], ev[2 * e2 + 1] + km[2 * e2 + 1]);
+          float b0 = AFFINE ? fmaf(xv[2 * e2], sc[2 * e2], sh[2 * e2]) : xv[2 * e2];
+          float b1 = AFFINE ? fmaf(xv[2 * e2 + 1], sc[2 * e2 + 1], sh[2 * e2 + 1]) : xv[2 * e2 + 1];
+          if (relu) { b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f); }
+          __nv_bfloat162 hd = __floats2bfloat162_rn(valid ? a0 : 0.f, valid ? a1 : 0.f);
+          __nv_bfloat162 hx = __floats2bfloat162_rn(valid ? b0 : 0.f, valid ? b1 : 0.f);
+          pd[e2] = *reinterpret_cast<uint32_t*>(&hd);
+          px[e2] = *reinterpret_cast<uint32_t*>(&hx);
+        }
+        *reinterpret_cast<uint4*>(e_w + off) = make_uint4(pd[0], pd[1], pd[2], pd[3]);
+        *reinterpret_cast<uint4*>(d_w + off) = make_uint4(px[0], px[1], px[2], px[3]);
       }
+      __syncthreads();
+    }
+    const uint8_t* xin_s = d_s;  // SIDE only: the transformed input tile
+
+    auto load_plain = [&](const uint8_t* tile, int rr, int cc, float (&out)[8]) {
+      unpack8f(*reinterpret_cast<const uint4*>(tile + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
     };
 
     float win[3][3][8];
     if (role == 0) {
       // ---- data gradient: g = sum_k dd[shifted] * w[8-k], masked by the ReLU of the (virtual) input
       auto load_row = [&](int slot, int rr) {
-        const int iy = oy0 - 1 + rr;
-        const bool rvalid = iy >= 0 && iy < p.h;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) load_dd(rr, col + kw, rvalid && cvalid[kw], win[slot][kw]);
+        for (int kw = 0; kw < 3; ++kw) load_plain(dd_s, rr, col + kw, win[slot][kw]);
       };
       load_row(0, 0);
       load_row(1, 1);
 #pragma unroll 1
       for (int r3 = 0; r3 < kFY; r3 += 3) {
+        if (oy0 + r3 >= p.h) break;  // the rest of this tile lies below the image
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const int r = r3 + j;
@@ -331,10 +363,17 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
             for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
               for (int e = 0; e < 8; ++e) acc[e] = fmaf(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
-          unpack8f(*reinterpret_cast<const uint4*>(x_s + (((r + 1) * (kFX + 2) + col + 1) * 64 + cv * 8) * 2), xc);
+          load_plain(x_s, r + 1, col + 1, xc);
           if (relu) {
+            if (SIDE) {
+              float xt[8];
+              load_plain(xin_s, r + 1, col + 1, xt);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(xc[e], sc[e], sh[e]) > 0.f ? acc[e] : 0.f;
+              for (int e = 0; e < 8; ++e) acc[e] = xt[e] > 0.f ? acc[e] : 0.f;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[e] = fmaf(xc[e], sc[e], sh[e]) > 0.f ? acc[e] : 0.f;
+            }
           }
           if (out_ok) {
             float av[8];
@@ -364,19 +403,22 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
         const int iy = oy0 - 1 + rr;
         const bool rvalid = iy >= 0 && iy < p.h;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          load_virtual<AFFINE>(x_s, rr, col + kw, cv, sc, sh, relu, rvalid && cvalid[kw], win[slot][kw]);
+        for (int kw = 0; kw < 3; ++kw) {
+          if (SIDE) load_plain(xin_s, rr, col + kw, win[slot][kw]);
+          else load_virtual<AFFINE>(x_s, rr, col + kw, cv, sc, sh, relu, rvalid && cvalid[kw], win[slot][kw]);
+        }
       };
       load_row(0, 0);
       load_row(1, 1);
 #pragma unroll 1
       for (int r3 = 0; r3 < kFY; r3 += 3) {
+        if (oy0 + r3 >= p.h) break;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const int r = r3 + j;
           load_row((j + 2) % 3, r + 2);
           float gv[8];  // dd at the output pixel: zero outside the image / channel range
-          load_dd(r + 1, col + 1, (oy0 + r) < p.h && ox < p.w, gv);
+          load_plain(dd_s, r + 1, col + 1, gv);
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
