@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
 // single-CTA kernel's (A: 4 KB + B: 4 KB per 128x256x16 half-MMA), which lifts the smem-bandwidth
 // ceiling that bounds the 1-CTA kernel at ~70 % of the tensor peak, and every weight tile is
 // fetched from L2 once per pair instead of once per CTA.
-constexpr int k2Stages = 6;
+constexpr int k2Stages = 5;
 constexpr int k2BBytes = 128 * 128;                 // half of a 256-row weight tile
 constexpr int k2StageBytes = kABytes + k2BBytes;    // 32 KB
 
@@ -579,14 +579,76 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
       : "memory");
 }
 
+// ---- TMA store helpers (epilogue staging -> global, clipped to the tensor bounds by the hardware)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+constexpr int kEpiBufBytes = 128 * 128;  // one 128-pixel x 64-channel bf16 chunk, SWIZZLE_128B rows
+
+// 32 accumulator columns of one row -> (+bias, +side) -> 16 packed bf16 pairs; `vals` receives the rounded values
+// (zero where the column is outside the tensor) when statistics are wanted.
+template <bool EXTRA>
+__device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&r)[32], int col0, int cout, bool row_ok,
+                                              const __nv_bfloat16* srow, uint32_t (&packed)[16], float (&vals)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int c = col0 + g * 8;          // absolute output channel of this group of 8
+    const bool ok = c < cout;             // cout % 8 == 0: whole groups are in or out
+    float bv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bv[j] = 0.f;
+    if (ep.bias && ok) {
+      if ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) {  // parameter views of a flat buffer may be unaligned
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + 4));
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = __ldg(ep.bias + c + j);
+      }
+    }
+    float sd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sd[j] = 0.f;
+    if (EXTRA && ep.side && ok && row_ok) {
+      const uint4 sv = __ldg(reinterpret_cast<const uint4*>(srow + c));
+      const uint32_t su[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sd[2 * j] = __ldg(ep.side_scale + c + 2 * j) * __uint_as_float(su[j] << 16);
+        sd[2 * j + 1] = __ldg(ep.side_scale + c + 2 * j + 1) * __uint_as_float(su[j] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = __uint_as_float(r[g * 8 + 2 * j]) + bv[2 * j] + sd[2 * j];
+      const float v1 = __uint_as_float(r[g * 8 + 2 * j + 1]) + bv[2 * j + 1] + sd[2 * j + 1];
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
+      packed[g * 4 + j] = u;
+      if (EXTRA) {
+        vals[g * 8 + 2 * j] = (ok && row_ok) ? __uint_as_float(u << 16) : 0.f;
+        vals[g * 8 + 2 * j + 1] = (ok && row_ok) ? __uint_as_float(u & 0xffff0000u) : 0.f;
+      }
+    }
+  }
+}
+
 template <bool EXTRA>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                        const TcEpi ep, __nv_bfloat16* __restrict__ y, TcFwdParams p, int n_tiles,
+                        const __grid_constant__ CUtensorMap tmap_y, const TcEpi ep, TcFwdParams p, int n_tiles,
                         int m_tiles, int total_pair_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint8_t* epi_buf = smem + k2Stages * k2StageBytes;  // 2 x 16 KB, 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + 2 * kEpiBufBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * k2Stages + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * k2Stages;
@@ -602,6 +664,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
+    tma_prefetch_desc(&tmap_y);
     for (int s = 0; s < k2Stages; ++s) {
       mbar_init(full0 + 8 * s, 2);   // leader's expect_tx arrival + the peer producer's arrival
       mbar_init(empty0 + 8 * s, 1);  // leader's multicast commit
@@ -623,7 +686,10 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t it = 0;
+      // ---- TMA producer: running counters only (no divisions inside the k loop)
+      uint32_t s = 0, ph = 0;
+      const uint32_t tx_bytes = 2 * (kABytes + (p.tile_n >> 1) * 128);
+      const uint32_t lead_full0 = map_to_cta(full0, 0);
       for (int pt = pair; pt < total_pair_tiles; pt += npairs) {
         const int nt = pt % n_tiles;
         const int mtile = 2 * (pt / n_tiles) + (int)rank;
@@ -634,27 +700,31 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           ty = mt % p.tiles_y;
           img = mt / p.tiles_y;
         }
-        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * p.tile_n;
+        const int n0 = nt * p.tile_n;
         int n_eff = p.cout - n0;
         n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
         const int brow0 = n0 + (int)rank * (n_eff >> 1);
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % k2Stages;
-          mbar_wait(empty0 + 8 * s, ((it / k2Stages) & 1) ^ 1);
-          const int tap = kb / kcb, cb = kb - tap * kcb;
-          const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+        const int xb = tx * p.bw - p.pad, yb = ty * p.bh - p.pad;
+        int cb = 0, kwi = 0, khi = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
           const uint32_t sa = smem_base + s * k2StageBytes;
           const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;  // the leader CTA's barrier (peer bit cleared)
-          if (leader) mbar_expect_tx(full0 + 8 * s, 2 * (kABytes + (p.tile_n >> 1) * 128));
-          else mbar_arrive_cluster(map_to_cta(full0 + 8 * s, 0));
-          tma_load_4d_2sm(sa, &tmap_x, lead_full, cb * 64, ox0 - p.pad + kwi * p.dil, oy0 - p.pad + khi * p.dil, img);
-          tma_load_3d_2sm(sa + kABytes, &tmap_w, lead_full, cb * 64, brow0, tap);
+          if (leader) mbar_expect_tx(full0 + 8 * s, tx_bytes);
+          else mbar_arrive_cluster(lead_full0 + 8 * s);
+          tma_load_4d_2sm(sa, &tmap_x, lead_full, cb * 64, xb + kwi * p.dil, yb + khi * p.dil, img);
+          tma_load_3d_2sm(sa + kABytes, &tmap_w, lead_full, cb * 64, brow0, khi * p.kw + kwi);
+          if (++cb == kcb) { cb = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
+          if (++s == k2Stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      uint32_t it = 0, tcount = 0;
+      // ---- MMA issuer
+      uint32_t s = 0, ph = 0, tcount = 0;
+      const int last_ksteps = (p.cin - (kcb - 1) * 64 >= 64) ? 4 : (p.cin - (kcb - 1) * 64 + 15) / 16;
+      const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
       for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
         const int nt = pt % n_tiles;
         const int n0 = nt * p.tile_n;
@@ -665,35 +735,38 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kPBN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % k2Stages;
-          mbar_wait(full0 + 8 * s, (it / k2Stages) & 1);
+        int cb = 0;
+        uint32_t accum = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const int cb = kb % kcb;
-          const int crem = p.cin - cb * 64;
-          const int ksteps = crem >= 64 ? 4 : (crem + 15) / 16;
+          const int ksteps = (cb == kcb - 1) ? last_ksteps : 4;
           const uint32_t sa = smem_base + s * k2StageBytes;
-          const uint32_t sb = sa + kABytes;
+          const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t bd = desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
           for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
-            const uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-            umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum);
+            accum = 1;
           }
           umma_commit_2sm(empty0 + 8 * s);
+          if (++cb == kcb) cb = 0;
+          if (++s == k2Stages) { s = 0; ph ^= 1; }
         }
         umma_commit_2sm(tfull0 + 8 * acc);
       }
     }
   } else {
+    // ---- epilogue: TMEM -> registers -> bf16 -> swizzled smem chunk (128 px x 64 ch) -> TMA store
     const int lg = warp & 3;
     const uint32_t lead_tempty0 = map_to_cta(tempty0, 0);
     const int epi_tid = threadIdx.x - 64;
+    const int row = lg * 32 + lane;
     float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
     if (EXTRA && ep.stats) {
       for (int i = epi_tid; i < n_tiles * 512; i += 128) stats_sm[i] = 0.f;
       epi_bar_sync();
     }
-    uint32_t tcount = 0;
+    uint32_t tcount = 0, chunk_count = 0;
     for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
       const int nt = pt % n_tiles;
       const int mtile = 2 * (pt / n_tiles) + (int)rank;
@@ -703,23 +776,71 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int ty = mt % p.tiles_y;
       const int img = mt / p.tiles_y;
       const int n0 = nt * p.tile_n;
-      const int row = lg * 32 + lane;
       const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
       const bool row_ok = tile_ok && oy < p.ho && ox < p.wo;
-      const size_t roff = (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout + n0;
+      const __nv_bfloat16* srow = (EXTRA && ep.side) ? ep.side + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout : nullptr;
+      int ncols = p.cout - n0;
+      ncols = ncols > p.tile_n ? p.tile_n : ncols;
+      const int nchunks = (ncols + 63) >> 6;
       const int acc = tcount & 1;
       mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
-      if (EXTRA)
-        tc_epilogue_tile(ep, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff, ep.side ? ep.side + roff : nullptr,
-                         stats_sm + nt * 512, lane);
-      else
-        tc_epilogue_tile_plain(ep.bias, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8 * acc);
+#pragma unroll 1
+      for (int q = 0; q < nchunks; ++q) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_addr + (uint32_t)(q * 64), r0);
+        tmem_ld32(t_addr + (uint32_t)(q * 64 + 32), r1);
+        tmem_ld_wait();
+        if (q == nchunks - 1) {  // the accumulator is in registers: hand it back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8 * acc);
+        }
+        if (!tile_ok) continue;  // CTA-uniform: the odd tile of the last pair
+        uint32_t pk0[16], pk1[16];
+        float v0[32], v1[32];
+        const int col0 = n0 + q * 64;
+        epi_convert32<EXTRA>(ep, r0, col0, p.cout, row_ok, srow, pk0, v0);
+        epi_convert32<EXTRA>(ep, r1, col0 + 32, p.cout, row_ok, srow, pk1, v1);
+        if (EXTRA && ep.stats) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sq[i] = v0[i] * v0[i];
+          warp_colsum32(v0, lane);
+          warp_colsum32(sq, lane);
+          int c = q * 64 + lane;
+          if (n0 + c < p.cout) { atomicAdd(&stats_sm[nt * 512 + c], v0[0]); atomicAdd(&stats_sm[nt * 512 + 256 + c], sq[0]); }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sq[i] = v1[i] * v1[i];
+          warp_colsum32(v1, lane);
+          warp_colsum32(sq, lane);
+          c += 32;
+          if (n0 + c < p.cout) { atomicAdd(&stats_sm[nt * 512 + c], v1[0]); atomicAdd(&stats_sm[nt * 512 + 256 + c], sq[0]); }
+        }
+        const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
+        if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
+        epi_bar_sync();
+        {
+          uint8_t* rowp = epi_buf + buf + row * 128;
+          const int sw = row & 7;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk0[4 * j], pk0[4 * j + 1], pk0[4 * j + 2], pk0[4 * j + 3]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(rowp + (((j + 4) ^ sw) << 4)) = make_uint4(pk1[4 * j], pk1[4 * j + 1], pk1[4 * j + 2], pk1[4 * j + 3]);
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (epi_tid == 0) {
+          tma_store_4d(&tmap_y, smem_u32(epi_buf + buf), col0, tx * p.bw, ty * p.bh, img);
+          bulk_commit();
+        }
+        ++chunk_count;
+      }
     }
+    if (epi_tid == 0) bulk_wait_read<0>();
     if (EXTRA && ep.stats) tc_epilogue_flush_stats(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
   }
   tc_fence_before();
@@ -934,13 +1055,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
         int ci_n = p.cin - ci0;
         ci_n = ci_n > p.ci_tile ? p.ci_tile : ci_n;
         const int ci_boxes = (ci_n + 63) / 64;
+        int tt = t_begin;
+        int tx = tt % p.tiles_x; tt /= p.tiles_x;
+        int ty = tt % p.tiles_y;
+        int img = tt / p.tiles_y;
         for (int t = t_begin; t < t_end; ++t, ++it) {
           const int s = it % kWPStages;
           mbar_wait(empty0 + 8 * s, ((it / kWPStages) & 1) ^ 1);
-          int tt = t;
-          const int tx = tt % p.tiles_x; tt /= p.tiles_x;
-          const int ty = tt % p.tiles_y;
-          const int img = tt / p.tiles_y;
           const int ox0 = tx * p.bw, oy0 = ty * p.bh;
           const uint32_t sa = smem_base + s * kWPStageBytes;
           mbar_expect_tx(full0 + 8 * s, kWPABytes + ci_boxes * kWBox);
@@ -949,6 +1070,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
           for (int j = 0; j < ci_boxes; ++j)
             tma_load_4d(sa + kWPABytes + j * kWBox, &tmap_x, full0 + 8 * s, ci0 + j * 64, ox0 - p.pad + kwi * p.dil,
                         oy0 - p.pad + khi * p.dil, img);
+          if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img; } }
         }
       }
     }
@@ -1021,6 +1143,195 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------ wgrad, CTA pair (cta_group::2)
+// One pair = one (256 output channels) x (<= 256 input channels) accumulator per tap and pixel split: each CTA
+// stages 64 pixels of ITS 128 output channels of dY and ITS half of the input channels of X (32 KB per 64 pixels
+// instead of the single-CTA kernel's 48 KB for the same MMA work), which is what bounds this kernel: the L2 -> SM
+// operand stream, not the tensor pipe.
+constexpr int kW2Stages = 6;
+constexpr int kW2ABytes = 2 * kWBox;                 // 128 co x 64 px
+constexpr int kW2BBytes = 2 * kWBox;                 // up to 128 ci x 64 px
+constexpr int kW2StageBytes = kW2ABytes + kW2BBytes;  // 32 KB
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+conv_tc_wgrad_2cta_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
+                          float* __restrict__ dw, TcWgradPParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kW2Stages * kW2StageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kW2Stages + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kW2Stages;
+  const uint32_t tfull0 = empty0 + 8 * kW2Stages, tempty0 = tfull0 + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int taps = p.kh * p.kw;
+  const int ptiles = p.n * p.tiles_y * p.tiles_x;
+  const int per = (ptiles + p.splits - 1) / p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_dy);
+    tma_prefetch_desc(&tmap_x);
+    for (int s = 0; s < kW2Stages; ++s) {
+      mbar_init(full0 + 8 * s, 2);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull0 + 8 * a, 1);
+      mbar_init(tempty0 + 8 * a, 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (co tile fastest, ci tile, tap, split slowest)
+  auto decode = [&](int item, int& cot, int& cit, int& tap, int& t_begin, int& t_end) {
+    cot = item % p.co_tiles; item /= p.co_tiles;
+    cit = item % p.ci_tiles; item /= p.ci_tiles;
+    tap = item % taps;
+    const int split = item / taps;
+    t_begin = split * per;
+    t_end = min(t_begin + per, ptiles);
+  };
+  // input channels of one ci tile, rounded so that each CTA's half is a multiple of 16
+  auto ci_count = [&](int ci0) {
+    int ci_n = p.cin - ci0;
+    return ci_n > p.ci_tile ? p.ci_tile : ((ci_n + 31) & ~31);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t s = 0, ph = 0;
+      const uint32_t lead_full0 = map_to_cta(full0, 0);
+      for (int item = pair; item < p.total_items; item += npairs) {
+        int cot, cit, tap, t_begin, t_end;
+        decode(item, cot, cit, tap, t_begin, t_end);
+        const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+        const int ci0 = cit * p.ci_tile;
+        const int half = ci_count(ci0) >> 1;
+        const int co_r = cot * 256 + (int)rank * 128, ci_r = ci0 + (int)rank * half;
+        const int nb = (half + 63) >> 6;
+        const uint32_t tx_bytes = 2 * (kW2ABytes + nb * kWBox);
+        int tt = t_begin;
+        int tx = tt % p.tiles_x; tt /= p.tiles_x;
+        int ty = tt % p.tiles_y;
+        int img = tt / p.tiles_y;
+        const int dx = kwi * p.dil - p.pad, dy = khi * p.dil - p.pad;
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(empty0 + 8 * s, ph ^ 1);
+          const int ox0 = tx * p.bw, oy0 = ty * p.bh;
+          const uint32_t sa = smem_base + s * kW2StageBytes;
+          const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;
+          if (leader) mbar_expect_tx(full0 + 8 * s, tx_bytes);
+          else mbar_arrive_cluster(lead_full0 + 8 * s);
+          tma_load_4d_2sm(sa, &tmap_dy, lead_full, co_r, ox0, oy0, img);
+          tma_load_4d_2sm(sa + kWBox, &tmap_dy, lead_full, co_r + 64, ox0, oy0, img);
+          tma_load_4d_2sm(sa + kW2ABytes, &tmap_x, lead_full, ci_r, ox0 + dx, oy0 + dy, img);
+          if (nb > 1) tma_load_4d_2sm(sa + kW2ABytes + kWBox, &tmap_x, lead_full, ci_r + 64, ox0 + dx, oy0 + dy, img);
+          if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img; } }
+          if (++s == kW2Stages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      uint32_t s = 0, ph = 0, icount = 0;
+      // MN-major operands: LBO = distance between 64-channel atoms, SBO = distance between 8-pixel groups
+      const uint64_t desc_hi = ((uint64_t)(kWBox >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+                               ((uint64_t)2 << 61);
+      for (int item = pair; item < p.total_items; item += npairs, ++icount) {
+        int cot, cit, tap, t_begin, t_end;
+        decode(item, cot, cit, tap, t_begin, t_end);
+        const uint32_t idesc = make_idesc(256, ci_count(cit * p.ci_tile), 1, 1);
+        const int acc = icount & 1;
+        mbar_wait(tempty0 + 8 * acc, ((icount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        uint32_t accum = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+          mbar_wait(full0 + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * kW2StageBytes;
+          const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+          const uint64_t bd = desc_hi | (uint64_t)(((sa + kW2ABytes) >> 4) & 0x3FFF);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 pixels per MMA = 16 smem rows of 128 B
+            umma_bf16_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (2048 >> 4)), idesc, accum);
+            accum = 1;
+          }
+          umma_commit_2sm(empty0 + 8 * s);
+          if (++s == kW2Stages) { s = 0; ph ^= 1; }
+        }
+        umma_commit_2sm(tfull0 + 8 * acc);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const uint32_t lead_tempty0 = map_to_cta(tempty0, 0);
+    uint32_t icount = 0;
+    for (int item = pair; item < p.total_items; item += npairs, ++icount) {
+      int cot, cit, tap, t_begin, t_end;
+      decode(item, cot, cit, tap, t_begin, t_end);
+      const int ci0 = cit * p.ci_tile;
+      const int co = cot * 256 + (int)rank * 128 + lg * 32 + lane;
+      const int acc = icount & 1;
+      mbar_wait(tfull0 + 8 * acc, (icount >> 1) & 1);
+      tc_fence_after();
+      if (t_end > t_begin) {
+        float* drow = dw + ((size_t)tap * p.cout + co) * p.cin + ci0;
+        const uint32_t t_addr = tmem_base + acc * 256 + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < p.ci_tile; c0 += 32) {
+          if (ci0 + c0 >= p.cin) break;
+          uint32_t r[32];
+          tmem_ld32(t_addr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (co < p.cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (ci0 + c0 + j < p.cin && c0 + j < p.ci_tile)  // cin % 8 == 0: whole groups of 4 are in or out
+                red_add_v4(drow + c0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                           __uint_as_float(r[j + 3]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// pixel splits for a persistent wgrad launch: fill `workers` CTAs (or pairs) in whole rounds, keeping every item
+// long enough (>= 8 pixel tiles) that its fixed cost (accumulator drain, pipeline refill) stays small
+static int pick_wgrad_splits(int out_tiles, int ptiles, int workers) {
+  int best = 1;
+  double best_cost = 1e30;
+  const int max_splits = ptiles / 8 > 1 ? ptiles / 8 : 1;
+  for (int s = 1; s <= max_splits && s <= 4096; ++s) {
+    const long items = (long)out_tiles * s;
+    const long rounds = (items + workers - 1) / workers;
+    const int per = (ptiles + s - 1) / s;
+    const double cost = (double)rounds * (per + 6.0);  // 6 pixel tiles ~ drain + refill of one item
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    if (rounds > 8) break;
+  }
+  return best;
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -1102,10 +1413,16 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     CVX_CHECK_ARG(stride == 2 && p.bw * 2 <= 256 && p.bh * 2 <= 256 && !use_v1, "conv_tc: unsupported stride %d", stride);
   }
   if (use_2cta && stride == 1) {
-    CUtensorMap mx, mw;
+    // the epilogue stores 64-channel chunks by TMA: tiles start on multiples of 64 channels
+    {
+      const int nt = (ncol + kPBN - 1) / kPBN;
+      p.tile_n = ((ncol + nt - 1) / nt + 63) & ~63;
+    }
+    CUtensorMap mx, mw, my;
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
     if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n >> 1)) return rc;
-    constexpr int smem = k2Stages * k2StageBytes + 1024 + 256 + kEpiStatsBytes;
+    if (int rc = make_act_map(&my, dst, n, ho, wo, ncol, p.bw, p.bh)) return rc;
+    constexpr int smem = k2Stages * k2StageBytes + 2 * kEpiBufBytes + 1024 + 256 + kEpiStatsBytes;
     static bool configured = false;
     if (!configured) {
       CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1118,9 +1435,9 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
     CVX_CHECK_ARG(!ep.stats || n_tiles <= kEpiMaxNTiles, "conv_tc: fused statistics need C_out <= %d", kEpiMaxNTiles * kPBN);
     if (ep.side || ep.stats)
-      conv_tc_fwd_2cta_kernel<true><<<2 * pairs, 192, smem, st>>>(mx, mw, ep, (__nv_bfloat16*)dst, p, n_tiles, m_tiles, total);
+      conv_tc_fwd_2cta_kernel<true><<<2 * pairs, 192, smem, st>>>(mx, mw, my, ep, p, n_tiles, m_tiles, total);
     else
-      conv_tc_fwd_2cta_kernel<false><<<2 * pairs, 192, smem, st>>>(mx, mw, ep, (__nv_bfloat16*)dst, p, n_tiles, m_tiles, total);
+      conv_tc_fwd_2cta_kernel<false><<<2 * pairs, 192, smem, st>>>(mx, mw, my, ep, p, n_tiles, m_tiles, total);
     CVX_LAUNCH_OK();
     return CVX_OK;
   }
@@ -1222,27 +1539,40 @@ int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, flo
   CVX_CHECK_ARG(x && dy && dw_packed, "conv_wgrad_tc: null pointer");
   static const bool wgrad_v1 = getenv("CERVIX_TC_WGRAD_V1") != nullptr;
   if (!wgrad_v1) {
+    static const bool wgrad_1cta = getenv("CERVIX_TC_WGRAD_1CTA") != nullptr;
+    const bool pairk = !wgrad_1cta && d->cout > 128;  // the pair tile is 256 output channels tall
     TcWgradPParams q;
     q.n = d->n; q.ho = d->ho; q.wo = d->wo; q.cout = d->cout; q.cin = d->cin;
     q.kh = d->kh; q.kw = d->kw; q.pad = d->pad; q.dil = d->dil;
     pick_tile(d->ho, d->wo, 64, &q.bw, &q.bh);
     q.tiles_x = (d->wo + q.bw - 1) / q.bw;
     q.tiles_y = (d->ho + q.bh - 1) / q.bh;
-    q.co_tiles = (d->cout + 127) / 128;
+    q.co_tiles = pairk ? (d->cout + 255) / 256 : (d->cout + 127) / 128;
     q.ci_tiles = (d->cin + 255) / 256;
-    q.ci_tile = ((d->cin + q.ci_tiles - 1) / q.ci_tiles + 15) & ~15;
+    const int ci_round = pairk ? 31 : 15;
+    q.ci_tile = ((d->cin + q.ci_tiles - 1) / q.ci_tiles + ci_round) & ~ci_round;
     if (q.ci_tile > 256) q.ci_tile = 256;
     q.ci_tiles = (d->cin + q.ci_tile - 1) / q.ci_tile;
     const int ptiles = q.n * q.tiles_y * q.tiles_x;
     const int out_tiles = q.co_tiles * q.ci_tiles * d->kh * d->kw;
-    int splits = (2 * kNumSMs + out_tiles - 1) / out_tiles;
-    if (splits > ptiles / 8) splits = ptiles / 8;  // keep >= 8 pixel tiles (512 pixels) per item
-    if (splits < 1) splits = 1;
-    q.splits = splits;
-    q.total_items = out_tiles * splits;
+    const int workers = pairk ? kNumSMs / 2 : kNumSMs;
+    q.splits = pick_wgrad_splits(out_tiles, ptiles, workers);
+    q.total_items = out_tiles * q.splits;
     CUtensorMap mdy, mx;
     if (int rc = make_act_map(&mdy, dy, d->n, d->ho, d->wo, d->cout, q.bw, q.bh)) return rc;
     if (int rc = make_act_map(&mx, x, d->n, d->h, d->w, d->cin, q.bw, q.bh)) return rc;
+    if (pairk) {
+      constexpr int smem2 = kW2Stages * kW2StageBytes + 1024 + 256;
+      static bool configured2 = false;
+      if (!configured2) {
+        CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        configured2 = true;
+      }
+      const int pairs = q.total_items < workers ? q.total_items : workers;
+      conv_tc_wgrad_2cta_kernel<<<2 * pairs, 192, smem2, as_stream(stream)>>>(mdy, mx, dw_packed, q);
+      CVX_LAUNCH_OK();
+      return CVX_OK;
+    }
     constexpr int smem = kWPStages * kWPStageBytes + 1024 + 256;
     static bool configured = false;
     if (!configured) {
