@@ -93,6 +93,11 @@ CVX_API int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w
                     void* y, void* stream);
 CVX_API int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
 CVX_API int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
+/* Tuning knob of cvx_conv_fwd_tc / cvx_conv_dgrad_tc: CTA pairs per thread-block cluster (1, 2 or 4) that share one
+ * weight tile through TMA multicast.  force != 0 keeps the setting even for problems too small to fill the machine
+ * (tests).  Default 1 (measured fastest on B200: the large convolutions already run at the power-limited tensor
+ * peak), or CERVIX_TC_PAIRS in the environment. */
+CVX_API int cvx_conv_tc_set_pairs(int pairs, int force);
 /* im2col of a narrow-channel input (C_in <= 4): patches[n,ho,wo,kpad], k = tap*C_in + ci, zero padded
  * to kpad (a multiple of 8).  Turns the ResNet-101 7x7/2 stem of the classifier's patch encoder
  * (MM/Graph_Structure(data_augmentation).py:136) into a 1x1 tensor-core GEMM. */

@@ -45,6 +45,7 @@ PROTOTYPES = {
     "cvx_conv_fwd_tc": [_D, _P, _P, _P, _P, _P],
     "cvx_conv_dgrad_tc": [_D, _P, _P, _P, _P],
     "cvx_conv_wgrad_tc": [_D, _P, _P, _P, _P],
+    "cvx_conv_tc_set_pairs": [C.c_int, C.c_int],
     "cvx_im2col_narrow": [_D, _P, _P, _I, _P],
     "cvx_subsample": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "cvx_subsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _P],

@@ -572,10 +572,20 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, u
       : "memory");
 }
 // commit -> arrive on the barrier at this smem offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t cta_mask = 3) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-      ::"r"(bar), "h"((uint16_t)3)
+      ::"r"(bar), "h"(cta_mask)
+      : "memory");
+}
+// weight tile shared by several CTA pairs of one cluster: ONE L2 read lands in every CTA of `cta_mask` (same smem
+// offset) and completes bytes on the full barrier of each destination's pair leader
+__device__ __forceinline__ void tma_load_3d_2sm_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                   int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
       : "memory");
 }
 
@@ -591,11 +601,11 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 
 constexpr int kEpiBufBytes = 128 * 128;  // one 128-pixel x 64-channel bf16 chunk, SWIZZLE_128B rows
 
-// 32 accumulator columns of one row -> (+bias, +side) -> 16 packed bf16 pairs; `vals` receives the rounded values
-// (zero where the column is outside the tensor) when statistics are wanted.
+// 32 accumulator columns of one row -> (+bias, +side) -> 16 packed bf16 pairs (EXTRA: zero where the row or the
+// column lies outside the tensor, so the staged chunk can be summed for the statistics as it is).
 template <bool EXTRA>
 __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&r)[32], int col0, int cout, bool row_ok,
-                                              const __nv_bfloat16* srow, uint32_t (&packed)[16], float (&vals)[32]) {
+                                              const __nv_bfloat16* srow, uint32_t (&packed)[16]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int c = col0 + g * 8;          // absolute output channel of this group of 8
@@ -631,17 +641,17 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
       const float v1 = __uint_as_float(r[g * 8 + 2 * j + 1]) + bv[2 * j + 1] + sd[2 * j + 1];
       __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
       const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
-      packed[g * 4 + j] = u;
-      if (EXTRA) {
-        vals[g * 8 + 2 * j] = (ok && row_ok) ? __uint_as_float(u << 16) : 0.f;
-        vals[g * 8 + 2 * j + 1] = (ok && row_ok) ? __uint_as_float(u & 0xffff0000u) : 0.f;
-      }
+      packed[g * 4 + j] = (EXTRA && !(ok && row_ok)) ? 0u : u;   // rows / channels outside the tensor must not reach the statistics
     }
   }
 }
 
-template <bool EXTRA>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+// kPairs CTA pairs form one cluster (launch attribute, 2*kPairs CTAs): they work on the SAME output-channel tile of
+// kPairs consecutive pixel-tile pairs, so the weight tile is read from L2 once per cluster - every CTA fetches
+// 1/kPairs of its half and multicasts it to the CTAs that hold the same half in the other pairs.  The operand
+// stream L2 -> SM is what bounds this kernel (32 KB per CTA and k-block without sharing, ~6.3 KB/clk chip-wide).
+template <bool EXTRA, int kPairs>
+__global__ void __launch_bounds__(192, 1)
 conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_y, const TcEpi ep, TcFwdParams p, int n_tiles,
                         int m_tiles, int total_pair_tiles) {
@@ -655,9 +665,12 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   const uint32_t tfull0 = empty0 + 8 * k2Stages, tempty0 = tfull0 + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const uint32_t crank = cluster_ctarank();   // 0 .. 2*kPairs-1
+  const uint32_t rank = crank & 1;            // rank inside the CTA pair
+  const uint32_t pidx = crank >> 1;           // pair inside the cluster
+  const uint32_t lead_rank = crank & ~1u;
   const bool leader = rank == 0;
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pair = blockIdx.x / (2 * kPairs), npairs = gridDim.x / (2 * kPairs);   // cluster index / count
   const int kcb = (p.cin + 63) / 64;
   const int num_kb = p.kh * p.kw * kcb;
 
@@ -667,7 +680,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     tma_prefetch_desc(&tmap_y);
     for (int s = 0; s < k2Stages; ++s) {
       mbar_init(full0 + 8 * s, 2);   // leader's expect_tx arrival + the peer producer's arrival
-      mbar_init(empty0 + 8 * s, 1);  // leader's multicast commit
+      mbar_init(empty0 + 8 * s, kPairs);  // one multicast commit per pair leader of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
@@ -689,10 +702,14 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       // ---- TMA producer: running counters only (no divisions inside the k loop)
       uint32_t s = 0, ph = 0;
       const uint32_t tx_bytes = 2 * (kABytes + (p.tile_n >> 1) * 128);
-      const uint32_t lead_full0 = map_to_cta(full0, 0);
+      const uint32_t lead_full0 = map_to_cta(full0, lead_rank);
+      const int bq_rows = p.tile_n / (2 * kPairs);   // weight rows per multicast box
+      uint16_t bmask = 0;
+#pragma unroll
+      for (int q = 0; q < kPairs; ++q) bmask |= (uint16_t)(1u << (2 * q + rank));
       for (int pt = pair; pt < total_pair_tiles; pt += npairs) {
         const int nt = pt % n_tiles;
-        const int mtile = 2 * (pt / n_tiles) + (int)rank;
+        const int mtile = 2 * ((pt / n_tiles) * kPairs + (int)pidx) + (int)rank;
         int tx = 0, ty = 0, img = p.n;  // img == n -> every TMA coordinate is out of bounds (zero fill)
         if (mtile < m_tiles) {
           int mt = mtile;
@@ -703,7 +720,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         const int n0 = nt * p.tile_n;
         int n_eff = p.cout - n0;
         n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
-        const int brow0 = n0 + (int)rank * (n_eff >> 1);
+        const int brow0 = n0 + (int)rank * (n_eff >> 1) + (int)pidx * bq_rows;
         const int xb = tx * p.bw - p.pad, yb = ty * p.bh - p.pad;
         int cb = 0, kwi = 0, khi = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -713,7 +730,10 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           if (leader) mbar_expect_tx(full0 + 8 * s, tx_bytes);
           else mbar_arrive_cluster(lead_full0 + 8 * s);
           tma_load_4d_2sm(sa, &tmap_x, lead_full, cb * 64, xb + kwi * p.dil, yb + khi * p.dil, img);
-          tma_load_3d_2sm(sa + kABytes, &tmap_w, lead_full, cb * 64, brow0, khi * p.kw + kwi);
+          if (kPairs == 1)
+            tma_load_3d_2sm(sa + kABytes, &tmap_w, lead_full, cb * 64, brow0, khi * p.kw + kwi);
+          else
+            tma_load_3d_2sm_mc(sa + kABytes + pidx * bq_rows * 128, &tmap_w, lead_full, cb * 64, brow0, khi * p.kw + kwi, bmask);
           if (++cb == kcb) { cb = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
           if (++s == k2Stages) { s = 0; ph ^= 1; }
         }
@@ -748,17 +768,17 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum);
             accum = 1;
           }
-          umma_commit_2sm(empty0 + 8 * s);
+          umma_commit_2sm(empty0 + 8 * s, (uint16_t)((1u << (2 * kPairs)) - 1));
           if (++cb == kcb) cb = 0;
           if (++s == k2Stages) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(tfull0 + 8 * acc);
+        umma_commit_2sm(tfull0 + 8 * acc, (uint16_t)(3u << (2 * pidx)));
       }
     }
   } else {
     // ---- epilogue: TMEM -> registers -> bf16 -> swizzled smem chunk (128 px x 64 ch) -> TMA store
     const int lg = warp & 3;
-    const uint32_t lead_tempty0 = map_to_cta(tempty0, 0);
+    const uint32_t lead_tempty0 = map_to_cta(tempty0, lead_rank);
     const int epi_tid = threadIdx.x - 64;
     const int row = lg * 32 + lane;
     float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
@@ -769,7 +789,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     uint32_t tcount = 0, chunk_count = 0;
     for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
       const int nt = pt % n_tiles;
-      const int mtile = 2 * (pt / n_tiles) + (int)rank;
+      const int mtile = 2 * ((pt / n_tiles) * kPairs + (int)pidx) + (int)rank;
       const bool tile_ok = mtile < m_tiles;
       int mt = tile_ok ? mtile : 0;
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
@@ -799,25 +819,9 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         if (!tile_ok) continue;  // CTA-uniform: the odd tile of the last pair
         uint32_t pk0[16], pk1[16];
-        float v0[32], v1[32];
         const int col0 = n0 + q * 64;
-        epi_convert32<EXTRA>(ep, r0, col0, p.cout, row_ok, srow, pk0, v0);
-        epi_convert32<EXTRA>(ep, r1, col0 + 32, p.cout, row_ok, srow, pk1, v1);
-        if (EXTRA && ep.stats) {
-          float sq[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = v0[i] * v0[i];
-          warp_colsum32(v0, lane);
-          warp_colsum32(sq, lane);
-          int c = q * 64 + lane;
-          if (n0 + c < p.cout) { atomicAdd(&stats_sm[nt * 512 + c], v0[0]); atomicAdd(&stats_sm[nt * 512 + 256 + c], sq[0]); }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) sq[i] = v1[i] * v1[i];
-          warp_colsum32(v1, lane);
-          warp_colsum32(sq, lane);
-          c += 32;
-          if (n0 + c < p.cout) { atomicAdd(&stats_sm[nt * 512 + c], v1[0]); atomicAdd(&stats_sm[nt * 512 + 256 + c], sq[0]); }
-        }
+        epi_convert32<EXTRA>(ep, r0, col0, p.cout, row_ok, srow, pk0);
+        epi_convert32<EXTRA>(ep, r1, col0 + 32, p.cout, row_ok, srow, pk1);
         const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
         if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
         epi_bar_sync();
@@ -836,6 +840,26 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         if (epi_tid == 0) {
           tma_store_4d(&tmap_y, smem_u32(epi_buf + buf), col0, tx * p.bw, ty * p.bh, img);
           bulk_commit();
+        }
+        if (EXTRA && ep.stats) {
+          // column sums of the staged (bf16-rounded) chunk: warp lg sums 32 rows, lane = one pair of channels;
+          // a warp reads one whole 128-byte row per step, so the swizzled layout is conflict-free here too
+          const uint8_t* bufp = epi_buf + buf;
+          float2 sm = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f);
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r = lg * 32 + rr;
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(bufp + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            const float2 v = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+            sm = __fadd2_rn(sm, v);
+            sq = __ffma2_rn(v, v, sq);
+          }
+          const int c = q * 64 + 2 * lane;
+          if (n0 + c < p.cout) {
+            float* st = stats_sm + nt * 512;
+            atomicAdd(&st[c], sm.x); atomicAdd(&st[c + 1], sm.y);
+            atomicAdd(&st[256 + c], sq.x); atomicAdd(&st[256 + c + 1], sq.y);
+          }
         }
         ++chunk_count;
       }
@@ -1392,6 +1416,59 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const float*
   return CVX_OK;
 }
 
+// pairs per cluster of the forward / data-gradient kernel (cvx_conv_tc_set_pairs; CERVIX_TC_PAIRS at load time)
+static int g_tc_pairs = [] {
+  const char* e = getenv("CERVIX_TC_PAIRS");
+  const int v = e ? atoi(e) : 1;
+  return (v == 1 || v == 2 || v == 4) ? v : 1;
+}();
+static int g_tc_pairs_force = 0;
+
+// launch the CTA-pair forward kernel with `kp` pairs per cluster (cluster size 2*kp as a launch attribute)
+template <bool EXTRA, int kPairs>
+static int launch_fwd_pairs_t(int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const TcEpi& ep,
+                              const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
+  auto kern = conv_tc_fwd_2cta_kernel<EXTRA, kPairs>;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * kPairs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters == 0) {
+    CVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cfg.gridDim = dim3(kNumSMs / (2 * kPairs) * (2 * kPairs));
+    int n = 0;
+    CVX_CUDA_OK(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    if (n < 1) { set_error("conv_tc: no cluster of %d CTAs fits on this device", 2 * kPairs); return CVX_ECUDA; }
+    max_clusters = n < kNumSMs / (2 * kPairs) ? n : kNumSMs / (2 * kPairs);
+  }
+  const int total = ((m_tiles + 2 * kPairs - 1) / (2 * kPairs)) * n_tiles;
+  const int clusters = total < max_clusters ? total : max_clusters;
+  cfg.gridDim = dim3(clusters * 2 * kPairs);
+  CVX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, mw, my, ep, p, n_tiles, m_tiles, total));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+static int launch_fwd_pairs(int kp, bool extra, int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
+                            const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
+  if (extra) {
+    if (kp == 4) return launch_fwd_pairs_t<true, 4>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    if (kp == 2) return launch_fwd_pairs_t<true, 2>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    return launch_fwd_pairs_t<true, 1>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+  }
+  if (kp == 4) return launch_fwd_pairs_t<false, 4>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+  if (kp == 2) return launch_fwd_pairs_t<false, 2>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+  return launch_fwd_pairs_t<false, 1>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+}
+
 // rows = output pixels [n,ho,wo] ; src = [n,hs,ws,cred] ; wp = [taps][ncol][cred]
 static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, int kh, int kw, int pad, int dil,
                      const void* src, const void* wp, const TcEpi& ep, void* dst, cudaStream_t st, int stride = 1) {
@@ -1418,28 +1495,19 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
       const int nt = (ncol + kPBN - 1) / kPBN;
       p.tile_n = ((ncol + nt - 1) / nt + 63) & ~63;
     }
-    CUtensorMap mx, mw, my;
-    if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
-    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n >> 1)) return rc;
-    if (int rc = make_act_map(&my, dst, n, ho, wo, ncol, p.bw, p.bh)) return rc;
     constexpr int smem = k2Stages * k2StageBytes + 2 * kEpiBufBytes + 1024 + 256 + kEpiStatsBytes;
-    static bool configured = false;
-    if (!configured) {
-      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      CVX_CUDA_OK(cudaFuncSetAttribute(conv_tc_fwd_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = true;
-    }
     const int n_tiles = (ncol + p.tile_n - 1) / p.tile_n;
     const int m_tiles = n * p.tiles_y * p.tiles_x;
-    const int total = ((m_tiles + 1) / 2) * n_tiles;
-    const int pairs = total < kNumSMs / 2 ? total : kNumSMs / 2;
     CVX_CHECK_ARG(!ep.stats || n_tiles <= kEpiMaxNTiles, "conv_tc: fused statistics need C_out <= %d", kEpiMaxNTiles * kPBN);
-    if (ep.side || ep.stats)
-      conv_tc_fwd_2cta_kernel<true><<<2 * pairs, 192, smem, st>>>(mx, mw, my, ep, p, n_tiles, m_tiles, total);
-    else
-      conv_tc_fwd_2cta_kernel<false><<<2 * pairs, 192, smem, st>>>(mx, mw, my, ep, p, n_tiles, m_tiles, total);
-    CVX_LAUNCH_OK();
-    return CVX_OK;
+    const bool extra = ep.side || ep.stats;
+    // pairs per cluster: share the weight tile among 2 pairs when there are enough pixel tiles to keep the machine full
+    int kp = g_tc_pairs;
+    while (kp > 1 && ((p.tile_n / (2 * kp)) % 8 != 0 || (!g_tc_pairs_force && m_tiles < 2 * kp * 16))) kp >>= 1;
+    CUtensorMap mx, mw, my;
+    if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
+    if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n / (2 * kp))) return rc;
+    if (int rc = make_act_map(&my, dst, n, ho, wo, ncol, p.bw, p.bh)) return rc;
+    return launch_fwd_pairs(kp, extra, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
   }
   if (!use_v1) {
     CUtensorMap mx, mw;
@@ -1491,6 +1559,13 @@ static int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, float* dw
 using namespace cvx;
 
 extern "C" {
+
+int cvx_conv_tc_set_pairs(int pairs, int force) {
+  CVX_CHECK_ARG(pairs == 1 || pairs == 2 || pairs == 4, "conv_tc_set_pairs: pairs must be 1, 2 or 4 (got %d)", pairs);
+  g_tc_pairs = pairs;
+  g_tc_pairs_force = force != 0;
+  return CVX_OK;
+}
 
 int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y,
                     void* stream) {

@@ -37,10 +37,24 @@ __device__ __forceinline__ void unpack8f(const uint4& r, float (&v)[8]) {
     v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
   }
 }
+// 8 bf16 -> 4 packed fp32 pairs: the arithmetic below runs on FFMA2 / FADD2 (two fp32 lanes per instruction,
+// sm_100), which halves the issue slots of the 9-tap loops that bound these kernels
+__device__ __forceinline__ void unpack4x2(const uint4& r, float2 (&v)[4]) {
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(u[i] << 16), __uint_as_float(u[i] & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
 
-// reduce per-thread [K][8] partials over the 16 column-threads that share a channel vector, then fp64 atomics
+// reduce per-thread [K][4] float2 partials over the 16 column-threads that share a channel vector, then fp64 atomics
 template <int K>
-__device__ __forceinline__ void reduce_to_global(float (&part)[K][8], float* red /* [K][64] smem */, int t_in_group,
+__device__ __forceinline__ void reduce_to_global(float2 (&part)[K][4], float* red /* [K][64] smem */, int t_in_group,
                                                  int cv, int cchunk, int C, double* out, int group_bar) {
   for (int i = t_in_group; i < K * 64; i += 128) red[i] = 0.f;
   asm volatile("bar.sync %0, 128;" ::"r"(group_bar) : "memory");
@@ -48,7 +62,7 @@ __device__ __forceinline__ void reduce_to_global(float (&part)[K][8], float* red
   for (int k = 0; k < K; ++k)
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float v = part[k][e];
+      float v = (e & 1) ? part[k][e >> 1].y : part[k][e >> 1].x;
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
       if ((t_in_group & 31) < 8) atomicAdd(&red[k * 64 + cv * 8 + e], v);
@@ -62,19 +76,19 @@ __device__ __forceinline__ void reduce_to_global(float (&part)[K][8], float* red
 
 // one 16-byte channel vector of the (virtual) depthwise input act(s*x+t) at halo-tile position (rr, cc)
 template <bool AFFINE>
-__device__ __forceinline__ void load_virtual(const uint8_t* tile, int rr, int cc, int cv, const float (&sc)[8],
-                                             const float (&sh)[8], bool relu, bool valid, float (&out)[8]) {
-  unpack8f(*reinterpret_cast<const uint4*>(tile + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
+__device__ __forceinline__ void load_virtual(const uint8_t* tile, int rr, int cc, int cv, const float2 (&sc)[4],
+                                             const float2 (&sh)[4], bool relu, bool valid, float2 (&out)[4]) {
+  unpack4x2(*reinterpret_cast<const uint4*>(tile + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
   if (AFFINE) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = fmaf(out[e], sc[e], sh[e]);
-      if (relu) v = fmaxf(v, 0.f);
-      out[e] = valid ? v : 0.f;   // zero padding applies to the virtual tensor, not to the raw one
+    for (int e = 0; e < 4; ++e) {
+      float2 v = __ffma2_rn(out[e], sc[e], sh[e]);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+      out[e] = valid ? v : make_float2(0.f, 0.f);   // zero padding applies to the virtual tensor, not to the raw one
     }
   } else if (relu) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) out[e] = fmaxf(out[e], 0.f);
+    for (int e = 0; e < 4; ++e) { out[e].x = fmaxf(out[e].x, 0.f); out[e].y = fmaxf(out[e].y, 0.f); }
   }
 }
 
@@ -96,17 +110,19 @@ __global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__
   const bool ch_ok = c0 < p.c;
   const bool relu = p.relu_in != 0;
 
-  float wreg[9][8], sc[8], sh[8], s1[8], s2[8];
+  float2 wreg[9][4], sc[4], sh[4], s12[2][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    sc[i] = (AFFINE && ch_ok) ? __ldg(in_scale + c0 + i) : 1.f;
-    sh[i] = (AFFINE && ch_ok) ? __ldg(in_shift + c0 + i) : 0.f;
-    s1[i] = s2[i] = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    sc[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_scale + c0 + 2 * i), __ldg(in_scale + c0 + 2 * i + 1)) : make_float2(1.f, 1.f);
+    sh[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_shift + c0 + 2 * i), __ldg(in_shift + c0 + 2 * i + 1)) : make_float2(0.f, 0.f);
+    s12[0][i] = s12[1][i] = make_float2(0.f, 0.f);
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) wreg[k][i] = ch_ok ? __ldg(w9c + k * p.c + c0 + i) : 0.f;
+    for (int i = 0; i < 4; ++i)
+      wreg[k][i] = ch_ok ? make_float2(__ldg(w9c + k * p.c + c0 + 2 * i), __ldg(w9c + k * p.c + c0 + 2 * i + 1))
+                         : make_float2(0.f, 0.f);
 
   if (t == 0) {
     tma_prefetch_desc(&tmap);
@@ -147,7 +163,7 @@ __global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) cvalid[kw] = (ox - 1 + kw) >= 0 && (ox - 1 + kw) < p.w;
 
-    float win[3][3][8];
+    float2 win[3][3][4];
     auto load_row = [&](int slot, int rr) {
       const int iy = oy0 - 1 + rr;
       const bool rvalid = iy >= 0 && iy < p.h;
@@ -164,24 +180,23 @@ __global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__
       for (int j = 0; j < 3; ++j) {
         const int r = r3 + j;
         load_row((j + 2) % 3, r + 2);
-        float acc[8];
+        float2 acc[4];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] = fmaf(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
+            for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
         if (col_ok && (oy0 + r) < p.h) {
           uint32_t pk[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 hh = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
-            pk[e] = *reinterpret_cast<uint32_t*>(&hh);
-            const float a = __uint_as_float(pk[e] << 16), b = __uint_as_float(pk[e] & 0xffff0000u);
-            s1[2 * e] += a; s1[2 * e + 1] += b;
-            s2[2 * e] = fmaf(a, a, s2[2 * e]); s2[2 * e + 1] = fmaf(b, b, s2[2 * e + 1]);
+            pk[e] = pack_bf16x2(acc[e]);
+            const float2 ab = unpack_bf16x2(pk[e]);
+            s12[0][e] = __fadd2_rn(s12[0][e], ab);
+            s12[1][e] = __ffma2_rn(ab, ab, s12[1][e]);
           }
           *reinterpret_cast<uint4*>(dst + (((size_t)img * p.h + oy0 + r) * p.w + ox) * p.c + c0) =
               make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -191,12 +206,7 @@ __global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__
     __syncthreads();
   }
 
-  if (stats) {
-    float part[2][8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { part[0][e] = s1[e]; part[1][e] = s2[e]; }
-    reduce_to_global<2>(part, reinterpret_cast<float*>(smem), t, cv, cchunk, p.c, stats, 1);
-  }
+  if (stats) reduce_to_global<2>(s12, reinterpret_cast<float*>(smem), t, cv, cchunk, p.c, stats, 1);
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -231,19 +241,22 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
   const bool relu = p.relu_in != 0;
 
   // role 0: wreg = flipped taps ; role 1: wreg = weight-gradient accumulators
-  float wreg[9][8], sc[8], sh[8], nk[8], km[8], s1[8], s2[8];
+  float2 wreg[9][4], sc[4], sh[4], nk[4], km[4], s12[2][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    sc[i] = (AFFINE && ch_ok) ? __ldg(in_scale + c0 + i) : 1.f;
-    sh[i] = (AFFINE && ch_ok) ? __ldg(in_shift + c0 + i) : 0.f;
-    nk[i] = (SIDE && ch_ok) ? __ldg(negk + c0 + i) : 0.f;
-    km[i] = (SIDE && ch_ok) ? __ldg(kmean + c0 + i) : 0.f;
-    s1[i] = s2[i] = 0.f;
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + 2 * i;
+    sc[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_scale + c), __ldg(in_scale + c + 1)) : make_float2(1.f, 1.f);
+    sh[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_shift + c), __ldg(in_shift + c + 1)) : make_float2(0.f, 0.f);
+    nk[i] = (SIDE && ch_ok) ? make_float2(__ldg(negk + c), __ldg(negk + c + 1)) : make_float2(0.f, 0.f);
+    km[i] = (SIDE && ch_ok) ? make_float2(__ldg(kmean + c), __ldg(kmean + c + 1)) : make_float2(0.f, 0.f);
+    s12[0][i] = s12[1][i] = make_float2(0.f, 0.f);
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) wreg[k][i] = (role == 0 && ch_ok) ? __ldg(w9c + (8 - k) * p.c + c0 + i) : 0.f;
+    for (int i = 0; i < 4; ++i)
+      wreg[k][i] = (role == 0 && ch_ok) ? make_float2(__ldg(w9c + (8 - k) * p.c + c0 + 2 * i), __ldg(w9c + (8 - k) * p.c + c0 + 2 * i + 1))
+                                        : make_float2(0.f, 0.f);
 
   if (t == 0) {
     tma_prefetch_desc(&tmap_dd);
@@ -306,22 +319,20 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
         if (iy > p.h) break;  // rows below the image feed nothing (warp-uniform up to the last partial row)
         const bool valid = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
         const int off = (pix * 64 + cv * 8) * 2;
-        float ev[8], dv[8], xv[8];
-        unpack8f(*reinterpret_cast<const uint4*>(e_w + off), ev);
-        unpack8f(*reinterpret_cast<const uint4*>(d_w + off), dv);
-        unpack8f(*reinterpret_cast<const uint4*>(x_s + off), xv);
-        uint32_t pd[4], px[4];
+        uint32_t pd[4] = {0u, 0u, 0u, 0u}, px[4] = {0u, 0u, 0u, 0u};
+        if (valid) {
+          float2 ev[4], dv[4], xv[4];
+          unpack4x2(*reinterpret_cast<const uint4*>(e_w + off), ev);
+          unpack4x2(*reinterpret_cast<const uint4*>(d_w + off), dv);
+          unpack4x2(*reinterpret_cast<const uint4*>(x_s + off), xv);
 #pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {
-          float a0 = fmaf(nk[2 * e2], dv[2 * e2], ev[2 * e2] + km[2 * e2]);
-          float a1 = fmaf(nk[2 * e2 + 1], dv[2 * e2 + 1], ev[2 * e2 + 1] + km[2 * e2 + 1]);
-          float b0 = AFFINE ? fmaf(xv[2 * e2], sc[2 * e2], sh[2 * e2]) : xv[2 * e2];
-          float b1 = AFFINE ? fmaf(xv[2 * e2 + 1], sc[2 * e2 + 1], sh[2 * e2 + 1]) : xv[2 * e2 + 1];
-          if (relu) { b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f); }
-          __nv_bfloat162 hd = __floats2bfloat162_rn(valid ? a0 : 0.f, valid ? a1 : 0.f);
-          __nv_bfloat162 hx = __floats2bfloat162_rn(valid ? b0 : 0.f, valid ? b1 : 0.f);
-          pd[e2] = *reinterpret_cast<uint32_t*>(&hd);
-          px[e2] = *reinterpret_cast<uint32_t*>(&hx);
+          for (int e2 = 0; e2 < 4; ++e2) {
+            const float2 a = __ffma2_rn(nk[e2], dv[e2], __fadd2_rn(ev[e2], km[e2]));
+            float2 b = AFFINE ? __ffma2_rn(xv[e2], sc[e2], sh[e2]) : xv[e2];
+            if (relu) { b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); }
+            pd[e2] = pack_bf16x2(a);
+            px[e2] = pack_bf16x2(b);
+          }
         }
         *reinterpret_cast<uint4*>(e_w + off) = make_uint4(pd[0], pd[1], pd[2], pd[3]);
         *reinterpret_cast<uint4*>(d_w + off) = make_uint4(px[0], px[1], px[2], px[3]);
@@ -330,11 +341,11 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
     }
     const uint8_t* xin_s = d_s;  // SIDE only: the transformed input tile
 
-    auto load_plain = [&](const uint8_t* tile, int rr, int cc, float (&out)[8]) {
-      unpack8f(*reinterpret_cast<const uint4*>(tile + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
+    auto load_plain = [&](const uint8_t* tile, int rr, int cc, float2 (&out)[4]) {
+      unpack4x2(*reinterpret_cast<const uint4*>(tile + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
     };
 
-    float win[3][3][8];
+    float2 win[3][3][4];
     if (role == 0) {
       // ---- data gradient: g = sum_k dd[shifted] * w[8-k], masked by the ReLU of the (virtual) input
       auto load_row = [&](int slot, int rr) {
@@ -354,43 +365,47 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
           uint4 add_raw = make_uint4(0, 0, 0, 0);
           if (addend && out_ok) add_raw = __ldg(reinterpret_cast<const uint4*>(addend + off));  // issued ahead of its use
           load_row((j + 2) % 3, r + 2);
-          float acc[8], xc[8];
+          float2 acc[4], xc[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-              for (int e = 0; e < 8; ++e) acc[e] = fmaf(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
+              for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
           load_plain(x_s, r + 1, col + 1, xc);
           if (relu) {
             if (SIDE) {
-              float xt[8];
-              load_plain(xin_s, r + 1, col + 1, xt);
+              // xin = relu(..) >= 0 was stored as bf16: it is positive iff its bit pattern is non-zero
+              const uint4 xt = *reinterpret_cast<const uint4*>(xin_s + (((r + 1) * (kFX + 2) + col + 1) * 64 + cv * 8) * 2);
+              const uint32_t xu[4] = {xt.x, xt.y, xt.z, xt.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) acc[e] = xt[e] > 0.f ? acc[e] : 0.f;
+              for (int e = 0; e < 4; ++e) {
+                acc[e].x = (xu[e] & 0x0000ffffu) ? acc[e].x : 0.f;
+                acc[e].y = (xu[e] & 0xffff0000u) ? acc[e].y : 0.f;
+              }
             } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) acc[e] = fmaf(xc[e], sc[e], sh[e]) > 0.f ? acc[e] : 0.f;
+              for (int e = 0; e < 4; ++e) {
+                const float2 pre = __ffma2_rn(xc[e], sc[e], sh[e]);
+                acc[e].x = pre.x > 0.f ? acc[e].x : 0.f;
+                acc[e].y = pre.y > 0.f ? acc[e].y : 0.f;
+              }
             }
           }
           if (out_ok) {
-            float av[8];
-            if (addend) unpack8f(add_raw, av);
+            float2 av[4];
+            if (addend) unpack4x2(add_raw, av);
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               // the BatchNorm reduction uses g as the apply kernel will read it back (bf16), without the addend
-              __nv_bfloat162 hh = __floats2bfloat162_rn(acc[2 * e], acc[2 * e + 1]);
-              uint32_t u = *reinterpret_cast<uint32_t*>(&hh);
-              const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
-              s1[2 * e] += a; s1[2 * e + 1] += b;
-              s2[2 * e] = fmaf(a, xc[2 * e], s2[2 * e]); s2[2 * e + 1] = fmaf(b, xc[2 * e + 1], s2[2 * e + 1]);
-              if (addend) {
-                hh = __floats2bfloat162_rn(acc[2 * e] + av[2 * e], acc[2 * e + 1] + av[2 * e + 1]);
-                u = *reinterpret_cast<uint32_t*>(&hh);
-              }
+              uint32_t u = pack_bf16x2(acc[e]);
+              const float2 ab = unpack_bf16x2(u);
+              s12[0][e] = __fadd2_rn(s12[0][e], ab);
+              s12[1][e] = __ffma2_rn(ab, xc[e], s12[1][e]);
+              if (addend) u = pack_bf16x2(__fadd2_rn(acc[e], av[e]));
               pk[e] = u;
             }
             *reinterpret_cast<uint4*>(gout + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -417,15 +432,15 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
         for (int j = 0; j < 3; ++j) {
           const int r = r3 + j;
           load_row((j + 2) % 3, r + 2);
-          float gv[8];  // dd at the output pixel: zero outside the image / channel range
+          float2 gv[4];  // dd at the output pixel: zero outside the image / channel range
           load_plain(dd_s, r + 1, col + 1, gv);
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-              for (int e = 0; e < 8; ++e)
-                wreg[kh * 3 + kw][e] = fmaf(gv[e], win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e]);
+              for (int e = 0; e < 4; ++e)
+                wreg[kh * 3 + kw][e] = __ffma2_rn(gv[e], win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e]);
         }
       }
     }
@@ -436,10 +451,7 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
   if (role == 1) {
     reduce_to_global<9>(wreg, red, tg, cv, cchunk, p.c, dw_out, 2);
   } else if (sums) {
-    float part[2][8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { part[0][e] = s1[e]; part[1][e] = s2[e]; }
-    reduce_to_global<2>(part, red, tg, cv, cchunk, p.c, sums, 1);
+    reduce_to_global<2>(s12, red, tg, cv, cchunk, p.c, sums, 1);
   }
 }
 

@@ -18,6 +18,7 @@ normalisation, unbiased into the running buffers); tests/test_fused_block_*.py c
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -47,8 +48,13 @@ class _Sep:
     __slots__ = ("w9c", "d", "p", "mean1", "invstd1", "scale1", "wpt", "mean2", "invstd2", "scale2", "shift2")
 
 
+# bn2's statistics come out of the pointwise GEMM's epilogue (column sums of the staged output chunk) unless
+# CERVIX_STATS_EPILOGUE=0 asks for the separate reduction pass (kept for A/B timing).
+_STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "1") != "0"
+
+
 def _sep_forward(B, x, in_scale, in_shift, relu_in, dw_w, g1, b1, pw_w, g2, b2, bn1: BnBuffers, bn2: BnBuffers,
-                 stats_in_epilogue: bool = False) -> _Sep:
+                 stats_in_epilogue: bool = _STATS_IN_EPILOGUE) -> _Sep:
     n, h, w, cin = x.shape
     cout = pw_w.shape[0]
     rows = n * h * w

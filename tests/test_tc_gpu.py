@@ -13,10 +13,23 @@ pytestmark = pytest.mark.gpu
 EMU = EmuBackend()
 
 
+@pytest.fixture(params=[1, 2, 4])
+def pairs(request):
+    """CTA pairs per cluster of the forward / data-gradient kernel, forced even for tiny problems so that the
+    weight-multicast paths are exercised on every shape."""
+    from cervix_b200 import _lib
+    lib = _lib.load()
+    assert lib.cvx_conv_tc_set_pairs(request.param, 1) == 0
+    yield request.param
+    assert lib.cvx_conv_tc_set_pairs(1, 0) == 0
+
+
 @pytest.mark.parametrize("idx", range(len(CASES)))
-def test_tc_conv_case(idx):
+def test_tc_conv_case(idx, pairs):
     torch.backends.cudnn.allow_tf32 = False
     kind, n, h, w, cin, cout, k, pad, dil, bias = CASES[idx]
+    if pairs != 1 and kind not in ("fwd", "dgrad"):
+        pytest.skip("pairs per cluster only affects the stride-1 forward / data-gradient kernel")
     B = get_backend()
     g = ConvGeom(n, h, w, cin, cout, k, k, 2 if kind == "fwd_s2" else 1, pad, dil)
     gen = torch.Generator(device="cuda").manual_seed(idx)
