@@ -9,17 +9,19 @@
 //       dw[k][c] += sum dd * act(s*x + t)[shifted by tap k]
 //       sums[0/1][c] += sum g, sum g * x                   the previous BatchNorm's backward reduction
 //
-// Tiling as in dwconv_tiled.cu: a CTA walks over 8x16-pixel tiles of one 64-channel chunk, every halo tile
-// (10 x 18 pixels x 64 ch) arrives by ONE 4-D TMA box load (zero fill = padding / channel tail), 3 tiles in
-// flight.  The backward CTA has two warpgroups reading the same staged tiles: threads 0-127 hold the 9 taps and
-// produce g, threads 128-255 hold the 9 weight-gradient accumulators.
+// A CTA (256 threads = 16 output columns x 16 channel quads) walks over 12x16-pixel tiles of one 64-channel chunk;
+// every halo tile (14 x 18 pixels x 64 ch) arrives by ONE 4-D TMA box load (zero fill = padding / channel tail),
+// 2-3 tiles in flight.  Each thread walks down the 12 rows of its column with a 3x3 register window, four channels
+// wide; the arithmetic runs on FFMA2 / FADD2 (two fp32 lanes per instruction, sm_100) and all shared-memory traffic
+// uses 32-bit shared addresses with immediate offsets, so the 9-tap loops, not address arithmetic, fill the issue slots.
 #include "dwconv_fused.cuh"
 #include "tma_utils.cuh"
 
 namespace cvx {
 
 constexpr int kFY = 12, kFX = 16;                     // output tile; rows are walked 3 at a time (window period)
-constexpr int kFTile = (kFY + 2) * (kFX + 2) * 128;   // 32256 bytes: one halo tile of 64 channels
+constexpr int kFRow = (kFX + 2) * 128;                // bytes of one halo row (18 pixels x 64 ch)
+constexpr int kFTile = (kFY + 2) * kFRow;             // 32256 bytes: one halo tile of 64 channels
 constexpr int kFwdStages = 3;                         // forward: 3 tiles in flight, 2 CTAs per SM
 static_assert(kFY % 3 == 0, "the row loop is unrolled over the 3-row register window");
 
@@ -29,20 +31,13 @@ struct DwFParams {
   int relu_in;
 };
 
-__device__ __forceinline__ void unpack8f(const uint4& r, float (&v)[8]) {
-  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[2 * i] = __uint_as_float(u[i] << 16);
-    v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
-  }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
 }
-// 8 bf16 -> 4 packed fp32 pairs: the arithmetic below runs on FFMA2 / FADD2 (two fp32 lanes per instruction,
-// sm_100), which halves the issue slots of the 9-tap loops that bound these kernels
-__device__ __forceinline__ void unpack4x2(const uint4& r, float2 (&v)[4]) {
-  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(u[i] << 16), __uint_as_float(u[i] & 0xffff0000u));
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
   __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
@@ -51,76 +46,76 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float2 v) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
+// four bf16 channels at a shared address -> two packed fp32 pairs
+__device__ __forceinline__ void load4(uint32_t addr, float2 (&v)[2]) {
+  const uint2 r = lds64(addr);
+  v[0] = unpack_bf16x2(r.x);
+  v[1] = unpack_bf16x2(r.y);
+}
+__device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
 
-// reduce per-thread [K][4] float2 partials over the 16 column-threads that share a channel vector, then fp64 atomics
+// reduce per-thread [K][2] float2 partials over the 16 column-threads that share a channel quad, then fp64 atomics
 template <int K>
-__device__ __forceinline__ void reduce_to_global(float2 (&part)[K][4], float* red /* [K][64] smem */, int t_in_group,
-                                                 int cv, int cchunk, int C, double* out, int group_bar) {
-  for (int i = t_in_group; i < K * 64; i += 128) red[i] = 0.f;
-  asm volatile("bar.sync %0, 128;" ::"r"(group_bar) : "memory");
+__device__ __forceinline__ void reduce4_to_global(float2 (&part)[K][2], float* red /* [K][64] smem */, int t, int cq,
+                                                  int cchunk, int C, double* out) {
+  for (int i = t; i < K * 64; i += 256) red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < K; ++k)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 4; ++e) {
       float v = (e & 1) ? part[k][e >> 1].y : part[k][e >> 1].x;
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((t_in_group & 31) < 8) atomicAdd(&red[k * 64 + cv * 8 + e], v);
+      if ((t & 31) < 16) atomicAdd(&red[k * 64 + cq * 4 + e], v);
     }
-  asm volatile("bar.sync %0, 128;" ::"r"(group_bar) : "memory");
-  for (int i = t_in_group; i < K * 64; i += 128) {
+  __syncthreads();
+  for (int i = t; i < K * 64; i += 256) {
     const int k = i / 64, cc = cchunk * 64 + (i % 64);
     if (cc < C) atomicAdd(out + (size_t)k * C + cc, (double)red[i]);
   }
+  __syncthreads();
 }
 
-// one 16-byte channel vector of the (virtual) depthwise input act(s*x+t) at halo-tile position (rr, cc)
-template <bool AFFINE>
-__device__ __forceinline__ void load_virtual(const uint8_t* tile, int rr, int cc, int cv, const float2 (&sc)[4],
-                                             const float2 (&sh)[4], bool relu, bool valid, float2 (&out)[4]) {
-  unpack4x2(*reinterpret_cast<const uint4*>(tile + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
-  if (AFFINE) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 v = __ffma2_rn(out[e], sc[e], sh[e]);
-      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
-      out[e] = valid ? v : make_float2(0.f, 0.f);   // zero padding applies to the virtual tensor, not to the raw one
-    }
-  } else if (relu) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) { out[e].x = fmaxf(out[e].x, 0.f); out[e].y = fmaxf(out[e].y, 0.f); }
-  }
+// tile index -> (image, tile row, tile column)
+__device__ __forceinline__ void tile_coords(const DwFParams& p, int tile, int& tx, int& ty, int& img) {
+  tx = tile % p.tiles_x;
+  const int t1 = tile / p.tiles_x;
+  ty = t1 % p.tiles_y;
+  img = t1 / p.tiles_y;
 }
 
 // ------------------------------------------------------------------------------------------ forward
+// AFFINE: a pre-pass turns the staged halo tile into the virtual input act(s*x+t) ONCE per element (zero outside the
+// image: the padding applies to the virtual tensor), instead of once per tap column in the window loads.
 template <bool AFFINE>
-__global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(256, 2) dwf_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
                                                          const float* __restrict__ w9c, const float* __restrict__ in_scale,
                                                          const float* __restrict__ in_shift, __nv_bfloat16* __restrict__ dst,
                                                          double* __restrict__ stats, DwFParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFwdStages * kFTile);
-  const uint32_t smem_base = smem_u32(smem), bar0 = smem_u32(bars);
+  const uint32_t smem_base = smem_u32(smem), bar0 = smem_base + kFwdStages * kFTile;
 
   const int t = threadIdx.x;
-  const int cv = t & 7, col = t >> 3;
+  const int cq = t & 15, col = t >> 4;
   const int cchunk = blockIdx.y;
-  const int c0 = cchunk * 64 + cv * 8;
+  const int c0 = cchunk * 64 + cq * 4;
   const bool ch_ok = c0 < p.c;
   const bool relu = p.relu_in != 0;
+  const uint32_t thr_off = col * 128 + cq * 8;   // this thread's (column, quad) inside a halo row
 
-  float2 wreg[9][4], sc[4], sh[4], s12[2][4];
+  float2 wreg[9][2], sc[2], sh[2], s12[2][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    sc[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_scale + c0 + 2 * i), __ldg(in_scale + c0 + 2 * i + 1)) : make_float2(1.f, 1.f);
-    sh[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_shift + c0 + 2 * i), __ldg(in_shift + c0 + 2 * i + 1)) : make_float2(0.f, 0.f);
+  for (int i = 0; i < 2; ++i) {
+    const int c = c0 + 2 * i;
+    sc[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_scale + c), __ldg(in_scale + c + 1)) : make_float2(1.f, 1.f);
+    sh[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_shift + c), __ldg(in_shift + c + 1)) : make_float2(0.f, 0.f);
     s12[0][i] = s12[1][i] = make_float2(0.f, 0.f);
   }
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
       wreg[k][i] = ch_ok ? make_float2(__ldg(w9c + k * p.c + c0 + 2 * i), __ldg(w9c + k * p.c + c0 + 2 * i + 1))
                          : make_float2(0.f, 0.f);
 
@@ -133,10 +128,8 @@ __global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__
 
   const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto issue = [&](int i) {  // thread 0 only
-    const int tile = blockIdx.x + i * gridDim.x;
-    const int tx = tile % p.tiles_x;
-    const int t1 = tile / p.tiles_x;
-    const int ty = t1 % p.tiles_y, img = t1 / p.tiles_y;
+    int tx, ty, img;
+    tile_coords(p, blockIdx.x + i * gridDim.x, tx, ty, img);
     const int s = i % kFwdStages;
     mbar_expect_tx(bar0 + 8 * s, kFTile);
     tma_load_4d(smem_base + s * kFTile, &tmap, bar0 + 8 * s, cchunk * 64, tx * kFX - 1, ty * kFY - 1, img);
@@ -151,68 +144,94 @@ __global__ void __launch_bounds__(128, 2) dwf_fwd_kernel(const __grid_constant__
     }
     const int s = i % kFwdStages;
     mbar_wait(bar0 + 8 * s, (i / kFwdStages) & 1);
-    const uint8_t* tile_s = smem + s * kFTile;
-
-    const int tile = blockIdx.x + i * gridDim.x;
-    const int tx = tile % p.tiles_x;
-    const int t1 = tile / p.tiles_x;
-    const int ty = t1 % p.tiles_y, img = t1 / p.tiles_y;
+    const uint32_t tile_a = smem_base + s * kFTile;
+    int tx, ty, img;
+    tile_coords(p, blockIdx.x + i * gridDim.x, tx, ty, img);
     const int ox = tx * kFX + col, oy0 = ty * kFY;
-    const bool col_ok = ch_ok && ox < p.w;
-    bool cvalid[3];
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) cvalid[kw] = (ox - 1 + kw) >= 0 && (ox - 1 + kw) < p.w;
 
-    float2 win[3][3][4];
-    auto load_row = [&](int slot, int rr) {
-      const int iy = oy0 - 1 + rr;
-      const bool rvalid = iy >= 0 && iy < p.h;
+    if (AFFINE) {
+      // ---- pre-pass over the 14 x 18 x 16 quads of the halo tile; v & 15 == cq in every iteration
+      int rr = t / ((kFX + 2) * 16), rem = t - rr * ((kFX + 2) * 16);
+      int cc = rem >> 4;
+      uint32_t a = tile_a + rr * kFRow + cc * 128 + cq * 8;
+      for (; rr < kFY + 2; ) {
+        const int iy = oy0 - 1 + rr, ix = tx * kFX - 1 + cc;
+        if (iy > p.h) break;  // rows below the image feed nothing
+        const bool valid = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+        uint2 out = make_uint2(0u, 0u);
+        if (valid) {
+          const uint2 r = lds64(a);
+          float2 v0 = __ffma2_rn(unpack_bf16x2(r.x), sc[0], sh[0]), v1 = __ffma2_rn(unpack_bf16x2(r.y), sc[1], sh[1]);
+          if (relu) { v0 = relu2(v0); v1 = relu2(v1); }
+          out = make_uint2(pack_bf16x2(v0), pack_bf16x2(v1));
+        }
+        sts64(a, out);
+        // advance by 256 threads = 16 pixels
+        cc += 16; a += 16 * 128;
+        if (cc >= kFX + 2) { cc -= kFX + 2; ++rr; }
+      }
+      __syncthreads();
+    }
+
+    if (ch_ok && ox < p.w) {
+      const uint32_t wa = tile_a + thr_off;
+      float2 win[3][3][2];
+      auto load_row = [&](int slot, uint32_t ra) {
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw)
-        load_virtual<AFFINE>(tile_s, rr, col + kw, cv, sc, sh, relu, rvalid && cvalid[kw], win[slot][kw]);
-    };
-    load_row(0, 0);
-    load_row(1, 1);
+        for (int kw = 0; kw < 3; ++kw) {
+          load4(ra + kw * 128, win[slot][kw]);
+          if (!AFFINE && relu) { win[slot][kw][0] = relu2(win[slot][kw][0]); win[slot][kw][1] = relu2(win[slot][kw][1]); }
+        }
+      };
+      load_row(0, wa);
+      load_row(1, wa + kFRow);
+      uint32_t ra = wa + 2 * kFRow;
+      __nv_bfloat16* out = dst + (((size_t)img * p.h + oy0) * p.w + ox) * p.c + c0;
+      const size_t out_row = (size_t)p.w * p.c;
 #pragma unroll 1
-    for (int r3 = 0; r3 < kFY; r3 += 3) {
-      if (oy0 + r3 >= p.h) break;  // the rest of this tile lies below the image
+      for (int r3 = 0; r3 < kFY; r3 += 3) {
+        if (oy0 + r3 >= p.h) break;  // the rest of this tile lies below the image
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int r = r3 + j;
-        load_row((j + 2) % 3, r + 2);
-        float2 acc[4];
+        for (int j = 0; j < 3; ++j) {
+          load_row((j + 2) % 3, ra);
+          ra += kFRow;
+          float2 acc[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
+          for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw)
+              for (int e = 0; e < 2; ++e) acc[e] = __ffma2_rn(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
+          if (oy0 + r3 + j < p.h) {
+            uint32_t pk[2];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
-        if (col_ok && (oy0 + r) < p.h) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            pk[e] = pack_bf16x2(acc[e]);
-            const float2 ab = unpack_bf16x2(pk[e]);
-            s12[0][e] = __fadd2_rn(s12[0][e], ab);
-            s12[1][e] = __ffma2_rn(ab, ab, s12[1][e]);
+            for (int e = 0; e < 2; ++e) {
+              pk[e] = pack_bf16x2(acc[e]);
+              const float2 ab = unpack_bf16x2(pk[e]);
+              s12[0][e] = __fadd2_rn(s12[0][e], ab);
+              s12[1][e] = __ffma2_rn(ab, ab, s12[1][e]);
+            }
+            *reinterpret_cast<uint2*>(out) = make_uint2(pk[0], pk[1]);
           }
-          *reinterpret_cast<uint4*>(dst + (((size_t)img * p.h + oy0 + r) * p.w + ox) * p.c + c0) =
-              make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          out += out_row;
         }
       }
     }
     __syncthreads();
   }
 
-  if (stats) reduce_to_global<2>(s12, reinterpret_cast<float*>(smem), t, cv, cchunk, p.c, stats, 1);
+  if (stats) reduce4_to_global<2>(s12, reinterpret_cast<float*>(smem), t, cq, cchunk, p.c, stats);
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// SIDE: the incoming gradient is not materialised either - it is assembled on load from the pointwise conv's
-// data gradient e and the depthwise output d:  dd = e + negk*d + kmean  (bn1's backward, see sepconv.cu), zero
-// outside the image.
+// The same 3x3 window of the incoming gradient dd feeds BOTH gradients:
+//     g[q]        = sum_{i,j} dd[q + (i-1, j-1)] * w[2-i][2-j]          (data gradient, flipped taps)
+//     dw[2-i][2-j] += dd[q + (i-1, j-1)] * xin[q]                        (weight gradient in scatter form)
+// so per output element there are 3 shared-memory loads of dd, one of x, and 18 FMAs - no second warpgroup
+// re-reading the tile, no role imbalance at the tile barrier.
+// SIDE: the incoming gradient is not materialised - a pre-pass assembles it in place from the pointwise conv's data
+// gradient e and the depthwise output d:  dd = e + negk*d + kmean  (bn1's backward, see sepconv.cu), zero outside
+// the image (TMA's zero fill covers the plain case).
 template <bool AFFINE, bool SIDE>
 __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__ CUtensorMap tmap_dd,
                                                          const __grid_constant__ CUtensorMap tmap_d,
@@ -228,22 +247,19 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
   constexpr int kStages = SIDE ? 2 : 3;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStage);
-  const uint32_t smem_base = smem_u32(smem), bar0 = smem_u32(bars);
+  const uint32_t smem_base = smem_u32(smem), bar0 = smem_base + kStages * kStage;
 
   const int t = threadIdx.x;
-  const int role = t >> 7;           // 0: data gradient, 1: weight gradient
-  const int tg = t & 127;
-  const int cv = tg & 7, col = tg >> 3;
+  const int cq = t & 15, col = t >> 4;   // channel quad inside the 64-channel chunk, output column inside the tile
   const int cchunk = blockIdx.y;
-  const int c0 = cchunk * 64 + cv * 8;
-  const bool ch_ok = c0 < p.c;
+  const int c0 = cchunk * 64 + cq * 4;
+  const bool ch_ok = c0 < p.c;           // C % 8 == 0: quads are whole
   const bool relu = p.relu_in != 0;
+  const uint32_t thr_off = col * 128 + cq * 8;
 
-  // role 0: wreg = flipped taps ; role 1: wreg = weight-gradient accumulators
-  float2 wreg[9][4], sc[4], sh[4], nk[4], km[4], s12[2][4];
+  float2 wf[9][2], acc[9][2], sc[2], sh[2], nk[2], km[2], s12[2][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 2; ++i) {
     const int c = c0 + 2 * i;
     sc[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_scale + c), __ldg(in_scale + c + 1)) : make_float2(1.f, 1.f);
     sh[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_shift + c), __ldg(in_shift + c + 1)) : make_float2(0.f, 0.f);
@@ -254,9 +270,12 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      wreg[k][i] = (role == 0 && ch_ok) ? make_float2(__ldg(w9c + (8 - k) * p.c + c0 + 2 * i), __ldg(w9c + (8 - k) * p.c + c0 + 2 * i + 1))
-                                        : make_float2(0.f, 0.f);
+    for (int i = 0; i < 2; ++i) {
+      // window position k = (i_row, j_col) pairs with the flipped tap 8-k
+      wf[k][i] = ch_ok ? make_float2(__ldg(w9c + (8 - k) * p.c + c0 + 2 * i), __ldg(w9c + (8 - k) * p.c + c0 + 2 * i + 1))
+                       : make_float2(0.f, 0.f);
+      acc[k][i] = make_float2(0.f, 0.f);
+    }
 
   if (t == 0) {
     tma_prefetch_desc(&tmap_dd);
@@ -269,10 +288,8 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
 
   const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto issue = [&](int i) {  // thread 0 only
-    const int tile = blockIdx.x + i * gridDim.x;
-    const int tx = tile % p.tiles_x;
-    const int t1 = tile / p.tiles_x;
-    const int ty = t1 % p.tiles_y, img = t1 / p.tiles_y;
+    int tx, ty, img;
+    tile_coords(p, blockIdx.x + i * gridDim.x, tx, ty, img);
     const int s = i % kStages;
     const uint32_t dstp = smem_base + s * kStage;
     mbar_expect_tx(bar0 + 8 * s, kStage);
@@ -290,169 +307,108 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
     }
     const int s = i % kStages;
     mbar_wait(bar0 + 8 * s, (i / kStages) & 1);
-    const uint8_t* dd_s = smem + s * kStage;
-    const uint8_t* x_s = dd_s + kFTile;
-    const uint8_t* d_s = dd_s + 2 * kFTile;
-
-    const int tile = blockIdx.x + i * gridDim.x;
-    const int tx = tile % p.tiles_x;
-    const int t1 = tile / p.tiles_x;
-    const int ty = t1 % p.tiles_y, img = t1 / p.tiles_y;
+    const uint32_t dd_a = smem_base + s * kStage;
+    int tx, ty, img;
+    tile_coords(p, blockIdx.x + i * gridDim.x, tx, ty, img);
     const int ox = tx * kFX + col, oy0 = ty * kFY;
-    const bool col_ok = ch_ok && ox < p.w;
-    bool cvalid[3];
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) cvalid[kw] = (ox - 1 + kw) >= 0 && (ox - 1 + kw) < p.w;
 
     if (SIDE) {
-      // ---- pre-pass, all 256 threads: assemble each halo element ONCE instead of once per tap and per role:
-      //   dd  = e + negk*d + kmean  (bn1's backward)          -> written over the e tile
-      //   xin = act(in_scale*x + in_shift)  (virtual input)   -> written over the d tile
-      // both zero outside the image; thread t always handles channel vector t & 7 (= cv).
-      uint8_t* e_w = smem + s * kStage;
-      uint8_t* d_w = e_w + 2 * kFTile;
-      const int ox0 = tx * kFX;
-      for (int v = t; v < (kFY + 2) * (kFX + 2) * 8; v += 256) {
-        const int pix = v >> 3;
-        const int rr = pix / (kFX + 2), cc = pix - rr * (kFX + 2);
-        const int iy = oy0 - 1 + rr, ix = ox0 - 1 + cc;
-        if (iy > p.h) break;  // rows below the image feed nothing (warp-uniform up to the last partial row)
+      // ---- pre-pass: dd = e + negk*d + kmean over the halo tile, in place, zero outside the image
+      int rr = t / ((kFX + 2) * 16), rem = t - rr * ((kFX + 2) * 16);
+      int cc = rem >> 4;
+      uint32_t a = dd_a + rr * kFRow + cc * 128 + cq * 8;
+      for (; rr < kFY + 2; ) {
+        const int iy = oy0 - 1 + rr, ix = tx * kFX - 1 + cc;
+        if (iy > p.h) break;  // rows below the image feed nothing
         const bool valid = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-        const int off = (pix * 64 + cv * 8) * 2;
-        uint32_t pd[4] = {0u, 0u, 0u, 0u}, px[4] = {0u, 0u, 0u, 0u};
+        uint2 out = make_uint2(0u, 0u);
         if (valid) {
-          float2 ev[4], dv[4], xv[4];
-          unpack4x2(*reinterpret_cast<const uint4*>(e_w + off), ev);
-          unpack4x2(*reinterpret_cast<const uint4*>(d_w + off), dv);
-          unpack4x2(*reinterpret_cast<const uint4*>(x_s + off), xv);
-#pragma unroll
-          for (int e2 = 0; e2 < 4; ++e2) {
-            const float2 a = __ffma2_rn(nk[e2], dv[e2], __fadd2_rn(ev[e2], km[e2]));
-            float2 b = AFFINE ? __ffma2_rn(xv[e2], sc[e2], sh[e2]) : xv[e2];
-            if (relu) { b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); }
-            pd[e2] = pack_bf16x2(a);
-            px[e2] = pack_bf16x2(b);
-          }
+          const uint2 e = lds64(a), d = lds64(a + 2 * kFTile);
+          out.x = pack_bf16x2(__ffma2_rn(nk[0], unpack_bf16x2(d.x), __fadd2_rn(unpack_bf16x2(e.x), km[0])));
+          out.y = pack_bf16x2(__ffma2_rn(nk[1], unpack_bf16x2(d.y), __fadd2_rn(unpack_bf16x2(e.y), km[1])));
         }
-        *reinterpret_cast<uint4*>(e_w + off) = make_uint4(pd[0], pd[1], pd[2], pd[3]);
-        *reinterpret_cast<uint4*>(d_w + off) = make_uint4(px[0], px[1], px[2], px[3]);
+        sts64(a, out);
+        cc += 16; a += 16 * 128;
+        if (cc >= kFX + 2) { cc -= kFX + 2; ++rr; }
       }
       __syncthreads();
     }
-    const uint8_t* xin_s = d_s;  // SIDE only: the transformed input tile
 
-    auto load_plain = [&](const uint8_t* tile, int rr, int cc, float2 (&out)[4]) {
-      unpack4x2(*reinterpret_cast<const uint4*>(tile + ((rr * (kFX + 2) + cc) * 64 + cv * 8) * 2), out);
-    };
-
-    float2 win[3][3][4];
-    if (role == 0) {
-      // ---- data gradient: g = sum_k dd[shifted] * w[8-k], masked by the ReLU of the (virtual) input
-      auto load_row = [&](int slot, int rr) {
+    if (ch_ok && ox < p.w) {
+      const uint32_t wa = dd_a + thr_off;
+      float2 win[3][3][2];
+      auto load_row = [&](int slot, uint32_t ra) {
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) load_plain(dd_s, rr, col + kw, win[slot][kw]);
+        for (int kw = 0; kw < 3; ++kw) load4(ra + kw * 128, win[slot][kw]);
       };
-      load_row(0, 0);
-      load_row(1, 1);
+      load_row(0, wa);
+      load_row(1, wa + kFRow);
+      uint32_t ra = wa + 2 * kFRow;                         // next window row
+      uint32_t xa = wa + kFTile + kFRow + 128;              // x at the output pixel (row r+1, column col+1)
+      size_t off = (((size_t)img * p.h + oy0) * p.w + ox) * p.c + c0;
+      const size_t out_row = (size_t)p.w * p.c;
 #pragma unroll 1
       for (int r3 = 0; r3 < kFY; r3 += 3) {
         if (oy0 + r3 >= p.h) break;  // the rest of this tile lies below the image
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const int r = r3 + j;
-          const bool out_ok = col_ok && (oy0 + r) < p.h;
-          const size_t off = (((size_t)img * p.h + oy0 + r) * p.w + ox) * p.c + c0;
-          uint4 add_raw = make_uint4(0, 0, 0, 0);
-          if (addend && out_ok) add_raw = __ldg(reinterpret_cast<const uint4*>(addend + off));  // issued ahead of its use
-          load_row((j + 2) % 3, r + 2);
-          float2 acc[4], xc[4];
+          const bool row_ok = oy0 + r3 + j < p.h;
+          uint2 add_raw = make_uint2(0u, 0u);
+          if (addend && row_ok) add_raw = __ldg(reinterpret_cast<const uint2*>(addend + off));  // issued ahead of its use
+          load_row((j + 2) % 3, ra);
+          ra += kFRow;
+          float2 xc[2], xin[2], g[2];
+          load4(xa, xc);
+          xa += kFRow;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[e] = make_float2(0.f, 0.f);
+          for (int e = 0; e < 2; ++e) {
+            xin[e] = AFFINE ? __ffma2_rn(xc[e], sc[e], sh[e]) : xc[e];
+            if (relu) xin[e] = relu2(xin[e]);
+            if (!row_ok) xin[e] = make_float2(0.f, 0.f);   // rows below the image feed nothing
+            g[e] = make_float2(0.f, 0.f);
+          }
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
-              for (int e = 0; e < 4; ++e) acc[e] = __ffma2_rn(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
-          load_plain(x_s, r + 1, col + 1, xc);
-          if (relu) {
-            if (SIDE) {
-              // xin = relu(..) >= 0 was stored as bf16: it is positive iff its bit pattern is non-zero
-              const uint4 xt = *reinterpret_cast<const uint4*>(xin_s + (((r + 1) * (kFX + 2) + col + 1) * 64 + cv * 8) * 2);
-              const uint32_t xu[4] = {xt.x, xt.y, xt.z, xt.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                acc[e].x = (xu[e] & 0x0000ffffu) ? acc[e].x : 0.f;
-                acc[e].y = (xu[e] & 0xffff0000u) ? acc[e].y : 0.f;
+              for (int e = 0; e < 2; ++e) {
+                const float2 d = win[(j + kh) % 3][kw][e];
+                g[e] = __ffma2_rn(d, wf[kh * 3 + kw][e], g[e]);
+                acc[kh * 3 + kw][e] = __ffma2_rn(d, xin[e], acc[kh * 3 + kw][e]);
               }
-            } else {
+          if (row_ok) {
+            uint32_t pk[2];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 pre = __ffma2_rn(xc[e], sc[e], sh[e]);
-                acc[e].x = pre.x > 0.f ? acc[e].x : 0.f;
-                acc[e].y = pre.y > 0.f ? acc[e].y : 0.f;
+            for (int e = 0; e < 2; ++e) {
+              if (relu) {
+                g[e].x = xin[e].x > 0.f ? g[e].x : 0.f;
+                g[e].y = xin[e].y > 0.f ? g[e].y : 0.f;
               }
-            }
-          }
-          if (out_ok) {
-            float2 av[4];
-            if (addend) unpack4x2(add_raw, av);
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
               // the BatchNorm reduction uses g as the apply kernel will read it back (bf16), without the addend
-              uint32_t u = pack_bf16x2(acc[e]);
+              uint32_t u = pack_bf16x2(g[e]);
               const float2 ab = unpack_bf16x2(u);
               s12[0][e] = __fadd2_rn(s12[0][e], ab);
               s12[1][e] = __ffma2_rn(ab, xc[e], s12[1][e]);
-              if (addend) u = pack_bf16x2(__fadd2_rn(acc[e], av[e]));
+              if (addend) u = pack_bf16x2(__fadd2_rn(g[e], unpack_bf16x2(e == 0 ? add_raw.x : add_raw.y)));
               pk[e] = u;
             }
-            *reinterpret_cast<uint4*>(gout + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint2*>(gout + off) = make_uint2(pk[0], pk[1]);
           }
-        }
-      }
-    } else {
-      // ---- weight gradient: dw[k] += dd[centre] * act(s*x+t)[shifted by k]
-      auto load_row = [&](int slot, int rr) {
-        const int iy = oy0 - 1 + rr;
-        const bool rvalid = iy >= 0 && iy < p.h;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          if (SIDE) load_plain(xin_s, rr, col + kw, win[slot][kw]);
-          else load_virtual<AFFINE>(x_s, rr, col + kw, cv, sc, sh, relu, rvalid && cvalid[kw], win[slot][kw]);
-        }
-      };
-      load_row(0, 0);
-      load_row(1, 1);
-#pragma unroll 1
-      for (int r3 = 0; r3 < kFY; r3 += 3) {
-        if (oy0 + r3 >= p.h) break;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int r = r3 + j;
-          load_row((j + 2) % 3, r + 2);
-          float2 gv[4];  // dd at the output pixel: zero outside the image / channel range
-          load_plain(dd_s, r + 1, col + 1, gv);
-#pragma unroll
-          for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                wreg[kh * 3 + kw][e] = __ffma2_rn(gv[e], win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e]);
+          off += out_row;
         }
       }
     }
-    __syncthreads();  // both roles are done with slot s before it is refilled
+    __syncthreads();  // everyone is done with slot s before it is refilled
   }
 
-  float* red = reinterpret_cast<float*>(smem) + role * (9 * 64);
-  if (role == 1) {
-    reduce_to_global<9>(wreg, red, tg, cv, cchunk, p.c, dw_out, 2);
-  } else if (sums) {
-    reduce_to_global<2>(s12, red, tg, cv, cchunk, p.c, sums, 1);
-  }
+  // acc[k] pairs window position k with tap 8-k
+  float2 dwp[9][2];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { dwp[k][0] = acc[8 - k][0]; dwp[k][1] = acc[8 - k][1]; }
+  float* red = reinterpret_cast<float*>(smem);
+  reduce4_to_global<9>(dwp, red, t, cq, cchunk, p.c, dw_out);
+  if (sums) reduce4_to_global<2>(s12, red, t, cq, cchunk, p.c, sums);
 }
 
 static bool dwf_supported(const cvx_conv_desc* d) {
@@ -476,7 +432,7 @@ int dwf_fwd_launch(const cvx_conv_desc* d, const void* x, const float* w9c, cons
   CUtensorMap map;
   if (int rc = make_act_map(&map, x, d->n, d->h, d->w, d->cin, kFX + 2, kFY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   const int chunks = (d->cin + 63) / 64;
-  int gx = (kNumSMs * 2) / chunks;
+  int gx = (kNumSMs * 2) / chunks;   // two 256-thread CTAs per SM
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
   constexpr int smem = kFwdStages * kFTile + 128 + 64;
@@ -488,9 +444,9 @@ int dwf_fwd_launch(const cvx_conv_desc* d, const void* x, const float* w9c, cons
   }
   if (stats) CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cin, st));
   if (in_scale)
-    dwf_fwd_kernel<true><<<dim3(gx, chunks), 128, smem, st>>>(map, w9c, in_scale, in_shift, (__nv_bfloat16*)y, stats, p);
+    dwf_fwd_kernel<true><<<dim3(gx, chunks), 256, smem, st>>>(map, w9c, in_scale, in_shift, (__nv_bfloat16*)y, stats, p);
   else
-    dwf_fwd_kernel<false><<<dim3(gx, chunks), 128, smem, st>>>(map, w9c, nullptr, nullptr, (__nv_bfloat16*)y, stats, p);
+    dwf_fwd_kernel<false><<<dim3(gx, chunks), 256, smem, st>>>(map, w9c, nullptr, nullptr, (__nv_bfloat16*)y, stats, p);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

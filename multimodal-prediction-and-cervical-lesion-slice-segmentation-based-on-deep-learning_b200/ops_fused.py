@@ -48,9 +48,10 @@ class _Sep:
     __slots__ = ("w9c", "d", "p", "mean1", "invstd1", "scale1", "wpt", "mean2", "invstd2", "scale2", "shift2")
 
 
-# bn2's statistics come out of the pointwise GEMM's epilogue (column sums of the staged output chunk) unless
-# CERVIX_STATS_EPILOGUE=0 asks for the separate reduction pass (kept for A/B timing).
-_STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "1") != "0"
+# CERVIX_STATS_EPILOGUE=1 takes bn2's statistics from the pointwise GEMM's epilogue (column sums of the staged
+# output chunk) instead of a separate reduction pass; measured on B200 the two are within 1 % of each other
+# (the GEMM epilogue is on that kernel's critical path), so the separate pass stays the default.
+_STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "0") == "1"
 
 
 def _sep_forward(B, x, in_scale, in_shift, relu_in, dw_w, g1, b1, pw_w, g2, b2, bn1: BnBuffers, bn2: BnBuffers,

@@ -18,6 +18,7 @@ ap.add_argument("--c", type=int, default=728)
 ap.add_argument("--only", default="")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--no-flush", action="store_true")
+ap.add_argument("--graph", action="store_true", help="time 10 launches replayed as a CUDA graph (no host latency)")
 args = ap.parse_args()
 B = get_backend()
 n, h, c = args.batch, args.hw, args.c
@@ -60,14 +61,35 @@ for name, (fn, passes) in OPS.items():
         continue
     for _ in range(3):
         fn()
+    torch.cuda.synchronize()
     ts = []
-    for _ in range(args.reps):
-        if not args.no_flush:
-            flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record()
+    if args.graph:
+        # GPU time without host launch latency: `inner` back-to-back launches replayed as one CUDA graph
+        inner = 10
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            fn()
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(inner):
+                    fn()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        for _ in range(max(3, args.reps // 4)):
+            if not args.no_flush:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) / inner)
+    else:
+        for _ in range(args.reps):
+            if not args.no_flush:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
     ts.sort()
     ms = ts[len(ts) // 2]
     extra = "  %6.0f TF/s" % (gf / ms) if "conv" in name else ""
