@@ -274,6 +274,13 @@ CVX_API int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int6
 CVX_API int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 
+/* ---- inference post-processing (reference: deeplab.py:141-154 detect_image, :304-345 get_miou_png) ----------
+ * softmax over the c class planes of ONE image's logits [c][h][w] (fp32, NCHW) -> crop (crop_y, crop_x, crop_h, crop_w:
+ * the un-letterboxed region) -> bilinear resize to out_h x out_w with cv2.resize(INTER_LINEAR) coordinates ->
+ * argmax.  cls[out_h][out_w] receives the class index; probs (nullable) the resized probabilities [out_h][out_w][c]. */
+CVX_API int cvx_seg_postprocess(const float* logits, int c, int h, int w, int crop_y, int crop_x, int crop_h, int crop_w,
+                                int out_h, int out_w, unsigned char* cls, float* probs, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -625,6 +625,19 @@ class CudaBackend:
         check(self.lib.cvx_sgd_step(_p(p), _p(g), _p(buf), p.numel(), float(lr), float(momentum), float(wd),
                                     int(nesterov), int(first_step), float(grad_scale), self._stream()), "cvx_sgd_step")
 
+    # ------------------------------------------------------------------ inference post-processing
+    def seg_postprocess(self, logits, crop, out_hw, want_probs: bool = False):
+        """logits [C,H,W] fp32 (one image, NCHW) -> (uint8 class map [out_h,out_w], probabilities or None)."""
+        self._chk(logits)
+        c, h, w = logits.shape
+        cy, cx, ch, cw = (int(v) for v in crop)
+        oh, ow = int(out_hw[0]), int(out_hw[1])
+        cls = torch.empty((oh, ow), dtype=torch.uint8, device=logits.device)
+        probs = torch.empty((oh, ow, c), dtype=torch.float32, device=logits.device) if want_probs else None
+        check(self.lib.cvx_seg_postprocess(_p(logits), c, h, w, cy, cx, ch, cw, oh, ow, _p(cls), _p(probs), self._stream()),
+              "cvx_seg_postprocess")
+        return cls, probs
+
 
 _BACKEND = None
 

@@ -1,0 +1,6 @@
+"""Drop-in for the reference's ``nets/deeplabv3_training.py``: re-exports the B200 implementation."""
+import _bootstrap  # noqa: F401
+from cervix_b200.nets.deeplabv3_training import *  # noqa: F401,F403
+from cervix_b200.nets import deeplabv3_training as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

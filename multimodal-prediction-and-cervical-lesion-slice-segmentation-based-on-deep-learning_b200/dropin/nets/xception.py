@@ -1,0 +1,6 @@
+"""Drop-in for the reference's ``nets/xception.py``: re-exports the B200 implementation."""
+import _bootstrap  # noqa: F401
+from cervix_b200.nets.xception import *  # noqa: F401,F403
+from cervix_b200.nets import xception as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

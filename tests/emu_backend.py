@@ -535,3 +535,34 @@ class EmuBackend:
                 buf.mul_(momentum).add_(gi)
             gi = gi + momentum * buf if nesterov else buf
         p.sub_(lr * gi)
+
+    # ------------------------------------------------------------------ inference post-processing
+    def seg_postprocess(self, logits, crop, out_hw, want_probs=False):
+        """Plain-torch statement of csrc/postprocess.cu (cv2.resize INTER_LINEAR coordinates, fp32)."""
+        c, h, w = logits.shape
+        cy, cx, ch, cw = (int(v) for v in crop)
+        oh, ow = int(out_hw[0]), int(out_hw[1])
+        pr = torch.softmax(logits.float(), 0)[:, cy:cy + ch, cx:cx + cw]
+
+        def coords(n_out, n_src):
+            scale = torch.tensor(float(n_src) / float(n_out), dtype=torch.float64).float()
+            f = (torch.arange(n_out, dtype=torch.float32) + 0.5) * scale - 0.5
+            s = torch.floor(f)
+            f = f - s
+            s = s.long()
+            lo = s < 0
+            s = torch.where(lo, torch.zeros_like(s), s)
+            f = torch.where(lo, torch.zeros_like(f), f)
+            hi = s >= n_src - 1
+            s = torch.where(hi, torch.full_like(s, n_src - 1), s)
+            f = torch.where(hi, torch.zeros_like(f), f)
+            return s, torch.clamp(s + 1, max=n_src - 1), f
+
+        y0, y1, fy = coords(oh, ch)
+        x0, x1, fx = coords(ow, cw)
+        top = pr[:, y0][:, :, x0] * (1 - fx) + pr[:, y0][:, :, x1] * fx
+        bot = pr[:, y1][:, :, x0] * (1 - fx) + pr[:, y1][:, :, x1] * fx
+        out = top * (1 - fy)[None, :, None] + bot * fy[None, :, None]
+        cls = out.argmax(0).to(torch.uint8)
+        return cls, (out.permute(1, 2, 0).contiguous() if want_probs else None)
+
