@@ -144,6 +144,72 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- four-modal classifier leg
+def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int = 512):
+    """BASELINE configs[1]: one training step of the four-modal severity classifier on `patients` patients -
+    three colposcopic images per patient (resize 1024 -> 16 patches of 256 -> frozen ResNet-101 encoder, as
+    Graph_Structure(data_augmentation).py:136-200 does) + the clinical node features, then the fusion head's
+    forward, objective (my_train(full).py:309-347), backward and Adam on the flat parameters.  Inputs are resident in
+    HBM; returns patients/s and 512x512 images/s with the time split encoder / head."""
+    import numpy as np
+    import torch
+    from cervix_b200.backend import get_backend
+    from cervix_b200.engine import FlatParams
+    from cervix_b200.multimodal.my_mae_model import (fusion_model_mae_2, fusion_objective, get_edge_index_full,
+                                                     get_edge_index_image)
+    from cervix_b200.multimodal.patch_encoder import ResNet101Encoder, split_patches
+    B = get_backend()
+    torch.manual_seed(0)
+    enc = ResNet101Encoder().cuda().eval()
+    for m in enc.modules():   # ImageNet weights are not available offline: random init + non-trivial running statistics
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    types = ["imgN", "imgA", "imgL", "cli"]
+    head = fusion_model_mae_2(1024, 512, 512, 0.3, 4).cuda().train()
+    flat = FlatParams(head)
+    m1, v1 = torch.zeros_like(flat.data), torch.zeros_like(flat.data)
+    imgs = torch.rand(patients, 3, 3, size, size, device="cuda")
+    cli = torch.randn(patients, 4, 1024, device="cuda")
+    labels = torch.randint(0, 4, (patients,), device="cuda")
+    edges = {"imgN": get_edge_index_image(), "imgA": get_edge_index_image(), "imgL": get_edge_index_image(),
+             "cli": get_edge_index_full(4)}
+    rng = np.random.RandomState(0)
+    masks = np.ones((patients, 4), dtype=bool)
+    masks[np.arange(patients), rng.randint(0, 4, patients)] = False   # exactly one visible modality per patient
+    t = [0]
+
+    def encode():
+        with torch.no_grad():
+            return {mname: enc(split_patches(imgs[:, i])).view(patients, 16, 1024) for i, mname in enumerate(types[:3])}
+
+    def head_step(feats):
+        feats = dict(feats, cli=cli)
+        flat.grad.zero_()
+        out = head.forward_batch(feats, edges, types, types, masks, True)
+        loss = fusion_objective(out, labels, masks)
+        loss.backward()
+        t[0] += 1
+        B.adam_step(flat.data, flat.grad, m1, v1, 1e-4, 0.9, 0.999, 1e-8, 5e-4, t[0])
+        return loss
+
+    for _ in range(warmup):
+        head_step(encode())
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    enc_ms = head_ms = 0.0
+    for _ in range(steps):
+        ev[0].record(); f = encode(); ev[1].record(); loss = head_step(f); ev[2].record()
+        torch.cuda.synchronize()
+        enc_ms += ev[0].elapsed_time(ev[1]); head_ms += ev[1].elapsed_time(ev[2])
+    ms = (enc_ms + head_ms) / steps
+    return {"workload": "four-modal severity classifier train step, %d patients x 3 images %dx%d (ResNet-101 patch "
+                        "encoder bf16, frozen) + clinical nodes -> fusion head fwd/bwd + Adam (BASELINE configs[1])" % (patients, size, size),
+            "patients_per_s": patients / (ms * 1e-3), "images_per_s": 3 * patients / (ms * 1e-3), "ms_per_step": ms,
+            "encoder_ms": enc_ms / steps, "head_ms": head_ms / steps,
+            "encoder_tflops": 3 * patients * 16 * 20.38e9 / (enc_ms / steps * 1e-3) / 1e12, "loss_last_step": float(loss)}
+
+
 # ----------------------------------------------------------------------------- our arm
 def time_dominant_kernel(batch: int, peaks):
     """Roofline of the dominant kernel class: the tcgen05 implicit-GEMM conv, timed on the
@@ -305,6 +371,11 @@ def run_ours(args):
         cpu_baseline = {"value": cpu_ips, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d timed steps of the oracle port's train step, batch 2 at 512x512 (%.1f s/step)" % (cpu_steps, cpu_sec)}
     h2d = imgs_h.numel() * 4 + pngs_h.numel() * 8
+    classifier = None
+    if world == 1 and not args.no_classifier:
+        del trainer, model
+        torch.cuda.empty_cache()
+        classifier = classifier_throughput(max(2, min(args.steps, 4)), 2)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -323,6 +394,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "classifier": classifier,
         "losses_last_step": {"ce": losses[0], "focal": losses[1], "dice": losses[2], "f_score": losses[3]},
     }
     print(json.dumps(line), flush=True)
@@ -339,6 +411,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-classifier", action="store_true", help="skip the four-modal classifier leg (N=1 only)")
     ap.add_argument("--no-graph", action="store_true", help="run the single-GPU step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
