@@ -192,6 +192,118 @@ __global__ void __launch_bounds__(256) narrow_out_dgrad_kernel(const T* __restri
   }
 }
 
+// ---- bf16 fast paths of the class-logit conv (256 -> 5 at 128x128: one 268 MB read / write per call at batch 32).
+// Weights live in registers (a lane owns one 8-channel vector of the input for all COUT outputs), eight pixels are in
+// flight per warp, and the 8 x COUT partial sums are combined by a reduce-scatter butterfly: N/2 + N/4 + ... shuffles
+// for N values instead of 5 per value.
+template <int N, int OFF>
+__device__ __forceinline__ void warp_reduce_scatter(float* v, int lane, int& base, int& cnt) {
+  if constexpr (OFF > 0) {
+    constexpr int H = (N + 1) / 2;
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float lo = v[i], hi = (H + i < N) ? v[H + i] : 0.f;
+      const float send = up ? lo : hi, keep = up ? hi : lo;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+    }
+    if (up) { base += H; cnt = cnt > H ? cnt - H : 0; }
+    else cnt = cnt < H ? cnt : H;
+    warp_reduce_scatter<H, OFF / 2>(v, lane, base, cnt);
+  }
+}
+template <int N, int OFF>
+struct ScatterWidth { static constexpr int value = ScatterWidth<(N + 1) / 2, OFF / 2>::value; };
+template <int N>
+struct ScatterWidth<N, 0> { static constexpr int value = N; };
+
+template <int COUT>
+__global__ void __launch_bounds__(256) narrow_out_fwd_fast_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                  const __nv_bfloat16* __restrict__ wp,
+                                                                  const float* __restrict__ bias,
+                                                                  __nv_bfloat16* __restrict__ y, int64_t npix, int cin) {
+  constexpr int PX = 8, NV = PX * COUT;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool active = lane * 8 < cin;
+  float w[COUT][8];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[c][i] = active ? __bfloat162float(wp[c * cin + lane * 8 + i]) : 0.f;
+  float bv[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) bv[c] = bias ? bias[c] : 0.f;
+
+  for (int64_t p0 = warp0 * PX; p0 < npix; p0 += nwarps * PX) {
+    uint4 raw[PX];
+#pragma unroll
+    for (int px = 0; px < PX; ++px)
+      raw[px] = (active && p0 + px < npix) ? __ldg(reinterpret_cast<const uint4*>(x + (p0 + px) * cin + lane * 8))
+                                           : make_uint4(0u, 0u, 0u, 0u);
+    float v[NV];
+#pragma unroll
+    for (int px = 0; px < PX; ++px) {
+      const uint32_t u[4] = {raw[px].x, raw[px].y, raw[px].z, raw[px].w};
+      float xv[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { xv[2 * i] = __uint_as_float(u[i] << 16); xv[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s = fmaf(xv[i], w[c][i], s);
+        v[px * COUT + c] = s;
+      }
+    }
+    int base = 0, cnt = NV;
+    warp_reduce_scatter<NV, 16>(v, lane, base, cnt);
+    constexpr int W = ScatterWidth<NV, 16>::value;
+    const int64_t limit = (npix - p0) * COUT;   // outputs of this group that exist
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const int idx = base + i;
+      if (i < cnt && idx < limit) y[p0 * COUT + idx] = __float2bfloat16_rn(v[i] + bv[idx % COUT]);
+    }
+  }
+}
+
+// dx[p][ci] = sum_co dy[p][co] * Wt[ci][co]: a thread keeps its channel vector for its whole life (the grid stride is
+// a multiple of the vectors per pixel), so its 8 x COUT weights are registers and the loop is 5 broadcast loads,
+// 40 FMAs and one 16-byte store per pixel
+template <int COUT>
+__global__ void __launch_bounds__(256) narrow_out_dgrad_fast_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                    const __nv_bfloat16* __restrict__ wpt,
+                                                                    __nv_bfloat16* __restrict__ dx, int64_t npix, int cin) {
+  const int cvn = cin / 8;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int cv = (int)(tid % cvn);
+  float w[8][COUT];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) w[i][c] = __bfloat162float(wpt[(cv * 8 + i) * COUT + c]);
+  const int64_t pstep = nthreads / cvn;
+#pragma unroll 2
+  for (int64_t p = tid / cvn; p < npix; p += pstep) {
+    float g[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) g[c] = __bfloat162float(dy[p * COUT + c]);
+    uint32_t pk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) { s0 = fmaf(g[c], w[2 * i][c], s0); s1 = fmaf(g[c], w[2 * i + 1][c], s1); }
+      __nv_bfloat162 h = __floats2bfloat162_rn(s0, s1);
+      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(dx + p * cin + cv * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 template <typename T>
 struct NarrowWgradF {
   static constexpr int NACC = kMaxNarrowOut;
@@ -274,6 +386,12 @@ int narrow_conv_fwd(const cvx_conv_desc* d, const void* x, const void* wp, const
     return CVX_OK;
   }
   if (is_narrow_out(d)) {
+    if (d->dtype == CVX_BF16 && d->cout == 5 && d->cin <= 256) {   // the reference's 5-class head (deeplabv3_plus.py:167)
+      narrow_out_fwd_fast_kernel<5><<<cap_blocks(ceil_div64(npix, 64), 8), 256, 0, st>>>(
+          (const __nv_bfloat16*)x, (const __nv_bfloat16*)wp, bias, (__nv_bfloat16*)y, npix, d->cin);
+      CVX_LAUNCH_OK();
+      return CVX_OK;
+    }
     const size_t smem = sizeof(float) * d->cin * d->cout;
     CVX_DISPATCH_DTYPE(d->dtype, T, (narrow_out_fwd_kernel<T><<<cap_blocks(ceil_div64(npix, 8), 8), 256, smem, st>>>(
                                         (const T*)x, (const T*)wp, bias, (T*)y, npix, d->cin, d->cout)));
@@ -287,6 +405,12 @@ int narrow_conv_dgrad(const cvx_conv_desc* d, const void* dy, const void* wpt, v
   if (!is_narrow_out(d)) return CVX_EUNSUPPORTED;
   const int64_t npix = (int64_t)d->n * d->h * d->w;
   const int vec = d->dtype == CVX_F32 ? 4 : 8;
+  if (d->dtype == CVX_BF16 && d->cout == 5 && 256 % (d->cin / 8) == 0) {
+    narrow_out_dgrad_fast_kernel<5><<<cap_blocks(ceil_div64(npix * (d->cin / 8), 256 * 4), 8), 256, 0, st>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)wpt, (__nv_bfloat16*)dx, npix, d->cin);
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
   const size_t smem = sizeof(float) * d->cin * d->cout;
   CVX_DISPATCH_DTYPE(d->dtype, T, (narrow_out_dgrad_kernel<T><<<cap_blocks(ceil_div64(npix * (d->cin / vec), 256), 8), 256, smem, st>>>(
                                       (const T*)dy, (const T*)wpt, (T*)dx, npix, d->cin, d->cout)));

@@ -74,6 +74,8 @@ CONV_CASES = [
     (2, 16, 12, 64, 128, 1, 2, 0, 1, False),   # strided skip
     (1, 12, 12, 72, 40, 3, 1, 6, 6, True),     # atrous, ragged channels
     (3, 9, 7, 40, 5, 1, 1, 0, 1, True),        # classifier
+    (2, 13, 11, 256, 5, 1, 1, 0, 1, True),     # classifier at the real channel count (register-resident fast paths)
+    (1, 5, 3, 128, 5, 1, 1, 0, 1, False),
     (1, 8, 8, 24, 24, 3, 2, 1, 1, False),
 ]
 
