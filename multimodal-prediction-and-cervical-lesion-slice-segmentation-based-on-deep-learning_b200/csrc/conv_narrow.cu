@@ -69,35 +69,64 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const T* __restrict__ x, 
 }
 
 // ---------------------------------------------------------------- narrow in: weight gradient
-// block = 256 threads; thread (k, cg) owns dW[k][4*cg .. 4*cg+3]; pixels staged 64 at a time
+// block = 288 threads; thread (k, cg) owns dW[k][4*cg .. 4*cg+3]; pixels staged 64 at a time.  Staging keeps the
+// index arithmetic out of the inner loops: 64 threads decompose the pixel index once per batch, the gather threads
+// keep their (tap, channel) for the whole kernel, and the dY rows are one linear copy.
 template <typename T>
 __global__ void __launch_bounds__(288) stem_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                          float* __restrict__ dw, NGeom g) {
   constexpr int P = 64;
   __shared__ float xs[P][kStemMaxK + 1];
   __shared__ __align__(16) float dys[P][kStemCout];
+  __shared__ int py0[P], px0[P], pimg[P];
   const int K = g.kh * g.kw * g.cin;
   const int k = threadIdx.x >> 3, cg = threadIdx.x & 7;
   const bool owner = k < K;
+  // gather role: kk = lane (fixed), pixel lanes = warp index
+  const int gk = threadIdx.x & 31, gl = threadIdx.x >> 5;   // 9 warps
+  int g_dy[2] = {0, 0}, g_dx[2] = {0, 0}, g_ci[2] = {0, 0};   // kk = gk and gk + 32 (K <= 36)
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int kk = gk + 32 * j;
+    if (kk < K) {
+      const int tap = kk / g.cin;
+      g_ci[j] = kk - tap * g.cin;
+      g_dy[j] = (tap / g.kw) * g.dil;
+      g_dx[j] = (tap % g.kw) * g.dil;
+    }
+  }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int64_t npix = (int64_t)g.n * g.ho * g.wo;
   for (int64_t p0 = (int64_t)blockIdx.x * P; p0 < npix; p0 += (int64_t)gridDim.x * P) {
-    for (int i = threadIdx.x; i < P * kStemCout; i += blockDim.x) {
-      const int pp = i / kStemCout, co = i % kStemCout;
-      dys[pp][co] = (p0 + pp < npix) ? Elem<T>::ld(dy + (p0 + pp) * kStemCout + co) : 0.f;
-    }
-    for (int i = threadIdx.x; i < P * K; i += blockDim.x) {
-      const int pp = i / K, kk = i % K;
-      const int64_t p = p0 + pp;
-      float v = 0.f;
+    if (threadIdx.x < P) {
+      const int64_t p = p0 + threadIdx.x;
+      int iy0 = -(1 << 28), ix0 = 0, img = 0;   // far outside the image: the gather stores zeros
       if (p < npix) {
-        const int ox = (int)(p % g.wo), oy = (int)((p / g.wo) % g.ho), nn = (int)(p / ((int64_t)g.wo * g.ho));
-        const int tap = kk / g.cin, ci = kk % g.cin;
-        const int iy = oy * g.stride - g.pad + (tap / g.kw) * g.dil;
-        const int ix = ox * g.stride - g.pad + (tap % g.kw) * g.dil;
-        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) v = Elem<T>::ld(x + (((size_t)nn * g.h + iy) * g.w + ix) * g.cin + ci);
+        const int64_t t = p / g.wo;
+        const int ox = (int)(p - t * g.wo), oy = (int)(t % g.ho);
+        img = (int)(t / g.ho);
+        iy0 = oy * g.stride - g.pad;
+        ix0 = ox * g.stride - g.pad;
       }
-      xs[pp][kk] = v;
+      py0[threadIdx.x] = iy0; px0[threadIdx.x] = ix0; pimg[threadIdx.x] = img;
+    }
+    for (int i = threadIdx.x; i < P * kStemCout; i += blockDim.x) {
+      const int pp = i / kStemCout;
+      (&dys[0][0])[i] = (p0 + pp < npix) ? Elem<T>::ld(dy + p0 * kStemCout + i) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kk = gk + 32 * j;
+      if (kk < K) {
+        for (int pp = gl; pp < P; pp += 9) {
+          const int iy = py0[pp] + g_dy[j], ix = px0[pp] + g_dx[j];
+          float v = 0.f;
+          if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w)
+            v = Elem<T>::ld(x + (((size_t)pimg[pp] * g.h + iy) * g.w + ix) * g.cin + g_ci[j]);
+          xs[pp][kk] = v;
+        }
+      }
     }
     __syncthreads();
     if (owner) {

@@ -35,6 +35,23 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
   }
 }
 
+// C <= 4 (the RGB image batch): one thread per pixel reads its C planes (coalesced) and writes C adjacent elements;
+// the 32x32 tile transpose above would keep 3 of 32 lanes busy on the store side.
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_smallc_kernel(const float* __restrict__ src, T* __restrict__ dst,
+                                                                  int c, int hw) {
+  const float* s = src + (size_t)blockIdx.y * c * hw;
+  T* d = dst + (size_t)blockIdx.y * c * hw;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    float v[4];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) v[cc] = cc < c ? __ldg(s + (size_t)cc * hw + p) : 0.f;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      if (cc < c) Elem<T>::st(d + (size_t)p * c + cc, v[cc]);
+  }
+}
+
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int c, int hw) {
   __shared__ float tile[32][33];
@@ -145,6 +162,14 @@ int cvx_device_is_sm100(void) {
 int cvx_nchw_to_nhwc(const float* src, void* dst, int n, int c, int h, int w, int dtype, void* stream) {
   CVX_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad arguments");
   const int hw = h * w;
+  if (c <= 4 && n <= 65535) {
+    int bx = (hw + 1023) / 1024;
+    const int cap = (kNumSMs * 8 + n - 1) / n;
+    if (bx > cap) bx = cap;
+    CVX_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_smallc_kernel<T><<<dim3(bx, n), 256, 0, as_stream(stream)>>>(src, (T*)dst, c, hw)));
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
   dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
   CVX_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "nchw_to_nhwc: grid too large");
   CVX_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_kernel<T><<<grid, block, 0, as_stream(stream)>>>(src, (T*)dst, c, hw)));

@@ -17,20 +17,24 @@ struct PixelSoftmax {
   float logp_t;  // log-softmax at the target class (0 when ignored)
 };
 
+// CT > 0: class count known at compile time (CT = 5 is the reference's head): the per-class loops unroll to exactly
+// CT iterations with no predicates; CT = 0 keeps the generic <= kMaxC form.
+template <int CT>
 __device__ __forceinline__ void softmax_px(const float* __restrict__ logits, int64_t base, int64_t cstride, int C,
                                            float* p, float* lse) {
+  constexpr int NC = CT > 0 ? CT : kMaxC;
   float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
-    if (c < C) { p[c] = logits[base + c * cstride]; mx = fmaxf(mx, p[c]); }
+  for (int c = 0; c < NC; ++c)
+    if (c < C) { p[c] = __ldg(logits + base + c * cstride); mx = fmaxf(mx, p[c]); }
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
+  for (int c = 0; c < NC; ++c)
     if (c < C) { p[c] = __expf(p[c] - mx); s += p[c]; }
   const float inv = 1.f / s;
   *lse = mx + __logf(s);
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c)
+  for (int c = 0; c < NC; ++c)
     if (c < C) p[c] *= inv;
 }
 
@@ -42,32 +46,37 @@ __device__ __forceinline__ float pow_gamma(float base, float gamma) {
 }
 
 // stats layout: [0] sum w*nll [1] sum w [2] sum focal [3] pixels | tp[C] sp[C] st[C] | tph[C] sph[C] st[C]
+template <int CT>
 __global__ void __launch_bounds__(256) seg_loss_stats_kernel(const float* __restrict__ logits,
                                                              const int64_t* __restrict__ target,
                                                              const float* __restrict__ onehot,
                                                              const float* __restrict__ cls_w,
                                                              double* __restrict__ stats, int64_t npix, int64_t hw,
-                                                             int C, float alpha, float gamma, float thr) {
+                                                             int C_rt, float alpha, float gamma, float thr) {
+  constexpr int NC = CT > 0 ? CT : kMaxC;
+  const int C = CT > 0 ? CT : C_rt;
   __shared__ float sm[4 + 6 * kMaxC];
   const int nstat = 4 + 6 * C;
   for (int i = threadIdx.x; i < nstat; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
 
   float a_ce = 0.f, a_w = 0.f, a_focal = 0.f, a_cnt = 0.f;
-  float tp[kMaxC], sp[kMaxC], st[kMaxC], tph[kMaxC], sph[kMaxC];
+  float tp[NC], sp[NC], st[NC], tph[NC], sph[NC];
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c) tp[c] = sp[c] = st[c] = tph[c] = sph[c] = 0.f;
+  for (int c = 0; c < NC; ++c) tp[c] = sp[c] = st[c] = tph[c] = sph[c] = 0.f;
 
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t nn = i / hw, r = i - nn * hw;
-    float p[kMaxC], lse;
-    softmax_px(logits, nn * C * hw + r, hw, C, p, &lse);
+  // grid = (pixel blocks, images): no 64-bit division per pixel
+  const int64_t nn = blockIdx.y;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < hw; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = nn * hw + r;
+    float p[NC], lse;
+    softmax_px<CT>(logits, nn * C * hw + r, hw, C, p, &lse);
     const int t = (int)target[i];
     const bool valid = t >= 0 && t < C;
     a_cnt += 1.f;
     if (valid) {
       const float w = cls_w ? cls_w[t] : 1.f;
-      const float logp_t = logits[nn * C * hw + (int64_t)t * hw + r] - lse;
+      const float logp_t = __ldg(logits + nn * C * hw + (int64_t)t * hw + r) - lse;
       const float u = w * logp_t;  // class-weighted log-prob ("logpt" of Focal_Loss)
       a_ce -= u;
       a_w += w;
@@ -75,7 +84,7 @@ __global__ void __launch_bounds__(256) seg_loss_stats_kernel(const float* __rest
       a_focal -= pow_gamma(1.f - pt, gamma) * alpha * u;
     }
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       if (c < C) {
         const float tc = onehot ? onehot[i * (C + 1) + c] : (t == c ? 1.f : 0.f);
         const float hard = p[c] > thr ? 1.f : 0.f;
@@ -94,7 +103,7 @@ __global__ void __launch_bounds__(256) seg_loss_stats_kernel(const float* __rest
     atomicAdd(&sm[0], a_ce); atomicAdd(&sm[1], a_w); atomicAdd(&sm[2], a_focal); atomicAdd(&sm[3], a_cnt);
   }
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     if (c < C) {
       const float v0 = warp_sum(tp[c]), v1 = warp_sum(sp[c]), v2 = warp_sum(st[c]);
       const float v3 = warp_sum(tph[c]), v4 = warp_sum(sph[c]);
@@ -128,21 +137,24 @@ __global__ void seg_loss_finalize_kernel(const double* __restrict__ stats, float
   results[3] = (float)dice_score(stats + 4 + 3 * C, stats + 4 + 4 * C, stats + 4 + 5 * C, C, beta, smooth);
 }
 
+template <int CT>
 __global__ void __launch_bounds__(256) seg_loss_grad_kernel(const float* __restrict__ logits,
                                                             const int64_t* __restrict__ target,
                                                             const float* __restrict__ onehot,
                                                             const float* __restrict__ cls_w,
                                                             const double* __restrict__ stats,
                                                             const float* __restrict__ gup, float* __restrict__ dlogits,
-                                                            int64_t npix, int64_t hw, int C, float alpha, float gamma,
+                                                            int64_t npix, int64_t hw, int C_rt, float alpha, float gamma,
                                                             float beta, float smooth) {
+  constexpr int NC = CT > 0 ? CT : kMaxC;
+  const int C = CT > 0 ? CT : C_rt;
   const float g_ce = gup[0], g_focal = gup[1], g_dice = gup[2];
   const float inv_wsum = (float)(1.0 / stats[1]);
   const float inv_npix = (float)(1.0 / stats[3]);
   const float b2 = beta * beta;
-  float dA[kMaxC], dB[kMaxC];  // dice: dL/dp_c = -(dA[c]*t_c - dB[c])
+  float dA[NC], dB[NC];  // dice: dL/dp_c = -(dA[c]*t_c - dB[c])
 #pragma unroll
-  for (int c = 0; c < kMaxC; ++c) {
+  for (int c = 0; c < NC; ++c) {
     if (c < C) {
       const double tp = stats[4 + c], sp = stats[4 + C + c], st = stats[4 + 2 * C + c];
       const double D = b2 * st + sp + smooth;  // (1+b2)tp + b2*fn + fp + smooth with fn=st-tp, fp=sp-tp
@@ -151,27 +163,28 @@ __global__ void __launch_bounds__(256) seg_loss_grad_kernel(const float* __restr
       dB[c] = (float)(N / (D * D) / C);
     }
   }
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t nn = i / hw, r = i - nn * hw;
+  const int64_t nn = blockIdx.y;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < hw; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = nn * hw + r;
     const int64_t base = nn * C * hw + r;
-    float p[kMaxC], lse;
-    softmax_px(logits, base, hw, C, p, &lse);
+    float p[NC], lse;
+    softmax_px<CT>(logits, base, hw, C, p, &lse);
     const int t = (int)target[i];
     const bool valid = t >= 0 && t < C;
     float k_onehot = 0.f;  // coefficient of (1[k==t] - p_k)
     if (valid) {
       const float w = cls_w ? cls_w[t] : 1.f;
-      const float logp_t = logits[base + (int64_t)t * hw] - lse;
+      const float logp_t = __ldg(logits + base + (int64_t)t * hw) - lse;
       const float u = w * logp_t;
       const float pt = __expf(u);
       const float om = 1.f - pt;
       const float dfdu = -alpha * (pow_gamma(om, gamma) - gamma * pow_gamma(om, gamma - 1.f) * pt * u);
       k_onehot = -g_ce * w * inv_wsum + g_focal * inv_npix * dfdu * w;
     }
-    float G[kMaxC], dot = 0.f;
+    float G[NC], dot = 0.f;
     if (g_dice != 0.f) {
 #pragma unroll
-      for (int c = 0; c < kMaxC; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (c < C) {
           const float tc = onehot ? onehot[i * (C + 1) + c] : (t == c ? 1.f : 0.f);
           G[c] = -g_dice * (dA[c] * tc - dB[c]);
@@ -180,7 +193,7 @@ __global__ void __launch_bounds__(256) seg_loss_grad_kernel(const float* __restr
       }
     }
 #pragma unroll
-    for (int c = 0; c < kMaxC; ++c) {
+    for (int c = 0; c < NC; ++c) {
       if (c < C) {
         float d = k_onehot * ((c == t ? 1.f : 0.f) - p[c]);
         if (g_dice != 0.f) d += p[c] * (G[c] - dot);
@@ -204,9 +217,17 @@ int cvx_seg_loss_stats(const float* logits, const int64_t* target, const float* 
   cudaStream_t st = as_stream(stream);
   CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * (4 + 6 * c), st));
   const int64_t npix = (int64_t)n * h * w;
-  int blocks = (int)(ceil_div64(npix, 256 * 4) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(npix, 256 * 4));
-  seg_loss_stats_kernel<<<blocks, 256, 0, st>>>(logits, target, onehot, cls_weights, stats, npix, (int64_t)h * w, c,
-                                                focal_alpha, focal_gamma, threshold);
+  const int64_t hw = (int64_t)h * w;
+  CVX_CHECK_ARG(n <= 65535, "seg_loss_stats: batch %d exceeds the grid's image dimension", n);
+  int64_t bx = ceil_div64(hw, 256 * 4), cap = ceil_div64((int64_t)kNumSMs * 8, n);
+  if (bx > cap) bx = cap;
+  const dim3 grid((unsigned)bx, (unsigned)n);
+  if (c == 5)
+    seg_loss_stats_kernel<5><<<grid, 256, 0, st>>>(logits, target, onehot, cls_weights, stats, npix, hw, c, focal_alpha,
+                                                   focal_gamma, threshold);
+  else
+    seg_loss_stats_kernel<0><<<grid, 256, 0, st>>>(logits, target, onehot, cls_weights, stats, npix, hw, c, focal_alpha,
+                                                   focal_gamma, threshold);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -224,10 +245,17 @@ int cvx_seg_loss_grad(const float* logits, const int64_t* target, const float* o
   CVX_CHECK_ARG(logits && target && stats && g && dlogits && n > 0 && c > 0 && c <= kMaxC && h > 0 && w > 0,
                 "seg_loss_grad: bad arguments");
   const int64_t npix = (int64_t)n * h * w;
-  int blocks = (int)(ceil_div64(npix, 256) > kNumSMs * 16 ? kNumSMs * 16 : ceil_div64(npix, 256));
-  seg_loss_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(logits, target, onehot, cls_weights, stats, g, dlogits,
-                                                              npix, (int64_t)h * w, c, focal_alpha, focal_gamma, beta,
-                                                              smooth);
+  const int64_t hw = (int64_t)h * w;
+  CVX_CHECK_ARG(n <= 65535, "seg_loss_grad: batch %d exceeds the grid's image dimension", n);
+  int64_t bx = ceil_div64(hw, 256 * 2), cap = ceil_div64((int64_t)kNumSMs * 16, n);
+  if (bx > cap) bx = cap;
+  const dim3 grid((unsigned)bx, (unsigned)n);
+  if (c == 5)
+    seg_loss_grad_kernel<5><<<grid, 256, 0, as_stream(stream)>>>(logits, target, onehot, cls_weights, stats, g, dlogits,
+                                                                 npix, hw, c, focal_alpha, focal_gamma, beta, smooth);
+  else
+    seg_loss_grad_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(logits, target, onehot, cls_weights, stats, g, dlogits,
+                                                                 npix, hw, c, focal_alpha, focal_gamma, beta, smooth);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
