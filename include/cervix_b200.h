@@ -280,6 +280,11 @@ CVX_API int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float 
  * argmax.  cls[out_h][out_w] receives the class index; probs (nullable) the resized probabilities [out_h][out_w][c]. */
 CVX_API int cvx_seg_postprocess(const float* logits, int c, int h, int w, int crop_y, int crop_x, int crop_h, int crop_w,
                                 int out_h, int out_w, unsigned char* cls, float* probs, void* stream);
+/* Confusion matrix for mIoU / mPA / accuracy (reference: utils_metrics.py:37-47 fast_hist): hist[gt][pred] += 1 over the
+ * n pixels whose ground truth is < classes (255 / ignore labels drop out).  hist is [classes][classes] int64 and is
+ * ACCUMULATED into, so one matrix collects a whole validation set without leaving the device. */
+CVX_API int cvx_confusion_matrix(const unsigned char* pred, const unsigned char* gt, int64_t n, int classes, int64_t* hist,
+                                 void* stream);
 
 #ifdef __cplusplus
 }

@@ -638,6 +638,15 @@ class CudaBackend:
               "cvx_seg_postprocess")
         return cls, probs
 
+    def confusion_matrix(self, pred, gt, classes: int, hist=None):
+        """hist[gt][pred] += 1 over the pixels with gt < classes; pred / gt uint8 tensors of equal size."""
+        self._chk(pred, gt)
+        if hist is None:
+            hist = torch.zeros((classes, classes), dtype=torch.int64, device=pred.device)
+        check(self.lib.cvx_confusion_matrix(_p(pred), _p(gt), pred.numel(), int(classes), _p(hist), self._stream()),
+              "cvx_confusion_matrix")
+        return hist
+
 
 _BACKEND = None
 

@@ -65,6 +65,28 @@ __global__ void seg_postprocess_kernel(const float* __restrict__ logits, int c, 
   cls[(size_t)oy * out_w + ox] = (uint8_t)best;
 }
 
+// Confusion matrix of a predicted class map against the ground truth (reference: utils_metrics.py:37-47 fast_hist =
+// np.bincount(n * gt[k] + pred[k]) over the pixels k with 0 <= gt < n): per-block shared-memory histogram, one global
+// atomic per non-empty cell and block.  Accumulates into hist, so a whole validation set is one [n][n] matrix on the
+// device (the reference round-trips every prediction through a PNG file, callbacks.py:163-176).
+constexpr int kMaxHistClasses = 32;
+
+__global__ void __launch_bounds__(256) confusion_matrix_kernel(const uint8_t* __restrict__ pred,
+                                                               const uint8_t* __restrict__ gt, int64_t n, int classes,
+                                                               unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sm[kMaxHistClasses * kMaxHistClasses];
+  const int cells = classes * classes;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) sm[i] = 0u;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = gt[i], b = pred[i];
+    if (a < classes && b < classes) atomicAdd(&sm[a * classes + b], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cells; i += blockDim.x)
+    if (sm[i]) atomicAdd(hist + i, (unsigned long long)sm[i]);
+}
+
 }  // namespace cvx
 
 using namespace cvx;
@@ -81,6 +103,20 @@ extern "C" int cvx_seg_postprocess(const float* logits, int c, int h, int w, int
   const dim3 grid((out_w + 127) / 128, out_h);
   seg_postprocess_kernel<<<grid, 128, 0, as_stream(stream)>>>(logits, c, h, w, crop_y, crop_x, crop_h, crop_w, out_h, out_w,
                                                              sy, sx, cls, probs);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+extern "C" int cvx_confusion_matrix(const unsigned char* pred, const unsigned char* gt, int64_t n, int classes,
+                                    int64_t* hist, void* stream) {
+  CVX_CHECK_ARG(pred && gt && hist && n >= 0, "confusion_matrix: null pointer");
+  CVX_CHECK_ARG(classes >= 1 && classes <= kMaxHistClasses, "confusion_matrix: 1..%d classes supported (got %d)",
+                kMaxHistClasses, classes);
+  if (n == 0) return CVX_OK;
+  int64_t blocks = ceil_div64(n, 256 * 16);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  confusion_matrix_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pred, gt, n, classes,
+                                                                         reinterpret_cast<unsigned long long*>(hist));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -566,3 +566,10 @@ class EmuBackend:
         cls = out.argmax(0).to(torch.uint8)
         return cls, (out.permute(1, 2, 0).contiguous() if want_probs else None)
 
+    def confusion_matrix(self, pred, gt, classes, hist=None):
+        if hist is None:
+            hist = torch.zeros((classes, classes), dtype=torch.int64)
+        a, b = gt.reshape(-1).long(), pred.reshape(-1).long()
+        k = (a < classes) & (b < classes)
+        hist += torch.bincount(classes * a[k] + b[k], minlength=classes * classes).reshape(classes, classes)
+        return hist

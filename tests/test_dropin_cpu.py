@@ -161,3 +161,26 @@ def test_predictor_matches_reference_postprocessing(size, mix):
     if mix == 1:
         assert (np.array(out) == np.array(pred.colors, np.uint8)[got]).all()
     assert pred.get_FPS(img, 1) > 0
+
+
+def test_miou_metrics_match_numpy_reference():
+    """fast_hist / per_class_iu / PA / precision / accuracy vs the reference formulas (utils_metrics.py:37-118)."""
+    from cervix_b200.utils.utils_metrics import fast_hist, per_Accuracy, per_class_iu, per_class_PA_Recall, per_class_Precision
+    rng = np.random.RandomState(0)
+    n = 5
+    gt = rng.randint(0, 6, (2, 37, 41)).astype(np.uint8)
+    gt[gt == 5] = 255                       # ignore label, as in the VOC-style PNGs
+    pred = rng.randint(0, 5, (2, 37, 41)).astype(np.uint8)
+    a, b = gt.reshape(-1), pred.reshape(-1)
+    k = (a >= 0) & (a < n)
+    ref = np.bincount(n * a[k].astype(int) + b[k], minlength=n ** 2).reshape(n, n)
+    got = fast_hist(a, b, n)
+    assert got.dtype == np.int64 and (got == ref).all()
+    acc = torch.zeros(n, n, dtype=torch.int64)
+    for i in range(2):                       # accumulation over a set
+        fast_hist(gt[i], pred[i], n, acc)
+    assert (acc.numpy() == ref).all()
+    assert np.allclose(per_class_iu(got), np.diag(ref) / np.maximum(ref.sum(1) + ref.sum(0) - np.diag(ref), 1))
+    assert np.allclose(per_class_PA_Recall(got), np.diag(ref) / np.maximum(ref.sum(1), 1))
+    assert np.allclose(per_class_Precision(got), np.diag(ref) / np.maximum(ref.sum(0), 1))
+    assert np.isclose(per_Accuracy(got), np.diag(ref).sum() / max(ref.sum(), 1))

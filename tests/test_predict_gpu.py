@@ -101,3 +101,19 @@ def test_fit_one_epoch_on_device(tmp_path):
     assert sum(f.startswith("ep00") for f in files) == 2 and "best_epoch_weights.pth" in files
     sd = torch.load(os.path.join(tmp_path, "last_epoch_weights.pth"))
     assert set(sd) == set(model.state_dict())
+
+
+def test_confusion_matrix_on_device():
+    from cervix_b200.utils.utils_metrics import fast_hist, per_class_iu
+    g = torch.Generator().manual_seed(0)
+    for n, size in ((5, 512 * 512 * 3 + 17), (21, 100003), (2, 1)):
+        gt = torch.randint(0, n + 1, (size,), generator=g).to(torch.uint8)
+        gt[gt == n] = 255
+        pred = torch.randint(0, n, (size,), generator=g).to(torch.uint8)
+        ref = EmuBackend().confusion_matrix(pred, gt, n)
+        hist = torch.zeros(n, n, dtype=torch.int64, device="cuda")
+        fast_hist(gt.cuda(), pred.cuda(), n, hist)
+        fast_hist(gt.cuda(), pred.cuda(), n, hist)       # accumulates
+        assert (hist.cpu() == 2 * ref).all()
+        assert (fast_hist(gt.numpy(), pred.numpy(), n) == ref.numpy()).all()
+        assert per_class_iu(hist).shape == (n,)
