@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(NT, MINB) colreduce_kernel(F f, int64_t rows, 
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > rows) r1 = rows;
-#pragma unroll 4
+#pragma unroll 8
     for (int64_t r = r0 + lane; r < r1; r += lanes) f(r, cvec * VEC, acc);
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
@@ -64,7 +64,19 @@ static int colreduce_launch(const F& f, int64_t rows, int C, double* out, cudaSt
   const int cvn = C / VEC;
   int maxchunk = (12288 / F::NACC) / VEC;  // keep the block's partial-sum tile within 48 KB
   if (maxchunk > NT) maxchunk = NT;
-  const int colchunk = cvn < maxchunk ? cvn : maxchunk;
+  // column chunk = channel vectors per block: pick the width that keeps the most threads busy (row lanes x chunk of NT,
+  // times the fill of the last chunk) among chunks of >= 8 vectors (128 contiguous bytes per row segment); e.g. 728
+  // channels = 91 vectors: one 91-wide chunk uses 182 of 256 threads, four 23-wide chunks use 253
+  int colchunk = cvn < maxchunk ? cvn : maxchunk;
+  {
+    double best = -1.0;
+    const int lo = cvn < 8 ? cvn : 8;
+    for (int cc = colchunk; cc >= lo; --cc) {
+      const int yc = (cvn + cc - 1) / cc;
+      const double use = (double)((NT / cc) * cc) / NT * (double)cvn / (double)(yc * cc);
+      if (use > best + 0.02) { best = use; colchunk = cc; }   // prefer wider chunks unless clearly better
+    }
+  }
   const int lanes = NT / colchunk;
   const int ychunks = (cvn + colchunk - 1) / colchunk;
   // one wave of resident blocks, each walking >= 16 rows per lane
