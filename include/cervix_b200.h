@@ -274,6 +274,15 @@ CVX_API int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int6
 CVX_API int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 
+/* Gather of n gradient tensors into one flat fp32 buffer in a single launch (the engine's replacement for autograd's
+ * per-parameter accumulate kernels, utils_fit.py:88-90 `loss.backward()` + DDP's bucket copies, train.py:386):
+ * src_ptrs[i] = device address of tensor i (0 = no gradient -> zeros), sizes[i] its element count, dst_offsets[i] its
+ * place in dst (multiples of 4 floats); the (chunk_tensor, chunk_start) tables enumerate the
+ * cvx_multi_gather_chunk()-float chunks of all tensors.  All tables live in device memory (graph-replay safe). */
+CVX_API int cvx_multi_gather_chunk(void);
+CVX_API int cvx_multi_gather(const int64_t* src_ptrs, const int32_t* chunk_tensor, const int32_t* chunk_start,
+                             const int64_t* dst_offsets, const int64_t* sizes, int nchunks, float* dst, void* stream);
+
 /* ---- inference post-processing (reference: deeplab.py:141-154 detect_image, :304-345 get_miou_png) ----------
  * softmax over the c class planes of ONE image's logits [c][h][w] (fp32, NCHW) -> crop (crop_y, crop_x, crop_h, crop_w:
  * the un-letterboxed region) -> bilinear resize to out_h x out_w with cv2.resize(INTER_LINEAR) coordinates ->

@@ -100,6 +100,8 @@ PROTOTYPES = {
     "cvx_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "cvx_adam_step_dev": [_P, _P, _P, _P, _L, _P, _P, _P],
     "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],
+    "cvx_multi_gather_chunk": [],
+    "cvx_multi_gather": [_P, _P, _P, _P, _P, _I, _P, _P],
     "cvx_seg_postprocess": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "cvx_confusion_matrix": [_P, _P, _L, _I, _P, _P],
 }

@@ -625,6 +625,15 @@ class CudaBackend:
         check(self.lib.cvx_sgd_step(_p(p), _p(g), _p(buf), p.numel(), float(lr), float(momentum), float(wd),
                                     int(nesterov), int(first_step), float(grad_scale), self._stream()), "cvx_sgd_step")
 
+    def multi_gather_chunk(self) -> int:
+        return int(self.lib.cvx_multi_gather_chunk())
+
+    def multi_gather(self, src_ptrs, chunk_tensor, chunk_start, dst_offsets, sizes, dst):
+        """dst[dst_offsets[i] : +sizes[i]] = tensor at address src_ptrs[i] (zeros when the address is 0)."""
+        self._chk(src_ptrs, chunk_tensor, chunk_start, dst_offsets, sizes, dst)
+        check(self.lib.cvx_multi_gather(_p(src_ptrs), _p(chunk_tensor), _p(chunk_start), _p(dst_offsets), _p(sizes),
+                                        int(chunk_tensor.numel()), _p(dst), self._stream()), "cvx_multi_gather")
+
     # ------------------------------------------------------------------ inference post-processing
     def seg_postprocess(self, logits, crop, out_hw, want_probs: bool = False):
         """logits [C,H,W] fp32 (one image, NCHW) -> (uint8 class map [out_h,out_w], probabilities or None)."""

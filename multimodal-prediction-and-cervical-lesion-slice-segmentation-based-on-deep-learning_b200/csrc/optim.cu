@@ -40,6 +40,33 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   }
 }
 
+// Gather of many gradient tensors into the flat gradient buffer in ONE launch (replaces one accumulate kernel per
+// parameter, 435 for DeepLab-Xception): block b copies chunk b of tensor chunk_tensor[b]; a null source writes zeros
+// (parameters that received no gradient).  Sources may be unaligned views, destinations are 16-byte aligned.
+constexpr int kGatherChunk = 2048;   // floats per block
+
+__global__ void __launch_bounds__(256) multi_gather_kernel(const int64_t* __restrict__ src_ptrs,
+                                                           const int32_t* __restrict__ chunk_tensor,
+                                                           const int32_t* __restrict__ chunk_start,
+                                                           const int64_t* __restrict__ dst_offsets,
+                                                           const int64_t* __restrict__ sizes, float* __restrict__ dst) {
+  const int tsr = chunk_tensor[blockIdx.x];
+  const int64_t start = chunk_start[blockIdx.x];
+  const int64_t size = sizes[tsr];
+  const float* src = reinterpret_cast<const float*>(src_ptrs[tsr]);
+  float* out = dst + dst_offsets[tsr];
+  int64_t end = start + kGatherChunk;
+  if (end > size) end = size;
+  if (src != nullptr && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int64_t v0 = start / 4, v1 = end / 4;   // start is a multiple of the chunk size
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += blockDim.x)
+      reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+    for (int64_t i = v1 * 4 + threadIdx.x; i < end; i += blockDim.x) out[i] = src[i];
+  } else {
+    for (int64_t i = start + threadIdx.x; i < end; i += blockDim.x) out[i] = src ? src[i] : 0.f;
+  }
+}
+
 __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n,
                            float lr, float mom, float wd, int nesterov, int first, float gscale) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -78,6 +105,18 @@ int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
   CVX_CHECK_ARG(p && g && m && v && hyper && step && n > 0, "adam_step_dev: bad arguments");
   int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
   adam_dev_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, hyper, step);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_multi_gather_chunk(void) { return kGatherChunk; }
+
+int cvx_multi_gather(const int64_t* src_ptrs, const int32_t* chunk_tensor, const int32_t* chunk_start,
+                     const int64_t* dst_offsets, const int64_t* sizes, int nchunks, float* dst, void* stream) {
+  CVX_CHECK_ARG(src_ptrs && chunk_tensor && chunk_start && dst_offsets && sizes && dst && nchunks >= 0,
+                "multi_gather: bad arguments");
+  if (nchunks == 0) return CVX_OK;
+  multi_gather_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(src_ptrs, chunk_tensor, chunk_start, dst_offsets, sizes, dst);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -33,10 +33,53 @@ class FlatParams:
         self.numel = off
         self.data = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad_views = []
         for p, o in zip(self.params, self.offsets):
             self.data[o:o + p.numel()].copy_(p.data.reshape(-1))
             p.data = self.data[o:o + p.numel()].view(p.shape)
-            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+            self.grad_views.append(self.grad[o:o + p.numel()].view(p.shape))
+        self.attach_grad_views()
+
+    def attach_grad_views(self):
+        """``p.grad`` = a view of the flat gradient: autograd then accumulates in place (one add kernel per parameter)."""
+        for p, g in zip(self.params, self.grad_views):
+            if p.grad is not g:
+                p.grad = g
+
+    def detach_grads(self):
+        """``p.grad = None``: autograd then just keeps the gradient tensor each backward produced (no kernel), and
+        ``GradGather`` copies all of them into the flat buffer in one launch."""
+        for p in self.params:
+            p.grad = None
+
+
+class GradGather:
+    """One-launch gather of the per-parameter gradients into ``FlatParams.grad`` (C ABI: cvx_multi_gather)."""
+
+    def __init__(self, flat: FlatParams):
+        B = get_backend()
+        ch = B.multi_gather_chunk()
+        dev = flat.data.device
+        sizes = [p.numel() for p in flat.params]
+        tids, starts = [], []
+        for i, n in enumerate(sizes):
+            for st in range(0, n, ch):
+                tids.append(i)
+                starts.append(st)
+        self.flat = flat
+        self.chunk_tensor = torch.tensor(tids, dtype=torch.int32, device=dev)
+        self.chunk_start = torch.tensor(starts, dtype=torch.int32, device=dev)
+        self.dst_offsets = torch.tensor(flat.offsets, dtype=torch.int64, device=dev)
+        self.sizes = torch.tensor(sizes, dtype=torch.int64, device=dev)
+
+    def new_table(self) -> torch.Tensor:
+        return torch.zeros(len(self.flat.params), dtype=torch.int64, device=self.flat.data.device)
+
+    def pointers(self) -> List[int]:
+        return [0 if p.grad is None else p.grad.data_ptr() for p in self.flat.params]
+
+    def launch(self, table: torch.Tensor):
+        get_backend().multi_gather(table, self.chunk_tensor, self.chunk_start, self.dst_offsets, self.sizes, self.flat.grad)
 
 
 class SegTrainer:
@@ -65,6 +108,12 @@ class SegTrainer:
                                       dtype=torch.float32, device=dev)
         self.graph = None
         self._hooks_off = False
+        # gradients are gathered into the flat buffer by ONE kernel whenever no per-bucket hooks need them there
+        # early (single GPU, or the graph-captured data-parallel step); device tensors only
+        self._gather = GradGather(self.flat) if self.flat.grad.is_cuda else None
+        self._table_eager = self._gather.new_table() if self._gather else None
+        self._table_graph = self._gather.new_table() if self._gather else None
+        self._captured_ptrs = None
         self._nbt = [m.num_batches_tracked for m in model.modules()
                      if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
         if world_size > 1:
@@ -136,7 +185,12 @@ class SegTrainer:
         return losses
 
     def _forward_backward(self, imgs, pngs, labels):
-        self.flat.grad.zero_()
+        gather = self._gather is not None and (self._hooks_off or self.world == 1)
+        if gather:
+            self.flat.detach_grads()
+        else:
+            self.flat.attach_grad_views()
+            self.flat.grad.zero_()
         self.step_dev.add_(1)
         ops.set_step_counter(self.step_dev)
         with ops.defer_batch_counters():
@@ -146,6 +200,15 @@ class SegTrainer:
         ce, focal, dice, fs = seg_objective(out, pngs, labels, self.cls_weights, self.num_classes)
         loss = (focal if self.focal else ce) + (dice if self.dice else 0.0)
         loss.backward()
+        if gather:
+            ptrs = self._gather.pointers()
+            if torch.cuda.is_current_stream_capturing():
+                # the table is filled right after the capture ends; replays always see the same addresses
+                self._captured_ptrs = ptrs
+                self._gather.launch(self._table_graph)
+            else:
+                self._table_eager.copy_(torch.tensor(ptrs, dtype=torch.int64))
+                self._gather.launch(self._table_eager)
         self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
         return self.last
 
@@ -191,6 +254,8 @@ class SegTrainer:
                 self.s_out = self._forward_backward(self.s_imgs, self.s_pngs, self.s_labels)
             else:
                 self.s_out = self.step(self.s_imgs, self.s_pngs, self.s_labels)
+        if self._captured_ptrs is not None:
+            self._table_graph.copy_(torch.tensor(self._captured_ptrs, dtype=torch.int64))
         return self
 
     def step_graphed(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None):
