@@ -150,25 +150,32 @@ __global__ void __launch_bounds__(256, 2) dwf_fwd_kernel(const __grid_constant__
     const int ox = tx * kFX + col, oy0 = ty * kFY;
 
     if (AFFINE) {
-      // ---- pre-pass over the 14 x 18 x 16 quads of the halo tile; v & 15 == cq in every iteration
-      int rr = t / ((kFX + 2) * 16), rem = t - rr * ((kFX + 2) * 16);
-      int cc = rem >> 4;
-      uint32_t a = tile_a + rr * kFRow + cc * 128 + cq * 8;
-      for (; rr < kFY + 2; ) {
-        const int iy = oy0 - 1 + rr, ix = tx * kFX - 1 + cc;
-        if (iy > p.h) break;  // rows below the image feed nothing
-        const bool valid = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-        uint2 out = make_uint2(0u, 0u);
-        if (valid) {
-          const uint2 r = lds64(a);
-          float2 v0 = __ffma2_rn(unpack_bf16x2(r.x), sc[0], sh[0]), v1 = __ffma2_rn(unpack_bf16x2(r.y), sc[1], sh[1]);
-          if (relu) { v0 = relu2(v0); v1 = relu2(v1); }
-          out = make_uint2(pack_bf16x2(v0), pack_bf16x2(v1));
+      // ---- pre-pass over the 14 x 18 x 16 quads of the halo tile, two elements per thread in flight; the element
+      // index advances by 256 threads = 16 pixels, so a thread keeps its channel quad (v & 15 == cq)
+      constexpr int kElems = (kFY + 2) * (kFX + 2) * 16;
+      const int ox0 = tx * kFX - 1, oyb = oy0 - 1;
+      for (int v = t; v < kElems; v += 512) {
+        uint2 raw[2];
+        bool valid[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int pix = (v + 256 * u) >> 4;
+          const int rr = pix / (kFX + 2), cc = pix - rr * (kFX + 2);
+          const int iy = oyb + rr, ix = ox0 + cc;
+          valid[u] = v + 256 * u < kElems && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+          raw[u] = valid[u] ? lds64(tile_a + (v + 256 * u) * 8) : make_uint2(0u, 0u);
         }
-        sts64(a, out);
-        // advance by 256 threads = 16 pixels
-        cc += 16; a += 16 * 128;
-        if (cc >= kFX + 2) { cc -= kFX + 2; ++rr; }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (v + 256 * u >= kElems) break;
+          uint2 out = make_uint2(0u, 0u);
+          if (valid[u]) {
+            float2 v0 = __ffma2_rn(unpack_bf16x2(raw[u].x), sc[0], sh[0]), v1 = __ffma2_rn(unpack_bf16x2(raw[u].y), sc[1], sh[1]);
+            if (relu) { v0 = relu2(v0); v1 = relu2(v1); }
+            out = make_uint2(pack_bf16x2(v0), pack_bf16x2(v1));
+          }
+          sts64(tile_a + (v + 256 * u) * 8, out);
+        }
       }
       __syncthreads();
     }
@@ -313,23 +320,35 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
     const int ox = tx * kFX + col, oy0 = ty * kFY;
 
     if (SIDE) {
-      // ---- pre-pass: dd = e + negk*d + kmean over the halo tile, in place, zero outside the image
-      int rr = t / ((kFX + 2) * 16), rem = t - rr * ((kFX + 2) * 16);
-      int cc = rem >> 4;
-      uint32_t a = dd_a + rr * kFRow + cc * 128 + cq * 8;
-      for (; rr < kFY + 2; ) {
-        const int iy = oy0 - 1 + rr, ix = tx * kFX - 1 + cc;
-        if (iy > p.h) break;  // rows below the image feed nothing
-        const bool valid = iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
-        uint2 out = make_uint2(0u, 0u);
-        if (valid) {
-          const uint2 e = lds64(a), d = lds64(a + 2 * kFTile);
-          out.x = pack_bf16x2(__ffma2_rn(nk[0], unpack_bf16x2(d.x), __fadd2_rn(unpack_bf16x2(e.x), km[0])));
-          out.y = pack_bf16x2(__ffma2_rn(nk[1], unpack_bf16x2(d.y), __fadd2_rn(unpack_bf16x2(e.y), km[1])));
+      // ---- pre-pass: dd = e + negk*d + kmean over the halo tile, in place, zero outside the image; two elements per
+      // thread in flight (element index advances by 256 threads = 16 pixels: the channel quad stays cq)
+      constexpr int kElems = (kFY + 2) * (kFX + 2) * 16;
+      const int ox0 = tx * kFX - 1, oyb = oy0 - 1;
+      for (int v = t; v < kElems; v += 512) {
+        uint2 e[2], d[2];
+        bool valid[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int pix = (v + 256 * u) >> 4;
+          const int rr = pix / (kFX + 2), cc = pix - rr * (kFX + 2);
+          const int iy = oyb + rr, ix = ox0 + cc;
+          valid[u] = v + 256 * u < kElems && iy >= 0 && iy < p.h && ix >= 0 && ix < p.w;
+          e[u] = d[u] = make_uint2(0u, 0u);
+          if (valid[u]) {
+            e[u] = lds64(dd_a + (v + 256 * u) * 8);
+            d[u] = lds64(dd_a + 2 * kFTile + (v + 256 * u) * 8);
+          }
         }
-        sts64(a, out);
-        cc += 16; a += 16 * 128;
-        if (cc >= kFX + 2) { cc -= kFX + 2; ++rr; }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (v + 256 * u >= kElems) break;
+          uint2 out = make_uint2(0u, 0u);
+          if (valid[u]) {
+            out.x = pack_bf16x2(__ffma2_rn(nk[0], unpack_bf16x2(d[u].x), __fadd2_rn(unpack_bf16x2(e[u].x), km[0])));
+            out.y = pack_bf16x2(__ffma2_rn(nk[1], unpack_bf16x2(d[u].y), __fadd2_rn(unpack_bf16x2(e[u].y), km[1])));
+          }
+          sts64(dd_a + (v + 256 * u) * 8, out);
+        }
       }
       __syncthreads();
     }
