@@ -605,7 +605,7 @@ constexpr int kEpiBufBytes = 128 * 128;  // one 128-pixel x 64-channel bf16 chun
 // column lies outside the tensor, so the staged chunk can be summed for the statistics as it is).
 template <bool EXTRA>
 __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&r)[32], int col0, int cout, bool row_ok,
-                                              const __nv_bfloat16* srow, uint32_t (&packed)[16]) {
+                                              const uint4 (&side_raw)[4], uint32_t (&packed)[16]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int c = col0 + g * 8;          // absolute output channel of this group of 8
@@ -627,12 +627,21 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 8; ++j) sd[j] = 0.f;
     if (EXTRA && ep.side && ok && row_ok) {
-      const uint4 sv = __ldg(reinterpret_cast<const uint4*>(srow + c));
+      const uint4 sv = side_raw[g];   // prefetched by the caller ahead of the TMEM load (one L2 round trip per chunk)
       const uint32_t su[4] = {sv.x, sv.y, sv.z, sv.w};
+      float ss[8];
+      if ((reinterpret_cast<uintptr_t>(ep.side_scale) & 15) == 0) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(ep.side_scale + c));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(ep.side_scale + c + 4));
+        ss[0] = s0.x; ss[1] = s0.y; ss[2] = s0.z; ss[3] = s0.w; ss[4] = s1.x; ss[5] = s1.y; ss[6] = s1.z; ss[7] = s1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss[j] = __ldg(ep.side_scale + c + j);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        sd[2 * j] = __ldg(ep.side_scale + c + 2 * j) * __uint_as_float(su[j] << 16);
-        sd[2 * j + 1] = __ldg(ep.side_scale + c + 2 * j + 1) * __uint_as_float(su[j] & 0xffff0000u);
+        sd[2 * j] = ss[2 * j] * __uint_as_float(su[j] << 16);
+        sd[2 * j + 1] = ss[2 * j + 1] * __uint_as_float(su[j] & 0xffff0000u);
       }
     }
 #pragma unroll
@@ -808,6 +817,16 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
       for (int q = 0; q < nchunks; ++q) {
+        const int col0 = n0 + q * 64;
+        uint4 sd0[4], sd1[4];
+        if (EXTRA && ep.side) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = col0 + g * 8;
+            sd0[g] = (row_ok && c < p.cout) ? __ldg(reinterpret_cast<const uint4*>(srow + c)) : make_uint4(0u, 0u, 0u, 0u);
+            sd1[g] = (row_ok && c + 32 < p.cout) ? __ldg(reinterpret_cast<const uint4*>(srow + c + 32)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         uint32_t r0[32], r1[32];
         tmem_ld32(t_addr + (uint32_t)(q * 64), r0);
         tmem_ld32(t_addr + (uint32_t)(q * 64 + 32), r1);
@@ -819,9 +838,8 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         if (!tile_ok) continue;  // CTA-uniform: the odd tile of the last pair
         uint32_t pk0[16], pk1[16];
-        const int col0 = n0 + q * 64;
-        epi_convert32<EXTRA>(ep, r0, col0, p.cout, row_ok, srow, pk0);
-        epi_convert32<EXTRA>(ep, r1, col0 + 32, p.cout, row_ok, srow, pk1);
+        epi_convert32<EXTRA>(ep, r0, col0, p.cout, row_ok, sd0, pk0);
+        epi_convert32<EXTRA>(ep, r1, col0 + 32, p.cout, row_ok, sd1, pk1);
         const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
         if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
         epi_bar_sync();

@@ -52,6 +52,11 @@ class _Sep:
 # output chunk) instead of a separate reduction pass; measured on B200 the two are within 1 % of each other
 # (the GEMM epilogue is on that kernel's critical path), so the separate pass stays the default.
 _STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "0") == "1"
+# CERVIX_BN1_IN_DGRAD=1 moves bn1's backward from the depthwise backward kernel (one more tensor read and an in-place
+# pre-pass there) into the data-gradient GEMM's epilogue.  Measured on B200: the GEMM grows from 46 to 106 us (its
+# per-thread side-row loads are uncoalesced; a TMA-staged side tile is the missing piece) while the depthwise kernel
+# saves ~25 us, 600 vs 641 img/s for the whole step - so it is off by default.
+_BN1_IN_DGRAD = os.environ.get("CERVIX_BN1_IN_DGRAD", "0") == "1"
 
 
 def _sep_forward(B, x, in_scale, in_shift, relu_in, dw_w, g1, b1, pw_w, g2, b2, bn1: BnBuffers, bn2: BnBuffers,
@@ -89,8 +94,14 @@ def _sep_backward(B, s: _Sep, dp, x, in_scale, in_shift, relu_in, pw_w, addend, 
     gp = ConvGeom(n, h, w, cin, cout, 1, 1, 1, 0, 1)
     G = B.conv_wgrad(s.d, dp, gp, True)
     d_pw, d_g1, d_b1, negk, kmean = B.pw_bwd_coef(G, pw_w.detach(), s.scale1, s.invstd1, s.mean1, rows)
-    e = B.conv_dgrad(dp, s.wpt, gp, True)          # = scale1 (.) dz ; bn1's backward is applied by dwf_bwd on load
-    gx, dw9c, sums = B.dwf_bwd(e, s.d, negk, kmean, x, s.w9c, in_scale, in_shift, relu_in, addend, gd, want_sums)
+    if _BN1_IN_DGRAD:
+        # bn1's backward applied by the data-gradient GEMM's epilogue from the fp32 accumulator:
+        #   dd = dp W^T (scaled by bn1) + negk (.) d + kmean ; the depthwise kernel then needs neither d nor a pre-pass
+        dd = B.conv_dgrad_ex(dp, s.wpt, gp, kmean, s.d, negk)
+        gx, dw9c, sums = B.dwf_bwd(dd, None, None, None, x, s.w9c, in_scale, in_shift, relu_in, addend, gd, want_sums)
+    else:
+        e = B.conv_dgrad(dp, s.wpt, gp, True)      # = scale1 (.) dz ; bn1's backward is applied by dwf_bwd on load
+        gx, dw9c, sums = B.dwf_bwd(e, s.d, negk, kmean, x, s.w9c, in_scale, in_shift, relu_in, addend, gd, want_sums)
     return gx, sums, B.unpack_dw_wgrad(dw9c), d_g1, d_b1, d_pw
 
 
