@@ -603,7 +603,8 @@ constexpr int kEpiBufBytes = 128 * 128;  // one 128-pixel x 64-channel bf16 chun
 
 // 32 accumulator columns of one row -> (+bias, +side) -> 16 packed bf16 pairs (EXTRA: zero where the row or the
 // column lies outside the tensor, so the staged chunk can be summed for the statistics as it is).
-template <bool EXTRA>
+// MODE bit 0: BatchNorm statistics of the output, bit 1: side input (each epilogue variant carries only its own code)
+template <int MODE>
 __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&r)[32], int col0, int cout, bool row_ok,
                                               const uint4 (&side_raw)[4], uint32_t (&packed)[16]) {
 #pragma unroll
@@ -626,7 +627,7 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
     float sd[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sd[j] = 0.f;
-    if (EXTRA && ep.side && ok && row_ok) {
+    if ((MODE & 2) && ok && row_ok) {
       const uint4 sv = side_raw[g];   // prefetched by the caller ahead of the TMEM load (one L2 round trip per chunk)
       const uint32_t su[4] = {sv.x, sv.y, sv.z, sv.w};
       float ss[8];
@@ -650,7 +651,7 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
       const float v1 = __uint_as_float(r[g * 8 + 2 * j + 1]) + bv[2 * j + 1] + sd[2 * j + 1];
       __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
       const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
-      packed[g * 4 + j] = (EXTRA && !(ok && row_ok)) ? 0u : u;   // rows / channels outside the tensor must not reach the statistics
+      packed[g * 4 + j] = ((MODE & 1) && !(ok && row_ok)) ? 0u : u;   // rows / channels outside the tensor must not reach the statistics
     }
   }
 }
@@ -659,7 +660,7 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
 // kPairs consecutive pixel-tile pairs, so the weight tile is read from L2 once per cluster - every CTA fetches
 // 1/kPairs of its half and multicasts it to the CTAs that hold the same half in the other pairs.  The operand
 // stream L2 -> SM is what bounds this kernel (32 KB per CTA and k-block without sharing, ~6.3 KB/clk chip-wide).
-template <bool EXTRA, int kPairs>
+template <int MODE, int kPairs>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_y, const TcEpi ep, TcFwdParams p, int n_tiles,
@@ -791,7 +792,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     const int epi_tid = threadIdx.x - 64;
     const int row = lg * 32 + lane;
     float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
-    if (EXTRA && ep.stats) {
+    if (MODE & 1) {
       for (int i = epi_tid; i < n_tiles * 512; i += 128) stats_sm[i] = 0.f;
       epi_bar_sync();
     }
@@ -807,7 +808,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int n0 = nt * p.tile_n;
       const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
       const bool row_ok = tile_ok && oy < p.ho && ox < p.wo;
-      const __nv_bfloat16* srow = (EXTRA && ep.side) ? ep.side + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout : nullptr;
+      const __nv_bfloat16* srow = (MODE & 2) ? ep.side + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout : nullptr;
       int ncols = p.cout - n0;
       ncols = ncols > p.tile_n ? p.tile_n : ncols;
       const int nchunks = (ncols + 63) >> 6;
@@ -819,7 +820,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       for (int q = 0; q < nchunks; ++q) {
         const int col0 = n0 + q * 64;
         uint4 sd0[4], sd1[4];
-        if (EXTRA && ep.side) {
+        if (MODE & 2) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int c = col0 + g * 8;
@@ -838,8 +839,8 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         if (!tile_ok) continue;  // CTA-uniform: the odd tile of the last pair
         uint32_t pk0[16], pk1[16];
-        epi_convert32<EXTRA>(ep, r0, col0, p.cout, row_ok, sd0, pk0);
-        epi_convert32<EXTRA>(ep, r1, col0 + 32, p.cout, row_ok, sd1, pk1);
+        epi_convert32<MODE>(ep, r0, col0, p.cout, row_ok, sd0, pk0);
+        epi_convert32<MODE>(ep, r1, col0 + 32, p.cout, row_ok, sd1, pk1);
         const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
         if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
         epi_bar_sync();
@@ -859,7 +860,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           tma_store_4d(&tmap_y, smem_u32(epi_buf + buf), col0, tx * p.bw, ty * p.bh, img);
           bulk_commit();
         }
-        if (EXTRA && ep.stats) {
+        if (MODE & 1) {
           // column sums of the staged (bf16-rounded) chunk: warp lg sums 32 rows, lane = one pair of channels;
           // a warp reads one whole 128-byte row per step, so the swizzled layout is conflict-free here too
           const uint8_t* bufp = epi_buf + buf;
@@ -883,7 +884,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       }
     }
     if (epi_tid == 0) bulk_wait_read<0>();
-    if (EXTRA && ep.stats) tc_epilogue_flush_stats(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
+    if (MODE & 1) tc_epilogue_flush_stats(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1443,10 +1444,10 @@ static int g_tc_pairs = [] {
 static int g_tc_pairs_force = 0;
 
 // launch the CTA-pair forward kernel with `kp` pairs per cluster (cluster size 2*kp as a launch attribute)
-template <bool EXTRA, int kPairs>
+template <int MODE, int kPairs>
 static int launch_fwd_pairs_t(int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const TcEpi& ep,
                               const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
-  auto kern = conv_tc_fwd_2cta_kernel<EXTRA, kPairs>;
+  auto kern = conv_tc_fwd_2cta_kernel<MODE, kPairs>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -1475,16 +1476,22 @@ static int launch_fwd_pairs_t(int smem, const CUtensorMap& mx, const CUtensorMap
   return CVX_OK;
 }
 
-static int launch_fwd_pairs(int kp, bool extra, int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
-                            const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
-  if (extra) {
-    if (kp == 4) return launch_fwd_pairs_t<true, 4>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-    if (kp == 2) return launch_fwd_pairs_t<true, 2>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-    return launch_fwd_pairs_t<true, 1>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+template <int kPairs>
+static int launch_fwd_pairs_m(int mode, int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
+                              const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
+  switch (mode) {
+    case 0: return launch_fwd_pairs_t<0, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    case 1: return launch_fwd_pairs_t<1, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    case 2: return launch_fwd_pairs_t<2, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    default: return launch_fwd_pairs_t<3, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
   }
-  if (kp == 4) return launch_fwd_pairs_t<false, 4>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-  if (kp == 2) return launch_fwd_pairs_t<false, 2>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-  return launch_fwd_pairs_t<false, 1>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+}
+
+static int launch_fwd_pairs(int kp, int mode, int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
+                            const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
+  if (kp == 4) return launch_fwd_pairs_m<4>(mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+  if (kp == 2) return launch_fwd_pairs_m<2>(mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+  return launch_fwd_pairs_m<1>(mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
 }
 
 // rows = output pixels [n,ho,wo] ; src = [n,hs,ws,cred] ; wp = [taps][ncol][cred]
@@ -1517,7 +1524,7 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     const int n_tiles = (ncol + p.tile_n - 1) / p.tile_n;
     const int m_tiles = n * p.tiles_y * p.tiles_x;
     CVX_CHECK_ARG(!ep.stats || n_tiles <= kEpiMaxNTiles, "conv_tc: fused statistics need C_out <= %d", kEpiMaxNTiles * kPBN);
-    const bool extra = ep.side || ep.stats;
+    const int mode = (ep.stats ? 1 : 0) | (ep.side ? 2 : 0);
     // pairs per cluster: share the weight tile among 2 pairs when there are enough pixel tiles to keep the machine full
     int kp = g_tc_pairs;
     while (kp > 1 && ((p.tile_n / (2 * kp)) % 8 != 0 || (!g_tc_pairs_force && m_tiles < 2 * kp * 16))) kp >>= 1;
@@ -1525,7 +1532,7 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
     if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n / (2 * kp))) return rc;
     if (int rc = make_act_map(&my, dst, n, ho, wo, ncol, p.bw, p.bh)) return rc;
-    return launch_fwd_pairs(kp, extra, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    return launch_fwd_pairs(kp, mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
   }
   if (!use_v1) {
     CUtensorMap mx, mw;

@@ -48,10 +48,11 @@ class _Sep:
     __slots__ = ("w9c", "d", "p", "mean1", "invstd1", "scale1", "wpt", "mean2", "invstd2", "scale2", "shift2")
 
 
-# CERVIX_STATS_EPILOGUE=1 takes bn2's statistics from the pointwise GEMM's epilogue (column sums of the staged
-# output chunk) instead of a separate reduction pass; measured on B200 the two are within 1 % of each other
-# (the GEMM epilogue is on that kernel's critical path), so the separate pass stays the default.
-_STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "0") == "1"
+# bn2's statistics come out of the pointwise GEMM's epilogue (column sums of the staged output chunk, the stats-only
+# epilogue variant); CERVIX_STATS_EPILOGUE=0 asks for the separate reduction pass instead.  Measured on B200 for the
+# 728-channel middle-flow shape: GEMM 49 -> 58 us with the statistics vs 49 + 18 us for GEMM + reduction pass
+# (647 vs 644 img/s for the whole step).
+_STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "1") != "0"
 # CERVIX_BN1_IN_DGRAD=1 moves bn1's backward from the depthwise backward kernel (one more tensor read and an in-place
 # pre-pass there) into the data-gradient GEMM's epilogue.  Measured on B200: the GEMM grows from 46 to 106 us (its
 # per-thread side-row loads are uncoalesced; a TMA-staged side tile is the missing piece) while the depthwise kernel
