@@ -603,6 +603,15 @@ constexpr int kEpiBufBytes = 128 * 128;  // one 128-pixel x 64-channel bf16 chun
 
 // 32 accumulator columns of one row -> (+bias, +side) -> 16 packed bf16 pairs (EXTRA: zero where the row or the
 // column lies outside the tensor, so the staged chunk can be summed for the statistics as it is).
+// shared-memory plan of the CTA-pair forward kernel per epilogue variant (227 KB per CTA): only the variant with both
+// the side-input staging buffers and the statistics scratch gives up one pipeline stage
+template <int MODE>
+struct TcFwdSmem {
+  static constexpr int kStages = (MODE == 3) ? 4 : 5;   // side + statistics together do not leave room for 5
+  static constexpr int kBytes = kStages * k2StageBytes + 2 * kEpiBufBytes + ((MODE & 2) ? 2 * kEpiBufBytes : 0) + 1024 + 256 +
+                                ((MODE & 1) ? kEpiStatsBytes : 0);
+};
+
 // MODE bit 0: BatchNorm statistics of the output, bit 1: side input (each epilogue variant carries only its own code)
 template <int MODE>
 __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&r)[32], int col0, int cout, bool row_ok,
@@ -663,16 +672,18 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
 template <int MODE, int kPairs>
 __global__ void __launch_bounds__(192, 1)
 conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                        const __grid_constant__ CUtensorMap tmap_y, const TcEpi ep, TcFwdParams p, int n_tiles,
-                        int m_tiles, int total_pair_tiles) {
+                        const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_s,
+                        const TcEpi ep, TcFwdParams p, int n_tiles, int m_tiles, int total_pair_tiles) {
+  constexpr int kSt = TcFwdSmem<MODE>::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_buf = smem + k2Stages * k2StageBytes;  // 2 x 16 KB, 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_buf + 2 * kEpiBufBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * k2Stages + 4);
+  uint8_t* epi_buf = smem + kSt * k2StageBytes;          // 2 x 16 KB output staging, 1024-aligned
+  uint8_t* side_buf = epi_buf + 2 * kEpiBufBytes;        // MODE & 2: 2 x 16 KB side-input staging (TMA destination)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(side_buf + ((MODE & 2) ? 2 * kEpiBufBytes : 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 6);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * k2Stages;
-  const uint32_t tfull0 = empty0 + 8 * k2Stages, tempty0 = tfull0 + 16;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kSt;
+  const uint32_t tfull0 = empty0 + 8 * kSt, tempty0 = tfull0 + 16, sfull0 = tempty0 + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();   // 0 .. 2*kPairs-1
@@ -688,7 +699,12 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     tma_prefetch_desc(&tmap_x);
     tma_prefetch_desc(&tmap_w);
     tma_prefetch_desc(&tmap_y);
-    for (int s = 0; s < k2Stages; ++s) {
+    if (MODE & 2) {
+      tma_prefetch_desc(&tmap_s);
+      mbar_init(sfull0, 1);
+      mbar_init(sfull0 + 8, 1);
+    }
+    for (int s = 0; s < kSt; ++s) {
       mbar_init(full0 + 8 * s, 2);   // leader's expect_tx arrival + the peer producer's arrival
       mbar_init(empty0 + 8 * s, kPairs);  // one multicast commit per pair leader of the cluster
     }
@@ -745,7 +761,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           else
             tma_load_3d_2sm_mc(sa + kABytes + pidx * bq_rows * 128, &tmap_w, lead_full, cb * 64, brow0, khi * p.kw + kwi, bmask);
           if (++cb == kcb) { cb = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
-          if (++s == k2Stages) { s = 0; ph ^= 1; }
+          if (++s == kSt) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -780,7 +796,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           }
           umma_commit_2sm(empty0 + 8 * s, (uint16_t)((1u << (2 * kPairs)) - 1));
           if (++cb == kcb) cb = 0;
-          if (++s == k2Stages) { s = 0; ph ^= 1; }
+          if (++s == kSt) { s = 0; ph ^= 1; }
         }
         umma_commit_2sm(tfull0 + 8 * acc, (uint16_t)(3u << (2 * pidx)));
       }
@@ -796,6 +812,31 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       for (int i = epi_tid; i < n_tiles * 512; i += 128) stats_sm[i] = 0.f;
       epi_bar_sync();
     }
+    // MODE & 2: the side chunk (128 pixels x 64 channels, the box of the output store) is fetched by TMA one chunk
+    // ahead into a 2-deep staging ring; epi_tid 0 walks the same (tile, chunk) sequence as the consumers below
+    int s_pt = pair, s_q = 0;
+    uint32_t s_count = 0;
+    auto side_issue = [&]() {
+      while (s_pt < total_pair_tiles) {
+        const int nt = s_pt % n_tiles;
+        const int mtile = 2 * ((s_pt / n_tiles) * kPairs + (int)pidx) + (int)rank;
+        const int n0 = nt * p.tile_n;
+        int ncols = p.cout - n0;
+        ncols = ncols > p.tile_n ? p.tile_n : ncols;
+        if (mtile >= m_tiles || s_q >= ((ncols + 63) >> 6)) { s_pt += npairs; s_q = 0; continue; }
+        int mt = mtile;
+        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+        const int ty = mt % p.tiles_y;
+        const int img = mt / p.tiles_y;
+        const uint32_t b = s_count & 1;
+        mbar_expect_tx(sfull0 + 8 * b, kEpiBufBytes);
+        tma_load_4d(smem_u32(side_buf) + b * kEpiBufBytes, &tmap_s, sfull0 + 8 * b, n0 + s_q * 64, tx * p.bw, ty * p.bh, img);
+        ++s_q;
+        ++s_count;
+        return;
+      }
+    };
+    if ((MODE & 2) && epi_tid == 0) { side_issue(); side_issue(); }
     uint32_t tcount = 0, chunk_count = 0;
     for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
       const int nt = pt % n_tiles;
@@ -808,7 +849,6 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int n0 = nt * p.tile_n;
       const int oy = ty * p.bh + row / p.bw, ox = tx * p.bw + row % p.bw;
       const bool row_ok = tile_ok && oy < p.ho && ox < p.wo;
-      const __nv_bfloat16* srow = (MODE & 2) ? ep.side + (((size_t)img * p.ho + oy) * p.wo + ox) * p.cout : nullptr;
       int ncols = p.cout - n0;
       ncols = ncols > p.tile_n ? p.tile_n : ncols;
       const int nchunks = (ncols + 63) >> 6;
@@ -820,12 +860,16 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       for (int q = 0; q < nchunks; ++q) {
         const int col0 = n0 + q * 64;
         uint4 sd0[4], sd1[4];
-        if (MODE & 2) {
+        if ((MODE & 2) && tile_ok) {
+          // this row's 128 bytes of the staged side chunk (zero where the box left the tensor)
+          const uint32_t sb = chunk_count & 1;
+          mbar_wait(sfull0 + 8 * sb, (chunk_count >> 1) & 1);
+          const uint8_t* rowp = side_buf + sb * kEpiBufBytes + row * 128;
+          const int sw = row & 7;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const int c = col0 + g * 8;
-            sd0[g] = (row_ok && c < p.cout) ? __ldg(reinterpret_cast<const uint4*>(srow + c)) : make_uint4(0u, 0u, 0u, 0u);
-            sd1[g] = (row_ok && c + 32 < p.cout) ? __ldg(reinterpret_cast<const uint4*>(srow + c + 32)) : make_uint4(0u, 0u, 0u, 0u);
+            sd0[g] = *reinterpret_cast<const uint4*>(rowp + ((g ^ sw) << 4));
+            sd1[g] = *reinterpret_cast<const uint4*>(rowp + (((g + 4) ^ sw) << 4));
           }
         }
         uint32_t r0[32], r1[32];
@@ -844,6 +888,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
         if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
         epi_bar_sync();
+        if ((MODE & 2) && epi_tid == 0) side_issue();   // every thread has read its side row: refill that buffer
         {
           uint8_t* rowp = epi_buf + buf + row * 128;
           const int sw = row & 7;
@@ -1445,8 +1490,9 @@ static int g_tc_pairs_force = 0;
 
 // launch the CTA-pair forward kernel with `kp` pairs per cluster (cluster size 2*kp as a launch attribute)
 template <int MODE, int kPairs>
-static int launch_fwd_pairs_t(int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const TcEpi& ep,
-                              const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
+static int launch_fwd_pairs_t(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const CUtensorMap& ms,
+                              const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
+  constexpr int smem = TcFwdSmem<MODE>::kBytes;
   auto kern = conv_tc_fwd_2cta_kernel<MODE, kPairs>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
@@ -1471,27 +1517,29 @@ static int launch_fwd_pairs_t(int smem, const CUtensorMap& mx, const CUtensorMap
   const int total = ((m_tiles + 2 * kPairs - 1) / (2 * kPairs)) * n_tiles;
   const int clusters = total < max_clusters ? total : max_clusters;
   cfg.gridDim = dim3(clusters * 2 * kPairs);
-  CVX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, mw, my, ep, p, n_tiles, m_tiles, total));
+  CVX_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, mx, mw, my, ms, ep, p, n_tiles, m_tiles, total));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 template <int kPairs>
-static int launch_fwd_pairs_m(int mode, int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
-                              const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
+static int launch_fwd_pairs_m(int mode, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
+                              const CUtensorMap& ms, const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles,
+                              cudaStream_t st) {
   switch (mode) {
-    case 0: return launch_fwd_pairs_t<0, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-    case 1: return launch_fwd_pairs_t<1, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-    case 2: return launch_fwd_pairs_t<2, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-    default: return launch_fwd_pairs_t<3, kPairs>(smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    case 0: return launch_fwd_pairs_t<0, kPairs>(mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
+    case 1: return launch_fwd_pairs_t<1, kPairs>(mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
+    case 2: return launch_fwd_pairs_t<2, kPairs>(mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
+    default: return launch_fwd_pairs_t<3, kPairs>(mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
   }
 }
 
-static int launch_fwd_pairs(int kp, int mode, int smem, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
-                            const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles, cudaStream_t st) {
-  if (kp == 4) return launch_fwd_pairs_m<4>(mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-  if (kp == 2) return launch_fwd_pairs_m<2>(mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
-  return launch_fwd_pairs_m<1>(mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+static int launch_fwd_pairs(int kp, int mode, const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my,
+                            const CUtensorMap& ms, const TcEpi& ep, const TcFwdParams& p, int n_tiles, int m_tiles,
+                            cudaStream_t st) {
+  if (kp == 4) return launch_fwd_pairs_m<4>(mode, mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
+  if (kp == 2) return launch_fwd_pairs_m<2>(mode, mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
+  return launch_fwd_pairs_m<1>(mode, mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
 }
 
 // rows = output pixels [n,ho,wo] ; src = [n,hs,ws,cred] ; wp = [taps][ncol][cred]
@@ -1520,7 +1568,6 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
       const int nt = (ncol + kPBN - 1) / kPBN;
       p.tile_n = ((ncol + nt - 1) / nt + 63) & ~63;
     }
-    constexpr int smem = k2Stages * k2StageBytes + 2 * kEpiBufBytes + 1024 + 256 + kEpiStatsBytes;
     const int n_tiles = (ncol + p.tile_n - 1) / p.tile_n;
     const int m_tiles = n * p.tiles_y * p.tiles_x;
     CVX_CHECK_ARG(!ep.stats || n_tiles <= kEpiMaxNTiles, "conv_tc: fused statistics need C_out <= %d", kEpiMaxNTiles * kPBN);
@@ -1532,7 +1579,10 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
     if (int rc = make_weight_map(&mw, wp, kh * kw, ncol, cred, p.tile_n / (2 * kp))) return rc;
     if (int rc = make_act_map(&my, dst, n, ho, wo, ncol, p.bw, p.bh)) return rc;
-    return launch_fwd_pairs(kp, mode, smem, mx, mw, my, ep, p, n_tiles, m_tiles, st);
+    CUtensorMap ms = my;
+    if (ep.side)
+      if (int rc = make_act_map(&ms, ep.side, n, ho, wo, ncol, p.bw, p.bh)) return rc;
+    return launch_fwd_pairs(kp, mode, mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
   }
   if (!use_v1) {
     CUtensorMap mx, mw;

@@ -54,9 +54,9 @@ class _Sep:
 # (647 vs 644 img/s for the whole step).
 _STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "1") != "0"
 # CERVIX_BN1_IN_DGRAD=1 moves bn1's backward from the depthwise backward kernel (one more tensor read and an in-place
-# pre-pass there) into the data-gradient GEMM's epilogue.  Measured on B200: the GEMM grows from 46 to 106 us (its
-# per-thread side-row loads are uncoalesced; a TMA-staged side tile is the missing piece) while the depthwise kernel
-# saves ~25 us, 600 vs 641 img/s for the whole step - so it is off by default.
+# pre-pass there) into the data-gradient GEMM's epilogue, whose side tile is staged by TMA.  Measured on B200 for the
+# 728-channel middle-flow shape: the GEMM grows from 46 to 76 us (its epilogue becomes the critical path) while the
+# depthwise kernel saves ~25 us - 637 vs 638 img/s for the whole step, a wash - so it stays off by default.
 _BN1_IN_DGRAD = os.environ.get("CERVIX_BN1_IN_DGRAD", "0") == "1"
 
 

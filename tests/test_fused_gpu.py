@@ -86,6 +86,13 @@ def test_conv_epilogue_side_and_stats(n, h, w, cin, cout):
     yr, _ = EMU.conv_fwd_ex(x, wp, bias, g, None, None, False)
     assert rel(y.float(), yr.float()) < 1.2e-2
     assert rel(st, EMU._stats(y)) < 1e-5
+    # forward with side input AND statistics (both epilogue extras at once)
+    sidef = rnd(n, h, w, cout, seed=8, dtype=torch.bfloat16)
+    ssf = rnd(cout, seed=9)
+    y2, st2 = B.conv_fwd_ex(x, wp, bias, g, sidef, ssf, True)
+    y2r, _ = EMU.conv_fwd_ex(x, wp, bias, g, sidef, ssf, False)
+    assert rel(y2.float(), y2r.float()) < 1.2e-2
+    assert rel(st2, EMU._stats(y2)) < 1e-5
     # data gradient with the side term: dx = dy . W^T + bias + side_scale * side
     dy = rnd(n, h, w, cout, seed=4, dtype=torch.bfloat16)
     side = rnd(n, h, w, cin, seed=5, dtype=torch.bfloat16)
