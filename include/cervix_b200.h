@@ -180,6 +180,13 @@ CVX_API int cvx_seg_loss_grad(const float* logits, const int64_t* target, const 
 /* cvx_conv_fwd_tc with epilogue extras: y = conv + bias[c] + side_scale[c]*side[row][c]; stats += (sum y, sum y^2) */
 CVX_API int cvx_conv_fwd_tc_ex(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                        const void* side, const float* side_scale, double* stats, void* y, void* stream);
+/* Inference form: y = act(conv + bias[c] + side_scale[c]*side[row][c]) with act = CVX_ACT_NONE / CVX_ACT_RELU
+ * (side_scale == NULL: plain residual add).  With an
+ * eval-mode BatchNorm folded into w_packed / bias and the residual branch as the side input this is a whole
+ * conv -> bn -> (+identity) -> relu group of torchvision's Bottleneck (the classifier's ResNet-101 patch encoder,
+ * MM/Graph_Structure(data_augmentation).py:136-168) in one kernel. */
+CVX_API int cvx_conv_fwd_tc_act(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                        const void* side, const float* side_scale, int act, void* y, void* stream);
 /* cvx_conv_dgrad_tc with the same epilogue (side has the shape of dx) */
 CVX_API int cvx_conv_dgrad_tc_ex(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, const float* bias,
                          const void* side, const float* side_scale, void* dx, void* stream);

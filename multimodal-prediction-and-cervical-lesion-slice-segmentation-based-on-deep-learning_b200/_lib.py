@@ -71,6 +71,7 @@ PROTOTYPES = {
     "cvx_seg_loss_finalize": [_P, _P, _I, _F, _F, _P],
     "cvx_seg_loss_grad": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P],
     "cvx_conv_fwd_tc_ex": [_D, _P, _P, _P, _P, _P, _P, _P, _P],
+    "cvx_conv_fwd_tc_act": [_D, _P, _P, _P, _P, _P, _I, _P, _P],
     "cvx_conv_dgrad_tc_ex": [_D, _P, _P, _P, _P, _P, _P, _P],
     "cvx_dwf_fwd": [_D, _P, _P, _P, _P, _I, _P, _P, _P],
     "cvx_dwf_bwd": [_D, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P],

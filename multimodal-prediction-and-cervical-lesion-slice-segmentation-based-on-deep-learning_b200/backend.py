@@ -557,6 +557,15 @@ class CudaBackend:
                                           self._stream()), "cvx_conv_fwd_tc_ex")
         return y, stats
 
+    def conv_fwd_act(self, x, wp, bias, g: ConvGeom, act: int = 0, side=None, side_scale=None):
+        """y = act(conv(x) + bias + side_scale * side): the inference group conv -> folded bn -> (+identity) -> relu."""
+        self._chk(x, wp, bias, side, side_scale)
+        y = torch.empty((g.n, g.ho, g.wo, g.cout), dtype=x.dtype, device=x.device)
+        d = g.desc(_dt(x))
+        check(self.lib.cvx_conv_fwd_tc_act(C.byref(d), _p(x), _p(wp), _p(bias), _p(side), _p(side_scale), int(act), _p(y),
+                                           self._stream()), "cvx_conv_fwd_tc_act")
+        return y
+
     def conv_dgrad_ex(self, dy, wpt, g: ConvGeom, bias=None, side=None, side_scale=None):
         self._chk(dy, wpt, bias, side, side_scale)
         dx = torch.empty((g.n, g.h, g.w, g.cin), dtype=dy.dtype, device=dy.device)

@@ -110,6 +110,7 @@ struct TcEpi {
   const __nv_bfloat16* side;
   const float* side_scale;
   double* stats;
+  int relu;   // y = max(y, 0) after bias and side (inference: BatchNorm folded into the weights, residual as side)
 };
 constexpr int kEpiMaxNTiles = 8;
 constexpr int kEpiStatsBytes = kEpiMaxNTiles * 256 * 2 * 4;  // per-CTA fp32 staging [n_tile][2][256]
@@ -190,7 +191,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcEpi& ep, uint32_t t_add
 
 // lean epilogue of the plain (bias-only) kernels
 __device__ __forceinline__ void tc_epilogue_tile_plain(const float* __restrict__ bias, uint32_t t_addr, int tile_n, int n0,
-                                                       int cout, bool row_ok, __nv_bfloat16* yrow) {
+                                                       int cout, bool row_ok, __nv_bfloat16* yrow, bool relu = false) {
 #pragma unroll 1
   for (int c0 = 0; c0 < tile_n; c0 += 32) {
     if (n0 + c0 >= cout) break;  // warp-uniform
@@ -218,6 +219,7 @@ __device__ __forceinline__ void tc_epilogue_tile_plain(const float* __restrict__
           for (int j = 0; j < 4; ++j) {
             float v0 = __uint_as_float(r[g * 8 + 2 * j]), v1 = __uint_as_float(r[g * 8 + 2 * j + 1]);
             if (bias) { v0 += bv[2 * j]; v1 += bv[2 * j + 1]; }
+            if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
             packed[j] = *reinterpret_cast<uint32_t*>(&h);
           }
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
         tc_epilogue_tile(ep, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff, ep.side ? ep.side + roff : nullptr,
                          stats_sm + nt * 512, lane);
       else
-        tc_epilogue_tile_plain(ep.bias, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff);
+        tc_epilogue_tile_plain(ep.bias, t_addr, p.tile_n, n0, p.cout, row_ok, y + roff, ep.relu != 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
@@ -640,7 +642,10 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
       const uint4 sv = side_raw[g];   // prefetched by the caller ahead of the TMEM load (one L2 round trip per chunk)
       const uint32_t su[4] = {sv.x, sv.y, sv.z, sv.w};
       float ss[8];
-      if ((reinterpret_cast<uintptr_t>(ep.side_scale) & 15) == 0) {
+      if (ep.side_scale == nullptr) {            // plain residual add
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss[j] = 1.f;
+      } else if ((reinterpret_cast<uintptr_t>(ep.side_scale) & 15) == 0) {
         const float4 s0 = __ldg(reinterpret_cast<const float4*>(ep.side_scale + c));
         const float4 s1 = __ldg(reinterpret_cast<const float4*>(ep.side_scale + c + 4));
         ss[0] = s0.x; ss[1] = s0.y; ss[2] = s0.z; ss[3] = s0.w; ss[4] = s1.x; ss[5] = s1.y; ss[6] = s1.z; ss[7] = s1.w;
@@ -656,8 +661,9 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float v0 = __uint_as_float(r[g * 8 + 2 * j]) + bv[2 * j] + sd[2 * j];
-      const float v1 = __uint_as_float(r[g * 8 + 2 * j + 1]) + bv[2 * j + 1] + sd[2 * j + 1];
+      float v0 = __uint_as_float(r[g * 8 + 2 * j]) + bv[2 * j] + sd[2 * j];
+      float v1 = __uint_as_float(r[g * 8 + 2 * j + 1]) + bv[2 * j + 1] + sd[2 * j + 1];
+      if (ep.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
       __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
       const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
       packed[g * 4 + j] = ((MODE & 1) && !(ok && row_ok)) ? 0u : u;   // rows / channels outside the tensor must not reach the statistics
@@ -1646,7 +1652,7 @@ int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w_packed,
                     void* stream) {
   if (int rc = tc_supported(d, "conv_fwd_tc", true)) return rc;
   CVX_CHECK_ARG(x && w_packed && y, "conv_fwd_tc: null pointer");
-  const TcEpi ep{bias, nullptr, nullptr, nullptr};
+  const TcEpi ep{bias, nullptr, nullptr, nullptr, 0};
   return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, ep, y,
                    as_stream(stream), d->stride);
 }
@@ -1656,7 +1662,18 @@ int cvx_conv_fwd_tc_ex(const cvx_conv_desc* d, const void* x, const void* w_pack
   if (int rc = tc_supported(d, "conv_fwd_tc_ex", true)) return rc;
   CVX_CHECK_ARG(x && w_packed && y && (!side || side_scale), "conv_fwd_tc_ex: null pointer");
   if (stats) CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, as_stream(stream)));
-  const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, stats};
+  const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, stats, 0};
+  return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, ep, y,
+                   as_stream(stream), d->stride);
+}
+
+int cvx_conv_fwd_tc_act(const cvx_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* side,
+                        const float* side_scale, int act, void* y, void* stream) {
+  if (int rc = tc_supported(d, "conv_fwd_tc_act", true)) return rc;
+  CVX_CHECK_ARG(x && w_packed && y, "conv_fwd_tc_act: null pointer");   // side_scale == NULL: plain residual add
+  CVX_CHECK_ARG(act == CVX_ACT_NONE || act == CVX_ACT_RELU, "conv_fwd_tc_act: activation %d not supported", act);
+  CVX_CHECK_ARG(!side || d->stride == 1, "conv_fwd_tc_act: the side input needs a stride-1 convolution");
+  const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, nullptr, act == CVX_ACT_RELU ? 1 : 0};
   return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, ep, y,
                    as_stream(stream), d->stride);
 }
@@ -1667,7 +1684,7 @@ int cvx_conv_dgrad_tc_ex(const cvx_conv_desc* d, const void* dy, const void* w_p
   CVX_CHECK_ARG(dy && w_packed_t && dx && (!side || side_scale), "conv_dgrad_tc_ex: null pointer");
   const int pad_t = d->dil * (d->kh - 1) - d->pad;
   CVX_CHECK_ARG(pad_t >= 0 && d->kh == d->kw, "conv_dgrad_tc_ex: unsupported padding/filter");
-  const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, nullptr};
+  const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, nullptr, 0};
   return run_igemm(d->n, d->ho, d->wo, d->cout, d->h, d->w, d->cin, d->kh, d->kw, pad_t, d->dil, dy, w_packed_t, ep, dx,
                    as_stream(stream));
 }
@@ -1679,7 +1696,7 @@ int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_pack
   // padding dil*(k-1) - pad
   const int pad_t = d->dil * (d->kh - 1) - d->pad;
   CVX_CHECK_ARG(pad_t >= 0 && d->kh == d->kw, "conv_dgrad_tc: unsupported padding/filter");
-  const TcEpi ep{nullptr, nullptr, nullptr, nullptr};
+  const TcEpi ep{nullptr, nullptr, nullptr, nullptr, 0};
   return run_igemm(d->n, d->ho, d->wo, d->cout, d->h, d->w, d->cin, d->kh, d->kw, pad_t, d->dil, dy, w_packed_t, ep, dx,
                    as_stream(stream));
 }

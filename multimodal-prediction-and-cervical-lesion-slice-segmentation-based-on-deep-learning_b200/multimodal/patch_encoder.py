@@ -14,6 +14,48 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..backend import ConvGeom, get_backend
+
+
+def _fold_bn(conv_weight: torch.Tensor, bn: nn.BatchNorm2d):
+    """Eval-mode BatchNorm folded into the preceding bias-free conv: w' = w * g/sqrt(var+eps), b' = beta - mean*g/sqrt(..)."""
+    scale = bn.weight.detach().float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+    w = conv_weight.detach().float() * scale.view(-1, 1, 1, 1)
+    b = bn.bias.detach().float() - bn.running_mean.float() * scale
+    return w, b.contiguous()
+
+
+class _FoldedConv:
+    """Packed bf16 weights + fp32 bias of one conv+bn pair of the frozen encoder, rebuilt when its tensors change."""
+
+    def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d):
+        self.conv, self.bn = conv, bn
+        self.key = None
+        self.wp = self.bias = None
+
+    def get(self):
+        t = (self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
+        key = tuple((x.data_ptr(), x._version) for x in t)
+        if key != self.key:
+            w, self.bias = _fold_bn(self.conv.weight, self.bn)
+            self.wp = get_backend().pack_weight(w.contiguous(), torch.bfloat16, False)
+            self.key = key
+        return self.wp, self.bias
+
+
+def _conv_act(x, fc: _FoldedConv, act: int, residual=None, ones=None):
+    """act(conv(x) + folded bn (+ residual)) as ONE tensor-core kernel (cvx_conv_fwd_tc_act)."""
+    B = get_backend()
+    conv = fc.conv
+    wp, bias = fc.get()
+    cout, cin, kh, kw = conv.weight.shape
+    stride, pad = conv.stride[0], conv.padding[0]
+    if stride != 1 and kh == 1:        # 1x1 stride-s conv == 1x1 conv of the subsampled input
+        x = B.subsample(x, stride)
+        stride = 1
+    n, h, w, _ = x.shape
+    g = ConvGeom(n, h, w, cin, cout, kh, kw, stride, pad, 1)
+    return B.conv_fwd_act(x.contiguous(), wp, bias, g, act, residual, ones)
 
 
 class Bottleneck(nn.Module):
@@ -30,6 +72,19 @@ class Bottleneck(nn.Module):
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
         self.stride = stride
+        self._folded = None
+
+    def forward_folded(self, x, ones):
+        """Inference fast path (eval mode, bf16 engine, no autograd): three fused conv+bn(+residual)+relu kernels."""
+        if self._folded is None:
+            self._folded = [_FoldedConv(self.conv1, self.bn1), _FoldedConv(self.conv2, self.bn2),
+                            _FoldedConv(self.conv3, self.bn3),
+                            _FoldedConv(self.downsample[0], self.downsample[1]) if self.downsample is not None else None]
+        f1, f2, f3, fd = self._folded
+        identity = x if fd is None else _conv_act(x, fd, ops.ACT_NONE)
+        y = _conv_act(x, f1, ops.ACT_RELU)
+        y = _conv_act(y, f2, ops.ACT_RELU)
+        return _conv_act(y, f3, ops.ACT_RELU, identity, None)
 
     def forward(self, x):
         identity = x
@@ -82,15 +137,30 @@ class ResNet101Encoder(nn.Module):
         self._cervix_dtype = dtype
         return self
 
+    def _fold_ok(self, x) -> bool:
+        B = get_backend()
+        return (not self.training and not torch.is_grad_enabled() and self._cervix_dtype == torch.bfloat16 and x.is_cuda
+                and getattr(B, "is_sm100", lambda: False)() and hasattr(B, "conv_fwd_act"))
+
     def forward(self, x):
+        fold = self._fold_ok(x)
         x = ops.to_nhwc(x, self._cervix_dtype)
         c1 = self.conv1
         x = ops.conv2d_narrow_in(x, c1.weight, c1.stride[0], c1.padding[0])
         x = ops.batchnorm_act(x, self.bn1, ops.ACT_RELU)
         x = ops.maxpool3x3s2(x)
-        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
-            for blk in layer:
-                x = blk(x)
+        if fold:
+            # frozen eval-mode network (the only way the reference uses it): BatchNorm folded into the conv weights,
+            # bias + residual + ReLU in the GEMM epilogue - no separate normalisation pass over any activation
+            if getattr(self, "_ones", None) is None or self._ones.device != x.device:
+                self._ones = torch.ones(2048, dtype=torch.float32, device=x.device)
+            for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+                for blk in layer:
+                    x = blk.forward_folded(x, self._ones)
+        else:
+            for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+                for blk in layer:
+                    x = blk(x)
         x = ops.global_avg_pool(x)                                        # [N,1,1,2048]
         w = self.fc.weight.reshape(self.fc.out_features, self.fc.in_features, 1, 1)
         y = ops.conv2d(x.float() if self._cervix_dtype == torch.float32 else x, w, self.fc.bias, 1, 0, 1)

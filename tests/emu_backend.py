@@ -349,6 +349,15 @@ class EmuBackend:
         y = _nhwc(y, x.dtype)
         return y, (self._stats(y) if want_stats else None)
 
+    def conv_fwd_act(self, x, wp, bias, g, act=0, side=None, side_scale=None):
+        y = F.conv2d(_nchw(x), self._unpack(wp, g), None if bias is None else bias.float(), g.stride, g.pad, g.dil)
+        y = y.permute(0, 2, 3, 1).float()
+        if side is not None:
+            y = y + (side.float() if side_scale is None else side.float() * side_scale.view(1, 1, 1, -1))
+        if act == 1:
+            y = torch.relu(y)
+        return y.to(x.dtype)
+
     def conv_dgrad_ex(self, dy, wpt, g, bias=None, side=None, side_scale=None):
         w = self._unpack_t(wpt, g)
         dx = torch.nn.grad.conv2d_input((g.n, g.cin, g.h, g.w), w, _nchw(dy), g.stride, g.pad, g.dil)

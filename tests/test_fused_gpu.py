@@ -103,6 +103,32 @@ def test_conv_epilogue_side_and_stats(n, h, w, cin, cout):
     assert rel(dx.float(), dxr.float()) < 1.2e-2
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,k,stride", [(2, 16, 16, 256, 1024, 1, 1), (3, 20, 12, 64, 64, 3, 1),
+                                                      (2, 32, 32, 128, 128, 3, 2), (1, 8, 8, 1024, 256, 1, 1)])
+def test_conv_act_epilogue(n, h, w, cin, cout, k, stride):
+    """cvx_conv_fwd_tc_act: act(conv + bias + side_scale*side) - the folded conv/bn/residual/relu group of the
+    classifier's ResNet-101 encoder; the stride-2 3x3 takes the single-CTA kernel, whose epilogue has the ReLU too."""
+    B = get_backend()
+    g = ConvGeom(n, h, w, cin, cout, k, k, stride, k // 2, 1)
+    x = rnd(n, h, w, cin, seed=1, dtype=torch.bfloat16)
+    wt = rnd(cout, cin, k, k, seed=2, scale=(1.0 / (cin * k * k)) ** 0.5)
+    bias = rnd(cout, seed=3)
+    wp = B.pack_weight(wt, torch.bfloat16, False)
+    y = B.conv_fwd_act(x, wp, bias, g, 1)
+    yr = EMU.conv_fwd_act(x, wp, bias, g, 1)
+    assert float(y.float().min()) >= 0.0 and rel(y.float(), yr.float()) < 1.2e-2
+    if stride == 1:
+        side = rnd(n, g.ho, g.wo, cout, seed=4, dtype=torch.bfloat16)
+        ss = rnd(cout, seed=5).abs() + 0.5
+        y2 = B.conv_fwd_act(x, wp, bias, g, 1, side, ss)
+        y2r = EMU.conv_fwd_act(x, wp, bias, g, 1, side, ss)
+        assert rel(y2.float(), y2r.float()) < 1.2e-2
+        y4 = B.conv_fwd_act(x, wp, bias, g, 1, side, None)          # plain residual add
+        assert rel(y4.float(), EMU.conv_fwd_act(x, wp, bias, g, 1, side, None).float()) < 1.2e-2
+        y3 = B.conv_fwd_act(x, wp, None, g, 0, side, ss)
+        assert rel(y3.float(), EMU.conv_fwd_act(x, wp, None, g, 0, side, ss).float()) < 1.2e-2
+
+
 def test_small_kernels():
     B = get_backend()
     c, cout, rows = 728, 1024, 4096

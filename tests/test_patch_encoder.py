@@ -38,6 +38,33 @@ def test_cpu_host_graph_matches_torchvision():
         backend.set_backend(prev)
 
 
+def test_folded_bottleneck_matches_unfolded_on_emulation():
+    """The inference fast path (BatchNorm folded into the conv weights, bias + residual + ReLU in the conv epilogue)
+    against the operator-by-operator eval forward of the same block, on the emulated C ABI."""
+    from cervix_b200.multimodal.patch_encoder import Bottleneck
+    prev = backend.set_backend(EmuBackend())
+    try:
+        torch.manual_seed(0)
+        for inpl, planes, stride in ((64, 16, 1), (64, 32, 2)):
+            down = None
+            if stride != 1 or inpl != planes * 4:
+                down = torch.nn.Sequential(torch.nn.Conv2d(inpl, planes * 4, 1, stride, bias=False),
+                                           torch.nn.BatchNorm2d(planes * 4))
+            blk = Bottleneck(inpl, planes, stride, down).eval()
+            for m in blk.modules():
+                if isinstance(m, torch.nn.BatchNorm2d):
+                    m.running_mean.normal_(0, 0.2); m.running_var.uniform_(0.5, 1.5)
+                    m.weight.data.uniform_(0.5, 1.5); m.bias.data.normal_(0, 0.2)
+            x = torch.randn(2, 12, 10, inpl)            # NHWC fp32: the emulation keeps full precision
+            with torch.no_grad():
+                want = blk(x)
+                got = blk.forward_folded(x, torch.ones(2048))
+            assert got.shape == want.shape
+            assert float((got - want).abs().max()) < 2e-2 * float(want.abs().max())   # weights are packed in bf16
+    finally:
+        backend.set_backend(prev)
+
+
 def test_split_patches_order_and_normalisation():
     img = torch.rand(1, 3, 1024, 1024)
     p = split_patches(img)
