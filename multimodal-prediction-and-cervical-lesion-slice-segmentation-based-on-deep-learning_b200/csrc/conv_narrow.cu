@@ -389,6 +389,51 @@ __global__ void im2col_narrow_kernel(const T* __restrict__ x, T* __restrict__ y,
   }
 }
 
+// Same result, row-wise: a thread keeps ONE 8-wide slice of the patch vector (its taps / channels are decoded once),
+// a block walks whole output rows, so the inner loop is 8 bounds checks + loads and one 16-byte store per pixel.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_narrow_rows_kernel(const T* __restrict__ x, T* __restrict__ y, NGeom g,
+                                                                 int kpad) {
+  constexpr int V = Elem<T>::kVec;
+  const int kv = kpad / V;                        // <= 32 (host-checked)
+  const int K = g.kh * g.kw * g.cin;
+  const int kvi = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  if (kvi >= kv) return;
+  int dy[V], dx[V], ci[V];
+  bool kok[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int k = kvi * V + i;
+    kok[i] = k < K;
+    const int tap = kok[i] ? k / g.cin : 0;
+    ci[i] = kok[i] ? k - tap * g.cin : 0;
+    dy[i] = (tap / g.kw) * g.dil - g.pad;
+    dx[i] = (tap % g.kw) * g.dil - g.pad;
+  }
+  const int rows = g.n * g.ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int nn = row / g.ho, oy = row - nn * g.ho;
+    const T* rp[V];
+    bool rok[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int iy = oy * g.stride + dy[i];
+      rok[i] = kok[i] && iy >= 0 && iy < g.h;
+      rp[i] = x + ((size_t)nn * g.h + (rok[i] ? iy : 0)) * g.w * g.cin + ci[i];
+    }
+    T* out = y + ((size_t)row * g.wo) * kpad + kvi * V;
+    for (int ox = pl; ox < g.wo; ox += 8) {
+      Vec<T> o;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int ix = ox * g.stride + dx[i];
+        o.v[i] = (rok[i] && ix >= 0 && ix < g.w) ? Elem<T>::ld(rp[i] + (size_t)ix * g.cin) : 0.f;
+      }
+      o.store(out + (size_t)ox * kpad);
+    }
+  }
+}
+
 static bool is_stem(const cvx_conv_desc* d) {
   return d->cin <= 4 && d->cout == kStemCout && d->kh * d->kw * d->cin <= kStemMaxK;
 }
@@ -482,6 +527,12 @@ extern "C" int cvx_im2col_narrow(const cvx_conv_desc* d, const void* x, void* pa
   CVX_CHECK_ARG(d->cin <= 4 && kpad % vec == 0 && kpad >= d->kh * d->kw * d->cin, "im2col_narrow: bad geometry");
   const NGeom g = ngeom(d);
   const int64_t total = (int64_t)d->n * d->ho * d->wo * (kpad / vec);
+  if (kpad / vec <= 32 && (int64_t)d->n * d->ho < (1 << 30)) {
+    CVX_DISPATCH_DTYPE(d->dtype, T, (im2col_narrow_rows_kernel<T><<<cap_blocks((int64_t)d->n * d->ho, 8), 256, 0, as_stream(stream)>>>(
+                                        (const T*)x, (T*)patches, g, kpad)));
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
   CVX_DISPATCH_DTYPE(d->dtype, T, (im2col_narrow_kernel<T><<<cap_blocks(ceil_div64(total, 256), 16), 256, 0, as_stream(stream)>>>(
                                       (const T*)x, (T*)patches, g, kpad)));
   CVX_LAUNCH_OK();
