@@ -170,7 +170,9 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
     flat = FlatParams(head)
     m1, v1 = torch.zeros_like(flat.data), torch.zeros_like(flat.data)
     imgs = torch.rand(patients, 3, 3, size, size, device="cuda")
-    cli = torch.randn(patients, 4, 1024, device="cuda")
+    from cervix_b200.multimodal.cli_features import AgeNodeFeatures
+    ages = torch.randint(20, 81, (patients,))                       # random age scalars (BASELINE north_star inputs)
+    cli = AgeNodeFeatures(max_age=100).cuda()(ages, 20, 80)         # [patients, 4, 1024] clinical node rows
     labels = torch.randint(0, 4, (patients,), device="cuda")
     edges = {"imgN": get_edge_index_image(), "imgA": get_edge_index_image(), "imgL": get_edge_index_image(),
              "cli": get_edge_index_full(4)}

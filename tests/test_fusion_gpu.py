@@ -193,3 +193,15 @@ def test_train_step_with_dropout_decreases_loss():
         losses.append(float(loss))
     assert all(np.isfinite(losses)), losses
     assert np.mean(losses[-3:]) < np.mean(losses[:3]), losses
+
+
+def test_age_node_features_on_device():
+    """Row C2 on the GPU (embedding look-ups through the CUDA row gather) equals the CPU assembly."""
+    from cervix_b200.multimodal.cli_features import AgeNodeFeatures
+    ages = [23, 35, 41, 58, 64, 79, 30, 52, 23, 79]
+    torch.manual_seed(0)
+    mod = AgeNodeFeatures(max_age=90)
+    ref = mod(ages, 20, 80)
+    got = mod.cuda()(ages, 20, 80)
+    assert got.is_cuda and got.shape == (len(ages), 4, 1024)
+    assert torch.equal(got.cpu(), ref)

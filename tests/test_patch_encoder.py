@@ -99,3 +99,22 @@ def test_gpu_bf16_tracks_torchvision():
     cos = torch.nn.functional.cosine_similarity(a, b, dim=1)
     assert float(cos.min()) > 0.995, float(cos.min())
     assert float((a - b).abs().max()) < 0.08 * float(b.abs().max())
+
+
+def test_age_node_features_match_reference_recipe():
+    """x_cli rows against a numpy restatement of Graph_Structure(...).py:70-127."""
+    import numpy as np
+    from cervix_b200.multimodal.cli_features import AgeNodeFeatures, age_to_one_hot
+    ages = [23, 35, 41, 58, 64, 79, 30, 52]
+    torch.manual_seed(0)
+    mod = AgeNodeFeatures(max_age=max(ages))
+    got = mod(ages)
+    assert got.shape == (len(ages), 4, 1024)
+    hi, lo = max(ages), min(ages)
+    for g, age in enumerate(ages):
+        norm = (age - (hi + lo) / 2) / (hi - lo) * 2
+        assert np.array_equal(got[g, 0].numpy(), age_to_one_hot(age).astype(np.float32))
+        assert np.array_equal(got[g, 1].numpy(), age_to_one_hot(norm).astype(np.float32))   # bin 0 or the LAST bin
+        assert torch.equal(got[g, 2], mod.age_table[age])
+        assert torch.equal(got[g, 3], mod.age_std_table[int((norm + 1) / 2 * 100)])
+    assert got[ages.index(23), 1].argmax() == 19 and got[ages.index(79), 1].argmax() == 0
