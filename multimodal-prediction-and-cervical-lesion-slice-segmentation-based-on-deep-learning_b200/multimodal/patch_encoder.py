@@ -185,8 +185,49 @@ def split_patches(images: torch.Tensor, new_size: int = 1024, patch_size: int = 
     return x.reshape(b * k * k, 3, patch_size, patch_size).contiguous()
 
 
+def resize_and_split_image(image, target_size: int = 1024, split_size: int = 256):
+    """PIL form of the reference helper (:151-161): path or PIL image -> bilinear resize to target_size^2 -> the
+    16 PIL patches in the reference's order (outer loop over x)."""
+    from PIL import Image
+    img = Image.open(image) if isinstance(image, (str, bytes)) or hasattr(image, "__fspath__") else image
+    resized = img.resize((target_size, target_size), Image.BILINEAR)
+    return [resized.crop((i, j, i + split_size, j + split_size))
+            for i in range(0, target_size, split_size) for j in range(0, target_size, split_size)]
+
+
+def _pil_to_tensor(image) -> torch.Tensor:
+    import numpy as np
+    a = np.asarray(image.convert("RGB"), dtype=np.float32) / 255.0
+    return torch.from_numpy(a).permute(2, 0, 1).contiguous()
+
+
 @torch.no_grad()
-def extract_features(patches: torch.Tensor, model: ResNet101Encoder) -> torch.Tensor:
-    """``extract_features`` (:164-168) for a whole batch of patches at once: [P,3,256,256] -> [P,1024]."""
+def extract_features(image, model: ResNet101Encoder, transform=None, device=None):
+    """Two call forms.
+      * reference form (:164-168): ``extract_features(pil_patch, model, transform, device) -> np.ndarray[1024]``
+        (``transform`` defaults to ToTensor + ImageNet normalisation);
+      * batched form: ``extract_features(patches[P,3,256,256], model) -> Tensor[P,1024]`` - all patches of all
+        modalities in ONE pass through the encoder, which is how the B200 path is meant to be driven."""
     model.eval()
-    return model(patches)
+    if torch.is_tensor(image):
+        return model(image)
+    dev = device if device is not None else next(model.parameters()).device
+    if transform is not None:
+        x = transform(image)
+    else:
+        mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
+        std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
+        x = (_pil_to_tensor(image) - mean) / std
+    return model(x.unsqueeze(0).to(dev)).float().cpu().numpy().flatten()
+
+
+@torch.no_grad()
+def extract_patient_features(image, model: ResNet101Encoder, device=None):
+    """All 16 patch features of one colposcopic image in one encoder pass: PIL image / path -> np.ndarray[16, 1024]
+    (what the reference's per-patch loop, :196-200, accumulates into ``patch_features_dict``)."""
+    model.eval()
+    dev = device if device is not None else next(model.parameters()).device
+    mean = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    x = torch.stack([_pil_to_tensor(p) for p in resize_and_split_image(image)])
+    return model(((x - mean) / std).to(dev)).float().cpu().numpy()

@@ -118,3 +118,32 @@ def test_age_node_features_match_reference_recipe():
         assert torch.equal(got[g, 2], mod.age_table[age])
         assert torch.equal(got[g, 3], mod.age_std_table[int((norm + 1) / 2 * 100)])
     assert got[ages.index(23), 1].argmax() == 19 and got[ages.index(79), 1].argmax() == 0
+
+
+def test_pil_entry_points_match_the_batched_path():
+    """resize_and_split_image / extract_features in the reference's PIL-in numpy-out form (Graph_Structure...py:151-168)
+    against the tensor path, on the emulated C ABI."""
+    import numpy as np
+    from PIL import Image
+    from cervix_b200.multimodal.patch_encoder import extract_patient_features, resize_and_split_image
+    prev = backend.set_backend(EmuBackend())
+    try:
+        _, enc = _pair(3)
+        enc.set_compute_dtype(torch.float32)
+        rng = np.random.RandomState(0)
+        img = Image.fromarray(rng.randint(0, 255, (96, 80, 3), dtype=np.uint8))
+        patches = resize_and_split_image(img, 256, 64)       # small sizes keep the CPU test quick
+        assert len(patches) == 16 and patches[0].size == (64, 64)
+        resized = np.asarray(img.resize((256, 256), Image.BILINEAR))
+        assert np.array_equal(np.asarray(patches[1]), resized[64:128, 0:64])       # index 1 = (x block 0, y block 1)
+        assert np.array_equal(np.asarray(patches[4]), resized[0:64, 64:128])       # index 4 = (x block 1, y block 0)
+        one = extract_features(patches[5], enc)
+        assert isinstance(one, np.ndarray) and one.shape == (1024,)
+        import torchvision.transforms as T
+        tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+        same = extract_features(patches[5], enc, tf, torch.device("cpu"))
+        assert np.allclose(one, same, rtol=1e-4, atol=1e-5)
+        batch = torch.stack([tf(p) for p in patches[4:7]])
+        assert np.allclose(extract_features(batch, enc)[1].numpy(), one, rtol=1e-3, atol=1e-4)
+    finally:
+        backend.set_backend(prev)
