@@ -35,6 +35,8 @@ def test_reference_import_paths_resolve():
         "from utils.utils import cvtColor, preprocess_input, resize_image, show_config, get_lr, seed_everything\n"
         "from deeplab import DeeplabV3\n"
         "from my_mae_model import fusion_model_mae_2\n"
+        "from mae_utils import generate_mask\n"
+        "from util import Logger, adjust_learning_rate\n"
         "import inspect\n"
         "print(list(inspect.signature(fit_one_epoch).parameters))\n" % DROPIN)
     out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=300)
