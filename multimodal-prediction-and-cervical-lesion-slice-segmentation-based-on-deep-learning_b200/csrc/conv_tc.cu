@@ -729,36 +729,41 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The producer and the issuer warps run their loops WARP-UNIFORMLY (all 32 lanes compute the same counters and
+  // addresses and wait on the same barriers); only the TMA / tcgen05 instructions themselves sit under elect_one().
+  // With the loops inside an `if (lane == 0)` the compiler must treat every operand as divergent and wraps each MMA
+  // in ~25 instructions of ELECT / R2UR.BROADCAST loops (seen in the ncu source view: ~125 instructions and
+  // 700-900 cycles per 64-channel k-block on the single issuing thread - the bound of every launch of this kernel).
   if (warp == 0) {
-    if (lane == 0) {
-      // ---- TMA producer: running counters only (no divisions inside the k loop)
-      uint32_t s = 0, ph = 0;
-      const uint32_t tx_bytes = 2 * (kABytes + (p.tile_n >> 1) * 128);
-      const uint32_t lead_full0 = map_to_cta(full0, lead_rank);
-      const int bq_rows = p.tile_n / (2 * kPairs);   // weight rows per multicast box
-      uint16_t bmask = 0;
+    // ---- TMA producer: running counters only (no divisions inside the k loop)
+    uint32_t s = 0, ph = 0;
+    const uint32_t tx_bytes = 2 * (kABytes + (p.tile_n >> 1) * 128);
+    const uint32_t lead_full0 = map_to_cta(full0, lead_rank);
+    const int bq_rows = p.tile_n / (2 * kPairs);   // weight rows per multicast box
+    uint16_t bmask = 0;
 #pragma unroll
-      for (int q = 0; q < kPairs; ++q) bmask |= (uint16_t)(1u << (2 * q + rank));
-      for (int pt = pair; pt < total_pair_tiles; pt += npairs) {
-        const int nt = pt % n_tiles;
-        const int mtile = 2 * ((pt / n_tiles) * kPairs + (int)pidx) + (int)rank;
-        int tx = 0, ty = 0, img = p.n;  // img == n -> every TMA coordinate is out of bounds (zero fill)
-        if (mtile < m_tiles) {
-          int mt = mtile;
-          tx = mt % p.tiles_x; mt /= p.tiles_x;
-          ty = mt % p.tiles_y;
-          img = mt / p.tiles_y;
-        }
-        const int n0 = nt * p.tile_n;
-        int n_eff = p.cout - n0;
-        n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
-        const int brow0 = n0 + (int)rank * (n_eff >> 1) + (int)pidx * bq_rows;
-        const int xb = tx * p.bw - p.pad, yb = ty * p.bh - p.pad;
-        int cb = 0, kwi = 0, khi = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          const uint32_t sa = smem_base + s * k2StageBytes;
-          const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;  // the leader CTA's barrier (peer bit cleared)
+    for (int q = 0; q < kPairs; ++q) bmask |= (uint16_t)(1u << (2 * q + rank));
+    for (int pt = pair; pt < total_pair_tiles; pt += npairs) {
+      const int nt = pt % n_tiles;
+      const int mtile = 2 * ((pt / n_tiles) * kPairs + (int)pidx) + (int)rank;
+      int tx = 0, ty = 0, img = p.n;  // img == n -> every TMA coordinate is out of bounds (zero fill)
+      if (mtile < m_tiles) {
+        int mt = mtile;
+        tx = mt % p.tiles_x; mt /= p.tiles_x;
+        ty = mt % p.tiles_y;
+        img = mt / p.tiles_y;
+      }
+      const int n0 = nt * p.tile_n;
+      int n_eff = p.cout - n0;
+      n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
+      const int brow0 = n0 + (int)rank * (n_eff >> 1) + (int)pidx * bq_rows;
+      const int xb = tx * p.bw - p.pad, yb = ty * p.bh - p.pad;
+      int cb = 0, kwi = 0, khi = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t sa = smem_base + s * k2StageBytes;
+        const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;  // the leader CTA's barrier (peer bit cleared)
+        if (elect_one()) {
           if (leader) mbar_expect_tx(full0 + 8 * s, tx_bytes);
           else mbar_arrive_cluster(lead_full0 + 8 * s);
           tma_load_4d_2sm(sa, &tmap_x, lead_full, cb * 64, xb + kwi * p.dil, yb + khi * p.dil, img);
@@ -766,17 +771,19 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             tma_load_3d_2sm(sa + kABytes, &tmap_w, lead_full, cb * 64, brow0, khi * p.kw + kwi);
           else
             tma_load_3d_2sm_mc(sa + kABytes + pidx * bq_rows * 128, &tmap_w, lead_full, cb * 64, brow0, khi * p.kw + kwi, bmask);
-          if (++cb == kcb) { cb = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
-          if (++s == kSt) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++cb == kcb) { cb = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
+        if (++s == kSt) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
-      // ---- MMA issuer
+    if (leader) {
+      // ---- MMA issuer (elect_one() picks the same lane every time, so all MMAs and commits come from one thread)
       uint32_t s = 0, ph = 0, tcount = 0;
       const int last_ksteps = (p.cin - (kcb - 1) * 64 >= 64) ? 4 : (p.cin - (kcb - 1) * 64 + 15) / 16;
       const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+      const uint16_t all_mask = (uint16_t)((1u << (2 * kPairs)) - 1), pair_mask = (uint16_t)(3u << (2 * pidx));
       for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
         const int nt = pt % n_tiles;
         const int n0 = nt * p.tile_n;
@@ -792,19 +799,27 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
-          const int ksteps = (cb == kcb - 1) ? last_ksteps : 4;
           const uint32_t sa = smem_base + s * k2StageBytes;
           const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
           const uint64_t bd = desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
-          for (int k = 0; k < ksteps; ++k) {
-            umma_bf16_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, accum);
-            accum = 1;
+          if (elect_one()) {
+            if (cb != kcb - 1 || last_ksteps == 4) {   // full 64-channel block: four K=16 steps, unrolled
+              umma_bf16_2sm(d_tmem, ad, bd, idesc, accum);
+              umma_bf16_2sm(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              umma_bf16_2sm(d_tmem, ad + 4, bd + 4, idesc, 1u);
+              umma_bf16_2sm(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            } else {
+              for (int kk = 0; kk < last_ksteps; ++kk) umma_bf16_2sm(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, kk ? 1u : accum);
+            }
+            umma_commit_2sm(empty0 + 8 * s, all_mask);
           }
-          umma_commit_2sm(empty0 + 8 * s, (uint16_t)((1u << (2 * kPairs)) - 1));
+          __syncwarp();
+          accum = 1;
           if (++cb == kcb) cb = 0;
           if (++s == kSt) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(tfull0 + 8 * acc, (uint16_t)(3u << (2 * pidx)));
+        if (elect_one()) umma_commit_2sm(tfull0 + 8 * acc, pair_mask);
+        __syncwarp();
       }
     }
   } else {
