@@ -1153,66 +1153,73 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
     t_end = min(t_begin + per, ptiles);
   };
 
+  // warp-uniform producer / issuer loops, elect_one() around the TMA / tcgen05 instructions (see the pair kernels)
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        int cot, cit, tap, t_begin, t_end;
-        decode(item, cot, cit, tap, t_begin, t_end);
-        const int khi = tap / p.kw, kwi = tap - khi * p.kw;
-        const int co0 = cot * 128, ci0 = cit * p.ci_tile;
-        int ci_n = p.cin - ci0;
-        ci_n = ci_n > p.ci_tile ? p.ci_tile : ci_n;
-        const int ci_boxes = (ci_n + 63) / 64;
-        int tt = t_begin;
-        int tx = tt % p.tiles_x; tt /= p.tiles_x;
-        int ty = tt % p.tiles_y;
-        int img = tt / p.tiles_y;
-        for (int t = t_begin; t < t_end; ++t, ++it) {
-          const int s = it % kWPStages;
-          mbar_wait(empty0 + 8 * s, ((it / kWPStages) & 1) ^ 1);
-          const int ox0 = tx * p.bw, oy0 = ty * p.bh;
-          const uint32_t sa = smem_base + s * kWPStageBytes;
+    uint32_t s = 0, ph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int cot, cit, tap, t_begin, t_end;
+      decode(item, cot, cit, tap, t_begin, t_end);
+      const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+      const int co0 = cot * 128, ci0 = cit * p.ci_tile;
+      int ci_n = p.cin - ci0;
+      ci_n = ci_n > p.ci_tile ? p.ci_tile : ci_n;
+      const int ci_boxes = (ci_n + 63) / 64;
+      int tt = t_begin;
+      int tx = tt % p.tiles_x; tt /= p.tiles_x;
+      int ty = tt % p.tiles_y;
+      int img = tt / p.tiles_y;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const int ox0 = tx * p.bw, oy0 = ty * p.bh;
+        const uint32_t sa = smem_base + s * kWPStageBytes;
+        if (elect_one()) {
           mbar_expect_tx(full0 + 8 * s, kWPABytes + ci_boxes * kWBox);
           tma_load_4d(sa, &tmap_dy, full0 + 8 * s, co0, ox0, oy0, img);
           tma_load_4d(sa + kWBox, &tmap_dy, full0 + 8 * s, co0 + 64, ox0, oy0, img);
           for (int j = 0; j < ci_boxes; ++j)
             tma_load_4d(sa + kWPABytes + j * kWBox, &tmap_x, full0 + 8 * s, ci0 + j * 64, ox0 - p.pad + kwi * p.dil,
                         oy0 - p.pad + khi * p.dil, img);
-          if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img; } }
         }
+        __syncwarp();
+        if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img; } }
+        if (++s == kWPStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, icount = 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++icount) {
-        int cot, cit, tap, t_begin, t_end;
-        decode(item, cot, cit, tap, t_begin, t_end);
-        const int ci0 = cit * p.ci_tile;
-        int ci_n = p.cin - ci0;
-        ci_n = ci_n > p.ci_tile ? p.ci_tile : ((ci_n + 15) & ~15);
-        const uint32_t idesc = make_idesc(128, ci_n, 1, 1);  // both operands MN-major
-        const int acc = icount & 1;
-        mbar_wait(tempty0 + 8 * acc, ((icount >> 1) & 1) ^ 1);
+    uint32_t s = 0, ph = 0, icount = 0;
+    const uint64_t desc_hi = ((uint64_t)(kWBox >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+                             ((uint64_t)2 << 61);
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++icount) {
+      int cot, cit, tap, t_begin, t_end;
+      decode(item, cot, cit, tap, t_begin, t_end);
+      const int ci0 = cit * p.ci_tile;
+      int ci_n = p.cin - ci0;
+      ci_n = ci_n > p.ci_tile ? p.ci_tile : ((ci_n + 15) & ~15);
+      const uint32_t idesc = make_idesc(128, ci_n, 1, 1);  // both operands MN-major
+      const int acc = icount & 1;
+      mbar_wait(tempty0 + 8 * acc, ((icount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 256;
+      uint32_t accum = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int t = t_begin; t < t_end; ++t, ++it) {
-          const int s = it % kWPStages;
-          mbar_wait(full0 + 8 * s, (it / kWPStages) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * kWPStageBytes;
-          const uint32_t sb = sa + kWPABytes;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * 2048, kWBox, 1024);
-            const uint64_t bd = make_smem_desc(sb + k * 2048, kWBox, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (t > t_begin || k > 0) ? 1u : 0u);
-          }
+        const uint32_t sa = smem_base + s * kWPStageBytes;
+        const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+        const uint64_t bd = desc_hi | (uint64_t)(((sa + kWPABytes) >> 4) & 0x3FFF);
+        if (elect_one()) {
+          umma_bf16(d_tmem, ad, bd, idesc, accum);
+          umma_bf16(d_tmem, ad + (uint64_t)(2048 >> 4), bd + (uint64_t)(2048 >> 4), idesc, 1u);
+          umma_bf16(d_tmem, ad + (uint64_t)(2 * (2048 >> 4)), bd + (uint64_t)(2 * (2048 >> 4)), idesc, 1u);
+          umma_bf16(d_tmem, ad + (uint64_t)(3 * (2048 >> 4)), bd + (uint64_t)(3 * (2048 >> 4)), idesc, 1u);
           umma_commit(empty0 + 8 * s);
         }
-        umma_commit(tfull0 + 8 * acc);
+        __syncwarp();
+        accum = 1;
+        if (++s == kWPStages) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) umma_commit(tfull0 + 8 * acc);
+      __syncwarp();
     }
   } else {
     const int lg = warp & 3;
@@ -1319,42 +1326,45 @@ conv_tc_wgrad_2cta_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
     return ci_n > p.ci_tile ? p.ci_tile : ((ci_n + 31) & ~31);
   };
 
+  // producer and issuer loops are warp-uniform; only the TMA / tcgen05 instructions sit under elect_one() (see the
+  // forward kernel: a divergent single-lane loop costs ~125 instructions per k-block on the issuing thread)
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
-      const uint32_t lead_full0 = map_to_cta(full0, 0);
-      for (int item = pair; item < p.total_items; item += npairs) {
-        int cot, cit, tap, t_begin, t_end;
-        decode(item, cot, cit, tap, t_begin, t_end);
-        const int khi = tap / p.kw, kwi = tap - khi * p.kw;
-        const int ci0 = cit * p.ci_tile;
-        const int half = ci_count(ci0) >> 1;
-        const int co_r = cot * 256 + (int)rank * 128, ci_r = ci0 + (int)rank * half;
-        const int nb = (half + 63) >> 6;
-        const uint32_t tx_bytes = 2 * (kW2ABytes + nb * kWBox);
-        int tt = t_begin;
-        int tx = tt % p.tiles_x; tt /= p.tiles_x;
-        int ty = tt % p.tiles_y;
-        int img = tt / p.tiles_y;
-        const int dx = kwi * p.dil - p.pad, dy = khi * p.dil - p.pad;
-        for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(empty0 + 8 * s, ph ^ 1);
-          const int ox0 = tx * p.bw, oy0 = ty * p.bh;
-          const uint32_t sa = smem_base + s * kW2StageBytes;
-          const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;
+    uint32_t s = 0, ph = 0;
+    const uint32_t lead_full0 = map_to_cta(full0, 0);
+    for (int item = pair; item < p.total_items; item += npairs) {
+      int cot, cit, tap, t_begin, t_end;
+      decode(item, cot, cit, tap, t_begin, t_end);
+      const int khi = tap / p.kw, kwi = tap - khi * p.kw;
+      const int ci0 = cit * p.ci_tile;
+      const int half = ci_count(ci0) >> 1;
+      const int co_r = cot * 256 + (int)rank * 128, ci_r = ci0 + (int)rank * half;
+      const int nb = (half + 63) >> 6;
+      const uint32_t tx_bytes = 2 * (kW2ABytes + nb * kWBox);
+      int tt = t_begin;
+      int tx = tt % p.tiles_x; tt /= p.tiles_x;
+      int ty = tt % p.tiles_y;
+      int img = tt / p.tiles_y;
+      const int dx = kwi * p.dil - p.pad, dy = khi * p.dil - p.pad;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const int ox0 = tx * p.bw, oy0 = ty * p.bh;
+        const uint32_t sa = smem_base + s * kW2StageBytes;
+        const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;
+        if (elect_one()) {
           if (leader) mbar_expect_tx(full0 + 8 * s, tx_bytes);
           else mbar_arrive_cluster(lead_full0 + 8 * s);
           tma_load_4d_2sm(sa, &tmap_dy, lead_full, co_r, ox0, oy0, img);
           tma_load_4d_2sm(sa + kWBox, &tmap_dy, lead_full, co_r + 64, ox0, oy0, img);
           tma_load_4d_2sm(sa + kW2ABytes, &tmap_x, lead_full, ci_r, ox0 + dx, oy0 + dy, img);
           if (nb > 1) tma_load_4d_2sm(sa + kW2ABytes + kWBox, &tmap_x, lead_full, ci_r + 64, ox0 + dx, oy0 + dy, img);
-          if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img; } }
-          if (++s == kW2Stages) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++tx == p.tiles_x) { tx = 0; if (++ty == p.tiles_y) { ty = 0; ++img; } }
+        if (++s == kW2Stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (leader && lane == 0) {
+    if (leader) {
       uint32_t s = 0, ph = 0, icount = 0;
       // MN-major operands: LBO = distance between 64-channel atoms, SBO = distance between 8-pixel groups
       const uint64_t desc_hi = ((uint64_t)(kWBox >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
@@ -1374,15 +1384,19 @@ conv_tc_wgrad_2cta_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
           const uint32_t sa = smem_base + s * kW2StageBytes;
           const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
           const uint64_t bd = desc_hi | (uint64_t)(((sa + kW2ABytes) >> 4) & 0x3FFF);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 16 pixels per MMA = 16 smem rows of 128 B
-            umma_bf16_2sm(d_tmem, ad + (uint64_t)(k * (2048 >> 4)), bd + (uint64_t)(k * (2048 >> 4)), idesc, accum);
-            accum = 1;
+          if (elect_one()) {   // 16 pixels per MMA = 16 smem rows of 128 B
+            umma_bf16_2sm(d_tmem, ad, bd, idesc, accum);
+            umma_bf16_2sm(d_tmem, ad + (uint64_t)(2048 >> 4), bd + (uint64_t)(2048 >> 4), idesc, 1u);
+            umma_bf16_2sm(d_tmem, ad + (uint64_t)(2 * (2048 >> 4)), bd + (uint64_t)(2 * (2048 >> 4)), idesc, 1u);
+            umma_bf16_2sm(d_tmem, ad + (uint64_t)(3 * (2048 >> 4)), bd + (uint64_t)(3 * (2048 >> 4)), idesc, 1u);
+            umma_commit_2sm(empty0 + 8 * s);
           }
-          umma_commit_2sm(empty0 + 8 * s);
+          __syncwarp();
+          accum = 1;
           if (++s == kW2Stages) { s = 0; ph ^= 1; }
         }
-        umma_commit_2sm(tfull0 + 8 * acc);
+        if (elect_one()) umma_commit_2sm(tfull0 + 8 * acc);
+        __syncwarp();
       }
     }
   } else {
