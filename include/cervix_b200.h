@@ -94,9 +94,10 @@ CVX_API int cvx_conv_fwd_tc(const cvx_conv_desc* d, const void* x, const void* w
 CVX_API int cvx_conv_dgrad_tc(const cvx_conv_desc* d, const void* dy, const void* w_packed_t, void* dx, void* stream);
 CVX_API int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, float* dw_packed, void* stream);
 /* Tuning knob of cvx_conv_fwd_tc / cvx_conv_dgrad_tc: CTA pairs per thread-block cluster (1, 2 or 4) that share one
- * weight tile through TMA multicast.  force != 0 keeps the setting even for problems too small to fill the machine
- * (tests).  Default 1 (measured fastest on B200: the large convolutions already run at the power-limited tensor
- * peak), or CERVIX_TC_PAIRS in the environment. */
+ * weight tile through TMA multicast; 0 = the library's per-shape choice (2 pairs where the reduction rows are long and
+ * not 128-byte aligned, e.g. 728 channels, else 1 - measured on B200).  force != 0 keeps an
+ * explicit setting even for problems too small to fill the machine (tests).  CERVIX_TC_PAIRS in the environment sets
+ * the initial value. */
 CVX_API int cvx_conv_tc_set_pairs(int pairs, int force);
 /* im2col of a narrow-channel input (C_in <= 4): patches[n,ho,wo,kpad], k = tap*C_in + ci, zero padded
  * to kpad (a multiple of 8).  Turns the ResNet-101 7x7/2 stem of the classifier's patch encoder

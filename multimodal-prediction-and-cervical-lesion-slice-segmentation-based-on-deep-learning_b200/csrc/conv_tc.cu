@@ -1518,8 +1518,8 @@ static int launch_fwd(const CUtensorMap& mx, const CUtensorMap& mw, const float*
 // pairs per cluster of the forward / data-gradient kernel (cvx_conv_tc_set_pairs; CERVIX_TC_PAIRS at load time)
 static int g_tc_pairs = [] {
   const char* e = getenv("CERVIX_TC_PAIRS");
-  const int v = e ? atoi(e) : 1;
-  return (v == 1 || v == 2 || v == 4) ? v : 1;
+  const int v = e ? atoi(e) : 0;
+  return (v == 1 || v == 2 || v == 4) ? v : 0;   // 0 = per-shape choice
 }();
 static int g_tc_pairs_force = 0;
 
@@ -1608,7 +1608,11 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
     CVX_CHECK_ARG(!ep.stats || n_tiles <= kEpiMaxNTiles, "conv_tc: fused statistics need C_out <= %d", kEpiMaxNTiles * kPBN);
     const int mode = (ep.stats ? 1 : 0) | (ep.side ? 2 : 0);
     // pairs per cluster: share the weight tile among 2 pairs when there are enough pixel tiles to keep the machine full
-    int kp = g_tc_pairs;
+    // Pairs per cluster.  Default (g_tc_pairs == 0): two pairs share the weight tile by TMA multicast only where it
+    // measured faster - long reduction rows that are NOT 128-byte aligned (728 channels = 1456 B: every 128-byte box
+    // row straddles two L2 lines, so the operand stream is what bounds those launches; -12 % on the 728 -> 728
+    // middle-flow GEMMs, +5..10 % everywhere else, profiles/r01_conv_shapes_pairs_v6.txt).
+    int kp = g_tc_pairs ? g_tc_pairs : (((cred * 2) % 128 != 0 && cred >= 512) ? 2 : 1);
     while (kp > 1 && ((p.tile_n / (2 * kp)) % 8 != 0 || (!g_tc_pairs_force && m_tiles < 2 * kp * 16))) kp >>= 1;
     CUtensorMap mx, mw, my;
     if (int rc = make_act_map(&mx, src, n, hs, ws, cred, p.bw, p.bh)) return rc;
@@ -1671,7 +1675,8 @@ using namespace cvx;
 extern "C" {
 
 int cvx_conv_tc_set_pairs(int pairs, int force) {
-  CVX_CHECK_ARG(pairs == 1 || pairs == 2 || pairs == 4, "conv_tc_set_pairs: pairs must be 1, 2 or 4 (got %d)", pairs);
+  CVX_CHECK_ARG(pairs == 0 || pairs == 1 || pairs == 2 || pairs == 4,
+                "conv_tc_set_pairs: pairs must be 0 (per-shape default), 1, 2 or 4 (got %d)", pairs);
   g_tc_pairs = pairs;
   g_tc_pairs_force = force != 0;
   return CVX_OK;

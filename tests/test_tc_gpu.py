@@ -21,7 +21,7 @@ def pairs(request):
     lib = _lib.load()
     assert lib.cvx_conv_tc_set_pairs(request.param, 1) == 0
     yield request.param
-    assert lib.cvx_conv_tc_set_pairs(1, 0) == 0
+    assert lib.cvx_conv_tc_set_pairs(0, 0) == 0
 
 
 @pytest.mark.parametrize("idx", range(len(CASES)))
