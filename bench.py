@@ -237,13 +237,13 @@ def time_dominant_kernel(batch: int, peaks):
     flops = 2.0 * batch * 128 * 128 * 256 * 304 * 9
     achieved = flops / (ms * 1e-3) / 1e12
     # DRAM traffic of this launch from the committed `ncu --set full` capture at batch 32
-    # (profiles/r01_ncu_conv_kernels_v4.txt: dram__bytes_read.sum 320.2 MB + dram__bytes_write.sum 233.3 MB; the
+    # (profiles/r01_ncu_conv_kernels_v6.txt: dram__bytes_read.sum 320.2 MB + dram__bytes_write.sum 233.6 MB; the
     # algorithmic bytes are 318.8 MB of input + 268.4 MB of output + 1.4 MB of weights - the tail of the output is
     # still in L2 when the capture ends).  Reported only for the batch it was captured at.
-    traffic = 553.5e6 if batch == 32 else None
+    traffic = 553.8e6 if batch == 32 else None
     return {"bound": "tensor", "kernel": "conv_tc_fwd_2cta_kernel<false, 1> (cat_conv.0: 3x3 304->256 @128x128, batch %d)" % batch,
             "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
-            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_ncu_conv_kernels_v4.txt (bytes per launch)",
+            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_ncu_conv_kernels_v6.txt (bytes per launch)",
             "peak_source": peaks["source"] + " burst bf16 (kernel timed alone)",
             "flops_per_launch": flops, "ms_per_launch": ms}
 
