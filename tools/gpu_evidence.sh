@@ -8,4 +8,4 @@ TAILN=1 stage bench_default 1200 python bench.py
 TAILN=2 stage bench_fused_graph 600 python tools/bench_fused.py --graph
 TAILN=2 stage conv_shapes 900 python tools/bench_conv_shapes.py
 TAILN=2 stage prof_b32 900 python tools/profile_step.py
-bash tools/gpu_round_g.sh
+bash tools/gpu_ncu_dwf.sh
