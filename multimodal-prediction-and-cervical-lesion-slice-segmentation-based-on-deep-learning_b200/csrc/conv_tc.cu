@@ -416,60 +416,65 @@ __global__ void __launch_bounds__(192, 1) conv_tc_fwd_persistent_kernel(const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // warp-uniform producer / issuer loops, elect_one() around the TMA / tcgen05 instructions (see the pair kernel)
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % n_tiles;
-        int mt = tile / n_tiles;
-        const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-        const int ty = mt % p.tiles_y;
-        const int img = mt / p.tiles_y;
-        const int ox0 = tx * p.bw, oy0 = ty * p.bh, n0 = nt * p.tile_n;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % kPStages;
-          mbar_wait(empty0 + 8 * s, ((it / kPStages) & 1) ^ 1);
-          const int tap = kb / kcb, cb = kb - tap * kcb;
-          const int khi = tap / p.kw, kwi = tap - khi * p.kw;
-          const uint32_t sa = smem_base + s * kPStageBytes;
+    uint32_t s = 0, ph = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % n_tiles;
+      int mt = tile / n_tiles;
+      const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+      const int ty = mt % p.tiles_y;
+      const int img = mt / p.tiles_y;
+      const int n0 = nt * p.tile_n;
+      const int xb = tx * p.bw * p.stride - p.pad, yb = ty * p.bh * p.stride - p.pad;
+      int cb = 0, kwi = 0, khi = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty0 + 8 * s, ph ^ 1);
+        const uint32_t sa = smem_base + s * kPStageBytes;
+        if (elect_one()) {
           mbar_expect_tx(full0 + 8 * s, kABytes + p.tile_n * 128);
-          tma_load_4d(sa, &tmap_x, full0 + 8 * s, cb * 64, ox0 * p.stride - p.pad + kwi * p.dil,
-                      oy0 * p.stride - p.pad + khi * p.dil, img);
-          tma_load_3d(sa + kABytes, &tmap_w, full0 + 8 * s, cb * 64, n0, tap);
+          tma_load_4d(sa, &tmap_x, full0 + 8 * s, cb * 64, xb + kwi * p.dil, yb + khi * p.dil, img);
+          tma_load_3d(sa + kABytes, &tmap_w, full0 + 8 * s, cb * 64, n0, khi * p.kw + kwi);
         }
+        __syncwarp();
+        if (++cb == kcb) { cb = 0; if (++kwi == p.kw) { kwi = 0; ++khi; } }
+        if (++s == kPStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
-        const int nt = tile % n_tiles;
-        const int n0 = nt * p.tile_n;
-        int n_eff = p.cout - n0;
-        n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
-        const uint32_t idesc = make_idesc(128, n_eff, 0, 0);
-        const int acc = tcount & 1;
-        mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
+    uint32_t s = 0, ph = 0, tcount = 0;
+    const int last_ksteps = (p.cin - (kcb - 1) * 64 >= 64) ? 4 : (p.cin - (kcb - 1) * 64 + 15) / 16;
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      const int nt = tile % n_tiles;
+      const int n0 = nt * p.tile_n;
+      int n_eff = p.cout - n0;
+      n_eff = n_eff > p.tile_n ? p.tile_n : ((n_eff + 15) & ~15);
+      const uint32_t idesc = make_idesc(128, n_eff, 0, 0);
+      const int acc = tcount & 1;
+      mbar_wait(tempty0 + 8 * acc, ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kPBN;
+      int cb = 0;
+      uint32_t accum = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kPBN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % kPStages;
-          mbar_wait(full0 + 8 * s, (it / kPStages) & 1);
-          tc_fence_after();
-          const int cb = kb % kcb;
-          const int crem = p.cin - cb * 64;
-          const int ksteps = crem >= 64 ? 4 : (crem + 15) / 16;
-          const uint32_t sa = smem_base + s * kPStageBytes;
-          const uint32_t sb = sa + kABytes;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * 32, 0, 1024);
-            const uint64_t bd = make_smem_desc(sb + k * 32, 0, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+        const int ksteps = (cb == kcb - 1) ? last_ksteps : 4;
+        const uint32_t sa = smem_base + s * kPStageBytes;
+        const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
+        const uint64_t bd = desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
+        if (elect_one()) {
+          for (int kk = 0; kk < ksteps; ++kk) umma_bf16(d_tmem, ad + 2 * kk, bd + 2 * kk, idesc, kk ? 1u : accum);
           umma_commit(empty0 + 8 * s);
         }
-        umma_commit(tfull0 + 8 * acc);
+        __syncwarp();
+        accum = 1;
+        if (++cb == kcb) cb = 0;
+        if (++s == kPStages) { s = 0; ph ^= 1; }
       }
+      if (elect_one()) umma_commit(tfull0 + 8 * acc);
+      __syncwarp();
     }
   } else {
     const int lg = warp & 3;  // TMEM lane group this warp may access
