@@ -610,13 +610,14 @@ constexpr int kEpiBufBytes = 128 * 128;  // one 128-pixel x 64-channel bf16 chun
 
 // 32 accumulator columns of one row -> (+bias, +side) -> 16 packed bf16 pairs (EXTRA: zero where the row or the
 // column lies outside the tensor, so the staged chunk can be summed for the statistics as it is).
-// shared-memory plan of the CTA-pair forward kernel per epilogue variant (227 KB per CTA): only the variant with both
-// the side-input staging buffers and the statistics scratch gives up one pipeline stage
+// shared-memory plan of the CTA-pair forward kernel per epilogue variant (227 KB per CTA): the side variants trade
+// pipeline stages for a 4-deep side-input staging ring (their epilogue, not the main loop, is the critical path)
 template <int MODE>
 struct TcFwdSmem {
-  static constexpr int kStages = (MODE == 3) ? 4 : 5;   // side + statistics together do not leave room for 5
-  static constexpr int kBytes = kStages * k2StageBytes + 2 * kEpiBufBytes + ((MODE & 2) ? 2 * kEpiBufBytes : 0) + 1024 + 256 +
-                                ((MODE & 1) ? kEpiStatsBytes : 0);
+  static constexpr int kSideBufs = 4;                    // side-input staging ring: fetched 3 chunks ahead
+  static constexpr int kStages = (MODE == 3) ? 3 : ((MODE & 2) ? 4 : 5);
+  static constexpr int kBytes = kStages * k2StageBytes + 2 * kEpiBufBytes + ((MODE & 2) ? kSideBufs * kEpiBufBytes : 0) +
+                                1024 + 256 + ((MODE & 1) ? kEpiStatsBytes : 0);
 };
 
 // MODE bit 0: BatchNorm statistics of the output, bit 1: side input (each epilogue variant carries only its own code)
@@ -689,9 +690,10 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_buf = smem + kSt * k2StageBytes;          // 2 x 16 KB output staging, 1024-aligned
-  uint8_t* side_buf = epi_buf + 2 * kEpiBufBytes;        // MODE & 2: 2 x 16 KB side-input staging (TMA destination)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(side_buf + ((MODE & 2) ? 2 * kEpiBufBytes : 0));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 6);
+  constexpr int kSB = TcFwdSmem<MODE>::kSideBufs;
+  uint8_t* side_buf = epi_buf + 2 * kEpiBufBytes;        // MODE & 2: kSB x 16 KB side-input staging (TMA destination)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(side_buf + ((MODE & 2) ? kSB * kEpiBufBytes : 0));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSt + 4 + kSB);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kSt;
   const uint32_t tfull0 = empty0 + 8 * kSt, tempty0 = tfull0 + 16, sfull0 = tempty0 + 16;
@@ -712,8 +714,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     tma_prefetch_desc(&tmap_y);
     if (MODE & 2) {
       tma_prefetch_desc(&tmap_s);
-      mbar_init(sfull0, 1);
-      mbar_init(sfull0 + 8, 1);
+      for (int i = 0; i < kSB; ++i) mbar_init(sfull0 + 8 * i, 1);
     }
     for (int s = 0; s < kSt; ++s) {
       mbar_init(full0 + 8 * s, 2);   // leader's expect_tx arrival + the peer producer's arrival
@@ -838,8 +839,8 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       for (int i = epi_tid; i < n_tiles * 512; i += 128) stats_sm[i] = 0.f;
       epi_bar_sync();
     }
-    // MODE & 2: the side chunk (128 pixels x 64 channels, the box of the output store) is fetched by TMA one chunk
-    // ahead into a 2-deep staging ring; epi_tid 0 walks the same (tile, chunk) sequence as the consumers below
+    // MODE & 2: the side chunk (128 pixels x 64 channels, the box of the output store) is fetched by TMA kSB-1 chunks
+    // ahead into a kSB-deep staging ring; epi_tid 0 walks the same (tile, chunk) sequence as the consumers below
     int s_pt = pair, s_q = 0;
     uint32_t s_count = 0;
     auto side_issue = [&]() {
@@ -854,7 +855,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         const int tx = mt % p.tiles_x; mt /= p.tiles_x;
         const int ty = mt % p.tiles_y;
         const int img = mt / p.tiles_y;
-        const uint32_t b = s_count & 1;
+        const uint32_t b = s_count % kSB;
         mbar_expect_tx(sfull0 + 8 * b, kEpiBufBytes);
         tma_load_4d(smem_u32(side_buf) + b * kEpiBufBytes, &tmap_s, sfull0 + 8 * b, n0 + s_q * 64, tx * p.bw, ty * p.bh, img);
         ++s_q;
@@ -862,7 +863,8 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         return;
       }
     };
-    if ((MODE & 2) && epi_tid == 0) { side_issue(); side_issue(); }
+    if ((MODE & 2) && epi_tid == 0)
+      for (int i = 0; i < kSB - 1; ++i) side_issue();
     uint32_t tcount = 0, chunk_count = 0;
     for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
       const int nt = pt % n_tiles;
@@ -888,8 +890,8 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         uint4 sd0[4], sd1[4];
         if ((MODE & 2) && tile_ok) {
           // this row's 128 bytes of the staged side chunk (zero where the box left the tensor)
-          const uint32_t sb = chunk_count & 1;
-          mbar_wait(sfull0 + 8 * sb, (chunk_count >> 1) & 1);
+          const uint32_t sb = chunk_count % kSB;
+          mbar_wait(sfull0 + 8 * sb, (chunk_count / kSB) & 1);
           const uint8_t* rowp = side_buf + sb * kEpiBufBytes + row * 128;
           const int sw = row & 7;
 #pragma unroll
