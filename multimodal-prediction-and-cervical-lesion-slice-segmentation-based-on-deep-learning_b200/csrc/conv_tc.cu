@@ -130,6 +130,8 @@ __device__ __forceinline__ void warp_colsum32(float (&v)[32], int lane) {
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+constexpr int kPairThreads = 320;   // CTA-pair forward kernel: producer warp + issuer warp + 8 epilogue warps
 
 // Drain this warp's 32 rows x tile_n columns of one accumulator: TMEM -> (+bias, +side) -> bf16 -> global.
 __device__ __forceinline__ void tc_epilogue_tile(const TcEpi& ep, uint32_t t_addr, int tile_n, int n0, int cout,
@@ -231,10 +233,11 @@ __device__ __forceinline__ void tc_epilogue_tile_plain(const float* __restrict__
 }
 
 // flush the per-CTA statistics staging to the fp64 accumulators (called by the 128 epilogue threads)
+template <int NT = 128>
 __device__ __forceinline__ void tc_epilogue_flush_stats(const TcEpi& ep, const float* stats_sm, int n_tiles, int tile_n,
                                                         int cout, int epi_tid) {
-  epi_bar_sync();
-  for (int i = epi_tid; i < n_tiles * 512; i += 128) {
+  if (NT == 256) epi_bar_sync256(); else epi_bar_sync();
+  for (int i = epi_tid; i < n_tiles * 512; i += NT) {
     const float v = stats_sm[i];
     if (v == 0.f) continue;
     const int nt = i >> 9, which = (i >> 8) & 1, c = i & 255;
@@ -682,7 +685,7 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
 // 1/kPairs of its half and multicasts it to the CTAs that hold the same half in the other pairs.  The operand
 // stream L2 -> SM is what bounds this kernel (32 KB per CTA and k-block without sharing, ~6.3 KB/clk chip-wide).
 template <int MODE, int kPairs>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kPairThreads, 1)
 conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_s,
                         const TcEpi ep, TcFwdParams p, int n_tiles, int m_tiles, int total_pair_tiles) {
@@ -722,7 +725,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull0 + 8 * a, 1);
-      mbar_init(tempty0 + 8 * a, 8);  // 4 epilogue warps x 2 CTAs (leader's copy is the one used)
+      mbar_init(tempty0 + 8 * a, 16);  // 8 epilogue warps x 2 CTAs (leader's copy is the one used)
     }
     fence_barrier_init();
   }
@@ -829,15 +832,19 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       }
     }
   } else {
-    // ---- epilogue: TMEM -> registers -> bf16 -> swizzled smem chunk (128 px x 64 ch) -> TMA store
+    // ---- epilogue: TMEM -> registers -> bf16 -> swizzled smem chunk (128 px x 64 ch) -> TMA store.
+    // EIGHT warps: warp w may touch TMEM lanes 32*(w%4)..+31 only, so warps 2-5 take columns 0-31 of every 64-column
+    // chunk and warps 6-9 columns 32-63 of the same rows - two warps per scheduler instead of one (the epilogue of
+    // short-K launches is issue-bound: ~300 instructions per thread and chunk with one warp per scheduler).
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     const uint32_t lead_tempty0 = map_to_cta(tempty0, lead_rank);
     const int epi_tid = threadIdx.x - 64;
     const int row = lg * 32 + lane;
     float* stats_sm = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
     if (MODE & 1) {
-      for (int i = epi_tid; i < n_tiles * 512; i += 128) stats_sm[i] = 0.f;
-      epi_bar_sync();
+      for (int i = epi_tid; i < n_tiles * 512; i += 256) stats_sm[i] = 0.f;
+      epi_bar_sync256();
     }
     // MODE & 2: the side chunk (128 pixels x 64 channels, the box of the output store) is fetched by TMA kSB-1 chunks
     // ahead into a kSB-deep staging ring; epi_tid 0 walks the same (tile, chunk) sequence as the consumers below
@@ -887,7 +894,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
 #pragma unroll 1
       for (int q = 0; q < nchunks; ++q) {
         const int col0 = n0 + q * 64;
-        uint4 sd0[4], sd1[4];
+        uint4 sd0[4];
         if ((MODE & 2) && tile_ok) {
           // this row's 128 bytes of the staged side chunk (zero where the box left the tensor)
           const uint32_t sb = chunk_count % kSB;
@@ -895,14 +902,10 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           const uint8_t* rowp = side_buf + sb * kEpiBufBytes + row * 128;
           const int sw = row & 7;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            sd0[g] = *reinterpret_cast<const uint4*>(rowp + ((g ^ sw) << 4));
-            sd1[g] = *reinterpret_cast<const uint4*>(rowp + (((g + 4) ^ sw) << 4));
-          }
+          for (int g = 0; g < 4; ++g) sd0[g] = *reinterpret_cast<const uint4*>(rowp + (((half * 4 + g) ^ sw) << 4));
         }
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_addr + (uint32_t)(q * 64), r0);
-        tmem_ld32(t_addr + (uint32_t)(q * 64 + 32), r1);
+        uint32_t r0[32];
+        tmem_ld32(t_addr + (uint32_t)(q * 64 + half * 32), r0);
         tmem_ld_wait();
         if (q == nchunks - 1) {  // the accumulator is in registers: hand it back to the MMA issuer
           tc_fence_before();
@@ -910,37 +913,34 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
           if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8 * acc);
         }
         if (!tile_ok) continue;  // CTA-uniform: the odd tile of the last pair
-        uint32_t pk0[16], pk1[16];
-        epi_convert32<MODE>(ep, r0, col0, p.cout, row_ok, sd0, pk0);
-        epi_convert32<MODE>(ep, r1, col0 + 32, p.cout, row_ok, sd1, pk1);
+        uint32_t pk0[16];
+        epi_convert32<MODE>(ep, r0, col0 + half * 32, p.cout, row_ok, sd0, pk0);
         const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
         if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
-        epi_bar_sync();
+        epi_bar_sync256();
         if ((MODE & 2) && epi_tid == 0) side_issue();   // every thread has read its side row: refill that buffer
         {
           uint8_t* rowp = epi_buf + buf + row * 128;
           const int sw = row & 7;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk0[4 * j], pk0[4 * j + 1], pk0[4 * j + 2], pk0[4 * j + 3]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(rowp + (((j + 4) ^ sw) << 4)) = make_uint4(pk1[4 * j], pk1[4 * j + 1], pk1[4 * j + 2], pk1[4 * j + 3]);
+            *reinterpret_cast<uint4*>(rowp + (((half * 4 + j) ^ sw) << 4)) =
+                make_uint4(pk0[4 * j], pk0[4 * j + 1], pk0[4 * j + 2], pk0[4 * j + 3]);
         }
         fence_proxy_async();
-        epi_bar_sync();
+        epi_bar_sync256();
         if (epi_tid == 0) {
           tma_store_4d(&tmap_y, smem_u32(epi_buf + buf), col0, tx * p.bw, ty * p.bh, img);
           bulk_commit();
         }
         if (MODE & 1) {
-          // column sums of the staged (bf16-rounded) chunk: warp lg sums 32 rows, lane = one pair of channels;
-          // a warp reads one whole 128-byte row per step, so the swizzled layout is conflict-free here too
+          // column sums of the staged (bf16-rounded) chunk: each of the 8 warps sums 16 rows, lane = one pair of
+          // channels; a warp reads one whole 128-byte row per step, so the swizzled layout is conflict-free here too
           const uint8_t* bufp = epi_buf + buf;
           float2 sm = make_float2(0.f, 0.f), sq = make_float2(0.f, 0.f);
 #pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            const int r = lg * 32 + rr;
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = lg * 32 + half * 16 + rr;
             const uint32_t u = *reinterpret_cast<const uint32_t*>(bufp + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
             const float2 v = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
             sm = __fadd2_rn(sm, v);
@@ -957,7 +957,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       }
     }
     if (epi_tid == 0) bulk_wait_read<0>();
-    if (MODE & 1) tc_epilogue_flush_stats(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
+    if (MODE & 1) tc_epilogue_flush_stats<256>(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1543,7 +1543,7 @@ static int launch_fwd_pairs_t(const CUtensorMap& mx, const CUtensorMap& mw, cons
   attr[0].val.clusterDim.x = 2 * kPairs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(kPairThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cfg.attrs = attr;
