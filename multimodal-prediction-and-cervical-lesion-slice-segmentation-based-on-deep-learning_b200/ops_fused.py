@@ -53,11 +53,11 @@ class _Sep:
 # 728-channel middle-flow shape: GEMM 49 -> 58 us with the statistics vs 49 + 18 us for GEMM + reduction pass
 # (647 vs 644 img/s for the whole step).
 _STATS_IN_EPILOGUE = os.environ.get("CERVIX_STATS_EPILOGUE", "1") != "0"
-# CERVIX_BN1_IN_DGRAD=1 moves bn1's backward from the depthwise backward kernel (one more tensor read and an in-place
-# pre-pass there) into the data-gradient GEMM's epilogue, whose side tile is staged by TMA.  Measured on B200 for the
-# 728-channel middle-flow shape: the GEMM grows from 46 to 76 us (its epilogue becomes the critical path) while the
-# depthwise kernel saves ~25 us - 637 vs 638 img/s for the whole step, a wash - so it stays off by default.
-_BN1_IN_DGRAD = os.environ.get("CERVIX_BN1_IN_DGRAD", "0") == "1"
+# bn1's backward is applied by the data-gradient GEMM's epilogue (side tile staged by TMA, eight epilogue warps) instead
+# of by the depthwise backward kernel (one more tensor read and an in-place pre-pass there); CERVIX_BN1_IN_DGRAD=0
+# restores the latter.  Measured on B200 for the 728-channel middle-flow shape: the GEMM grows from 38 to 58 us, the
+# depthwise kernel saves ~25 us; 678 vs 670 img/s for the whole step.
+_BN1_IN_DGRAD = os.environ.get("CERVIX_BN1_IN_DGRAD", "1") != "0"
 
 
 def _sep_forward(B, x, in_scale, in_shift, relu_in, dw_w, g1, b1, pw_w, g2, b2, bn1: BnBuffers, bn2: BnBuffers,
