@@ -27,6 +27,18 @@ TRAIN_GFLOP_PER_IMAGE = 496.4   # fwd+dgrad+wgrad conv FLOPs, Xception ds=16 (BA
 CLS_WEIGHTS = [1, 1, 5, 3, 4]   # train.py:274
 
 
+def synthetic_batch(batch: int, size: int = 512, num_classes: int = 5, seed: int = 0, ignore_frac: float = 0.01):
+    """Synthetic inputs per SURVEY.md section 8d (dataloader contract, row L): images U[0,1) fp32 NCHW, masks int64 in
+    [0, num_classes) with ``ignore_frac`` of the pixels set to num_classes (ignore_index), one-hot labels [B,H,W,C+1]."""
+    import torch
+    g = torch.Generator().manual_seed(1000 + seed)
+    imgs = torch.rand(batch, 3, size, size, generator=g)
+    pngs = torch.randint(0, num_classes, (batch, size, size), generator=g)
+    ign = torch.rand(batch, size, size, generator=g) < ignore_frac
+    pngs = torch.where(ign, torch.full_like(pngs, num_classes), pngs)
+    return imgs, pngs, torch.eye(num_classes + 1)[pngs]
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -267,7 +279,6 @@ def run_ours(args):
     from cervix_b200.backend import get_backend
     from cervix_b200.engine import SegTrainer
     from cervix_b200.nets.deeplabv3_plus import DeepLab
-    from oracle import deeplab_ref as O  # synthetic-input generator only (test infrastructure)
 
     B = get_backend()
     peaks = load_peaks()
@@ -284,7 +295,7 @@ def run_ours(args):
             dist.broadcast(p.data, 0)
     trainer = SegTrainer(model, lr=1e-4, betas=(0.9, 0.999), cls_weights=CLS_WEIGHTS, num_classes=5, world_size=world)
 
-    imgs_h, pngs_h, labels_h = O.synthetic_batch(bsz, size, seed=rank)
+    imgs_h, pngs_h, labels_h = synthetic_batch(bsz, size, seed=rank)   # the product arm never touches oracle/
     imgs_h, pngs_h, labels_h = imgs_h.pin_memory(), pngs_h.pin_memory(), labels_h.pin_memory()
     imgs, pngs, labels = imgs_h.cuda(), pngs_h.cuda(), labels_h.cuda()
 

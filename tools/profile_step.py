@@ -12,7 +12,7 @@ from torch.profiler import ProfilerActivity, profile
 
 from cervix_b200.engine import SegTrainer
 from cervix_b200.nets.deeplabv3_plus import DeepLab
-from oracle import deeplab_ref as O
+from bench import synthetic_batch
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
@@ -23,7 +23,7 @@ args = ap.parse_args()
 torch.manual_seed(0)
 model = DeepLab(5, args.backbone, False, 16).set_compute_dtype(torch.bfloat16).cuda().train()
 trainer = SegTrainer(model, cls_weights=[1, 1, 5, 3, 4])
-imgs, pngs, labels = [t.cuda() for t in O.synthetic_batch(args.batch, 512, seed=0)]
+imgs, pngs, labels = [t.cuda() for t in synthetic_batch(args.batch, 512, seed=0)]
 for _ in range(2):
     trainer.step(imgs, pngs, labels)
 torch.cuda.synchronize()
