@@ -157,71 +157,92 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- four-modal classifier leg
-def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int = 512):
-    """BASELINE configs[1]: one training step of the four-modal severity classifier on `patients` patients -
-    three colposcopic images per patient (resize 1024 -> 16 patches of 256 -> frozen ResNet-101 encoder, as
-    Graph_Structure(data_augmentation).py:136-200 does) + the clinical node features, then the fusion head's
-    forward, objective (my_train(full).py:309-347), backward and Adam on the flat parameters.  Inputs are resident in
-    HBM; returns patients/s and 512x512 images/s with the time split encoder / head."""
+def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int = 512, world: int = 1, rank: int = 0,
+                          variants=(("imgN", "imgA", "imgL", "cli"),)):
+    """BASELINE configs[1] (N=1, 16 patients) / configs[4] (N>1, `patients` per GPU, fusion-head gradients all-reduced
+    over NCCL): one training step of the severity classifier on `patients` patients per rank - the colposcopic
+    images of each patient (resize 1024 -> 16 patches of 256 -> frozen ResNet-101 encoder, as
+    Graph_Structure(data_augmentation).py:136-200 does; resize + split + normalise is one kernel) + the clinical
+    node features, then the fusion head's forward, objective (my_train(full).py:309-347), backward, gradient
+    all-reduce and Adam on the flat parameters (engine.FusionTrainer).  Inputs are resident in HBM.  `variants` lists
+    the modality sets to time (the reference's 2-/3-/4-modal scripts); the first is the headline.  Times are the max
+    over ranks; returns patients/s over all ranks with the split encoder / head."""
     import numpy as np
     import torch
-    from cervix_b200.backend import get_backend
-    from cervix_b200.engine import FlatParams
-    from cervix_b200.multimodal.my_mae_model import (fusion_model_mae_2, fusion_objective, get_edge_index_full,
-                                                     get_edge_index_image)
-    from cervix_b200.multimodal.patch_encoder import ResNet101Encoder, split_patches
-    B = get_backend()
+    import torch.distributed as dist
+    from cervix_b200.engine import FusionTrainer
+    from cervix_b200.multimodal.cli_features import AgeNodeFeatures
+    from cervix_b200.multimodal.my_mae_model import fusion_model_mae_2, get_edge_index_full, get_edge_index_image
+    from cervix_b200.multimodal.patch_encoder import ResNet101Encoder
     torch.manual_seed(0)
     enc = ResNet101Encoder().cuda().eval()
     for m in enc.modules():   # ImageNet weights are not available offline: random init + non-trivial running statistics
         if isinstance(m, torch.nn.BatchNorm2d):
             m.running_mean.normal_(0, 0.1)
             m.running_var.uniform_(0.5, 1.5)
-    types = ["imgN", "imgA", "imgL", "cli"]
-    head = fusion_model_mae_2(1024, 512, 512, 0.3, 4).cuda().train()
-    flat = FlatParams(head)
-    m1, v1 = torch.zeros_like(flat.data), torch.zeros_like(flat.data)
-    imgs = torch.rand(patients, 3, 3, size, size, device="cuda")
-    from cervix_b200.multimodal.cli_features import AgeNodeFeatures
-    ages = torch.randint(20, 81, (patients,))                       # random age scalars (BASELINE north_star inputs)
-    cli = AgeNodeFeatures(max_age=100).cuda()(ages, 20, 80)         # [patients, 4, 1024] clinical node rows
+    torch.manual_seed(100 + rank)
+    imgs = torch.rand(3, patients, 3, size, size, device="cuda")       # [modality][patient] images of this rank's shard
+    ages = torch.randint(20, 81, (patients,))                          # random age scalars (BASELINE north_star inputs)
+    cli = AgeNodeFeatures(max_age=100).cuda()(ages, 20, 80)            # [patients, 4, 1024] clinical node rows
     labels = torch.randint(0, 4, (patients,), device="cuda")
-    edges = {"imgN": get_edge_index_image(), "imgA": get_edge_index_image(), "imgL": get_edge_index_image(),
-             "cli": get_edge_index_full(4)}
-    rng = np.random.RandomState(0)
-    masks = np.ones((patients, 4), dtype=bool)
-    masks[np.arange(patients), rng.randint(0, 4, patients)] = False   # exactly one visible modality per patient
-    t = [0]
+    all_edges = {"imgN": get_edge_index_image(), "imgA": get_edge_index_image(), "imgL": get_edge_index_image(),
+                 "cli": get_edge_index_full(4)}
+    img_index = {"imgN": 0, "imgA": 1, "imgL": 2}
+    chunk = 16                                                         # patients per encoder pass (256 patches)
+    results = []
+    for types in variants:
+        types = list(types)
+        torch.manual_seed(0)                                           # identical initial head on every rank
+        head = fusion_model_mae_2(1024, 512, 512, 0.3, len(types)).cuda().train()
+        trainer = FusionTrainer(head, types, lr=1e-4, weight_decay=5e-4 if len(types) == 4 else 1e-3, world_size=world)
+        edges = {m: all_edges[m] for m in types}
+        rng = np.random.RandomState(rank)
+        masks = np.ones((patients, len(types)), dtype=bool)
+        masks[np.arange(patients), rng.randint(0, len(types), patients)] = False   # one visible modality per patient
+        n_img = sum(1 for m in types if m in img_index)
 
-    def encode():
-        with torch.no_grad():
-            return {mname: enc(split_patches(imgs[:, i])).view(patients, 16, 1024) for i, mname in enumerate(types[:3])}
+        def encode():
+            feats = {}
+            with torch.no_grad():
+                for m in types:
+                    if m in img_index:
+                        f = [enc.encode_images(imgs[img_index[m], i:i + chunk]) for i in range(0, patients, chunk)]
+                        feats[m] = torch.cat(f).view(patients, 16, 1024)
+            if "cli" in types:
+                feats["cli"] = cli
+            return feats
 
-    def head_step(feats):
-        feats = dict(feats, cli=cli)
-        flat.grad.zero_()
-        out = head.forward_batch(feats, edges, types, types, masks, True)
-        loss = fusion_objective(out, labels, masks)
-        loss.backward()
-        t[0] += 1
-        B.adam_step(flat.data, flat.grad, m1, v1, 1e-4, 0.9, 0.999, 1e-8, 5e-4, t[0])
-        return loss
-
-    for _ in range(warmup):
-        head_step(encode())
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    enc_ms = head_ms = 0.0
-    for _ in range(steps):
-        ev[0].record(); f = encode(); ev[1].record(); loss = head_step(f); ev[2].record()
+        for _ in range(warmup):
+            trainer.step(encode(), edges, labels, masks)
         torch.cuda.synchronize()
-        enc_ms += ev[0].elapsed_time(ev[1]); head_ms += ev[1].elapsed_time(ev[2])
-    ms = (enc_ms + head_ms) / steps
-    return {"workload": "four-modal severity classifier train step, %d patients x 3 images %dx%d (ResNet-101 patch "
-                        "encoder bf16, frozen) + clinical nodes -> fusion head fwd/bwd + Adam (BASELINE configs[1])" % (patients, size, size),
-            "patients_per_s": patients / (ms * 1e-3), "images_per_s": 3 * patients / (ms * 1e-3), "ms_per_step": ms,
-            "encoder_ms": enc_ms / steps, "head_ms": head_ms / steps,
-            "encoder_tflops": 3 * patients * 16 * 20.38e9 / (enc_ms / steps * 1e-3) / 1e12, "loss_last_step": float(loss)}
+        if world > 1:
+            dist.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        enc_ms = head_ms = 0.0
+        for _ in range(steps):
+            ev[0].record(); f = encode(); ev[1].record(); loss = trainer.step(f, edges, labels, masks); ev[2].record()
+            torch.cuda.synchronize()
+            enc_ms += ev[0].elapsed_time(ev[1]); head_ms += ev[1].elapsed_time(ev[2])
+        t = torch.tensor([enc_ms / steps, head_ms / steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        enc_ms, head_ms = float(t[0]), float(t[1])
+        ms = enc_ms + head_ms
+        results.append({"modalities": types, "patients_per_s": world * patients / (ms * 1e-3),
+                        "images_per_s": world * n_img * patients / (ms * 1e-3), "ms_per_step": ms, "encoder_ms": enc_ms,
+                        "head_ms": head_ms,
+                        "encoder_tflops_per_gpu": (n_img * patients * 16 * 20.38e9 / (enc_ms * 1e-3) / 1e12) if n_img else None,
+                        "loss_last_step": float(loss)})
+        del trainer, head
+    out = dict(results[0])
+    out["workload"] = ("%d-modal severity classifier train step, %d patients per GPU x %d images %dx%d (ResNet-101 patch "
+                       "encoder bf16, frozen) + clinical nodes -> fusion head fwd/bwd + %sAdam (BASELINE configs[%d])"
+                       % (len(results[0]["modalities"]), patients, 3, size, size, "NCCL all-reduce + " if world > 1 else "",
+                          1 if world == 1 else 4))
+    out["global_patients"] = world * patients
+    if len(results) > 1:
+        out["variants"] = results[1:]
+    return out
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -367,6 +388,13 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
+    classifier = None
+    if not args.no_classifier:      # every rank takes part (patients are sharded, head gradients all-reduced)
+        del step_fn, trainer, model, pf
+        torch.cuda.empty_cache()
+        classifier = classifier_throughput(max(2, min(args.steps, 4)), 2, patients=16 if world == 1 else 64,
+                                           world=world, rank=rank,
+                                           variants=(("imgN", "imgA", "imgL", "cli"), ("imgN", "imgA", "imgL"), ("imgN", "imgL")))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -384,11 +412,6 @@ def run_ours(args):
         cpu_baseline = {"value": cpu_ips, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d timed steps of the oracle port's train step, batch 2 at 512x512 (%.1f s/step)" % (cpu_steps, cpu_sec)}
     h2d = imgs_h.numel() * 4 + pngs_h.numel() * 8
-    classifier = None
-    if world == 1 and not args.no_classifier:
-        del trainer, model
-        torch.cuda.empty_cache()
-        classifier = classifier_throughput(max(2, min(args.steps, 4)), 2)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -424,7 +447,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-classifier", action="store_true", help="skip the four-modal classifier leg (N=1 only)")
+    ap.add_argument("--no-classifier", action="store_true", help="skip the severity-classifier leg")
     ap.add_argument("--no-graph", action="store_true", help="run the single-GPU step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

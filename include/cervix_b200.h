@@ -303,6 +303,23 @@ CVX_API int cvx_seg_postprocess(const float* logits, int c, int h, int w, int cr
 CVX_API int cvx_confusion_matrix(const unsigned char* pred, const unsigned char* gt, int64_t n, int classes, int64_t* hist,
                                  void* stream);
 
+/* ---- input side -----------------------------------------------------------
+ * Classifier patch pipeline (reference: MM/Graph_Structure(data_augmentation).py:145-161 - PIL resize to
+ * new_size x new_size, (new_size/patch)^2 crops enumerated x-major, ToTensor + Normalize): images fp32 NCHW
+ * [n,3,h,w] in [0,1] -> patches NHWC [n*k*k, patch, patch, 3] (k = new_size/patch, patch index = ix*k + iy) in
+ * `dtype`, value = (bilinear(half-pixel centres, no antialias) - mean[c]) / std[c].  mean / std are HOST arrays of c
+ * floats. */
+CVX_API int cvx_split_patches(const float* images, void* patches, int n, int c, int h, int w, int new_size, int patch,
+                              const float* mean, const float* std, int dtype, void* stream);
+/* Tail of the segmentation loader on the device (reference: SEG/utils/dataloader.py:40-42 + utils/utils.py:63-65
+ * preprocess_input): images_u8 (n_image_elems bytes, [n][h][w][3] as PIL / numpy hold them, 16-byte aligned) -> NHWC
+ * activation in `dtype` scaled by 1/255; labels_u8 (n_pixels bytes, nullable together with labels_out) -> int64 with
+ * values >= num_classes set to num_classes (the ignore label).  The one-hot expansion of :47 is implicit in
+ * cvx_seg_loss_* (onehot == NULL). */
+CVX_API int cvx_finish_batch_u8(const unsigned char* images_u8, void* images_out, int64_t n_image_elems,
+                                const unsigned char* labels_u8, int64_t* labels_out, int64_t n_pixels, int num_classes,
+                                int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,35 @@ class CudaBackend:
         check(self.lib.cvx_nchw_to_nhwc(_p(x), _p(y), n, c, h, w, _dt(y), self._stream()), "cvx_nchw_to_nhwc")
         return y
 
+    def split_patches(self, images: torch.Tensor, new_size: int, patch: int, mean, std, dtype: torch.dtype) -> torch.Tensor:
+        """[n,3,h,w] fp32 in [0,1] -> [n*k*k, patch, patch, 3] NHWC `dtype`: bilinear resize to new_size^2, x-major
+        patch split and (v - mean) / std in one launch (cvx_split_patches)."""
+        self._chk(images)
+        if images.dtype != torch.float32:
+            raise TypeError("split_patches: fp32 NCHW images expected, got %s" % images.dtype)
+        n, c, h, w = images.shape
+        k = new_size // patch
+        y = torch.empty((n * k * k, patch, patch, c), dtype=dtype, device=images.device)
+        m = (C.c_float * c)(*[float(v) for v in mean])
+        s = (C.c_float * c)(*[float(v) for v in std])
+        check(self.lib.cvx_split_patches(_p(images), _p(y), n, c, h, w, new_size, patch, m, s, _dt(y), self._stream()),
+              "cvx_split_patches")
+        return y
+
+    def finish_batch_u8(self, images_u8: torch.Tensor, labels_u8: Optional[torch.Tensor], num_classes: int,
+                        dtype: torch.dtype):
+        """uint8 [n,h,w,3] pixels (+ uint8 [n,h,w] class map) -> (NHWC activation / 255 in `dtype`, int64 class map
+        with values >= num_classes clamped to num_classes) - the loader tail of dataloader.py:40-42 on the device."""
+        self._chk(images_u8, labels_u8)
+        if images_u8.dtype != torch.uint8 or (labels_u8 is not None and labels_u8.dtype != torch.uint8):
+            raise TypeError("finish_batch_u8: uint8 tensors expected")
+        x = torch.empty(images_u8.shape, dtype=dtype, device=images_u8.device)
+        t = None if labels_u8 is None else torch.empty(labels_u8.shape, dtype=torch.int64, device=labels_u8.device)
+        check(self.lib.cvx_finish_batch_u8(_p(images_u8), _p(x), images_u8.numel(), _p(labels_u8), _p(t),
+                                           0 if labels_u8 is None else labels_u8.numel(), num_classes, _dt(x),
+                                           self._stream()), "cvx_finish_batch_u8")
+        return x, t
+
     def to_nchw(self, x: torch.Tensor) -> torch.Tensor:
         self._chk(x)
         n, h, w, c = x.shape

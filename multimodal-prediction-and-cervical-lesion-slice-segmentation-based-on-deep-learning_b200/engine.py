@@ -271,6 +271,42 @@ class SegTrainer:
         return self.s_out
 
 
+class FusionTrainer:
+    """One data-parallel training step of the multimodal fusion head over a batch of patients: forward of all
+    patients at once (``fusion_model_mae_2.forward_batch``), the reference's objective (my_train(full).py:309-347:
+    CE_all + 0.3 CE_img* + 0.2 CE_cli + the masked-auto-encoder MSE), backward, gradient sum-all-reduce across ranks
+    (patients are sharded) and ``torch.optim.Adam(lr=1e-4, weight_decay=5e-4)`` math
+    (my_train(full).py:233-236) as one fused launch on the flat parameters.  The reference steps once per 8
+    patients; a rank's shard plays that role here and the all-reduced gradient is divided by the world size."""
+
+    def __init__(self, head: torch.nn.Module, train_types, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 5e-4, world_size: int = 1):
+        self.head = head
+        self.train_types = list(train_types)
+        self.flat = FlatParams(head)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(self.flat.data)
+        self.v = torch.zeros_like(self.flat.data)
+        self.t = 0
+        self.world = world_size
+
+    def step(self, feats, edges, labels: torch.Tensor, masks, use_types=None, mix: bool = True) -> torch.Tensor:
+        """feats[m]: ``[G, nodes_m, 1024]`` node features of this rank's G patients; masks: bool ``[G, T]`` (True =
+        masked modality).  Returns this rank's loss (device scalar, no host sync)."""
+        from .multimodal.my_mae_model import fusion_objective
+        self.flat.attach_grad_views()
+        self.flat.grad.zero_()
+        out = self.head.forward_batch(feats, edges, self.train_types, use_types or self.train_types, masks, mix)
+        loss = fusion_objective(out, labels, masks)
+        loss.backward()
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
+        self.t += 1
+        get_backend().adam_step(self.flat.data, self.flat.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1],
+                                self.eps, self.wd, self.t, 1.0 / self.world)
+        return loss.detach()
+
+
 class BatchPrefetcher:
     """Moves pinned host batches to the device one step ahead on a side stream, so the
     host->device copy of step i+1 overlaps the compute of step i (replaces the synchronous

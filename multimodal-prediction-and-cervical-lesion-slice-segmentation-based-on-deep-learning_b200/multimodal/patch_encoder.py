@@ -143,8 +143,16 @@ class ResNet101Encoder(nn.Module):
                 and getattr(B, "is_sm100", lambda: False)() and hasattr(B, "conv_fwd_act"))
 
     def forward(self, x):
+        return self.forward_nhwc(ops.to_nhwc(x, self._cervix_dtype))
+
+    def encode_images(self, images, new_size: int = 1024, patch_size: int = 256):
+        """[B,3,H,W] fp32 images in [0,1] -> [B*16, out] features: resize + x-major patch split + ImageNet
+        normalisation as one kernel straight into the stem's NHWC layout (``split_patches_nhwc``), then the encoder."""
+        return self.forward_nhwc(split_patches_nhwc(images, new_size, patch_size, self._cervix_dtype))
+
+    def forward_nhwc(self, x):
+        """Encoder body on an NHWC tensor already in the compute dtype."""
         fold = self._fold_ok(x)
-        x = ops.to_nhwc(x, self._cervix_dtype)
         c1 = self.conv1
         x = ops.conv2d_narrow_in(x, c1.weight, c1.stride[0], c1.padding[0])
         x = ops.batchnorm_act(x, self.bn1, ops.ACT_RELU)
@@ -171,18 +179,18 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
+def split_patches_nhwc(images: torch.Tensor, new_size: int = 1024, patch_size: int = 256,
+                       dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """Tensor form of ``resize_and_split_image`` (:151-161) + ToTensor/Normalize (:145-148) as ONE kernel
+    (``cvx_split_patches``): [B,3,H,W] fp32 in [0,1] -> [B*16, 256, 256, 3] NHWC in the encoder's compute dtype,
+    patches enumerated x-major (outer loop over columns) as the reference's list comprehension does."""
+    return get_backend().split_patches(images.contiguous(), new_size, patch_size, IMAGENET_MEAN, IMAGENET_STD, dtype)
+
+
 def split_patches(images: torch.Tensor, new_size: int = 1024, patch_size: int = 256) -> torch.Tensor:
-    """Tensor form of ``resize_and_split_image`` (:151-161) + the ImageNet normalisation (:145-148):
-    [B,3,H,W] in [0,1] -> [B*16, 3, 256, 256], patches enumerated x-major (outer loop over columns)."""
-    x = torch.nn.functional.interpolate(images, size=(new_size, new_size), mode="bilinear", align_corners=False)
-    mean = torch.tensor(IMAGENET_MEAN, device=x.device).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD, device=x.device).view(1, 3, 1, 1)
-    x = (x - mean) / std
-    k = new_size // patch_size
-    b = x.shape[0]
-    x = x.reshape(b, 3, k, patch_size, k, patch_size)          # [b, c, iy, py, ix, px]
-    x = x.permute(0, 4, 2, 1, 3, 5)                             # [b, ix, iy, c, py, px]  (x-major patch order)
-    return x.reshape(b * k * k, 3, patch_size, patch_size).contiguous()
+    """NCHW fp32 view of ``split_patches_nhwc`` ([B*16, 3, 256, 256]) for callers that want the layout the
+    reference's ``transform(patch)`` produces; the encoder itself is fed by ``ResNet101Encoder.encode_images``."""
+    return split_patches_nhwc(images, new_size, patch_size, torch.float32).permute(0, 3, 1, 2).contiguous()
 
 
 def resize_and_split_image(image, target_size: int = 1024, split_size: int = 256):

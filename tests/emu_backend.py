@@ -31,6 +31,19 @@ class EmuBackend:
     def to_nhwc(self, x, dtype):
         return _nhwc(x.float(), dtype)
 
+    def split_patches(self, images, new_size, patch, mean, std, dtype):
+        x = F.interpolate(images.float(), size=(new_size, new_size), mode="bilinear", align_corners=False)
+        c = x.shape[1]
+        x = (x - torch.tensor(list(mean)).view(1, c, 1, 1)) / torch.tensor(list(std)).view(1, c, 1, 1)
+        k, b = new_size // patch, x.shape[0]
+        x = x.reshape(b, c, k, patch, k, patch).permute(0, 4, 2, 3, 5, 1)      # [b, ix, iy, py, px, c]
+        return x.reshape(b * k * k, patch, patch, c).contiguous().to(dtype)
+
+    def finish_batch_u8(self, images_u8, labels_u8, num_classes, dtype):
+        x = (images_u8.float() * (1.0 / 255.0)).to(dtype)
+        t = None if labels_u8 is None else labels_u8.long().clamp(max=num_classes)
+        return x, t
+
     def to_nchw(self, x):
         return _nchw(x).contiguous()
 

@@ -93,3 +93,63 @@ def test_two_rank_gloo_allreduce_matches_manual_average(tmp_path):
     finally:
         backend.set_backend(prev)
     assert float((r0["grad"] - total).abs().max()) <= 1e-5 * float(total.abs().max())
+
+
+# ---- fusion head (classifier) data parallelism: patients sharded across ranks ----------------
+def _fusion_setup(rank, types):
+    import numpy as np
+    from cervix_b200.multimodal.my_mae_model import fusion_model_mae_2
+    from oracle import fusion_ref as FR
+    from tests.fusion_cases import batch_of
+    torch.manual_seed(0)
+    head = fusion_model_mae_2(1024, 512, 512, 0.3, len(types))
+    head.load_state_dict(FR.randomize_state(head.state_dict(), seed=3), strict=True)
+    head.eval()                                       # dropout off: the two runs must see the same function
+    patients = [FR.synthetic_patient(2 * rank + i) for i in range(2)]
+    feats, edges = batch_of(patients, types, "cpu")
+    masks = np.ones((2, len(types)), dtype=bool)
+    masks[0, rank % len(types)] = False
+    masks[1, (rank + 1) % len(types)] = False
+    labels = torch.tensor([rank % 4, (rank + 2) % 4])
+    return head, feats, edges, labels, masks
+
+
+def _fusion_worker(rank, world, port, out_dir):
+    from cervix_b200.engine import FusionTrainer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    backend.set_backend(EmuBackend())
+    torch.set_num_threads(2)
+    types = ["imgN", "imgA", "imgL", "cli"]
+    head, feats, edges, labels, masks = _fusion_setup(rank, types)
+    tr = FusionTrainer(head, types, lr=1e-3, world_size=world)
+    loss = tr.step(feats, edges, labels, masks)
+    torch.save({"grad": tr.flat.grad.clone(), "data": tr.flat.data.clone(), "loss": float(loss)},
+               os.path.join(out_dir, "f%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_fusion_two_rank_gloo_allreduce_matches_manual_sum(tmp_path):
+    from cervix_b200.engine import FusionTrainer
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_fusion_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "f0.pt"), torch.load(tmp_path / "f1.pt")
+    assert torch.equal(r0["grad"], r1["grad"]) and torch.equal(r0["data"], r1["data"])
+    assert r0["loss"] != r1["loss"]                       # each rank worked on its own patients
+    prev = backend.set_backend(EmuBackend())
+    try:
+        types = ["imgN", "imgA", "imgL", "cli"]
+        total, start = None, None
+        for rank in range(2):
+            head, feats, edges, labels, masks = _fusion_setup(rank, types)
+            tr = FusionTrainer(head, types, lr=0.0, weight_decay=0.0)
+            start = tr.flat.data.clone()
+            tr.step(feats, edges, labels, masks)
+            total = tr.flat.grad.clone() if total is None else total + tr.flat.grad
+        # the optimizer saw the mean of the two shards' gradients: redo Adam's first step by hand
+        g = total / 2 + 5e-4 * start
+        want = start - 1e-3 * g / (g.abs() + 1e-8)
+    finally:
+        backend.set_backend(prev)
+    assert float((r0["grad"] - total).abs().max()) <= 1e-5 * float(total.abs().max())
+    assert float((r0["data"] - want).abs().max()) <= 2e-6

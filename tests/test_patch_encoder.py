@@ -66,8 +66,12 @@ def test_folded_bottleneck_matches_unfolded_on_emulation():
 
 
 def test_split_patches_order_and_normalisation():
-    img = torch.rand(1, 3, 1024, 1024)
-    p = split_patches(img)
+    prev = backend.set_backend(EmuBackend())
+    try:
+        img = torch.rand(1, 3, 1024, 1024)
+        p = split_patches(img)
+    finally:
+        backend.set_backend(prev)
     assert p.shape == (16, 3, 256, 256)
     mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1); std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
     # reference loop order: for i in x-blocks: for j in y-blocks -> patch index = i*4 + j
@@ -76,11 +80,67 @@ def test_split_patches_order_and_normalisation():
         assert torch.allclose(p[i * 4 + j], want, atol=1e-5)
 
 
+def _split_spec(img, new_size, patch):
+    """What cvx_split_patches must produce, from stock torch ops on the CPU (NHWC fp32)."""
+    return EmuBackend().split_patches(img.cpu(), new_size, patch, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225),
+                                      torch.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,new_size,patch", [((2, 3, 512, 512), 1024, 256), ((1, 3, 300, 280), 1024, 256),
+                                                  ((1, 3, 1024, 1024), 1024, 256), ((1, 3, 1500, 1210), 1024, 256),
+                                                  ((3, 3, 96, 80), 256, 64), ((1, 3, 37, 53), 64, 16)])
+def test_gpu_split_patches_kernel(shape, new_size, patch):
+    """The one-launch resize + x-major split + normalise kernel against F.interpolate + slicing, fp32 and bf16."""
+    from cervix_b200.multimodal.patch_encoder import split_patches_nhwc
+    torch.manual_seed(sum(shape))
+    img = torch.rand(*shape)
+    want = _split_spec(img, new_size, patch)
+    got = split_patches_nhwc(img.cuda(), new_size, patch, torch.float32).cpu()
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) < 2e-5
+    got16 = split_patches_nhwc(img.cuda(), new_size, patch, torch.bfloat16)
+    assert got16.dtype == torch.bfloat16
+    assert float((got16.float().cpu() - want).abs().max()) < 2e-2          # bf16 storage of values in [-2.2, 2.7]
+    nchw = split_patches(img.cuda(), new_size, patch).cpu()
+    assert torch.equal(nchw, got.permute(0, 3, 1, 2))
+
+
+@pytest.mark.gpu
+def test_gpu_encode_images_equals_split_then_forward():
+    _, enc = _pair(4)
+    enc.set_compute_dtype(torch.bfloat16).cuda()
+    img = torch.rand(2, 3, 128, 160).cuda()
+    with torch.no_grad():
+        a = enc.encode_images(img, 256, 64)
+        b = enc(split_patches(img, 256, 64))
+    assert a.shape == (32, 1024)
+    assert float((a - b).abs().max()) < 2e-2 * float(b.abs().max())
+
+
+@pytest.mark.gpu
+def test_gpu_finish_batch_u8():
+    """uint8 loader tail (dataloader.py:40-42 + preprocess_input) against numpy."""
+    import numpy as np
+    B = backend.get_backend()
+    rng = np.random.RandomState(0)
+    for n, h, w in ((2, 64, 48), (1, 7, 5), (3, 33, 31)):
+        img = rng.randint(0, 256, (n, h, w, 3), dtype=np.uint8)
+        lab = rng.randint(0, 9, (n, h, w), dtype=np.uint8)
+        lab[0, 0, 0] = 255
+        x, t = B.finish_batch_u8(torch.from_numpy(img).cuda(), torch.from_numpy(lab).cuda(), 5, torch.float32)
+        want_t = lab.astype(np.int64); want_t[want_t >= 5] = 5
+        assert np.array_equal(t.cpu().numpy(), want_t)
+        assert float((x.cpu() - torch.from_numpy(img.astype(np.float32) / 255.0)).abs().max()) < 1e-7
+        xb, _ = B.finish_batch_u8(torch.from_numpy(img).cuda(), None, 5, torch.bfloat16)
+        assert torch.equal(xb.cpu(), torch.from_numpy(img.astype(np.float32) / 255.0).bfloat16())
+
+
 @pytest.mark.gpu
 def test_gpu_fp32_matches_torchvision():
     ref, enc = _pair(1)
     enc.set_compute_dtype(torch.float32).cuda()
-    x = split_patches(torch.rand(1, 3, 300, 280))[:6]
+    x = split_patches(torch.rand(1, 3, 300, 280).cuda())[:6].cpu()
     with torch.no_grad():
         b = ref(x)
         a = extract_features(x.cuda(), enc).cpu()
@@ -92,7 +152,7 @@ def test_gpu_fp32_matches_torchvision():
 def test_gpu_bf16_tracks_torchvision():
     ref, enc = _pair(2)
     enc.set_compute_dtype(torch.bfloat16).cuda()
-    x = split_patches(torch.rand(1, 3, 256, 256))
+    x = split_patches(torch.rand(1, 3, 256, 256).cuda()).cpu()
     with torch.no_grad():
         b = ref(x)
         a = extract_features(x.cuda(), enc).cpu()
