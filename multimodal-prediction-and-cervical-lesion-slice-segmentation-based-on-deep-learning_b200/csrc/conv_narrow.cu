@@ -148,6 +148,139 @@ __global__ void __launch_bounds__(288) stem_wgrad_kernel(const T* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------- narrow in: weight gradient on warp MMAs (bf16)
+// dW[kk][co] = sum_p patch[p][kk] * dY[p][co] with kk = tap*cin + ci < 32 and co < 32 is a 32 x 32 x (pixels) product:
+// 8 mma.m16n8k16 per 16 pixels and warp.  The A fragments (patch^T, row = kk, column = pixel) are gathered straight
+// from x into registers - a thread needs 4 values of kk (gid + 8j) at 4 pixels (2 tig, +1, +8, +9), 16 two-byte loads
+// that hit L1 (each x element is used by ~2 windows) - and the B fragments (dY, 16 pixels x 32 channels = 1 KB,
+// fetched with two coalesced 16-byte loads per lane) go through an 80-byte-pitch shared tile and ldmatrix.trans.
+// The kernel reads x and dY once at streaming rate; the SIMT version above is bound by its shared-memory loads
+// (2 LDS per 4 FMAs) and ran at 0.35 TB/s.
+__device__ __forceinline__ uint32_t pack_raw_bf16(unsigned short lo, unsigned short hi) {
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+
+__global__ void __launch_bounds__(128) stem_wgrad_mma_kernel(const __nv_bfloat16* __restrict__ x,
+                                                             const __nv_bfloat16* __restrict__ dy,
+                                                             float* __restrict__ dw, NGeom g) {
+  constexpr int kPitch = 80;                                  // bytes per staged dY row (64 + 16: conflict-free ldmatrix)
+  __shared__ __align__(16) uint8_t dys[4][16 * kPitch];
+  __shared__ float red[32 * kStemCout];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int K = g.kh * g.kw * g.cin;
+  for (int i = threadIdx.x; i < 32 * kStemCout; i += blockDim.x) red[i] = 0.f;
+  int koff[4], kdy[4], kdx[4];
+  bool kval[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int kk = gid + 8 * j;
+    kval[j] = kk < K;
+    const int tap = kval[j] ? kk / g.cin : 0;
+    const int ci = kval[j] ? kk - tap * g.cin : 0;
+    kdy[j] = (tap / g.kw) * g.dil;
+    kdx[j] = (tap % g.kw) * g.dil;
+    koff[j] = (kdy[j] * g.w + kdx[j]) * g.cin + ci;
+  }
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+  const int64_t npix = (int64_t)g.n * g.ho * g.wo;
+  const int64_t nblk = (npix + 15) >> 4;
+  const bool row_blocks = (g.wo & 15) == 0;                   // a 16-pixel block never straddles an output row
+  const unsigned short* xr = reinterpret_cast<const unsigned short*>(x);
+  const uint32_t tile = (uint32_t)__cvta_generic_to_shared(&dys[warp][0]);
+  const uint32_t ld_addr = tile + ((lane & 7) + 8 * ((lane >> 3) & 1)) * kPitch + (lane >> 4) * 16;
+  __syncthreads();
+  for (int64_t blk = (int64_t)blockIdx.x * 4 + warp; blk < nblk; blk += (int64_t)gridDim.x * 4) {
+    const int64_t p0 = blk << 4;
+    // ---- dY tile -> shared (rows past the end are zero)
+    uint4 dv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = lane + 32 * r, row = i >> 2, c16 = i & 3;
+      dv[r] = (p0 + row < npix) ? __ldg(reinterpret_cast<const uint4*>(dy + (p0 + row) * kStemCout + c16 * 8))
+                                : make_uint4(0, 0, 0, 0);
+    }
+    // ---- patch gather
+    int oxb = 0, oyb = 0, nb = 0;
+    if (row_blocks) {
+      const int64_t t = p0 / g.wo;
+      oxb = (int)(p0 - t * g.wo); oyb = (int)(t % g.ho); nb = (int)(t / g.ho);
+    }
+    unsigned short xv[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int pl = 2 * tig + (q & 1) + 8 * (q >> 1);
+      int ox, oy, nn;
+      if (row_blocks) {
+        ox = oxb + pl; oy = oyb; nn = nb;
+      } else {
+        const int64_t pp = p0 + pl, t = pp / g.wo;
+        ox = (int)(pp - t * g.wo); oy = (int)(t % g.ho); nn = (int)(t / g.ho);
+      }
+      const bool pok = p0 + pl < npix;
+      const int iy0 = oy * g.stride - g.pad, ix0 = ox * g.stride - g.pad;
+      const int64_t base = (((int64_t)nn * g.h + iy0) * g.w + ix0) * g.cin;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int iy = iy0 + kdy[j], ix = ix0 + kdx[j];
+        const bool ok = pok && kval[j] && iy >= 0 && iy < g.h && ix >= 0 && ix < g.w;
+        xv[q][j] = ok ? __ldg(xr + base + koff[j]) : (unsigned short)0;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int i = lane + 32 * r, row = i >> 2, c16 = i & 3;
+      *reinterpret_cast<uint4*>(&dys[warp][row * kPitch + c16 * 16]) = dv[r];
+    }
+    __syncwarp();
+    uint32_t bf[4][2];                                         // [n tile][k half]
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(bf[2 * h2][0]), "=r"(bf[2 * h2][1]), "=r"(bf[2 * h2 + 1][0]), "=r"(bf[2 * h2 + 1][1])
+                   : "r"(ld_addr + h2 * 32));
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t a0 = pack_raw_bf16(xv[0][2 * mt], xv[1][2 * mt]);
+      const uint32_t a1 = pack_raw_bf16(xv[0][2 * mt + 1], xv[1][2 * mt + 1]);
+      const uint32_t a2 = pack_raw_bf16(xv[2][2 * mt], xv[3][2 * mt]);
+      const uint32_t a3 = pack_raw_bf16(xv[2][2 * mt + 1], xv[3][2 * mt + 1]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                     "{%0, %1, %2, %3};"
+                     : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                     : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[nt][0]), "r"(bf[nt][1]));
+      }
+    }
+    __syncwarp();                                              // the tile is rewritten by the next iteration
+  }
+  // ---- block reduction in shared memory, then one global atomic per (kk, co) and block
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r0 = 16 * mt + gid, c0 = 8 * nt + 2 * tig;
+      atomicAdd(&red[r0 * kStemCout + c0], acc[mt][nt][0]);
+      atomicAdd(&red[r0 * kStemCout + c0 + 1], acc[mt][nt][1]);
+      atomicAdd(&red[(r0 + 8) * kStemCout + c0], acc[mt][nt][2]);
+      atomicAdd(&red[(r0 + 8) * kStemCout + c0 + 1], acc[mt][nt][3]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * kStemCout; i += blockDim.x) {
+    const int kk = i / kStemCout, co = i - kk * kStemCout;
+    const int tap = kk / g.cin, ci = kk - tap * g.cin;
+    atomicAdd(dw + ((size_t)tap * kStemCout + co) * g.cin + ci, red[i]);
+  }
+}
+
 // ---------------------------------------------------------------- narrow out (1x1, C_out <= 8)
 constexpr int kMaxNarrowOut = 8;
 constexpr int kMaxNarrowCin = 1024;
@@ -497,6 +630,13 @@ int narrow_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, flo
   if (is_stem(d)) {
     const NGeom g = ngeom(d);
     const int64_t npix = (int64_t)d->n * d->ho * d->wo;
+    if (d->dtype == CVX_BF16 && d->kh * d->kw * d->cin <= 32 &&
+        (int64_t)d->n * d->h * d->w * d->cin < (1ll << 40)) {
+      stem_wgrad_mma_kernel<<<cap_blocks(ceil_div64(npix, 64), 8), 128, 0, st>>>(
+          (const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, dwp, g);
+      CVX_LAUNCH_OK();
+      return CVX_OK;
+    }
     CVX_DISPATCH_DTYPE(d->dtype, T, (stem_wgrad_kernel<T><<<cap_blocks(ceil_div64(npix, 64), 4), 288, 0, st>>>(
                                         (const T*)x, (const T*)dy, dwp, g)));
     CVX_LAUNCH_OK();

@@ -121,6 +121,81 @@ __global__ void __launch_bounds__(128, 4) dw_stream_kernel(const T* __restrict__
   }
 }
 
+// ---- stride 2, pad 1, dilation 1 data gradient (the three entry-flow down-sampling separable convs) ----------
+// A thread owns a channel vector and a 2x2 quad of INPUT pixels (rows 2a, 2a+1; columns 2b, 2b+1).  With stride 2
+// only taps of matching parity reach a pixel, so the quad needs exactly the 2x2 window dy[a..a+1][b..b+1] and 9
+// multiply-adds per channel (the generic stencil walks all 9 taps of every pixel and masks 3/4 of them off):
+//   dx[2a  ][2b  ] = w11 dy[a][b]                    dx[2a  ][2b+1] = w10 dy[a][b+1] + w12 dy[a][b]
+//   dx[2a+1][2b  ] = w01 dy[a+1][b] + w21 dy[a][b]   dx[2a+1][2b+1] = w00 dy[a+1][b+1] + w02 dy[a+1][b]
+//                                                                   + w20 dy[a][b+1]  + w22 dy[a][b]
+// All eight loads (4 of dy, 4 of the relu mask source) are issued before the first use.
+template <typename T>
+__global__ void __launch_bounds__(128, 3) dw_s2_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w9c,
+                                                             const T* __restrict__ xmask, T* __restrict__ dx, DwGeom g,
+                                                             int relu_in, int64_t stride_items) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int cvn = g.c / VEC;
+  const int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e0 >= stride_items) return;
+  const int c0 = (int)(e0 % cvn) * VEC;
+  float wreg[9][VEC];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) wreg[t][i] = __ldg(w9c + t * g.c + c0 + i);
+  const int qh = (g.h + 1) >> 1, qw = (g.w + 1) >> 1;
+  const int nquads = g.n * qh * qw;
+  const int qstep = (int)(stride_items / cvn);
+  for (int q = (int)(e0 / cvn); q < nquads; q += qstep) {
+    const int b = q % qw;
+    const int t1 = q / qw;
+    const int a = t1 % qh;
+    const int nn = t1 / qh;
+    const bool a1 = a + 1 < g.ho, b1 = b + 1 < g.wo;          // (a < ho and b < wo always: ho = ceil(h/2))
+    const bool r1 = 2 * a + 1 < g.h, c1 = 2 * b + 1 < g.w;    // second row / column of the quad inside the image
+    const T* dyp = dy + (((int64_t)nn * g.ho + a) * g.wo + b) * g.c + c0;
+    const int64_t xoff = (((int64_t)nn * g.h + 2 * a) * g.w + 2 * b) * g.c + c0;
+    const int64_t xrow = (int64_t)g.w * g.c;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    const uint4 d00 = __ldg(reinterpret_cast<const uint4*>(dyp));
+    const uint4 d01 = b1 ? __ldg(reinterpret_cast<const uint4*>(dyp + g.c)) : z;
+    const uint4 d10 = a1 ? __ldg(reinterpret_cast<const uint4*>(dyp + (int64_t)g.wo * g.c)) : z;
+    const uint4 d11 = (a1 && b1) ? __ldg(reinterpret_cast<const uint4*>(dyp + (int64_t)g.wo * g.c + g.c)) : z;
+    uint4 m00 = z, m01 = z, m10 = z, m11 = z;
+    if (relu_in) {
+      m00 = __ldg(reinterpret_cast<const uint4*>(xmask + xoff));
+      if (c1) m01 = __ldg(reinterpret_cast<const uint4*>(xmask + xoff + g.c));
+      if (r1) m10 = __ldg(reinterpret_cast<const uint4*>(xmask + xoff + xrow));
+      if (r1 && c1) m11 = __ldg(reinterpret_cast<const uint4*>(xmask + xoff + xrow + g.c));
+    }
+    float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
+    raw_to_float<T>(d00, v00); raw_to_float<T>(d01, v01); raw_to_float<T>(d10, v10); raw_to_float<T>(d11, v11);
+    Vec<T> o00, o01, o10, o11;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      o00.v[i] = wreg[4][i] * v00[i];
+      o01.v[i] = fmaf(wreg[3][i], v01[i], wreg[5][i] * v00[i]);
+      o10.v[i] = fmaf(wreg[1][i], v10[i], wreg[7][i] * v00[i]);
+      o11.v[i] = fmaf(wreg[0][i], v11[i], fmaf(wreg[2][i], v10[i], fmaf(wreg[6][i], v01[i], wreg[8][i] * v00[i])));
+    }
+    if (relu_in) {
+      float k00[VEC], k01[VEC], k10[VEC], k11[VEC];
+      raw_to_float<T>(m00, k00); raw_to_float<T>(m01, k01); raw_to_float<T>(m10, k10); raw_to_float<T>(m11, k11);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        o00.v[i] = k00[i] > 0.f ? o00.v[i] : 0.f;
+        o01.v[i] = k01[i] > 0.f ? o01.v[i] : 0.f;
+        o10.v[i] = k10[i] > 0.f ? o10.v[i] : 0.f;
+        o11.v[i] = k11[i] > 0.f ? o11.v[i] : 0.f;
+      }
+    }
+    o00.store(dx + xoff);
+    if (c1) o01.store(dx + xoff + g.c);
+    if (r1) o10.store(dx + xoff + xrow);
+    if (r1 && c1) o11.store(dx + xoff + xrow + g.c);
+  }
+}
+
 // ---- stride 1, dilation 1 (the 60 middle/exit-flow depthwise convs of Xception) -------------
 // A thread owns a channel vector AND walks a strip of SX consecutive output columns with a
 // sliding 3x3 window held in registers: 3 new 16-byte loads per output instead of 9, and the
@@ -368,6 +443,17 @@ int cvx_dwconv_bwd_data(const cvx_conv_desc* d, const void* dy, const float* w9c
     dw_s1_grid(g, g.c / vec, &blocks, &stride);
     CVX_DISPATCH_DTYPE(d->dtype, T, (dw_s1_kernel<T, 1><<<blocks, 128, 0, as_stream(stream)>>>(
                                         (const T*)dy, w9c, (const T*)x, (T*)dx, nullptr, g.n, g.h, g.w, g.c, relu_in, stride)));
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
+  if (g.stride == 2 && g.pad == 1 && g.dil == 1 && g.ho == (g.h + 1) / 2 && g.wo == (g.w + 1) / 2) {
+    const int64_t items = (int64_t)g.n * ((g.h + 1) / 2) * ((g.w + 1) / 2) * (g.c / vec);
+    int64_t want = (int64_t)kNumSMs * 3 * 128 * 4;
+    if (want > items) want = items;
+    stride = ceil_div64(want, g.c / vec) * (g.c / vec);
+    blocks = (int)ceil_div64(stride, 128);
+    CVX_DISPATCH_DTYPE(d->dtype, T, (dw_s2_dgrad_kernel<T><<<blocks, 128, 0, as_stream(stream)>>>(
+                                        (const T*)dy, w9c, (const T*)x, (T*)dx, g, relu_in, stride)));
     CVX_LAUNCH_OK();
     return CVX_OK;
   }

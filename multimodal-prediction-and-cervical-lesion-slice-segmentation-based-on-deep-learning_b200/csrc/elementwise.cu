@@ -203,11 +203,15 @@ __global__ void upsample_to_nchw_fwd_kernel(const T* __restrict__ x, float* __re
 template <typename T>
 __global__ void upsample_to_nchw_bwd_kernel(const float* __restrict__ dy, T* __restrict__ dx, int n, int hi, int wi,
                                             int ho, int wo, int c, float sh, float sw) {
+  // e enumerates [n][c][iy][ix] with ix fastest: the threads of a warp gather from adjacent windows of the SAME
+  // rows of one dy plane (coalesced reads of the large fp32 NCHW gradient); the small NHWC result takes the
+  // strided 2-byte stores instead.
   const int64_t total = (int64_t)n * hi * wi * c;
   CVX_GRID_STRIDE(e, total) {
-    const int cc = (int)(e % c);
-    int64_t p = e / c;
-    const int ix = (int)(p % wi), iy = (int)((p / wi) % hi), nn = (int)(p / ((int64_t)wi * hi));
+    const int ix = (int)(e % wi);
+    int64_t q = e / wi;
+    const int iy = (int)(q % hi); q /= hi;
+    const int cc = (int)(q % c), nn = (int)(q / c);
     int ylo, yhi, xlo, xhi;
     lerp_range(iy, sh, ho, &ylo, &yhi);
     lerp_range(ix, sw, wo, &xlo, &xhi);
@@ -218,10 +222,10 @@ __global__ void upsample_to_nchw_bwd_kernel(const float* __restrict__ dy, T* __r
       if (wy == 0.f) continue;
       for (int ox = xlo; ox <= xhi; ++ox) {
         const float wgt = wy * lerp_weight(ix, ox, sw, wi);
-        if (wgt != 0.f) acc = fmaf(wgt, plane[(size_t)oy * wo + ox], acc);
+        if (wgt != 0.f) acc = fmaf(wgt, __ldg(plane + (size_t)oy * wo + ox), acc);
       }
     }
-    Elem<T>::st(dx + e, acc);
+    Elem<T>::st(dx + (((size_t)nn * hi + iy) * wi + ix) * c + cc, acc);
   }
 }
 

@@ -70,6 +70,8 @@ def test_layout_roundtrip(B, dtype):
 CONV_CASES = [
     # n, h, w, cin, cout, k, stride, pad, dil, bias
     (2, 19, 23, 3, 32, 3, 2, 1, 1, False),     # stem
+    (2, 33, 64, 3, 32, 3, 2, 1, 1, False),     # stem, output rows of 32 pixels (whole 16-pixel MMA blocks per row)
+    (1, 19, 21, 3, 32, 3, 2, 1, 1, False),     # stem, 110 output pixels (ragged last MMA block)
     (2, 16, 16, 32, 64, 3, 1, 1, 1, False),
     (2, 16, 12, 64, 128, 1, 2, 0, 1, False),   # strided skip
     (1, 12, 12, 72, 40, 3, 1, 6, 6, True),     # atrous, ragged channels
