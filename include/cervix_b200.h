@@ -125,9 +125,11 @@ CVX_API int cvx_bn_forward(const void* x, const void* residual, void* y, const f
                    float* running_mean, float* running_var, float* save_mean, float* save_invstd,
                    double* ws, int64_t rows, int c, int dtype, int act, int training,
                    float momentum, float eps, void* stream);
-/* dx (and dres = d(act) if non-null), dgamma, dbeta (overwritten).  y is required when
- * act != NONE (activation mask).  training=0 treats mean/invstd as constants. */
-CVX_API int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* gamma,
+/* dx (and dres = d(act) if non-null), dgamma, dbeta (overwritten).  The activation mask (act != NONE) is read off y,
+ * or - when beta is given (only valid if the forward had no residual; dres must be NULL) - recomputed from x with the
+ * forward's own fma(x, gamma*invstd, beta - mean*gamma*invstd), so that y is not read at all (5 instead of 7 passes
+ * over the tensor).  training=0 treats mean/invstd as constants. */
+CVX_API int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* gamma, const float* beta,
                     const float* save_mean, const float* save_invstd, void* dx, void* dres,
                     float* dgamma, float* dbeta, double* ws, int64_t rows, int c, int dtype,
                     int act, int training, void* stream);

@@ -53,7 +53,7 @@ PROTOTYPES = {
     "cvx_dwconv_bwd_data": [_D, _P, _P, _P, _P, _I, _P],
     "cvx_dwconv_bwd_weight": [_D, _P, _P, _P, _P, _I, _P],
     "cvx_bn_forward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _P],
-    "cvx_bn_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
+    "cvx_bn_backward": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _P],
     "cvx_relu_fwd": [_P, _P, _L, _I, _P],
     "cvx_relu_bwd": [_P, _P, _P, _L, _I, _P],
     "cvx_add": [_P, _P, _P, _L, _I, _P],

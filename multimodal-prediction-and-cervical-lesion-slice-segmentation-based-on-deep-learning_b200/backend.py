@@ -280,8 +280,9 @@ class CudaBackend:
                                       float(eps), self._stream()), "cvx_bn_forward")
         return y, mean, invstd
 
-    def bn_backward(self, dy, x, y, gamma, mean, invstd, act: int, training: bool, want_dres: bool):
-        self._chk(dy, x, y, gamma, mean, invstd)
+    def bn_backward(self, dy, x, y, gamma, mean, invstd, act: int, training: bool, want_dres: bool, beta=None):
+        """beta given (forward without residual): the activation mask is recomputed from x and y is not read."""
+        self._chk(dy, x, y, gamma, mean, invstd, beta)
         c = int(x.shape[-1])
         rows = x.numel() // c
         dx = torch.empty_like(x)
@@ -289,7 +290,7 @@ class CudaBackend:
         dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
         ws = torch.empty((2 * c + 2,), dtype=torch.float64, device=x.device)
-        check(self.lib.cvx_bn_backward(_p(dy), _p(x), _p(y), _p(gamma), _p(mean), _p(invstd), _p(dx), _p(dres),
+        check(self.lib.cvx_bn_backward(_p(dy), _p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(invstd), _p(dx), _p(dres),
                                        _p(dgamma), _p(dbeta), _p(ws), rows, c, _dt(x), act, int(training),
                                        self._stream()), "cvx_bn_backward")
         return dx, dres, dgamma, dbeta

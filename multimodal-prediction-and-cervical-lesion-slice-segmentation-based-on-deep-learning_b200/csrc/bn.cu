@@ -45,23 +45,41 @@ struct BnBwdF {
   static constexpr int NACC = 2;
   const T* dy;
   const T* x;
-  const T* y;  // may be null when act == NONE
+  const T* y;  // activation output: source of the mask unless beta is given; may be null when act == NONE
+  const float* gamma;
+  const float* beta;  // non-null: the mask is recomputed from x exactly as the forward computed y (no residual)
   const float* mean;
   const float* invstd;
   int C, act;
-  __device__ __forceinline__ void operator()(int64_t row, int c0, float (&acc)[2][Elem<T>::kVec]) const {
+  struct Ctx {
+    float mean[Elem<T>::kVec], is[Elem<T>::kVec], sc[Elem<T>::kVec], sh[Elem<T>::kVec];
+  };
+  __device__ __forceinline__ void init(int c0, Ctx& k) const {
+#pragma unroll
+    for (int i = 0; i < Elem<T>::kVec; ++i) {
+      k.mean[i] = mean[c0 + i];
+      k.is[i] = invstd[c0 + i];
+      k.sc[i] = beta ? gamma[c0 + i] * k.is[i] : 0.f;
+      k.sh[i] = beta ? beta[c0 + i] - k.mean[i] * k.sc[i] : 0.f;
+    }
+  }
+  __device__ __forceinline__ void operator()(int64_t row, int c0, float (&acc)[2][Elem<T>::kVec], const Ctx& k) const {
     Vec<T> g, xv, yv;
     g.load(dy + row * C + c0);
     xv.load(x + row * C + c0);
-    if (act != CVX_ACT_NONE) yv.load(y + row * C + c0);
+    const bool from_y = act != CVX_ACT_NONE && beta == nullptr;
+    if (from_y) yv.load(y + row * C + c0);
 #pragma unroll
     for (int i = 0; i < Vec<T>::N; ++i) {
       float dz = g.v[i];
-      if (act != CVX_ACT_NONE) dz *= act_mask(yv.v[i], act);
-      const float xhat = (xv.v[i] - __ldg(mean + c0 + i)) * __ldg(invstd + c0 + i);
+      if (act != CVX_ACT_NONE) dz *= act_mask(from_y ? yv.v[i] : fmaf(xv.v[i], k.sc[i], k.sh[i]), act);
       acc[0][i] += dz;
-      acc[1][i] = fmaf(dz, xhat, acc[1][i]);
+      acc[1][i] = fmaf(dz, xv.v[i] - k.mean[i], acc[1][i]);   // x 1/sigma in finish(): sum dz * xhat
     }
+  }
+  __device__ __forceinline__ void finish(float (&acc)[2][Elem<T>::kVec], const Ctx& k) const {
+#pragma unroll
+    for (int i = 0; i < Elem<T>::kVec; ++i) acc[1][i] *= k.is[i];
   }
 };
 
@@ -124,21 +142,24 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
-    const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ acc,
-    T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int act, int training, int64_t stride_vecs) {
+    const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+    const double* __restrict__ acc, T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int act,
+    int training, int64_t stride_vecs) {
   constexpr int VEC = Elem<T>::kVec;
   const int cvn = C / VEC;
   const int64_t total = rows * cvn;
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= stride_vecs) return;
   const int c0 = (int)(e % cvn) * VEC;
-  float k[VEC], mu[VEC], is[VEC], m1[VEC], m2[VEC];
+  float k[VEC], mu[VEC], is[VEC], m1[VEC], m2[VEC], sh[VEC];
   const float inv_n = 1.0f / (float)rows;
+  const bool from_y = act != CVX_ACT_NONE && beta == nullptr;   // else the mask is recomputed from x (forward's fma)
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     mu[i] = mean[c0 + i];
     is[i] = invstd[c0 + i];
     k[i] = gamma[c0 + i] * is[i];
+    sh[i] = beta ? beta[c0 + i] - mu[i] * k[i] : 0.f;
     m1[i] = training ? (float)(acc[c0 + i] * (double)inv_n) : 0.f;
     m2[i] = training ? (float)(acc[C + c0 + i] * (double)inv_n) : 0.f;
   }
@@ -146,11 +167,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     Vec<T> g, xv, yv;
     g.load(dy + e * VEC);
     xv.load(x + e * VEC);
-    if (act != CVX_ACT_NONE) yv.load(y + e * VEC);
+    if (from_y) yv.load(y + e * VEC);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       float dz = g.v[i];
-      if (act != CVX_ACT_NONE) dz *= act_mask(yv.v[i], act);
+      if (act != CVX_ACT_NONE) dz *= act_mask(from_y ? yv.v[i] : fmaf(xv.v[i], k[i], sh[i]), act);
       g.v[i] = dz;
       const float xhat = (xv.v[i] - mu[i]) * is[i];
       xv.v[i] = k[i] * (dz - m1[i] - xhat * m2[i]);
@@ -406,7 +427,7 @@ int cvx_bn_forward(const void* x, const void* residual, void* y, const float* ga
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "bn_forward: C=%d not a multiple of %d", c, vec);
   static const bool no_fused = getenv("CERVIX_BN_FUSED") == nullptr;  // single-launch variant measured no faster: opt-in
-  if (training && !no_fused && (size_t)2 * c * sizeof(float) <= 48 * 1024) {
+  if (training && !no_fused && !beta && (size_t)2 * c * sizeof(float) <= 48 * 1024) {
     // ws holds 2*C doubles of sums + one barrier counter
     CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * (2 * c + 2), st));
     int blocks = 0; int64_t stride = 0; int rc = CVX_EUNSUPPORTED;
@@ -442,12 +463,14 @@ int cvx_bn_forward(const void* x, const void* residual, void* y, const float* ga
   return CVX_OK;
 }
 
-int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* gamma, const float* save_mean,
-                    const float* save_invstd, void* dx, void* dres, float* dgamma, float* dbeta, double* ws,
-                    int64_t rows, int c, int dtype, int act, int training, void* stream) {
+int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* gamma, const float* beta,
+                    const float* save_mean, const float* save_invstd, void* dx, void* dres, float* dgamma,
+                    float* dbeta, double* ws, int64_t rows, int c, int dtype, int act, int training, void* stream) {
   CVX_CHECK_ARG(dy && x && gamma && save_mean && save_invstd && dx && ws && rows > 0 && c > 0,
                 "bn_backward: bad arguments");
-  CVX_CHECK_ARG(act == CVX_ACT_NONE || y, "bn_backward: activation mask needs y");
+  CVX_CHECK_ARG(act == CVX_ACT_NONE || y || beta, "bn_backward: the activation mask needs y, or beta to recompute it from x");
+  CVX_CHECK_ARG(!(beta && dres), "bn_backward: the mask can only be recomputed from x when the forward had no residual");
+  if (act == CVX_ACT_NONE) beta = nullptr;
   cudaStream_t st = as_stream(stream);
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "bn_backward: C=%d not a multiple of %d", c, vec);
@@ -472,13 +495,13 @@ int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* g
   CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
   int rc = CVX_OK;
   CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, BnBwdF<T>, 256, 3>(
-                                   BnBwdF<T>{(const T*)dy, (const T*)x, (const T*)y, save_mean, save_invstd, c, act},
+                                   BnBwdF<T>{(const T*)dy, (const T*)x, (const T*)y, gamma, beta, save_mean, save_invstd, c, act},
                                    rows, c, ws, st)));
   if (rc) return rc;
   int blocks; int64_t stride;
   stream_grid(rows * (c / vec), c / vec, &blocks, &stride);
   CVX_DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<blocks, 256, 0, st>>>(
-                                   (const T*)dy, (const T*)x, (const T*)y, gamma, save_mean, save_invstd, ws, (T*)dx,
+                                   (const T*)dy, (const T*)x, (const T*)y, gamma, beta, save_mean, save_invstd, ws, (T*)dx,
                                    (T*)dres, rows, c, act, training, stride)));
   CVX_LAUNCH_OK();
   if (dgamma || dbeta) {

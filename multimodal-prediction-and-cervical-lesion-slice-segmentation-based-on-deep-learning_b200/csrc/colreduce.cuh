@@ -8,10 +8,18 @@
 
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace cvx {
 
 // F must provide:  static constexpr int NACC;
 //   __device__ void operator()(int64_t row, int c0, float (&acc)[NACC][VEC]) const;
+// or, with per-thread channel constants held in registers for the whole walk (a thread owns one channel vector):
+//   struct Ctx;  __device__ void init(int c0, Ctx&) const;
+//   __device__ void operator()(int64_t row, int c0, float (&acc)[NACC][VEC], const Ctx&) const;
+//   __device__ void finish(float (&acc)[NACC][VEC], const Ctx&) const;
+template <typename F, typename = void> struct ColHasCtx : std::false_type {};
+template <typename F> struct ColHasCtx<F, std::void_t<typename F::Ctx>> : std::true_type {};
 template <typename T, typename F, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) colreduce_kernel(F f, int64_t rows, int C, int colchunk_vecs,
                                                              int64_t rows_per_block, double* __restrict__ out) {
@@ -38,8 +46,16 @@ __global__ void __launch_bounds__(NT, MINB) colreduce_kernel(F f, int64_t rows, 
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     int64_t r1 = r0 + rows_per_block;
     if (r1 > rows) r1 = rows;
+    if constexpr (ColHasCtx<F>::value) {
+      typename F::Ctx ctx;
+      f.init(cvec * VEC, ctx);
 #pragma unroll 8
-    for (int64_t r = r0 + lane; r < r1; r += lanes) f(r, cvec * VEC, acc);
+      for (int64_t r = r0 + lane; r < r1; r += lanes) f(r, cvec * VEC, acc, ctx);
+      f.finish(acc, ctx);
+    } else {
+#pragma unroll 8
+      for (int64_t r = r0 + lane; r < r1; r += lanes) f(r, cvec * VEC, acc);
+    }
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
 #pragma unroll

@@ -174,16 +174,20 @@ class BatchNormAct(Function):
             residual = residual.contiguous()
         y, mean, invstd = B.bn_forward(x, residual, gamma.detach(), beta.detach(), running_mean, running_var, act,
                                        training, momentum, eps)
-        ctx.save_for_backward(x, y if act != ACT_NONE else None, gamma, mean, invstd)
+        # without a residual the backward recomputes the activation mask from x (saves two passes over y)
+        ctx.mask_from_x = act != ACT_NONE and residual is None
+        ctx.save_for_backward(x, y if (act != ACT_NONE and not ctx.mask_from_x) else None, gamma, mean, invstd,
+                              beta if ctx.mask_from_x else None)
         ctx.act, ctx.training, ctx.has_res = act, training, residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         B = get_backend()
-        x, y, gamma, mean, invstd = ctx.saved_tensors
+        x, y, gamma, mean, invstd, beta = ctx.saved_tensors
         dx, dres, dgamma, dbeta = B.bn_backward(dy.contiguous(), x, y, gamma.detach(), mean, invstd, ctx.act,
-                                                ctx.training, ctx.has_res and ctx.needs_input_grad[5])
+                                                ctx.training, ctx.has_res and ctx.needs_input_grad[5],
+                                                None if beta is None else beta.detach())
         if not ctx.needs_input_grad[1]:
             dgamma = None
         if not ctx.needs_input_grad[2]:

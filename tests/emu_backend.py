@@ -175,10 +175,13 @@ class EmuBackend:
             y = y + residual.float().reshape(-1, c)
         return self._act(y, act).reshape(x.shape).to(x.dtype), mean, invstd
 
-    def bn_backward(self, dy, x, y, gamma, mean, invstd, act, training, want_dres):
+    def bn_backward(self, dy, x, y, gamma, mean, invstd, act, training, want_dres, beta=None):
         c = x.shape[-1]
         dz = dy.float().reshape(-1, c)
         if act != 0:
+            if beta is not None:      # mask recomputed from x (forward without residual): y is not needed
+                sc = gamma.float() * invstd
+                y = self._act(x.float().reshape(-1, c) * sc + (beta.float() - mean * sc), act)
             dz = dz * self._mask(y.float().reshape(-1, c), act)
         xhat = (x.float().reshape(-1, c) - mean) * invstd
         dbeta = dz.double().sum(0).float()

@@ -155,6 +155,18 @@ def test_batchnorm(B, dtype, training, c, act, res):
     if res:
         check(out[1], oute[1], tol(dtype), "dres")
     check(out[2], oute[2], 1e-4, "dgamma"); check(out[3], oute[3], 1e-4, "dbeta")
+    if act != 0 and not res:
+        # mask recomputed from x (beta given, y not read) against the same recipe in fp32 torch ops ...
+        outx = B.bn_backward(dy, x, None, gamma, mean, invstd, act, training, False, beta)
+        outs = EMU.bn_backward(dy, x, None, gamma, me, ie, act, training, False, beta)
+        check(outx[0], outs[0], tol(dtype) * 2, "dx (mask from x)")
+        check(outx[2], outs[2], 2e-4, "dgamma (mask from x)"); check(outx[3], outs[3], 2e-4, "dbeta (mask from x)")
+        if act == 1 or dtype == torch.float32:
+            # ... and identical to the mask read off the product's own y (ReLU6 in bf16 differs where y rounds to 6.0:
+            # the recomputed mask is the fp32 one, as torch's hardtanh_backward uses the pre-activation value)
+            outy = B.bn_backward(dy, x, y, gamma, mean, invstd, act, training, False)
+            check(outx[0], outy[0], 1e-6, "dx (mask from x vs y)")
+            check(outx[2], outy[2], 1e-6, "dgamma (mask from x vs y)"); check(outx[3], outy[3], 1e-6, "dbeta (mask from x vs y)")
 
 
 def test_batchnorm_tiny_batch_rows(B):
