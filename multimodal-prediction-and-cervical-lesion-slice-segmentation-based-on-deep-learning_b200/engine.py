@@ -310,12 +310,19 @@ class FusionTrainer:
 class BatchPrefetcher:
     """Moves pinned host batches to the device one step ahead on a side stream, so the
     host->device copy of step i+1 overlaps the compute of step i (replaces the synchronous
-    ``imgs.cuda(local_rank)`` calls of utils/utils_fit.py:52-58)."""
+    ``imgs.cuda(local_rank)`` calls of utils/utils_fit.py:52-58).  The device side is two fixed buffer sets used
+    alternately (no allocator traffic in the steady state): a set is overwritten only after the work that was
+    enqueued on the compute stream while it was the current batch has finished (event recorded at the next
+    ``__next__``), so a yielded batch stays valid until the one after next is requested."""
 
     def __init__(self, batches, device=None):
         self.it = iter(batches)
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.stream = torch.cuda.Stream(self.device)
+        self.slots = [None, None]
+        self.consumed = [None, None]
+        self.k = 0
+        self.last_slot = None
         self.next = None
         self._fetch()
 
@@ -325,19 +332,37 @@ class BatchPrefetcher:
         except StopIteration:
             self.next = None
             return
+        s = self.k & 1
+        self.k += 1
         with torch.cuda.stream(self.stream):
-            self.next = tuple(None if t is None else t.to(self.device, non_blocking=True) for t in host)
+            if self.consumed[s] is not None:
+                self.stream.wait_event(self.consumed[s])
+            bufs = self.slots[s]
+            if bufs is None or len(bufs) != len(host) or any(
+                    (b is None) != (t is None) or (b is not None and (b.shape != t.shape or b.dtype != t.dtype))
+                    for b, t in zip(bufs, host)):
+                bufs = tuple(None if t is None else torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in host)
+                for b in bufs:
+                    if b is not None:
+                        b.record_stream(torch.cuda.current_stream(self.device))
+                self.slots[s] = bufs
+            for b, t in zip(bufs, host):
+                if b is not None:
+                    b.copy_(t, non_blocking=True)
+        self.next = (s, bufs)
 
     def __iter__(self):
         return self
 
     def __next__(self):
+        if self.last_slot is not None:      # everything that used the previous batch has been enqueued by now
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.consumed[self.last_slot] = ev
         if self.next is None:
             raise StopIteration
-        torch.cuda.current_stream().wait_stream(self.stream)
-        cur = self.next
-        for t in cur:
-            if t is not None:
-                t.record_stream(torch.cuda.current_stream())
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        s, cur = self.next
+        self.last_slot = s
         self._fetch()
         return cur
