@@ -56,8 +56,8 @@ class MobileNetV2(nn.Module):
 
 def _conv_bn_relu(x, seq, idx=0):
     conv, bn = seq[idx], seq[idx + 1]
-    y = ops.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], conv.dilation[0])
-    return ops.batchnorm_act(y, bn, ops.ACT_RELU)
+    return ops.conv_bn_act(x, conv.weight, conv.stride[0], conv.padding[0], conv.dilation[0], bn, ops.ACT_RELU, None,
+                           conv.bias)
 
 
 class ASPP(nn.Module):

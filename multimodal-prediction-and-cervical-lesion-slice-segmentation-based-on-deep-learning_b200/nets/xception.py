@@ -50,10 +50,9 @@ class SeparableConv2d(nn.Module):
         mid_act = ops.ACT_NONE if self.activate_first else ops.ACT_RELU
         y = ops.dwconv3x3(x, dw.weight, dw.stride[0], dw.padding[0], dw.dilation[0], relu_in=self.activate_first)
         y = ops.batchnorm_act(y, self.bn1, mid_act)
-        y = ops.conv2d(y, self.pointwise.weight, None, 1, 0, 1)
         if not self.activate_first:
             out_act = ops.ACT_RELU
-        return ops.batchnorm_act(y, self.bn2, out_act, residual)
+        return ops.conv_bn_act(y, self.pointwise.weight, 1, 0, 1, self.bn2, out_act, residual)
 
 
 class Block(nn.Module):
@@ -93,8 +92,7 @@ class Block(nn.Module):
             return ops_fused.sep_chain(seps, inp, None, True, out_act)
         if self.skip is not None:
             s = self.skip
-            skip = ops.conv2d(inp, s.weight, None, s.stride[0], 0, 1)
-            skip = ops.batchnorm_act(skip, self.skipbn, ops.ACT_NONE)
+            skip = ops.conv_bn_act(inp, s.weight, s.stride[0], 0, 1, self.skipbn, ops.ACT_NONE)
             if fuse and ops_fused.chain_fusable(seps, inp):
                 self.hook_layer = None          # stride-1 block with a 1x1 skip (block20): all three fused
                 return ops_fused.sep_chain(seps, inp, skip, False, out_act)
@@ -154,8 +152,7 @@ class Xception(nn.Module):
         self.layers = []
         x = ops.conv2d(x, self.conv1.weight, None, 2, 1, 1)
         x = ops.batchnorm_act(x, self.bn1, ops.ACT_RELU)
-        x = ops.conv2d(x, self.conv2.weight, None, 1, 1, 1)
-        x = ops.batchnorm_act(x, self.bn2, ops.ACT_RELU)
+        x = ops.conv_bn_act(x, self.conv2.weight, 1, 1, 1, self.bn2, ops.ACT_RELU)
         x = self.block1(x)
         x = self.block2(x)
         low_level = self.block2.hook_layer

@@ -98,6 +98,61 @@ class Conv2d(Function):
         return dx, dw, db, None, None, None
 
 
+class ConvBnAct(Function):
+    """Training-mode ``act(BatchNorm2d(conv(x)) + residual)`` for a bias-free dense conv on the tensor-core path, with
+    the batch statistics taken in the GEMM epilogue (cvx_conv_fwd_tc_ex) instead of by a separate pass over the conv
+    output: conv -> (sum, sum^2 per channel) -> scale/shift (cvx_bn_affine, also updates the running buffers) ->
+    one apply pass.  Same math as ``Conv2d`` followed by ``BatchNormAct``."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, residual, stride, pad, dil, momentum, eps,
+                act):
+        B = get_backend()
+        x = x.contiguous()
+        n, h, w, cin = x.shape
+        cout, _, kh, kw = weight.shape
+        sub = 1
+        if stride != 1 and kh == 1 and kw == 1 and pad == 0:
+            x = B.subsample(x, stride)
+            sub, stride = stride, 1
+        g = ConvGeom(x.shape[0], x.shape[1], x.shape[2], cin, cout, kh, kw, stride, pad, dil)
+        wp = B.pack_weight(weight.detach(), x.dtype, False)
+        p, stats = B.conv_fwd_ex(x, wp, None if bias is None else bias.detach(), g, None, None, True)
+        rows = p.numel() // cout
+        mean, invstd, scale, shift = B.bn_affine(stats, rows, gamma.detach(), beta.detach(), running_mean, running_var,
+                                                 momentum, eps)
+        if residual is not None:
+            residual = residual.contiguous()
+        y = B.affine_act(p, scale, shift, residual, act)
+        mask_from_x = act != ACT_NONE and residual is None
+        ctx.save_for_backward(x, weight, p, y if (act != ACT_NONE and not mask_from_x) else None, gamma, mean, invstd,
+                              beta if mask_from_x else None)
+        ctx.g, ctx.sub, ctx.in_hw, ctx.act, ctx.has_res = g, sub, (h, w), act, residual is not None
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B = get_backend()
+        x, weight, p, y, gamma, mean, invstd, beta = ctx.saved_tensors
+        g = ctx.g
+        dz, dres, dgamma, dbeta = B.bn_backward(dy.contiguous(), p, y, gamma.detach(), mean, invstd, ctx.act, True,
+                                                ctx.has_res and ctx.needs_input_grad[7],
+                                                None if beta is None else beta.detach())
+        tc = g.stride == 1
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wpt = B.pack_weight(weight.detach(), dz.dtype, True)
+            dx = B.conv_dgrad(dz, wpt, g, tc)
+            if ctx.sub != 1:
+                dx = B.subsample_bwd(dx, ctx.in_hw[0], ctx.in_hw[1], ctx.sub)
+        if ctx.needs_input_grad[1]:
+            dw = B.unpack_wgrad(B.conv_wgrad(x, dz, g, tc), g.cout, g.cin, g.kh, g.kw)
+        db = B.bias_grad(dz) if (ctx.has_bias and ctx.needs_input_grad[2]) else None   # (sums to ~0 behind a BatchNorm)
+        return (dx, dw, db, dgamma if ctx.needs_input_grad[3] else None, dbeta if ctx.needs_input_grad[4] else None,
+                None, None, dres, None, None, None, None, None, None)
+
+
 class MaxPool3x3S2(Function):
     """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) on NHWC."""
 
@@ -369,6 +424,31 @@ def batchnorm_act(x, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None):
     momentum = 0.0 if bn.momentum is None else bn.momentum
     return BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training, momentum,
                               bn.eps, act)
+
+
+# Measured (batch 32, A/B over the whole step): the composite is a wash - 45.8 ms with it off, 45.7 .. 46.2 ms with it on
+# for the long-K layers only (K >= 1024: decoder 3x3, ASPP), 46.1 ms for all layers - because the epilogue's column sums
+# cost about what the separate statistics pass does.  It therefore stays OFF by default; CERVIX_CONV_BN_MINK=<K> turns
+# it on for convolutions whose reduction length cin*kh*kw is at least K.
+_CONV_BN_MIN_K = int(os.environ.get("CERVIX_CONV_BN_MINK", str(1 << 30)))
+
+
+def conv_bn_act(x, conv_weight, stride, pad, dil, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None, bias=None):
+    """``act(bn(conv(x)) + residual)``: one composite with the BatchNorm statistics from the GEMM
+    epilogue when the layer trains on the tensor-core path, else ``conv2d`` followed by ``batchnorm_act``."""
+    cout, cin, kh, kw = conv_weight.shape
+    B = get_backend()
+    fused = (bn.training and bn.running_mean is not None and _tc_ok(x, cin, cout) and hasattr(B, "conv_fwd_ex")
+             and cin * kh * kw >= _CONV_BN_MIN_K
+             and (stride == 1 or (kh == 1 and kw == 1 and pad == 0) or stride == 2)
+             and x.shape[0] * x.shape[1] * x.shape[2] >= 1024)
+    if not fused:
+        return batchnorm_act(conv2d(x, conv_weight, bias, stride, pad, dil), bn, act, residual)
+    if bn.track_running_stats and bn.num_batches_tracked is not None and not _DEFER_NBT[0]:
+        bn.num_batches_tracked.add_(1)
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    return ConvBnAct.apply(x, conv_weight, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, stride,
+                           pad, dil, momentum, bn.eps, act)
 
 
 def relu(x):

@@ -225,3 +225,55 @@ def test_fused_block_is_as_accurate_as_operator_path_bf16(relu_out, shape):
             continue
         ea, eb = err(a[k].float(), r), err(b[k].float(), r)
         assert eb < 1.5 * ea + 5e-3, (k, ea, eb)
+
+
+@pytest.mark.parametrize("case", [
+    # n, h, w, cin, cout, k, stride, pad, dil, act, residual, bias
+    (2, 24, 28, 304, 256, 3, 1, 1, 1, 1, False, True),     # decoder cat_conv
+    (4, 16, 16, 2048, 256, 3, 1, 6, 6, 1, False, True),    # ASPP atrous branch
+    (2, 32, 32, 256, 48, 1, 1, 0, 1, 1, False, True),      # decoder shortcut
+    (2, 32, 32, 128, 256, 1, 2, 0, 1, 0, False, False),    # strided 1x1 skip conv + skipbn
+    (4, 16, 16, 728, 1024, 1, 1, 0, 1, 0, True, False),    # pointwise + bn2 + residual (exit flow)
+    (2, 40, 40, 32, 64, 3, 1, 1, 1, 1, False, False),      # stem conv2
+])
+def test_conv_bn_act_composite_matches_separate_ops(case):
+    """ops.conv_bn_act (BatchNorm statistics from the GEMM epilogue) against ops.conv2d + ops.batchnorm_act on the same
+    bf16 inputs: output, running buffers, and all gradients."""
+    from cervix_b200 import ops
+    n, h, w, cin, cout, k, stride, pad, dil, act, with_res, with_bias = case
+    x0 = rnd(n, h, w, cin, seed=1, dtype=torch.bfloat16)
+    wt0 = rnd(cout, cin, k, k, seed=2, scale=(cin * k * k) ** -0.5)
+    b0 = rnd(cout, seed=3, scale=0.3) if with_bias else None
+    ho = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    wo = (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    r0 = rnd(n, ho, wo, cout, seed=4, dtype=torch.bfloat16) if with_res else None
+    dy = rnd(n, ho, wo, cout, seed=5, dtype=torch.bfloat16)
+    outs = []
+    for fused in (True, False):
+        ops._CONV_BN_MIN_K = 0 if fused else (1 << 30)          # (the composite is off by default: see ops.conv_bn_act)
+        bn = torch.nn.BatchNorm2d(cout, momentum=0.1).cuda().train()
+        with torch.no_grad():
+            bn.weight.copy_(1 + 0.2 * rnd(cout, seed=6)); bn.bias.copy_(0.2 * rnd(cout, seed=7))
+        x = x0.clone().requires_grad_(True)
+        wt = wt0.clone().requires_grad_(True)
+        b = None if b0 is None else b0.clone().requires_grad_(True)
+        r = None if r0 is None else r0.clone().requires_grad_(True)
+        if fused:
+            y = ops.conv_bn_act(x, wt, stride, pad, dil, bn, act, r, b)
+            assert type(y.grad_fn).__name__.startswith("ConvBnAct")
+        else:
+            y = ops.conv_bn_act(x, wt, stride, pad, dil, bn, act, r, b)
+            assert type(y.grad_fn).__name__.startswith("BatchNormAct")
+        ops._CONV_BN_MIN_K = 1 << 30
+        y.backward(dy)
+        outs.append(dict(y=y.detach(), dx=x.grad, dw=wt.grad, dg=bn.weight.grad, db=bn.bias.grad, rm=bn.running_mean.clone(),
+                         rv=bn.running_var.clone(), dr=None if r is None else r.grad, nbt=int(bn.num_batches_tracked)))
+    a, b_ = outs
+    assert a["nbt"] == b_["nbt"] == 1
+    assert rel(a["rm"], b_["rm"]) < 1e-4 and rel(a["rv"], b_["rv"]) < 1e-4
+    assert rel(a["y"].float(), b_["y"].float()) < 1e-2          # one bf16 ulp where scale/shift differ in the last bit
+    assert rel(a["dx"].float(), b_["dx"].float()) < 2e-2
+    assert rel(a["dw"], b_["dw"]) < 2e-2
+    assert rel(a["dg"], b_["dg"]) < 1e-2 and rel(a["db"], b_["db"]) < 1e-2
+    if with_res:
+        assert rel(a["dr"].float(), b_["dr"].float()) < 1e-2
