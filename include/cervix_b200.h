@@ -315,8 +315,8 @@ CVX_API int cvx_split_patches(const float* images, void* patches, int n, int c, 
                               const float* mean, const float* std, int dtype, void* stream);
 /* Tail of the segmentation loader on the device (reference: SEG/utils/dataloader.py:40-42 + utils/utils.py:63-65
  * preprocess_input): images_u8 (n_image_elems bytes, [n][h][w][3] as PIL / numpy hold them, 16-byte aligned) -> NHWC
- * activation in `dtype` scaled by 1/255; labels_u8 (n_pixels bytes, nullable together with labels_out) -> int64 with
- * values >= num_classes set to num_classes (the ignore label).  The one-hot expansion of :47 is implicit in
+ * activation in `dtype` scaled by 1/255 (nullable together with images_out); labels_u8 (n_pixels bytes, nullable together
+ * with labels_out) -> int64 with values >= num_classes set to num_classes (the ignore label).  The one-hot expansion of :47 is implicit in
  * cvx_seg_loss_* (onehot == NULL). */
 CVX_API int cvx_finish_batch_u8(const unsigned char* images_u8, void* images_out, int64_t n_image_elems,
                                 const unsigned char* labels_u8, int64_t* labels_out, int64_t n_pixels, int num_classes,

@@ -105,12 +105,13 @@ class CudaBackend:
         """uint8 [n,h,w,3] pixels (+ uint8 [n,h,w] class map) -> (NHWC activation / 255 in `dtype`, int64 class map
         with values >= num_classes clamped to num_classes) - the loader tail of dataloader.py:40-42 on the device."""
         self._chk(images_u8, labels_u8)
-        if images_u8.dtype != torch.uint8 or (labels_u8 is not None and labels_u8.dtype != torch.uint8):
+        if any(t is not None and t.dtype != torch.uint8 for t in (images_u8, labels_u8)):
             raise TypeError("finish_batch_u8: uint8 tensors expected")
-        x = torch.empty(images_u8.shape, dtype=dtype, device=images_u8.device)
+        x = None if images_u8 is None else torch.empty(images_u8.shape, dtype=dtype, device=images_u8.device)
         t = None if labels_u8 is None else torch.empty(labels_u8.shape, dtype=torch.int64, device=labels_u8.device)
-        check(self.lib.cvx_finish_batch_u8(_p(images_u8), _p(x), images_u8.numel(), _p(labels_u8), _p(t),
-                                           0 if labels_u8 is None else labels_u8.numel(), num_classes, _dt(x),
+        check(self.lib.cvx_finish_batch_u8(_p(images_u8), _p(x), 0 if images_u8 is None else images_u8.numel(), _p(labels_u8), _p(t),
+                                           0 if labels_u8 is None else labels_u8.numel(), num_classes,
+                                           _lib.BF16 if dtype == torch.bfloat16 else _lib.F32,
                                            self._stream()), "cvx_finish_batch_u8")
         return x, t
 

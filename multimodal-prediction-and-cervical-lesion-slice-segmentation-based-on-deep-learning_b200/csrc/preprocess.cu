@@ -150,14 +150,19 @@ extern "C" int cvx_split_patches(const float* images, void* patches, int n, int 
 extern "C" int cvx_finish_batch_u8(const unsigned char* images_u8, void* images_out, int64_t n_image_elems,
                                    const unsigned char* labels_u8, int64_t* labels_out, int64_t n_pixels,
                                    int num_classes, int dtype, void* stream) {
-  CVX_CHECK_ARG(images_u8 && images_out && n_image_elems > 0, "finish_batch_u8: bad image arguments");
+  CVX_CHECK_ARG((images_u8 == nullptr) == (images_out == nullptr), "finish_batch_u8: images in/out must both be given or both be NULL");
   CVX_CHECK_ARG((labels_u8 == nullptr) == (labels_out == nullptr), "finish_batch_u8: labels in/out must both be given or both be NULL");
-  CVX_CHECK_ARG(((uintptr_t)images_u8 & 15) == 0, "finish_batch_u8: image buffer must be 16-byte aligned");
-  const int64_t nvec = n_image_elems / 16;
-  const unsigned grid = stream_grid(nvec > 0 ? nvec : n_image_elems, 256);
-  CVX_DISPATCH_DTYPE(dtype, T, (u8_to_unit_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(images_u8, (T*)images_out, nvec,
-                                                                                         n_image_elems)));
-  CVX_LAUNCH_OK();
+  CVX_CHECK_ARG(images_u8 || labels_u8, "finish_batch_u8: nothing to do");
+  if (images_u8) {
+    CVX_CHECK_ARG(n_image_elems > 0, "finish_batch_u8: bad image element count");
+    CVX_CHECK_ARG(((uintptr_t)images_u8 & 15) == 0 && ((uintptr_t)images_out & 15) == 0,
+                  "finish_batch_u8: image buffers must be 16-byte aligned");
+    const int64_t nvec = n_image_elems / 16;
+    const unsigned grid = stream_grid(nvec > 0 ? nvec : n_image_elems, 256);
+    CVX_DISPATCH_DTYPE(dtype, T, (u8_to_unit_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(images_u8, (T*)images_out, nvec,
+                                                                                           n_image_elems)));
+    CVX_LAUNCH_OK();
+  }
   if (labels_u8) {
     CVX_CHECK_ARG(n_pixels > 0 && num_classes >= 1 && num_classes <= 255, "finish_batch_u8: bad label arguments");
     u8_labels_kernel<<<stream_grid(n_pixels, 256), 256, 0, as_stream(stream)>>>(labels_u8, labels_out, n_pixels, num_classes);

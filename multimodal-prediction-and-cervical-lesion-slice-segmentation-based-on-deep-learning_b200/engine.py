@@ -177,7 +177,8 @@ class SegTrainer:
 
     # ------------------------------------------------------------------ step
     def step(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None):
-        """imgs: fp32 NCHW in [0,1]; pngs: int64 class map (num_classes = ignore); labels: the
+        """imgs: fp32 NCHW in [0,1] (or the decoded uint8 [B,H,W,3] pixels); pngs: int64 class map (num_classes =
+        ignore; or the uint8 class map as read from the PNG, clamped on the device); labels: the
         reference's fp32 one-hot [B,H,W,C+1] (optional).  Returns the 4-vector
         (ce, focal, dice, f_score) as a device tensor (no host sync)."""
         losses = self._forward_backward(imgs, pngs, labels)
@@ -191,6 +192,8 @@ class SegTrainer:
         else:
             self.flat.attach_grad_views()
             self.flat.grad.zero_()
+        if pngs.dtype == torch.uint8:      # loader tail on the device: png[png >= num_classes] = num_classes, as int64
+            pngs = get_backend().finish_batch_u8(None, pngs.contiguous(), self.num_classes, torch.float32)[1]
         self.step_dev.add_(1)
         ops.set_step_counter(self.step_dev)
         with ops.defer_batch_counters():

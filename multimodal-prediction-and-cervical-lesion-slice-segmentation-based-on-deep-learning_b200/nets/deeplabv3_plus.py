@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..backend import get_backend
 from .mobilenetv2 import mobilenetv2
 from .xception import xception
 
@@ -121,7 +122,12 @@ class DeepLab(nn.Module):
 
     def forward_lowres(self, x):
         """Logits before the final x4 bilinear upsample, NHWC in the engine dtype."""
-        x = ops.to_nhwc(x, self._cervix_dtype)
+        if x.dtype == torch.uint8:
+            # decoded pixels as PIL / numpy hold them, [B,H,W,3] uint8: /255 (utils.preprocess_input) and the layout
+            # the stem reads in one pass - the loader's float conversion and NCHW transpose (dataloader.py:40) skipped
+            x = get_backend().finish_batch_u8(x.contiguous(), None, 0, self._cervix_dtype)[0]
+        else:
+            x = ops.to_nhwc(x, self._cervix_dtype)
         low_level_features, x = self.backbone(x)
         x = self.aspp(x)
         low_level_features = _conv_bn_relu(low_level_features, self.shortcut_conv)
@@ -135,5 +141,5 @@ class DeepLab(nn.Module):
         return ops.conv2d(x, c.weight, c.bias, 1, 0, 1)
 
     def forward(self, x):
-        H, W = x.size(2), x.size(3)
+        H, W = (x.size(1), x.size(2)) if x.dtype == torch.uint8 else (x.size(2), x.size(3))
         return ops.upsample_to_nchw(self.forward_lowres(x), H, W)

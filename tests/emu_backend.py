@@ -40,7 +40,7 @@ class EmuBackend:
         return x.reshape(b * k * k, patch, patch, c).contiguous().to(dtype)
 
     def finish_batch_u8(self, images_u8, labels_u8, num_classes, dtype):
-        x = (images_u8.float() * (1.0 / 255.0)).to(dtype)
+        x = None if images_u8 is None else (images_u8.float() * (1.0 / 255.0)).to(dtype)
         t = None if labels_u8 is None else labels_u8.long().clamp(max=num_classes)
         return x, t
 

@@ -23,3 +23,35 @@ def test_batch_prefetcher_double_buffers_keep_batches_intact():
     assert seen == 6
     for i, (sa, sb) in enumerate(sums):
         assert float(sa) == i * 4 * 3 * 64 * 64 and int(sb) == i * 4 * 64 * 64
+
+
+def test_uint8_batches_match_the_float_contract():
+    """The decoded uint8 [B,H,W,3] pixels + uint8 class map (what the reference's loader holds before its float
+    conversion, dataloader.py:40-42) against the fp32 NCHW / int64 tensors the loader hands to fit_one_epoch."""
+    import numpy as np
+    from cervix_b200.engine import SegTrainer
+    from cervix_b200.nets.deeplabv3_plus import DeepLab
+    rng = np.random.RandomState(0)
+    u8 = torch.from_numpy(rng.randint(0, 256, (2, 64, 64, 3), dtype=np.uint8)).cuda()
+    lab = rng.randint(0, 5, (2, 64, 64)).astype(np.uint8)
+    lab[0, :4] = 255                                          # VOC-style white border -> ignore label
+    lab_u8 = torch.from_numpy(lab).cuda()
+    f32 = (u8.float() / 255.0).permute(0, 3, 1, 2).contiguous()
+    i64 = lab_u8.long().clamp(max=5)
+    torch.manual_seed(0)
+    model = DeepLab(5, "mobilenet", False, 16).set_compute_dtype(torch.bfloat16).cuda().eval()
+    with torch.no_grad():
+        a, b = model(u8), model(f32)
+    assert a.shape == b.shape == (2, 5, 64, 64)
+    assert torch.equal(a, b)                                  # same bf16 activations enter the stem
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    model.train()
+    tr = SegTrainer(model, lr=0.0, cls_weights=[1, 1, 5, 3, 4])
+    la = tr.step(u8, lab_u8).clone()
+    ga = tr.flat.grad.clone()
+    lb = tr.step(f32, i64).clone()
+    # same inputs reach the same kernels; the only differences are the summation order of the atomics
+    assert float((la - lb).abs().max()) <= 1e-5 * float(lb.abs().max())
+    assert float((ga - tr.flat.grad).abs().max()) <= 1e-3 * float(tr.flat.grad.abs().max())
