@@ -158,7 +158,7 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- four-modal classifier leg
 def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int = 512, world: int = 1, rank: int = 0,
-                          variants=(("imgN", "imgA", "imgL", "cli"),)):
+                          variants=(("imgN", "imgA", "imgL", "cli"),), use_graph: bool = True):
     """BASELINE configs[1] (N=1, 16 patients) / configs[4] (N>1, `patients` per GPU, fusion-head gradients all-reduced
     over NCCL): one training step of the severity classifier on `patients` patients per rank - the colposcopic
     images of each patient (resize 1024 -> 16 patches of 256 -> frozen ResNet-101 encoder, as
@@ -212,15 +212,27 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
                 feats["cli"] = cli
             return feats
 
-        for _ in range(warmup):
-            trainer.step(encode(), edges, labels, masks)
+        def draw_masks():
+            mk = np.ones((patients, len(types)), dtype=bool)
+            mk[np.arange(patients), rng.randint(0, len(types), patients)] = False
+            return mk
+
+        # the head's step is ~600 launches of a few microseconds: captured once as a CUDA graph (new masks, dropout
+        # streams and Adam step count reach every replay through device memory), eager with --no-graph
+        if use_graph:
+            trainer.capture(encode(), edges, labels, masks, warmup=max(warmup, 1))
+            head_step = lambda f: trainer.step_graphed(f, labels, draw_masks())      # noqa: E731
+        else:
+            for _ in range(warmup):
+                trainer.step(encode(), edges, labels, masks)
+            head_step = lambda f: trainer.step(f, edges, labels, draw_masks())       # noqa: E731
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         enc_ms = head_ms = 0.0
         for _ in range(steps):
-            ev[0].record(); f = encode(); ev[1].record(); loss = trainer.step(f, edges, labels, masks); ev[2].record()
+            ev[0].record(); f = encode(); ev[1].record(); loss = head_step(f); ev[2].record()
             torch.cuda.synchronize()
             enc_ms += ev[0].elapsed_time(ev[1]); head_ms += ev[1].elapsed_time(ev[2])
         t = torch.tensor([enc_ms / steps, head_ms / steps], dtype=torch.float64, device="cuda")
@@ -240,6 +252,7 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
                        % (len(results[0]["modalities"]), patients, 3, size, size, "NCCL all-reduce + " if world > 1 else "",
                           1 if world == 1 else 4))
     out["global_patients"] = world * patients
+    out["head_cuda_graph"] = bool(use_graph)
     if len(results) > 1:
         out["variants"] = results[1:]
     return out
@@ -394,7 +407,8 @@ def run_ours(args):
         torch.cuda.empty_cache()
         classifier = classifier_throughput(max(2, min(args.steps, 4)), 2, patients=16 if world == 1 else 64,
                                            world=world, rank=rank,
-                                           variants=(("imgN", "imgA", "imgL", "cli"), ("imgN", "imgA", "imgL"), ("imgN", "imgL")))
+                                           variants=(("imgN", "imgA", "imgL", "cli"), ("imgN", "imgA", "imgL"), ("imgN", "imgL")),
+                                           use_graph=use_graph)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -254,11 +254,13 @@ CVX_API int cvx_gate_pool_fwd(const float* x, const float* gate, float* pooled, 
                       void* stream);
 CVX_API int cvx_gate_pool_bwd(const float* dpooled, const float* x, const float* att, float* dx, float* dgate, int groups,
                       int seg, int c, void* stream);
-/* multi-head attention over <= 8 tokens (mae_utils.py:58-102): qkv [b,n,3,h,d] -> out [b,n,h*d], probs [b,h,n,n] */
+/* multi-head attention over <= 8 tokens (mae_utils.py:58-102): qkv [b,n,3,h,d] -> out [b,n,h*d], probs [b,h,n,n].
+ * step_dev (nullable device int) is mixed into the attention-dropout seed, as in cvx_dropout_fwd, so that a CUDA-graph
+ * replay draws a new mask every step; forward and backward of one step must see the same value. */
 CVX_API int cvx_attn_small_fwd(const float* qkv, float* out, float* probs, int b, int n, int h, int d, float scale,
-                       float drop_p, uint64_t seed, void* stream);
+                       float drop_p, uint64_t seed, const int* step_dev, void* stream);
 CVX_API int cvx_attn_small_bwd(const float* dout, const float* qkv, const float* probs, float* dqkv, int b, int n, int h,
-                       int d, float scale, float drop_p, uint64_t seed, void* stream);
+                       int d, float scale, float drop_p, uint64_t seed, const int* step_dev, void* stream);
 /* F.normalize(dim=1) (my_mae_model.py:679) */
 CVX_API int cvx_l2norm_fwd(const float* x, float* y, float* norms, int rows, int c, void* stream);
 CVX_API int cvx_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int rows, int c, void* stream);

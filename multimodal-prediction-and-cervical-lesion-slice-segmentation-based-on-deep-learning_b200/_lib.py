@@ -90,8 +90,8 @@ PROTOTYPES = {
     "cvx_graph_gather": [_P, _P, _I, _I, _I, _P, _P, _P, _P],
     "cvx_gate_pool_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "cvx_gate_pool_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
-    "cvx_attn_small_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, _P],
-    "cvx_attn_small_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, _P],
+    "cvx_attn_small_fwd": [_P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, _P, _P],
+    "cvx_attn_small_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, _P, _P],
     "cvx_l2norm_fwd": [_P, _P, _P, _I, _I, _P],
     "cvx_l2norm_bwd": [_P, _P, _P, _P, _I, _I, _P],
     "cvx_rows_gather": [_P, _P, _P, _P, _I, _I, _P],

@@ -459,19 +459,19 @@ class CudaBackend:
               "cvx_gate_pool_bwd")
         return dx, dgate
 
-    def attn_small_fwd(self, qkv, b: int, n: int, h: int, d: int, scale: float, drop_p: float, seed: int):
-        self._chk(qkv)
+    def attn_small_fwd(self, qkv, b: int, n: int, h: int, d: int, scale: float, drop_p: float, seed: int, step_dev=None):
+        self._chk(qkv, step_dev)
         out = torch.empty((b, n, h * d), dtype=torch.float32, device=qkv.device)
         probs = torch.empty((b, h, n, n), dtype=torch.float32, device=qkv.device)
         check(self.lib.cvx_attn_small_fwd(_p(qkv), _p(out), _p(probs), b, n, h, d, float(scale), float(drop_p),
-                                          int(seed) & (2 ** 64 - 1), self._stream()), "cvx_attn_small_fwd")
+                                          int(seed) & (2 ** 64 - 1), _p(step_dev), self._stream()), "cvx_attn_small_fwd")
         return out, probs
 
-    def attn_small_bwd(self, dout, qkv, probs, b, n, h, d, scale, drop_p, seed):
-        self._chk(dout, qkv, probs)
+    def attn_small_bwd(self, dout, qkv, probs, b, n, h, d, scale, drop_p, seed, step_dev=None):
+        self._chk(dout, qkv, probs, step_dev)
         dqkv = torch.empty_like(qkv)
         check(self.lib.cvx_attn_small_bwd(_p(dout), _p(qkv), _p(probs), _p(dqkv), b, n, h, d, float(scale), float(drop_p),
-                                          int(seed) & (2 ** 64 - 1), self._stream()), "cvx_attn_small_bwd")
+                                          int(seed) & (2 ** 64 - 1), _p(step_dev), self._stream()), "cvx_attn_small_bwd")
         return dqkv
 
     def l2norm_fwd(self, x):

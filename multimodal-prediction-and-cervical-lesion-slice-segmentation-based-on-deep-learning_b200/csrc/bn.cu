@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
     const double* __restrict__ acc, T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int act,
@@ -151,17 +151,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= stride_vecs) return;
   const int c0 = (int)(e % cvn) * VEC;
-  float k[VEC], mu[VEC], is[VEC], m1[VEC], m2[VEC], sh[VEC];
+  // dx = k (dz - m1 - xhat m2) with xhat = (x - mu) is  ==  k dz + bx x + cx : three per-channel constants (+ the
+  // forward's shift for the recomputed mask) instead of five - ncu showed this kernel at 33 % warp occupancy, limited
+  // by its 80 registers; with 64 a fourth block is resident per SM
+  float k[VEC], bx[VEC], cx[VEC], sh[VEC];
   const float inv_n = 1.0f / (float)rows;
   const bool from_y = act != CVX_ACT_NONE && beta == nullptr;   // else the mask is recomputed from x (forward's fma)
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    mu[i] = mean[c0 + i];
-    is[i] = invstd[c0 + i];
-    k[i] = gamma[c0 + i] * is[i];
-    sh[i] = beta ? beta[c0 + i] - mu[i] * k[i] : 0.f;
-    m1[i] = training ? (float)(acc[c0 + i] * (double)inv_n) : 0.f;
-    m2[i] = training ? (float)(acc[C + c0 + i] * (double)inv_n) : 0.f;
+    const float mu = mean[c0 + i], is = invstd[c0 + i];
+    k[i] = gamma[c0 + i] * is;
+    sh[i] = beta ? beta[c0 + i] - mu * k[i] : 0.f;
+    const float m1 = training ? (float)(acc[c0 + i] * (double)inv_n) : 0.f;
+    const float m2 = training ? (float)(acc[C + c0 + i] * (double)inv_n) : 0.f;
+    bx[i] = -k[i] * m2 * is;
+    cx[i] = -k[i] * m1 - bx[i] * mu;
   }
   for (; e < total; e += stride_vecs) {
     Vec<T> g, xv, yv;
@@ -173,8 +177,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       float dz = g.v[i];
       if (act != CVX_ACT_NONE) dz *= act_mask(from_y ? yv.v[i] : fmaf(xv.v[i], k[i], sh[i]), act);
       g.v[i] = dz;
-      const float xhat = (xv.v[i] - mu[i]) * is[i];
-      xv.v[i] = k[i] * (dz - m1[i] - xhat * m2[i]);
+      xv.v[i] = fmaf(k[i], dz, fmaf(bx[i], xv.v[i], cx[i]));
     }
     xv.store(dx + e * VEC);
     if (dres) g.store(dres + e * VEC);

@@ -166,9 +166,11 @@ __device__ __forceinline__ float hash_uniform(uint64_t z) {
 }
 
 __global__ void attn_small_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ probs,
-                                      int B, int N, int H, int D, float scale, float drop_p, uint64_t seed) {
+                                      int B, int N, int H, int D, float scale, float drop_p, uint64_t seed,
+                                      const int* __restrict__ step_dev) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= B * H) return;
+  if (step_dev) seed += 0x9e3779b97f4a7c15ull * (uint64_t)(*step_dev);  // per-step stream under CUDA-graph replay
   const int b = wid / H, h = wid % H;
   const size_t tok = (size_t)3 * H * D;  // stride between tokens
   const float* base = qkv + (size_t)b * N * tok + (size_t)h * D;
@@ -203,7 +205,8 @@ __global__ void attn_small_fwd_kernel(const float* __restrict__ qkv, float* __re
 
 __global__ void attn_small_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                       const float* __restrict__ probs, float* __restrict__ dqkv, int B, int N, int H, int D,
-                                      float scale, float drop_p, uint64_t seed) {
+                                      float scale, float drop_p, uint64_t seed, const int* __restrict__ step_dev) {
+  if (step_dev) seed += 0x9e3779b97f4a7c15ull * (uint64_t)(*step_dev);
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= B * H) return;
   const int b = wid / H, h = wid % H;
@@ -411,20 +414,20 @@ int cvx_gate_pool_bwd(const float* dpooled, const float* x, const float* att, fl
 }
 
 int cvx_attn_small_fwd(const float* qkv, float* out, float* probs, int b, int n, int h, int d, float scale, float drop_p,
-                       uint64_t seed, void* stream) {
+                       uint64_t seed, const int* step_dev, void* stream) {
   CVX_CHECK_ARG(qkv && out && probs && b > 0 && n > 0 && n <= kMaxTok && h > 0 && d > 0 && drop_p >= 0.f && drop_p < 1.f,
                 "attn_small_fwd: bad arguments (at most %d tokens)", kMaxTok);
   const int warps = b * h;
-  attn_small_fwd_kernel<<<(warps * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(qkv, out, probs, b, n, h, d, scale, drop_p, seed);
+  attn_small_fwd_kernel<<<(warps * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(qkv, out, probs, b, n, h, d, scale, drop_p, seed, step_dev);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_attn_small_bwd(const float* dout, const float* qkv, const float* probs, float* dqkv, int b, int n, int h, int d,
-                       float scale, float drop_p, uint64_t seed, void* stream) {
+                       float scale, float drop_p, uint64_t seed, const int* step_dev, void* stream) {
   CVX_CHECK_ARG(dout && qkv && probs && dqkv && b > 0 && n > 0 && n <= kMaxTok && h > 0 && d > 0, "attn_small_bwd: bad arguments");
   const int warps = b * h;
-  attn_small_bwd_kernel<<<(warps * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(dout, qkv, probs, dqkv, b, n, h, d, scale, drop_p, seed);
+  attn_small_bwd_kernel<<<(warps * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(dout, qkv, probs, dqkv, b, n, h, d, scale, drop_p, seed, step_dev);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

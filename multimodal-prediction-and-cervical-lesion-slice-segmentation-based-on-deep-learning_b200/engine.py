@@ -293,21 +293,80 @@ class FusionTrainer:
         self.t = 0
         self.world = world_size
 
-    def step(self, feats, edges, labels: torch.Tensor, masks, use_types=None, mix: bool = True) -> torch.Tensor:
-        """feats[m]: ``[G, nodes_m, 1024]`` node features of this rank's G patients; masks: bool ``[G, T]`` (True =
-        masked modality).  Returns this rank's loss (device scalar, no host sync)."""
+    def _forward_backward(self, feats, edges, labels, masks, use_types=None, mix: bool = True):
         from .multimodal.my_mae_model import fusion_objective
         self.flat.attach_grad_views()
         self.flat.grad.zero_()
         out = self.head.forward_batch(feats, edges, self.train_types, use_types or self.train_types, masks, mix)
         loss = fusion_objective(out, labels, masks)
         loss.backward()
+        return loss.detach()
+
+    def step(self, feats, edges, labels: torch.Tensor, masks, use_types=None, mix: bool = True) -> torch.Tensor:
+        """feats[m]: ``[G, nodes_m, 1024]`` node features of this rank's G patients; masks: bool ``[G, T]`` (True =
+        masked modality).  Returns this rank's loss (device scalar, no host sync)."""
+        loss = self._forward_backward(feats, edges, labels, masks, use_types, mix)
         if self.world > 1:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
         self.t += 1
         get_backend().adam_step(self.flat.data, self.flat.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1],
                                 self.eps, self.wd, self.t, 1.0 / self.world)
-        return loss.detach()
+        return loss
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    def capture(self, feats, edges, labels: torch.Tensor, masks, warmup: int = 2):
+        """Capture the head's train step (~600 launches of a few microseconds each: the eager step is bound by the
+        host, not the GPU) into a CUDA graph over static copies of the inputs.  The modality masks enter through a
+        ``MaskPlan`` whose device-side index tables the graph re-reads, the dropout / attention-dropout streams and
+        Adam's step count through a device counter, so every replay is a fresh training step.  Data parallel: forward
+        + backward are captured; the all-reduce and the fused Adam follow each replay."""
+        from .multimodal.my_mae_model import MaskPlan
+        dev = self.flat.data.device
+        self.s_feats = {m: t.detach().clone() for m, t in feats.items()}
+        self.s_edges = edges
+        self.s_labels = labels.clone()
+        self.plan = MaskPlan(masks, dev)
+        self.step_dev = torch.full((1,), self.t, dtype=torch.int32, device=dev)
+        self.hyper_dev = torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1.0 / self.world],
+                                      dtype=torch.float32, device=dev)
+
+        def body():
+            self.step_dev.add_(1)
+            ops.set_step_counter(self.step_dev)
+            loss = self._forward_backward(self.s_feats, self.s_edges, self.s_labels, self.plan)
+            if self.world == 1:
+                get_backend().adam_step_dev(self.flat.data, self.flat.grad, self.m, self.v, self.hyper_dev, self.step_dev)
+            return loss
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                body()
+                if self.world > 1:
+                    self._reduce_and_update_dev()
+                self.t += 1
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.s_loss = body()
+        # (the capture itself does not execute: step_dev still equals the number of steps taken)
+        return self
+
+    def _reduce_and_update_dev(self):
+        dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
+        get_backend().adam_step_dev(self.flat.data, self.flat.grad, self.m, self.v, self.hyper_dev, self.step_dev)
+
+    def step_graphed(self, feats, labels: torch.Tensor, masks) -> torch.Tensor:
+        for m, t in feats.items():
+            self.s_feats[m].copy_(t, non_blocking=True)
+        self.s_labels.copy_(labels, non_blocking=True)
+        self.plan.update(masks)
+        self.graph.replay()
+        if self.world > 1:
+            self._reduce_and_update_dev()
+        self.t += 1
+        return self.s_loss
 
 
 class BatchPrefetcher:

@@ -18,6 +18,7 @@ restated by the kernels and pinned by tests/golden/fusion_*.npz.
 """
 from __future__ import annotations
 
+import collections
 import math
 from typing import Dict, List, Optional, Sequence
 
@@ -31,6 +32,51 @@ from . import rowops as R
 MODALITIES = ("imgN", "imgA", "imgL", "cli")
 _EDGE_ATTR = {"imgN": "edge_index_imageN", "imgA": "edge_index_imageA", "imgL": "edge_index_imageL",
               "cli": "edge_index_cli"}
+
+
+# ----------------------------------------------------------------------------- modality-mask index tables
+class MaskPlan:
+    """Device-side index tables of one batch's modality masks (``[G, T]`` bool, True = masked; every patient has the
+    same number of visible modalities, as ``generate_mask`` guarantees): which rows the MAE encoder keeps
+    (``x[~mask]``, my_mae_model.py:143), how the decoder input is assembled from visible tokens and mask tokens, the
+    position row of every decoder token, the un-shuffle back to modality order (:325-335) and the 0/1 selector of the
+    masked rows for the reconstruction loss (my_train(full).py:253).  The tensors keep their addresses, so a captured
+    CUDA graph of the train step reads new masks after ``update``."""
+
+    def __init__(self, masks, device):
+        masks = np.asarray(masks, dtype=bool)
+        self.G, self.T = masks.shape
+        self.device = device
+        self.n_vis = int((~masks[0]).sum())
+        lists, sel = self._lists(masks)
+        self.tables = torch.tensor(lists, dtype=torch.int32, device=device)        # [4, G*T] (vis_idx is padded)
+        self.sel = torch.tensor(sel, dtype=torch.uint8, device=device)
+        n = self.G * self.n_vis
+        self.vis_idx, self.dec_idx = self.tables[0, :n], self.tables[1]
+        self.dec_pos, self.unshuffle = self.tables[2], self.tables[3]
+
+    def _lists(self, masks):
+        G, T, n_vis = self.G, self.T, self.n_vis
+        if masks.shape != (G, T) or any(int((~m).sum()) != n_vis for m in masks):
+            raise ValueError("all patients of a batch must have the same number of visible modalities")
+        vis_idx, dec_idx, dec_pos, unshuffle = [], [], [], []
+        for g in range(G):
+            vis = [t for t in range(T) if not masks[g, t]]
+            msk = [t for t in range(T) if masks[g, t]]
+            vis_idx += [g * T + t for t in vis]
+            dec_idx += [g * n_vis + j for j in range(n_vis)] + [-1] * len(msk)
+            dec_pos += vis + msk
+            slot = {t: j for j, t in enumerate(vis + msk)}
+            unshuffle += [g * T + slot[t] for t in range(T)]
+        vis_idx += [0] * (G * T - len(vis_idx))
+        return [vis_idx, dec_idx, dec_pos, unshuffle], masks.reshape(-1).astype(np.uint8).tolist()
+
+    def update(self, masks):
+        """New masks of the same shape and visible count into the same device tensors (two small H2D copies)."""
+        lists, sel = self._lists(np.asarray(masks, dtype=bool))
+        self.tables.copy_(torch.tensor(lists, dtype=torch.int32))
+        self.sel.copy_(torch.tensor(sel, dtype=torch.uint8))
+        return self
 
 
 # ----------------------------------------------------------------------------- parameter holders
@@ -191,6 +237,7 @@ class fusion_model_mae_2(nn.Module):
         self.train_type_num = train_type_num
         self._topo: Dict[tuple, R.GraphTopology] = {}
         self._const: Dict[tuple, torch.Tensor] = {}
+        self._plans: "collections.OrderedDict[tuple, MaskPlan]" = collections.OrderedDict()
 
     # ------------------------------------------------------------------ helpers
     def _topology(self, edge_index, nodes: int, device) -> R.GraphTopology:
@@ -232,36 +279,37 @@ class fusion_model_mae_2(nn.Module):
         h = R.linear(R.gelu(R.linear(R.layernorm(x, blk.norm2), blk.mlp.fc1)), blk.mlp.fc2)
         return ops.Add.apply(x, h)
 
-    def _mae(self, tokens, masks: np.ndarray):
-        """tokens [G*T, C] (modality order); masks [G, T] bool, True = masked.  Every patient of the batch must
-        have the same number of visible tokens (the training mask has exactly one, generate_mask mae_utils.py:11-21).
-        Returns the reconstructed tokens [G*T, C] in modality order (my_mae_model.py:305-335)."""
-        G, T = masks.shape
+    def _plan(self, masks: np.ndarray, device) -> MaskPlan:
+        """MaskPlan of a numpy mask batch, from a small LRU cache (training draws new masks every step)."""
+        masks = np.asarray(masks, dtype=bool)
+        key = (str(device), masks.shape, masks.tobytes())
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._plans[key] = MaskPlan(masks, device)
+            if len(self._plans) > 64:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        return plan
+
+    def _mae(self, tokens, plan: MaskPlan):
+        """tokens [G*T, C] (modality order); plan: the index tables of the batch's masks.  Returns the reconstructed
+        tokens [G*T, C] in modality order (my_mae_model.py:305-335)."""
+        G, T, n_vis = plan.G, plan.T, plan.n_vis
         dev = tokens.device
-        n_vis = int((~masks[0]).sum())
-        if any(int((~m).sum()) != n_vis for m in masks):
-            raise ValueError("all patients of a batch must have the same number of visible modalities")
         mae = self.mae
-        vis_idx, vis_pos, dec_idx, dec_pos, unshuffle = [], [], [], [], []
-        for g in range(G):
-            vis = [t for t in range(T) if not masks[g, t]]
-            msk = [t for t in range(T) if masks[g, t]]
-            vis_idx += [g * T + t for t in vis]
-            dec_idx += [g * n_vis + j for j in range(n_vis)] + [-1] * len(msk)
-            dec_pos += vis + msk
-            slot = {t: j for j, t in enumerate(vis + msk)}
-            unshuffle += [g * T + slot[t] for t in range(T)]
         x = R.linear(tokens, mae.encoder.patch_embed)
         x = ops.Add.apply(x, self._pos_rows(list(range(T)) * G, dev))
-        x = R.RowsGather.apply(x, self._idx(vis_idx, dev), None)                       # x[~mask]
+        x = R.RowsGather.apply(x, plan.vis_idx, None)                                  # x[~mask]
         x = self._block(x, mae.encoder.blocks[0], G, n_vis)
         x = R.linear(R.layernorm(x, mae.encoder.norm), mae.encoder_to_decoder)
         # decoder input: visible tokens first, then mask tokens, each plus its own position row
-        x = R.RowsGather.apply(x, self._idx(dec_idx, dev), mae.mask_token if n_vis < T else None)
-        x = ops.Add.apply(x, self._pos_rows(dec_pos, dev))
+        x = R.RowsGather.apply(x, plan.dec_idx, mae.mask_token if n_vis < T else None)
+        pos = R.RowsGather.apply(self._pos_rows(list(range(T)), dev), plan.dec_pos, None)
+        x = ops.Add.apply(x, pos)
         x = self._block(x, mae.decoder.blocks[0], G, T)
         x = R.linear(R.layernorm(x, mae.decoder.norm), mae.decoder.head)
-        return R.RowsGather.apply(x, self._idx(unshuffle, dev), None)
+        return R.RowsGather.apply(x, plan.unshuffle, None)
 
     def _mixer(self, x, G: int, T: int):
         """MixerBlock (my_mae_model.py:345-369) on [G*T, C]: the same graph-mode LayerNorm twice, token mixing on
@@ -284,9 +332,10 @@ class fusion_model_mae_2(nn.Module):
     # ------------------------------------------------------------------ batched forward
     def forward_batch(self, feats: Dict[str, torch.Tensor], edges: Dict[str, torch.Tensor],
                       train_use_type: Sequence[str], use_type: Optional[Sequence[str]] = None,
-                      masks: Optional[np.ndarray] = None, mix: bool = True) -> Dict[str, torch.Tensor]:
+                      masks=None, mix: bool = True) -> Dict[str, torch.Tensor]:
         """feats[m]: fp32 ``[G, nodes_m, in_feats]`` on the device; edges[m]: ``[2, E]`` topology shared by all
-        patients; masks: bool ``[G, T]`` over ``train_use_type`` (True = masked), None = nothing masked.
+        patients; masks: bool ``[G, T]`` over ``train_use_type`` (True = masked) as a numpy array or a ``MaskPlan``
+        (its device-side index tables, which a captured graph can re-read), None = nothing masked.
         Returns a dict of batched tensors: logits_all / logits_<m> ``[G, 4]``, one_x ``[G, 8]``, multi_x
         ``[G, T', 8]``, fea ``[G, T', 512]``, mae_out / mae_labels, att_2 / att_3 (lists of ``[G, nodes]``)."""
         train_use_type = list(train_use_type)
@@ -312,8 +361,14 @@ class fusion_model_mae_2(nn.Module):
         pool_x = (ops.cat_channels(pooled) if len(pooled) > 1 else pooled[0]).reshape(G * len(present), C)
         out = {"mae_labels": pool_x.reshape(G, len(present), C), "att_2": att_2}
         if Tt > 1:
+            plan = None
             if use_type == train_use_type:
-                mk = np.zeros((G, Tt), dtype=bool) if masks is None else np.asarray(masks, dtype=bool).reshape(G, Tt)
+                if isinstance(masks, MaskPlan):
+                    plan = masks
+                    if (plan.G, plan.T) != (G, Tt):
+                        raise ValueError("mask plan of shape (%d, %d) for a batch of (%d, %d)" % (plan.G, plan.T, G, Tt))
+                else:
+                    mk = np.zeros((G, Tt), dtype=bool) if masks is None else np.asarray(masks, dtype=bool).reshape(G, Tt)
                 tokens = pool_x
             else:
                 # inference with missing modalities (my_mae_model.py:597-612): absent tokens are zero and masked
@@ -328,7 +383,10 @@ class fusion_model_mae_2(nn.Module):
                     mk[:] = False
                 idx = [(-1 if s < 0 else g * len(present) + s) for g in range(G) for s in slot]
                 tokens = R.RowsGather.apply(pool_x, self._idx(idx, dev), None)
-            mae_x = self._mae(tokens, mk)
+            if plan is None:
+                plan = self._plan(mk, dev)
+            out["mask_plan"] = plan
+            mae_x = self._mae(tokens, plan)
             out["mae_out"] = mae_x.reshape(G, Tt, C)
             out["after_mae"] = mae_x.reshape(G, Tt, C)
             if mix:
@@ -392,14 +450,17 @@ class fusion_model_mae_2(nn.Module):
 MODALITY_LOSS_WEIGHT = {"imgN": 0.3, "imgA": 0.3, "imgL": 0.3, "cli": 0.2}
 
 
-def fusion_objective(out: Dict[str, torch.Tensor], labels: torch.Tensor, masks: np.ndarray, mse_factor: float = 5.0):
+def fusion_objective(out: Dict[str, torch.Tensor], labels: torch.Tensor, masks=None, mse_factor: float = 5.0):
     """my_train(full).py:309-347 for a batch of G patients: CE(all) + 0.3 CE(img*) + 0.2 CE(cli) on the stacked
     ``[G, 4]`` logits + sum_g mse_factor * MSE(mae_out[g][masked], pool_x[g][masked]) / G / 5."""
     present = out["present"]
     G, T, C = out["mae_out"].shape
-    masks = np.asarray(masks, dtype=bool).reshape(G, T)
-    n_masked = int(masks[0].sum())
-    sel = torch.from_numpy(masks.reshape(-1).astype(np.uint8)).to(labels.device)
+    # the masks are the ones forward_batch was given: their device-side tables travel in ``out`` (no host work here)
+    plan = masks if isinstance(masks, MaskPlan) else out.get("mask_plan")
+    if plan is None:
+        plan = MaskPlan(np.asarray(masks, dtype=bool).reshape(G, T), labels.device)
+    n_masked = T - plan.n_vis
+    sel = plan.sel
     logits = [out["logits_all"]] + [out["logits_" + m] for m in present]
     weights = [1.0] + [MODALITY_LOSS_WEIGHT[m] for m in present]
     inv_count = 1.0 / max(n_masked * C, 1)

@@ -118,9 +118,10 @@ class AttnSmall(Function):
     @staticmethod
     def forward(ctx, qkv, b, n, h, d, scale, drop_p, seed):
         qkv = qkv.contiguous()
-        out, probs = get_backend().attn_small_fwd(qkv, b, n, h, d, scale, drop_p, seed)
+        step_dev = ops._STEP_DEV[0] if drop_p > 0.0 else None      # graph replays: a new dropout mask every step
+        out, probs = get_backend().attn_small_fwd(qkv, b, n, h, d, scale, drop_p, seed, step_dev)
         ctx.save_for_backward(qkv, probs)
-        ctx.cfg = (b, n, h, d, scale, drop_p, seed)
+        ctx.cfg = (b, n, h, d, scale, drop_p, seed, step_dev)
         return out
 
     @staticmethod

@@ -487,11 +487,11 @@ class EmuBackend:
         p = ((q * scale) @ k.transpose(-2, -1)).softmax(-1)
         return (p @ v).transpose(1, 2).reshape(b, n, h * d), p
 
-    def attn_small_fwd(self, qkv, b, n, h, d, scale, drop_p, seed):
+    def attn_small_fwd(self, qkv, b, n, h, d, scale, drop_p, seed, step_dev=None):
         assert drop_p == 0.0, "the emulation backend covers the deterministic (eval) attention only"
         return self._attn(qkv, b, n, h, d, scale)
 
-    def attn_small_bwd(self, dout, qkv, probs, b, n, h, d, scale, drop_p, seed):
+    def attn_small_bwd(self, dout, qkv, probs, b, n, h, d, scale, drop_p, seed, step_dev=None):
         with torch.enable_grad():
             qi = qkv.detach().requires_grad_(True)
             self._attn(qi, b, n, h, d, scale)[0].backward(dout)

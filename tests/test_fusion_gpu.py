@@ -205,3 +205,48 @@ def test_age_node_features_on_device():
     got = mod.cuda()(ages, 20, 80)
     assert got.is_cuda and got.shape == (len(ages), 4, 1024)
     assert torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("types", [("imgN", "imgA", "imgL", "cli"), ("imgN", "imgL")])
+def test_graph_captured_train_step_equals_eager(types):
+    """FusionTrainer.capture / step_graphed (CUDA graph over static inputs, masks through a MaskPlan's device tables)
+    against the eager step on the same sequence of batches and masks; dropout off so both see the same function."""
+    from cervix_b200.engine import FusionTrainer
+    types = list(types)
+    T, G = len(types), 6
+    all_edges = {"imgN": get_edge_index_image(), "imgA": get_edge_index_image(), "imgL": get_edge_index_image(),
+                 "cli": get_edge_index_full(4)}
+    edges = {m: all_edges[m] for m in types}
+    rng = np.random.RandomState(1)
+
+    def batch(seed):
+        feats = {m: rnd(G, 4 if m == "cli" else 16, 1024, seed=seed * 10 + i) for i, m in enumerate(types)}
+        labels = torch.from_numpy(rng.randint(0, 4, G)).cuda()
+        masks = np.ones((G, T), dtype=bool)
+        masks[np.arange(G), rng.randint(0, T, G)] = False
+        return feats, labels, masks
+
+    batches = [batch(s) for s in range(4)]
+    trainers = []
+    for _ in range(2):
+        torch.manual_seed(0)
+        head = fusion_model_mae_2(1024, 512, 512, 0.3, T).cuda().eval()
+        trainers.append(FusionTrainer(head, types, lr=1e-3, weight_decay=1e-3))
+    eager, graphed = trainers
+    f0, l0, m0 = batches[0]
+    graphed.capture(f0, edges, l0, m0, warmup=2)               # two real steps on batch 0, then the capture
+    losses_e = [float(eager.step(f0, edges, l0, m0)) for _ in range(2)]
+    assert graphed.t == eager.t == 2
+    for f, l, m in batches[1:]:
+        le = float(eager.step(f, edges, l, m))
+        lg = float(graphed.step_graphed(f, l, m))
+        assert abs(le - lg) <= 2e-4 * abs(le), (le, lg)
+    assert graphed.t == eager.t == 5
+    diff = float((eager.flat.data - graphed.flat.data).abs().max())
+    assert diff < 2e-5, diff
+    # the masks really went through: a replay with other masks gives another loss on the same batch
+    f, l, m = batches[1]
+    a = float(graphed.step_graphed(f, l, m))
+    m2 = np.roll(m, 1, axis=1)
+    b = float(graphed.step_graphed(f, l, m2))
+    assert abs(a - b) > 1e-6

@@ -199,6 +199,12 @@ def test_small_ops(B, dtype):
     check(B.upsample_to_nchw_fwd(z, 24, 40), EMU.upsample_to_nchw_fwd(z, 24, 40), 1e-5 if dtype == torch.float32 else 1e-5, "to_nchw fwd")
     dz = rnd((2, 5, 24, 40), torch.float32, 7)
     check(B.upsample_to_nchw_bwd(dz, 6, 10, dtype), EMU.upsample_to_nchw_bwd(dz, 6, 10, dtype), tol(dtype), "to_nchw bwd")
+    # separable row kernel (up-sampling) on odd sizes, rows wider than a block, the identity size; gather kernel otherwise
+    for shape, (hi, wi) in (((3, 5, 37, 53), (10, 14)), ((1, 5, 128, 128), (32, 32)), ((1, 3, 40, 300), (10, 150)),
+                            ((2, 5, 6, 10), (6, 10)), ((1, 5, 6, 10), (12, 20)), ((1, 2, 64, 64), (1, 1))):
+        dz = rnd(shape, torch.float32, 8)
+        check(B.upsample_to_nchw_bwd(dz, hi, wi, dtype), EMU.upsample_to_nchw_bwd(dz, hi, wi, dtype), tol(dtype),
+              "to_nchw bwd %s -> %dx%d" % (shape, hi, wi))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
