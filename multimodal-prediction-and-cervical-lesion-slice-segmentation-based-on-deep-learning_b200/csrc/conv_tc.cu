@@ -873,10 +873,32 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     if ((MODE & 2) && epi_tid == 0)
       for (int i = 0; i < kSB - 1; ++i) side_issue();
     uint32_t tcount = 0, chunk_count = 0;
+    // MODE & 1: a warp's column sums of its 16 rows stay in registers (lane = one channel pair of each of the <= 4
+    // chunks of an output-channel tile) and go to the shared staging only when the output-channel tile changes - once
+    // per launch when C_out fits one tile.  (One shared fp32 atomic per value and chunk, eight warps on the same 64
+    // addresses, is a CAS loop per add: it cost ~1 800 cycles per chunk and doubled the time of short-K launches.)
+    float2 rs0 = make_float2(0.f, 0.f), rs1 = rs0, rs2 = rs0, rs3 = rs0, rq0 = rs0, rq1 = rs0, rq2 = rs0, rq3 = rs0;
+    int stats_nt = -1;
+    auto stats_flush = [&]() {
+      if (stats_nt < 0) return;
+      float* st = stats_sm + stats_nt * 512;
+      const int n0f = stats_nt * p.tile_n;
+      const float2 vs[4] = {rs0, rs1, rs2, rs3}, vq[4] = {rq0, rq1, rq2, rq3};
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int c = qq * 64 + 2 * lane;
+        if (c < p.tile_n && n0f + c < p.cout && (vq[qq].x != 0.f || vq[qq].y != 0.f)) {
+          atomicAdd(&st[c], vs[qq].x); atomicAdd(&st[c + 1], vs[qq].y);
+          atomicAdd(&st[256 + c], vq[qq].x); atomicAdd(&st[256 + c + 1], vq[qq].y);
+        }
+      }
+      rs0 = rs1 = rs2 = rs3 = rq0 = rq1 = rq2 = rq3 = make_float2(0.f, 0.f);
+    };
     for (int pt = pair; pt < total_pair_tiles; pt += npairs, ++tcount) {
       const int nt = pt % n_tiles;
       const int mtile = 2 * ((pt / n_tiles) * kPairs + (int)pidx) + (int)rank;
       const bool tile_ok = mtile < m_tiles;
+      if ((MODE & 1) && nt != stats_nt) { stats_flush(); stats_nt = nt; }
       int mt = tile_ok ? mtile : 0;
       const int tx = mt % p.tiles_x; mt /= p.tiles_x;
       const int ty = mt % p.tiles_y;
@@ -946,16 +968,15 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
             sm = __fadd2_rn(sm, v);
             sq = __ffma2_rn(v, v, sq);
           }
-          const int c = q * 64 + 2 * lane;
-          if (n0 + c < p.cout) {
-            float* st = stats_sm + nt * 512;
-            atomicAdd(&st[c], sm.x); atomicAdd(&st[c + 1], sm.y);
-            atomicAdd(&st[256 + c], sq.x); atomicAdd(&st[256 + c + 1], sq.y);
-          }
+          if (q == 0) { rs0 = __fadd2_rn(rs0, sm); rq0 = __fadd2_rn(rq0, sq); }
+          else if (q == 1) { rs1 = __fadd2_rn(rs1, sm); rq1 = __fadd2_rn(rq1, sq); }
+          else if (q == 2) { rs2 = __fadd2_rn(rs2, sm); rq2 = __fadd2_rn(rq2, sq); }
+          else { rs3 = __fadd2_rn(rs3, sm); rq3 = __fadd2_rn(rq3, sq); }
         }
         ++chunk_count;
       }
     }
+    if (MODE & 1) stats_flush();
     if (epi_tid == 0) bulk_wait_read<0>();
     if (MODE & 1) tc_epilogue_flush_stats<256>(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
   }

@@ -44,18 +44,17 @@ def test_uint8_batches_match_the_float_contract():
         a, b = model(u8), model(f32)
     assert a.shape == b.shape == (2, 5, 64, 64)
     assert torch.equal(a, b)                                  # same bf16 activations enter the stem
-    for m in model.modules():
-        if isinstance(m, torch.nn.Dropout):
-            m.p = 0.0
-    model.train()
+    # gradients through the trainer, BatchNorm on its running statistics: with batch statistics this tiny train-mode
+    # network (2 images, 4x4 high-level features) amplifies the summation order of the fp32 atomics so much that two
+    # steps on IDENTICAL inputs give gradients with a cosine of ~0.3, which would hide the input path
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.running_mean.normal_(0, 0.1); mod.running_var.uniform_(0.5, 1.5)
     tr = SegTrainer(model, lr=0.0, cls_weights=[1, 1, 5, 3, 4])
     la = tr.step(u8, lab_u8).clone()
     ga = tr.flat.grad.clone()
     lb = tr.step(f32, i64).clone()
-    # same inputs reach the same kernels; what differs is the summation order of the fp32 atomics in the batch
-    # statistics, which this train-mode network amplifies: two runs on IDENTICAL inputs differ
-    # by ~1e-3 in the loss, so the check is the noise floor of repeated steps - loss within 2 %, gradient direction
     gb = tr.flat.grad
-    assert float((la - lb).abs().max()) <= 2e-2 * float(lb.abs().max())
+    assert float((la - lb).abs().max()) <= 1e-4 * float(lb.abs().max())
     cos = float(torch.dot(ga, gb) / (ga.norm() * gb.norm()))
-    assert cos > 0.98, cos
+    assert cos > 0.999, cos
