@@ -624,26 +624,38 @@ struct TcFwdSmem {
 };
 
 // MODE bit 0: BatchNorm statistics of the output, bit 1: side input (each epilogue variant carries only its own code)
+// the 32 bias values of a thread's column group, fetched by the caller BETWEEN the issue of the TMEM load and its wait
+// so that their latency hides behind the accumulator read (inside epi_convert32 they were exposed once per chunk)
+__device__ __forceinline__ void epi_load_bias32(const float* __restrict__ bias, int col0, int cout, float (&bv)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+  if (bias == nullptr) return;
+  if ((reinterpret_cast<uintptr_t>(bias) & 15) == 0) {  // parameter views of a flat buffer may be unaligned
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (col0 + g * 4 < cout) {           // cout % 8 == 0: whole groups of 4 are in or out
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + g * 4));
+        bv[4 * g] = b.x; bv[4 * g + 1] = b.y; bv[4 * g + 2] = b.z; bv[4 * g + 3] = b.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < cout) bv[j] = __ldg(bias + col0 + j);
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&r)[32], int col0, int cout, bool row_ok,
-                                              const uint4 (&side_raw)[4], uint32_t (&packed)[16]) {
+                                              const uint4 (&side_raw)[4], const float (&bias32)[32],
+                                              uint32_t (&packed)[16]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int c = col0 + g * 8;          // absolute output channel of this group of 8
     const bool ok = c < cout;             // cout % 8 == 0: whole groups are in or out
     float bv[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) bv[j] = 0.f;
-    if (ep.bias && ok) {
-      if ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) {  // parameter views of a flat buffer may be unaligned
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(ep.bias + c));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + c + 4));
-        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bv[j] = __ldg(ep.bias + c + j);
-      }
-    }
+    for (int j = 0; j < 8; ++j) bv[j] = bias32[g * 8 + j];
     float sd[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sd[j] = 0.f;
@@ -928,6 +940,8 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         uint32_t r0[32];
         tmem_ld32(t_addr + (uint32_t)(q * 64 + half * 32), r0);
+        float bias32[32];
+        epi_load_bias32(ep.bias, col0 + half * 32, p.cout, bias32);
         tmem_ld_wait();
         if (q == nchunks - 1) {  // the accumulator is in registers: hand it back to the MMA issuer
           tc_fence_before();
@@ -936,7 +950,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         if (!tile_ok) continue;  // CTA-uniform: the odd tile of the last pair
         uint32_t pk0[16];
-        epi_convert32<MODE>(ep, r0, col0 + half * 32, p.cout, row_ok, sd0, pk0);
+        epi_convert32<MODE>(ep, r0, col0 + half * 32, p.cout, row_ok, sd0, bias32, pk0);
         const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
         if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
         epi_bar_sync256();
