@@ -219,6 +219,9 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
 
         # the head's step is ~600 launches of a few microseconds: captured once as a CUDA graph (new masks, dropout
         # streams and Adam step count reach every replay through device memory), eager with --no-graph
+        for _ in range(max(warmup, 2)):          # untimed encoder passes (allocator, lazy weight folding)
+            encode()
+        torch.cuda.synchronize()
         if use_graph:
             trainer.capture(encode(), edges, labels, masks, warmup=max(warmup, 1))
             head_step = lambda f: trainer.step_graphed(f, labels, draw_masks())      # noqa: E731

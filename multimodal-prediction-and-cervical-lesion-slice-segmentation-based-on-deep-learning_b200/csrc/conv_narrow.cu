@@ -530,8 +530,11 @@ __global__ void __launch_bounds__(256) im2col_narrow_rows_kernel(const T* __rest
   constexpr int V = Elem<T>::kVec;
   const int kv = kpad / V;                        // <= 32 (host-checked)
   const int K = g.kh * g.kw * g.cin;
-  const int kvi = threadIdx.x & 31, pl = threadIdx.x >> 5;
-  if (kvi >= kv) return;
+  // (pixel lane, slice) = divmod(thread, kv): with kv = 19 slices (the ResNet stem's 7x7x3 -> 152) that keeps 247 of the
+  // 256 threads busy; one warp per pixel lane left 13 of 32 lanes idle in this instruction-bound kernel
+  const int kvi = threadIdx.x % kv, pl = threadIdx.x / kv;
+  const int plN = 256 / kv;
+  if (pl >= plN) return;
   int dy[V], dx[V], ci[V];
   bool kok[V];
 #pragma unroll
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(256) im2col_narrow_rows_kernel(const T* __rest
       rp[i] = x + ((size_t)nn * g.h + (rok[i] ? iy : 0)) * g.w * g.cin + ci[i];
     }
     T* out = y + ((size_t)row * g.wo) * kpad + kvi * V;
-    for (int ox = pl; ox < g.wo; ox += 8) {
+    for (int ox = pl; ox < g.wo; ox += plN) {
       Vec<T> o;
 #pragma unroll
       for (int i = 0; i < V; ++i) {

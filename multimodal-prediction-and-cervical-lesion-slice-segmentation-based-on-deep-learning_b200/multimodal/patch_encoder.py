@@ -43,6 +43,35 @@ class _FoldedConv:
         return self.wp, self.bias
 
 
+class _FoldedStem(_FoldedConv):
+    """The 7x7/2 stem of the frozen encoder as an im2col + 1x1 tensor-core conv with bn1 folded in: the filter becomes a
+    [cout, 152] matrix over the K-padded patch vector (tap-major, 3 channels per tap), bias + ReLU in the epilogue."""
+
+    def get(self):
+        t = (self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
+        key = tuple((x.data_ptr(), x._version) for x in t)
+        if key != self.key:
+            w, self.bias = _fold_bn(self.conv.weight, self.bn)
+            cout, cin, kh, kw = w.shape
+            k = kh * kw * cin
+            self.kpad = (k + 7) // 8 * 8
+            w2 = torch.nn.functional.pad(w.permute(0, 2, 3, 1).reshape(cout, k), (0, self.kpad - k))
+            self.wp = get_backend().pack_weight(w2.reshape(cout, self.kpad, 1, 1).contiguous(), torch.bfloat16, False)
+            self.key = key
+        return self.wp, self.bias
+
+    def __call__(self, x):
+        B = get_backend()
+        wp, bias = self.get()
+        conv = self.conv
+        cout, cin, kh, kw = conv.weight.shape
+        n, h, w, _ = x.shape
+        g = ConvGeom(n, h, w, cin, cout, kh, kw, conv.stride[0], conv.padding[0], 1)
+        patches = B.im2col_narrow(x.contiguous(), g, self.kpad)
+        g1 = ConvGeom(n, g.ho, g.wo, self.kpad, cout, 1, 1, 1, 0, 1)
+        return B.conv_fwd_act(patches, wp, bias, g1, ops.ACT_RELU, None, None)
+
+
 def _conv_act(x, fc: _FoldedConv, act: int, residual=None, ones=None):
     """act(conv(x) + folded bn (+ residual)) as ONE tensor-core kernel (cvx_conv_fwd_tc_act)."""
     B = get_backend()
@@ -154,8 +183,13 @@ class ResNet101Encoder(nn.Module):
         """Encoder body on an NHWC tensor already in the compute dtype."""
         fold = self._fold_ok(x)
         c1 = self.conv1
-        x = ops.conv2d_narrow_in(x, c1.weight, c1.stride[0], c1.padding[0])
-        x = ops.batchnorm_act(x, self.bn1, ops.ACT_RELU)
+        if fold and c1.weight.shape[1] <= 4:
+            if getattr(self, "_stem", None) is None:
+                self._stem = _FoldedStem(self.conv1, self.bn1)
+            x = self._stem(x)                     # conv1 + bn1 + relu: im2col, then one tensor-core kernel
+        else:
+            x = ops.conv2d_narrow_in(x, c1.weight, c1.stride[0], c1.padding[0])
+            x = ops.batchnorm_act(x, self.bn1, ops.ACT_RELU)
         x = ops.maxpool3x3s2(x)
         if fold:
             # frozen eval-mode network (the only way the reference uses it): BatchNorm folded into the conv weights,
