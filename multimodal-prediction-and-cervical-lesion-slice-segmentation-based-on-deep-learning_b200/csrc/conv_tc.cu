@@ -648,7 +648,7 @@ __device__ __forceinline__ void epi_load_bias32(const float* __restrict__ bias, 
 template <int MODE>
 __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&r)[32], int col0, int cout, bool row_ok,
                                               const uint4 (&side_raw)[4], const float (&bias32)[32],
-                                              uint32_t (&packed)[16]) {
+                                              const float (&sscale32)[32], uint32_t (&packed)[16]) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     const int c = col0 + g * 8;          // absolute output channel of this group of 8
@@ -662,18 +662,9 @@ __device__ __forceinline__ void epi_convert32(const TcEpi& ep, const uint32_t (&
     if ((MODE & 2) && ok && row_ok) {
       const uint4 sv = side_raw[g];   // prefetched by the caller ahead of the TMEM load (one L2 round trip per chunk)
       const uint32_t su[4] = {sv.x, sv.y, sv.z, sv.w};
-      float ss[8];
-      if (ep.side_scale == nullptr) {            // plain residual add
+      float ss[8];   // per-channel scale of the side input (1 for a plain residual add), prefetched by the caller
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss[j] = 1.f;
-      } else if ((reinterpret_cast<uintptr_t>(ep.side_scale) & 15) == 0) {
-        const float4 s0 = __ldg(reinterpret_cast<const float4*>(ep.side_scale + c));
-        const float4 s1 = __ldg(reinterpret_cast<const float4*>(ep.side_scale + c + 4));
-        ss[0] = s0.x; ss[1] = s0.y; ss[2] = s0.z; ss[3] = s0.w; ss[4] = s1.x; ss[5] = s1.y; ss[6] = s1.z; ss[7] = s1.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss[j] = __ldg(ep.side_scale + c + j);
-      }
+      for (int j = 0; j < 8; ++j) ss[j] = sscale32[g * 8 + j];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         sd[2 * j] = ss[2 * j] * __uint_as_float(su[j] << 16);
@@ -940,8 +931,15 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         uint32_t r0[32];
         tmem_ld32(t_addr + (uint32_t)(q * 64 + half * 32), r0);
-        float bias32[32];
+        float bias32[32], sscale32[32];
         epi_load_bias32(ep.bias, col0 + half * 32, p.cout, bias32);
+        if (MODE & 2) {
+          epi_load_bias32(ep.side_scale, col0 + half * 32, p.cout, sscale32);
+          if (ep.side_scale == nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sscale32[j] = 1.f;
+          }
+        }
         tmem_ld_wait();
         if (q == nchunks - 1) {  // the accumulator is in registers: hand it back to the MMA issuer
           tc_fence_before();
@@ -950,7 +948,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         if (!tile_ok) continue;  // CTA-uniform: the odd tile of the last pair
         uint32_t pk0[16];
-        epi_convert32<MODE>(ep, r0, col0 + half * 32, p.cout, row_ok, sd0, bias32, pk0);
+        epi_convert32<MODE>(ep, r0, col0 + half * 32, p.cout, row_ok, sd0, bias32, sscale32, pk0);
         const uint32_t buf = (chunk_count & 1) * kEpiBufBytes;
         if (epi_tid == 0) bulk_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
         epi_bar_sync256();
