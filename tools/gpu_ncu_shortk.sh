@@ -33,3 +33,7 @@ python tools/run_conv_once.py 32 fwd 64 128 1 256 > /dev/null 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:conv_tc_fwd -s 2 -c 1 -o gpurun_out/ncu_shortk_plain \
     python tools/run_conv_once.py 32 fwd 64 128 1 256 > gpurun_out/ncu_shortk_plain.log 2>&1
 echo "rc=$?"
+python tools/run_conv_once.py 32 fwd_ex 64 128 1 256 > /dev/null 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:conv_tc_fwd -s 2 -c 1 -o gpurun_out/ncu_shortk_stats \
+    python tools/run_conv_once.py 32 fwd_ex 64 128 1 256 > gpurun_out/ncu_shortk_stats.log 2>&1
+echo "rc=$?"
