@@ -206,8 +206,19 @@ def _gate(dim):
 
 # ----------------------------------------------------------------------------- the model
 class fusion_model_mae_2(nn.Module):
-    def __init__(self, in_feats, n_hidden, out_classes, dropout=0.3, train_type_num=4):
+    # What the reference's per-variant copies of this class change: the default number of
+    # training modalities, the default of ``mix``, four never-used ``norm3_*`` LayerNorms in the state_dict (156
+    # instead of 148 entries), and which per-modality logits ``forward`` returns.  The subclasses at the end of this
+    # module set them; the arithmetic is the same.
+    _DEFAULT_TYPES = 4
+    _DEFAULT_MIX = True
+    _NORM3 = False
+    _RETURN_LOGITS = ("imgN", "imgA", "imgL", "cli")
+
+    def __init__(self, in_feats, n_hidden, out_classes, dropout=0.3, train_type_num=None):
         super().__init__()
+        if train_type_num is None:
+            train_type_num = self._DEFAULT_TYPES
         C = out_classes
         for m in MODALITIES:
             setattr(self, m + "_gnn_2", SAGEConv(in_feats, C))
@@ -228,6 +239,9 @@ class fusion_model_mae_2(nn.Module):
             setattr(self, "norm1_" + m, LayerNorm(C // 4))
         for m in MODALITIES:
             setattr(self, "norm2_" + m, LayerNorm(C // 16))
+        if self._NORM3:                        # my_mae_model_2*.py:479-482, my_mae_model_three.py:485-488 (never used)
+            for m in MODALITIES:
+                setattr(self, "norm3_" + m, LayerNorm(C // 64))
         self.relu = nn.ReLU()
         self.dropout = nn.Dropout(p=dropout)
         self.classifier = nn.Linear(C // 64, 4)
@@ -332,12 +346,14 @@ class fusion_model_mae_2(nn.Module):
     # ------------------------------------------------------------------ batched forward
     def forward_batch(self, feats: Dict[str, torch.Tensor], edges: Dict[str, torch.Tensor],
                       train_use_type: Sequence[str], use_type: Optional[Sequence[str]] = None,
-                      masks=None, mix: bool = True) -> Dict[str, torch.Tensor]:
+                      masks=None, mix: Optional[bool] = None) -> Dict[str, torch.Tensor]:
         """feats[m]: fp32 ``[G, nodes_m, in_feats]`` on the device; edges[m]: ``[2, E]`` topology shared by all
         patients; masks: bool ``[G, T]`` over ``train_use_type`` (True = masked) as a numpy array or a ``MaskPlan``
         (its device-side index tables, which a captured graph can re-read), None = nothing masked.
         Returns a dict of batched tensors: logits_all / logits_<m> ``[G, 4]``, one_x ``[G, 8]``, multi_x
         ``[G, T', 8]``, fea ``[G, T', 512]``, mae_out / mae_labels, att_2 / att_3 (lists of ``[G, nodes]``)."""
+        if mix is None:
+            mix = self._DEFAULT_MIX
         train_use_type = list(train_use_type)
         use_type = list(train_use_type if use_type is None else use_type)
         Tt = len(train_use_type)
@@ -422,7 +438,9 @@ class fusion_model_mae_2(nn.Module):
         return out
 
     # ------------------------------------------------------------------ reference signature (one patient)
-    def forward(self, all_thing, train_use_type=None, use_type=None, in_mask=[], mix=True):
+    def forward(self, all_thing, train_use_type=None, use_type=None, in_mask=[], mix=None):
+        if mix is None:
+            mix = self._DEFAULT_MIX
         get = (lambda k: all_thing[k]) if isinstance(all_thing, dict) else (lambda k: getattr(all_thing, k))
         train_use_type = list(train_use_type)
         use_type = list(train_use_type if use_type is None else use_type)
@@ -442,8 +460,43 @@ class fusion_model_mae_2(nn.Module):
         lg = {m: (o["logits_" + m][0] if m in o["present"] else None) for m in MODALITIES}
         att_2 = [a.reshape(-1, 1) for a in o["att_2"]]
         att_3 = [a.reshape(-1, 1) for a in o["att_3"]]
-        return ((o["one_x"][0], o["multi_x"][0]), save_fea, (att_2, att_3), fea_dict, o["logits_all"][0],
-                lg["imgN"], lg["imgA"], lg["imgL"], lg["cli"])
+        head = ((o["one_x"][0], o["multi_x"][0]), save_fea, (att_2, att_3), fea_dict, o["logits_all"][0])
+        if self._RETURN_LOGITS == "img+cli":   # my_mae_model_2.py:771-779: the one image modality present, then cli
+            img = None
+            for m in ("imgN", "imgA", "imgL"):
+                if lg[m] is not None:
+                    img = lg[m]                # the reference overwrites img_logits in this order (:230-260)
+            return head + (img, lg["cli"])
+        return head + tuple(lg[m] for m in self._RETURN_LOGITS)
+
+
+# ----------------------------------------------------------------------------- the reference's per-variant classes
+class fusion_model_mae_three(fusion_model_mae_2):
+    """``Three_Modal/my_mae_model_three.py``: 3 training modalities by default, ``mix=False`` by default, the unused
+    ``norm3_*`` layers, the four-modal 9-tuple (absent modalities' logits are None)."""
+    _DEFAULT_TYPES, _DEFAULT_MIX, _NORM3 = 3, False, True
+
+
+class fusion_model_mae_two(fusion_model_mae_2):
+    """``Two_Modal/my_mae_model_2.py`` (one image modality + clinical: train(NC|AC|LC).py): 7-tuple ending in
+    (all_logits, img_logits, cli_logits)."""
+    _DEFAULT_TYPES, _DEFAULT_MIX, _NORM3 = 2, False, True
+    _RETURN_LOGITS = "img+cli"
+
+
+class fusion_model_mae_two_NL(fusion_model_mae_two):
+    """``Two_Modal/my_mae_model_2_NL.py``: (all_logits, imgN_logits, imgL_logits)."""
+    _RETURN_LOGITS = ("imgN", "imgL")
+
+
+class fusion_model_mae_two_AL(fusion_model_mae_two):
+    """``Two_Modal/my_mae_model_2_AL.py``: (all_logits, imgA_logits, imgL_logits)."""
+    _RETURN_LOGITS = ("imgA", "imgL")
+
+
+class fusion_model_mae_two_NA(fusion_model_mae_two):
+    """``Two_Modal/my_mae_model_2_NA.py``: (all_logits, imgN_logits, imgA_logits)."""
+    _RETURN_LOGITS = ("imgN", "imgA")
 
 
 # ----------------------------------------------------------------------------- objective + train step

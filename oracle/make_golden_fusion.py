@@ -129,7 +129,75 @@ def main():
             payload["grad:" + k] = gk.reshape(-1)[:: gk.numel() // 8192 + 1].numpy()
         payload["state_keys"] = np.array(list(state.keys()))
         np.savez_compressed(os.path.join(out_dir, "fusion_%s.npz" % tag), **payload)
+    variants(out_dir, Data)
     print("fusion golden vectors written")
+
+
+def load_variant(subdir, fname):
+    """Import one of the reference's per-variant copies (Two_Modal/my_mae_model_2*.py, Three_Modal/my_mae_model_three.py)
+    unmodified, with ITS directory's mae_utils / util on the path."""
+    import importlib.util
+    d = os.path.join("/root/reference/MultiModal Prediction", subdir)
+    for k in ("mae_utils", "util"):
+        sys.modules.pop(k, None)
+    sys.path.insert(0, d)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_" + fname[:-3], os.path.join(d, fname))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path.remove(d)
+    mod.device = torch.device("cpu")
+    return mod
+
+
+VARIANTS = (  # tag, directory, file, modalities of the train script, names of the logits the 7-/9-tuple ends with
+    ("two_NC", "Two_Modal", "my_mae_model_2.py", ["imgN", "cli"], ["img", "cli"]),
+    ("two_LC", "Two_Modal", "my_mae_model_2.py", ["imgL", "cli"], ["img", "cli"]),
+    ("two_NL", "Two_Modal", "my_mae_model_2_NL.py", ["imgN", "imgL"], ["imgN", "imgL"]),
+    ("two_AL", "Two_Modal", "my_mae_model_2_AL.py", ["imgA", "imgL"], ["imgA", "imgL"]),
+    ("two_NA", "Two_Modal", "my_mae_model_2_NA.py", ["imgN", "imgA"], ["imgN", "imgA"]),
+    ("three_NAL", "Three_Modal", "my_mae_model_three.py", ["imgN", "imgA", "imgL"], ["imgN", "imgA", "imgL", "cli"]),
+    ("three_NLC", "Three_Modal", "my_mae_model_three.py", ["imgN", "imgL", "cli"], ["imgN", "imgA", "imgL", "cli"]),
+)
+
+
+def variants(out_dir, Data):
+    """tests/golden/fusion_variants.npz: for every per-variant model file of the reference its state_dict key list and
+    one patient's forward with the file's OWN defaults (train_type_num, mix), checked against the oracle."""
+    payload = {}
+    for tag, subdir, fname, use_types, tail in VARIANTS:
+        M = load_variant(subdir, fname)
+        T = len(use_types)
+        torch.manual_seed(0)
+        ref = M.fusion_model_mae_2(1024, 512, 512, 0.3)          # the file's default train_type_num
+        assert ref.train_type_num == T if hasattr(ref, "train_type_num") else True
+        state = FR.randomize_state(ref.state_dict(), seed=5)
+        ref.load_state_dict(state, strict=True)
+        ref.eval()
+        mask = np.array([[[False] + [True] * (T - 1)]])
+        g = FR.synthetic_patient(7)
+        with legacy_index(), torch.no_grad():
+            res = ref(to_data(Data, g, use_types), use_types, use_types, mask)      # mix: the file's default (False)
+        (one_x, multi_x), _, (att2, att3), fea, l_all = res[:5]
+        assert len(res) == 5 + len(tail), (tag, len(res))
+        o = FR.fusion_forward(g, {k: v for k, v in state.items() if not k.startswith("norm3_")}, use_types, mask[0, 0],
+                              mix=False)
+        for name, a, b in (("one_x", one_x, o["one_x"]), ("multi_x", multi_x, o["multi_x"]), ("logits_all", l_all, o["logits_all"]),
+                           ("mae_out", fea["mae_out"], o["mae_out"])):
+            err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+            assert err < 2e-5, (tag, name, err)
+            payload["%s:%s" % (tag, name)] = a.detach().numpy()
+        for i, name in enumerate(tail):
+            v = res[5 + i]
+            payload["%s:tail%d" % (tag, i)] = np.zeros(0, dtype=np.float32) if v is None else v.detach().numpy()
+        payload["%s:state_keys" % tag] = np.array(list(state.keys()))
+        payload["%s:use_types" % tag] = np.array(use_types)
+        payload["%s:mask" % tag] = mask[0, 0]
+        print("%s (%s/%s): %d state entries, %d-tuple, oracle agrees" % (tag, subdir, fname, len(state), len(res)))
+    payload["tags"] = np.array([v[0] for v in VARIANTS])
+    payload["files"] = np.array([v[2] for v in VARIANTS])
+    np.savez_compressed(os.path.join(out_dir, "fusion_variants.npz"), **payload)
 
 
 if __name__ == "__main__":

@@ -125,3 +125,46 @@ def oracle_missing(graph, state, train_types, present):
     x = F.normalize(torch.cat(feats, 0), dim=1)
     multi = torch.stack([FR._head(x[i], state, m)[0] for i, m in enumerate(present)])
     return {"mae_out": mae_out, "logits_all": FR._lin(multi.mean(0), state, "classifier")}
+
+
+# ---- the reference's per-variant model files (Two_Modal/my_mae_model_2*.py, Three_Modal/my_mae_model_three.py) -------
+VARIANT_CLASS = {"my_mae_model_2.py": "fusion_model_mae_two", "my_mae_model_2_NL.py": "fusion_model_mae_two_NL",
+                 "my_mae_model_2_AL.py": "fusion_model_mae_two_AL", "my_mae_model_2_NA.py": "fusion_model_mae_two_NA",
+                 "my_mae_model_three.py": "fusion_model_mae_three"}
+
+
+def variant_tags():
+    g = np.load(os.path.join(GOLDEN, "fusion_variants.npz"))
+    return [str(t) for t in g["tags"]]
+
+
+def check_variant(tag, device, tol=2e-4):
+    """One patient through the class that mirrors the variant file, constructed and called with the file's OWN defaults
+    (train_type_num, mix), against tests/golden/fusion_variants.npz: same state_dict schema (156 entries with the
+    never-used norm3_* layers), same tuple length and logits order, same values."""
+    import cervix_b200.multimodal.my_mae_model as MM
+    g = np.load(os.path.join(GOLDEN, "fusion_variants.npz"))
+    fname = str(g["files"][[str(t) for t in g["tags"]].index(tag)])
+    cls = getattr(MM, VARIANT_CLASS[fname])
+    use_types = [str(u) for u in g[tag + ":use_types"]]
+    model = cls(1024, 512, 512, 0.3)
+    assert model.train_type_num == len(use_types)
+    keys = [str(k) for k in g[tag + ":state_keys"]]
+    assert list(model.state_dict().keys()) == keys and len(keys) == 156
+    model.load_state_dict(FR.randomize_state(model.state_dict(), seed=5), strict=True)
+    model.to(device).eval()
+    p = dict(FR.synthetic_patient(7), data_id="p", data_type=use_types)
+    with torch.no_grad():
+        res = model(p, use_types, use_types, g[tag + ":mask"][None, None, :])
+    n_tail = len([k for k in g.files if k.startswith(tag + ":tail")])
+    assert len(res) == 5 + n_tail
+    (one_x, multi_x), save_fea, _, fea, l_all = res[:5]
+    assert "after_mix" not in save_fea                       # mix defaults to False in these files
+    for name, got in (("one_x", one_x), ("multi_x", multi_x), ("logits_all", l_all), ("mae_out", fea["mae_out"])):
+        assert relerr(got, g["%s:%s" % (tag, name)]) < tol, (tag, name)
+    for i in range(n_tail):
+        want = g["%s:tail%d" % (tag, i)]
+        if want.size == 0:
+            assert res[5 + i] is None, (tag, i)
+        else:
+            assert relerr(res[5 + i], want) < tol, (tag, i)

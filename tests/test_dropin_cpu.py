@@ -47,6 +47,25 @@ def test_reference_import_paths_resolve():
          "save_period", "save_dir", "local_rank"])
 
 
+def test_two_and_three_modal_script_imports_resolve():
+    """``from my_mae_model_2_NL import fusion_model_mae_2`` etc. (Two_Modal/train(*).py:30, Three_Modal/train(*).py:30):
+    each module name gives the class with that file's defaults and its 156-entry state_dict."""
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import inspect\n"
+        "for name, t in (('my_mae_model_2', 2), ('my_mae_model_2_NL', 2), ('my_mae_model_2_AL', 2), ('my_mae_model_2_NA', 2),\n"
+        "                ('my_mae_model_three', 3), ('my_mae_model', 4)):\n"
+        "    mod = __import__(name)\n"
+        "    m = mod.fusion_model_mae_2(1024, 512, 512, 0.3)\n"
+        "    print(name, m.train_type_num, len(m.state_dict()), m._DEFAULT_MIX)\n"
+        "    assert m.train_type_num == t\n" % DROPIN)
+    out = subprocess.run([sys.executable, "-c", code], cwd="/tmp", capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "my_mae_model_2 2 156 False" and lines[4] == "my_mae_model_three 3 156 False"
+    assert lines[5] == "my_mae_model 4 148 True"
+
+
 class _History:
     def __init__(self):
         self.losses, self.val_loss = [], []

@@ -27,3 +27,9 @@ def test_reference_signature_single_patient(tag):
 
 def test_missing_modality_inference():
     FC.check_missing_modality(torch.device("cpu"))
+
+
+@pytest.mark.parametrize("tag", FC.variant_tags())
+def test_reference_variant_files(tag):
+    """Two_Modal/my_mae_model_2*.py and Three_Modal/my_mae_model_three.py: schema, defaults, tuple layout, values."""
+    FC.check_variant(tag, torch.device("cpu"))

@@ -250,3 +250,9 @@ def test_graph_captured_train_step_equals_eager(types):
     m2 = np.roll(m, 1, axis=1)
     b = float(graphed.step_graphed(f, l, m2))
     assert abs(a - b) > 1e-6
+
+
+@pytest.mark.parametrize("tag", FC.variant_tags())
+def test_reference_variant_files(tag):
+    """The reference's 2- / 3-modal model files on the CUDA kernels (golden: tests/golden/fusion_variants.npz)."""
+    FC.check_variant(tag, torch.device("cuda"))
