@@ -83,14 +83,31 @@ __global__ void __launch_bounds__(256) igemm_simt_kernel(const T* __restrict__ s
     const T* arow = src + (((int64_t)a_n * src_h + sy) * src_w + sx) * cred;
     const T* brow = wp + ((int64_t)tap * ncol + bcol) * cred;
 
+    // software pipeline: the global loads of k-block c0 + BK are issued before the multiply-adds of k-block c0, so
+    // their latency hides behind the 16 x 16 FMAs per thread (the row operators' linear layers - 256 rows, K = 1024,
+    // 32 CTAs on 148 SMs - were bound by exactly that latency, 64 exposed round trips per launch)
+    float ra[4], rb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lk + i;
+      ra[i] = (pix_ok && c < cred) ? Elem<T>::ld(arow + c) : 0.f;
+      rb[i] = (bcol_ok && c < cred) ? Elem<T>::ld(brow + c) : 0.f;
+    }
     for (int c0 = 0; c0 < cred; c0 += BK) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int c = c0 + lk + i;
-        As[lk + i][lrow] = (pix_ok && c < cred) ? Elem<T>::ld(arow + c) : 0.f;
-        Bs[lk + i][lrow] = (bcol_ok && c < cred) ? Elem<T>::ld(brow + c) : 0.f;
+        As[lk + i][lrow] = ra[i];
+        Bs[lk + i][lrow] = rb[i];
       }
       __syncthreads();
+      if (c0 + BK < cred) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + BK + lk + i;
+          ra[i] = (pix_ok && c < cred) ? Elem<T>::ld(arow + c) : 0.f;
+          rb[i] = (bcol_ok && c < cred) ? Elem<T>::ld(brow + c) : 0.f;
+        }
+      }
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
         const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
