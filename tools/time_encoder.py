@@ -1,3 +1,4 @@
+"""Wall / device time of the frozen patch encoder over 3 x 16 images (768 patches), four repetitions (GPU box only)."""
 import os, sys, time
 sys.path.insert(0, os.getcwd())
 import torch
