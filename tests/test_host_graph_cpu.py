@@ -105,3 +105,24 @@ def test_state_dict_schema_and_errors():
         DeepLab(5, "resnet", False, 16)
     with pytest.raises(TypeError):  # the reference's '%d' % os quirk
         DeepLab(5, "xception", False, 32)
+
+
+def test_uint8_batch_enters_the_model_like_the_float_batch():
+    """DeepLab.forward on the decoded uint8 [B,H,W,3] pixels (loader tail on the device, dataloader.py:40 +
+    preprocess_input) equals the fp32 NCHW call, on the emulated C ABI."""
+    import numpy as np
+    import cervix_b200.backend as backend
+    from cervix_b200.nets.deeplabv3_plus import DeepLab
+    from tests.emu_backend import EmuBackend
+    prev = backend.set_backend(EmuBackend())
+    try:
+        torch.manual_seed(0)
+        model = DeepLab(5, "mobilenet", False, 16).set_compute_dtype(torch.float32).eval()
+        u8 = torch.from_numpy(np.random.RandomState(0).randint(0, 256, (1, 32, 48, 3), dtype=np.uint8))
+        f32 = (u8.float() / 255.0).permute(0, 3, 1, 2).contiguous()
+        with torch.no_grad():
+            a, b = model(u8), model(f32)
+        assert a.shape == b.shape == (1, 5, 32, 48)
+        assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+    finally:
+        backend.set_backend(prev)
