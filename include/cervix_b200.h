@@ -266,7 +266,9 @@ CVX_API int cvx_l2norm_fwd(const float* x, float* y, float* norms, int rows, int
 CVX_API int cvx_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int rows, int c, void* stream);
 /* token (un)shuffling of the masked auto-encoder (my_mae_model.py:143,318-335): y[i] = idx[i] >= 0 ? x[idx[i]] : fill */
 CVX_API int cvx_rows_gather(const float* x, const int* idx, const float* fill, float* y, int rows, int c, void* stream);
-CVX_API int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int c, void* stream);
+/* backward of cvx_rows_gather in gather form (fixed summation order, writes every element of dx [src_rows, c] / dfill) */
+CVX_API int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int src_rows, int c,
+                         void* stream);
 /* classifier objective (my_train(full).py:309-347): loss += weight * mean CE ; masked-row MSE */
 CVX_API int cvx_softmax_ce(const float* logits, const int64_t* labels, float* loss, float* dlogits, int b, int k,
                    float weight, void* stream);

@@ -95,7 +95,7 @@ PROTOTYPES = {
     "cvx_l2norm_fwd": [_P, _P, _P, _I, _I, _P],
     "cvx_l2norm_bwd": [_P, _P, _P, _P, _I, _I, _P],
     "cvx_rows_gather": [_P, _P, _P, _P, _I, _I, _P],
-    "cvx_rows_scatter_add": [_P, _P, _P, _P, _I, _I, _P],
+    "cvx_rows_scatter_add": [_P, _P, _P, _P, _I, _I, _I, _P],
     "cvx_softmax_ce": [_P, _P, _P, _P, _I, _I, _F, _P],
     "cvx_masked_mse": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _P],
     "cvx_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],

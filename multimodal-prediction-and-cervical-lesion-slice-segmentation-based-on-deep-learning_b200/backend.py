@@ -499,9 +499,9 @@ class CudaBackend:
     def rows_scatter_add(self, dy, idx, src_rows: int, want_fill: bool):
         self._chk(dy, idx)
         rows, c = dy.shape
-        dx = torch.zeros((src_rows, c), dtype=torch.float32, device=dy.device)
-        dfill = torch.zeros((c,), dtype=torch.float32, device=dy.device) if want_fill else None
-        check(self.lib.cvx_rows_scatter_add(_p(dy), _p(idx), _p(dx), _p(dfill), rows, c, self._stream()),
+        dx = torch.empty((src_rows, c), dtype=torch.float32, device=dy.device)
+        dfill = torch.empty((c,), dtype=torch.float32, device=dy.device) if want_fill else None
+        check(self.lib.cvx_rows_scatter_add(_p(dy), _p(idx), _p(dx), _p(dfill), rows, src_rows, c, self._stream()),
               "cvx_rows_scatter_add")
         return dx, dfill
 

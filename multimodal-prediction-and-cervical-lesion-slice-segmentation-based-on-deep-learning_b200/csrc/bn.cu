@@ -185,192 +185,6 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
 }
 
 
-// ---- single-launch training forward / backward ------------------------------------------------
-// Statistics and apply in ONE cooperative kernel: every thread reduces exactly the elements it will
-// later normalise (so the second read comes from L1/L2 for the many 728-channel 32x32 layers whose
-// tensors fit in the 126 MB L2), a software grid barrier separates the two phases.  Replaces
-// 4 launches (memset, reduce, finalize, apply) by 2 (memset, fused).
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
-    unsigned int spins = 0;
-    while (*reinterpret_cast<volatile unsigned int*>(counter) < nblocks) {
-      if (++spins > (1u << 28)) { printf("cervix_b200: grid barrier timed out\n"); __trap(); }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256, 4) bn_fused_fwd_kernel(
-    const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, const float* __restrict__ gamma,
-    const float* __restrict__ beta, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-    double* ws, int64_t rows, int C, int act, float momentum, float eps, int64_t stride_vecs) {
-  constexpr int VEC = Elem<T>::kVec;
-  extern __shared__ float sm[];  // [2][C]
-  const int cvn = C / VEC;
-  const int64_t total = rows * cvn;
-  const int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const bool active = e0 < stride_vecs;
-  const int c0 = (int)(e0 % cvn) * VEC;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  if (active) {
-    float s[VEC], ss[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) s[i] = ss[i] = 0.f;
-#pragma unroll 4
-    for (int64_t e = e0; e < total; e += stride_vecs) {
-      Vec<T> v;
-      v.load(x + e * VEC);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) { s[i] += v.v[i]; ss[i] = fmaf(v.v[i], v.v[i], ss[i]); }
-    }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { atomicAdd(&sm[c0 + i], s[i]); atomicAdd(&sm[C + c0 + i], ss[i]); }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
-    if (sm[i] != 0.f) atomicAdd(ws + i, (double)sm[i]);
-  grid_barrier(reinterpret_cast<unsigned int*>(ws + 2 * C), gridDim.x);
-
-  const double n = (double)rows;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double mean = __ldcg(ws + c) / n;
-      double var = __ldcg(ws + C + c) / n - mean * mean;
-      if (var < 0) var = 0;
-      save_mean[c] = (float)mean;
-      save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-      if (running_mean) {
-        const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
-        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
-        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
-      }
-    }
-  }
-  if (!active) return;
-  float sc[VEC], sh[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    const double mean = __ldcg(ws + c0 + i) / n;
-    double var = __ldcg(ws + C + c0 + i) / n - mean * mean;
-    if (var < 0) var = 0;
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    sc[i] = gamma[c0 + i] * invstd;
-    sh[i] = beta[c0 + i] - (float)mean * sc[i];
-  }
-  for (int64_t e = e0; e < total; e += stride_vecs) {
-    Vec<T> v, r;
-    v.load(x + e * VEC);
-    if (res) r.load(res + e * VEC);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float o = fmaf(v.v[i], sc[i], sh[i]);
-      if (res) o += r.v[i];
-      v.v[i] = act_apply(o, act);
-    }
-    v.store(y + e * VEC);
-  }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256, 3) bn_fused_bwd_kernel(
-    const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
-    const float* __restrict__ mean, const float* __restrict__ invstd, T* __restrict__ dx, T* __restrict__ dres,
-    float* dgamma, float* dbeta, double* ws, int64_t rows, int C, int act, int64_t stride_vecs) {
-  constexpr int VEC = Elem<T>::kVec;
-  extern __shared__ float sm[];  // [2][C]
-  const int cvn = C / VEC;
-  const int64_t total = rows * cvn;
-  const int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const bool active = e0 < stride_vecs;
-  const int c0 = (int)(e0 % cvn) * VEC;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  float mu[VEC], is[VEC];
-  if (active) {
-    float s1[VEC], s2[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { s1[i] = s2[i] = 0.f; mu[i] = mean[c0 + i]; is[i] = invstd[c0 + i]; }
-#pragma unroll 2
-    for (int64_t e = e0; e < total; e += stride_vecs) {
-      Vec<T> g, xv, yv;
-      g.load(dy + e * VEC);
-      xv.load(x + e * VEC);
-      if (act != CVX_ACT_NONE) yv.load(y + e * VEC);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        float dz = g.v[i];
-        if (act != CVX_ACT_NONE) dz *= act_mask(yv.v[i], act);
-        s1[i] += dz;
-        s2[i] = fmaf(dz, (xv.v[i] - mu[i]) * is[i], s2[i]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { atomicAdd(&sm[c0 + i], s1[i]); atomicAdd(&sm[C + c0 + i], s2[i]); }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
-    if (sm[i] != 0.f) atomicAdd(ws + i, (double)sm[i]);
-  grid_barrier(reinterpret_cast<unsigned int*>(ws + 2 * C), gridDim.x);
-
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (float)__ldcg(ws + c);
-      if (dgamma) dgamma[c] = (float)__ldcg(ws + C + c);
-    }
-  }
-  if (!active) return;
-  const double inv_n = 1.0 / (double)rows;
-  float k[VEC], m1[VEC], m2[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    k[i] = gamma[c0 + i] * is[i];
-    m1[i] = (float)(__ldcg(ws + c0 + i) * inv_n);
-    m2[i] = (float)(__ldcg(ws + C + c0 + i) * inv_n);
-  }
-  for (int64_t e = e0; e < total; e += stride_vecs) {
-    Vec<T> g, xv, yv;
-    g.load(dy + e * VEC);
-    xv.load(x + e * VEC);
-    if (act != CVX_ACT_NONE) yv.load(y + e * VEC);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      float dz = g.v[i];
-      if (act != CVX_ACT_NONE) dz *= act_mask(yv.v[i], act);
-      g.v[i] = dz;
-      xv.v[i] = k[i] * (dz - m1[i] - (xv.v[i] - mu[i]) * is[i] * m2[i]);
-    }
-    xv.store(dx + e * VEC);
-    if (dres) g.store(dres + e * VEC);
-  }
-}
-
-// co-resident grid for the fused kernels: a multiple of the channel-vector count worth of threads
-template <typename K>
-static int fused_grid(K kernel, size_t smem, int64_t total_vecs, int cvn, int* blocks, int64_t* stride) {
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) return CVX_ECUDA;
-  int64_t max_threads = (int64_t)sm_count * occ * 256;
-  int64_t want = total_vecs < max_threads ? total_vecs : max_threads;
-  int64_t s = (want / cvn) * cvn;           // round DOWN so the grid stays co-resident
-  if (s < cvn) s = cvn;
-  if (s > max_threads) return CVX_EUNSUPPORTED;  // more channel vectors than resident threads
-  *stride = s;
-  *blocks = (int)ceil_div64(s, 256);
-  return CVX_OK;
-}
-
 __global__ void bn_param_grad_kernel(const double* __restrict__ acc, float* dgamma, float* dbeta, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -429,25 +243,6 @@ int cvx_bn_forward(const void* x, const void* residual, void* y, const float* ga
   cudaStream_t st = as_stream(stream);
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "bn_forward: C=%d not a multiple of %d", c, vec);
-  static const bool no_fused = getenv("CERVIX_BN_FUSED") == nullptr;  // single-launch variant measured no faster: opt-in
-  if (training && !no_fused && !beta && (size_t)2 * c * sizeof(float) <= 48 * 1024) {
-    // ws holds 2*C doubles of sums + one barrier counter
-    CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * (2 * c + 2), st));
-    int blocks = 0; int64_t stride = 0; int rc = CVX_EUNSUPPORTED;
-    const size_t smem = sizeof(float) * 2 * c;
-    const int64_t total_vecs = rows * (c / vec);
-    if (dtype == CVX_F32) rc = fused_grid(bn_fused_fwd_kernel<float>, smem, total_vecs, c / vec, &blocks, &stride);
-    else rc = fused_grid(bn_fused_fwd_kernel<__nv_bfloat16>, smem, total_vecs, c / vec, &blocks, &stride);
-    if (rc == CVX_OK) {
-      void* args[] = {(void*)&x, (void*)&residual, (void*)&y, (void*)&gamma, (void*)&beta, (void*)&running_mean,
-                      (void*)&running_var, (void*)&save_mean, (void*)&save_invstd, (void*)&ws, (void*)&rows, (void*)&c,
-                      (void*)&act, (void*)&momentum, (void*)&eps, (void*)&stride};
-      const void* fn = dtype == CVX_F32 ? (const void*)bn_fused_fwd_kernel<float> : (const void*)bn_fused_fwd_kernel<__nv_bfloat16>;
-      CVX_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, smem, st));
-      ++g_kernel_launches;
-      return CVX_OK;
-    }
-  }
   if (training) {
     CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
     int rc = CVX_OK;
@@ -477,24 +272,6 @@ int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* g
   cudaStream_t st = as_stream(stream);
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "bn_backward: C=%d not a multiple of %d", c, vec);
-  static const bool no_fused = getenv("CERVIX_BN_FUSED") == nullptr;  // single-launch variant measured no faster: opt-in
-  if (training && !no_fused && (size_t)2 * c * sizeof(float) <= 48 * 1024) {
-    CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * (2 * c + 2), st));
-    int blocks = 0; int64_t stride = 0; int rc2 = CVX_EUNSUPPORTED;
-    const size_t smem = sizeof(float) * 2 * c;
-    const int64_t total_vecs = rows * (c / vec);
-    if (dtype == CVX_F32) rc2 = fused_grid(bn_fused_bwd_kernel<float>, smem, total_vecs, c / vec, &blocks, &stride);
-    else rc2 = fused_grid(bn_fused_bwd_kernel<__nv_bfloat16>, smem, total_vecs, c / vec, &blocks, &stride);
-    if (rc2 == CVX_OK) {
-      void* args[] = {(void*)&dy, (void*)&x, (void*)&y, (void*)&gamma, (void*)&save_mean, (void*)&save_invstd, (void*)&dx,
-                      (void*)&dres, (void*)&dgamma, (void*)&dbeta, (void*)&ws, (void*)&rows, (void*)&c, (void*)&act,
-                      (void*)&stride};
-      const void* fn = dtype == CVX_F32 ? (const void*)bn_fused_bwd_kernel<float> : (const void*)bn_fused_bwd_kernel<__nv_bfloat16>;
-      CVX_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, smem, st));
-      ++g_kernel_launches;
-      return CVX_OK;
-    }
-  }
   CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
   int rc = CVX_OK;
   CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, BnBwdF<T>, 256, 3>(

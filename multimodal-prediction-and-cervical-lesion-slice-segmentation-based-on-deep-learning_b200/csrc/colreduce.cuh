@@ -2,8 +2,11 @@
 //
 // Bandwidth-bound: every thread owns one 16-byte channel vector and walks down the rows, so
 // a warp always reads whole contiguous 512-byte spans (4 independent rows in flight per
-// thread); partial sums are combined through shared-memory atomics once per block and fp64
-// global atomics per channel.  Few, long-lived blocks keep that epilogue negligible.
+// thread); partial sums are combined once per block in shared memory in a FIXED order (row lane 0,
+// 1, 2, ... - no shared atomics, so a block's partial is bit-reproducible) and then through fp64
+// global atomics per channel.  The fp64 sum of a few hundred fp32 partials of comparable magnitude is
+// exact (24-bit mantissas inside a 53-bit accumulator), hence independent of the arrival order.
+// Few, long-lived blocks keep that epilogue negligible.
 #pragma once
 
 #include "common.cuh"
@@ -56,12 +59,34 @@ __global__ void __launch_bounds__(NT, MINB) colreduce_kernel(F f, int64_t rows, 
 #pragma unroll 8
       for (int64_t r = r0 + lane; r < r1; r += lanes) f(r, cvec * VEC, acc);
     }
+  }
+  // fixed-order combine (no shared atomics).  When the chunk width divides the warp, the row lanes of a warp are first
+  // folded by a shuffle tree; then the remaining contributors add their registers to the block tile one after the
+  // other (the threads of one turn own distinct columns).
+  int turn = lane, turns = lanes;
+  bool contributes = active;
+  if ((32 % colchunk_vecs) == 0) {
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) atomicAdd(&sm_acc[a * chunk_elems + cv * VEC + i], acc[a][i]);
+      for (int i = 0; i < VEC; ++i) {
+        float v = acc[a][i];
+        for (int o = 16; o >= colchunk_vecs; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[a][i] = v;
+      }
+    turn = threadIdx.x >> 5;
+    turns = NT / 32;
+    contributes = active && (threadIdx.x & 31) < colchunk_vecs;
   }
-  __syncthreads();
+  for (int l = 0; l < turns; ++l) {
+    if (contributes && turn == l) {
+#pragma unroll
+      for (int a = 0; a < NACC; ++a)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sm_acc[a * chunk_elems + cv * VEC + i] += acc[a][i];
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < NACC * chunk_elems; i += NT) {
     const int a = i / chunk_elems, e = i % chunk_elems;
     const int c = blockIdx.y * chunk_elems + e;

@@ -301,6 +301,9 @@ int cvx_conv_wgrad(const cvx_conv_desc* d, const void* x, const void* dy, float*
   const int taps = g.kh * g.kw;
   const int tiles = ((g.cout + BM - 1) / BM) * ((g.cin + BN - 1) / BN) * taps;
   int splits = (2 * kNumSMs + tiles - 1) / tiles;
+  // the row operators of the fusion head (M = patients x nodes <= a few thousand rows): one block per output tile, so
+  // every element is one fixed-order sum and the head's gradients are bit-reproducible (no split-K atomics)
+  if (M <= 4096) splits = 1;
   const int64_t max_splits = ceil_div64(M, 4 * BK);
   if (splits > max_splits) splits = (int)max_splits;
   if (splits < 1) splits = 1;

@@ -183,9 +183,13 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcEpi& ep, uint32_t t_add
       warp_colsum32(vals, lane);
       warp_colsum32(sq, lane);
       const int c = c0 + lane;
-      if (n0 + c < cout && c < tile_n) {
-        atomicAdd(&stats_sm[c], vals[0]);
-        atomicAdd(&stats_sm[256 + c], sq[0]);
+      // the four epilogue warps take turns (fixed order, no shared atomics); every warp of the CTA walks the same chunks
+      for (int turn = 0; turn < 4; ++turn) {
+        if (((threadIdx.x >> 5) & 3) == turn && n0 + c < cout && c < tile_n) {
+          stats_sm[c] += vals[0];
+          stats_sm[256 + c] += sq[0];
+        }
+        epi_bar_sync();
       }
     }
   }
@@ -887,13 +891,21 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       float* st = stats_sm + stats_nt * 512;
       const int n0f = stats_nt * p.tile_n;
       const float2 vs[4] = {rs0, rs1, rs2, rs3}, vq[4] = {rq0, rq1, rq2, rq3};
+      // the eight warps add their registers in turn (fixed order, plain adds): a CTA's partial statistics are
+      // bit-reproducible, and the fp64 global sum of those partials is exact.  The flush runs once per change of the
+      // output-channel tile, CTA-uniformly, so the extra barriers are noise next to a tile's epilogue.
+      for (int turn = 0; turn < 8; ++turn) {
+        if (warp - 2 == turn) {
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int c = qq * 64 + 2 * lane;
-        if (c < p.tile_n && n0f + c < p.cout && (vq[qq].x != 0.f || vq[qq].y != 0.f)) {
-          atomicAdd(&st[c], vs[qq].x); atomicAdd(&st[c + 1], vs[qq].y);
-          atomicAdd(&st[256 + c], vq[qq].x); atomicAdd(&st[256 + c + 1], vq[qq].y);
+          for (int qq = 0; qq < 4; ++qq) {
+            const int c = qq * 64 + 2 * lane;
+            if (c < p.tile_n && n0f + c < p.cout) {
+              st[c] += vs[qq].x; st[c + 1] += vs[qq].y;
+              st[256 + c] += vq[qq].x; st[256 + c + 1] += vq[qq].y;
+            }
+          }
         }
+        epi_bar_sync256();
       }
       rs0 = rs1 = rs2 = rs3 = rq0 = rq1 = rq2 = rq3 = make_float2(0.f, 0.f);
     };

@@ -54,7 +54,9 @@ __device__ __forceinline__ void load4(uint32_t addr, float2 (&v)[2]) {
 }
 __device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
 
-// reduce per-thread [K][2] float2 partials over the 16 column-threads that share a channel quad, then fp64 atomics
+// reduce per-thread [K][2] float2 partials over the 16 column-threads that share a channel quad, then fp64 atomics.
+// Fixed order inside the block (shuffle fold of the two half-warps, then the eight warps take turns on the 64-entry tile -
+// no shared atomics), so a block's partial is bit-reproducible; the fp64 global sum of such partials is exact.
 template <int K>
 __device__ __forceinline__ void reduce4_to_global(float2 (&part)[K][2], float* red /* [K][64] smem */, int t, int cq,
                                                   int cchunk, int C, double* out) {
@@ -66,9 +68,17 @@ __device__ __forceinline__ void reduce4_to_global(float2 (&part)[K][2], float* r
     for (int e = 0; e < 4; ++e) {
       float v = (e & 1) ? part[k][e >> 1].y : part[k][e >> 1].x;
       v += __shfl_xor_sync(0xffffffffu, v, 16);
-      if ((t & 31) < 16) atomicAdd(&red[k * 64 + cq * 4 + e], v);
+      if (e & 1) part[k][e >> 1].y = v; else part[k][e >> 1].x = v;
     }
-  __syncthreads();
+  for (int w = 0; w < 8; ++w) {
+    if ((t >> 5) == w && (t & 31) < 16) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) red[k * 64 + cq * 4 + e] += (e & 1) ? part[k][e >> 1].y : part[k][e >> 1].x;
+    }
+    __syncthreads();
+  }
   for (int i = t; i < K * 64; i += 256) {
     const int k = i / 64, cc = cchunk * 64 + (i % 64);
     if (cc < C) atomicAdd(out + (size_t)k * C + cc, (double)red[i]);

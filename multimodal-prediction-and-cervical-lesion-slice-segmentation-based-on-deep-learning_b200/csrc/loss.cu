@@ -98,20 +98,27 @@ __global__ void __launch_bounds__(256) seg_loss_stats_kernel(const float* __rest
   }
   // warp -> block -> global
   a_ce = warp_sum(a_ce); a_w = warp_sum(a_w); a_focal = warp_sum(a_focal); a_cnt = warp_sum(a_cnt);
+  // the eight warp leaders add in turn (fixed order, no shared atomics): a block's partial is bit-reproducible and the
+  // fp64 global sum of the block partials is exact for these magnitudes
   const bool lead = (threadIdx.x & 31) == 0;
-  if (lead) {
-    atomicAdd(&sm[0], a_ce); atomicAdd(&sm[1], a_w); atomicAdd(&sm[2], a_focal); atomicAdd(&sm[3], a_cnt);
-  }
+  float wv[5 * NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
-    if (c < C) {
-      const float v0 = warp_sum(tp[c]), v1 = warp_sum(sp[c]), v2 = warp_sum(st[c]);
-      const float v3 = warp_sum(tph[c]), v4 = warp_sum(sph[c]);
-      if (lead) {
-        atomicAdd(&sm[4 + c], v0); atomicAdd(&sm[4 + C + c], v1); atomicAdd(&sm[4 + 2 * C + c], v2);
-        atomicAdd(&sm[4 + 3 * C + c], v3); atomicAdd(&sm[4 + 4 * C + c], v4); atomicAdd(&sm[4 + 5 * C + c], v2);
+    wv[5 * c] = warp_sum(tp[c]); wv[5 * c + 1] = warp_sum(sp[c]); wv[5 * c + 2] = warp_sum(st[c]);
+    wv[5 * c + 3] = warp_sum(tph[c]); wv[5 * c + 4] = warp_sum(sph[c]);
+  }
+  for (int turn = 0; turn < (int)(blockDim.x >> 5); ++turn) {
+    if (lead && (int)(threadIdx.x >> 5) == turn) {
+      sm[0] += a_ce; sm[1] += a_w; sm[2] += a_focal; sm[3] += a_cnt;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if (c < C) {
+          sm[4 + c] += wv[5 * c]; sm[4 + C + c] += wv[5 * c + 1]; sm[4 + 2 * C + c] += wv[5 * c + 2];
+          sm[4 + 3 * C + c] += wv[5 * c + 3]; sm[4 + 4 * C + c] += wv[5 * c + 4]; sm[4 + 5 * C + c] += wv[5 * c + 2];
+        }
       }
     }
+    __syncthreads();
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nstat; i += blockDim.x) atomicAdd(stats + i, (double)sm[i]);

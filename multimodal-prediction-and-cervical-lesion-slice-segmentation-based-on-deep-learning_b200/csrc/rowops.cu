@@ -51,11 +51,10 @@ __global__ void seg_layernorm_fwd_kernel(const float* __restrict__ x, const floa
   }
 }
 
-// dx, and dw/db accumulated with atomics (caller zeroes dw, db)
+// dx only; the affine gradients are a column reduction over all rows (ln_param_grad_kernel below, fixed summation order)
 __global__ void seg_layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                          const float* __restrict__ w, const float* __restrict__ stats,
-                                         float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int seg,
-                                         int C, float eps, int mode) {
+                                         float* __restrict__ dx, int seg, int C, float eps, int mode) {
   __shared__ float sh[32];
   const int g = blockIdx.x;
   const int n = seg * C;
@@ -76,8 +75,35 @@ __global__ void seg_layernorm_bwd_kernel(const float* __restrict__ dy, const flo
     const int c = i % C;
     const float xc = xs[i] - mean;
     dx[(size_t)g * n + i] = r * (gs[i] * w[c] - Sg / n) - xc * K;
-    if (dw) atomicAdd(dw + c, gs[i] * xc * r);
-    if (db) atomicAdd(db + c, gs[i]);
+  }
+}
+
+// dw[c] = sum_rows dy * (x - mean_g) * r_g ; db[c] = sum_rows dy.  32 channels x 8 row lanes per block; every partial is
+// summed in a fixed order (no atomics), so the head's gradients are bit-reproducible run to run.
+__global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                            const float* __restrict__ stats, float* __restrict__ dw,
+                                                            float* __restrict__ db, int rows, int seg, int C) {
+  __shared__ float pw[8][33], pb[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float aw = 0.f, ab = 0.f;
+  if (c < C) {
+    for (int r = ry; r < rows; r += 8) {
+      const int g = r / seg;
+      const float gi = dy[(size_t)r * C + c];
+      aw = fmaf(gi * (x[(size_t)r * C + c] - stats[3 * g]), stats[3 * g + 1], aw);
+      ab += gi;
+    }
+  }
+  pw[ry][cx] = aw;
+  pb[ry][cx] = ab;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float sw = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sw += pw[k][cx]; sb += pb[k][cx]; }
+    if (dw) dw[c] = sw;
+    if (db) db[c] = sb;
   }
 }
 
@@ -300,32 +326,43 @@ __global__ void rows_gather_kernel(const float* __restrict__ x, const int* __res
     y[i] = s >= 0 ? x[(size_t)s * C + c] : (fill ? fill[c] : 0.f);
   }
 }
-// dx[idx[i],:] += dy[i,:] (idx >= 0) ; dfill[:] += dy[i,:] (idx < 0).  Caller zeroes dx / dfill.
+// dx[s,:] = sum_{i: idx[i] == s} dy[i,:] ; dfill[:] = sum_{i: idx[i] < 0} dy[i,:].  Gather form of the scatter-add: one
+// block per source row (block src_rows = the fill row), rows visited in increasing order -> no atomics, fixed order.
 __global__ void rows_scatter_add_kernel(const float* __restrict__ dy, const int* __restrict__ idx, float* __restrict__ dx,
-                                        float* __restrict__ dfill, int rows, int C) {
-  const int64_t total = (int64_t)rows * C;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / C), c = (int)(i % C);
-    const int s = idx[r];
-    if (s >= 0) atomicAdd(dx + (size_t)s * C + c, dy[i]);
-    else if (dfill) atomicAdd(dfill + c, dy[i]);
+                                        float* __restrict__ dfill, int rows, int src_rows, int C) {
+  const int s = blockIdx.x;
+  const bool fill = s == src_rows;
+  float* out = fill ? dfill : dx + (size_t)s * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < rows; ++i) {
+      const int t = idx[i];
+      if (fill ? t < 0 : t == s) acc += dy[(size_t)i * C + c];
+    }
+    out[c] = acc;
   }
 }
 
 // ---- losses of the classifier (my_train(full).py:309-347) -----------------------------------------------
 // mean cross entropy of [B, K] logits; loss accumulated (atomic) scaled by `weight`, dlogits written scaled
+// (one block; the loss terms of a launch are summed in a fixed order and added to *loss by one thread - launches on a
+// stream are ordered, so the accumulated objective is bit-reproducible)
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                   float* __restrict__ loss, float* __restrict__ dlogits, int B, int K, float weight) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= B) return;
-  float mx = -INFINITY, s = 0.f;
-  for (int k = 0; k < K; ++k) mx = fmaxf(mx, logits[r * K + k]);
-  for (int k = 0; k < K; ++k) s += expf(logits[r * K + k] - mx);
-  const float lse = mx + logf(s);
-  const int t = (int)labels[r];
-  atomicAdd(loss, weight * (lse - logits[r * K + t]) / B);
-  if (dlogits)
-    for (int k = 0; k < K; ++k) dlogits[r * K + k] = weight * (expf(logits[r * K + k] - lse) - (k == t ? 1.f : 0.f)) / B;
+  __shared__ float sh[32];
+  float part = 0.f;
+  for (int r = threadIdx.x; r < B; r += blockDim.x) {
+    float mx = -INFINITY, s = 0.f;
+    for (int k = 0; k < K; ++k) mx = fmaxf(mx, logits[r * K + k]);
+    for (int k = 0; k < K; ++k) s += expf(logits[r * K + k] - mx);
+    const float lse = mx + logf(s);
+    const int t = (int)labels[r];
+    part += weight * (lse - logits[r * K + t]) / B;
+    if (dlogits)
+      for (int k = 0; k < K; ++k) dlogits[r * K + k] = weight * (expf(logits[r * K + k] - lse) - (k == t ? 1.f : 0.f)) / B;
+  }
+  part = block_sum(part, sh);
+  if (threadIdx.x == 0) *loss += part;
 }
 
 // masked MSE between rows of a and b: loss += weight * mean over (selected rows x C) ; da written (0 on unselected rows)
@@ -333,16 +370,18 @@ __global__ void masked_mse_kernel(const float* __restrict__ a, const float* __re
                                   float* __restrict__ loss, float* __restrict__ da, float* __restrict__ db_, int rows, int C,
                                   float weight, float inv_count) {
   __shared__ float sh[32];
-  const int r = blockIdx.x;
-  float s = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float d = sel[r] ? a[(size_t)r * C + c] - b[(size_t)r * C + c] : 0.f;
-    s = fmaf(d, d, s);
-    if (da) da[(size_t)r * C + c] = 2.f * d * weight * inv_count;
-    if (db_) db_[(size_t)r * C + c] = -2.f * d * weight * inv_count;
+  float s = 0.f;          // one block walks every row: a single fixed-order sum, no atomics
+  for (int r = 0; r < rows; ++r) {
+    const bool on = sel[r] != 0;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float d = on ? a[(size_t)r * C + c] - b[(size_t)r * C + c] : 0.f;
+      s = fmaf(d, d, s);
+      if (da) da[(size_t)r * C + c] = 2.f * d * weight * inv_count;
+      if (db_) db_[(size_t)r * C + c] = -2.f * d * weight * inv_count;
+    }
   }
   s = block_sum(s, sh);
-  if (threadIdx.x == 0 && sel[r]) atomicAdd(loss, weight * s * inv_count);
+  if (threadIdx.x == 0) *loss += weight * s * inv_count;
 }
 
 static inline int rgrid(int64_t total) {
@@ -369,10 +408,12 @@ int cvx_seg_layernorm_bwd(const float* dy, const float* x, const float* w, const
                           float* db, int groups, int seg, int c, float eps, int mode, void* stream) {
   CVX_CHECK_ARG(dy && x && w && stats && dx && groups > 0 && seg > 0 && c > 0, "seg_layernorm_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
-  if (dw) CVX_CUDA_OK(cudaMemsetAsync(dw, 0, sizeof(float) * c, st));
-  if (db) CVX_CUDA_OK(cudaMemsetAsync(db, 0, sizeof(float) * c, st));
-  seg_layernorm_bwd_kernel<<<groups, 256, 0, st>>>(dy, x, w, stats, dx, dw, db, seg, c, eps, mode);
+  seg_layernorm_bwd_kernel<<<groups, 256, 0, st>>>(dy, x, w, stats, dx, seg, c, eps, mode);
   CVX_LAUNCH_OK();
+  if (dw || db) {
+    ln_param_grad_kernel<<<(c + 31) / 32, 256, 0, st>>>(dy, x, stats, dw, db, groups * seg, seg, c);
+    CVX_LAUNCH_OK();
+  }
   return CVX_OK;
 }
 
@@ -453,9 +494,10 @@ int cvx_rows_gather(const float* x, const int* idx, const float* fill, float* y,
   return CVX_OK;
 }
 
-int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int c, void* stream) {
-  CVX_CHECK_ARG(dy && idx && dx && rows > 0 && c > 0, "rows_scatter_add: bad arguments");
-  rows_scatter_add_kernel<<<rgrid((int64_t)rows * c), 256, 0, as_stream(stream)>>>(dy, idx, dx, dfill, rows, c);
+int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int src_rows, int c,
+                         void* stream) {
+  CVX_CHECK_ARG(dy && idx && dx && rows > 0 && src_rows > 0 && c > 0, "rows_scatter_add: bad arguments");
+  rows_scatter_add_kernel<<<src_rows + (dfill ? 1 : 0), 128, 0, as_stream(stream)>>>(dy, idx, dx, dfill, rows, src_rows, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -463,7 +505,7 @@ int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfil
 int cvx_softmax_ce(const float* logits, const int64_t* labels, float* loss, float* dlogits, int b, int k, float weight,
                    void* stream) {
   CVX_CHECK_ARG(logits && labels && loss && b > 0 && k > 0, "softmax_ce: bad arguments");
-  softmax_ce_kernel<<<(b + 127) / 128, 128, 0, as_stream(stream)>>>(logits, labels, loss, dlogits, b, k, weight);
+  softmax_ce_kernel<<<1, 128, 0, as_stream(stream)>>>(logits, labels, loss, dlogits, b, k, weight);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -471,7 +513,7 @@ int cvx_softmax_ce(const float* logits, const int64_t* labels, float* loss, floa
 int cvx_masked_mse(const float* a, const float* b, const uint8_t* sel, float* loss, float* da, float* db, int rows, int c,
                    float weight, float inv_count, void* stream) {
   CVX_CHECK_ARG(a && b && sel && loss && rows > 0 && c > 0, "masked_mse: bad arguments");
-  masked_mse_kernel<<<rows, 128, 0, as_stream(stream)>>>(a, b, sel, loss, da, db, rows, c, weight, inv_count);
+  masked_mse_kernel<<<1, 512, 0, as_stream(stream)>>>(a, b, sel, loss, da, db, rows, c, weight, inv_count);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -19,12 +19,30 @@ from .backend import ConvGeom, get_backend
 ACT_NONE, ACT_RELU, ACT_RELU6 = _lib.ACT_NONE, _lib.ACT_RELU, _lib.ACT_RELU6
 
 
+_TC_WARNED = [False]
+
+
 def _tc_ok(x: torch.Tensor, cin: int, cout: int) -> bool:
-    """Tensor-core (tcgen05) eligibility of a dense conv: bf16 storage, 16-byte rows."""
-    if os.environ.get("CERVIX_DISABLE_TC") == "1":
-        return False
+    """Tensor-core (tcgen05) eligibility of a dense conv: bf16 storage, 16-byte rows.  There is no quiet slow path:
+    bf16 convolutions on a device that is not sm_100 raise, and the debugging switch ``CERVIX_DISABLE_TC=1`` (the SIMT
+    kernels, ~10x slower) announces itself on stderr."""
     B = get_backend()
-    return (x.dtype == torch.bfloat16 and cin % 8 == 0 and cout % 8 == 0 and getattr(B, "is_sm100", lambda: False)())
+    if x.dtype != torch.bfloat16 or cin % 8 != 0 or cout % 8 != 0:
+        return False
+    if os.environ.get("CERVIX_DISABLE_TC") == "1":
+        if not _TC_WARNED[0]:
+            _TC_WARNED[0] = True
+            import sys
+            print("cervix_b200: CERVIX_DISABLE_TC=1 - bf16 convolutions run on the SIMT kernels (debugging mode, ~10x slower)",
+                  file=sys.stderr, flush=True)
+        return False
+    probe = getattr(B, "is_sm100", None)
+    if probe is None:               # the CPU emulation backend of the host-logic tests
+        return False
+    if not probe():
+        raise RuntimeError("cervix_b200: the bf16 convolution path needs an sm_100 device (tcgen05); "
+                           "there is no fallback - use set_compute_dtype(torch.float32) for the exact SIMT path")
+    return True
 
 
 class ToNHWC(Function):
@@ -416,12 +434,21 @@ class defer_batch_counters:
         _DEFER_NBT[0] = self.prev
 
 
+def _bn_momentum(bn) -> float:
+    """The reference only builds BatchNorm2d(momentum=0.0003 | 0.1) (xception.py:7, deeplabv3_plus.py:64).  ``momentum=None``
+    means a cumulative moving average in torch, which the kernels do not implement: refuse instead of silently freezing
+    the running statistics."""
+    if bn.momentum is None:
+        raise ValueError("cervix_b200: BatchNorm2d(momentum=None) (cumulative average) is not supported")
+    return float(bn.momentum)
+
+
 def batchnorm_act(x, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None):
     """Apply an ``nn.BatchNorm2d`` parameter holder to an NHWC tensor (never calls bn.forward)."""
     training = bn.training or (bn.running_mean is None)
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None and not _DEFER_NBT[0]:
         bn.num_batches_tracked.add_(1)
-    momentum = 0.0 if bn.momentum is None else bn.momentum
+    momentum = _bn_momentum(bn)
     return BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, training, momentum,
                               bn.eps, act)
 
@@ -446,7 +473,7 @@ def conv_bn_act(x, conv_weight, stride, pad, dil, bn: torch.nn.BatchNorm2d, act=
         return batchnorm_act(conv2d(x, conv_weight, bias, stride, pad, dil), bn, act, residual)
     if bn.track_running_stats and bn.num_batches_tracked is not None and not _DEFER_NBT[0]:
         bn.num_batches_tracked.add_(1)
-    momentum = 0.0 if bn.momentum is None else bn.momentum
+    momentum = _bn_momentum(bn)
     return ConvBnAct.apply(x, conv_weight, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, stride,
                            pad, dil, momentum, bn.eps, act)
 

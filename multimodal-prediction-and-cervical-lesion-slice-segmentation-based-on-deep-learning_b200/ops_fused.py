@@ -39,7 +39,7 @@ class BnBuffers:
         track = bn.track_running_stats and bn.running_mean is not None
         self.mean = bn.running_mean if track else None
         self.var = bn.running_var if track else None
-        self.momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+        self.momentum = ops._bn_momentum(bn)
         self.eps = float(bn.eps)
 
 

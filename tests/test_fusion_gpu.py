@@ -242,14 +242,50 @@ def test_graph_captured_train_step_equals_eager(types):
         lg = float(graphed.step_graphed(f, l, m))
         assert abs(le - lg) <= 2e-4 * abs(le), (le, lg)
     assert graphed.t == eager.t == 5
-    diff = float((eager.flat.data - graphed.flat.data).abs().max())
-    assert diff < 2e-5, diff
+    # The head's reductions have a fixed summation order (csrc/rowops.cu, colreduce.cuh, conv_simt.cu), so both trainers
+    # see the same gradients; what is left is adam_step (host scalars) against adam_step_dev (device scalars).
+    delta = (eager.flat.data - graphed.flat.data).abs()
+    diff = float(delta.max())
+    if diff >= 2e-5:
+        names = [n for n, _ in eager.head.named_parameters()]
+        worst = []
+        for n, p, o in zip(names, eager.flat.params, eager.flat.offsets):
+            d = float(delta[o:o + p.numel()].max())
+            if d >= 2e-5:
+                worst.append((n, d, float(eager.v[o:o + p.numel()].max().sqrt())))
+        raise AssertionError("graphed and eager parameters differ: %s" % worst[:12])
     # the masks really went through: a replay with other masks gives another loss on the same batch
     f, l, m = batches[1]
     a = float(graphed.step_graphed(f, l, m))
     m2 = np.roll(m, 1, axis=1)
     b = float(graphed.step_graphed(f, l, m2))
     assert abs(a - b) > 1e-6
+
+
+def test_head_train_step_is_bit_reproducible():
+    """Two trainers built from the same seed and fed the same batches end with IDENTICAL parameters: every reduction of
+    the head (LayerNorm affine gradients, token scatter, objective, linear weight / bias gradients) sums in a fixed
+    order - no floating-point atomics on this path."""
+    from cervix_b200.engine import FusionTrainer
+    types = ["imgN", "imgA", "imgL", "cli"]
+    G = 16
+    edges = {"imgN": get_edge_index_image(), "imgA": get_edge_index_image(), "imgL": get_edge_index_image(),
+             "cli": get_edge_index_full(4)}
+    rng = np.random.RandomState(3)
+    feats = {m: rnd(G, 4 if m == "cli" else 16, 1024, seed=70 + i) for i, m in enumerate(types)}
+    labels = torch.from_numpy(rng.randint(0, 4, G)).cuda()
+    masks = np.ones((G, 4), dtype=bool)
+    masks[np.arange(G), rng.randint(0, 4, G)] = False
+    finals, losses = [], []
+    for _ in range(2):
+        torch.manual_seed(0)
+        head = fusion_model_mae_2(1024, 512, 512, 0.3, 4).cuda().eval()
+        tr = FusionTrainer(head, types, lr=1e-3, weight_decay=1e-3)
+        losses.append([float(tr.step(feats, edges, labels, masks)) for _ in range(3)])
+        finals.append((tr.flat.data.clone(), tr.flat.grad.clone()))
+    assert losses[0] == losses[1], losses
+    assert torch.equal(finals[0][1], finals[1][1]), float((finals[0][1] - finals[1][1]).abs().max())
+    assert torch.equal(finals[0][0], finals[1][0])
 
 
 @pytest.mark.parametrize("tag", FC.variant_tags())
