@@ -4,8 +4,10 @@
 
 One "step" = one full training step (forward, focal+dice loss, backward, gradient all-reduce
 over NCCL for N>1, fused Adam) on a synthetic batch of B images per GPU (weak scaling).  Rank 0
-prints ONE JSON line (contract in the round brief).  ``--impl reference`` times the CPU oracle
-port of the reference's own train step on the host cores instead.
+prints ONE JSON line (contract in the round brief).  ``--impl reference`` times the UNMODIFIED reference's own
+``fit_one_epoch`` (installed under baseline/_ref by oracle/build_ref.py) on the host cores instead; when that install
+is absent it falls back to the oracle port and says so (``kind``).  The product arm never imports ``oracle/``: the
+reference legs (``cpu_baseline``, ``torch_gpu_baseline``) run ``oracle/ref_runner.py`` in a subprocess.
 """
 from __future__ import annotations
 
@@ -138,22 +140,93 @@ def cpu_train_throughput(steps: int, warmup: int, budget_s: float, size: int = 5
     return batch / sec, len(times), cores, sec
 
 
+def cpu_model_name() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def ref_subprocess(argv, timeout_s: float):
+    """Run oracle/ref_runner.py (the unmodified reference's fit_one_epoch on synthetic batches) in a child process and
+    return its JSON line, or {"error": ...}.  A child keeps the reference's top-level ``nets`` / ``utils`` packages and its
+    cuDNN state out of this process."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py")] + [str(a) for a in argv]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout_s, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        return {"error": "timed out after %.0f s" % timeout_s}
+    for line in reversed(out.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            try:
+                return json.loads(line)
+            except ValueError:
+                break
+    return {"error": "rc=%d: %s" % (out.returncode, (out.stderr or out.stdout).strip().splitlines()[-1:] or "no output")}
+
+
+def reference_installed() -> bool:
+    return os.path.exists(os.path.join(ROOT, "baseline", "_ref", "MANIFEST.json"))
+
+
+def cpu_reference_baseline(steps: int, warmup: int, budget_s: float):
+    """The reference's CPU path for this workload on the box's host cores: its own fit_one_epoch (fp32 eager, all
+    threads) on batch-2 steps at 512x512 (BatchNorm needs >= 2 images; a batch-32 step is ~20 s of CPU work).  Falls back
+    to the oracle port when baseline/_ref is not installed."""
+    cores = os.cpu_count() or 1
+    if reference_installed():
+        r = ref_subprocess(["--device", "cpu", "--batch", 2, "--steps", steps, "--warmup", warmup, "--threads", cores,
+                            "--budget-s", budget_s], timeout_s=budget_s * 3 + 120)
+        if "error" not in r:
+            return {"value": r["images_per_s"], "unit": UNIT, "cores": cores, "kind": "reference", "cpu": cpu_model_name(),
+                    "sample": "%d timed steps of the unmodified reference's fit_one_epoch (utils_fit.py:31-198; fp32, Adam, "
+                              "focal+dice), Xception ds=16, batch 2 at 512x512 (%.2f s/step)" % (r["steps_timed"], r["ms_per_step"] / 1e3),
+                    "ms_per_step": r["ms_per_step"], "steps": r["steps_timed"]}
+        err = r["error"]
+    else:
+        err = "baseline/_ref not installed"
+    ips, nsteps, cores, sec = cpu_train_throughput(steps, warmup, budget_s=budget_s)
+    return {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "cpu": cpu_model_name(),
+            "sample": "%d timed steps of the oracle port's train step, batch 2 at 512x512 (%.2f s/step); unmodified reference "
+                      "unavailable: %s" % (nsteps, sec, err), "ms_per_step": sec * 1e3, "steps": nsteps}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ips, nsteps, cores, sec = cpu_train_throughput(args.steps, min(args.warmup, 1), budget_s=200.0)
-    sample = "oracle port (torch fp32 eager) of the reference train step, Xception ds=16, batch 2 at 512x512 per step"
+    cb = cpu_reference_baseline(args.steps, min(args.warmup, 1), budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": nsteps,
-        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"],
+        "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DeepLabv3+ Xception ds=16 training step at 512x512 on host CPU cores",
+        "config": {"workload": "DeepLabv3+ Xception ds=16 training step (fwd + focal+dice + bwd + Adam) at 512x512, 5 classes, "
+                               "on the host CPU cores (bounded sample of BASELINE configs[2]: batch 2 per step)",
                    "batch_per_step": 2},
-        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "cpu", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def torch_gpu_baseline(batch: int, size: int):
+    """SURVEY section 8d "the real bar": the unmodified reference's fit_one_epoch on THIS B200 under stock PyTorch / cuDNN
+    with fp16 autocast + GradScaler (train.py:82, utils_fit.py:92-121), same batch; and the same with
+    ``channels_last`` weights and inputs (a tuning the reference does not apply, listed for completeness)."""
+    if not reference_installed():
+        return {"unavailable": "baseline/_ref not installed on this box"}
+    out = {"what": "unmodified reference fit_one_epoch on this GPU, stock PyTorch/cuDNN (cudnn.benchmark as train.py:383), "
+                   "per-step time includes its own H2D copies and .item() syncs", "batch": batch, "size": size}
+    for key, extra in (("fp16_autocast", []), ("fp16_autocast_channels_last", ["--channels-last"])):
+        r = ref_subprocess(["--device", "cuda", "--batch", batch, "--size", size, "--steps", 6, "--warmup", 3, "--fp16"] + extra,
+                           timeout_s=420)
+        out[key] = r if "error" in r else {"images_per_s": r["images_per_s"], "ms_per_step": r["ms_per_step"],
+                                            "steps": r["steps_timed"]}
+    return out
 
 
 # ----------------------------------------------------------------------------- four-modal classifier leg
@@ -219,7 +292,7 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
 
         # the head's step is ~600 launches of a few microseconds: captured once as a CUDA graph (new masks, dropout
         # streams and Adam step count reach every replay through device memory), eager with --no-graph
-        for _ in range(max(warmup, 2)):          # untimed encoder passes (allocator, lazy weight folding)
+        for _ in range(max(warmup, 4)):          # untimed encoder passes (allocator, lazy weight folding, clocks)
             encode()
         torch.cuda.synchronize()
         if use_graph:
@@ -238,16 +311,76 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
             ev[0].record(); f = encode(); ev[1].record(); loss = head_step(f); ev[2].record()
             torch.cuda.synchronize()
             enc_ms += ev[0].elapsed_time(ev[1]); head_ms += ev[1].elapsed_time(ev[2])
-        t = torch.tensor([enc_ms / steps, head_ms / steps], dtype=torch.float64, device="cuda")
+        # ---- end to end: the patients' images start in pinned HOST memory every step (fp32 [modality, patient, 3, H, W],
+        # what the reference's PIL -> ToTensor path produces); the copy of step i+1 runs on a side stream under the compute
+        # of step i (two device buffers); the loss is read back every step
+        n_img_all = len([m for m in types if m in img_index])
+        e2e_ms = None
+        if n_img_all:
+            used = sorted(img_index[m] for m in types if m in img_index)
+            host = imgs[used].cpu().pin_memory()
+            dev_buf = [torch.empty_like(imgs[used]) for _ in range(2)]
+            copy_stream = torch.cuda.Stream()
+            done = [torch.cuda.Event(), torch.cuda.Event()]
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+            def fetch(k):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done[k & 1])
+                    dev_buf[k & 1].copy_(host, non_blocking=True)
+                    ready[k & 1].record(copy_stream)
+
+            def encode_from(buf):
+                feats = {}
+                with torch.no_grad():
+                    for j, m in enumerate(mm for mm in types if mm in img_index):
+                        f = [enc.encode_images(buf[j, i:i + chunk]) for i in range(0, patients, chunk)]
+                        feats[m] = torch.cat(f).view(patients, 16, 1024)
+                if "cli" in types:
+                    feats["cli"] = cli
+                return feats
+
+            torch.cuda.synchronize()
+            for e in done:
+                e.record()
+            t0 = time.perf_counter()
+            ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ee0.record()
+            fetch(0)
+            prev = None
+            for k in range(steps):
+                if k + 1 < steps:
+                    fetch(k + 1)
+                torch.cuda.current_stream().wait_event(ready[k & 1])
+                l = head_step(encode_from(dev_buf[k & 1]))
+                done[k & 1].record()
+                l = l.clone()
+                if prev is not None:
+                    float(prev)
+                prev = l
+            float(prev)
+            ee1.record()
+            torch.cuda.synchronize()
+            e2e_ms = max(ee0.elapsed_time(ee1), (time.perf_counter() - t0) * 1e3) / steps
+            h2d = host.numel() * 4
+            del host, dev_buf
+        t = torch.tensor([enc_ms / steps, head_ms / steps, e2e_ms or 0.0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        enc_ms, head_ms = float(t[0]), float(t[1])
+        enc_ms, head_ms, e2e_ms = float(t[0]), float(t[1]), float(t[2])
         ms = enc_ms + head_ms
-        results.append({"modalities": types, "patients_per_s": world * patients / (ms * 1e-3),
-                        "images_per_s": world * n_img * patients / (ms * 1e-3), "ms_per_step": ms, "encoder_ms": enc_ms,
-                        "head_ms": head_ms,
-                        "encoder_tflops_per_gpu": (n_img * patients * 16 * 20.38e9 / (enc_ms * 1e-3) / 1e12) if n_img else None,
-                        "loss_last_step": float(loss)})
+        enc_tf = (n_img * patients * 16 * 20.38e9 / (enc_ms * 1e-3) / 1e12) if n_img else None
+        res = {"modalities": types, "patients_per_s": world * patients / (ms * 1e-3),
+               "images_per_s": world * n_img * patients / (ms * 1e-3), "ms_per_step": ms, "encoder_ms": enc_ms,
+               "head_ms": head_ms, "steps": steps, "encoder_tflops_per_gpu": enc_tf, "loss_last_step": float(loss)}
+        if e2e_ms:
+            res["e2e"] = {"value": world * patients / (e2e_ms * 1e-3), "unit": "patients/s", "ms_per_step": e2e_ms,
+                          "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+        if enc_tf:
+            res["roofline"] = {"bound": "tensor", "scope": "ResNet-101 patch encoder forward (20.38 GF per 256x256 patch)",
+                               "achieved": enc_tf, "peak": load_peaks()["tf_sustained"], "unit": "TFLOP/s",
+                               "frac": enc_tf / load_peaks()["tf_sustained"]}
+        results.append(res)
         del trainer, head
     out = dict(results[0])
     out["workload"] = ("%d-modal severity classifier train step, %d patients per GPU x %d images %dx%d (ResNet-101 patch "
@@ -261,40 +394,117 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
     return out
 
 
+def classifier_cpu_baseline(size: int = 512, reps: int = 1):
+    """CPU baseline of the classifier's train step on a BOUNDED sample (one patient = 3 images = 48 patches): the
+    reference's own feature extractor - torchvision ``resnet101`` with ``fc = Linear(2048, 1024)`` in eval mode, one
+    batch of the 48 ImageNet-normalised 256x256 crops of the 1024x1024 bilinear resize
+    (Graph_Structure(data_augmentation).py:136-200) - followed by the oracle port of the fusion head's forward, objective
+    and backward for that patient (oracle/fusion_ref.py), all host threads, fp32."""
+    import torch
+    import torch.nn.functional as F
+    import torchvision
+    from cervix_b200.multimodal.my_mae_model import fusion_model_mae_2
+    from oracle import fusion_ref as FR
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    enc = torchvision.models.resnet101(weights=None)
+    enc.fc = torch.nn.Linear(2048, 1024)
+    enc.eval()
+    state = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in
+             fusion_model_mae_2(1024, 512, 512, 0.3, 4).state_dict().items()}
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    imgs = torch.rand(3, 3, size, size)
+    mask = [False, True, True, True]
+    times = []
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            big = F.interpolate(imgs, size=(1024, 1024), mode="bilinear", align_corners=False)
+            patches = torch.stack([big[m, :, y:y + 256, x:x + 256] for m in range(3) for x in range(0, 1024, 256)
+                                   for y in range(0, 1024, 256)])
+            feats = enc((patches - mean) / std)
+        graph = {"x_imgN": feats[0:16], "x_imgA": feats[16:32], "x_imgL": feats[32:48], "x_cli": torch.randn(4, 1024),
+                 "edge_index_imageN": FR.image_edge_index(), "edge_index_imageA": FR.image_edge_index(),
+                 "edge_index_imageL": FR.image_edge_index(), "edge_index_cli": FR.cli_edge_index()}
+        out = FR.fusion_forward(graph, state, mask=mask)
+        loss = FR.fusion_loss([out], [mask], torch.tensor([1]))
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+    sec = sum(times[1:]) / len(times[1:])
+    return {"value": 1.0 / sec, "unit": "patients/s", "cores": cores, "kind": "port", "cpu": cpu_model_name(),
+            "sample": "%d timed single-patient steps (48 patches through torchvision resnet101 fp32 + oracle fusion head "
+                      "fwd/objective/bwd), %.2f s each" % (reps, sec)}
+
+
 # ----------------------------------------------------------------------------- our arm
-def time_dominant_kernel(batch: int, peaks):
-    """Roofline of the dominant kernel class: the tcgen05 implicit-GEMM conv, timed on the
-    decoder's 3x3 304->256 @128x128 convolution (22.95 GF per image forward, the largest single
-    launch of the step).  CUDA events on the launching stream, L2 flushed between launches."""
+def _time_launch(fn, flush, reps: int = 10):
+    """Average duration of one launch: CUDA events on the launching (current) stream, L2 flushed between launches."""
+    import torch
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts)
+
+
+def kernel_rooflines(batch: int, peaks):
+    """Live per-launch rooflines of the kernels that dominate the step (ncu launch list: profiles/r02_ncu_launches_*):
+      * tensor: the middle-flow pointwise GEMM 728 -> 728 @32x32 (150 launches per step = the time-dominant GEMM shape:
+        forward with the BatchNorm-statistics epilogue, weight gradient), and the decoder 3x3 304 -> 256 @128x128 (the
+        largest single launch) for contrast;
+      * hbm: the fused depthwise backward of the same middle-flow tensor (the time-dominant bandwidth kernel).
+    Algorithmic flops = 2*M*N*K; algorithmic bytes = each tensor the kernel must touch, once."""
     import torch
     from cervix_b200.backend import ConvGeom, get_backend
     B = get_backend()
-    g = ConvGeom(batch, 128, 128, 304, 256, 3, 3, 1, 1, 1)
-    x = torch.randn((batch, 128, 128, 304), device="cuda").bfloat16()
-    wp = torch.randn((9, 256, 304), device="cuda").bfloat16()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    for _ in range(3):
-        B.conv_fwd(x, wp, None, g, True)
-    ts = []
-    for _ in range(10):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); B.conv_fwd(x, wp, None, g, True); e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ms = sum(ts) / len(ts)
-    flops = 2.0 * batch * 128 * 128 * 256 * 304 * 9
-    achieved = flops / (ms * 1e-3) / 1e12
-    # DRAM traffic of this launch from the committed `ncu --set full` capture at batch 32
-    # (profiles/r01_ncu_conv_kernels_v6.txt: dram__bytes_read.sum 320.2 MB + dram__bytes_write.sum 233.6 MB; the
-    # algorithmic bytes are 318.8 MB of input + 268.4 MB of output + 1.4 MB of weights - the tail of the output is
-    # still in L2 when the capture ends).  Reported only for the batch it was captured at.
-    traffic = 553.8e6 if batch == 32 else None
-    return {"bound": "tensor", "kernel": "conv_tc_fwd_2cta_kernel<false, 1> (cat_conv.0: 3x3 304->256 @128x128, batch %d)" % batch,
-            "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
-            "traffic": traffic, "traffic_source": "ncu --set full, profiles/r01_ncu_conv_kernels_v6.txt (bytes per launch)",
-            "peak_source": peaks["source"] + " burst bf16 (kernel timed alone)",
-            "flops_per_launch": flops, "ms_per_launch": ms}
+    bf = lambda *shape: torch.randn(shape, device="cuda").bfloat16()   # noqa: E731
+    out = {}
+    # ---- middle-flow pointwise GEMM
+    g = ConvGeom(batch, 32, 32, 728, 728, 1, 1, 1, 0, 1)
+    x, dy, wp = bf(batch, 32, 32, 728), bf(batch, 32, 32, 728), bf(1, 728, 728)
+    bias = torch.zeros(728, device="cuda")
+    flops = 2.0 * batch * 32 * 32 * 728 * 728
+    ms_f = _time_launch(lambda: B.conv_fwd_ex(x, wp, bias, g, want_stats=True), flush)
+    ms_w = _time_launch(lambda: B.conv_wgrad(x, dy, g, True), flush)
+    out["mid_pw_fwd"] = {"kernel": "conv_tc_fwd_2cta_kernel<1, 2> (middle-flow pointwise 728->728 @32x32, batch %d, BN statistics "
+                                   "epilogue; 51 launches/step)" % batch, "ms_per_launch": ms_f, "flops_per_launch": flops,
+                         "achieved": flops / (ms_f * 1e-3) / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s"}
+    out["mid_pw_wgrad"] = {"kernel": "conv_tc_wgrad_2cta_kernel (same shape; 51 launches/step)", "ms_per_launch": ms_w,
+                           "flops_per_launch": flops, "achieved": flops / (ms_w * 1e-3) / 1e12, "peak": peaks["tf_burst"],
+                           "unit": "TFLOP/s"}
+    # ---- largest single launch
+    g2 = ConvGeom(batch, 128, 128, 304, 256, 3, 3, 1, 1, 1)
+    x2, wp2 = bf(batch, 128, 128, 304), bf(9, 256, 304)
+    flops2 = 2.0 * batch * 128 * 128 * 256 * 304 * 9
+    ms2 = _time_launch(lambda: B.conv_fwd(x2, wp2, None, g2, True), flush)
+    out["cat_conv0_fwd"] = {"kernel": "conv_tc_fwd_2cta_kernel<0, 1> (decoder 3x3 304->256 @128x128, batch %d)" % batch,
+                            "ms_per_launch": ms2, "flops_per_launch": flops2, "achieved": flops2 / (ms2 * 1e-3) / 1e12,
+                            "peak": peaks["tf_burst"], "unit": "TFLOP/s"}
+    for v in out.values():
+        v["frac"] = v["achieved"] / v["peak"]
+        v["peak_source"] = peaks["source"] + " burst bf16 (kernel timed alone)"
+    del x2, wp2
+    # ---- dominant bandwidth kernel: fused depthwise backward (data + weight gradient + BatchNorm backward sums)
+    gd = ConvGeom(batch, 32, 32, 728, 728, 3, 3, 1, 1, 1)
+    w9c = torch.randn(9, 728, device="cuda")
+    sc, sh = torch.rand(728, device="cuda") + 0.5, torch.randn(728, device="cuda") * 0.1
+    ms_d = _time_launch(lambda: B.dwf_bwd(dy, None, None, None, x, w9c, sc, sh, True, None, gd, True), flush)
+    nbytes = 3.0 * batch * 32 * 32 * 728 * 2          # read dd, read x, write g (bf16)
+    hbm = {"bound": "hbm", "kernel": "dwf_bwd_kernel<true, false> (depthwise 3x3 backward of the middle-flow tensor [%d,32,32,728]: "
+                                      "data gradient + weight gradient + previous BatchNorm's backward sums; 37 launches/step)" % batch,
+           "achieved": nbytes / (ms_d * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "bytes_per_launch": nbytes,
+           "ms_per_launch": ms_d, "peak_source": peaks["source"] + " HBM copy bandwidth",
+           "traffic": None, "traffic_source": "see profiles/ (ncu --set full of this launch)"}
+    hbm["frac"] = hbm["achieved"] / hbm["peak"]
+    return out, hbm
 
 
 def run_ours(args):
@@ -371,44 +581,55 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     losses = [float(v) for v in res.cpu()]
 
-    # ---- end to end: every step's batch comes from pinned HOST memory (imgs fp32 + int64 class map,
-    # the one-hot labels are derived on the device), prefetched one step ahead on a copy stream;
-    # the 4 loss/metric scalars are read back to the host every step.
+    # ---- end to end: every step's batch comes from pinned HOST memory, prefetched one step ahead on a copy stream
+    # (two device buffer sets, so two copies can be in flight); the 4 loss/metric scalars are read back to the host every
+    # step.  Two input contracts are timed:
+    #   "u8"   what a loader decodes: uint8 [B,H,W,3] pixels + uint8 class maps (dataloader.py:40-42 run on the device by
+    #          cvx_finish_batch_u8) - 1 MB per image; this is the headline e2e
+    #   "f32"  the reference DataLoader's tensors as they arrive in fit_one_epoch (utils_fit.py:52-58): fp32 NCHW images +
+    #          int64 class maps - 5.2 MB per image
     from cervix_b200.engine import BatchPrefetcher
 
-    def host_batches(k):
-        for _ in range(k):
-            yield (imgs_h, pngs_h)
+    def e2e_run(host_batch, k):
+        def host_batches(n):
+            for _ in range(n):
+                yield host_batch
+        for bi, bp in BatchPrefetcher(host_batches(2)):
+            step_fn(bi, bp, None).cpu()
+        sync_all()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e2.record()
+        pf = BatchPrefetcher(host_batches(k))            # first copy is inside the timed region
+        prev = None
+        for bi, bp in pf:
+            r = step_fn(bi, bp, None)
+            if use_graph:
+                r = r.clone()                             # the graph's output buffer is overwritten by the next replay
+            if prev is not None:
+                prev.cpu()                                # result of the previous step (keeps 1 step in flight)
+            prev = r
+        prev.cpu()
+        e3.record()
+        sync_all()
+        return max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
 
-    for bi, bp in BatchPrefetcher(host_batches(2)):
-        step_fn(bi, bp, None).cpu()
-    sync_all()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e2.record()
-    pf = BatchPrefetcher(host_batches(args.steps))   # first copy is inside the timed region
-    prev = None
-    for bi, bp in pf:
-        r = step_fn(bi, bp, None)
-        if use_graph:
-            r = r.clone()                             # the graph's output buffer is overwritten by the next replay
-        if prev is not None:
-            prev.cpu()                                # result of the previous step (keeps 1 step in flight)
-        prev = r
-    prev.cpu()
-    e3.record()
-    sync_all()
-    ms_e2e = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    ms_e2e_f32 = e2e_run((imgs_h, pngs_h), args.steps)
+    imgs_u8_h = (imgs_h.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
+    pngs_u8_h = pngs_h.to(torch.uint8).pin_memory()
+    if use_graph:
+        trainer.capture(imgs_u8_h.cuda(), pngs_u8_h.cuda(), None)      # same step over uint8 static input buffers
+    ms_e2e = e2e_run((imgs_u8_h, pngs_u8_h), args.steps)
 
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_total, ms_e2e, ms_e2e_f32], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_total, ms_e2e, ms_e2e_f32 = float(t[0]), float(t[1]), float(t[2])
     classifier = None
     if not args.no_classifier:      # every rank takes part (patients are sharded, head gradients all-reduced)
-        del step_fn, trainer, model, pf
+        del step_fn, trainer, model
         torch.cuda.empty_cache()
-        classifier = classifier_throughput(max(2, min(args.steps, 4)), 2, patients=16 if world == 1 else 64,
+        classifier = classifier_throughput(max(args.steps, 20), 3, patients=16 if world == 1 else 64,
                                            world=world, rank=rank,
                                            variants=(("imgN", "imgA", "imgL", "cli"), ("imgN", "imgA", "imgL"), ("imgN", "imgL")),
                                            use_graph=use_graph)
@@ -420,15 +641,35 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * bsz * args.steps / (ms_total * 1e-3)
     e2e_value = world * bsz * args.steps / (ms_e2e * 1e-3)
-    roof = time_dominant_kernel(bsz, peaks)
+    e2e_f32_value = world * bsz * args.steps / (ms_e2e_f32 * 1e-3)
+    kernels, roof_hbm = kernel_rooflines(bsz, peaks)
     step_tf = value / world * TRAIN_GFLOP_PER_IMAGE / 1e3
-    cpu_ips, cpu_steps, cores, cpu_sec = (None, 0, os.cpu_count(), None)
-    cpu_baseline = None
+    # `roofline` describes the STEP (what the metric measures): convolution flops of one training step / step time against
+    # the sustained bf16 peak.  `dominant_kernel` is the time-dominant GEMM shape of the committed launch list, timed live;
+    # `roofline_hbm` is the time-dominant bandwidth kernel.
+    roof = {"bound": "tensor", "scope": "whole training step (all kernels, GEMM and bandwidth-bound alike)",
+            "achieved": step_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": step_tf / peaks["tf_sustained"],
+            "flops_per_step": TRAIN_GFLOP_PER_IMAGE * 1e9 * bsz, "ms_per_step": ms_step,
+            "peak_source": peaks["source"] + " sustained bf16 (kernel timed inside a long step)",
+            "traffic": None, "kernel": kernels["mid_pw_fwd"]["kernel"], "dominant_kernel": kernels["mid_pw_fwd"],
+            "other_kernels": {k: v for k, v in kernels.items() if k != "mid_pw_fwd"}}
+    cpu_baseline = torch_gpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_ips, cpu_steps, cores, cpu_sec = cpu_train_throughput(3, 1, budget_s=45.0)
-        cpu_baseline = {"value": cpu_ips, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "%d timed steps of the oracle port's train step, batch 2 at 512x512 (%.1f s/step)" % (cpu_steps, cpu_sec)}
-    h2d = imgs_h.numel() * 4 + pngs_h.numel() * 8
+        torch.cuda.empty_cache()
+        cb = cpu_reference_baseline(4, 1, budget_s=25.0)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "cpu", "sample")}
+    if world == 1 and not args.no_gpu_baseline:
+        torch.cuda.empty_cache()
+        torch_gpu = torch_gpu_baseline(bsz, size)
+        for k in ("fp16_autocast", "fp16_autocast_channels_last"):
+            if isinstance(torch_gpu.get(k), dict) and "images_per_s" in torch_gpu[k]:
+                torch_gpu[k]["ours_over_this"] = value / torch_gpu[k]["images_per_s"]
+                torch_gpu[k]["ours_e2e_over_this"] = e2e_value / torch_gpu[k]["images_per_s"]
+    if classifier is not None and world == 1 and not args.no_cpu_baseline:
+        try:
+            classifier["cpu_baseline"] = classifier_cpu_baseline()
+        except Exception as e:   # torchvision missing etc.: report, never fail the bench line
+            classifier["cpu_baseline"] = {"error": repr(e)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -439,12 +680,15 @@ def run_ours(args):
                    "cuda_graph": bool(use_graph),
                    "l2": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2"},
         "roofline": roof,
-        "step_tensor": {"achieved_tflops_per_gpu": step_tf, "peak": peaks["tf_sustained"],
-                        "frac": step_tf / peaks["tf_sustained"], "flops_per_image": TRAIN_GFLOP_PER_IMAGE * 1e9,
-                        "peak_source": peaks["source"] + " sustained bf16"},
+        "roofline_hbm": roof_hbm,
         "cpu_baseline": cpu_baseline,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
-                "ms_per_step": ms_e2e / args.steps},
+        "torch_gpu_baseline": torch_gpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": imgs_u8_h.numel() + pngs_u8_h.numel(),
+                "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps,
+                "inputs": "pinned host uint8 [B,H,W,3] pixels + uint8 class maps (what a loader decodes)",
+                "fp32_contract": {"value": e2e_f32_value, "h2d_bytes_per_step": imgs_h.numel() * 4 + pngs_h.numel() * 8,
+                                  "ms_per_step": ms_e2e_f32 / args.steps,
+                                  "inputs": "pinned host fp32 NCHW images + int64 class maps (utils_fit.py:52-58)"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "classifier": classifier,
@@ -464,6 +708,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch run of the reference on this GPU")
     ap.add_argument("--no-classifier", action="store_true", help="skip the severity-classifier leg")
     ap.add_argument("--no-graph", action="store_true", help="run the single-GPU step eagerly instead of as a CUDA graph")
     args = ap.parse_args()
