@@ -285,6 +285,10 @@ CVX_API int cvx_adam_step(float* p, const float* g, float* m, float* v, int64_t 
 CVX_API int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, const int* step,
                       void* stream);
 /* torch.optim.SGD(momentum, nesterov) semantics */
+/* torch.optim.SGD(momentum, nesterov, weight_decay) (train.py:475) with lr / momentum / weight decay / gradient scale read
+ * from device memory: hyper = {lr, momentum, -, -, weight_decay, grad_scale} (the layout of cvx_adam_step_dev), so a
+ * captured CUDA graph follows the per-epoch learning-rate schedule (train.py:575).  buf starts zeroed. */
+CVX_API int cvx_sgd_step_dev(float* p, const float* g, float* buf, int64_t n, const float* hyper, int nesterov, void* stream);
 CVX_API int cvx_sgd_step(float* p, const float* g, float* buf, int64_t n, float lr, float momentum,
                  float weight_decay, int nesterov, int first_step, float grad_scale, void* stream);
 
@@ -317,6 +321,15 @@ CVX_API int cvx_confusion_matrix(const unsigned char* pred, const unsigned char*
  * floats. */
 CVX_API int cvx_split_patches(const float* images, void* patches, int n, int c, int h, int w, int new_size, int patch,
                               const float* mean, const float* std, int dtype, void* stream);
+/* The same pipeline on the DECODED uint8 image [n,h,w,3], reproducing PIL.Image.resize(BILINEAR) exactly (Pillow
+ * Resample.c: horizontal then vertical fixed-point pass with 22 fractional bits, uint8 rounding after each pass, a
+ * triangle that widens when the image is reduced).  xmin/xcnt [new_size], xk [new_size][xksize] (likewise y*): first
+ * source index, tap count and integer weights per output coordinate, device arrays built by the host
+ * (multimodal/pil_resample.py).  value = ((u8 / 255) - mean[c]) / std[c] with IEEE divisions. */
+CVX_API int cvx_split_patches_u8(const unsigned char* images, void* patches, int n, int h, int w, int c, int new_size,
+                                 int patch, const int* xmin, const int* xcnt, const int* xk, int xksize, const int* ymin,
+                                 const int* ycnt, const int* yk, int yksize, const float* mean, const float* std, int dtype,
+                                 void* stream);
 /* Tail of the segmentation loader on the device (reference: SEG/utils/dataloader.py:40-42 + utils/utils.py:63-65
  * preprocess_input): images_u8 (n_image_elems bytes, [n][h][w][3] as PIL / numpy hold them, 16-byte aligned) -> NHWC
  * activation in `dtype` scaled by 1/255 (nullable together with images_out); labels_u8 (n_pixels bytes, nullable together

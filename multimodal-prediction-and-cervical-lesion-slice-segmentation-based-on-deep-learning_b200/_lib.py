@@ -101,11 +101,14 @@ PROTOTYPES = {
     "cvx_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
     "cvx_adam_step_dev": [_P, _P, _P, _P, _L, _P, _P, _P],
     "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],
+    "cvx_sgd_step_dev": [_P, _P, _P, _L, _P, _I, _P],
     "cvx_multi_gather_chunk": [],
     "cvx_multi_gather": [_P, _P, _P, _P, _P, _I, _P, _P],
     "cvx_seg_postprocess": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "cvx_confusion_matrix": [_P, _P, _L, _I, _P, _P],
     "cvx_split_patches": [_P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _I, _P],
+    "cvx_split_patches_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, C.POINTER(C.c_float),
+                             C.POINTER(C.c_float), _I, _P],
     "cvx_finish_batch_u8": [_P, _P, _L, _P, _P, _L, _I, _I, _P],
 }
 _RESTYPES = {"cvx_last_error": C.c_char_p, "cvx_launch_count": C.c_int64}

@@ -100,6 +100,31 @@ class CudaBackend:
               "cvx_split_patches")
         return y
 
+    def split_patches_u8(self, images: torch.Tensor, new_size: int, patch: int, mean, std, dtype: torch.dtype) -> torch.Tensor:
+        """[n,h,w,3] uint8 (decoded images) -> [n*k*k, patch, patch, 3] NHWC `dtype`, bit-exact with
+        PIL.Image.resize((new_size, new_size), BILINEAR) -> crops -> ToTensor -> Normalize (cvx_split_patches_u8)."""
+        from .multimodal.pil_resample import bilinear_tables
+        self._chk(images)
+        if images.dtype != torch.uint8 or images.dim() != 4:
+            raise TypeError("split_patches_u8: uint8 [n,h,w,3] images expected, got %s %s" % (images.dtype, tuple(images.shape)))
+        n, h, w, c = images.shape
+        k = new_size // patch
+        key = (h, w, new_size, str(images.device))
+        tabs = self._pil_tables.get(key) if hasattr(self, "_pil_tables") else None
+        if tabs is None:
+            if not hasattr(self, "_pil_tables"):
+                self._pil_tables = {}
+            tabs = self._pil_tables[key] = tuple(torch.from_numpy(a).to(images.device).contiguous()
+                                                 for a in bilinear_tables(w, new_size) + bilinear_tables(h, new_size))
+        xmin, xcnt, xk, ymin, ycnt, yk = tabs
+        y = torch.empty((n * k * k, patch, patch, c), dtype=dtype, device=images.device)
+        m = (C.c_float * c)(*[float(v) for v in mean])
+        s = (C.c_float * c)(*[float(v) for v in std])
+        check(self.lib.cvx_split_patches_u8(_p(images), _p(y), n, h, w, c, new_size, patch, _p(xmin), _p(xcnt), _p(xk),
+                                            int(xk.shape[1]), _p(ymin), _p(ycnt), _p(yk), int(yk.shape[1]), m, s, _dt(y),
+                                            self._stream()), "cvx_split_patches_u8")
+        return y
+
     def finish_batch_u8(self, images_u8: torch.Tensor, labels_u8: Optional[torch.Tensor], num_classes: int,
                         dtype: torch.dtype):
         """uint8 [n,h,w,3] pixels (+ uint8 [n,h,w] class map) -> (NHWC activation / 255 in `dtype`, int64 class map
@@ -664,6 +689,11 @@ class CudaBackend:
         self._chk(p, g, buf)
         check(self.lib.cvx_sgd_step(_p(p), _p(g), _p(buf), p.numel(), float(lr), float(momentum), float(wd),
                                     int(nesterov), int(first_step), float(grad_scale), self._stream()), "cvx_sgd_step")
+
+    def sgd_step_dev(self, p, g, buf, hyper, nesterov: bool):
+        self._chk(p, g, buf, hyper)
+        check(self.lib.cvx_sgd_step_dev(_p(p), _p(g), _p(buf), p.numel(), _p(hyper), int(nesterov), self._stream()),
+              "cvx_sgd_step_dev")
 
     def multi_gather_chunk(self) -> int:
         return int(self.lib.cvx_multi_gather_chunk())

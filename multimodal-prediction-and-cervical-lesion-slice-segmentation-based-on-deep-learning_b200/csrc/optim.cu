@@ -82,6 +82,25 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
   }
 }
 
+// graph-capturable SGD: lr / momentum / weight decay / gradient scale from device memory (hyper layout shared with
+// adam_dev_kernel: [lr, momentum, -, -, weight_decay, grad_scale]).  torch's first-step rule (buf = grad) is what a
+// zero-initialised momentum buffer gives, so no step count is needed.
+__global__ void sgd_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n,
+                               const float* __restrict__ hyper, int nesterov) {
+  const float lr = hyper[0], mom = hyper[1], wd = hyper[4], gscale = hyper[5];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gscale;
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    if (mom != 0.f) {
+      const float b = fmaf(mom, buf[i], gi);
+      buf[i] = b;
+      gi = nesterov ? fmaf(mom, b, gi) : b;
+    }
+    p[i] = pi - lr * gi;
+  }
+}
+
 }  // namespace cvx
 
 using namespace cvx;
@@ -105,6 +124,14 @@ int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
   CVX_CHECK_ARG(p && g && m && v && hyper && step && n > 0, "adam_step_dev: bad arguments");
   int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
   adam_dev_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, hyper, step);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_sgd_step_dev(float* p, const float* g, float* buf, int64_t n, const float* hyper, int nesterov, void* stream) {
+  CVX_CHECK_ARG(p && g && buf && hyper && n > 0, "sgd_step_dev: bad arguments");
+  int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
+  sgd_dev_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, buf, n, hyper, nesterov);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

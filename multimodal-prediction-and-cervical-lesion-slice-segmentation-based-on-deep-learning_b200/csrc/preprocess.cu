@@ -78,6 +78,75 @@ __global__ void __launch_bounds__(256) split_patches_kernel(const float* __restr
   }
 }
 
+// ---- Pillow-exact variant on the decoded uint8 image ------------------------------------------------------------------
+// PIL.Image.resize(..., BILINEAR) on 8-bit images (Pillow Resample.c) is a separable fixed-point filter: horizontal pass
+// first, rounded and clipped to uint8, then the vertical pass on those bytes; weights carry 22 fractional bits, the
+// accumulator starts at one half; the triangle widens when the image is reduced (antialiasing) and is renormalised at the
+// borders.  The per-axis tables (first tap, tap count, integer weights) come from the host (multimodal/pil_resample.py,
+// checked bit for bit against the installed Pillow); here one thread produces one output pixel: for each of its source
+// rows the horizontal sum -> uint8, then the vertical sum -> uint8, then ToTensor (/255) and Normalize ((v - mean) / std)
+// with IEEE divisions, so an fp32 patch equals transforms.Normalize(ToTensor(patch)) of the reference bit for bit.
+constexpr int kPilBits = 22;
+
+struct PatchNormDiv {
+  float mean[kMaxImgChannels];
+  float std[kMaxImgChannels];
+};
+
+template <typename T, int C>
+__global__ void __launch_bounds__(256) split_patches_u8_kernel(const uint8_t* __restrict__ img, T* __restrict__ out, int h,
+                                                               int w, int new_size, int patch,
+                                                               const int* __restrict__ xmin, const int* __restrict__ xcnt,
+                                                               const int* __restrict__ xk, int xks,
+                                                               const int* __restrict__ ymin, const int* __restrict__ ycnt,
+                                                               const int* __restrict__ yk, int yks, PatchNormDiv nrm,
+                                                               int64_t total) {
+  const int k = new_size / patch;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    // idx enumerates [image][patch = ix*k + iy][py][px]: consecutive threads write consecutive pixels of a patch row
+    int64_t t = idx;
+    const int px = (int)(t % patch); t /= patch;
+    const int py = (int)(t % patch); t /= patch;
+    const int pidx = (int)(t % (k * k)); t /= (k * k);
+    const int64_t n = t;
+    const int ix = pidx / k, iy = pidx % k;          // x-major enumeration (outer loop over columns, :157-160)
+    const int oy = iy * patch + py, ox = ix * patch + px;
+    const int x0 = xmin[ox], nx = xcnt[ox], y0 = ymin[oy], ny = ycnt[oy];
+    const int* kx = xk + (int64_t)ox * xks;
+    const int* ky = yk + (int64_t)oy * yks;
+    const uint8_t* base = img + n * (int64_t)h * w * C;
+    int acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 1 << (kPilBits - 1);
+    for (int r = 0; r < ny; ++r) {
+      const uint8_t* row = base + ((int64_t)(y0 + r) * w + x0) * C;
+      int hs[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) hs[c] = 1 << (kPilBits - 1);
+      for (int x = 0; x < nx; ++x) {
+        const int wgt = __ldg(kx + x);
+#pragma unroll
+        for (int c = 0; c < C; ++c) hs[c] += (int)__ldg(row + x * C + c) * wgt;
+      }
+      const int wy = __ldg(ky + r);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        int b = hs[c] >> kPilBits;                   // the horizontal pass's uint8 result (clip8)
+        b = b < 0 ? 0 : (b > 255 ? 255 : b);
+        acc[c] += b * wy;
+      }
+    }
+    T* dst = out + idx * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int b = acc[c] >> kPilBits;
+      b = b < 0 ? 0 : (b > 255 ? 255 : b);
+      const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)b, 255.f), nrm.mean[c]), nrm.std[c]);
+      Elem<T>::st(dst + c, v);
+    }
+  }
+}
+
 // uint8 [n][h][w][c] -> T [n][h][w][c] * (1/255): 16 input bytes per thread.
 template <typename T>
 __global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst,
@@ -143,6 +212,31 @@ extern "C" int cvx_split_patches(const float* images, void* patches, int n, int 
   const unsigned grid = stream_grid(groups, 256);
   CVX_DISPATCH_DTYPE(dtype, T, (split_patches_kernel<T, 3, 4><<<grid, 256, 0, as_stream(stream)>>>(
                                    images, (T*)patches, h, w, new_size, patch, sy, sx, nrm, groups)));
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+extern "C" int cvx_split_patches_u8(const unsigned char* images, void* patches, int n, int h, int w, int c, int new_size,
+                                    int patch, const int* xmin, const int* xcnt, const int* xk, int xksize, const int* ymin,
+                                    const int* ycnt, const int* yk, int yksize, const float* mean, const float* std,
+                                    int dtype, void* stream) {
+  CVX_CHECK_ARG(images && patches && xmin && xcnt && xk && ymin && ycnt && yk && mean && std, "split_patches_u8: null pointer");
+  CVX_CHECK_ARG(n > 0 && h > 0 && w > 0, "split_patches_u8: bad image batch %dx%dx%d", n, h, w);
+  CVX_CHECK_ARG(c == 3, "split_patches_u8: 3-channel images only (got %d)", c);
+  CVX_CHECK_ARG(patch > 0 && new_size >= patch && new_size % patch == 0 && xksize > 0 && yksize > 0,
+                "split_patches_u8: new_size %d must be a multiple of the patch size %d", new_size, patch);
+  PatchNormDiv nrm;
+  for (int i = 0; i < kMaxImgChannels; ++i) { nrm.mean[i] = 0.f; nrm.std[i] = 1.f; }
+  for (int i = 0; i < c; ++i) {
+    CVX_CHECK_ARG(std[i] != 0.f, "split_patches_u8: std[%d] is zero", i);
+    nrm.mean[i] = mean[i];
+    nrm.std[i] = std[i];
+  }
+  const int64_t total = (int64_t)n * new_size * new_size;
+  const unsigned grid = stream_grid(total, 256);
+  CVX_DISPATCH_DTYPE(dtype, T, (split_patches_u8_kernel<T, 3><<<grid, 256, 0, as_stream(stream)>>>(
+                                   images, (T*)patches, h, w, new_size, patch, xmin, xcnt, xk, xksize, ymin, ycnt, yk, yksize,
+                                   nrm, total)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

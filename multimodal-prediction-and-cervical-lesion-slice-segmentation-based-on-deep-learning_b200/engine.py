@@ -20,11 +20,13 @@ from .nets.deeplabv3_training import seg_objective
 
 
 class FlatParams:
-    """All trainable parameters of a module re-homed into ONE contiguous fp32 buffer (and their
-    ``.grad`` into a second one), so the optimizer and the all-reduce see a single tensor."""
+    """Parameters of a module re-homed into ONE contiguous fp32 buffer (and their ``.grad`` into a second one), so the
+    optimizer and the all-reduce see a single tensor.  ``trainable_only=False`` takes every parameter, frozen ones
+    included, so that a later ``requires_grad = True`` (the reference's Freeze_Train schedule, train.py:531-551) needs no
+    re-homing and keeps the optimizer state."""
 
-    def __init__(self, module: torch.nn.Module):
-        self.params = [p for p in module.parameters() if p.requires_grad]
+    def __init__(self, module: torch.nn.Module, trainable_only: bool = True):
+        self.params = [p for p in module.parameters() if p.requires_grad or not trainable_only]
         dev = self.params[0].device
         self.offsets, off = [], 0
         for p in self.params:
@@ -40,60 +42,89 @@ class FlatParams:
             self.grad_views.append(self.grad[o:o + p.numel()].view(p.shape))
         self.attach_grad_views()
 
+    def padded(self, i: int) -> int:
+        return (self.params[i].numel() + 3) // 4 * 4
+
     def attach_grad_views(self):
         """``p.grad`` = a view of the flat gradient: autograd then accumulates in place (one add kernel per parameter)."""
         for p, g in zip(self.params, self.grad_views):
-            if p.grad is not g:
+            if p.requires_grad and p.grad is not g:
                 p.grad = g
 
     def detach_grads(self):
         """``p.grad = None``: autograd then just keeps the gradient tensor each backward produced (no kernel), and
-        ``GradGather`` copies all of them into the flat buffer in one launch."""
+        ``GradGather`` copies them into the flat buffer one bucket per launch."""
         for p in self.params:
             p.grad = None
 
 
 class GradGather:
-    """One-launch gather of the per-parameter gradients into ``FlatParams.grad`` (C ABI: cvx_multi_gather)."""
+    """One-launch gather of the gradients of parameters ``idx`` into ``FlatParams.grad`` (C ABI: cvx_multi_gather)."""
 
-    def __init__(self, flat: FlatParams):
+    def __init__(self, flat: FlatParams, idx: Optional[List[int]] = None):
         B = get_backend()
         ch = B.multi_gather_chunk()
         dev = flat.data.device
-        sizes = [p.numel() for p in flat.params]
+        self.idx = list(range(len(flat.params))) if idx is None else list(idx)
+        sizes = [flat.params[i].numel() for i in self.idx]
         tids, starts = [], []
-        for i, n in enumerate(sizes):
+        for k, n in enumerate(sizes):
             for st in range(0, n, ch):
-                tids.append(i)
+                tids.append(k)
                 starts.append(st)
         self.flat = flat
         self.chunk_tensor = torch.tensor(tids, dtype=torch.int32, device=dev)
         self.chunk_start = torch.tensor(starts, dtype=torch.int32, device=dev)
-        self.dst_offsets = torch.tensor(flat.offsets, dtype=torch.int64, device=dev)
+        self.dst_offsets = torch.tensor([flat.offsets[i] for i in self.idx], dtype=torch.int64, device=dev)
         self.sizes = torch.tensor(sizes, dtype=torch.int64, device=dev)
 
     def new_table(self) -> torch.Tensor:
-        return torch.zeros(len(self.flat.params), dtype=torch.int64, device=self.flat.data.device)
+        return torch.zeros(len(self.idx), dtype=torch.int64, device=self.flat.data.device)
 
     def pointers(self) -> List[int]:
-        return [0 if p.grad is None else p.grad.data_ptr() for p in self.flat.params]
+        ps = self.flat.params
+        return [0 if ps[i].grad is None else ps[i].grad.data_ptr() for i in self.idx]
 
     def launch(self, table: torch.Tensor):
         get_backend().multi_gather(table, self.chunk_tensor, self.chunk_start, self.dst_offsets, self.sizes, self.flat.grad)
 
 
+class _Bucket:
+    """A run of consecutive trainable parameters whose gradients are gathered and all-reduced together."""
+    __slots__ = ("idx", "start", "end", "pending", "gather", "table_eager", "table_graph", "captured_ptrs", "wire")
+
+    def __init__(self, idx, start, end):
+        self.idx, self.start, self.end, self.pending = idx, start, end, 0
+        self.gather = self.table_eager = self.table_graph = self.captured_ptrs = self.wire = None
+
+
 class SegTrainer:
-    """One data-parallel training step of DeepLab with the reference's default objective
-    (focal + dice, train.py:259-265) on the CUDA engine."""
+    """One data-parallel training step of DeepLab with the reference's objective (focal | CE, + dice; train.py:259-265) on
+    the CUDA engine: what ``DistributedDataParallel`` (train.py:386) + ``optimizer.step()`` (utils_fit.py:60-121) do for
+    the reference.
+
+    * every parameter lives in one flat fp32 buffer; the trainable ones are updated by ONE fused Adam / SGD-nesterov
+      launch per contiguous run (frozen parameters - the reference's Freeze_Train phase - are skipped exactly as
+      ``torch.optim`` skips parameters without gradient; a parameter that is unfrozen later starts its own Adam step
+      count, as it does in torch, and nobody's moments are reset);
+    * gradients are produced by autograd as separate tensors and copied into the flat gradient one bucket per launch as
+      soon as the bucket's last gradient exists (buckets are filled from the END of the parameter list: backward reaches
+      the decoder first); with more than one rank each bucket's all-reduce starts right there and runs under the rest of
+      backward; ranks start from rank 0's weights (broadcast at construction, as DDP does);
+    * ``capture`` records the WHOLE step - forward, objective, backward, bucket gathers, NCCL all-reduces, optimizer -
+      as one CUDA graph; learning rate, momentum / betas, weight decay and the step counts are read from device memory,
+      so ``set_lr`` and the per-epoch schedule (train.py:575) act on replays."""
 
     def __init__(self, model: torch.nn.Module, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0, optimizer: str = "adam", momentum: float = 0.9,
+                 weight_decay: float = 0.0, optimizer: str = "adam", momentum: float = 0.9, nesterov: bool = True,
                  cls_weights=None, num_classes: int = 5, dice: bool = True, focal: bool = True,
-                 bucket_mb: float = 32.0, world_size: int = 1):
+                 bucket_mb: float = 32.0, world_size: int = 1, wire_dtype: Optional[torch.dtype] = None):
+        if optimizer not in ("adam", "sgd"):
+            raise ValueError("optimizer must be 'adam' or 'sgd' (train.py:472-476), got %r" % (optimizer,))
         self.model = model
-        self.flat = FlatParams(model)
+        self.flat = FlatParams(model, trainable_only=False)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
-        self.optimizer, self.momentum = optimizer, momentum
+        self.optimizer, self.momentum, self.nesterov = optimizer, momentum, nesterov
         self.num_classes, self.dice, self.focal = num_classes, dice, focal
         dev = self.flat.data.device
         self.cls_weights = None if cls_weights is None else torch.as_tensor(cls_weights, dtype=torch.float32, device=dev)
@@ -101,79 +132,136 @@ class SegTrainer:
         self.v = torch.zeros_like(self.flat.data) if optimizer == "adam" else None
         self.t = 0
         self.world = world_size
+        self.wire_dtype = wire_dtype
+        self.bucket_mb = bucket_mb
         self.last = None
-        # device-side step counter + hyper-parameters: what a captured CUDA graph reads on every replay
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.hyper_dev = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0 / max(world_size, 1)],
+        # device-side hyper-parameters + step counters: what a captured CUDA graph reads on every replay
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)          # steps taken (dropout streams)
+        b1 = betas[0] if optimizer == "adam" else momentum
+        self.hyper_dev = torch.tensor([lr, b1, betas[1], eps, weight_decay, 1.0 / max(world_size, 1)],
                                       dtype=torch.float32, device=dev)
         self.graph = None
-        self._hooks_off = False
-        # gradients are gathered into the flat buffer by ONE kernel whenever no per-bucket hooks need them there
-        # early (single GPU, or the graph-captured data-parallel step); device tensors only
-        self._gather = GradGather(self.flat) if self.flat.grad.is_cuda else None
-        self._table_eager = self._gather.new_table() if self._gather else None
-        self._table_graph = self._gather.new_table() if self._gather else None
-        self._captured_ptrs = None
+        self._graph_key = None
+        self._use_gather = self.flat.grad.is_cuda      # CPU tensors (host-logic tests): autograd accumulates into views
         self._nbt = [m.num_batches_tracked for m in model.modules()
                      if isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.num_batches_tracked is not None]
-        if world_size > 1:
-            self._setup_buckets(bucket_mb)
+        self._t_start = {}                              # parameter index -> step count when it became trainable
+        self._sig = None
+        self.works = []
+        if world_size > 1 and dist.is_available() and dist.is_initialized():
+            # ranks start from rank 0's parameters and buffers, as DistributedDataParallel's constructor does
+            dist.broadcast(self.flat.data, 0)
+            for buf in model.buffers():
+                dist.broadcast(buf.data, 0)
+        self._hooked = set()                            # hooks can only be put on parameters that require grad
+        self._hooks_live = False
+        self.refresh_trainable()
+
+    # ------------------------------------------------------------------ trainable set, runs, buckets
+    def refresh_trainable(self) -> bool:
+        """Re-derive optimizer runs and gradient buckets from the parameters' ``requires_grad`` flags.  Called at every
+        step (a tuple comparison); does work only when a flag changed (Freeze_Train -> unfreeze).  Optimizer state is
+        kept; a captured graph is dropped (re-captured by the caller)."""
+        sig = tuple(p.requires_grad for p in self.flat.params)
+        if sig == self._sig:
+            return False
+        self._sig = sig
+        flat, n = self.flat, len(self.flat.params)
+        dev = flat.data.device
+        for i in range(n):
+            if sig[i]:
+                self._t_start.setdefault(i, self.t)
+                if i not in self._hooked:
+                    self._hooked.add(i)
+                    flat.params[i].register_post_accumulate_grad_hook(self._make_hook(i))
+            else:
+                self._t_start.pop(i, None)
+                flat.params[i].grad = None
+        flat.grad.zero_()
+        # optimizer runs: maximal stretches of consecutive trainable parameters with the same start step
+        starts = sorted(set(self._t_start.values()))
+        self._counter_of = {ts: k for k, ts in enumerate(starts)}
+        self.step_devs = torch.tensor([self.t - ts for ts in starts] or [0], dtype=torch.int32, device=dev)
+        self.runs = []                                  # [flat start, flat end, counter index]
+        for i in range(n):
+            if not sig[i]:
+                continue
+            k = self._counter_of[self._t_start[i]]
+            a, b = flat.offsets[i], flat.offsets[i] + flat.padded(i)
+            if self.runs and self.runs[-1][1] == a and self.runs[-1][2] == k:
+                self.runs[-1][1] = b
+            else:
+                self.runs.append([a, b, k])
+        # gradient buckets over the trainable parameters, from the end
+        cap = int(self.bucket_mb * 1024 * 1024 / 4)
+        self.buckets: List[_Bucket] = []
+        self.bucket_of = [-1] * n
+        cur, idx = 0, []
+        trainable = [i for i in range(n) if sig[i]]
+        for pos in range(len(trainable) - 1, -1, -1):
+            i = trainable[pos]
+            idx.append(i)
+            cur += flat.padded(i)
+            if cur >= cap or pos == 0:
+                lo, hi = min(idx), max(idx)
+                bk = _Bucket(sorted(idx), flat.offsets[lo], flat.offsets[hi] + flat.padded(hi))
+                if self._use_gather:
+                    bk.gather = GradGather(flat, bk.idx)
+                    bk.table_eager, bk.table_graph = bk.gather.new_table(), bk.gather.new_table()
+                for j in idx:
+                    self.bucket_of[j] = len(self.buckets)
+                self.buckets.append(bk)
+                cur, idx = 0, []
+        self.graph = None
+        self._graph_key = None
+        return True
 
     # ------------------------------------------------------------------ data parallel
-    def _setup_buckets(self, bucket_mb: float):
-        """Buckets are contiguous slices of the flat gradient, filled from the END (backward
-        produces decoder gradients first).  A bucket is all-reduced on a side stream as soon as
-        its last gradient has been accumulated."""
-        cap = int(bucket_mb * 1024 * 1024 / 4)
-        n = len(self.flat.params)
-        self.bucket_of = [0] * n
-        self.buckets: List[List[int]] = []  # [start, end, pending, total]
-        end = self.flat.numel
-        start_idx = n
-        cur = 0
-        for i in range(n - 1, -1, -1):
-            size = (self.flat.params[i].numel() + 3) // 4 * 4
-            cur += size
-            self.bucket_of[i] = len(self.buckets)
-            if cur >= cap or i == 0:
-                self.buckets.append([self.flat.offsets[i], end, 0, start_idx - i])
-                end, start_idx, cur = self.flat.offsets[i], i, 0
-        # (gloo / CPU tensors are only used by the host-logic tests: no streams there)
-        self.comm_stream = torch.cuda.Stream() if self.flat.grad.is_cuda else None
-        self.works = []
-        for i, p in enumerate(self.flat.params):
-            p.register_post_accumulate_grad_hook(self._make_hook(i))
-
     def _make_hook(self, i):
         def hook(_p):
-            if self._hooks_off:
+            if not self._hooks_live:
                 return
-            b = self.buckets[self.bucket_of[i]]
-            b[2] += 1
-            if b[2] == b[3]:
-                self._launch_bucket(b)
+            b = self.bucket_of[i]
+            if b < 0:
+                return
+            bk = self.buckets[b]
+            bk.pending += 1
+            if bk.pending == len(bk.idx):
+                self._bucket_ready(bk)
         return hook
 
-    def _launch_bucket(self, b):
-        if self.comm_stream is None:
-            self.works.append(dist.all_reduce(self.flat.grad[b[0]:b[1]], op=dist.ReduceOp.SUM, async_op=True))
-            return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
-            self.works.append(dist.all_reduce(self.flat.grad[b[0]:b[1]], op=dist.ReduceOp.SUM, async_op=True))
+    def _bucket_ready(self, bk: _Bucket):
+        """All gradients of the bucket exist: copy them into the flat gradient (one launch) and start its all-reduce, which
+        then runs on NCCL's stream under the rest of backward."""
+        bk.pending = -(1 << 30)                         # fired
+        if bk.gather is not None:
+            ptrs = bk.gather.pointers()
+            if torch.cuda.is_current_stream_capturing():
+                bk.captured_ptrs = ptrs                 # the table is filled right after the capture ends
+                bk.gather.launch(bk.table_graph)
+            else:
+                bk.table_eager.copy_(torch.tensor(ptrs, dtype=torch.int64))
+                bk.gather.launch(bk.table_eager)
+        if self.world > 1:
+            seg = self.flat.grad[bk.start:bk.end]
+            if self.wire_dtype is not None and self.wire_dtype != torch.float32:
+                bk.wire = seg.to(self.wire_dtype)       # halves the bytes on NVLink; summation in the wire type
+                self.works.append(dist.all_reduce(bk.wire, op=dist.ReduceOp.SUM, async_op=True))
+            else:
+                self.works.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, async_op=True))
 
-    def _finish_allreduce(self):
-        for b in self.buckets:          # frozen / unused parameters never fire their hook
-            if b[2] != b[3]:
-                self._launch_bucket(b)
-            b[2] = 0
+    def _finish_buckets(self):
+        for bk in self.buckets:                         # parameters that received no gradient never fire their hook
+            if bk.pending >= 0:
+                self._bucket_ready(bk)
+            bk.pending = 0
         for w in self.works:
-            w.wait()
+            w.wait()                                    # the compute stream waits for NCCL's stream (no host block on CUDA)
         self.works = []
-        if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        for bk in self.buckets:
+            if bk.wire is not None:
+                self.flat.grad[bk.start:bk.end].copy_(bk.wire)
+                bk.wire = None
 
     # ------------------------------------------------------------------ step
     def step(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None):
@@ -181,13 +269,14 @@ class SegTrainer:
         ignore; or the uint8 class map as read from the PNG, clamped on the device); labels: the
         reference's fp32 one-hot [B,H,W,C+1] (optional).  Returns the 4-vector
         (ce, focal, dice, f_score) as a device tensor (no host sync)."""
+        self.refresh_trainable()
         losses = self._forward_backward(imgs, pngs, labels)
-        self._reduce_and_update()
+        self._update()
+        self.t += 1
         return losses
 
     def _forward_backward(self, imgs, pngs, labels):
-        gather = self._gather is not None and (self._hooks_off or self.world == 1)
-        if gather:
+        if self._use_gather:
             self.flat.detach_grads()
         else:
             self.flat.attach_grad_views()
@@ -195,6 +284,7 @@ class SegTrainer:
         if pngs.dtype == torch.uint8:      # loader tail on the device: png[png >= num_classes] = num_classes, as int64
             pngs = get_backend().finish_batch_u8(None, pngs.contiguous(), self.num_classes, torch.float32)[1]
         self.step_dev.add_(1)
+        self.step_devs.add_(1)
         ops.set_step_counter(self.step_dev)
         with ops.defer_batch_counters():
             out = self.model(imgs)
@@ -202,47 +292,76 @@ class SegTrainer:
             torch._foreach_add_(self._nbt, 1)
         ce, focal, dice, fs = seg_objective(out, pngs, labels, self.cls_weights, self.num_classes)
         loss = (focal if self.focal else ce) + (dice if self.dice else 0.0)
-        loss.backward()
-        if gather:
-            ptrs = self._gather.pointers()
-            if torch.cuda.is_current_stream_capturing():
-                # the table is filled right after the capture ends; replays always see the same addresses
-                self._captured_ptrs = ptrs
-                self._gather.launch(self._table_graph)
-            else:
-                self._table_eager.copy_(torch.tensor(ptrs, dtype=torch.int64))
-                self._gather.launch(self._table_eager)
+        for bk in self.buckets:
+            bk.pending = 0
+        self._hooks_live = True
+        try:
+            loss.backward()
+        finally:
+            self._hooks_live = False
+        self._finish_buckets()
         self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
         return self.last
 
-    def _reduce_and_update(self):
+    def _update(self):
+        """The optimizer on every run of trainable parameters; hyper-parameters and step counts come from device memory."""
         B = get_backend()
-        gscale = 1.0
-        if self.world > 1:
-            if self._hooks_off:     # graph-replayed backward: one all-reduce of the whole flat gradient
-                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
+        d, g, m, v = self.flat.data, self.flat.grad, self.m, self.v
+        for a, b, k in self.runs:
+            cnt = self.step_devs[k:k + 1]
+            if self.optimizer == "adam":
+                B.adam_step_dev(d[a:b], g[a:b], m[a:b], v[a:b], self.hyper_dev, cnt)
             else:
-                self._finish_allreduce()
-            gscale = 1.0 / self.world
-        self.t += 1
-        if self.optimizer == "adam":
-            # step count and hyper-parameters are read from device memory (graph-replay safe)
-            B.adam_step_dev(self.flat.data, self.flat.grad, self.m, self.v, self.hyper_dev, self.step_dev)
-        else:
-            B.sgd_step(self.flat.data, self.flat.grad, self.m, self.lr, self.momentum, self.wd, True, self.t == 1,
-                       gscale)
+                B.sgd_step_dev(d[a:b], g[a:b], m[a:b], self.hyper_dev, bool(self.nesterov))
 
     def set_lr(self, lr: float):
-        self.lr = lr
-        self.hyper_dev[0] = lr
+        if lr != self.lr:
+            self.lr = lr
+            self.hyper_dev[0:1].fill_(lr)
+
+    def sync_hyper(self, group: dict):
+        """Adopt lr / betas / momentum / weight decay of a ``torch.optim`` param group (the reference changes the learning
+        rate every epoch through ``set_optimizer_lr``, train.py:575)."""
+        self.set_lr(float(group["lr"]))
+        wd = float(group.get("weight_decay", self.wd))
+        if wd != self.wd:
+            self.wd = wd
+            self.hyper_dev[4:5].fill_(wd)
+
+    # ------------------------------------------------------------------ checkpoint (optimizer + step state)
+    def state_dict(self) -> dict:
+        """Optimizer moments, step counts and hyper-parameters (the reference saves weights only, utils_fit.py:191-198; a
+        run resumed from those restarts Adam from zero moments).  Weights themselves stay in ``model.state_dict()``."""
+        n = len(self.flat.params)
+        return {"optimizer": self.optimizer, "t": self.t, "m": self.m.detach().cpu(),
+                "v": None if self.v is None else self.v.detach().cpu(),
+                "t_start": [self._t_start.get(i, -1) for i in range(n)],
+                "hyper": [float(x) for x in self.hyper_dev.cpu()], "numel": self.flat.numel,
+                "step_dev": int(self.step_dev.item())}
+
+    def load_state_dict(self, sd: dict):
+        if sd["optimizer"] != self.optimizer or sd["numel"] != self.flat.numel:
+            raise ValueError("trainer state is for optimizer %r with %d parameters" % (sd["optimizer"], sd["numel"]))
+        self.m.copy_(sd["m"])
+        if self.v is not None and sd["v"] is not None:
+            self.v.copy_(sd["v"])
+        self.t = int(sd["t"])
+        self.step_dev.fill_(int(sd["step_dev"]))
+        self._t_start = {i: ts for i, ts in enumerate(sd["t_start"]) if ts >= 0 and self.flat.params[i].requires_grad}
+        self._sig = None
+        self.refresh_trainable()
+        return self
 
     # ------------------------------------------------------------------ CUDA graph
-    def capture(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None, warmup: int = 3):
-        """Capture one training step (~1 800 kernel launches) into a CUDA graph over static input buffers.
-        Single GPU: forward, loss, backward and the optimizer are all inside the graph.  Data parallel:
-        forward + loss + backward are captured; the gradient all-reduce (one NCCL call on the flat 219 MB
-        gradient, ~0.5 ms on NVLink 5) and the fused Adam run right after each replay."""
-        self._hooks_off = self.world > 1
+    def capture(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None, warmup: int = 3,
+                comm_in_graph: bool = True):
+        """Capture one training step (~1 800 kernel launches) into a CUDA graph over static input buffers: forward,
+        objective, backward, the bucket gathers, the optimizer and - data parallel - the NCCL all-reduce of every bucket
+        (forked onto NCCL's stream where the bucket completes, joined before the optimizer), so a replay overlaps
+        communication with backward exactly as the eager step does.  ``comm_in_graph=False`` keeps the collective out of
+        the graph (one all-reduce of the flat gradient + the optimizer after each replay)."""
+        self.refresh_trainable()
+        self._comm_in_graph = comm_in_graph or self.world == 1
         self.s_imgs, self.s_pngs = imgs.clone(), pngs.clone()
         self.s_labels = None if labels is None else labels.clone()
         side = torch.cuda.Stream()
@@ -251,26 +370,41 @@ class SegTrainer:
             for _ in range(warmup):
                 self.step(self.s_imgs, self.s_pngs, self.s_labels)
         torch.cuda.current_stream().wait_stream(side)
+        world = self.world
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            if self.world > 1:
+        try:
+            if not self._comm_in_graph:
+                self.world = 1                          # no collective while capturing
+            with torch.cuda.graph(self.graph):
                 self.s_out = self._forward_backward(self.s_imgs, self.s_pngs, self.s_labels)
-            else:
-                self.s_out = self.step(self.s_imgs, self.s_pngs, self.s_labels)
-        if self._captured_ptrs is not None:
-            self._table_graph.copy_(torch.tensor(self._captured_ptrs, dtype=torch.int64))
+                if self._comm_in_graph:
+                    self._update()
+        finally:
+            self.world = world
+        for bk in self.buckets:
+            if bk.captured_ptrs is not None:
+                bk.table_graph.copy_(torch.tensor(bk.captured_ptrs, dtype=torch.int64))
+                bk.captured_ptrs = None
+        self._graph_key = (tuple(imgs.shape), imgs.dtype, tuple(pngs.shape), pngs.dtype,
+                           None if labels is None else tuple(labels.shape))
         return self
 
+    def graph_matches(self, imgs, pngs, labels=None) -> bool:
+        return self.graph is not None and self._graph_key == (
+            tuple(imgs.shape), imgs.dtype, tuple(pngs.shape), pngs.dtype, None if labels is None else tuple(labels.shape))
+
     def step_graphed(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None):
+        if self.refresh_trainable() or self.graph is None:
+            raise RuntimeError("the captured step is stale (the trainable set changed): call capture() again")
         self.s_imgs.copy_(imgs, non_blocking=True)
         self.s_pngs.copy_(pngs, non_blocking=True)
         if self.s_labels is not None and labels is not None:
             self.s_labels.copy_(labels, non_blocking=True)
         self.graph.replay()
-        if self.world > 1:
-            self._reduce_and_update()
-        else:
-            self.t += 1
+        if not self._comm_in_graph:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
+            self._update()
+        self.t += 1
         return self.s_out
 
 

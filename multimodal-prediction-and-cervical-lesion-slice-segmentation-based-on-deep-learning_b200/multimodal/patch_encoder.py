@@ -175,8 +175,10 @@ class ResNet101Encoder(nn.Module):
         return self.forward_nhwc(ops.to_nhwc(x, self._cervix_dtype))
 
     def encode_images(self, images, new_size: int = 1024, patch_size: int = 256):
-        """[B,3,H,W] fp32 images in [0,1] -> [B*16, out] features: resize + x-major patch split + ImageNet
-        normalisation as one kernel straight into the stem's NHWC layout (``split_patches_nhwc``), then the encoder."""
+        """[B,3,H,W] fp32 images in [0,1], or the decoded uint8 images [B,H,W,3] (then the resize is Pillow's own 8-bit
+        BILINEAR resampler, bit for bit what the reference's ``img.resize`` produces) -> [B*16, out] features: resize +
+        x-major patch split + ImageNet normalisation as one kernel straight into the stem's NHWC layout
+        (``split_patches_nhwc``), then the encoder."""
         return self.forward_nhwc(split_patches_nhwc(images, new_size, patch_size, self._cervix_dtype))
 
     def forward_nhwc(self, x):
@@ -218,6 +220,9 @@ def split_patches_nhwc(images: torch.Tensor, new_size: int = 1024, patch_size: i
     """Tensor form of ``resize_and_split_image`` (:151-161) + ToTensor/Normalize (:145-148) as ONE kernel
     (``cvx_split_patches``): [B,3,H,W] fp32 in [0,1] -> [B*16, 256, 256, 3] NHWC in the encoder's compute dtype,
     patches enumerated x-major (outer loop over columns) as the reference's list comprehension does."""
+    if images.dtype == torch.uint8:
+        # the decoded image itself, [B,H,W,3] as PIL / numpy hold it: Pillow's own fixed-point resampler, bit for bit
+        return get_backend().split_patches_u8(images.contiguous(), new_size, patch_size, IMAGENET_MEAN, IMAGENET_STD, dtype)
     return get_backend().split_patches(images.contiguous(), new_size, patch_size, IMAGENET_MEAN, IMAGENET_STD, dtype)
 
 

@@ -7,7 +7,17 @@ What is different underneath:
   * running loss / f_score stay on the device and are read back only when the progress line is refreshed and at the
     end of the phase - the reference synchronises twice per step (``.item()``, utils_fit.py:123-124);
   * ``fp16=True`` selects the bf16 tensor-core engine of the drop-in ``DeepLab`` (no loss scaling is needed in bf16,
-    so ``scaler`` may be None and is never stepped); ``fp16=False`` selects the fp32 exact-parity engine.
+    so ``scaler`` may be None and is never stepped); ``fp16=False`` selects the fp32 exact-parity engine;
+  * on a CUDA device with the drop-in ``DeepLab`` and the optimizers the reference builds (``optim.Adam`` /
+    ``optim.SGD(nesterov)`` over ``model.parameters()``, one param group; train.py:472-476) the training phase runs on
+    ``engine.SegTrainer``: flat parameters, ONE fused optimizer launch per run of trainable parameters with the
+    hyper-parameters of ``optimizer.param_groups[0]`` re-read every epoch (``set_optimizer_lr``, train.py:575), the whole
+    step replayed as a CUDA graph from the third batch on, host batches prefetched one step ahead, bucketed NCCL
+    all-reduce when ``model_train`` is ``DistributedDataParallel`` (train.py:386).  The math is torch.optim's; the torch
+    optimizer object itself is left untouched (its ``state`` stays empty) and the moments live in the trainer, saved next
+    to the weights as ``last_epoch_trainer_state.pth`` and restored from there when a run resumes.  Frozen parameters
+    (Freeze_Train, train.py:447-449,531-551) are skipped and join later with their own step count, as in torch.
+    ``CERVIX_FIT_EAGER=1`` keeps the plain autograd + ``optimizer.step()`` loop.
 """
 import os
 
@@ -68,6 +78,108 @@ def _to_device(batch, cls_weights, cuda, local_rank):
     return imgs, pngs, labels, weights
 
 
+_TRAINER_STATE = "last_epoch_trainer_state.pth"
+_EAGER_STEPS_BEFORE_CAPTURE = 2     # lazy initialisation (kernel attributes, allocator, NCCL) happens in real steps
+
+
+def _fast_trainer(model_train, optimizer, cuda, dice_loss, focal_loss, cls_weights, num_classes, save_dir, epoch):
+    """The ``SegTrainer`` that stands in for ``optimizer`` on this model, or None when the fast path does not apply."""
+    import torch.distributed as dist
+    from ..engine import SegTrainer
+    from ..nets.deeplabv3_plus import DeepLab
+    if not cuda or os.environ.get("CERVIX_FIT_EAGER") == "1":
+        return None
+    net = _unwrap(model_train)
+    if not isinstance(net, DeepLab) or not next(net.parameters()).is_cuda:
+        return None
+    ddp = isinstance(model_train, torch.nn.parallel.DistributedDataParallel)
+    if model_train is not net and not ddp:          # nn.DataParallel (train.py:388): single-process replicas, eager path
+        return None
+    if len(optimizer.param_groups) != 1:
+        return None
+    g = optimizer.param_groups[0]
+    if {id(p) for p in g["params"]} != {id(p) for p in net.parameters()}:
+        return None
+    if type(optimizer) is torch.optim.Adam:
+        if g.get("amsgrad") or g.get("maximize"):
+            return None
+        kind = "adam"
+        kw = dict(betas=tuple(g["betas"]), eps=g["eps"])
+    elif type(optimizer) is torch.optim.SGD:
+        if g.get("dampening", 0) != 0 or g.get("maximize"):
+            return None
+        kind = "sgd"
+        kw = dict(momentum=g["momentum"], nesterov=bool(g["nesterov"]))
+    else:
+        return None
+    world = dist.get_world_size() if (ddp and dist.is_available() and dist.is_initialized()) else 1
+    key = (id(optimizer), kind, bool(dice_loss), bool(focal_loss), world, tuple(float(w) for w in cls_weights))
+    tr = getattr(net, "_cvx_trainer", None)
+    if tr is None or getattr(tr, "_fit_key", None) != key:
+        tr = SegTrainer(net, lr=g["lr"], weight_decay=g["weight_decay"], optimizer=kind, cls_weights=cls_weights,
+                        num_classes=num_classes, dice=bool(dice_loss), focal=bool(focal_loss), world_size=world, **kw)
+        tr._fit_key = key
+        path = os.path.join(save_dir, _TRAINER_STATE) if save_dir else None
+        if epoch > 0 and path and os.path.exists(path):     # a resumed run (Init_Epoch > 0): continue from the saved moments
+            try:
+                tr.load_state_dict(torch.load(path, map_location="cpu"))
+            except Exception as e:
+                print("cervix_b200: optimizer state at %s not restored (%s)" % (path, e))
+        net._cvx_trainer = tr
+    tr.sync_hyper(g)
+    return tr
+
+
+def _implicit_onehot(pngs, labels, num_classes) -> bool:
+    """True when ``labels`` is exactly ``eye(C+1)[png]`` (what DeeplabDataset builds, dataloader.py:47): the loss kernels
+    then derive the one-hot target from the class map and the 6.3 MB per image tensor need not cross PCIe."""
+    if labels is None or labels.dim() != 4 or labels.shape[-1] != num_classes + 1 or labels.shape[:3] != pngs.shape:
+        return False
+    lab = labels.reshape(-1, num_classes + 1)
+    idx = pngs.reshape(-1).long().clamp(0, num_classes)
+    return bool((lab.sum(1) == 1).all() and (lab.gather(1, idx[:, None]) == 1).all())
+
+
+def _train_phase_fast(trainer, gen, epoch_step, cuda, local_rank, cls_weights, num_classes, dice_loss, focal_loss, bar, main,
+                      optimizer):
+    from ..engine import BatchPrefetcher
+    dev = torch.device("cuda", local_rank)
+    state = {"implicit": None}
+
+    def host_batches():
+        for iteration, batch in enumerate(gen):
+            if iteration >= epoch_step:
+                return
+            imgs, pngs, labels = batch
+            if state["implicit"] is None:       # checked once per epoch on the host, before anything is copied
+                state["implicit"] = (not labels.is_cuda) and _implicit_onehot(pngs, labels, num_classes)
+            yield (imgs, pngs, None if state["implicit"] else labels)
+
+    run = None
+    steps = 0
+    for imgs, pngs, labels in BatchPrefetcher(host_batches(), dev):
+        if trainer.graph_matches(imgs, pngs, labels):
+            out = trainer.step_graphed(imgs, pngs, labels)
+        elif trainer.t >= _EAGER_STEPS_BEFORE_CAPTURE and steps >= _EAGER_STEPS_BEFORE_CAPTURE:
+            trainer.capture(imgs, pngs, labels, warmup=0)       # recording does not execute: replay it for this batch
+            out = trainer.step_graphed(imgs, pngs, labels)
+        else:
+            out = trainer.step(imgs, pngs, labels)
+        with torch.no_grad():                   # (ce, focal, dice, f_score) stay on the device
+            run = out.clone() if run is None else run + out
+        steps += 1
+        if main and (steps % _REFRESH == 0 or steps == epoch_step):
+            r = run.tolist()
+            loss = (r[1] if focal_loss else r[0]) + (r[2] if dice_loss else 0.0)
+            bar.update(total_loss=loss / steps, f_score=r[3] / steps, lr=get_lr(optimizer))
+        else:
+            bar.update()
+    if run is None:
+        return 0.0
+    r = run.tolist()
+    return (r[1] if focal_loss else r[0]) + (r[2] if dice_loss else 0.0)
+
+
 def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, epoch, epoch_step, epoch_step_val, gen,
                   gen_val, Epoch, cuda, dice_loss, focal_loss, cls_weights, num_classes, fp16, scaler, save_period,
                   save_dir, local_rank=0):
@@ -79,6 +191,11 @@ def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, ep
     model_train.train()
     run_loss = run_fs = None
     steps = 0
+    trainer = _fast_trainer(model_train, optimizer, cuda, dice_loss, focal_loss, cls_weights, num_classes, save_dir, epoch)
+    if trainer is not None:
+        total_fast = _train_phase_fast(trainer, gen, epoch_step, cuda, local_rank, cls_weights, num_classes, dice_loss,
+                                       focal_loss, bar, main, optimizer)
+        gen = ()
     for iteration, batch in enumerate(gen):
         if iteration >= epoch_step:
             break
@@ -98,6 +215,8 @@ def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, ep
         else:
             bar.update()
     total_loss = float(run_loss) if run_loss is not None else 0.0
+    if trainer is not None:
+        total_loss = total_fast
     bar.close()
 
     if main:
@@ -139,3 +258,5 @@ def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, ep
         print("Save best model to best_epoch_weights.pth")
         torch.save(state, os.path.join(save_dir, "best_epoch_weights.pth"))
     torch.save(state, os.path.join(save_dir, "last_epoch_weights.pth"))
+    if trainer is not None:     # optimizer moments + step counts, which the reference's checkpoints omit
+        torch.save(trainer.state_dict(), os.path.join(save_dir, _TRAINER_STATE))

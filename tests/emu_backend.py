@@ -549,6 +549,10 @@ class EmuBackend:
         lr, b1, b2, eps, wd, gs = [float(t) for t in hyper]
         self.adam_step(p, g, m, v, lr, b1, b2, eps, wd, int(step_dev), gs)
 
+    def sgd_step_dev(self, p, g, buf, hyper, nesterov):
+        lr, mom, _, _, wd, gs = [float(t) for t in hyper]
+        self.sgd_step(p, g, buf, lr, mom, wd, nesterov, False, gs)
+
     def sgd_step(self, p, g, buf, lr, momentum, wd, nesterov, first_step, grad_scale=1.0):
         gi = g * grad_scale
         if wd != 0:

@@ -1,0 +1,84 @@
+"""Two-GPU NCCL tests of the data-parallel step: the bucketed all-reduce that
+``SegTrainer`` starts from its gradient hooks - eagerly and INSIDE the captured CUDA graph - must leave on every rank the
+sum of the shards' single-process gradients, and both ranks must take the same optimizer step.  Skipped on a box with one
+GPU (the world_size-2 gloo tests in tests/test_engine_cpu.py cover the host logic there)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+CLS_W = [1, 1, 5, 3, 4]
+
+
+def _model(dtype):
+    from cervix_b200.nets.deeplabv3_plus import DeepLab
+    from oracle import deeplab_ref as O
+    m = DeepLab(5, "mobilenet", False, 16).set_compute_dtype(dtype)
+    m.load_state_dict(O.make_state("mobilenet", 5, 16, seed=3, randomize_bn_stats=False))
+    m.cuda().train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m
+
+
+def _worker(rank, world, port, out_dir, mode):
+    from cervix_b200.engine import SegTrainer
+    from oracle import deeplab_ref as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    imgs, pngs, _ = O.synthetic_batch(4, 64, seed=10 + rank)
+    imgs, pngs = imgs.cuda(), pngs.cuda()
+    # this shard's single-process gradient from the common starting weights
+    solo = SegTrainer(_model(torch.float32), lr=0.0, cls_weights=CLS_W)
+    solo.step(imgs, pngs)
+    shard_grad = solo.flat.grad.clone()
+    total = shard_grad.clone()
+    dist.all_reduce(total)                              # reference: plain sum of the shard gradients
+    model = _model(torch.float32)
+    if rank == 1:                                       # ranks must end up with rank 0's weights (DDP's broadcast)
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(0.01)
+    # lr = 0 until the gradient has been looked at (SGD without weight decay then leaves the weights alone, warm-up included)
+    kw = dict(lr=0.0, optimizer="sgd", momentum=0.9, cls_weights=CLS_W, world_size=world, bucket_mb=1.0)
+    if mode == "bf16wire":
+        kw["wire_dtype"] = torch.bfloat16
+    tr = SegTrainer(model, **kw)
+    assert len(tr.buckets) >= 3
+    start = tr.flat.data.clone()
+    if mode == "graph":
+        tr.capture(imgs, pngs, None, warmup=1)          # one real step, then the capture (NCCL inside the graph)
+        tr.step_graphed(imgs, pngs)
+        grad = tr.flat.grad.clone()
+        tr.set_lr(1e-3)
+        tr.step_graphed(imgs, pngs)
+    else:
+        tr.step(imgs, pngs)
+        grad = tr.flat.grad.clone()
+        tr.set_lr(1e-3)
+        tr.step(imgs, pngs)
+    torch.save({"grad": grad.cpu(), "total": total.cpu(), "data": tr.flat.data.cpu(), "start": start.cpu()},
+               os.path.join(out_dir, "%s_r%d.pt" % (mode, rank)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (run with gpurun --gpus 2)")
+@pytest.mark.parametrize("mode", ["eager", "graph", "bf16wire"])
+def test_two_gpu_nccl_gradients_equal_the_sum_of_the_shards(tmp_path, mode):
+    port = 33500 + os.getpid() % 2000 + {"eager": 0, "graph": 1, "bf16wire": 2}[mode]
+    mp.spawn(_worker, args=(2, port, str(tmp_path), mode), nprocs=2, join=True)
+    r0 = torch.load(tmp_path / ("%s_r0.pt" % mode))
+    r1 = torch.load(tmp_path / ("%s_r1.pt" % mode))
+    assert torch.equal(r0["start"], r1["start"])                        # broadcast at construction
+    assert torch.equal(r0["grad"], r1["grad"]) and torch.equal(r0["data"], r1["data"])
+    scale = float(r0["total"].abs().max())
+    tol = 2e-2 if mode == "bf16wire" else 1e-4                          # bf16 wire: 8 mantissa bits per summand
+    assert float((r0["grad"] - r0["total"]).abs().max()) <= tol * scale
+    assert float((r0["data"] - r0["start"]).abs().max()) > 0

@@ -144,8 +144,10 @@ def test_trainer_gradient_gather_matches_accumulate_path():
             if isinstance(m, torch.nn.Dropout):
                 m.p = 0.0
         tr = SegTrainer(model, lr=1e-3, cls_weights=[1, 1, 5, 3, 4], num_classes=5)
-        if not gather:
-            tr._gather = None
+        if not gather:                      # the accumulate path: autograd adds into views of the flat gradient
+            tr._use_gather = False
+            for bk in tr.buckets:
+                bk.gather = None
         return tr
 
     def check_flat(tr):
