@@ -1,0 +1,225 @@
+"""Parity on BASELINE.json's own configurations (VERDICT r01 "what's weak" #3), through the C ABI on the B200, against the
+oracle run live on the same inputs:
+
+  configs[0]  DeepLabv3+ fp32 inference, batch 1, one 512x512x3 image, 5 classes - Xception and MobileNetV2, ds 16:
+              logits within 1e-3 relative, argmax >= 99.9 % identical (north_star); bf16 engine reported beside it;
+  configs[1]  four-modal classifier fp32 forward / backward, batch 16 (16 patients): logits, objective and gradients of
+              the batched CUDA head against the per-patient oracle;
+  configs[2]  bf16 training at batch 32, 512x512: the train-mode forward is bit-reproducible run to run (fixed-order
+              reductions) and the gradient's run-to-run spread (split-K fp32 atomics in the weight gradients) is bounded;
+  north_star  "bf16 training loss tracking the fp32 reference within 2 % over 200 steps", at 256x256 / batch 8 with the
+              oracle run in fp32 on the device (stock torch, TF32 off) so that 200 steps finish in seconds.
+"""
+import numpy as np
+import pytest
+import torch
+
+from cervix_b200.nets.deeplabv3_plus import DeepLab
+from cervix_b200.nets.deeplabv3_training import seg_objective
+from oracle import deeplab_ref as O
+from oracle import losses_ref as L
+
+pytestmark = pytest.mark.gpu
+CLS_W = torch.tensor([1, 1, 5, 3, 4], dtype=torch.float32)
+
+
+def _relerr(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------------- configs[0]
+@pytest.mark.parametrize("bb", ["xception", "mobilenet"])
+def test_config0_fp32_inference_512_batch1_matches_oracle(bb):
+    state = O.make_state(bb, 5, 16, seed=21)
+    imgs, _, _ = O.synthetic_batch(1, 512, seed=5)
+    with torch.no_grad():
+        ref = O.deeplab_forward(imgs, {k: v.clone() for k, v in state.items()}, bb, 16, False)
+    model = DeepLab(5, bb, False, 16).set_compute_dtype(torch.float32)
+    model.load_state_dict(state, strict=True)
+    model.cuda().eval()
+    with torch.no_grad():
+        y = model(imgs.cuda())
+    assert tuple(y.shape) == (1, 5, 512, 512) and y.dtype == torch.float32
+    err = _relerr(y, ref)
+    agree = float((y.argmax(1).cpu() == ref.argmax(1)).float().mean())
+    print("config0 %s fp32: logits rel err %.3e, argmax agreement %.5f" % (bb, err, agree))
+    assert err < 1e-3, err
+    assert agree >= 0.999, agree
+    # the bf16 tensor-core engine on the same input (8 mantissa bits through ~70 layers: reported, bounded loosely)
+    model.set_compute_dtype(torch.bfloat16)
+    with torch.no_grad():
+        y16 = model(imgs.cuda())
+    err16 = _relerr(y16, ref)
+    agree16 = float((y16.argmax(1).cpu() == ref.argmax(1)).float().mean())
+    print("config0 %s bf16: logits rel err %.3e, argmax agreement %.5f" % (bb, err16, agree16))
+    assert err16 < 5e-2 and agree16 >= 0.97, (err16, agree16)
+
+
+# ---------------------------------------------------------------------------------------------------------- configs[1]
+def test_config1_sixteen_patients_fp32_forward_backward_matches_oracle():
+    from cervix_b200.multimodal.my_mae_model import fusion_model_mae_2, fusion_objective
+    from oracle import fusion_ref as FR
+    from tests.fusion_cases import batch_of
+    types = list(FR.MODALITIES)
+    G = 16
+    torch.manual_seed(0)
+    head = fusion_model_mae_2(1024, 512, 512, 0.3, 4)
+    head.load_state_dict(FR.randomize_state(head.state_dict(), seed=9), strict=True)
+    state = {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in head.state_dict().items()}
+    patients = [FR.synthetic_patient(500 + i) for i in range(G)]
+    rng = np.random.RandomState(4)
+    masks = np.ones((G, 4), dtype=bool)
+    masks[np.arange(G), rng.randint(0, 4, G)] = False
+    labels = torch.from_numpy(rng.randint(0, 4, G))
+    # oracle: one patient at a time, as the reference does (my_train(full).py:246-253), objective over the 16
+    outs = [FR.fusion_forward(p, state, types, list(masks[i])) for i, p in enumerate(patients)]
+    ref_loss = FR.fusion_loss(outs, [list(m) for m in masks], labels, types)
+    ref_loss.backward()
+    # product: all 16 patients in one batched launch sequence on the device
+    head = head.cuda().eval()
+    feats, edges = batch_of(patients, types, torch.device("cuda"))
+    out = head.forward_batch(feats, edges, types, types, masks, True)
+    for i in range(G):
+        for name in ("logits_all", "one_x", "mae_out"):
+            assert _relerr(out[name][i], outs[i][name]) < 2e-4, (i, name)
+        for m in types:
+            assert _relerr(out["logits_" + m][i], outs[i]["logits_" + m]) < 2e-4, (i, m)
+    pred = torch.stack([o["logits_all"] for o in outs]).argmax(1)
+    assert torch.equal(out["logits_all"].argmax(1).cpu(), pred)                 # class predictions identical
+    loss = fusion_objective(out, labels.cuda(), masks)
+    assert abs(float(loss) - float(ref_loss)) < 1e-4 * abs(float(ref_loss)), (float(loss), float(ref_loss))
+    loss.backward()
+    worst, checked = 0.0, 0
+    for name, p in head.named_parameters():
+        g_ref = state[name].grad
+        if g_ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        scale = float(g_ref.abs().max())
+        if scale < 1e-7:        # shift-invariant biases (softmax gates): the true gradient is zero, both sides hold rounding
+            continue
+        e = float((p.grad.cpu() - g_ref).abs().max()) / scale
+        worst = max(worst, e)
+        checked += 1
+        assert e < 2e-3, (name, e)
+    print("config1: 16 patients, loss %.6f (oracle %.6f), %d gradient tensors, worst rel err %.2e" %
+          (float(loss), float(ref_loss), checked, worst))
+    assert checked > 100
+
+
+# ---------------------------------------------------------------------------------------------------------- configs[2]
+@pytest.mark.parametrize("size,bsz", [(64, 4), (512, 32)])
+def test_config2_bf16_train_step_is_reproducible(size, bsz):
+    """Same weights, same batch, twice: the losses must be IDENTICAL (every forward reduction - BatchNorm statistics in the
+    column-reduce kernels, in the depthwise kernels and in the GEMM epilogues, the loss sums - has a fixed summation order)
+    and the gradient may differ only by the fp32 atomics of the split-K weight gradients.  r01's smoke() saw 9.04 / 9.50
+    for the same input at 64x64: that was summation order through shared-memory atomics, amplified by bf16 rounding over
+    batch-statistics BatchNorm, not a race - with ordered reductions the spread is exactly zero."""
+    state = O.make_state("xception", 5, 16, seed=3)
+    imgs, pngs, _ = O.synthetic_batch(bsz, size, seed=1)
+    imgs, pngs = imgs.cuda(), pngs.cuda()
+    model = DeepLab(5, "xception", False, 16).set_compute_dtype(torch.bfloat16)
+    model.load_state_dict(state)
+    model.cuda().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    w = CLS_W.cuda()
+    losses, gnorms, grads = [], [], []
+    for _ in range(3):
+        model.load_state_dict(state)
+        model.zero_grad(set_to_none=True)
+        ce, focal, dice, fs = seg_objective(model(imgs), pngs, None, w, 5)
+        (focal + dice).backward()
+        losses.append((float(ce), float(focal), float(dice), float(fs)))
+        g = torch.cat([p.grad.reshape(-1).double() for p in model.parameters() if p.grad is not None])
+        gnorms.append(float(g.norm()))
+        grads.append(g if size <= 64 else None)
+    assert losses[0] == losses[1] == losses[2], losses
+    spread = (max(gnorms) - min(gnorms)) / gnorms[0]
+    print("bf16 %dx%d batch %d: focal %.5f three times; |grad| spread %.2e" % (size, size, bsz, losses[0][1], spread))
+    assert spread < 5e-3, gnorms
+    if grads[0] is not None:
+        cos = float(torch.dot(grads[0], grads[1]) / (grads[0].norm() * grads[1].norm()))
+        assert cos > 0.999, cos
+
+
+# ---------------------------------------------------------------------------------------------------------- north_star
+def _learnable_batch(bsz, size, seed):
+    g = torch.Generator().manual_seed(seed)
+    coarse = torch.rand(bsz, 3, size // 8, size // 8, generator=g)
+    imgs = torch.nn.functional.interpolate(coarse, size=(size, size), mode="bilinear", align_corners=False).clamp(0, 1)
+    pngs = (imgs.mean(1) * 8 - 1.5).floor().clamp(0, 4).long()
+    ign = torch.rand(bsz, size, size, generator=g) < 0.01
+    pngs = torch.where(ign, torch.full_like(pngs, 5), pngs)
+    return imgs.contiguous(), pngs, torch.eye(6)[pngs]
+
+
+def test_bf16_loss_tracks_fp32_reference_at_256_over_200_steps():
+    """tests/test_loss_tracking_gpu.py runs 96x96 / batch 4 against the HOST oracle.  Here 256x256 / batch 8 (8x the
+    BatchNorm populations): the fp32 side is the same oracle code executed by stock torch on the device in true fp32
+    (TF32 off), the bf16 side the product.  Bars: 2 % on the 200-step mean (the north-star statement); single 20-step
+    windows and the last 40 steps are bounded at 3 % because two FP32 runs of this network already differ by 2 % per
+    window through summation order alone - the product's fp32 engine against the same reference is run and printed as that
+    noise floor (measured on B200: bf16 200-step mean 0.56 %, last 40 steps 2.1 %, worst window 2.2 %; fp32-engine floor
+    worst window 1.97 %), and the bf16 run must stay within 1.5 points of it."""
+    steps, window = 200, 20
+    bb, size, bsz, lr = "xception", 256, 8, 3e-4
+    state = O.make_state(bb, 5, 16, seed=11, conv_std=0.02)
+    pool = [tuple(t.cuda() for t in _learnable_batch(bsz, size, seed=200 + i)) for i in range(4)]
+    w = CLS_W.cuda()
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        st = {k: (v.clone().cuda().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone().cuda())
+              for k, v in state.items()}
+        opt = torch.optim.Adam([v for v in st.values() if v.requires_grad], lr=lr)
+        ref = []
+        for step in range(steps):
+            imgs, pngs, labels = pool[step % len(pool)]
+            opt.zero_grad()
+            y = O.deeplab_forward(imgs, st, bb, 16, True, dropout=False)
+            loss = L.focal_loss(y, pngs, w, 5) + L.dice_loss(y, labels)
+            loss.backward()
+            opt.step()
+            ref.append(loss.detach())
+        ref = [float(v) for v in torch.stack(ref).cpu()]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+    def run_engine(dtype):
+        model = DeepLab(5, bb, False, 16).set_compute_dtype(dtype)
+        model.load_state_dict({k: v.clone() for k, v in state.items()}, strict=True)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        model = model.cuda().train()
+        opt = torch.optim.Adam(model.parameters(), lr=lr)
+        out = []
+        for step in range(steps):
+            imgs, pngs, labels = pool[step % len(pool)]
+            opt.zero_grad()
+            ce, focal, dice, _ = seg_objective(model(imgs), pngs, labels, w, 5)
+            loss = focal + dice
+            loss.backward()
+            opt.step()
+            out.append(loss.detach())
+        return [float(v) for v in torch.stack(out).cpu()]
+
+    got, got32 = run_engine(torch.bfloat16), run_engine(torch.float32)
+    ref_w = np.array(ref).reshape(-1, window).mean(1)
+    rel = np.abs(np.array(got).reshape(-1, window).mean(1) / ref_w - 1)
+    rel32 = np.abs(np.array(got32).reshape(-1, window).mean(1) / ref_w - 1)
+    total = abs(float(np.mean(got)) / float(np.mean(ref)) - 1)
+    tail = abs(float(np.mean(got[-40:])) / float(np.mean(ref[-40:])) - 1)
+    print("fp32 reference windows:", np.round(ref_w, 4).tolist())
+    print("rel bf16 engine vs reference per window:", np.round(rel, 4).tolist())
+    print("rel fp32 engine vs reference per window:", np.round(rel32, 4).tolist())
+    print("200-step mean rel %.4f ; last 40 steps rel %.4f ; worst window %.4f (fp32 engine floor %.4f)" %
+          (total, tail, rel.max(), rel32.max()))
+    assert ref_w[-1] < 0.9 * ref_w[0], "the reference run did not train"
+    assert total < 0.02, total
+    assert tail < 0.03 and rel.max() < 0.03, (tail, rel.tolist())
+    assert rel.max() < rel32.max() + 0.015, (rel.max(), rel32.max())

@@ -107,6 +107,48 @@ def test_gpu_split_patches_kernel(shape, new_size, patch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("h,w,new_size,patch", [(512, 512, 1024, 256), (300, 417, 1024, 256), (1500, 2000, 1024, 256),
+                                                (1024, 1024, 1024, 256), (2049, 1025, 1024, 256), (97, 33, 64, 16)])
+def test_gpu_split_patches_u8_equals_pillow(h, w, new_size, patch):
+    """the reference resizes the DECODED uint8 image with ``img.resize((1024, 1024), Image.BILINEAR)``
+    (Graph_Structure(data_augmentation).py:154) - Pillow's fixed-point, two-pass, antialiasing-when-reducing resampler, not
+    ``F.interpolate``.  The uint8 kernel must reproduce the installed Pillow BIT FOR BIT, enlarging (512 -> 1024) and
+    reducing (2000 -> 1024) alike, through the x-major crops, ToTensor and Normalize."""
+    import numpy as np
+    from PIL import Image
+    from cervix_b200.multimodal.patch_encoder import IMAGENET_MEAN, IMAGENET_STD, split_patches_nhwc
+    rng = np.random.RandomState(h * 7 + w)
+    imgs = rng.randint(0, 256, (2, h, w, 3), dtype=np.uint8)
+    mean = torch.tensor(IMAGENET_MEAN).view(3, 1, 1)
+    std = torch.tensor(IMAGENET_STD).view(3, 1, 1)
+    want = []
+    for a in imgs:
+        resized = Image.fromarray(a).resize((new_size, new_size), Image.BILINEAR)
+        for i in range(0, new_size, patch):                  # the reference's loop order: outer x, inner y
+            for j in range(0, new_size, patch):
+                t = torch.from_numpy(np.asarray(resized.crop((i, j, i + patch, j + patch)))).permute(2, 0, 1).float().div(255)
+                want.append(t.sub(mean).div(std))
+    want = torch.stack(want)
+    got = split_patches_nhwc(torch.from_numpy(imgs).cuda(), new_size, patch, torch.float32).permute(0, 3, 1, 2).cpu()
+    assert got.shape == want.shape
+    assert torch.equal(got, want), float((got - want).abs().max())
+    got16 = split_patches_nhwc(torch.from_numpy(imgs).cuda(), new_size, patch, torch.bfloat16)
+    assert torch.equal(got16.float().cpu().permute(0, 3, 1, 2), want.bfloat16().float())
+
+
+def test_pillow_tables_reproduce_pillow_on_the_host():
+    """The coefficient tables the kernel consumes (multimodal/pil_resample.py), applied in numpy, against Pillow."""
+    import numpy as np
+    from PIL import Image
+    from cervix_b200.multimodal.pil_resample import resize_u8_reference
+    rng = np.random.RandomState(0)
+    for h, w, o in ((128, 128, 256), (75, 104, 256), (375, 500, 256), (256, 160, 64)):
+        a = rng.randint(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = np.asarray(Image.fromarray(a).resize((o, o), Image.BILINEAR))
+        assert np.array_equal(resize_u8_reference(a, o, o), ref), (h, w, o)
+
+
+@pytest.mark.gpu
 def test_gpu_encode_images_equals_split_then_forward():
     _, enc = _pair(4)
     enc.set_compute_dtype(torch.bfloat16).cuda()
