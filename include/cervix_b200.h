@@ -53,6 +53,12 @@ CVX_API int         cvx_abi_version(void);
 CVX_API const char* cvx_last_error(void);
 /* number of kernels this library has launched so far in this process */
 CVX_API int64_t     cvx_launch_count(void);
+/* Workspace contract switch.  Reduction entry points (BatchNorm statistics / backward sums, depthwise weight gradient,
+ * loss statistics, GEMM-epilogue statistics) accumulate into caller-owned fp64 workspaces and clear them first.  A caller
+ * that hands out workspaces from an arena it has already zeroed (one fill per training step instead of ~360 memset nodes)
+ * sets on = 1 for the duration of that step; the library then skips its own cudaMemsetAsync.  Process-wide, not
+ * per-stream: one training step at a time per process (one process per GPU). */
+CVX_API int         cvx_set_ws_prezeroed(int on);
 /* 1 if the running device is sm_100 (tcgen05/TMA kernels usable), 0 otherwise */
 CVX_API int         cvx_device_is_sm100(void);
 
@@ -269,6 +275,26 @@ CVX_API int cvx_rows_gather(const float* x, const int* idx, const float* fill, f
 /* backward of cvx_rows_gather in gather form (fixed summation order, writes every element of dx [src_rows, c] / dfill) */
 CVX_API int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int src_rows, int c,
                          void* stream);
+/* ---- grouped fp32 GEMM: the per-modality linear layers of the fusion head as ONE launch --------------------------------
+ * Reference sites: the four SAGEConv (lin_l, lin_r), gate MLPs and per-modality head MLPs of fusion_model_mae_2
+ * (MultiModal Prediction/Four_Modal/my_mae_model.py:404-416, 544, 550, 657-674, 706-769) - same topology per modality,
+ * separate weights, each an nn.Linear call of its own in the reference.
+ * Problem i computes C[m,n] = sum_k A(m,k) * B(n,k) (+ bias[n]) with A(m,k) = a[m*lda_m + k*lda_k], B(n,k) = b[n*ldb_n +
+ * k*ldb_k], C(m,n) = c[m*ldc + n]; every operand must be contiguous along k or along its row index.  rowsum (nullable)
+ * receives sum_k A(m,k) - the bias gradient when the problem is a weight gradient (A = dY^T).  Up to
+ * CVX_MAX_GEMM_PROBLEMS problems per launch; the array is HOST memory, copied into the kernel's parameters (capturable).
+ * fp32 FMA, one fixed-order sum per output element (bit-reproducible). */
+#define CVX_MAX_GEMM_PROBLEMS 16
+typedef struct cvx_gemm_problem {
+  const float* a;
+  const float* b;
+  const float* bias;
+  float* c;
+  float* rowsum;
+  int64_t lda_m, lda_k, ldb_n, ldb_k, ldc;
+  int m, n, k, reserved;
+} cvx_gemm_problem;
+CVX_API int cvx_gemm_grouped(const cvx_gemm_problem* problems, int count, void* stream);
 /* classifier objective (my_train(full).py:309-347): loss += weight * mean CE ; masked-row MSE */
 CVX_API int cvx_softmax_ce(const float* logits, const int64_t* labels, float* loss, float* dlogits, int b, int k,
                    float weight, void* stream);

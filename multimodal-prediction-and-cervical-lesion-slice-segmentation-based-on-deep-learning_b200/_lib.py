@@ -22,6 +22,14 @@ class ConvDesc(C.Structure):
                                           "ho", "wo", "dtype")]
 
 
+class GemmProblem(C.Structure):
+    """cvx_gemm_problem of include/cervix_b200.h."""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("bias", C.c_void_p), ("c", C.c_void_p), ("rowsum", C.c_void_p),
+                ("lda_m", C.c_int64), ("lda_k", C.c_int64), ("ldb_n", C.c_int64), ("ldb_k", C.c_int64), ("ldc", C.c_int64),
+                ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("reserved", C.c_int32)]
+
+
+MAX_GEMM_PROBLEMS = 16
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _D = C.POINTER(ConvDesc)
 
@@ -102,7 +110,9 @@ PROTOTYPES = {
     "cvx_adam_step_dev": [_P, _P, _P, _P, _L, _P, _P, _P],
     "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],
     "cvx_sgd_step_dev": [_P, _P, _P, _L, _P, _I, _P],
+    "cvx_gemm_grouped": [C.POINTER(GemmProblem), _I, _P],
     "cvx_multi_gather_chunk": [],
+    "cvx_set_ws_prezeroed": [_I],
     "cvx_multi_gather": [_P, _P, _P, _P, _P, _I, _P, _P],
     "cvx_seg_postprocess": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "cvx_confusion_matrix": [_P, _P, _L, _I, _P, _P],

@@ -227,7 +227,7 @@ class CudaBackend:
         c = int(dy.shape[-1])
         rows = dy.numel() // c
         out = torch.empty((c,), dtype=torch.float32, device=dy.device)
-        ws = torch.empty((c,), dtype=torch.float64, device=dy.device)
+        ws = self._ws64((c,), dy.device)
         check(self.lib.cvx_bias_grad(_p(dy), _p(out), _p(ws), rows, c, _dt(dy), self._stream()), "cvx_bias_grad")
         return out
 
@@ -286,7 +286,7 @@ class CudaBackend:
     def dw_bwd_weight(self, x, dy, g: ConvGeom, relu_in: bool) -> torch.Tensor:
         self._chk(x, dy)
         out = torch.empty((9, g.cin), dtype=torch.float32, device=x.device)
-        ws = torch.empty((9 * g.cin,), dtype=torch.float64, device=x.device)
+        ws = self._ws64((9 * g.cin,), x.device)
         d = g.desc(_dt(x))
         check(self.lib.cvx_dwconv_bwd_weight(C.byref(d), _p(x), _p(dy), _p(out), _p(ws), int(relu_in), self._stream()),
               "cvx_dwconv_bwd_weight")
@@ -300,7 +300,7 @@ class CudaBackend:
         y = torch.empty_like(x)
         mean = torch.empty((c,), dtype=torch.float32, device=x.device)
         invstd = torch.empty((c,), dtype=torch.float32, device=x.device)
-        ws = torch.empty((2 * c + 2,), dtype=torch.float64, device=x.device)
+        ws = self._ws64((2 * c + 2,), x.device)
         check(self.lib.cvx_bn_forward(_p(x), _p(residual), _p(y), _p(gamma), _p(beta), _p(rmean), _p(rvar), _p(mean),
                                       _p(invstd), _p(ws), rows, c, _dt(x), act, int(training), float(momentum),
                                       float(eps), self._stream()), "cvx_bn_forward")
@@ -315,7 +315,7 @@ class CudaBackend:
         dres = torch.empty_like(x) if want_dres else None
         dgamma = torch.empty((c,), dtype=torch.float32, device=x.device)
         dbeta = torch.empty((c,), dtype=torch.float32, device=x.device)
-        ws = torch.empty((2 * c + 2,), dtype=torch.float64, device=x.device)
+        ws = self._ws64((2 * c + 2,), x.device)
         check(self.lib.cvx_bn_backward(_p(dy), _p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(invstd), _p(dx), _p(dres),
                                        _p(dgamma), _p(dbeta), _p(ws), rows, c, _dt(x), act, int(training),
                                        self._stream()), "cvx_bn_backward")
@@ -405,7 +405,7 @@ class CudaBackend:
     def seg_loss_stats(self, logits, target, onehot, cls_w, alpha: float, gamma: float, thr: float):
         self._chk(logits, target, onehot, cls_w)
         n, c, h, w = logits.shape
-        stats = torch.empty((4 + 6 * c,), dtype=torch.float64, device=logits.device)
+        stats = self._ws64((4 + 6 * c,), logits.device)
         check(self.lib.cvx_seg_loss_stats(_p(logits), _p(target), _p(onehot), _p(cls_w), _p(stats), n, c, h, w,
                                           float(alpha), float(gamma), float(thr), self._stream()), "cvx_seg_loss_stats")
         return stats
@@ -530,6 +530,32 @@ class CudaBackend:
               "cvx_rows_scatter_add")
         return dx, dfill
 
+    def gemm_grouped(self, problems):
+        """One launch for a list of independent fp32 GEMMs C = A B^T (+ bias) (cvx_gemm_grouped).  Each problem is a dict
+        with tensors ``a``, ``b``, ``c`` (+ optional ``bias``, ``rowsum``), ints ``m, n, k`` and element strides
+        ``lda_m, lda_k, ldb_n, ldb_k, ldc``.  Lists longer than the per-launch limit are split."""
+        lim = _lib.MAX_GEMM_PROBLEMS
+        for s0 in range(0, len(problems), lim):
+            chunk = problems[s0:s0 + lim]
+            arr = (_lib.GemmProblem * len(chunk))()
+            for i, q in enumerate(chunk):
+                self._chk_f32(q["a"], q["b"], q["c"], q.get("bias"), q.get("rowsum"))
+                arr[i].a, arr[i].b, arr[i].c = q["a"].data_ptr(), q["b"].data_ptr(), q["c"].data_ptr()
+                arr[i].bias = None if q.get("bias") is None else q["bias"].data_ptr()
+                arr[i].rowsum = None if q.get("rowsum") is None else q["rowsum"].data_ptr()
+                arr[i].m, arr[i].n, arr[i].k = int(q["m"]), int(q["n"]), int(q["k"])
+                arr[i].lda_m, arr[i].lda_k = int(q["lda_m"]), int(q["lda_k"])
+                arr[i].ldb_n, arr[i].ldb_k, arr[i].ldc = int(q["ldb_n"]), int(q["ldb_k"]), int(q["ldc"])
+            check(self.lib.cvx_gemm_grouped(arr, len(chunk), self._stream()), "cvx_gemm_grouped")
+
+    @staticmethod
+    def _chk_f32(*tensors):
+        for t in tensors:
+            if t is None:
+                continue
+            if not t.is_cuda or t.dtype != torch.float32:
+                raise _lib.CervixError("cervix_b200: gemm_grouped takes fp32 CUDA tensors (got %s on %s)" % (t.dtype, t.device))
+
     def softmax_ce(self, logits, labels, loss, weight: float, want_grad: bool):
         self._chk(logits, labels, loss)
         b, k = logits.shape
@@ -553,6 +579,38 @@ class CudaBackend:
         return (x.dtype == torch.bfloat16 and self.is_sm100() and stride == 1 and dil == 1 and pad == 1
                 and cin % 8 == 0 and cout % 8 == 0 and cout <= 2048)
 
+    # ------------------------------------------------------------------ per-step arena of zeroed fp64 workspaces
+    # Every statistics / reduction kernel accumulates into a small fp64 workspace that has to start at zero: ~360
+    # cudaMemsetAsync nodes per training step (0.5 ms).  A trainer brackets its step with zero_arena_begin / _end: the
+    # arena is cleared by ONE fill at the start of the step, workspaces are carved from it in call order (the same
+    # addresses on every step, so a captured graph stays valid) and the library is told to skip its own memsets.
+    _ARENA_DOUBLES = 4 * 1024 * 1024
+
+    def zero_arena_begin(self, device):
+        if getattr(self, "_arena", None) is None or self._arena.device != device:
+            self._arena = torch.zeros((self._ARENA_DOUBLES,), dtype=torch.float64, device=device)
+        else:
+            self._arena.zero_()
+        self._arena_pos = 0
+        self._arena_on = True
+        self.lib.cvx_set_ws_prezeroed(1)
+
+    def zero_arena_end(self):
+        self._arena_on = False
+        self.lib.cvx_set_ws_prezeroed(0)
+
+    def _ws64(self, shape, dev):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if getattr(self, "_arena_on", False):
+            a = (self._arena_pos + 1) & ~1              # 16-byte aligned slices
+            if a + n <= self._arena.numel() and self._arena.device == dev:
+                self._arena_pos = a + n
+                return self._arena[a:a + n].view(shape)
+            return torch.zeros(shape, dtype=torch.float64, device=dev)     # arena full: the library will not clear it
+        return torch.empty(shape, dtype=torch.float64, device=dev)
+
     @staticmethod
     def _f32(n, dev):
         return torch.empty((n,), dtype=torch.float32, device=dev)
@@ -560,7 +618,7 @@ class CudaBackend:
     def dwf_fwd(self, x, w9c, in_scale, in_shift, relu_in: bool, g: ConvGeom, want_stats: bool):
         self._chk(x, w9c, in_scale, in_shift)
         y = torch.empty_like(x)
-        stats = torch.empty((2, g.cin), dtype=torch.float64, device=x.device) if want_stats else None
+        stats = self._ws64((2, g.cin), x.device) if want_stats else None
         d = g.desc(_dt(x))
         check(self.lib.cvx_dwf_fwd(C.byref(d), _p(x), _p(w9c), _p(in_scale), _p(in_shift), int(relu_in), _p(y), _p(stats),
                                    self._stream()), "cvx_dwf_fwd")
@@ -570,8 +628,8 @@ class CudaBackend:
         self._chk(dd, dside, negk, kmean, x, w9c, in_scale, in_shift, addend)
         gout = torch.empty_like(x)
         dw9c = torch.empty((9, g.cin), dtype=torch.float32, device=x.device)
-        ws = torch.empty((9, g.cin), dtype=torch.float64, device=x.device)
-        sums = torch.empty((2, g.cin), dtype=torch.float64, device=x.device) if want_sums else None
+        ws = self._ws64((9, g.cin), x.device)
+        sums = self._ws64((2, g.cin), x.device) if want_sums else None
         d = g.desc(_dt(x))
         check(self.lib.cvx_dwf_bwd(C.byref(d), _p(dd), _p(dside), _p(negk), _p(kmean), _p(x), _p(w9c), _p(in_scale),
                                    _p(in_shift), int(relu_in), _p(addend), _p(gout), _p(dw9c), _p(ws), _p(sums),
@@ -581,7 +639,7 @@ class CudaBackend:
     def bn_stats(self, x):
         self._chk(x)
         c = int(x.shape[-1])
-        stats = torch.empty((2, c), dtype=torch.float64, device=x.device)
+        stats = self._ws64((2, c), x.device)
         check(self.lib.cvx_bn_stats(_p(x), _p(stats), x.numel() // c, c, _dt(x), self._stream()), "cvx_bn_stats")
         return stats
 
@@ -607,7 +665,7 @@ class CudaBackend:
     def conv_fwd_ex(self, x, wp, bias, g: ConvGeom, side=None, side_scale=None, want_stats=False):
         self._chk(x, wp, bias, side, side_scale)
         y = torch.empty((g.n, g.ho, g.wo, g.cout), dtype=x.dtype, device=x.device)
-        stats = torch.empty((2, g.cout), dtype=torch.float64, device=x.device) if want_stats else None
+        stats = self._ws64((2, g.cout), x.device) if want_stats else None
         d = g.desc(_dt(x))
         check(self.lib.cvx_conv_fwd_tc_ex(C.byref(d), _p(x), _p(wp), _p(bias), _p(side), _p(side_scale), _p(stats), _p(y),
                                           self._stream()), "cvx_conv_fwd_tc_ex")
@@ -641,7 +699,7 @@ class CudaBackend:
     def bn_bwd_sums(self, dy, y, p, act: int):
         self._chk(dy, y, p)
         c = int(p.shape[-1])
-        sums = torch.empty((2, c), dtype=torch.float64, device=p.device)
+        sums = self._ws64((2, c), p.device)
         check(self.lib.cvx_bn_bwd_sums(_p(dy), _p(y), _p(p), _p(sums), p.numel() // c, c, act, self._stream()), "cvx_bn_bwd_sums")
         return sums
 

@@ -244,7 +244,7 @@ int cvx_bn_forward(const void* x, const void* residual, void* y, const float* ga
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "bn_forward: C=%d not a multiple of %d", c, vec);
   if (training) {
-    CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
+    CVX_WS_ZERO(ws, sizeof(double) * 2 * c, st);
     int rc = CVX_OK;
     CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, StatsF<T>>(StatsF<T>{(const T*)x, c}, rows, c, ws, st)));
     if (rc) return rc;
@@ -272,7 +272,7 @@ int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* g
   cudaStream_t st = as_stream(stream);
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "bn_backward: C=%d not a multiple of %d", c, vec);
-  CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 2 * c, st));
+  CVX_WS_ZERO(ws, sizeof(double) * 2 * c, st);
   int rc = CVX_OK;
   CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, BnBwdF<T>, 256, 3>(
                                    BnBwdF<T>{(const T*)dy, (const T*)x, (const T*)y, gamma, beta, save_mean, save_invstd, c, act},
@@ -294,7 +294,7 @@ int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* g
 int cvx_bias_grad(const void* dy, float* dbias, double* ws, int64_t rows, int c, int dtype, void* stream) {
   CVX_CHECK_ARG(dy && dbias && ws && rows > 0 && c > 0, "bias_grad: bad arguments");
   cudaStream_t st = as_stream(stream);
-  CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * c, st));
+  CVX_WS_ZERO(ws, sizeof(double) * c, st);
   int rc = CVX_OK;
   const int vec = dtype == CVX_F32 ? 4 : 8;
   if (c % vec != 0) {

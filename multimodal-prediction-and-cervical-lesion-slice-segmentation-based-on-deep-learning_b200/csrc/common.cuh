@@ -12,6 +12,13 @@ namespace cvx {
 
 void set_error(const char* fmt, ...);
 extern unsigned long long g_kernel_launches;  // kernels launched by this library (bench.py's gpu_launches)
+extern int g_ws_prezeroed;                    // cvx_set_ws_prezeroed: fp64 workspaces arrive zeroed (caller's per-step arena)
+
+// clear an accumulation workspace unless the caller has promised it is already zero
+#define CVX_WS_ZERO(ptr, bytes, st)                                       \
+  do {                                                                    \
+    if (!cvx::g_ws_prezeroed) CVX_CUDA_OK(cudaMemsetAsync((ptr), 0, (bytes), (st))); \
+  } while (0)
 
 #define CVX_CHECK_ARG(cond, ...)                 \
   do {                                           \

@@ -1747,7 +1747,7 @@ int cvx_conv_fwd_tc_ex(const cvx_conv_desc* d, const void* x, const void* w_pack
                        const float* side_scale, double* stats, void* y, void* stream) {
   if (int rc = tc_supported(d, "conv_fwd_tc_ex", true)) return rc;
   CVX_CHECK_ARG(x && w_packed && y && (!side || side_scale), "conv_fwd_tc_ex: null pointer");
-  if (stats) CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cout, as_stream(stream)));
+  if (stats) CVX_WS_ZERO(stats, sizeof(double) * 2 * d->cout, as_stream(stream));
   const TcEpi ep{bias, (const __nv_bfloat16*)side, side_scale, stats, 0};
   return run_igemm(d->n, d->h, d->w, d->cin, d->ho, d->wo, d->cout, d->kh, d->kw, d->pad, d->dil, x, w_packed, ep, y,
                    as_stream(stream), d->stride);

@@ -470,7 +470,7 @@ int cvx_dwconv_bwd_weight(const cvx_conv_desc* d, const void* x, const void* dy,
   if (int rc = dw_check(d, "dwconv_bwd_weight", &g)) return rc;
   CVX_CHECK_ARG(x && dy && dw9c && ws, "dwconv_bwd_weight: null pointer");
   cudaStream_t st = as_stream(stream);
-  CVX_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(double) * 9 * g.c, st));
+  CVX_WS_ZERO(ws, sizeof(double) * 9 * g.c, st);
   const int64_t rows = (int64_t)g.n * g.ho * g.wo;
   int rc = CVX_OK;
   const int vec = d->dtype == CVX_F32 ? 4 : 8;

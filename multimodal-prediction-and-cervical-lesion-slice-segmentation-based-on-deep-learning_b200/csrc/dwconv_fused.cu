@@ -19,22 +19,33 @@
 
 namespace cvx {
 
-constexpr int kFY = 12, kFX = 16;                     // output tile; rows are walked 3 at a time (window period)
+constexpr int kFX = 16;                               // output tile width; the tile height FY is a template parameter
 constexpr int kFRow = (kFX + 2) * 128;                // bytes of one halo row (18 pixels x 64 ch)
-constexpr int kFTile = (kFY + 2) * kFRow;             // 32256 bytes: one halo tile of 64 channels
-constexpr int kFwdStages = 3;                         // forward: 3 tiles in flight, 2 CTAs per SM
-static_assert(kFY % 3 == 0, "the row loop is unrolled over the 3-row register window");
+__host__ __device__ constexpr int ftile_bytes(int fy) { return (fy + 2) * kFRow; }   // one halo tile of 64 channels (32256 bytes at FY = 12)
+constexpr int kFwdStages = 3;                         // forward: 3 tiles in flight
+// Two shapes of each kernel: the tall tile (12 rows: 17 % halo rows, fewest bytes staged) and the short tile (6 rows:
+// 33 % halo rows, but a stage is 18 KB so twice as many CTAs fit an SM).  These kernels are bound by latency at 8 - 16
+// resident warps per SM (ncu: 45 % issue-active, DRAM 24 %), so residency is worth more than the extra halo traffic
+// (which comes from L2); CERVIX_DWF_VARIANT selects among them for A/B measurements.
 
 struct DwFParams {
   int n, h, w, c;
   int tiles_x, tiles_y, ntiles;
   int relu_in;
 };
+// 0 = short tiles + weights in shared memory (default), 1 = tall tiles, weights in registers (the r01 kernels),
+// 2 = short tiles, weights in registers under the same register cap (the compiler spills)
+static const int g_dwf_variant = [] { const char* e = getenv("CERVIX_DWF_VARIANT"); return e ? atoi(e) : 0; }();
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   uint2 v;
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
+}
+// four fp32 (this thread's channel quad of one tap's weights) from shared memory as two packed pairs; volatile so the
+// compiler re-reads them every row instead of pinning 36 registers on loop-invariant weights (WSMEM variants)
+__device__ __forceinline__ void lds_w4(uint32_t addr, float2 (&w)[2]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(w[0].x), "=f"(w[0].y), "=f"(w[1].x), "=f"(w[1].y) : "r"(addr));
 }
 __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
@@ -97,11 +108,13 @@ __device__ __forceinline__ void tile_coords(const DwFParams& p, int tile, int& t
 // ------------------------------------------------------------------------------------------ forward
 // AFFINE: a pre-pass turns the staged halo tile into the virtual input act(s*x+t) ONCE per element (zero outside the
 // image: the padding applies to the virtual tensor), instead of once per tap column in the window loads.
-template <bool AFFINE>
-__global__ void __launch_bounds__(256, 2) dwf_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
+template <bool AFFINE, int FY, int MINB, bool WSMEM>
+__global__ void __launch_bounds__(256, MINB) dwf_fwd_kernel(const __grid_constant__ CUtensorMap tmap,
                                                          const float* __restrict__ w9c, const float* __restrict__ in_scale,
                                                          const float* __restrict__ in_shift, __nv_bfloat16* __restrict__ dst,
                                                          double* __restrict__ stats, DwFParams p) {
+  constexpr int kFY = FY, kFTile = ftile_bytes(FY);
+  static_assert(FY % 3 == 0, "the row loop is unrolled over the 3-row register window");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const uint32_t smem_base = smem_u32(smem), bar0 = smem_base + kFwdStages * kFTile;
@@ -114,7 +127,7 @@ __global__ void __launch_bounds__(256, 2) dwf_fwd_kernel(const __grid_constant__
   const bool relu = p.relu_in != 0;
   const uint32_t thr_off = col * 128 + cq * 8;   // this thread's (column, quad) inside a halo row
 
-  float2 wreg[9][2], sc[2], sh[2], s12[2][2];
+  float2 wreg[WSMEM ? 1 : 9][2], sc[2], sh[2], s12[2][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int c = c0 + 2 * i;
@@ -122,12 +135,22 @@ __global__ void __launch_bounds__(256, 2) dwf_fwd_kernel(const __grid_constant__
     sh[i] = (AFFINE && ch_ok) ? make_float2(__ldg(in_shift + c), __ldg(in_shift + c + 1)) : make_float2(0.f, 0.f);
     s12[0][i] = s12[1][i] = make_float2(0.f, 0.f);
   }
+  // the chunk's 9 x 64 tap weights: in registers (36 per thread), or staged once in shared memory [tap][channel]
+  const uint32_t wsm = bar0 + 64, w_thr = wsm + cq * 16;
+  if (WSMEM) {
+    float* wdst = reinterpret_cast<float*>(smem + kFwdStages * kFTile + 64);
+    for (int i = t; i < 9 * 64; i += 256) {
+      const int c = cchunk * 64 + (i & 63);
+      wdst[i] = c < p.c ? __ldg(w9c + (i >> 6) * p.c + c) : 0.f;
+    }
+  } else {
 #pragma unroll
-  for (int k = 0; k < 9; ++k)
+    for (int k = 0; k < (WSMEM ? 1 : 9); ++k)
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-      wreg[k][i] = ch_ok ? make_float2(__ldg(w9c + k * p.c + c0 + 2 * i), __ldg(w9c + k * p.c + c0 + 2 * i + 1))
-                         : make_float2(0.f, 0.f);
+      for (int i = 0; i < 2; ++i)
+        wreg[k][i] = ch_ok ? make_float2(__ldg(w9c + k * p.c + c0 + 2 * i), __ldg(w9c + k * p.c + c0 + 2 * i + 1))
+                           : make_float2(0.f, 0.f);
+  }
 
   if (t == 0) {
     tma_prefetch_desc(&tmap);
@@ -216,9 +239,13 @@ __global__ void __launch_bounds__(256, 2) dwf_fwd_kernel(const __grid_constant__
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
+            for (int kw = 0; kw < 3; ++kw) {
+              float2 wk[2];
+              if (WSMEM) lds_w4(w_thr + (kh * 3 + kw) * 256, wk);
+              else { wk[0] = wreg[WSMEM ? 0 : kh * 3 + kw][0]; wk[1] = wreg[WSMEM ? 0 : kh * 3 + kw][1]; }
 #pragma unroll
-              for (int e = 0; e < 2; ++e) acc[e] = __ffma2_rn(win[(j + kh) % 3][kw][e], wreg[kh * 3 + kw][e], acc[e]);
+              for (int e = 0; e < 2; ++e) acc[e] = __ffma2_rn(win[(j + kh) % 3][kw][e], wk[e], acc[e]);
+            }
           if (oy0 + r3 + j < p.h) {
             uint32_t pk[2];
 #pragma unroll
@@ -249,8 +276,8 @@ __global__ void __launch_bounds__(256, 2) dwf_fwd_kernel(const __grid_constant__
 // SIDE: the incoming gradient is not materialised - a pre-pass assembles it in place from the pointwise conv's data
 // gradient e and the depthwise output d:  dd = e + negk*d + kmean  (bn1's backward, see sepconv.cu), zero outside
 // the image (TMA's zero fill covers the plain case).
-template <bool AFFINE, bool SIDE>
-__global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__ CUtensorMap tmap_dd,
+template <bool AFFINE, bool SIDE, int FY, int MINB, bool WSMEM>
+__global__ void __launch_bounds__(256, MINB) dwf_bwd_kernel(const __grid_constant__ CUtensorMap tmap_dd,
                                                          const __grid_constant__ CUtensorMap tmap_d,
                                                          const __grid_constant__ CUtensorMap tmap_x,
                                                          const float* __restrict__ w9c, const float* __restrict__ in_scale,
@@ -259,6 +286,8 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
                                                          const __nv_bfloat16* __restrict__ addend,
                                                          __nv_bfloat16* __restrict__ gout, double* __restrict__ dw_out,
                                                          double* __restrict__ sums, DwFParams p) {
+  constexpr int kFY = FY, kFTile = ftile_bytes(FY);
+  static_assert(FY % 3 == 0, "the row loop is unrolled over the 3-row register window");
   constexpr int kTiles = SIDE ? 3 : 2;
   constexpr int kStage = kTiles * kFTile;
   constexpr int kStages = SIDE ? 2 : 3;
@@ -274,7 +303,7 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
   const bool relu = p.relu_in != 0;
   const uint32_t thr_off = col * 128 + cq * 8;
 
-  float2 wf[9][2], acc[9][2], sc[2], sh[2], nk[2], km[2], s12[2][2];
+  float2 wf[WSMEM ? 1 : 9][2], acc[9][2], sc[2], sh[2], nk[2], km[2], s12[2][2];
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const int c = c0 + 2 * i;
@@ -284,13 +313,23 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
     km[i] = (SIDE && ch_ok) ? make_float2(__ldg(kmean + c), __ldg(kmean + c + 1)) : make_float2(0.f, 0.f);
     s12[0][i] = s12[1][i] = make_float2(0.f, 0.f);
   }
+  // window position k = (i_row, j_col) pairs with the flipped tap 8-k.  The 9 x 64 flipped weights of the chunk live in
+  // registers (36 per thread) or, WSMEM, once in shared memory [position][channel] and are re-read every row
+  const uint32_t wsm = bar0 + 64, w_thr = wsm + cq * 16;
+  if (WSMEM) {
+    float* wdst = reinterpret_cast<float*>(smem + kStages * kStage + 64);
+    for (int i = t; i < 9 * 64; i += 256) {
+      const int c = cchunk * 64 + (i & 63);
+      wdst[i] = c < p.c ? __ldg(w9c + (8 - (i >> 6)) * p.c + c) : 0.f;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 9; ++k)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      // window position k = (i_row, j_col) pairs with the flipped tap 8-k
-      wf[k][i] = ch_ok ? make_float2(__ldg(w9c + (8 - k) * p.c + c0 + 2 * i), __ldg(w9c + (8 - k) * p.c + c0 + 2 * i + 1))
-                       : make_float2(0.f, 0.f);
+      if (!WSMEM)
+        wf[WSMEM ? 0 : k][i] = ch_ok ? make_float2(__ldg(w9c + (8 - k) * p.c + c0 + 2 * i), __ldg(w9c + (8 - k) * p.c + c0 + 2 * i + 1))
+                                     : make_float2(0.f, 0.f);
       acc[k][i] = make_float2(0.f, 0.f);
     }
 
@@ -399,13 +438,17 @@ __global__ void __launch_bounds__(256, 1) dwf_bwd_kernel(const __grid_constant__
 #pragma unroll
           for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
+            for (int kw = 0; kw < 3; ++kw) {
+              float2 wk[2];
+              if (WSMEM) lds_w4(w_thr + (kh * 3 + kw) * 256, wk);
+              else { wk[0] = wf[WSMEM ? 0 : kh * 3 + kw][0]; wk[1] = wf[WSMEM ? 0 : kh * 3 + kw][1]; }
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const float2 d = win[(j + kh) % 3][kw][e];
-                g[e] = __ffma2_rn(d, wf[kh * 3 + kw][e], g[e]);
+                g[e] = __ffma2_rn(d, wk[e], g[e]);
                 acc[kh * 3 + kw][e] = __ffma2_rn(d, xin[e], acc[kh * 3 + kw][e]);
               }
+            }
           if (row_ok) {
             uint32_t pk[2];
 #pragma unroll
@@ -445,83 +488,106 @@ static bool dwf_supported(const cvx_conv_desc* d) {
          d->cin % 8 == 0 && d->cin == d->cout;
 }
 
-static void dwf_params(const cvx_conv_desc* d, int relu_in, DwFParams* p) {
+static void dwf_params(const cvx_conv_desc* d, int relu_in, int fy, DwFParams* p) {
   p->n = d->n; p->h = d->h; p->w = d->w; p->c = d->cin;
   p->tiles_x = (d->w + kFX - 1) / kFX;
-  p->tiles_y = (d->h + kFY - 1) / kFY;
+  p->tiles_y = (d->h + fy - 1) / fy;
   p->ntiles = d->n * p->tiles_x * p->tiles_y;
   p->relu_in = relu_in;
+}
+
+constexpr int kWsmBytes = 9 * 64 * 4;   // the chunk's tap weights in shared memory (WSMEM variants)
+
+template <bool AFFINE, int FY, int MINB, bool WSMEM>
+static int dwf_fwd_launch_t(const cvx_conv_desc* d, const void* x, const float* w9c, const float* in_scale,
+                            const float* in_shift, int relu_in, void* y, double* stats, cudaStream_t st) {
+  DwFParams p;
+  dwf_params(d, relu_in, FY, &p);
+  CUtensorMap map;
+  if (int rc = make_act_map(&map, x, d->n, d->h, d->w, d->cin, kFX + 2, FY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  const int chunks = (d->cin + 63) / 64;
+  int gx = (kNumSMs * MINB) / chunks;   // MINB 256-thread CTAs per SM
+  if (gx < 1) gx = 1;
+  if (gx > p.ntiles) gx = p.ntiles;
+  constexpr int smem = kFwdStages * ftile_bytes(FY) + 128 + 64 + (WSMEM ? kWsmBytes : 0);
+  static bool configured = false;
+  if (!configured) {
+    CVX_CUDA_OK(cudaFuncSetAttribute(dwf_fwd_kernel<AFFINE, FY, MINB, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dwf_fwd_kernel<AFFINE, FY, MINB, WSMEM><<<dim3(gx, chunks), 256, smem, st>>>(map, w9c, in_scale, in_shift, (__nv_bfloat16*)y, stats, p);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
 }
 
 int dwf_fwd_launch(const cvx_conv_desc* d, const void* x, const float* w9c, const float* in_scale, const float* in_shift,
                    int relu_in, void* y, double* stats, cudaStream_t st) {
   if (!dwf_supported(d)) return CVX_EUNSUPPORTED;
+  if (stats) CVX_WS_ZERO(stats, sizeof(double) * 2 * d->cin, st);
+  if (g_dwf_variant == 1) {
+    if (in_scale) return dwf_fwd_launch_t<true, 12, 2, false>(d, x, w9c, in_scale, in_shift, relu_in, y, stats, st);
+    return dwf_fwd_launch_t<false, 12, 2, false>(d, x, w9c, nullptr, nullptr, relu_in, y, stats, st);
+  }
+  if (g_dwf_variant == 2) {
+    if (in_scale) return dwf_fwd_launch_t<true, 6, 3, false>(d, x, w9c, in_scale, in_shift, relu_in, y, stats, st);
+    return dwf_fwd_launch_t<false, 6, 3, false>(d, x, w9c, nullptr, nullptr, relu_in, y, stats, st);
+  }
+  if (in_scale) return dwf_fwd_launch_t<true, 6, 3, true>(d, x, w9c, in_scale, in_shift, relu_in, y, stats, st);
+  return dwf_fwd_launch_t<false, 6, 3, true>(d, x, w9c, nullptr, nullptr, relu_in, y, stats, st);
+}
+
+template <bool AFFINE, bool SIDE, int FY, int MINB, bool WSMEM>
+static int dwf_bwd_launch_t(const cvx_conv_desc* d, const void* dd, const void* dside, const void* x, const float* w9c,
+                            const float* in_scale, const float* in_shift, const float* negk, const float* kmean, int relu_in,
+                            const void* addend, void* g, double* dw_out, double* sums, cudaStream_t st) {
   DwFParams p;
-  dwf_params(d, relu_in, &p);
-  CUtensorMap map;
-  if (int rc = make_act_map(&map, x, d->n, d->h, d->w, d->cin, kFX + 2, kFY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  dwf_params(d, relu_in, FY, &p);
+  CUtensorMap mdd, md, mx;
+  if (int rc = make_act_map(&mdd, dd, d->n, d->h, d->w, d->cin, kFX + 2, FY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  if (int rc = make_act_map(&mx, x, d->n, d->h, d->w, d->cin, kFX + 2, FY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+  md = mx;
+  if (dside)
+    if (int rc = make_act_map(&md, dside, d->n, d->h, d->w, d->cin, kFX + 2, FY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
   const int chunks = (d->cin + 63) / 64;
-  int gx = (kNumSMs * 2) / chunks;   // two 256-thread CTAs per SM
+  int gx = (kNumSMs * MINB) / chunks;  // MINB 256-thread CTAs per SM
   if (gx < 1) gx = 1;
   if (gx > p.ntiles) gx = p.ntiles;
-  constexpr int smem = kFwdStages * kFTile + 128 + 64;
+  const dim3 grid(gx, chunks);
+  constexpr int smem = (SIDE ? 2 * 3 : 3 * 2) * ftile_bytes(FY) + 128 + 64 + (WSMEM ? kWsmBytes : 0);
   static bool configured = false;
   if (!configured) {
-    CVX_CUDA_OK(cudaFuncSetAttribute(dwf_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CVX_CUDA_OK(cudaFuncSetAttribute(dwf_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CVX_CUDA_OK(cudaFuncSetAttribute(dwf_bwd_kernel<AFFINE, SIDE, FY, MINB, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  if (stats) CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * d->cin, st));
-  if (in_scale)
-    dwf_fwd_kernel<true><<<dim3(gx, chunks), 256, smem, st>>>(map, w9c, in_scale, in_shift, (__nv_bfloat16*)y, stats, p);
-  else
-    dwf_fwd_kernel<false><<<dim3(gx, chunks), 256, smem, st>>>(map, w9c, nullptr, nullptr, (__nv_bfloat16*)y, stats, p);
+  dwf_bwd_kernel<AFFINE, SIDE, FY, MINB, WSMEM><<<grid, 256, smem, st>>>(mdd, md, mx, w9c, in_scale, in_shift, negk, kmean,
+                                                                  (const __nv_bfloat16*)addend, (__nv_bfloat16*)g, dw_out, sums, p);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
-template <bool AFFINE, bool SIDE>
-static int dwf_bwd_launch_t(const CUtensorMap& mdd, const CUtensorMap& md, const CUtensorMap& mx, const float* w9c,
-                            const float* in_scale, const float* in_shift, const float* negk, const float* kmean,
-                            const void* addend, void* g, double* dw_out, double* sums, const DwFParams& p, dim3 grid,
-                            cudaStream_t st) {
-  constexpr int smem = (SIDE ? 2 * 3 : 3 * 2) * kFTile + 128 + 64;
-  static bool configured = false;
-  if (!configured) {
-    CVX_CUDA_OK(cudaFuncSetAttribute(dwf_bwd_kernel<AFFINE, SIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
+template <int FY, int MINB, bool WSMEM>
+static int dwf_bwd_dispatch(const cvx_conv_desc* d, const void* dd, const void* dside, const float* negk, const float* kmean,
+                            const void* x, const float* w9c, const float* in_scale, const float* in_shift, int relu_in,
+                            const void* addend, void* g, double* dw_out, double* sums, cudaStream_t st) {
+  if (dside) {
+    if (in_scale) return dwf_bwd_launch_t<true, true, FY, MINB, WSMEM>(d, dd, dside, x, w9c, in_scale, in_shift, negk, kmean, relu_in, addend, g, dw_out, sums, st);
+    return dwf_bwd_launch_t<false, true, FY, MINB, WSMEM>(d, dd, dside, x, w9c, nullptr, nullptr, negk, kmean, relu_in, addend, g, dw_out, sums, st);
   }
-  dwf_bwd_kernel<AFFINE, SIDE><<<grid, 256, smem, st>>>(mdd, md, mx, w9c, in_scale, in_shift, negk, kmean,
-                                                        (const __nv_bfloat16*)addend, (__nv_bfloat16*)g, dw_out, sums, p);
-  CVX_LAUNCH_OK();
-  return CVX_OK;
+  if (in_scale) return dwf_bwd_launch_t<true, false, FY, MINB, WSMEM>(d, dd, nullptr, x, w9c, in_scale, in_shift, nullptr, nullptr, relu_in, addend, g, dw_out, sums, st);
+  return dwf_bwd_launch_t<false, false, FY, MINB, WSMEM>(d, dd, nullptr, x, w9c, nullptr, nullptr, nullptr, nullptr, relu_in, addend, g, dw_out, sums, st);
 }
 
 int dwf_bwd_launch(const cvx_conv_desc* d, const void* dd, const void* dside, const float* negk, const float* kmean,
                    const void* x, const float* w9c, const float* in_scale, const float* in_shift, int relu_in,
                    const void* addend, void* g, double* dw_out, double* sums, cudaStream_t st) {
   if (!dwf_supported(d)) return CVX_EUNSUPPORTED;
-  DwFParams p;
-  dwf_params(d, relu_in, &p);
-  CUtensorMap mdd, md, mx;
-  if (int rc = make_act_map(&mdd, dd, d->n, d->h, d->w, d->cin, kFX + 2, kFY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  if (int rc = make_act_map(&mx, x, d->n, d->h, d->w, d->cin, kFX + 2, kFY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  md = mx;
-  if (dside)
-    if (int rc = make_act_map(&md, dside, d->n, d->h, d->w, d->cin, kFX + 2, kFY + 2, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
-  const int chunks = (d->cin + 63) / 64;
-  int gx = kNumSMs / chunks;  // one 256-thread CTA per SM
-  if (gx < 1) gx = 1;
-  if (gx > p.ntiles) gx = p.ntiles;
-  const dim3 grid(gx, chunks);
-  CVX_CUDA_OK(cudaMemsetAsync(dw_out, 0, sizeof(double) * 9 * d->cin, st));
-  if (sums) CVX_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d->cin, st));
-  if (dside) {
-    if (in_scale) return dwf_bwd_launch_t<true, true>(mdd, md, mx, w9c, in_scale, in_shift, negk, kmean, addend, g, dw_out, sums, p, grid, st);
-    return dwf_bwd_launch_t<false, true>(mdd, md, mx, w9c, nullptr, nullptr, negk, kmean, addend, g, dw_out, sums, p, grid, st);
-  }
-  if (in_scale) return dwf_bwd_launch_t<true, false>(mdd, md, mx, w9c, in_scale, in_shift, nullptr, nullptr, addend, g, dw_out, sums, p, grid, st);
-  return dwf_bwd_launch_t<false, false>(mdd, md, mx, w9c, nullptr, nullptr, nullptr, nullptr, addend, g, dw_out, sums, p, grid, st);
+  CVX_WS_ZERO(dw_out, sizeof(double) * 9 * d->cin, st);
+  if (sums) CVX_WS_ZERO(sums, sizeof(double) * 2 * d->cin, st);
+  if (g_dwf_variant == 2)
+    return dwf_bwd_dispatch<6, 2, false>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);
+  if (g_dwf_variant == 1)
+    return dwf_bwd_dispatch<12, 1, false>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);
+  return dwf_bwd_dispatch<6, 2, true>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);
 }
 
 }  // namespace cvx

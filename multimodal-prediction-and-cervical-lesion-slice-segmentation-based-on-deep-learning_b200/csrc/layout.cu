@@ -8,6 +8,7 @@ namespace cvx {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_kernel_launches = 0;
+int g_ws_prezeroed = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -151,6 +152,10 @@ extern "C" {
 int cvx_abi_version(void) { return CVX_ABI_VERSION; }
 const char* cvx_last_error(void) { return cvx::g_err; }
 int64_t cvx_launch_count(void) { return (int64_t)cvx::g_kernel_launches; }
+int cvx_set_ws_prezeroed(int on) {
+  cvx::g_ws_prezeroed = on ? 1 : 0;
+  return CVX_OK;
+}
 
 int cvx_device_is_sm100(void) {
   int dev = 0, major = 0;

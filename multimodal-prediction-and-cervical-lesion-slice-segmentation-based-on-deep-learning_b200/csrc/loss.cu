@@ -222,7 +222,7 @@ int cvx_seg_loss_stats(const float* logits, const int64_t* target, const float* 
   CVX_CHECK_ARG(logits && target && stats && n > 0 && c > 0 && c <= kMaxC && h > 0 && w > 0,
                 "seg_loss_stats: bad arguments (C must be <= %d)", kMaxC);
   cudaStream_t st = as_stream(stream);
-  CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * (4 + 6 * c), st));
+  CVX_WS_ZERO(stats, sizeof(double) * (4 + 6 * c), st);
   const int64_t npix = (int64_t)n * h * w;
   const int64_t hw = (int64_t)h * w;
   CVX_CHECK_ARG(n <= 65535, "seg_loss_stats: batch %d exceeds the grid's image dimension", n);

@@ -265,7 +265,7 @@ int cvx_dwf_bwd(const cvx_conv_desc* d, const void* dd, const void* dside, const
 int cvx_bn_stats(const void* x, double* stats, int64_t rows, int c, int dtype, void* stream) {
   CVX_CHECK_ARG(x && stats && rows > 0 && c > 0, "bn_stats: bad arguments");
   cudaStream_t st = as_stream(stream);
-  CVX_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * c, st));
+  CVX_WS_ZERO(stats, sizeof(double) * 2 * c, st);
   CVX_CHECK_ARG(dtype == CVX_BF16 && c % 8 == 0, "bn_stats: bf16 with C %% 8 == 0 only");
   return colreduce_launch<__nv_bfloat16, RawStatsF>(RawStatsF{(const __nv_bfloat16*)x, c}, rows, c, stats, st);
 }
@@ -302,7 +302,7 @@ int cvx_affine_act(const void* p, const void* res, void* y, const float* scale, 
 int cvx_bn_bwd_sums(const void* dy, const void* y, const void* p, double* sums, int64_t rows, int c, int act, void* stream) {
   CVX_CHECK_ARG(dy && p && sums && (act == CVX_ACT_NONE || y) && rows > 0 && c > 0 && c % 8 == 0, "bn_bwd_sums: bad arguments");
   cudaStream_t st = as_stream(stream);
-  CVX_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * c, st));
+  CVX_WS_ZERO(sums, sizeof(double) * 2 * c, st);
   return colreduce_launch<__nv_bfloat16, BnRawBwdF, 256, 3>(
       BnRawBwdF{(const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)p, c, act}, rows, c, sums, st);
 }

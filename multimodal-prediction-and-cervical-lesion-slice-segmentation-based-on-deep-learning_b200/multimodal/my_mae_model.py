@@ -339,9 +339,20 @@ class fusion_model_mae_2(nn.Module):
         y = R.linear(R.gelu(R.linear(y, mix.mix_mip_2[0])), mix.mix_mip_2[2])
         return ops.Add.apply(x, y)
 
-    def _pool(self, x, pool: my_GlobalAttention, G: int, seg: int):
-        gate = R.linear(ops.relu(R.linear(x, pool.gate_nn[0])), pool.gate_nn[2])
-        return R.GatePool.apply(x, gate, G, seg)
+    @staticmethod
+    def _per_modality(xs: Dict[str, torch.Tensor], lins: Dict[str, nn.Linear]) -> Dict[str, torch.Tensor]:
+        """The same layer of every modality branch (own weights, own rows) as ONE grouped GEMM launch."""
+        ms = list(xs)
+        return R.linear_group([(xs[m], 0, xs[m].shape[0], lins[m], m, 0) for m in ms])
+
+    def _pool_all(self, xs: Dict[str, torch.Tensor], suffix: str, G: int, seg: Dict[str, int]):
+        """Gated attention pooling of every modality (my_GlobalAttention, my_mae_model.py:35-63): the two gate layers are
+        one grouped launch each; the per-graph softmax + weighted sum is one launch per modality."""
+        pools = {m: getattr(self, "mpool_" + m + suffix) for m in xs}
+        h = self._per_modality(xs, {m: pools[m].gate_nn[0] for m in xs})
+        h = {m: ops.relu(h[m]) for m in xs}
+        gate = self._per_modality(h, {m: pools[m].gate_nn[2] for m in xs})
+        return {m: R.GatePool.apply(xs[m], gate[m], G, seg[m]) for m in xs}
 
     # ------------------------------------------------------------------ batched forward
     def forward_batch(self, feats: Dict[str, torch.Tensor], edges: Dict[str, torch.Tensor],
@@ -362,17 +373,24 @@ class fusion_model_mae_2(nn.Module):
         dev = feats[present[0]].device
         C = self.hidden
         nodes, seg, pooled, att_2 = {}, {}, [], []
+        # SAGEConv of every modality (lin_l on the neighbourhood mean, lin_r on the node itself): 2 x P GEMMs, one launch
+        entries, xin = [], {}
         for m in present:
             x = feats[m].contiguous().float()
             seg[m] = int(x.shape[1])
             x = x.reshape(G * seg[m], x.shape[2])
             conv = getattr(self, m + "_gnn_2")
             agg = R.GraphMean.apply(x, self._topology(edges[m], seg[m], dev), G)
-            x = ops.Add.apply(R.linear(agg, conv.lin_l), R.linear(x, conv.lin_r))
+            entries.append((agg, 0, agg.shape[0], conv.lin_l, ("l", m), 0))
+            entries.append((x, 0, x.shape[0], conv.lin_r, ("r", m), 0))
+        sage = R.linear_group(entries)
+        for m in present:
+            x = ops.Add.apply(sage[("l", m)], sage[("r", m)])
             x = R.graph_layernorm(ops.relu(x), getattr(self, m + "_relu_2")[1], G, seg[m])
-            x = self._drop(x, getattr(self, m + "_relu_2")[2].p)
-            nodes[m] = x
-            px, att = self._pool(x, getattr(self, "mpool_" + m), G, seg[m])
+            nodes[m] = self._drop(x, getattr(self, m + "_relu_2")[2].p)
+        pools = self._pool_all(nodes, "", G, seg)
+        for m in present:
+            px, att = pools[m]
             pooled.append(px.reshape(G, 1, 1, C)); att_2.append(att.reshape(G, seg[m]))
         pool_x = (ops.cat_channels(pooled) if len(pooled) > 1 else pooled[0]).reshape(G * len(present), C)
         out = {"mae_labels": pool_x.reshape(G, len(present), C), "att_2": att_2}
@@ -415,18 +433,22 @@ class fusion_model_mae_2(nn.Module):
                     nodes[m] = ops.Add.apply(nodes[m], ops.broadcast_hw(row.reshape(G, 1, 1, C), seg[m], 1)
                                              .reshape(G * seg[m], C))
         att_3, heads, feas, logits = [], [], [], {}
+        pools = self._pool_all(nodes, "_2", G, seg)
+        f = {}
         for m in present:
-            px, att = self._pool(nodes[m], getattr(self, "mpool_" + m + "_2"), G, seg[m])
+            px, att = pools[m]
             att_3.append(att.reshape(G, seg[m]))
-            f = R.L2Norm.apply(px)                                                     # F.normalize(dim=1) is row-wise
-            feas.append(f.reshape(G, 1, 1, C))
-            v = R.graph_layernorm(ops.relu(R.linear(f, getattr(self, "lin1_" + m))), getattr(self, "norm1_" + m), G, 1)
-            v = self._drop(v, self.dropout.p)
-            v = R.graph_layernorm(ops.relu(R.linear(v, getattr(self, "lin2_" + m))), getattr(self, "norm2_" + m), G, 1)
-            v = self._drop(v, self.dropout.p)
-            v = R.linear(v, getattr(self, "lin3_" + m))
-            logits[m] = R.linear(v, getattr(self, "classifier_" + m))
-            heads.append(v.reshape(G, 1, 1, v.shape[1]))
+            f[m] = R.L2Norm.apply(px)                                                  # F.normalize(dim=1) is row-wise
+            feas.append(f[m].reshape(G, 1, 1, C))
+        # the per-modality heads 512 -> 128 -> 32 -> 8 (-> 4): every layer is one grouped launch over the modalities
+        v = self._per_modality(f, {m: getattr(self, "lin1_" + m) for m in present})
+        v = {m: self._drop(R.graph_layernorm(ops.relu(v[m]), getattr(self, "norm1_" + m), G, 1), self.dropout.p) for m in present}
+        v = self._per_modality(v, {m: getattr(self, "lin2_" + m) for m in present})
+        v = {m: self._drop(R.graph_layernorm(ops.relu(v[m]), getattr(self, "norm2_" + m), G, 1), self.dropout.p) for m in present}
+        v = self._per_modality(v, {m: getattr(self, "lin3_" + m) for m in present})
+        logits = self._per_modality(v, {m: getattr(self, "classifier_" + m) for m in present})
+        for m in present:
+            heads.append(v[m].reshape(G, 1, 1, v[m].shape[1]))
         K = heads[0].shape[3]
         P = len(present)
         multi_x = (ops.cat_channels(heads) if P > 1 else heads[0]).reshape(G, P, 1, K)

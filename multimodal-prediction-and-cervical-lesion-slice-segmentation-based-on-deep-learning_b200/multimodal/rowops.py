@@ -9,12 +9,117 @@ from .. import ops
 from ..backend import get_backend
 
 
-def linear(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
-    """nn.Linear on a [rows, C_in] matrix through the 1x1 convolution kernels."""
+def linear_conv(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
+    """nn.Linear on a [rows, C_in] matrix through the 1x1 convolution kernels (the r01 path; kept for A/B timing)."""
     rows = x.shape[0]
     w = lin.weight.reshape(lin.out_features, lin.in_features, 1, 1)
     y = ops.conv2d(x.reshape(rows, 1, 1, lin.in_features), w, lin.bias, 1, 0, 1)
     return y.reshape(rows, lin.out_features)
+
+
+class GroupedLinear(Function):
+    """A layer of independent ``nn.Linear`` calls - the per-modality branches of the fusion head
+    (my_mae_model.py:404-416, 544, 550, 657-674, 706-769) - as ONE grouped GEMM launch (``cvx_gemm_grouped``), forward,
+    data gradient and weight + bias gradient alike.  ``plan`` is a tuple of entries
+    ``(in_idx, in_row0, rows, w_idx, b_idx | -1, out_idx, out_row0)``: rows ``in_row0 .. +rows`` of input tensor
+    ``in_idx`` times weight ``w_idx`` go to rows ``out_row0 .. +rows`` of output ``out_idx`` - so the branches can read
+    from and write into tensors that stack the modalities along the rows, which lets the row operators between the
+    layers run once per stack instead of once per modality.  Weights stay in nn.Linear's [out, in] layout: no packing,
+    no transposes.  ``tensors`` = inputs, then weights, then biases."""
+
+    @staticmethod
+    def forward(ctx, plan, n_in, n_w, out_shapes, *tensors):
+        ins = [t.contiguous() for t in tensors[:n_in]]
+        ws = list(tensors[n_in:n_in + n_w])
+        bs = list(tensors[n_in + n_w:])
+        outs = [torch.empty(shape, dtype=torch.float32, device=ins[0].device) for shape in out_shapes]
+        probs = []
+        for (ii, r0, rows, wi, bi, oi, o0) in plan:
+            x, w = ins[ii], ws[wi].detach()
+            n, k = w.shape
+            assert x.shape[1] == k and outs[oi].shape[1] == n, "grouped linear: shape mismatch"
+            probs.append(dict(a=x[r0:r0 + rows], b=w, c=outs[oi][o0:o0 + rows], bias=None if bi < 0 else bs[bi].detach(),
+                              m=rows, n=n, k=k, lda_m=k, lda_k=1, ldb_n=k, ldb_k=1, ldc=n))
+        get_backend().gemm_grouped(probs)
+        ctx.save_for_backward(*ins, *ws)
+        ctx.plan, ctx.n_in, ctx.n_w, ctx.n_b = plan, n_in, n_w, len(bs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        B = get_backend()
+        saved = ctx.saved_tensors
+        ins, ws = saved[:ctx.n_in], saved[ctx.n_in:]
+        plan = ctx.plan
+        dys = [None if d is None else d.contiguous() for d in dys]
+        dev = ins[0].device
+        # ---- data gradients: dX[rows, k] = dY[rows, n] W[n, k], written into one buffer per input tensor
+        dxs = [None] * ctx.n_in
+        covered = [0] * ctx.n_in
+        probs = []
+        for (ii, r0, rows, wi, bi, oi, o0) in plan:
+            if not ctx.needs_input_grad[4 + ii] or dys[oi] is None:
+                continue
+            if dxs[ii] is None:
+                dxs[ii] = torch.empty_like(ins[ii])
+            n, k = ws[wi].shape
+            covered[ii] += rows
+            probs.append(dict(a=dys[oi][o0:o0 + rows], b=ws[wi].detach(), c=dxs[ii][r0:r0 + rows], m=rows, n=k, k=n,
+                              lda_m=n, lda_k=1, ldb_n=1, ldb_k=k, ldc=k))
+        for ii, dx in enumerate(dxs):
+            if dx is not None and covered[ii] != dx.shape[0]:      # rows no entry touched have no gradient
+                raise RuntimeError("grouped linear: the plan does not cover every row of input %d" % ii)
+        if probs:
+            B.gemm_grouped(probs)
+        # ---- weight and bias gradients: dW[n, k] = dY^T[n, rows] X[rows, k]; db[n] = row sums of dY^T (same launch)
+        dws = [None] * ctx.n_w
+        dbs = [None] * ctx.n_b
+        probs = []
+        for (ii, r0, rows, wi, bi, oi, o0) in plan:
+            if dys[oi] is None or not ctx.needs_input_grad[4 + ctx.n_in + wi]:
+                continue
+            if dws[wi] is not None:
+                raise RuntimeError("grouped linear: a weight may appear in one plan entry only")
+            n, k = ws[wi].shape
+            dws[wi] = torch.empty((n, k), dtype=torch.float32, device=dev)
+            db = None
+            if bi >= 0 and ctx.needs_input_grad[4 + ctx.n_in + ctx.n_w + bi]:
+                db = dbs[bi] = torch.empty((n,), dtype=torch.float32, device=dev)
+            probs.append(dict(a=dys[oi][o0:o0 + rows], b=ins[ii][r0:r0 + rows], c=dws[wi], rowsum=db, m=n, n=k, k=rows,
+                              lda_m=1, lda_k=n, ldb_n=1, ldb_k=k, ldc=k))
+        if probs:
+            B.gemm_grouped(probs)
+        return (None, None, None, None, *dxs, *dws, *dbs)
+
+
+def linear_group(entries):
+    """``entries``: list of ``(x, row0, rows, lin, out_key, out_row0)`` - rows of tensor ``x`` through ``lin`` into rows of
+    the output named ``out_key`` (outputs with the same key are one stacked tensor).  Returns {out_key: tensor}."""
+    ins, in_ids, ws, bs, plan = [], {}, [], [], []
+    out_rows, out_cols, out_keys = {}, {}, []
+    for (x, r0, rows, lin, key, o0) in entries:
+        if id(x) not in in_ids:
+            in_ids[id(x)] = len(ins)
+            ins.append(x)
+        if key not in out_rows:
+            out_rows[key], out_cols[key] = 0, lin.out_features
+            out_keys.append(key)
+        out_rows[key] = max(out_rows[key], o0 + rows)
+        assert out_cols[key] == lin.out_features, "stacked outputs must have one width"
+        ws.append(lin.weight)
+        bi = -1
+        if lin.bias is not None:
+            bi = len(bs)
+            bs.append(lin.bias)
+        plan.append((in_ids[id(x)], int(r0), int(rows), len(ws) - 1, bi, out_keys.index(key), int(o0)))
+    shapes = tuple((out_rows[k], out_cols[k]) for k in out_keys)
+    outs = GroupedLinear.apply(tuple(plan), len(ins), len(ws), shapes, *ins, *ws, *bs)
+    return dict(zip(out_keys, outs))
+
+
+def linear(x: torch.Tensor, lin: torch.nn.Linear) -> torch.Tensor:
+    """One nn.Linear on a [rows, C_in] matrix: a group of one (no weight packing, fixed-order sums)."""
+    return linear_group([(x, 0, x.shape[0], lin, 0, 0)])[0]
 
 
 class SegLayerNorm(Function):

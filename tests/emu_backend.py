@@ -549,6 +549,18 @@ class EmuBackend:
         lr, b1, b2, eps, wd, gs = [float(t) for t in hyper]
         self.adam_step(p, g, m, v, lr, b1, b2, eps, wd, int(step_dev), gs)
 
+    def gemm_grouped(self, problems):
+        for q in problems:
+            m, n, k = q["m"], q["n"], q["k"]
+            A = torch.as_strided(q["a"], (m, k), (q["lda_m"], q["lda_k"]))
+            Bm = torch.as_strided(q["b"], (n, k), (q["ldb_n"], q["ldb_k"]))
+            out = A.double() @ Bm.double().t()
+            if q.get("bias") is not None:
+                out = out + q["bias"].double()[None, :]
+            torch.as_strided(q["c"], (m, n), (q["ldc"], 1)).copy_(out.float())
+            if q.get("rowsum") is not None:
+                q["rowsum"].reshape(-1)[:m].copy_(A.double().sum(1).float())
+
     def sgd_step_dev(self, p, g, buf, hyper, nesterov):
         lr, mom, _, _, wd, gs = [float(t) for t in hyper]
         self.sgd_step(p, g, buf, lr, mom, wd, nesterov, False, gs)
