@@ -275,6 +275,36 @@ CVX_API int cvx_rows_gather(const float* x, const int* idx, const float* fill, f
 /* backward of cvx_rows_gather in gather form (fixed summation order, writes every element of dx [src_rows, c] / dfill) */
 CVX_API int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int src_rows, int c,
                          void* stream);
+/* ---- segment-table row operators: every modality branch of the fusion head in one launch -------------------------------
+ * The node rows of all modality branches are stacked in one [rows, c] matrix (modality-major); segment s = one patient
+ * graph of one modality = rows seg_start[s] .. +seg_len[s], with the LayerNorm affine of parameter set seg_set[s]
+ * (cvx_param_sets: per-set parameter / gradient pointers and the row range of each set, passed by value).  Replaces the
+ * per-modality calls of PyG LayerNorm (my_mae_model.py:396, 546), my_GlobalAttention (:35-63, 550, 657-674) and the
+ * "node features += reconstructed token" adds (:636-649).  All index tables are device int32 arrays; sums have a fixed
+ * order (no atomics). */
+#define CVX_MAX_PARAM_SETS 8
+typedef struct cvx_param_sets {
+  const float* w[CVX_MAX_PARAM_SETS];
+  const float* b[CVX_MAX_PARAM_SETS];
+  float* dw[CVX_MAX_PARAM_SETS];            /* backward only (nullable) */
+  float* db[CVX_MAX_PARAM_SETS];
+  int row_start[CVX_MAX_PARAM_SETS + 1];    /* rows of set i: row_start[i] .. row_start[i + 1] */
+  int sets;
+} cvx_param_sets;
+CVX_API int cvx_segtab_layernorm_fwd(const float* x, const cvx_param_sets* ps, float* y, float* stats, const int* seg_start,
+                                     const int* seg_len, const int* seg_set, int segments, int c, float eps, int mode,
+                                     void* stream);
+CVX_API int cvx_segtab_layernorm_bwd(const float* dy, const float* x, const cvx_param_sets* ps, const float* stats, float* dx,
+                                     const int* seg_start, const int* seg_len, const int* seg_set, const int* row_seg,
+                                     int segments, int c, float eps, int mode, void* stream);
+CVX_API int cvx_segtab_gate_pool_fwd(const float* x, const float* gate, float* pooled, float* att, const int* seg_start,
+                                     const int* seg_len, int segments, int max_len, int c, void* stream);
+CVX_API int cvx_segtab_gate_pool_bwd(const float* dpooled, const float* x, const float* att, float* dx, float* dgate,
+                                     const int* seg_start, const int* seg_len, int segments, int max_len, int c, void* stream);
+CVX_API int cvx_segtab_bcast_add(const float* x, const float* t, float* y, const int* row_seg, const int* tok_of_seg, int rows,
+                                 int c, void* stream);
+CVX_API int cvx_segtab_bcast_add_bwd(const float* dy, float* dt, const int* seg_of_tok, const int* seg_start,
+                                     const int* seg_len, int tokens, int c, void* stream);
 /* ---- grouped fp32 GEMM: the per-modality linear layers of the fusion head as ONE launch --------------------------------
  * Reference sites: the four SAGEConv (lin_l, lin_r), gate MLPs and per-modality head MLPs of fusion_model_mae_2
  * (MultiModal Prediction/Four_Modal/my_mae_model.py:404-416, 544, 550, 657-674, 706-769) - same topology per modality,

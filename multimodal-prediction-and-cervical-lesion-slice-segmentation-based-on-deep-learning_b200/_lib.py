@@ -30,6 +30,15 @@ class GemmProblem(C.Structure):
 
 
 MAX_GEMM_PROBLEMS = 16
+MAX_PARAM_SETS = 8
+
+
+class ParamSets(C.Structure):
+    """cvx_param_sets of include/cervix_b200.h."""
+    _fields_ = [("w", C.c_void_p * MAX_PARAM_SETS), ("b", C.c_void_p * MAX_PARAM_SETS), ("dw", C.c_void_p * MAX_PARAM_SETS),
+                ("db", C.c_void_p * MAX_PARAM_SETS), ("row_start", C.c_int32 * (MAX_PARAM_SETS + 1)), ("sets", C.c_int32)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _D = C.POINTER(ConvDesc)
 
@@ -111,6 +120,12 @@ PROTOTYPES = {
     "cvx_sgd_step": [_P, _P, _P, _L, _F, _F, _F, _I, _I, _F, _P],
     "cvx_sgd_step_dev": [_P, _P, _P, _L, _P, _I, _P],
     "cvx_gemm_grouped": [C.POINTER(GemmProblem), _I, _P],
+    "cvx_segtab_layernorm_fwd": [_P, C.POINTER(ParamSets), _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "cvx_segtab_layernorm_bwd": [_P, _P, C.POINTER(ParamSets), _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "cvx_segtab_gate_pool_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "cvx_segtab_gate_pool_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "cvx_segtab_bcast_add": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "cvx_segtab_bcast_add_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "cvx_multi_gather_chunk": [],
     "cvx_set_ws_prezeroed": [_I],
     "cvx_multi_gather": [_P, _P, _P, _P, _P, _I, _P, _P],

@@ -530,6 +530,80 @@ class CudaBackend:
               "cvx_rows_scatter_add")
         return dx, dfill
 
+    # ------------------------------------------------------------------ segment-table row operators (all modalities at once)
+    @staticmethod
+    def _param_sets(ws, bs, row_start, dws=None, dbs=None):
+        ps = _lib.ParamSets()
+        n = len(row_start) - 1
+        if n > _lib.MAX_PARAM_SETS:
+            raise _lib.CervixError("cervix_b200: at most %d parameter sets per launch" % _lib.MAX_PARAM_SETS)
+        ps.sets = n
+        for i in range(n):
+            ps.w[i] = None if ws is None else ws[i].data_ptr()
+            ps.b[i] = None if bs is None else bs[i].data_ptr()
+            ps.dw[i] = None if dws is None else dws[i].data_ptr()
+            ps.db[i] = None if dbs is None else dbs[i].data_ptr()
+        for i in range(n + 1):
+            ps.row_start[i] = int(row_start[i])
+        return ps
+
+    def segtab_layernorm_fwd(self, x, ws, bs, tab, eps: float, mode: int):
+        """tab: SegTable-like with device int32 ``seg_start, seg_len, seg_set, row_seg`` and host ``row_start, segments``."""
+        self._chk(x, *ws, *bs)
+        c = int(x.shape[-1])
+        y = torch.empty_like(x)
+        stats = torch.empty((tab.segments, 3), dtype=torch.float32, device=x.device)
+        ps = self._param_sets(ws, bs, tab.row_start)
+        check(self.lib.cvx_segtab_layernorm_fwd(_p(x), C.byref(ps), _p(y), _p(stats), _p(tab.seg_start), _p(tab.seg_len),
+                                                _p(tab.seg_set), tab.segments, c, float(eps), mode, self._stream()),
+              "cvx_segtab_layernorm_fwd")
+        return y, stats
+
+    def segtab_layernorm_bwd(self, dy, x, ws, stats, tab, eps: float, mode: int):
+        self._chk(dy, x, stats, *ws)
+        c = int(x.shape[-1])
+        dx = torch.empty_like(x)
+        dws = [torch.empty((c,), dtype=torch.float32, device=x.device) for _ in ws]
+        dbs = [torch.empty((c,), dtype=torch.float32, device=x.device) for _ in ws]
+        ps = self._param_sets(ws, None, tab.row_start, dws, dbs)
+        check(self.lib.cvx_segtab_layernorm_bwd(_p(dy), _p(x), C.byref(ps), _p(stats), _p(dx), _p(tab.seg_start),
+                                                _p(tab.seg_len), _p(tab.seg_set), _p(tab.row_seg), tab.segments, c, float(eps),
+                                                mode, self._stream()), "cvx_segtab_layernorm_bwd")
+        return dx, dws, dbs
+
+    def segtab_gate_pool_fwd(self, x, gate, tab):
+        self._chk(x, gate)
+        c = int(x.shape[-1])
+        pooled = torch.empty((tab.segments, c), dtype=torch.float32, device=x.device)
+        att = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_segtab_gate_pool_fwd(_p(x), _p(gate), _p(pooled), _p(att), _p(tab.seg_start), _p(tab.seg_len),
+                                                tab.segments, tab.max_len, c, self._stream()), "cvx_segtab_gate_pool_fwd")
+        return pooled, att
+
+    def segtab_gate_pool_bwd(self, dpooled, x, att, tab):
+        self._chk(dpooled, x, att)
+        c = int(x.shape[-1])
+        dx = torch.empty_like(x)
+        dgate = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+        check(self.lib.cvx_segtab_gate_pool_bwd(_p(dpooled), _p(x), _p(att), _p(dx), _p(dgate), _p(tab.seg_start),
+                                                _p(tab.seg_len), tab.segments, tab.max_len, c, self._stream()),
+              "cvx_segtab_gate_pool_bwd")
+        return dx, dgate
+
+    def segtab_bcast_add(self, x, t, tab, tok_of_seg):
+        self._chk(x, t, tok_of_seg)
+        y = torch.empty_like(x)
+        check(self.lib.cvx_segtab_bcast_add(_p(x), _p(t), _p(y), _p(tab.row_seg), _p(tok_of_seg), int(x.shape[0]),
+                                            int(x.shape[1]), self._stream()), "cvx_segtab_bcast_add")
+        return y
+
+    def segtab_bcast_add_bwd(self, dy, tab, seg_of_tok, tokens: int):
+        self._chk(dy, seg_of_tok)
+        dt = torch.empty((tokens, dy.shape[1]), dtype=torch.float32, device=dy.device)
+        check(self.lib.cvx_segtab_bcast_add_bwd(_p(dy), _p(dt), _p(seg_of_tok), _p(tab.seg_start), _p(tab.seg_len), tokens,
+                                                int(dy.shape[1]), self._stream()), "cvx_segtab_bcast_add_bwd")
+        return dt
+
     def gemm_grouped(self, problems):
         """One launch for a list of independent fp32 GEMMs C = A B^T (+ bias) (cvx_gemm_grouped).  Each problem is a dict
         with tensors ``a``, ``b``, ``c`` (+ optional ``bias``, ``rowsum``), ints ``m, n, k`` and element strides
@@ -556,10 +630,10 @@ class CudaBackend:
             if not t.is_cuda or t.dtype != torch.float32:
                 raise _lib.CervixError("cervix_b200: gemm_grouped takes fp32 CUDA tensors (got %s on %s)" % (t.dtype, t.device))
 
-    def softmax_ce(self, logits, labels, loss, weight: float, want_grad: bool):
-        self._chk(logits, labels, loss)
+    def softmax_ce(self, logits, labels, loss, weight: float, want_grad: bool, out=None):
+        self._chk(logits, labels, loss, out)
         b, k = logits.shape
-        d = torch.empty_like(logits) if want_grad else None
+        d = (out if out is not None else torch.empty_like(logits)) if want_grad else None
         check(self.lib.cvx_softmax_ce(_p(logits), _p(labels), _p(loss), _p(d), b, k, float(weight), self._stream()),
               "cvx_softmax_ce")
         return d

@@ -384,6 +384,176 @@ __global__ void masked_mse_kernel(const float* __restrict__ a, const float* __re
   if (threadIdx.x == 0) *loss += weight * s * inv_count;
 }
 
+// =====================================================================================================================
+// Segment-table operators: ALL modalities of the head in one launch.
+// The node rows of every modality branch are stacked in one [R, C] matrix (modality-major, then patient, then node); a
+// "segment" is one patient graph of one modality: rows seg_start[s] .. +seg_len[s], belonging to parameter set
+// seg_set[s] (= the modality, whose own LayerNorm affine / weights apply).  The ORDER of the segment ids is free, so the
+// pooled output can be produced patient-major (the token order of the masked auto-encoder) or modality-major (the row
+// blocks the per-modality head GEMMs need) without a gather.  Parameter sets arrive as a small by-value pointer table.
+constexpr int kMaxSets = CVX_MAX_PARAM_SETS;
+
+struct SetPtrs {
+  const float* w[kMaxSets];
+  const float* b[kMaxSets];
+  float* dw[kMaxSets];
+  float* db[kMaxSets];
+  int row_start[kMaxSets + 1];   // rows of set i: row_start[i] .. row_start[i+1] (stacked modality-major)
+  int sets;
+};
+
+__global__ void segtab_layernorm_fwd_kernel(const float* __restrict__ x, SetPtrs P, float* __restrict__ y,
+                                            float* __restrict__ stats, const int* __restrict__ seg_start,
+                                            const int* __restrict__ seg_len, const int* __restrict__ seg_set, int C,
+                                            float eps, int mode) {
+  __shared__ float sh[32];
+  const int g = blockIdx.x;
+  const int n = seg_len[g] * C;
+  const size_t off = (size_t)seg_start[g] * C;
+  const float* xs = x + off;
+  const float* w = P.w[seg_set[g]];
+  const float* b = P.b[seg_set[g]];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += xs[i];
+  const float mean = block_sum(s, sh) / n;
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float d = xs[i] - mean; v = fmaf(d, d, v); }
+  const float var = block_sum(v, sh) / n;
+  const float sd = sqrtf(var);
+  const float r = mode == 0 ? 1.f / (sd + eps) : rsqrtf(var + eps);
+  if (threadIdx.x == 0) { stats[3 * g] = mean; stats[3 * g + 1] = r; stats[3 * g + 2] = sd; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % C;
+    y[off + i] = (xs[i] - mean) * r * w[c] + b[c];
+  }
+}
+
+__global__ void segtab_layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, SetPtrs P,
+                                            const float* __restrict__ stats, float* __restrict__ dx,
+                                            const int* __restrict__ seg_start, const int* __restrict__ seg_len,
+                                            const int* __restrict__ seg_set, int C, float eps, int mode) {
+  __shared__ float sh[32];
+  const int g = blockIdx.x;
+  const int n = seg_len[g] * C;
+  const size_t off = (size_t)seg_start[g] * C;
+  const float mean = stats[3 * g], r = stats[3 * g + 1], sd = stats[3 * g + 2];
+  const float* xs = x + off;
+  const float* gs = dy + off;
+  const float* w = P.w[seg_set[g]];
+  float sg = 0.f, sgx = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float gi = gs[i] * w[i % C];
+    sg += gi;
+    sgx = fmaf(gi, xs[i] - mean, sgx);
+  }
+  const float Sg = block_sum(sg, sh);
+  const float Sgx = block_sum(sgx, sh);
+  const float K = mode == 0 ? (sd > 0.f ? Sgx * r * r / (n * sd) : 0.f) : Sgx * r * r * r / n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float xc = xs[i] - mean;
+    dx[off + i] = r * (gs[i] * w[i % C] - Sg / n) - xc * K;
+  }
+}
+
+// affine gradients of every parameter set: block (x = 32 channels, y = set); fixed summation order
+__global__ void __launch_bounds__(256) segtab_ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                   const float* __restrict__ stats,
+                                                                   const int* __restrict__ row_seg, SetPtrs P, int C) {
+  __shared__ float pw[8][33], pb[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx, set = blockIdx.y;
+  const int r0 = P.row_start[set], r1 = P.row_start[set + 1];
+  float aw = 0.f, ab = 0.f;
+  if (c < C) {
+    for (int r = r0 + ry; r < r1; r += 8) {
+      const int g = row_seg[r];
+      const float gi = dy[(size_t)r * C + c];
+      aw = fmaf(gi * (x[(size_t)r * C + c] - stats[3 * g]), stats[3 * g + 1], aw);
+      ab += gi;
+    }
+  }
+  pw[ry][cx] = aw;
+  pb[ry][cx] = ab;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float sw = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sw += pw[k][cx]; sb += pb[k][cx]; }
+    if (P.dw[set]) P.dw[set][c] = sw;
+    if (P.db[set]) P.db[set][c] = sb;
+  }
+}
+
+// gated attention pooling with a segment table: CTA s pools rows seg_start[s] .. +seg_len[s] into pooled row s
+__global__ void segtab_gate_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gate,
+                                            float* __restrict__ pooled, float* __restrict__ att,
+                                            const int* __restrict__ seg_start, const int* __restrict__ seg_len, int C) {
+  __shared__ float a[64];
+  const int s = blockIdx.x, r0 = seg_start[s], seg = seg_len[s];
+  if (threadIdx.x == 0) {
+    float mx = -INFINITY;
+    for (int i = 0; i < seg; ++i) mx = fmaxf(mx, gate[r0 + i]);
+    float sum = 0.f;
+    for (int i = 0; i < seg; ++i) { a[i] = expf(gate[r0 + i] - mx); sum += a[i]; }
+    for (int i = 0; i < seg; ++i) { a[i] = a[i] / (sum + 1e-16f); att[r0 + i] = a[i]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < seg; ++i) acc = fmaf(a[i], x[((size_t)r0 + i) * C + c], acc);
+    pooled[(size_t)s * C + c] = acc;
+  }
+}
+
+__global__ void segtab_gate_pool_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ x,
+                                            const float* __restrict__ att, float* __restrict__ dx,
+                                            float* __restrict__ dgate, const int* __restrict__ seg_start,
+                                            const int* __restrict__ seg_len, int C) {
+  __shared__ float sh[32];
+  __shared__ float datt[64];
+  const int s = blockIdx.x, r0 = seg_start[s], seg = seg_len[s];
+  for (int i = 0; i < seg; ++i) {
+    float v = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) v = fmaf(dpooled[(size_t)s * C + c], x[((size_t)r0 + i) * C + c], v);
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) datt[i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float dot = 0.f;
+    for (int i = 0; i < seg; ++i) dot = fmaf(att[r0 + i], datt[i], dot);
+    for (int i = 0; i < seg; ++i) dgate[r0 + i] = att[r0 + i] * (datt[i] - dot);
+  }
+  for (int i = 0; i < seg; ++i)
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      dx[((size_t)r0 + i) * C + c] = att[r0 + i] * dpooled[(size_t)s * C + c];
+}
+
+// y[row] = x[row] + t[tok_of_seg[row_seg[row]]]  (token -1: nothing added) - "node features += reconstructed modality
+// token" (my_mae_model.py:636-649) for every modality at once
+__global__ void segtab_bcast_add_kernel(const float* __restrict__ x, const float* __restrict__ t, float* __restrict__ y,
+                                        const int* __restrict__ row_seg, const int* __restrict__ tok_of_seg, int rows, int C) {
+  const int64_t total = (int64_t)rows * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / C), c = (int)(i % C);
+    const int tok = tok_of_seg[row_seg[r]];
+    y[i] = x[i] + (tok >= 0 ? t[(size_t)tok * C + c] : 0.f);
+  }
+}
+// its gradient w.r.t. the tokens: dt[tok] = sum of dy over the rows of the segment that took token tok (one CTA per token,
+// rows in order: no atomics); seg_of_tok[tok] = that segment or -1 (then dt[tok] = 0)
+__global__ void segtab_bcast_add_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dt,
+                                            const int* __restrict__ seg_of_tok, const int* __restrict__ seg_start,
+                                            const int* __restrict__ seg_len, int C) {
+  const int tok = blockIdx.x, s = seg_of_tok[tok];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    if (s >= 0)
+      for (int i = 0; i < seg_len[s]; ++i) acc += dy[((size_t)seg_start[s] + i) * C + c];
+    dt[(size_t)tok * C + c] = acc;
+  }
+}
+
 static inline int rgrid(int64_t total) {
   int64_t b = ceil_div64(total, 256);
   const int64_t cap = (int64_t)kNumSMs * 8;
@@ -414,6 +584,80 @@ int cvx_seg_layernorm_bwd(const float* dy, const float* x, const float* w, const
     ln_param_grad_kernel<<<(c + 31) / 32, 256, 0, st>>>(dy, x, stats, dw, db, groups * seg, seg, c);
     CVX_LAUNCH_OK();
   }
+  return CVX_OK;
+}
+
+static int fill_sets(SetPtrs* P, const cvx_param_sets* ps, const char* who) {
+  CVX_CHECK_ARG(ps && ps->sets > 0 && ps->sets <= kMaxSets, "%s: 1..%d parameter sets", who, kMaxSets);
+  P->sets = ps->sets;
+  for (int i = 0; i < kMaxSets; ++i) {
+    const bool on = i < ps->sets;
+    P->w[i] = on ? ps->w[i] : nullptr; P->b[i] = on ? ps->b[i] : nullptr;
+    P->dw[i] = on ? ps->dw[i] : nullptr; P->db[i] = on ? ps->db[i] : nullptr;
+    P->row_start[i] = on ? ps->row_start[i] : 0;
+  }
+  for (int i = ps->sets; i <= kMaxSets; ++i) P->row_start[i] = ps->row_start[ps->sets];
+  return CVX_OK;
+}
+
+int cvx_segtab_layernorm_fwd(const float* x, const cvx_param_sets* ps, float* y, float* stats, const int* seg_start,
+                             const int* seg_len, const int* seg_set, int segments, int c, float eps, int mode, void* stream) {
+  CVX_CHECK_ARG(x && y && stats && seg_start && seg_len && seg_set && segments > 0 && c > 0 && (mode == 0 || mode == 1),
+                "segtab_layernorm_fwd: bad arguments");
+  SetPtrs P;
+  if (int rc = fill_sets(&P, ps, "segtab_layernorm_fwd")) return rc;
+  for (int i = 0; i < P.sets; ++i) CVX_CHECK_ARG(P.w[i] && P.b[i], "segtab_layernorm_fwd: set %d has no affine parameters", i);
+  segtab_layernorm_fwd_kernel<<<segments, 256, 0, as_stream(stream)>>>(x, P, y, stats, seg_start, seg_len, seg_set, c, eps, mode);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_segtab_layernorm_bwd(const float* dy, const float* x, const cvx_param_sets* ps, const float* stats, float* dx,
+                             const int* seg_start, const int* seg_len, const int* seg_set, const int* row_seg, int segments,
+                             int c, float eps, int mode, void* stream) {
+  CVX_CHECK_ARG(dy && x && stats && dx && seg_start && seg_len && seg_set && row_seg && segments > 0 && c > 0,
+                "segtab_layernorm_bwd: bad arguments");
+  SetPtrs P;
+  if (int rc = fill_sets(&P, ps, "segtab_layernorm_bwd")) return rc;
+  cudaStream_t st = as_stream(stream);
+  segtab_layernorm_bwd_kernel<<<segments, 256, 0, st>>>(dy, x, P, stats, dx, seg_start, seg_len, seg_set, c, eps, mode);
+  CVX_LAUNCH_OK();
+  segtab_ln_param_grad_kernel<<<dim3((c + 31) / 32, P.sets), 256, 0, st>>>(dy, x, stats, row_seg, P, c);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_segtab_gate_pool_fwd(const float* x, const float* gate, float* pooled, float* att, const int* seg_start,
+                             const int* seg_len, int segments, int max_len, int c, void* stream) {
+  CVX_CHECK_ARG(x && gate && pooled && att && seg_start && seg_len && segments > 0 && max_len > 0 && max_len <= 64 && c > 0,
+                "segtab_gate_pool_fwd: bad arguments (segments of at most 64 rows)");
+  segtab_gate_pool_fwd_kernel<<<segments, 256, 0, as_stream(stream)>>>(x, gate, pooled, att, seg_start, seg_len, c);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_segtab_gate_pool_bwd(const float* dpooled, const float* x, const float* att, float* dx, float* dgate,
+                             const int* seg_start, const int* seg_len, int segments, int max_len, int c, void* stream) {
+  CVX_CHECK_ARG(dpooled && x && att && dx && dgate && seg_start && seg_len && segments > 0 && max_len > 0 && max_len <= 64 && c > 0,
+                "segtab_gate_pool_bwd: bad arguments");
+  segtab_gate_pool_bwd_kernel<<<segments, 256, 0, as_stream(stream)>>>(dpooled, x, att, dx, dgate, seg_start, seg_len, c);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_segtab_bcast_add(const float* x, const float* t, float* y, const int* row_seg, const int* tok_of_seg, int rows, int c,
+                         void* stream) {
+  CVX_CHECK_ARG(x && t && y && row_seg && tok_of_seg && rows > 0 && c > 0, "segtab_bcast_add: bad arguments");
+  segtab_bcast_add_kernel<<<rgrid((int64_t)rows * c), 256, 0, as_stream(stream)>>>(x, t, y, row_seg, tok_of_seg, rows, c);
+  CVX_LAUNCH_OK();
+  return CVX_OK;
+}
+
+int cvx_segtab_bcast_add_bwd(const float* dy, float* dt, const int* seg_of_tok, const int* seg_start, const int* seg_len,
+                             int tokens, int c, void* stream) {
+  CVX_CHECK_ARG(dy && dt && seg_of_tok && seg_start && seg_len && tokens > 0 && c > 0, "segtab_bcast_add_bwd: bad arguments");
+  segtab_bcast_add_bwd_kernel<<<tokens, 128, 0, as_stream(stream)>>>(dy, dt, seg_of_tok, seg_start, seg_len, c);
+  CVX_LAUNCH_OK();
   return CVX_OK;
 }
 

@@ -339,20 +339,27 @@ class fusion_model_mae_2(nn.Module):
         y = R.linear(R.gelu(R.linear(y, mix.mix_mip_2[0])), mix.mix_mip_2[2])
         return ops.Add.apply(x, y)
 
-    @staticmethod
-    def _per_modality(xs: Dict[str, torch.Tensor], lins: Dict[str, nn.Linear]) -> Dict[str, torch.Tensor]:
-        """The same layer of every modality branch (own weights, own rows) as ONE grouped GEMM launch."""
-        ms = list(xs)
-        return R.linear_group([(xs[m], 0, xs[m].shape[0], lins[m], m, 0) for m in ms])
+    def _segtab(self, G: int, nodes: Sequence[int], order: str, device) -> R.SegTable:
+        key = ("segtab", G, tuple(nodes), order, str(device))
+        t = self._const.get(key)
+        if t is None:
+            t = self._const[key] = R.SegTable(G, list(nodes), order, device)
+        return t
 
-    def _pool_all(self, xs: Dict[str, torch.Tensor], suffix: str, G: int, seg: Dict[str, int]):
-        """Gated attention pooling of every modality (my_GlobalAttention, my_mae_model.py:35-63): the two gate layers are
-        one grouped launch each; the per-graph softmax + weighted sum is one launch per modality."""
-        pools = {m: getattr(self, "mpool_" + m + suffix) for m in xs}
-        h = self._per_modality(xs, {m: pools[m].gate_nn[0] for m in xs})
-        h = {m: ops.relu(h[m]) for m in xs}
-        gate = self._per_modality(h, {m: pools[m].gate_nn[2] for m in xs})
-        return {m: R.GatePool.apply(xs[m], gate[m], G, seg[m]) for m in xs}
+    @staticmethod
+    def _per_set(x, tab: R.SegTable, lins: Sequence[nn.Linear]):
+        """The same layer of every modality branch on the stack ``x`` (own weights, own row block): ONE grouped GEMM."""
+        return R.linear_group([(x, tab.row_start[i], tab.row_start[i + 1] - tab.row_start[i], lin, 0, tab.row_start[i])
+                               for i, lin in enumerate(lins)])[0]
+
+    def _pool_stack(self, x, present: Sequence[str], suffix: str, tab: R.SegTable):
+        """Gated attention pooling (my_GlobalAttention, my_mae_model.py:35-63) of every modality at once: each gate layer is
+        one grouped GEMM over the modalities' row blocks, the per-graph softmax + weighted sum one launch over all
+        segments; pooled rows come out in the table's segment order."""
+        pools = [getattr(self, "mpool_" + m + suffix) for m in present]
+        h = ops.relu(self._per_set(x, tab, [pl.gate_nn[0] for pl in pools]))
+        gate = self._per_set(h, tab, [pl.gate_nn[2] for pl in pools])
+        return R.SegTabGatePool.apply(x, gate, tab)
 
     # ------------------------------------------------------------------ batched forward
     def forward_batch(self, feats: Dict[str, torch.Tensor], edges: Dict[str, torch.Tensor],
@@ -372,27 +379,34 @@ class fusion_model_mae_2(nn.Module):
         G = int(feats[present[0]].shape[0])
         dev = feats[present[0]].device
         C = self.hidden
-        nodes, seg, pooled, att_2 = {}, {}, [], []
-        # SAGEConv of every modality (lin_l on the neighbourhood mean, lin_r on the node itself): 2 x P GEMMs, one launch
-        entries, xin = [], {}
-        for m in present:
-            x = feats[m].contiguous().float()
-            seg[m] = int(x.shape[1])
-            x = x.reshape(G * seg[m], x.shape[2])
+        P = len(present)
+        seg = {m: int(feats[m].shape[1]) for m in present}
+        nodes_n = [seg[m] for m in present]
+        # every modality's node rows live in ONE stack [sum_m G * nodes_m, C] (modality-major); tab_gm numbers the patient
+        # graphs patient-major (pooled rows = the auto-encoder's token order), tab_mg modality-major (pooled rows = the row
+        # blocks of the per-modality heads), tab_row is the stack of the P * G pooled rows themselves (segments of one row)
+        tab_gm = self._segtab(G, nodes_n, "gm", dev)
+        tab_mg = self._segtab(G, nodes_n, "mg", dev)
+        tab_row = self._segtab(G, [1] * P, "mg", dev)
+        # SAGEConv of every modality (lin_l on the neighbourhood mean, lin_r on the node itself): 2 x P GEMMs, one launch,
+        # written straight into the stack
+        entries = []
+        for i, m in enumerate(present):
+            x = feats[m].contiguous().float().reshape(G * seg[m], -1)
             conv = getattr(self, m + "_gnn_2")
             agg = R.GraphMean.apply(x, self._topology(edges[m], seg[m], dev), G)
-            entries.append((agg, 0, agg.shape[0], conv.lin_l, ("l", m), 0))
-            entries.append((x, 0, x.shape[0], conv.lin_r, ("r", m), 0))
+            r0 = tab_gm.row_start[i]
+            entries.append((agg, 0, agg.shape[0], conv.lin_l, "l", r0))
+            entries.append((x, 0, x.shape[0], conv.lin_r, "r", r0))
         sage = R.linear_group(entries)
-        for m in present:
-            x = ops.Add.apply(sage[("l", m)], sage[("r", m)])
-            x = R.graph_layernorm(ops.relu(x), getattr(self, m + "_relu_2")[1], G, seg[m])
-            nodes[m] = self._drop(x, getattr(self, m + "_relu_2")[2].p)
-        pools = self._pool_all(nodes, "", G, seg)
-        for m in present:
-            px, att = pools[m]
-            pooled.append(px.reshape(G, 1, 1, C)); att_2.append(att.reshape(G, seg[m]))
-        pool_x = (ops.cat_channels(pooled) if len(pooled) > 1 else pooled[0]).reshape(G * len(present), C)
+        blocks = [getattr(self, m + "_relu_2") for m in present]
+        if len({blk[2].p for blk in blocks}) != 1:
+            raise ValueError("the modality branches must share one dropout rate")
+        x = ops.relu(ops.Add.apply(sage["l"], sage["r"]))
+        x = R.segtab_layernorm(x, tab_gm, [blk[1] for blk in blocks], 0)
+        nodes = self._drop(x, blocks[0][2].p)
+        pool_x, att = self._pool_stack(nodes, present, "", tab_gm)             # [G * P, C], patient-major
+        att_2 = [att[tab_gm.row_start[i]:tab_gm.row_start[i + 1]].reshape(G, seg[m]) for i, m in enumerate(present)]
         out = {"mae_labels": pool_x.reshape(G, len(present), C), "att_2": att_2}
         if Tt > 1:
             plan = None
@@ -426,37 +440,45 @@ class fusion_model_mae_2(nn.Module):
             if mix:
                 mae_x = self._mixer(mae_x, G, Tt)
                 out["after_mix"] = mae_x.reshape(G, Tt, C)
-            for m in present:
-                if m in train_use_type:
-                    i = train_use_type.index(m)
-                    row = R.RowsGather.apply(mae_x, self._idx([g * Tt + i for g in range(G)], dev), None)
-                    nodes[m] = ops.Add.apply(nodes[m], ops.broadcast_hw(row.reshape(G, 1, 1, C), seg[m], 1)
-                                             .reshape(G * seg[m], C))
-        att_3, heads, feas, logits = [], [], [], {}
-        pools = self._pool_all(nodes, "_2", G, seg)
-        f = {}
-        for m in present:
-            px, att = pools[m]
-            att_3.append(att.reshape(G, seg[m]))
-            f[m] = R.L2Norm.apply(px)                                                  # F.normalize(dim=1) is row-wise
-            feas.append(f[m].reshape(G, 1, 1, C))
-        # the per-modality heads 512 -> 128 -> 32 -> 8 (-> 4): every layer is one grouped launch over the modalities
-        v = self._per_modality(f, {m: getattr(self, "lin1_" + m) for m in present})
-        v = {m: self._drop(R.graph_layernorm(ops.relu(v[m]), getattr(self, "norm1_" + m), G, 1), self.dropout.p) for m in present}
-        v = self._per_modality(v, {m: getattr(self, "lin2_" + m) for m in present})
-        v = {m: self._drop(R.graph_layernorm(ops.relu(v[m]), getattr(self, "norm2_" + m), G, 1), self.dropout.p) for m in present}
-        v = self._per_modality(v, {m: getattr(self, "lin3_" + m) for m in present})
-        logits = self._per_modality(v, {m: getattr(self, "classifier_" + m) for m in present})
-        for m in present:
-            heads.append(v[m].reshape(G, 1, 1, v[m].shape[1]))
-        K = heads[0].shape[3]
-        P = len(present)
-        multi_x = (ops.cat_channels(heads) if P > 1 else heads[0]).reshape(G, P, 1, K)
-        one_x = ops.global_avg_pool(multi_x).reshape(G, K) if P > 1 else multi_x.reshape(G, K)
+            # node features += the reconstructed token of their modality (my_mae_model.py:636-649), all modalities at once
+            tkey = ("tok", G, tuple(present), tuple(train_use_type), str(dev))
+            tabs = self._const.get(tkey)
+            if tabs is None:
+                tok_of_seg = [-1] * (G * P)
+                seg_of_tok = [-1] * (G * Tt)
+                for i, m in enumerate(present):
+                    if m in train_use_type:
+                        j = train_use_type.index(m)
+                        for g in range(G):
+                            tok_of_seg[tab_mg.seg_id(i, g)] = g * Tt + j
+                            seg_of_tok[g * Tt + j] = tab_mg.seg_id(i, g)
+                tabs = self._const[tkey] = (torch.tensor(tok_of_seg, dtype=torch.int32, device=dev),
+                                            torch.tensor(seg_of_tok, dtype=torch.int32, device=dev))
+            nodes = R.SegTabBcastAdd.apply(nodes, mae_x, tab_mg, tabs[0], tabs[1])
+        pooled2, att = self._pool_stack(nodes, present, "_2", tab_mg)            # [P * G, C], modality-major
+        att_3 = [att[tab_mg.row_start[i]:tab_mg.row_start[i + 1]].reshape(G, seg[m]) for i, m in enumerate(present)]
+        f = R.L2Norm.apply(pooled2)                                                # F.normalize(dim=1) is row-wise
+        # the per-modality heads 512 -> 128 -> 32 -> 8 (-> 4): every layer is one grouped launch over the modalities' row
+        # blocks, the LayerNorms (PyG graph mode on a single row) one launch with each block's own affine
+        get = lambda name: [getattr(self, name + m) for m in present]           # noqa: E731
+        v = ops.relu(self._per_set(f, tab_row, get("lin1_")))
+        v = self._drop(R.segtab_layernorm(v, tab_row, get("norm1_"), 0), self.dropout.p)
+        v = ops.relu(self._per_set(v, tab_row, get("lin2_")))
+        v = self._drop(R.segtab_layernorm(v, tab_row, get("norm2_"), 0), self.dropout.p)
+        v = self._per_set(v, tab_row, get("lin3_"))                              # [P * G, 8]
+        logits_stack = self._per_set(v, tab_row, get("classifier_"))            # [P * G, 4]
+        K = v.shape[1]
+        if P > 1:       # modality-major -> patient-major for the [G, P, .] outputs and the mean over the modalities
+            to_gm = self._idx([i * G + g for g in range(G) for i in range(P)], dev)
+            multi_x = R.RowsGather.apply(v, to_gm, None).reshape(G, P, 1, K)
+            one_x = ops.global_avg_pool(multi_x).reshape(G, K)
+            fea = R.RowsGather.apply(f, to_gm, None).reshape(G, P, C)
+        else:
+            multi_x, one_x, fea = v.reshape(G, 1, 1, K), v.reshape(G, K), f.reshape(G, 1, C)
         out.update(one_x=one_x, multi_x=multi_x.reshape(G, P, K), logits_all=R.linear(one_x, self.classifier),
-                   att_3=att_3, fea=(ops.cat_channels(feas) if P > 1 else feas[0]).reshape(G, P, C), present=present)
-        for m in present:
-            out["logits_" + m] = logits[m]
+                   att_3=att_3, fea=fea, present=present, logits_stack=logits_stack)
+        for i, m in enumerate(present):
+            out["logits_" + m] = logits_stack[i * G:(i + 1) * G]
         return out
 
     # ------------------------------------------------------------------ reference signature (one patient)
@@ -536,11 +558,11 @@ def fusion_objective(out: Dict[str, torch.Tensor], labels: torch.Tensor, masks=N
         plan = MaskPlan(np.asarray(masks, dtype=bool).reshape(G, T), labels.device)
     n_masked = T - plan.n_vis
     sel = plan.sel
-    logits = [out["logits_all"]] + [out["logits_" + m] for m in present]
     weights = [1.0] + [MODALITY_LOSS_WEIGHT[m] for m in present]
     inv_count = 1.0 / max(n_masked * C, 1)
     return R.FusionObjective.apply(labels, sel, weights, mse_factor / G / 5.0, inv_count,
-                                   out["mae_out"].reshape(G * T, C), out["mae_labels"].reshape(G * T, C), *logits)
+                                   out["mae_out"].reshape(G * T, C), out["mae_labels"].reshape(G * T, C),
+                                   out["logits_all"], out["logits_stack"])
 
 
 def generate_mask(num=3):

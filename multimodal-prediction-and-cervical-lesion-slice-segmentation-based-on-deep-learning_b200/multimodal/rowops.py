@@ -148,6 +148,102 @@ def layernorm(x, ln: torch.nn.LayerNorm):
     return SegLayerNorm.apply(x, ln.weight, ln.bias, x.shape[0], 1, ln.eps, 1)
 
 
+class SegTable:
+    """Index tables of a stack of modality branches (csrc/rowops.cu "segment-table operators"): the node rows of the
+    modalities are stacked modality-major ``[sum_m G * nodes_m, C]``; segment = one patient graph of one modality.
+    ``order`` fixes the numbering of the segments and with it the row order of pooled outputs: ``"gm"`` patient-major
+    (segment g * P + m: the token order of the masked auto-encoder), ``"mg"`` modality-major (segment m * G + g: the
+    row blocks of the per-modality head GEMMs).  Built once per (G, node counts, order, device) and cached by the model."""
+
+    def __init__(self, G: int, nodes, order: str, device):
+        P = len(nodes)
+        self.G, self.P, self.nodes, self.order = G, list(nodes), order, device
+        base, off = [], 0
+        for n in nodes:
+            base.append(off)
+            off += G * n
+        self.rows = off
+        self.row_start = base + [off]                       # host: rows of parameter set (modality) i
+        self.segments = G * P
+        self.max_len = max(nodes)
+        start, length, sset = [0] * self.segments, [0] * self.segments, [0] * self.segments
+        row_seg = [0] * off
+        for m in range(P):
+            for g in range(G):
+                s = g * P + m if order == "gm" else m * G + g
+                start[s], length[s], sset[s] = base[m] + g * nodes[m], nodes[m], m
+                for i in range(nodes[m]):
+                    row_seg[start[s] + i] = s
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32, device=device)   # noqa: E731
+        self.seg_start, self.seg_len, self.seg_set, self.row_seg = i32(start), i32(length), i32(sset), i32(row_seg)
+        self._host_start, self._host_set = start, sset
+
+    def seg_id(self, m: int, g: int) -> int:
+        return g * self.P + m if self.order == "gm" else m * self.G + g
+
+    def rows_of(self, m: int):
+        return self.row_start[m], self.row_start[m + 1]
+
+
+class SegTabLayerNorm(Function):
+    """PyG graph-mode LayerNorm (mode 0) / nn.LayerNorm (mode 1, segments of one row) of every modality branch in one
+    launch, each segment with its own modality's affine parameters.  ``params`` = the weights, then the biases."""
+
+    @staticmethod
+    def forward(ctx, x, tab: SegTable, eps, mode, *params):
+        n = len(params) // 2
+        ws, bs = [p.detach().contiguous() for p in params[:n]], [p.detach().contiguous() for p in params[n:]]
+        x = x.contiguous()
+        y, stats = get_backend().segtab_layernorm_fwd(x, ws, bs, tab, eps, mode)
+        ctx.save_for_backward(x, stats, *params[:n])
+        ctx.tab, ctx.cfg, ctx.n = tab, (eps, mode), n
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, *ws = ctx.saved_tensors
+        dx, dws, dbs = get_backend().segtab_layernorm_bwd(dy.contiguous(), x, [w.detach().contiguous() for w in ws], stats,
+                                                          ctx.tab, *ctx.cfg)
+        return (dx, None, None, None, *dws, *dbs)
+
+
+def segtab_layernorm(x, tab: SegTable, lns, mode: int = 0):
+    return SegTabLayerNorm.apply(x, tab, lns[0].eps, mode, *[ln.weight for ln in lns], *[ln.bias for ln in lns])
+
+
+class SegTabGatePool(Function):
+    """my_GlobalAttention of every modality branch in one launch: pooled row s = softmax-weighted sum of segment s."""
+
+    @staticmethod
+    def forward(ctx, x, gate, tab: SegTable):
+        x = x.contiguous()
+        pooled, att = get_backend().segtab_gate_pool_fwd(x, gate.contiguous().reshape(-1), tab)
+        ctx.save_for_backward(x, att)
+        ctx.tab = tab
+        ctx.mark_non_differentiable(att)
+        return pooled, att
+
+    @staticmethod
+    def backward(ctx, dpooled, _datt):
+        x, att = ctx.saved_tensors
+        dx, dgate = get_backend().segtab_gate_pool_bwd(dpooled.contiguous(), x, att, ctx.tab)
+        return dx, dgate.reshape(-1, 1), None
+
+
+class SegTabBcastAdd(Function):
+    """x[rows of segment s] += t[tok_of_seg[s]] for every modality at once (my_mae_model.py:636-649)."""
+
+    @staticmethod
+    def forward(ctx, x, t, tab: SegTable, tok_of_seg, seg_of_tok):
+        ctx.tab, ctx.seg_of_tok, ctx.tokens = tab, seg_of_tok, t.shape[0]
+        return get_backend().segtab_bcast_add(x.contiguous(), t.contiguous(), tab, tok_of_seg)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        return dy, get_backend().segtab_bcast_add_bwd(dy, ctx.tab, ctx.seg_of_tok, ctx.tokens), None, None, None
+
+
 class GELU(Function):
     @staticmethod
     def forward(ctx, x):
@@ -267,18 +363,25 @@ class RowsGather(Function):
 
 class FusionObjective(Function):
     """my_train(full).py:309-347 for one mini-batch: CE(all) + sum_m w_m CE(m) + MSE(mae_out, mae_labels on the
-    masked tokens) * factor / B / 5.  logits: list of [B,4]; mae_out / mae_labels [B*T, C]; sel uint8 [B*T]."""
+    masked tokens) * factor / B / 5.  logits_all [B,4]; logits_stack [P*B,4] = the P modality heads' logits stacked
+    modality-major (rows m*B .. (m+1)*B belong to modality m, weight weights[1+m]); mae_out / mae_labels [B*T, C];
+    sel uint8 [B*T]."""
 
     @staticmethod
-    def forward(ctx, labels, sel, weights, mse_weight, inv_count, mae_out, mae_labels, *logits):
+    def forward(ctx, labels, sel, weights, mse_weight, inv_count, mae_out, mae_labels, logits_all, logits_stack):
         B = get_backend()
         loss = torch.zeros(1, dtype=torch.float32, device=mae_out.device)
-        grads = [B.softmax_ce(l.contiguous(), labels, loss, w, True) for l, w in zip(logits, weights)]
+        logits_all, logits_stack = logits_all.contiguous(), logits_stack.contiguous()
+        G = logits_all.shape[0]
+        d_all = B.softmax_ce(logits_all, labels, loss, weights[0], True)
+        d_stack = torch.empty_like(logits_stack)
+        for i, w in enumerate(weights[1:]):
+            B.softmax_ce(logits_stack[i * G:(i + 1) * G], labels, loss, w, True, out=d_stack[i * G:(i + 1) * G])
         da, db = B.masked_mse(mae_out.contiguous(), mae_labels.contiguous(), sel, loss, mse_weight, inv_count, True)
-        ctx.save_for_backward(da, db, *grads)
+        ctx.save_for_backward(da, db, d_all, d_stack)
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
-        da, db, *grads = ctx.saved_tensors
-        return (None, None, None, None, None, da * g, db * g) + tuple(d * g for d in grads)
+        da, db, d_all, d_stack = ctx.saved_tensors
+        return (None, None, None, None, None, da * g, db * g, d_all * g, d_stack * g)

@@ -126,24 +126,28 @@ class SepChainFn(Function):
             x, sc, sh = s.p, s.scale2, s.shift2
         res = inp if res_is_inp else (None if residual is None else residual.contiguous())
         out = B.affine_act(x, sc, sh, res, act)
-        ctx.seps, ctx.act, ctx.inp, ctx.params = seps, act, inp, params
+        # inputs and the OUTPUT go through save_for_backward (an output kept as a plain attribute would close the cycle
+        # out -> grad_fn -> ctx -> out, which only the cyclic GC frees, and would escape autograd's in-place checks);
+        # the intermediates of the chain are not graph tensors and simply live on ctx until the graph is freed
+        ctx.save_for_backward(inp, out if act != ACT_NONE else None, *params)
+        ctx.seps, ctx.act = seps, act
         ctx.has_res, ctx.res_is_inp = res is not None, res_is_inp
-        ctx.out = out if act != ACT_NONE else None
         return out
 
     @staticmethod
     def backward(ctx, dout):
         B = get_backend()
-        seps, act, inp, params = ctx.seps, ctx.act, ctx.inp, ctx.params
+        seps, act = ctx.seps, ctx.act
+        inp, out, *params = ctx.saved_tensors
         K = len(seps)
         dout = dout.contiguous()
         rows = inp.numel() // inp.shape[-1]
         grads: List[Optional[torch.Tensor]] = [None] * (K * PARAMS_PER_SEP)
         s = seps[K - 1]
         lbase = (K - 1) * PARAMS_PER_SEP
-        sums = B.bn_bwd_sums(dout, ctx.out, s.p, act)
+        sums = B.bn_bwd_sums(dout, out, s.p, act)
         a, b, cc, dgam, dbet = B.bn_bwd_coef(sums, rows, s.mean2, s.invstd2, params[lbase + 4].detach())
-        dp, gres = B.bn_bwd_affine(dout, ctx.out, s.p, a, b, cc, act, ctx.has_res and act != ACT_NONE)
+        dp, gres = B.bn_bwd_affine(dout, out, s.p, a, b, cc, act, ctx.has_res and act != ACT_NONE)
         if ctx.has_res and gres is None:
             gres = dout                       # no activation behind the add: the skip branch receives dout itself
         grads[lbase + 4], grads[lbase + 5] = dgam, dbet
@@ -166,7 +170,6 @@ class SepChainFn(Function):
                 grads[pbase + 4], grads[pbase + 5] = dgam, dbet
             else:
                 dinp = gx
-        ctx.seps = None
         dres = gres if (ctx.has_res and not ctx.res_is_inp) else None
         return (dinp, dres, None, None, None, *grads)
 

@@ -519,13 +519,17 @@ class EmuBackend:
         dfill = dy[~ok].sum(0) if want_fill else None
         return dx, dfill
 
-    def softmax_ce(self, logits, labels, loss, weight, want_grad):
+    def softmax_ce(self, logits, labels, loss, weight, want_grad, out=None):
         b = logits.shape[0]
         lse = torch.logsumexp(logits, 1)
         loss += weight * (lse - logits.gather(1, labels[:, None])[:, 0]).sum() / b
         if not want_grad:
             return None
-        return weight * (torch.softmax(logits, 1) - F.one_hot(labels, logits.shape[1]).float()) / b
+        d = weight * (torch.softmax(logits, 1) - F.one_hot(labels, logits.shape[1]).float()) / b
+        if out is not None:
+            out.copy_(d)
+            return out
+        return d
 
     def masked_mse(self, a, b, sel, loss, weight, inv_count, want_grad):
         d = (a - b) * sel.bool().unsqueeze(1)
@@ -548,6 +552,63 @@ class EmuBackend:
     def adam_step_dev(self, p, g, m, v, hyper, step_dev):
         lr, b1, b2, eps, wd, gs = [float(t) for t in hyper]
         self.adam_step(p, g, m, v, lr, b1, b2, eps, wd, int(step_dev), gs)
+
+    # ---- segment-table operators: plain loops over the segments with the fixed-size primitives above
+    @staticmethod
+    def _segs(tab):
+        return list(zip(tab.seg_start.tolist(), tab.seg_len.tolist(), tab.seg_set.tolist()))
+
+    def segtab_layernorm_fwd(self, x, ws, bs, tab, eps, mode):
+        y = torch.empty_like(x)
+        stats = torch.empty((tab.segments, 3), dtype=torch.float32)
+        for s, (r0, n, k) in enumerate(self._segs(tab)):
+            yy, st = self._ln(x[r0:r0 + n], ws[k].detach(), bs[k].detach(), 1, n, eps, mode)
+            y[r0:r0 + n] = yy
+            stats[s] = st[0]
+        return y, stats
+
+    def segtab_layernorm_bwd(self, dy, x, ws, stats, tab, eps, mode):
+        dx = torch.empty_like(x)
+        c = x.shape[-1]
+        dws = [torch.zeros(c) for _ in ws]
+        dbs = [torch.zeros(c) for _ in ws]
+        for (r0, n, k) in self._segs(tab):
+            a, b, d = self.seg_layernorm_bwd(dy[r0:r0 + n], x[r0:r0 + n], ws[k], None, 1, n, eps, mode)
+            dx[r0:r0 + n] = a
+            dws[k] += b
+            dbs[k] += d
+        return dx, dws, dbs
+
+    def segtab_gate_pool_fwd(self, x, gate, tab):
+        pooled = torch.empty((tab.segments, x.shape[-1]))
+        att = torch.empty((x.shape[0],))
+        for s, (r0, n, _) in enumerate(self._segs(tab)):
+            p, a = self._pool(x[r0:r0 + n], gate[r0:r0 + n], 1, n)
+            pooled[s] = p[0]
+            att[r0:r0 + n] = a
+        return pooled, att
+
+    def segtab_gate_pool_bwd(self, dpooled, x, att, tab):
+        dx = torch.empty_like(x)
+        dgate = torch.empty((x.shape[0],))
+        for s, (r0, n, _) in enumerate(self._segs(tab)):
+            a, b = self.gate_pool_bwd(dpooled[s:s + 1], x[r0:r0 + n], att[r0:r0 + n], 1, n)
+            dx[r0:r0 + n] = a
+            dgate[r0:r0 + n] = b
+        return dx, dgate
+
+    def segtab_bcast_add(self, x, t, tab, tok_of_seg):
+        tok = tok_of_seg.long()[tab.row_seg.long()]
+        add = torch.where((tok >= 0)[:, None], t[tok.clamp_min(0)], torch.zeros(1))
+        return x + add
+
+    def segtab_bcast_add_bwd(self, dy, tab, seg_of_tok, tokens):
+        dt = torch.zeros((tokens, dy.shape[1]))
+        starts, lens = tab.seg_start.tolist(), tab.seg_len.tolist()
+        for tok, s in enumerate(seg_of_tok.tolist()):
+            if s >= 0:
+                dt[tok] = dy[starts[s]:starts[s] + lens[s]].sum(0)
+        return dt
 
     def gemm_grouped(self, problems):
         for q in problems:
