@@ -552,7 +552,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     use_graph = not args.no_graph
-    comm_in_graph = os.environ.get("CERVIX_COMM_IN_GRAPH", "1") != "0"
+    comm_in_graph = os.environ.get("CERVIX_COMM_IN_GRAPH", "0") == "1"
     if use_graph:
         trainer.capture(imgs, pngs, None, comm_in_graph=comm_in_graph)
         step_fn = lambda a, b, c=None: trainer.step_graphed(a, b)   # noqa: E731
@@ -681,7 +681,7 @@ def run_ours(args):
                    "cuda_graph": bool(use_graph), "allreduce": (None if world == 1 else (
                        "bucketed NCCL all-reduce forked from the gradient hooks, captured inside the step's CUDA graph"
                        if (use_graph and comm_in_graph) else "bucketed NCCL all-reduce overlapped with backward" if not use_graph
-                       else "one NCCL all-reduce after the graph replay")),
+                       else "bucketed NCCL all-reduce after the graph replay, optimizer of bucket k under the all-reduce of bucket k+1")),
                    "l2": "per-step working set (tens of GB of activations) far exceeds the 126 MB L2"},
         "roofline": roof,
         "roofline_hbm": roof_hbm,

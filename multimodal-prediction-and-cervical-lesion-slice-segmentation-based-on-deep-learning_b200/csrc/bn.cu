@@ -86,6 +86,8 @@ struct BnBwdF {
 __global__ void bn_finalize_kernel(const double* __restrict__ acc, int64_t rows, float* running_mean,
                                    float* running_var, float* save_mean, float* save_invstd, int C, int training,
                                    float momentum, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (training) {
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, int64_t rows, int C,
                                                        int act, int64_t stride_vecs) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VEC = Elem<T>::kVec;
   const int cvn = C / VEC;
   const int64_t total = rows * cvn;
@@ -145,6 +149,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
     const double* __restrict__ acc, T* __restrict__ dx, T* __restrict__ dres, int64_t rows, int C, int act,
     int training, int64_t stride_vecs) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VEC = Elem<T>::kVec;
   const int cvn = C / VEC;
   const int64_t total = rows * cvn;
@@ -186,6 +192,8 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(
 
 
 __global__ void bn_param_grad_kernel(const double* __restrict__ acc, float* dgamma, float* dbeta, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (dbeta) dbeta[c] = (float)acc[c];
@@ -193,6 +201,8 @@ __global__ void bn_param_grad_kernel(const double* __restrict__ acc, float* dgam
 }
 
 __global__ void copy_d2f_kernel(const double* __restrict__ a, float* out, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)a[i];
 }
@@ -249,12 +259,12 @@ int cvx_bn_forward(const void* x, const void* residual, void* y, const float* ga
     CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, StatsF<T>>(StatsF<T>{(const T*)x, c}, rows, c, ws, st)));
     if (rc) return rc;
   }
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(ws, rows, running_mean, running_var, save_mean, save_invstd,
+  launch_pdl(bn_finalize_kernel, dim3((c + 127) / 128), dim3(128), 0, st, ws, rows, running_mean, running_var, save_mean, save_invstd,
                                                       c, training, momentum, eps);
   CVX_LAUNCH_OK();
   int blocks; int64_t stride;
   stream_grid(rows * (c / vec), c / vec, &blocks, &stride);
-  CVX_DISPATCH_DTYPE(dtype, T, (bn_apply_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, (const T*)residual, (T*)y, gamma,
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(bn_apply_kernel<T>, dim3(blocks), dim3(256), 0, st, (const T*)x, (const T*)residual, (T*)y, gamma,
                                                                           beta, save_mean, save_invstd, rows, c, act,
                                                                           stride)));
   CVX_LAUNCH_OK();
@@ -280,12 +290,12 @@ int cvx_bn_backward(const void* dy, const void* x, const void* y, const float* g
   if (rc) return rc;
   int blocks; int64_t stride;
   stream_grid(rows * (c / vec), c / vec, &blocks, &stride);
-  CVX_DISPATCH_DTYPE(dtype, T, (bn_bwd_apply_kernel<T><<<blocks, 256, 0, st>>>(
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(bn_bwd_apply_kernel<T>, dim3(blocks), dim3(256), 0, st, 
                                    (const T*)dy, (const T*)x, (const T*)y, gamma, beta, save_mean, save_invstd, ws, (T*)dx,
                                    (T*)dres, rows, c, act, training, stride)));
   CVX_LAUNCH_OK();
   if (dgamma || dbeta) {
-    bn_param_grad_kernel<<<(c + 127) / 128, 128, 0, st>>>(ws, dgamma, dbeta, c);
+    launch_pdl(bn_param_grad_kernel, dim3((c + 127) / 128), dim3(128), 0, st, ws, dgamma, dbeta, c);
     CVX_LAUNCH_OK();
   }
   return CVX_OK;
@@ -306,7 +316,7 @@ int cvx_bias_grad(const void* dy, float* dbias, double* ws, int64_t rows, int c,
     CVX_DISPATCH_DTYPE(dtype, T, rc = (colreduce_launch<T, SumF<T>>(SumF<T>{(const T*)dy, c}, rows, c, ws, st)));
     if (rc) return rc;
   }
-  copy_d2f_kernel<<<(c + 127) / 128, 128, 0, st>>>(ws, dbias, c);
+  launch_pdl(copy_d2f_kernel, dim3((c + 127) / 128), dim3(128), 0, st, ws, dbias, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

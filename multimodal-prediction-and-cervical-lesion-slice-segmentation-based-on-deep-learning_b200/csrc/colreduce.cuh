@@ -29,9 +29,11 @@ __global__ void __launch_bounds__(NT, MINB) colreduce_kernel(F f, int64_t rows, 
   constexpr int VEC = Elem<T>::kVec;
   constexpr int NACC = F::NACC;
   extern __shared__ float sm_acc[];  // [NACC][colchunk_vecs*VEC]
+  pdl_trigger();
   const int chunk_elems = colchunk_vecs * VEC;
   for (int i = threadIdx.x; i < NACC * chunk_elems; i += NT) sm_acc[i] = 0.f;
   __syncthreads();
+  pdl_wait();
 
   const int lanes = NT / colchunk_vecs;  // row lanes per block
   const int cv = threadIdx.x % colchunk_vecs;
@@ -130,7 +132,7 @@ static int colreduce_launch(const F& f, int64_t rows, int C, double* out, cudaSt
   const int64_t gx = ceil_div64(rows, rpb);
   dim3 grid((unsigned)gx, ychunks);
   const size_t smem = sizeof(float) * F::NACC * colchunk * VEC;
-  colreduce_kernel<T, F, NT, MINB><<<grid, NT, smem, stream>>>(f, rows, C, colchunk, rpb, out);
+  launch_pdl(colreduce_kernel<T, F, NT, MINB>, grid, dim3(NT), smem, stream, f, rows, C, colchunk, rpb, out);
   ++g_kernel_launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

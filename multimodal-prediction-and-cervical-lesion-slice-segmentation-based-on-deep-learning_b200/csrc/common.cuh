@@ -49,6 +49,35 @@ extern int g_ws_prezeroed;                    // cvx_set_ws_prezeroed: fp64 work
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// A training step is ~1 500 kernels of 5 - 500 us; between two dependent kernels the GPU normally drains completely, flushes,
+// and only then starts launching the next grid.  Kernels launched through launch_pdl() carry the programmatic-stream-
+// serialization attribute: their CTAs may become resident while the previous kernel is still draining (as its CTAs exit),
+// run their prologue (barrier / TMEM set-up, descriptor prefetch) and block in pdl_wait() until the previous grid has
+// completed and its writes are visible.  Every such kernel calls pdl_trigger() first thing, so the kernel AFTER it may be
+// scheduled early in turn.  Nothing may read or write global memory before pdl_wait().  CERVIX_PDL=0 turns the attribute
+// off (the device-side instructions are then no-ops).
+extern int g_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  static_assert(sizeof...(KArgs) == sizeof...(Args), "launch_pdl: argument count mismatch");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 __host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -697,6 +697,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
                         const __grid_constant__ CUtensorMap tmap_y, const __grid_constant__ CUtensorMap tmap_s,
                         const TcEpi ep, TcFwdParams p, int n_tiles, int m_tiles, int total_pair_tiles) {
   constexpr int kSt = TcFwdSmem<MODE>::kStages;
+  pdl_trigger();   // the next kernel's CTAs may take an SM as soon as this kernel's CTA on it has exited
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_buf = smem + kSt * k2StageBytes;          // 2 x 16 KB output staging, 1024-aligned
@@ -744,6 +745,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, TMEM and descriptors are set up: now wait for the producer of this kernel's inputs
 
   // The producer and the issuer warps run their loops WARP-UNIFORMLY (all 32 lanes compute the same counters and
   // addresses and wait on the same barriers); only the TMA / tcgen05 instructions themselves sit under elect_one().
@@ -1161,6 +1163,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const __grid_constant__ CUtensorMap tmap_dy,
                                                                           const __grid_constant__ CUtensorMap tmap_x,
                                                                           float* __restrict__ dw, TcWgradPParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWPStages * kWPStageBytes);
@@ -1194,6 +1197,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_persistent_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // item -> (co tile fastest, ci tile, tap, split slowest)
   auto decode = [&](int item, int& cot, int& cit, int& tap, int& t_begin, int& t_end) {
@@ -1326,6 +1330,7 @@ constexpr int kW2StageBytes = kW2ABytes + kW2BBytes;  // 32 KB
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 conv_tc_wgrad_2cta_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __grid_constant__ CUtensorMap tmap_x,
                           float* __restrict__ dw, TcWgradPParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kW2Stages * kW2StageBytes);
@@ -1362,6 +1367,7 @@ conv_tc_wgrad_2cta_kernel(const __grid_constant__ CUtensorMap tmap_dy, const __g
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   // item -> (co tile fastest, ci tile, tap, split slowest)
   auto decode = [&](int item, int& cot, int& cit, int& tap, int& t_begin, int& t_end) {
@@ -1583,16 +1589,18 @@ static int launch_fwd_pairs_t(const CUtensorMap& mx, const CUtensorMap& mw, cons
   auto kern = conv_tc_fwd_2cta_kernel<MODE, kPairs>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2 * kPairs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_trigger / pdl_wait in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.blockDim = dim3(kPairThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   if (max_clusters == 0) {
     CVX_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cfg.gridDim = dim3(kNumSMs / (2 * kPairs) * (2 * kPairs));
@@ -1822,7 +1830,7 @@ int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, flo
         configured2 = true;
       }
       const int pairs = q.total_items < workers ? q.total_items : workers;
-      conv_tc_wgrad_2cta_kernel<<<2 * pairs, 192, smem2, as_stream(stream)>>>(mdy, mx, dw_packed, q);
+      launch_pdl(conv_tc_wgrad_2cta_kernel, dim3(2 * pairs), dim3(192), smem2, as_stream(stream), mdy, mx, dw_packed, q);
       CVX_LAUNCH_OK();
       return CVX_OK;
     }
@@ -1833,7 +1841,7 @@ int cvx_conv_wgrad_tc(const cvx_conv_desc* d, const void* x, const void* dy, flo
       configured = true;
     }
     const int grid = q.total_items < kNumSMs ? q.total_items : kNumSMs;
-    conv_tc_wgrad_persistent_kernel<<<grid, 192, smem, as_stream(stream)>>>(mdy, mx, dw_packed, q);
+    launch_pdl(conv_tc_wgrad_persistent_kernel, dim3(grid), dim3(192), smem, as_stream(stream), mdy, mx, dw_packed, q);
     CVX_LAUNCH_OK();
     return CVX_OK;
   }

@@ -24,18 +24,21 @@ constexpr int kFRow = (kFX + 2) * 128;                // bytes of one halo row (
 __host__ __device__ constexpr int ftile_bytes(int fy) { return (fy + 2) * kFRow; }   // one halo tile of 64 channels (32256 bytes at FY = 12)
 constexpr int kFwdStages = 3;                         // forward: 3 tiles in flight
 // Two shapes of each kernel: the tall tile (12 rows: 17 % halo rows, fewest bytes staged) and the short tile (6 rows:
-// 33 % halo rows, but a stage is 18 KB so twice as many CTAs fit an SM).  These kernels are bound by latency at 8 - 16
-// resident warps per SM (ncu: 45 % issue-active, DRAM 24 %), so residency is worth more than the extra halo traffic
-// (which comes from L2); CERVIX_DWF_VARIANT selects among them for A/B measurements.
+// 33 % halo rows, but a stage is 18 KB so twice as many CTAs fit an SM).  The kernels sit at 8 - 16 resident warps per SM
+// (ncu: 45 % issue-active, DRAM 24 %); the short-tile experiment tested whether residency beats halo traffic - it does
+// not (see g_dwf_variant below); CERVIX_DWF_VARIANT selects among the shapes for A/B measurements.
 
 struct DwFParams {
   int n, h, w, c;
   int tiles_x, tiles_y, ntiles;
   int relu_in;
 };
-// 0 = short tiles + weights in shared memory (default), 1 = tall tiles, weights in registers (the r01 kernels),
-// 2 = short tiles, weights in registers under the same register cap (the compiler spills)
-static const int g_dwf_variant = [] { const char* e = getenv("CERVIX_DWF_VARIANT"); return e ? atoi(e) : 0; }();
+// 1 = tall tiles, weights in registers (default: measured fastest), 0 = short tiles + weights in shared memory,
+// 2 = short tiles, weights in registers under the same register cap (the compiler spills).  Measured on the middle-flow
+// tensor [32,32,32,728], CUDA-graph timing (profiles/r02_dwf_variants.txt): backward 59 us (1) / 120 us (0) / 200 us (2),
+// forward 44 / 57 / 68 us - residency bought with half-height tiles loses to the doubled per-tile overhead (TMA issue,
+// barrier round trip, pre-pass and index arithmetic per tile) and to the spills under the 128-register cap.
+static const int g_dwf_variant = [] { const char* e = getenv("CERVIX_DWF_VARIANT"); return e ? atoi(e) : 1; }();
 
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   uint2 v;
@@ -113,6 +116,8 @@ __global__ void __launch_bounds__(256, MINB) dwf_fwd_kernel(const __grid_constan
                                                          const float* __restrict__ w9c, const float* __restrict__ in_scale,
                                                          const float* __restrict__ in_shift, __nv_bfloat16* __restrict__ dst,
                                                          double* __restrict__ stats, DwFParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int kFY = FY, kFTile = ftile_bytes(FY);
   static_assert(FY % 3 == 0, "the row loop is unrolled over the 3-row register window");
   extern __shared__ uint8_t smem_raw[];
@@ -286,6 +291,8 @@ __global__ void __launch_bounds__(256, MINB) dwf_bwd_kernel(const __grid_constan
                                                          const __nv_bfloat16* __restrict__ addend,
                                                          __nv_bfloat16* __restrict__ gout, double* __restrict__ dw_out,
                                                          double* __restrict__ sums, DwFParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int kFY = FY, kFTile = ftile_bytes(FY);
   static_assert(FY % 3 == 0, "the row loop is unrolled over the 3-row register window");
   constexpr int kTiles = SIDE ? 3 : 2;
@@ -321,6 +328,10 @@ __global__ void __launch_bounds__(256, MINB) dwf_bwd_kernel(const __grid_constan
     for (int i = t; i < 9 * 64; i += 256) {
       const int c = cchunk * 64 + (i & 63);
       wdst[i] = c < p.c ? __ldg(w9c + (8 - (i >> 6)) * p.c + c) : 0.f;
+    }
+    if (AFFINE && t < 128) {          // the previous BatchNorm's scale | shift of the chunk, rows 9 and 10 of the table
+      const int c = cchunk * 64 + (t & 63);
+      wdst[9 * 64 + t] = c < p.c ? __ldg((t < 64 ? in_scale : in_shift) + c) : (t < 64 ? 1.f : 0.f);
     }
   }
 #pragma unroll
@@ -425,12 +436,14 @@ __global__ void __launch_bounds__(256, MINB) dwf_bwd_kernel(const __grid_constan
           if (addend && row_ok) add_raw = __ldg(reinterpret_cast<const uint2*>(addend + off));  // issued ahead of its use
           load_row((j + 2) % 3, ra);
           ra += kFRow;
-          float2 xc[2], xin[2], g[2];
+          float2 xc[2], xin[2], g[2], scr[2], shr[2];
           load4(xa, xc);
           xa += kFRow;
+          if (AFFINE && WSMEM) { lds_w4(w_thr + 9 * 256, scr); lds_w4(w_thr + 10 * 256, shr); }
+          else { scr[0] = sc[0]; scr[1] = sc[1]; shr[0] = sh[0]; shr[1] = sh[1]; }
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            xin[e] = AFFINE ? __ffma2_rn(xc[e], sc[e], sh[e]) : xc[e];
+            xin[e] = AFFINE ? __ffma2_rn(xc[e], scr[e], shr[e]) : xc[e];
             if (relu) xin[e] = relu2(xin[e]);
             if (!row_ok) xin[e] = make_float2(0.f, 0.f);   // rows below the image feed nothing
             g[e] = make_float2(0.f, 0.f);
@@ -496,7 +509,7 @@ static void dwf_params(const cvx_conv_desc* d, int relu_in, int fy, DwFParams* p
   p->relu_in = relu_in;
 }
 
-constexpr int kWsmBytes = 9 * 64 * 4;   // the chunk's tap weights in shared memory (WSMEM variants)
+constexpr int kWsmBytes = 11 * 64 * 4;  // the chunk's tap weights (+ BatchNorm scale, shift) in shared memory (WSMEM variants)
 
 template <bool AFFINE, int FY, int MINB, bool WSMEM>
 static int dwf_fwd_launch_t(const cvx_conv_desc* d, const void* x, const float* w9c, const float* in_scale,
@@ -515,7 +528,8 @@ static int dwf_fwd_launch_t(const cvx_conv_desc* d, const void* x, const float* 
     CVX_CUDA_OK(cudaFuncSetAttribute(dwf_fwd_kernel<AFFINE, FY, MINB, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dwf_fwd_kernel<AFFINE, FY, MINB, WSMEM><<<dim3(gx, chunks), 256, smem, st>>>(map, w9c, in_scale, in_shift, (__nv_bfloat16*)y, stats, p);
+  launch_pdl(dwf_fwd_kernel<AFFINE, FY, MINB, WSMEM>, dim3(gx, chunks), dim3(256), smem, st, map, w9c, in_scale, in_shift,
+             (__nv_bfloat16*)y, stats, p);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -531,6 +545,14 @@ int dwf_fwd_launch(const cvx_conv_desc* d, const void* x, const float* w9c, cons
   if (g_dwf_variant == 2) {
     if (in_scale) return dwf_fwd_launch_t<true, 6, 3, false>(d, x, w9c, in_scale, in_shift, relu_in, y, stats, st);
     return dwf_fwd_launch_t<false, 6, 3, false>(d, x, w9c, nullptr, nullptr, relu_in, y, stats, st);
+  }
+  if (g_dwf_variant == 3) {   // short tiles alone (no register cap, same residency as the tall kernel)
+    if (in_scale) return dwf_fwd_launch_t<true, 6, 2, false>(d, x, w9c, in_scale, in_shift, relu_in, y, stats, st);
+    return dwf_fwd_launch_t<false, 6, 2, false>(d, x, w9c, nullptr, nullptr, relu_in, y, stats, st);
+  }
+  if (g_dwf_variant == 4) {   // weights in shared memory alone (tall tiles)
+    if (in_scale) return dwf_fwd_launch_t<true, 12, 2, true>(d, x, w9c, in_scale, in_shift, relu_in, y, stats, st);
+    return dwf_fwd_launch_t<false, 12, 2, true>(d, x, w9c, nullptr, nullptr, relu_in, y, stats, st);
   }
   if (in_scale) return dwf_fwd_launch_t<true, 6, 3, true>(d, x, w9c, in_scale, in_shift, relu_in, y, stats, st);
   return dwf_fwd_launch_t<false, 6, 3, true>(d, x, w9c, nullptr, nullptr, relu_in, y, stats, st);
@@ -559,8 +581,8 @@ static int dwf_bwd_launch_t(const cvx_conv_desc* d, const void* dd, const void* 
     CVX_CUDA_OK(cudaFuncSetAttribute(dwf_bwd_kernel<AFFINE, SIDE, FY, MINB, WSMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dwf_bwd_kernel<AFFINE, SIDE, FY, MINB, WSMEM><<<grid, 256, smem, st>>>(mdd, md, mx, w9c, in_scale, in_shift, negk, kmean,
-                                                                  (const __nv_bfloat16*)addend, (__nv_bfloat16*)g, dw_out, sums, p);
+  launch_pdl(dwf_bwd_kernel<AFFINE, SIDE, FY, MINB, WSMEM>, grid, dim3(256), smem, st, mdd, md, mx, w9c, in_scale, in_shift, negk,
+             kmean, (const __nv_bfloat16*)addend, (__nv_bfloat16*)g, dw_out, sums, p);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -585,6 +607,10 @@ int dwf_bwd_launch(const cvx_conv_desc* d, const void* dd, const void* dside, co
   if (sums) CVX_WS_ZERO(sums, sizeof(double) * 2 * d->cin, st);
   if (g_dwf_variant == 2)
     return dwf_bwd_dispatch<6, 2, false>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);
+  if (g_dwf_variant == 3)
+    return dwf_bwd_dispatch<6, 1, false>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);
+  if (g_dwf_variant == 4)
+    return dwf_bwd_dispatch<12, 1, true>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);
   if (g_dwf_variant == 1)
     return dwf_bwd_dispatch<12, 1, false>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);
   return dwf_bwd_dispatch<6, 2, true>(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, dw_out, sums, st);

@@ -15,6 +15,8 @@ static inline int ew_grid(int64_t total, int block = 256) {
 
 template <typename T>
 __global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t nvec, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VEC = Elem<T>::kVec;
   CVX_GRID_STRIDE(i, nvec) {
     Vec<T> v;
@@ -31,6 +33,8 @@ __global__ void relu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int6
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, int64_t nvec,
                                 int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VEC = Elem<T>::kVec;
   CVX_GRID_STRIDE(i, nvec) {
     Vec<T> g, v;
@@ -47,6 +51,8 @@ __global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, int64_t nvec,
                            int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int VEC = Elem<T>::kVec;
   CVX_GRID_STRIDE(i, nvec) {
     Vec<T> u, v;
@@ -367,6 +373,8 @@ __device__ __forceinline__ uint32_t mix64(uint64_t z) {
 template <typename T>
 __global__ void dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
                                    float p, uint64_t seed, const int* __restrict__ step_dev) {
+  pdl_trigger();
+  pdl_wait();
   if (step_dev) seed += 0x9e3779b97f4a7c15ull * (uint64_t)(*step_dev);  // per-step stream under CUDA-graph replay
   const float keep_scale = 1.f / (1.f - p);
   const uint32_t thresh = (uint32_t)((double)p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)p * 4294967296.0);
@@ -381,6 +389,8 @@ __global__ void dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, u
 template <typename T>
 __global__ void dropout_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ mask, T* __restrict__ dx,
                                    int64_t n, float p) {
+  pdl_trigger();
+  pdl_wait();
   const float keep_scale = 1.f / (1.f - p);
   CVX_GRID_STRIDE(i, n) { Elem<T>::st(dx + i, mask[i] ? Elem<T>::ld(dy + i) * keep_scale : 0.f); }
 }
@@ -396,7 +406,7 @@ int cvx_relu_fwd(const void* x, void* y, int64_t n, int dtype, void* stream) {
   CVX_CHECK_ARG((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0, "relu_fwd: pointers must be 16-byte aligned");
   const int vec = dtype == CVX_F32 ? 4 : 8;
   const int64_t nvec = n / vec;
-  CVX_DISPATCH_DTYPE(dtype, T, (relu_fwd_kernel<T><<<ew_grid(nvec), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, nvec, n)));
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(relu_fwd_kernel<T>, dim3(ew_grid(nvec)), dim3(256), 0, as_stream(stream), (const T*)x, (T*)y, nvec, n)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -407,7 +417,7 @@ int cvx_relu_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, 
                 "relu_bwd: pointers must be 16-byte aligned");
   const int vec = dtype == CVX_F32 ? 4 : 8;
   const int64_t nvec = n / vec;
-  CVX_DISPATCH_DTYPE(dtype, T, (relu_bwd_kernel<T><<<ew_grid(nvec), 256, 0, as_stream(stream)>>>((const T*)dy, (const T*)y, (T*)dx, nvec, n)));
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(relu_bwd_kernel<T>, dim3(ew_grid(nvec)), dim3(256), 0, as_stream(stream), (const T*)dy, (const T*)y, (T*)dx, nvec, n)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -418,7 +428,7 @@ int cvx_add(const void* a, const void* b, void* out, int64_t n, int dtype, void*
                 "add: pointers must be 16-byte aligned");
   const int vec = dtype == CVX_F32 ? 4 : 8;
   const int64_t nvec = n / vec;
-  CVX_DISPATCH_DTYPE(dtype, T, (add_kernel<T><<<ew_grid(nvec), 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)out, nvec, n)));
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(add_kernel<T>, dim3(ew_grid(nvec)), dim3(256), 0, as_stream(stream), (const T*)a, (const T*)b, (T*)out, nvec, n)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -520,14 +530,14 @@ int cvx_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, void* dx,
 int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, const int* step_dev,
                     int dtype, void* stream) {
   CVX_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments");
-  CVX_DISPATCH_DTYPE(dtype, T, (dropout_fwd_kernel<T><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, mask, n, p, seed, step_dev)));
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(dropout_fwd_kernel<T>, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), (const T*)x, (T*)y, mask, n, p, seed, step_dev)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream) {
   CVX_CHECK_ARG(dy && dx && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_bwd: bad arguments");
-  CVX_DISPATCH_DTYPE(dtype, T, (dropout_bwd_kernel<T><<<ew_grid(n), 256, 0, as_stream(stream)>>>((const T*)dy, mask, (T*)dx, n, p)));
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(dropout_bwd_kernel<T>, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), (const T*)dy, mask, (T*)dx, n, p)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

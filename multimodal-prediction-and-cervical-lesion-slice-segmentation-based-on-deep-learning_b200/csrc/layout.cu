@@ -3,12 +3,14 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace cvx {
 
 static thread_local char g_err[512] = "";
 unsigned long long g_kernel_launches = 0;
 int g_ws_prezeroed = 0;
+int g_pdl = [] { const char* e = getenv("CERVIX_PDL"); return e ? atoi(e) : 1; }();
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -20,7 +20,7 @@
 
 namespace cvx {
 
-constexpr int kGM = 64, kGN = 64, kGK = 16;
+constexpr int kGM = 64, kGN = 64, kGK = 32;   // two 16-deep fragments per operand and iteration: 8 loads in flight per thread
 
 struct GemmBatch {
   cvx_gemm_problem p[CVX_MAX_GEMM_PROBLEMS];
@@ -61,9 +61,10 @@ __device__ __forceinline__ void store_frag(float (*S)[kGM + 4], const Frag& f, b
   }
 }
 
-__global__ void __launch_bounds__(256) gemm_grouped_kernel(const __grid_constant__ GemmBatch batch) {
+__global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const __grid_constant__ GemmBatch batch) {
   __shared__ float As[kGK][kGM + 4];
   __shared__ float Bs[kGK][kGN + 4];
+  pdl_trigger();
   // which problem does this tile belong to?  (<= 16 entries: a linear scan of kernel parameters)
   int pi = 0;
   while (pi + 1 < batch.count && (int)blockIdx.x >= batch.tile_start[pi + 1]) ++pi;
@@ -81,20 +82,26 @@ __global__ void __launch_bounds__(256) gemm_grouped_kernel(const __grid_constant
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   float rs[4] = {0.f, 0.f, 0.f, 0.f};                      // row sums of A (bias gradient of the wgrad problems)
   const bool want_rs = P.rowsum != nullptr && n0 == 0 && tx == 0;
+  pdl_wait();
 
-  // software pipeline: the loads of k-block i+1 are in flight while block i is multiplied
-  Frag fa = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, 0, P.k, t);
-  Frag fb = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, 0, P.k, t);
+  // software pipeline: the loads of k-block i+1 (two 16-deep fragments per operand) are in flight while block i is multiplied
+  Frag fa0 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, 0, P.k, t), fa1 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, 16, P.k, t);
+  Frag fb0 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, 0, P.k, t), fb1 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, 16, P.k, t);
   for (int k0 = 0; k0 < P.k; k0 += kGK) {
-    store_frag(As, fa, a_kc, t);
-    store_frag(Bs, fb, b_kc, t);
+    store_frag(As, fa0, a_kc, t);
+    store_frag(As + 16, fa1, a_kc, t);
+    store_frag(Bs, fb0, b_kc, t);
+    store_frag(Bs + 16, fb1, b_kc, t);
     __syncthreads();
     if (k0 + kGK < P.k) {
-      fa = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, k0 + kGK, P.k, t);
-      fb = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, k0 + kGK, P.k, t);
+      fa0 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, k0 + kGK, P.k, t);
+      fa1 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, k0 + kGK + 16, P.k, t);
+      fb0 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, k0 + kGK, P.k, t);
+      fb1 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, k0 + kGK + 16, P.k, t);
     }
-#pragma unroll
-    for (int kk = 0; kk < kGK; ++kk) {
+    const int kmax = P.k - k0 < kGK ? ((P.k - k0 + 3) & ~3) : kGK;   // short last block: skip the all-zero tail
+#pragma unroll 8
+    for (int kk = 0; kk < kmax; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
       const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -142,7 +149,7 @@ extern "C" int cvx_gemm_grouped(const cvx_gemm_problem* problems, int count, voi
   }
   batch.tile_start[count] = tiles;
   batch.count = count;
-  gemm_grouped_kernel<<<tiles, 256, 0, as_stream(stream)>>>(batch);
+  launch_pdl(gemm_grouped_kernel, dim3(tiles), dim3(256), 0, as_stream(stream), batch);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

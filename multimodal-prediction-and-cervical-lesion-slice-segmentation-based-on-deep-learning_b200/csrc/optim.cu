@@ -24,6 +24,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, int64_t n, const float* __restrict__ hyper,
                                 const int* __restrict__ step) {
+  pdl_trigger();
+  pdl_wait();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4], gscale = hyper[5];
   const float t = (float)(*step);
   const float bc1 = 1.f - powf(b1, t);
@@ -87,6 +89,8 @@ __global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, f
 // zero-initialised momentum buffer gives, so no step count is needed.
 __global__ void sgd_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, int64_t n,
                                const float* __restrict__ hyper, int nesterov) {
+  pdl_trigger();
+  pdl_wait();
   const float lr = hyper[0], mom = hyper[1], wd = hyper[4], gscale = hyper[5];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * gscale;
@@ -123,7 +127,7 @@ int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
                       void* stream) {
   CVX_CHECK_ARG(p && g && m && v && hyper && step && n > 0, "adam_step_dev: bad arguments");
   int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
-  adam_dev_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, hyper, step);
+  launch_pdl(adam_dev_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, m, v, n, hyper, step);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -131,7 +135,7 @@ int cvx_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, c
 int cvx_sgd_step_dev(float* p, const float* g, float* buf, int64_t n, const float* hyper, int nesterov, void* stream) {
   CVX_CHECK_ARG(p && g && buf && hyper && n > 0, "sgd_step_dev: bad arguments");
   int blocks = (int)(ceil_div64(n, 256) > kNumSMs * 8 ? kNumSMs * 8 : ceil_div64(n, 256));
-  sgd_dev_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, buf, n, hyper, nesterov);
+  launch_pdl(sgd_dev_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, buf, n, hyper, nesterov);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

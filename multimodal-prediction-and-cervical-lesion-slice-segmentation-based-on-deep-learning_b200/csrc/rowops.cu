@@ -32,6 +32,8 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 __global__ void seg_layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                          const float* __restrict__ b, float* __restrict__ y, float* __restrict__ stats,
                                          int seg, int C, float eps, int mode) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int g = blockIdx.x;
   const int n = seg * C;
@@ -55,6 +57,8 @@ __global__ void seg_layernorm_fwd_kernel(const float* __restrict__ x, const floa
 __global__ void seg_layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                          const float* __restrict__ w, const float* __restrict__ stats,
                                          float* __restrict__ dx, int seg, int C, float eps, int mode) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int g = blockIdx.x;
   const int n = seg * C;
@@ -83,6 +87,8 @@ __global__ void seg_layernorm_bwd_kernel(const float* __restrict__ dy, const flo
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ stats, float* __restrict__ dw,
                                                             float* __restrict__ db, int rows, int seg, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float pw[8][33], pb[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -109,12 +115,16 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restr
 
 // ---- GELU (erf form, nn.GELU default) ------------------------------------------------------------
 __global__ void gelu_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     y[i] = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
   }
 }
 __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = x[i];
     const float cdf = 0.5f * (1.f + erff(v * 0.70710678118654752f));
@@ -127,6 +137,8 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const float* __res
 __global__ void graph_gather_kernel(const float* __restrict__ x, float* __restrict__ out, int G, int nodes, int C,
                                     const int* __restrict__ rowptr, const int* __restrict__ col,
                                     const float* __restrict__ w) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)G * nodes * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -141,6 +153,8 @@ __global__ void graph_gather_kernel(const float* __restrict__ x, float* __restri
 // ---- gated attention pooling (my_GlobalAttention): one CTA per graph -------------------------------
 __global__ void gate_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gate, float* __restrict__ pooled,
                                      float* __restrict__ att, int seg, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float a[64];
   const int g = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -161,6 +175,8 @@ __global__ void gate_pool_fwd_kernel(const float* __restrict__ x, const float* _
 __global__ void gate_pool_bwd_kernel(const float* __restrict__ dpooled, const float* __restrict__ x,
                                      const float* __restrict__ att, float* __restrict__ dx, float* __restrict__ dgate,
                                      int seg, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   __shared__ float datt[64];
   const int g = blockIdx.x;
@@ -194,6 +210,8 @@ __device__ __forceinline__ float hash_uniform(uint64_t z) {
 __global__ void attn_small_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ out, float* __restrict__ probs,
                                       int B, int N, int H, int D, float scale, float drop_p, uint64_t seed,
                                       const int* __restrict__ step_dev) {
+  pdl_trigger();
+  pdl_wait();
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= B * H) return;
   if (step_dev) seed += 0x9e3779b97f4a7c15ull * (uint64_t)(*step_dev);  // per-step stream under CUDA-graph replay
@@ -232,6 +250,8 @@ __global__ void attn_small_fwd_kernel(const float* __restrict__ qkv, float* __re
 __global__ void attn_small_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ qkv,
                                       const float* __restrict__ probs, float* __restrict__ dqkv, int B, int N, int H, int D,
                                       float scale, float drop_p, uint64_t seed, const int* __restrict__ step_dev) {
+  pdl_trigger();
+  pdl_wait();
   if (step_dev) seed += 0x9e3779b97f4a7c15ull * (uint64_t)(*step_dev);
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (wid >= B * H) return;
@@ -296,6 +316,8 @@ __global__ void attn_small_bwd_kernel(const float* __restrict__ dout, const floa
 
 // ---- row L2 normalisation (F.normalize(dim=1)) ---------------------------------------------------
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norms, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int r = blockIdx.x;
   float s = 0.f;
@@ -306,6 +328,8 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict
 }
 __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ norms,
                                   float* __restrict__ dx, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int r = blockIdx.x;
   float s = 0.f;
@@ -319,6 +343,8 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 // ---- row gather: y[i,:] = (idx[i] >= 0) ? x[idx[i],:] : fill[:]  --------------------------------------
 __global__ void rows_gather_kernel(const float* __restrict__ x, const int* __restrict__ idx, const float* __restrict__ fill,
                                    float* __restrict__ y, int rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)rows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / C), c = (int)(i % C);
@@ -330,6 +356,8 @@ __global__ void rows_gather_kernel(const float* __restrict__ x, const int* __res
 // block per source row (block src_rows = the fill row), rows visited in increasing order -> no atomics, fixed order.
 __global__ void rows_scatter_add_kernel(const float* __restrict__ dy, const int* __restrict__ idx, float* __restrict__ dx,
                                         float* __restrict__ dfill, int rows, int src_rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x;
   const bool fill = s == src_rows;
   float* out = fill ? dfill : dx + (size_t)s * C;
@@ -349,6 +377,8 @@ __global__ void rows_scatter_add_kernel(const float* __restrict__ dy, const int*
 // stream are ordered, so the accumulated objective is bit-reproducible)
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                                   float* __restrict__ loss, float* __restrict__ dlogits, int B, int K, float weight) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   float part = 0.f;
   for (int r = threadIdx.x; r < B; r += blockDim.x) {
@@ -369,6 +399,8 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const int64_
 __global__ void masked_mse_kernel(const float* __restrict__ a, const float* __restrict__ b, const uint8_t* __restrict__ sel,
                                   float* __restrict__ loss, float* __restrict__ da, float* __restrict__ db_, int rows, int C,
                                   float weight, float inv_count) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   float s = 0.f;          // one block walks every row: a single fixed-order sum, no atomics
   for (int r = 0; r < rows; ++r) {
@@ -406,6 +438,8 @@ __global__ void segtab_layernorm_fwd_kernel(const float* __restrict__ x, SetPtrs
                                             float* __restrict__ stats, const int* __restrict__ seg_start,
                                             const int* __restrict__ seg_len, const int* __restrict__ seg_set, int C,
                                             float eps, int mode) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int g = blockIdx.x;
   const int n = seg_len[g] * C;
@@ -432,6 +466,8 @@ __global__ void segtab_layernorm_bwd_kernel(const float* __restrict__ dy, const 
                                             const float* __restrict__ stats, float* __restrict__ dx,
                                             const int* __restrict__ seg_start, const int* __restrict__ seg_len,
                                             const int* __restrict__ seg_set, int C, float eps, int mode) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   const int g = blockIdx.x;
   const int n = seg_len[g] * C;
@@ -459,6 +495,8 @@ __global__ void segtab_layernorm_bwd_kernel(const float* __restrict__ dy, const 
 __global__ void __launch_bounds__(256) segtab_ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                    const float* __restrict__ stats,
                                                                    const int* __restrict__ row_seg, SetPtrs P, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float pw[8][33], pb[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx, set = blockIdx.y;
@@ -488,6 +526,8 @@ __global__ void __launch_bounds__(256) segtab_ln_param_grad_kernel(const float* 
 __global__ void segtab_gate_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gate,
                                             float* __restrict__ pooled, float* __restrict__ att,
                                             const int* __restrict__ seg_start, const int* __restrict__ seg_len, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float a[64];
   const int s = blockIdx.x, r0 = seg_start[s], seg = seg_len[s];
   if (threadIdx.x == 0) {
@@ -509,6 +549,8 @@ __global__ void segtab_gate_pool_bwd_kernel(const float* __restrict__ dpooled, c
                                             const float* __restrict__ att, float* __restrict__ dx,
                                             float* __restrict__ dgate, const int* __restrict__ seg_start,
                                             const int* __restrict__ seg_len, int C) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[32];
   __shared__ float datt[64];
   const int s = blockIdx.x, r0 = seg_start[s], seg = seg_len[s];
@@ -533,6 +575,8 @@ __global__ void segtab_gate_pool_bwd_kernel(const float* __restrict__ dpooled, c
 // token" (my_mae_model.py:636-649) for every modality at once
 __global__ void segtab_bcast_add_kernel(const float* __restrict__ x, const float* __restrict__ t, float* __restrict__ y,
                                         const int* __restrict__ row_seg, const int* __restrict__ tok_of_seg, int rows, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = (int64_t)rows * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / C), c = (int)(i % C);
@@ -545,6 +589,8 @@ __global__ void segtab_bcast_add_kernel(const float* __restrict__ x, const float
 __global__ void segtab_bcast_add_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dt,
                                             const int* __restrict__ seg_of_tok, const int* __restrict__ seg_start,
                                             const int* __restrict__ seg_len, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int tok = blockIdx.x, s = seg_of_tok[tok];
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
@@ -569,7 +615,7 @@ extern "C" {
 int cvx_seg_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* stats, int groups, int seg, int c,
                           float eps, int mode, void* stream) {
   CVX_CHECK_ARG(x && w && b && y && stats && groups > 0 && seg > 0 && c > 0 && (mode == 0 || mode == 1), "seg_layernorm_fwd: bad arguments");
-  seg_layernorm_fwd_kernel<<<groups, 256, 0, as_stream(stream)>>>(x, w, b, y, stats, seg, c, eps, mode);
+  launch_pdl(seg_layernorm_fwd_kernel, dim3(groups), dim3(256), 0, as_stream(stream), x, w, b, y, stats, seg, c, eps, mode);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -578,10 +624,10 @@ int cvx_seg_layernorm_bwd(const float* dy, const float* x, const float* w, const
                           float* db, int groups, int seg, int c, float eps, int mode, void* stream) {
   CVX_CHECK_ARG(dy && x && w && stats && dx && groups > 0 && seg > 0 && c > 0, "seg_layernorm_bwd: bad arguments");
   cudaStream_t st = as_stream(stream);
-  seg_layernorm_bwd_kernel<<<groups, 256, 0, st>>>(dy, x, w, stats, dx, seg, c, eps, mode);
+  launch_pdl(seg_layernorm_bwd_kernel, dim3(groups), dim3(256), 0, st, dy, x, w, stats, dx, seg, c, eps, mode);
   CVX_LAUNCH_OK();
   if (dw || db) {
-    ln_param_grad_kernel<<<(c + 31) / 32, 256, 0, st>>>(dy, x, stats, dw, db, groups * seg, seg, c);
+    launch_pdl(ln_param_grad_kernel, dim3((c + 31) / 32), dim3(256), 0, st, dy, x, stats, dw, db, groups * seg, seg, c);
     CVX_LAUNCH_OK();
   }
   return CVX_OK;
@@ -607,7 +653,7 @@ int cvx_segtab_layernorm_fwd(const float* x, const cvx_param_sets* ps, float* y,
   SetPtrs P;
   if (int rc = fill_sets(&P, ps, "segtab_layernorm_fwd")) return rc;
   for (int i = 0; i < P.sets; ++i) CVX_CHECK_ARG(P.w[i] && P.b[i], "segtab_layernorm_fwd: set %d has no affine parameters", i);
-  segtab_layernorm_fwd_kernel<<<segments, 256, 0, as_stream(stream)>>>(x, P, y, stats, seg_start, seg_len, seg_set, c, eps, mode);
+  launch_pdl(segtab_layernorm_fwd_kernel, dim3(segments), dim3(256), 0, as_stream(stream), x, P, y, stats, seg_start, seg_len, seg_set, c, eps, mode);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -620,9 +666,9 @@ int cvx_segtab_layernorm_bwd(const float* dy, const float* x, const cvx_param_se
   SetPtrs P;
   if (int rc = fill_sets(&P, ps, "segtab_layernorm_bwd")) return rc;
   cudaStream_t st = as_stream(stream);
-  segtab_layernorm_bwd_kernel<<<segments, 256, 0, st>>>(dy, x, P, stats, dx, seg_start, seg_len, seg_set, c, eps, mode);
+  launch_pdl(segtab_layernorm_bwd_kernel, dim3(segments), dim3(256), 0, st, dy, x, P, stats, dx, seg_start, seg_len, seg_set, c, eps, mode);
   CVX_LAUNCH_OK();
-  segtab_ln_param_grad_kernel<<<dim3((c + 31) / 32, P.sets), 256, 0, st>>>(dy, x, stats, row_seg, P, c);
+  launch_pdl(segtab_ln_param_grad_kernel, dim3(dim3((c + 31) / 32, P.sets)), dim3(256), 0, st, dy, x, stats, row_seg, P, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -631,7 +677,7 @@ int cvx_segtab_gate_pool_fwd(const float* x, const float* gate, float* pooled, f
                              const int* seg_len, int segments, int max_len, int c, void* stream) {
   CVX_CHECK_ARG(x && gate && pooled && att && seg_start && seg_len && segments > 0 && max_len > 0 && max_len <= 64 && c > 0,
                 "segtab_gate_pool_fwd: bad arguments (segments of at most 64 rows)");
-  segtab_gate_pool_fwd_kernel<<<segments, 256, 0, as_stream(stream)>>>(x, gate, pooled, att, seg_start, seg_len, c);
+  launch_pdl(segtab_gate_pool_fwd_kernel, dim3(segments), dim3(256), 0, as_stream(stream), x, gate, pooled, att, seg_start, seg_len, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -640,7 +686,7 @@ int cvx_segtab_gate_pool_bwd(const float* dpooled, const float* x, const float* 
                              const int* seg_start, const int* seg_len, int segments, int max_len, int c, void* stream) {
   CVX_CHECK_ARG(dpooled && x && att && dx && dgate && seg_start && seg_len && segments > 0 && max_len > 0 && max_len <= 64 && c > 0,
                 "segtab_gate_pool_bwd: bad arguments");
-  segtab_gate_pool_bwd_kernel<<<segments, 256, 0, as_stream(stream)>>>(dpooled, x, att, dx, dgate, seg_start, seg_len, c);
+  launch_pdl(segtab_gate_pool_bwd_kernel, dim3(segments), dim3(256), 0, as_stream(stream), dpooled, x, att, dx, dgate, seg_start, seg_len, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -648,7 +694,7 @@ int cvx_segtab_gate_pool_bwd(const float* dpooled, const float* x, const float* 
 int cvx_segtab_bcast_add(const float* x, const float* t, float* y, const int* row_seg, const int* tok_of_seg, int rows, int c,
                          void* stream) {
   CVX_CHECK_ARG(x && t && y && row_seg && tok_of_seg && rows > 0 && c > 0, "segtab_bcast_add: bad arguments");
-  segtab_bcast_add_kernel<<<rgrid((int64_t)rows * c), 256, 0, as_stream(stream)>>>(x, t, y, row_seg, tok_of_seg, rows, c);
+  launch_pdl(segtab_bcast_add_kernel, dim3(rgrid((int64_t)rows * c)), dim3(256), 0, as_stream(stream), x, t, y, row_seg, tok_of_seg, rows, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -656,21 +702,21 @@ int cvx_segtab_bcast_add(const float* x, const float* t, float* y, const int* ro
 int cvx_segtab_bcast_add_bwd(const float* dy, float* dt, const int* seg_of_tok, const int* seg_start, const int* seg_len,
                              int tokens, int c, void* stream) {
   CVX_CHECK_ARG(dy && dt && seg_of_tok && seg_start && seg_len && tokens > 0 && c > 0, "segtab_bcast_add_bwd: bad arguments");
-  segtab_bcast_add_bwd_kernel<<<tokens, 128, 0, as_stream(stream)>>>(dy, dt, seg_of_tok, seg_start, seg_len, c);
+  launch_pdl(segtab_bcast_add_bwd_kernel, dim3(tokens), dim3(128), 0, as_stream(stream), dy, dt, seg_of_tok, seg_start, seg_len, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_gelu_fwd(const float* x, float* y, int64_t n, void* stream) {
   CVX_CHECK_ARG(x && y && n > 0, "gelu_fwd: bad arguments");
-  gelu_fwd_kernel<<<rgrid(n), 256, 0, as_stream(stream)>>>(x, y, n);
+  launch_pdl(gelu_fwd_kernel, dim3(rgrid(n)), dim3(256), 0, as_stream(stream), x, y, n);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, void* stream) {
   CVX_CHECK_ARG(dy && x && dx && n > 0, "gelu_bwd: bad arguments");
-  gelu_bwd_kernel<<<rgrid(n), 256, 0, as_stream(stream)>>>(dy, x, dx, n);
+  launch_pdl(gelu_bwd_kernel, dim3(rgrid(n)), dim3(256), 0, as_stream(stream), dy, x, dx, n);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -678,14 +724,14 @@ int cvx_gelu_bwd(const float* dy, const float* x, float* dx, int64_t n, void* st
 int cvx_graph_gather(const float* x, float* out, int groups, int nodes, int c, const int* rowptr, const int* col,
                      const float* w, void* stream) {
   CVX_CHECK_ARG(x && out && rowptr && col && w && groups > 0 && nodes > 0 && c > 0, "graph_gather: bad arguments");
-  graph_gather_kernel<<<rgrid((int64_t)groups * nodes * c), 256, 0, as_stream(stream)>>>(x, out, groups, nodes, c, rowptr, col, w);
+  launch_pdl(graph_gather_kernel, dim3(rgrid((int64_t)groups * nodes * c)), dim3(256), 0, as_stream(stream), x, out, groups, nodes, c, rowptr, col, w);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_gate_pool_fwd(const float* x, const float* gate, float* pooled, float* att, int groups, int seg, int c, void* stream) {
   CVX_CHECK_ARG(x && gate && pooled && att && groups > 0 && seg > 0 && seg <= 64 && c > 0, "gate_pool_fwd: bad arguments");
-  gate_pool_fwd_kernel<<<groups, 256, 0, as_stream(stream)>>>(x, gate, pooled, att, seg, c);
+  launch_pdl(gate_pool_fwd_kernel, dim3(groups), dim3(256), 0, as_stream(stream), x, gate, pooled, att, seg, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -693,7 +739,7 @@ int cvx_gate_pool_fwd(const float* x, const float* gate, float* pooled, float* a
 int cvx_gate_pool_bwd(const float* dpooled, const float* x, const float* att, float* dx, float* dgate, int groups, int seg,
                       int c, void* stream) {
   CVX_CHECK_ARG(dpooled && x && att && dx && dgate && groups > 0 && seg > 0 && seg <= 64 && c > 0, "gate_pool_bwd: bad arguments");
-  gate_pool_bwd_kernel<<<groups, 256, 0, as_stream(stream)>>>(dpooled, x, att, dx, dgate, seg, c);
+  launch_pdl(gate_pool_bwd_kernel, dim3(groups), dim3(256), 0, as_stream(stream), dpooled, x, att, dx, dgate, seg, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -703,7 +749,7 @@ int cvx_attn_small_fwd(const float* qkv, float* out, float* probs, int b, int n,
   CVX_CHECK_ARG(qkv && out && probs && b > 0 && n > 0 && n <= kMaxTok && h > 0 && d > 0 && drop_p >= 0.f && drop_p < 1.f,
                 "attn_small_fwd: bad arguments (at most %d tokens)", kMaxTok);
   const int warps = b * h;
-  attn_small_fwd_kernel<<<(warps * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(qkv, out, probs, b, n, h, d, scale, drop_p, seed, step_dev);
+  launch_pdl(attn_small_fwd_kernel, dim3((warps * 32 + 127) / 128), dim3(128), 0, as_stream(stream), qkv, out, probs, b, n, h, d, scale, drop_p, seed, step_dev);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -712,28 +758,28 @@ int cvx_attn_small_bwd(const float* dout, const float* qkv, const float* probs, 
                        float scale, float drop_p, uint64_t seed, const int* step_dev, void* stream) {
   CVX_CHECK_ARG(dout && qkv && probs && dqkv && b > 0 && n > 0 && n <= kMaxTok && h > 0 && d > 0, "attn_small_bwd: bad arguments");
   const int warps = b * h;
-  attn_small_bwd_kernel<<<(warps * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(dout, qkv, probs, dqkv, b, n, h, d, scale, drop_p, seed, step_dev);
+  launch_pdl(attn_small_bwd_kernel, dim3((warps * 32 + 127) / 128), dim3(128), 0, as_stream(stream), dout, qkv, probs, dqkv, b, n, h, d, scale, drop_p, seed, step_dev);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_l2norm_fwd(const float* x, float* y, float* norms, int rows, int c, void* stream) {
   CVX_CHECK_ARG(x && y && norms && rows > 0 && c > 0, "l2norm_fwd: bad arguments");
-  l2norm_fwd_kernel<<<rows, 128, 0, as_stream(stream)>>>(x, y, norms, c);
+  launch_pdl(l2norm_fwd_kernel, dim3(rows), dim3(128), 0, as_stream(stream), x, y, norms, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int rows, int c, void* stream) {
   CVX_CHECK_ARG(dy && y && norms && dx && rows > 0 && c > 0, "l2norm_bwd: bad arguments");
-  l2norm_bwd_kernel<<<rows, 128, 0, as_stream(stream)>>>(dy, y, norms, dx, c);
+  launch_pdl(l2norm_bwd_kernel, dim3(rows), dim3(128), 0, as_stream(stream), dy, y, norms, dx, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
 int cvx_rows_gather(const float* x, const int* idx, const float* fill, float* y, int rows, int c, void* stream) {
   CVX_CHECK_ARG(x && idx && y && rows > 0 && c > 0, "rows_gather: bad arguments");
-  rows_gather_kernel<<<rgrid((int64_t)rows * c), 256, 0, as_stream(stream)>>>(x, idx, fill, y, rows, c);
+  launch_pdl(rows_gather_kernel, dim3(rgrid((int64_t)rows * c)), dim3(256), 0, as_stream(stream), x, idx, fill, y, rows, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -741,7 +787,7 @@ int cvx_rows_gather(const float* x, const int* idx, const float* fill, float* y,
 int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfill, int rows, int src_rows, int c,
                          void* stream) {
   CVX_CHECK_ARG(dy && idx && dx && rows > 0 && src_rows > 0 && c > 0, "rows_scatter_add: bad arguments");
-  rows_scatter_add_kernel<<<src_rows + (dfill ? 1 : 0), 128, 0, as_stream(stream)>>>(dy, idx, dx, dfill, rows, src_rows, c);
+  launch_pdl(rows_scatter_add_kernel, dim3(src_rows + (dfill ? 1 : 0)), dim3(128), 0, as_stream(stream), dy, idx, dx, dfill, rows, src_rows, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -749,7 +795,7 @@ int cvx_rows_scatter_add(const float* dy, const int* idx, float* dx, float* dfil
 int cvx_softmax_ce(const float* logits, const int64_t* labels, float* loss, float* dlogits, int b, int k, float weight,
                    void* stream) {
   CVX_CHECK_ARG(logits && labels && loss && b > 0 && k > 0, "softmax_ce: bad arguments");
-  softmax_ce_kernel<<<1, 128, 0, as_stream(stream)>>>(logits, labels, loss, dlogits, b, k, weight);
+  launch_pdl(softmax_ce_kernel, dim3(1), dim3(128), 0, as_stream(stream), logits, labels, loss, dlogits, b, k, weight);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -757,7 +803,7 @@ int cvx_softmax_ce(const float* logits, const int64_t* labels, float* loss, floa
 int cvx_masked_mse(const float* a, const float* b, const uint8_t* sel, float* loss, float* da, float* db, int rows, int c,
                    float weight, float inv_count, void* stream) {
   CVX_CHECK_ARG(a && b && sel && loss && rows > 0 && c > 0, "masked_mse: bad arguments");
-  masked_mse_kernel<<<1, 512, 0, as_stream(stream)>>>(a, b, sel, loss, da, db, rows, c, weight, inv_count);
+  launch_pdl(masked_mse_kernel, dim3(1), dim3(512), 0, as_stream(stream), a, b, sel, loss, da, db, rows, c, weight, inv_count);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -23,6 +23,8 @@ __global__ void bn_affine_kernel(const double* __restrict__ acc, int64_t rows, c
                                  float* running_mean, float* running_var,
                                  float* __restrict__ mean_out, float* __restrict__ invstd_out, float* __restrict__ scale,
                                  float* __restrict__ shift, int C, float momentum, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double n = (double)rows;
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(128) pw_fold_kernel(const float* __restrict__ 
                                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ wp,
                                                       __nv_bfloat16* __restrict__ wpt, float* __restrict__ bias, int cout,
                                                       int cin) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[4];
   const int o = blockIdx.x;
   float part = 0.f;
@@ -69,6 +73,8 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, int64_t rows
                                    const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ A,
                                    float* __restrict__ Bc, float* __restrict__ Cc, float* __restrict__ dgamma,
                                    float* __restrict__ dbeta, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double n = (double)rows;
@@ -89,6 +95,8 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ sums, int64_t rows
 __global__ void __launch_bounds__(256) pw_bwd_coef_kernel(const float* __restrict__ G, const float* __restrict__ w,
                                                           const float* __restrict__ scale, float* __restrict__ dW,
                                                           float* __restrict__ colsum, int cout, int cin, int rows_per_block) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cx;
@@ -118,6 +126,8 @@ __global__ void pw_bwd_finalize_kernel(const float* __restrict__ colsum, const f
                                        const float* __restrict__ invstd, const float* __restrict__ mean, int64_t rows,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ negk,
                                        float* __restrict__ kmean, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float dgam = invstd[c] * colsum[c];
@@ -134,6 +144,8 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const __nv_bfloat16* __
                                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                          const float* __restrict__ shift, int64_t rows, int C, int act,
                                                          int64_t stride_vecs) {
+  pdl_trigger();
+  pdl_wait();
   const int cvn = C / 8;
   const int64_t total = rows * cvn;
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -196,6 +208,8 @@ __global__ void __launch_bounds__(256) bn_bwd_affine_kernel(const __nv_bfloat16*
                                                             const float* __restrict__ Bc, const float* __restrict__ Cc,
                                                             __nv_bfloat16* __restrict__ dp, __nv_bfloat16* __restrict__ gout,
                                                             int64_t rows, int C, int act, int64_t stride_vecs) {
+  pdl_trigger();
+  pdl_wait();
   const int cvn = C / 8;
   const int64_t total = rows * cvn;
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -230,6 +244,8 @@ static inline void sep_stream_grid(int64_t total_vecs, int cvn, int* blocks, int
 }
 
 __global__ void d2f_kernel(const double* __restrict__ a, float* __restrict__ out, int n) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = (float)a[i];
 }
@@ -257,7 +273,7 @@ int cvx_dwf_bwd(const cvx_conv_desc* d, const void* dd, const void* dside, const
   const int rc = dwf_bwd_launch(d, dd, dside, negk, kmean, x, w9c, in_scale, in_shift, relu_in, addend, g, ws, sums, st);
   if (rc == CVX_EUNSUPPORTED) set_error("dwf_bwd: needs bf16, 3x3, stride 1, dilation 1, pad 1, C %% 8 == 0");
   if (rc) return rc;
-  d2f_kernel<<<(9 * d->cin + 255) / 256, 256, 0, st>>>(ws, dw9c, 9 * d->cin);
+  launch_pdl(d2f_kernel, dim3((9 * d->cin + 255) / 256), dim3(256), 0, st, ws, dw9c, 9 * d->cin);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -274,7 +290,7 @@ int cvx_bn_affine(const double* stats, int64_t rows, const float* gamma, const f
                   float* running_mean, float* running_var, float* mean, float* invstd, float* scale, float* shift, int c,
                   float momentum, float eps, void* stream) {
   CVX_CHECK_ARG(stats && gamma && beta && mean && invstd && scale && shift && rows > 0 && c > 0, "bn_affine: bad arguments");
-  bn_affine_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(stats, rows, gamma, beta, mean_offset, running_mean,
+  launch_pdl(bn_affine_kernel, dim3((c + 127) / 128), dim3(128), 0, as_stream(stream), stats, rows, gamma, beta, mean_offset, running_mean,
                                                                    running_var, mean, invstd, scale, shift, c, momentum, eps);
   CVX_LAUNCH_OK();
   return CVX_OK;
@@ -283,7 +299,7 @@ int cvx_bn_affine(const double* stats, int64_t rows, const float* gamma, const f
 int cvx_pw_fold(const float* w, const float* scale, const float* shift, void* wp, void* wpt, float* bias, int cout, int cin,
                 void* stream) {
   CVX_CHECK_ARG(w && scale && shift && wp && wpt && bias && cout > 0 && cin > 0, "pw_fold: bad arguments");
-  pw_fold_kernel<<<cout, 128, 0, as_stream(stream)>>>(w, scale, shift, (__nv_bfloat16*)wp, (__nv_bfloat16*)wpt, bias, cout, cin);
+  launch_pdl(pw_fold_kernel, dim3(cout), dim3(128), 0, as_stream(stream), w, scale, shift, (__nv_bfloat16*)wp, (__nv_bfloat16*)wpt, bias, cout, cin);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -293,7 +309,7 @@ int cvx_affine_act(const void* p, const void* res, void* y, const float* scale, 
   CVX_CHECK_ARG(p && y && scale && shift && rows > 0 && c > 0 && c % 8 == 0, "affine_act: bad arguments");
   int blocks; int64_t stride;
   sep_stream_grid(rows * (c / 8), c / 8, &blocks, &stride);
-  affine_act_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)res,
+  launch_pdl(affine_act_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)p, (const __nv_bfloat16*)res,
                                                           (__nv_bfloat16*)y, scale, shift, rows, c, act, stride);
   CVX_LAUNCH_OK();
   return CVX_OK;
@@ -310,7 +326,7 @@ int cvx_bn_bwd_sums(const void* dy, const void* y, const void* p, double* sums, 
 int cvx_bn_bwd_coef(const double* sums, int64_t rows, const float* mean, const float* invstd, const float* gamma, float* a,
                     float* b, float* cc, float* dgamma, float* dbeta, int c, void* stream) {
   CVX_CHECK_ARG(sums && mean && invstd && gamma && a && b && cc && dgamma && dbeta && rows > 0 && c > 0, "bn_bwd_coef: bad arguments");
-  bn_bwd_coef_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, rows, mean, invstd, gamma, a, b, cc, dgamma, dbeta, c);
+  launch_pdl(bn_bwd_coef_kernel, dim3((c + 127) / 128), dim3(128), 0, as_stream(stream), sums, rows, mean, invstd, gamma, a, b, cc, dgamma, dbeta, c);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -321,7 +337,7 @@ int cvx_bn_bwd_affine(const void* dy, const void* y, const void* p, const float*
                 "bn_bwd_affine: bad arguments");
   int blocks; int64_t stride;
   sep_stream_grid(rows * (c / 8), c / 8, &blocks, &stride);
-  bn_bwd_affine_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+  launch_pdl(bn_bwd_affine_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
                                                              (const __nv_bfloat16*)p, a, b, cc, (__nv_bfloat16*)dp,
                                                              (__nv_bfloat16*)gout, rows, c, act, stride);
   CVX_LAUNCH_OK();
@@ -337,9 +353,9 @@ int cvx_pw_bwd_coef(const float* g_packed, const float* w, const float* scale, c
   CVX_CUDA_OK(cudaMemsetAsync(colsum, 0, sizeof(float) * cin, st));
   const int rpb = 64;
   dim3 grid((cin + 31) / 32, (cout + rpb - 1) / rpb);
-  pw_bwd_coef_kernel<<<grid, 256, 0, st>>>(g_packed, w, scale, dw, colsum, cout, cin, rpb);
+  launch_pdl(pw_bwd_coef_kernel, dim3(grid), dim3(256), 0, st, g_packed, w, scale, dw, colsum, cout, cin, rpb);
   CVX_LAUNCH_OK();
-  pw_bwd_finalize_kernel<<<(cin + 127) / 128, 128, 0, st>>>(colsum, scale, invstd, mean, rows, dgamma, dbeta, negk, kmean, cin);
+  launch_pdl(pw_bwd_finalize_kernel, dim3((cin + 127) / 128), dim3(128), 0, st, colsum, scale, invstd, mean, rows, dgamma, dbeta, negk, kmean, cin);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

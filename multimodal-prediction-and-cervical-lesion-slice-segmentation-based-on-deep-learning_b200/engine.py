@@ -311,11 +311,16 @@ class SegTrainer:
         self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
         return self.last
 
-    def _update(self):
-        """The optimizer on every run of trainable parameters; hyper-parameters and step counts come from device memory."""
+    def _update(self, lo: int = 0, hi: Optional[int] = None):
+        """The optimizer on every run of trainable parameters (clipped to the flat range lo..hi); hyper-parameters and step
+        counts come from device memory."""
         B = get_backend()
         d, g, m, v = self.flat.data, self.flat.grad, self.m, self.v
+        hi = self.flat.numel if hi is None else hi
         for a, b, k in self.runs:
+            a, b = max(a, lo), min(b, hi)
+            if a >= b:
+                continue
             cnt = self.step_devs[k:k + 1]
             if self.optimizer == "adam":
                 B.adam_step_dev(d[a:b], g[a:b], m[a:b], v[a:b], self.hyper_dev, cnt)
@@ -362,12 +367,14 @@ class SegTrainer:
 
     # ------------------------------------------------------------------ CUDA graph
     def capture(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None, warmup: int = 3,
-                comm_in_graph: bool = True):
+                comm_in_graph: bool = False):
         """Capture one training step (~1 800 kernel launches) into a CUDA graph over static input buffers: forward,
-        objective, backward, the bucket gathers, the optimizer and - data parallel - the NCCL all-reduce of every bucket
-        (forked onto NCCL's stream where the bucket completes, joined before the optimizer), so a replay overlaps
-        communication with backward exactly as the eager step does.  ``comm_in_graph=False`` keeps the collective out of
-        the graph (one all-reduce of the flat gradient + the optimizer after each replay)."""
+        objective, backward, the bucket gathers and - single GPU - the optimizer.  Data parallel (default): the graph ends
+        with the gathered flat gradient; after each replay the buckets are all-reduced back to back on NCCL's stream and
+        the optimizer of bucket k runs as soon as ITS all-reduce is done, i.e. under the all-reduce of bucket k+1
+        (``_reduce_update_pipelined``).  ``comm_in_graph=True`` records the bucket all-reduces inside the graph, forked
+        where each bucket completes, so that they overlap backward as in the eager step; with torch 2.11 / NCCL 2.28 on the
+        2 x B200 box that capture hung at replay (profiles/r02_multigpu_notes.txt), so it is opt-in."""
         self.refresh_trainable()
         self._comm_in_graph = comm_in_graph or self.world == 1
         self.s_imgs, self.s_pngs = imgs.clone(), pngs.clone()
@@ -410,10 +417,27 @@ class SegTrainer:
             self.s_labels.copy_(labels, non_blocking=True)
         self.graph.replay()
         if not self._comm_in_graph:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
-            self._update()
+            self._reduce_update_pipelined()
         self.t += 1
         return self.s_out
+
+    def _reduce_update_pipelined(self):
+        """All-reduce the buckets in order on NCCL's stream; the compute stream waits for bucket k only, then updates the
+        parameters of bucket k while bucket k+1 is still on the wire."""
+        works = []
+        for bk in self.buckets:
+            seg = self.flat.grad[bk.start:bk.end]
+            if self.wire_dtype is not None and self.wire_dtype != torch.float32:
+                bk.wire = seg.to(self.wire_dtype)
+                works.append(dist.all_reduce(bk.wire, op=dist.ReduceOp.SUM, async_op=True))
+            else:
+                works.append(dist.all_reduce(seg, op=dist.ReduceOp.SUM, async_op=True))
+        for bk, w in zip(self.buckets, works):
+            w.wait()
+            if bk.wire is not None:
+                self.flat.grad[bk.start:bk.end].copy_(bk.wire)
+                bk.wire = None
+            self._update(bk.start, bk.end)
 
 
 class FusionTrainer:
@@ -434,25 +458,49 @@ class FusionTrainer:
         self.v = torch.zeros_like(self.flat.data)
         self.t = 0
         self.world = world_size
+        # step count and hyper-parameters live in device memory for the eager step as well: the eager and the
+        # graph-replayed step then run the SAME optimizer arithmetic (bias corrections in fp32 on the device), so their
+        # parameters stay bit-identical - the head's gradients are ill-conditioned enough (LayerNorm over 32 post-ReLU
+        # values) for a one-ulp difference in a weight to move some gradients by 1e-3
+        dev = self.flat.data.device
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.hyper_dev = torch.tensor([lr, betas[0], betas[1], eps, weight_decay, 1.0 / max(world_size, 1)],
+                                      dtype=torch.float32, device=dev)
+        self._gather = GradGather(self.flat) if self.flat.grad.is_cuda else None
+        self._table_eager = self._gather.new_table() if self._gather else None
+        self._table_graph = self._gather.new_table() if self._gather else None
+        self._captured_ptrs = None
 
     def _forward_backward(self, feats, edges, labels, masks, use_types=None, mix: bool = True):
         from .multimodal.my_mae_model import fusion_objective
-        self.flat.attach_grad_views()
-        self.flat.grad.zero_()
+        gather = self._gather is not None
+        if gather:      # autograd keeps each parameter's gradient tensor (no accumulate kernel); ONE launch copies them all
+            self.flat.detach_grads()
+        else:
+            self.flat.attach_grad_views()
+            self.flat.grad.zero_()
         out = self.head.forward_batch(feats, edges, self.train_types, use_types or self.train_types, masks, mix)
         loss = fusion_objective(out, labels, masks)
         loss.backward()
+        if gather:
+            ptrs = self._gather.pointers()
+            if torch.cuda.is_current_stream_capturing():
+                self._captured_ptrs = ptrs              # the table is filled right after the capture ends
+                self._gather.launch(self._table_graph)
+            else:
+                self._table_eager.copy_(torch.tensor(ptrs, dtype=torch.int64))
+                self._gather.launch(self._table_eager)
         return loss.detach()
 
     def step(self, feats, edges, labels: torch.Tensor, masks, use_types=None, mix: bool = True) -> torch.Tensor:
         """feats[m]: ``[G, nodes_m, 1024]`` node features of this rank's G patients; masks: bool ``[G, T]`` (True =
         masked modality).  Returns this rank's loss (device scalar, no host sync)."""
+        self.step_dev.add_(1)
         loss = self._forward_backward(feats, edges, labels, masks, use_types, mix)
         if self.world > 1:
             dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM)
         self.t += 1
-        get_backend().adam_step(self.flat.data, self.flat.grad, self.m, self.v, self.lr, self.betas[0], self.betas[1],
-                                self.eps, self.wd, self.t, 1.0 / self.world)
+        get_backend().adam_step_dev(self.flat.data, self.flat.grad, self.m, self.v, self.hyper_dev, self.step_dev)
         return loss
 
     # ------------------------------------------------------------------ CUDA-graph step
@@ -468,9 +516,6 @@ class FusionTrainer:
         self.s_edges = edges
         self.s_labels = labels.clone()
         self.plan = MaskPlan(masks, dev)
-        self.step_dev = torch.full((1,), self.t, dtype=torch.int32, device=dev)
-        self.hyper_dev = torch.tensor([self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 1.0 / self.world],
-                                      dtype=torch.float32, device=dev)
 
         def body():
             self.step_dev.add_(1)
@@ -492,6 +537,9 @@ class FusionTrainer:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.s_loss = body()
+        if self._captured_ptrs is not None:
+            self._table_graph.copy_(torch.tensor(self._captured_ptrs, dtype=torch.int64))
+            self._captured_ptrs = None
         # (the capture itself does not execute: step_dev still equals the number of steps taken)
         return self
 

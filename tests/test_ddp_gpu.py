@@ -1,5 +1,6 @@
 """Two-GPU NCCL tests of the data-parallel step: the bucketed all-reduce that
-``SegTrainer`` starts from its gradient hooks - eagerly and INSIDE the captured CUDA graph - must leave on every rank the
+``SegTrainer`` starts from its gradient hooks in the eager step, and the per-bucket all-reduce + optimizer pipeline that
+follows a replay of the captured step, must leave on every rank the
 sum of the shards' single-process gradients, and both ranks must take the same optimizer step.  Skipped on a box with one
 GPU (the world_size-2 gloo tests in tests/test_engine_cpu.py cover the host logic there)."""
 import os
@@ -53,7 +54,9 @@ def _worker(rank, world, port, out_dir, mode):
     assert len(tr.buckets) >= 3
     start = tr.flat.data.clone()
     if mode == "graph":
-        tr.capture(imgs, pngs, None, warmup=1)          # one real step, then the capture (NCCL inside the graph)
+        # one real step, then the capture; the collective runs after each replay, pipelined with the optimizer per bucket
+        # (recording NCCL inside the graph is opt-in: it hung at replay on the 2 x B200 box, profiles/r02_multigpu_notes.txt)
+        tr.capture(imgs, pngs, None, warmup=1, comm_in_graph=os.environ.get("CERVIX_COMM_IN_GRAPH") == "1")
         tr.step_graphed(imgs, pngs)
         grad = tr.flat.grad.clone()
         tr.set_lr(1e-3)

@@ -240,13 +240,15 @@ def test_graph_captured_train_step_equals_eager(types):
     for f, l, m in batches[1:]:
         le = float(eager.step(f, edges, l, m))
         lg = float(graphed.step_graphed(f, l, m))
-        assert abs(le - lg) <= 2e-4 * abs(le), (le, lg)
+        assert abs(le - lg) <= 1e-6 * abs(le), (le, lg)
     assert graphed.t == eager.t == 5
-    # The head's reductions have a fixed summation order (csrc/rowops.cu, colreduce.cuh, conv_simt.cu), so both trainers
-    # see the same gradients; what is left is adam_step (host scalars) against adam_step_dev (device scalars).
+    # Every reduction of the head has a fixed summation order (csrc/rowops.cu, linear_grouped.cu) and both trainers run the
+    # same device-scalar Adam kernel, so the two trajectories must coincide to the last bit.  (r01's version of this test
+    # compared host-scalar against device-scalar Adam at 2e-5: a one-ulp difference in a weight moves some gradients of
+    # this head by 1e-3 - LayerNorm over 32 post-ReLU values is that ill-conditioned - and the test failed on and off.)
     delta = (eager.flat.data - graphed.flat.data).abs()
     diff = float(delta.max())
-    if diff >= 2e-5:
+    if diff > 1e-7:
         names = [n for n, _ in eager.head.named_parameters()]
         worst = []
         for n, p, o in zip(names, eager.flat.params, eager.flat.offsets):
