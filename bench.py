@@ -292,8 +292,9 @@ def classifier_throughput(steps: int, warmup: int, patients: int = 16, size: int
 
         # the head's step is ~600 launches of a few microseconds: captured once as a CUDA graph (new masks, dropout
         # streams and Adam step count reach every replay through device memory), eager with --no-graph
-        for _ in range(max(warmup, 4)):          # untimed encoder passes (allocator, lazy weight folding, clocks)
-            encode()
+        for _ in range(max(warmup, 4) if results else 30):   # untimed encoder passes (allocator, lazy weight folding); the
+            encode()                                         # first variant also burns in ~1 s so that the clocks / power
+                                                             # state left by the segmentation leg do not land in its timing
         torch.cuda.synchronize()
         if use_graph:
             trainer.capture(encode(), edges, labels, masks, warmup=max(warmup, 1))

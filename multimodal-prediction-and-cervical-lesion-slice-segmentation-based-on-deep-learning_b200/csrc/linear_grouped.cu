@@ -17,10 +17,11 @@
 // so the head's gradients stay bit-reproducible.  Weights are consumed in nn.Linear's own [out, in] layout: nothing is
 // packed, transposed or unpacked around the GEMM.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace cvx {
 
-constexpr int kGM = 64, kGN = 64, kGK = 32;   // two 16-deep fragments per operand and iteration: 8 loads in flight per thread
+constexpr int kGN = 64, kGK = 32;   // two 16-deep fragments per operand and iteration: 8 loads in flight per thread
 
 struct GemmBatch {
   cvx_gemm_problem p[CVX_MAX_GEMM_PROBLEMS];
@@ -28,41 +29,55 @@ struct GemmBatch {
   int count;
 };
 
-// stage a 64 (rows) x 16 (k) operand tile into registers: 4 elements per thread.  k-contiguous operands are read as 4
-// consecutive k of one row (16-byte segments), row-contiguous operands as 4 consecutive rows of one k.
+// stage a ROWS x 16 (k) slice of an operand tile into registers: 4 elements per thread of a 64-row slice (256 threads),
+// or of a 32-row slice when only threads 0..127 take part.  k-contiguous operands are read as 4 consecutive k of one row
+// (16-byte segments), row-contiguous operands as 4 consecutive rows of one k.
 struct Frag { float v[4]; };
 
 __device__ __forceinline__ Frag load_frag(const float* __restrict__ base, int64_t ld_r, int64_t ld_k, int r0, int rows,
-                                          int k0, int K, int t) {
+                                          int k0, int K, int t, int tile_rows) {
   Frag f;
   if (ld_k == 1) {
     const int r = r0 + (t >> 2), k = k0 + (t & 3) * 4;
+    const bool in = (t >> 2) < tile_rows && r < rows;
     const float* ptr = base + (int64_t)r * ld_r + k;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) f.v[i] = (r < rows && k + i < K) ? __ldg(ptr + i) : 0.f;
+    for (int i = 0; i < 4; ++i) f.v[i] = (in && k + i < K) ? __ldg(ptr + i) : 0.f;
   } else {
-    const int k = k0 + (t >> 4), r = r0 + (t & 15) * 4;
+    const int q = tile_rows >> 2;                          // threads per k: 16 (64 rows) or 8 (32 rows)
+    const int k = k0 + t / q, r = r0 + (t % q) * 4;
+    const bool in = t / q < 16 && k < K;
     const float* ptr = base + (int64_t)k * ld_k + (int64_t)r * ld_r;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) f.v[i] = (k < K && r + i < rows) ? __ldg(ptr + (int64_t)i * ld_r) : 0.f;
+    for (int i = 0; i < 4; ++i) f.v[i] = (in && r + i < rows) ? __ldg(ptr + (int64_t)i * ld_r) : 0.f;
   }
   return f;
 }
 
-__device__ __forceinline__ void store_frag(float (*S)[kGM + 4], const Frag& f, bool k_contig, int t) {
+template <int ROWS>
+__device__ __forceinline__ void store_frag(float (*S)[ROWS + 4], const Frag& f, bool k_contig, int t) {
   if (k_contig) {
     const int r = t >> 2, k = (t & 3) * 4;
+    if (r < ROWS) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) S[k + i][r] = f.v[i];
+      for (int i = 0; i < 4; ++i) S[k + i][r] = f.v[i];
+    }
   } else {
-    const int k = t >> 4, r = (t & 15) * 4;
+    constexpr int q = ROWS / 4;
+    const int k = t / q, r = (t % q) * 4;
+    if (k < 16) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) S[k][r + i] = f.v[i];
+      for (int i = 0; i < 4; ++i) S[k][r + i] = f.v[i];
+    }
   }
 }
 
+// BM = 64: 4 x 4 outputs per thread.  BM = 32: 2 x 4 outputs per thread - twice the tiles for layers whose 64-row tiling
+// would leave most of the 148 SMs with one or two CTAs (the auto-encoder's and the heads' GEMMs have 24 - 200 tiles).
+template <int BM>
 __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const __grid_constant__ GemmBatch batch) {
-  __shared__ float As[kGK][kGM + 4];
+  constexpr int TM = BM / 16;
+  __shared__ float As[kGK][BM + 4];
   __shared__ float Bs[kGK][kGN + 4];
   pdl_trigger();
   // which problem does this tile belong to?  (<= 16 entries: a linear scan of kernel parameters)
@@ -71,54 +86,63 @@ __global__ void __launch_bounds__(256, 2) gemm_grouped_kernel(const __grid_const
   const cvx_gemm_problem& P = batch.p[pi];
   const int tile = blockIdx.x - batch.tile_start[pi];
   const int tiles_n = (P.n + kGN - 1) / kGN;
-  const int m0 = (tile / tiles_n) * kGM, n0 = (tile % tiles_n) * kGN;
+  const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * kGN;
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   const bool a_kc = P.lda_k == 1, b_kc = P.ldb_k == 1;
 
-  float acc[4][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  float rs[4] = {0.f, 0.f, 0.f, 0.f};                      // row sums of A (bias gradient of the wgrad problems)
+  float rs[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) rs[i] = 0.f;                // row sums of A (bias gradient of the wgrad problems)
   const bool want_rs = P.rowsum != nullptr && n0 == 0 && tx == 0;
   pdl_wait();
 
   // software pipeline: the loads of k-block i+1 (two 16-deep fragments per operand) are in flight while block i is multiplied
-  Frag fa0 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, 0, P.k, t), fa1 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, 16, P.k, t);
-  Frag fb0 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, 0, P.k, t), fb1 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, 16, P.k, t);
+  Frag fa0 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, 0, P.k, t, BM), fa1 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, 16, P.k, t, BM);
+  Frag fb0 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, 0, P.k, t, kGN), fb1 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, 16, P.k, t, kGN);
   for (int k0 = 0; k0 < P.k; k0 += kGK) {
-    store_frag(As, fa0, a_kc, t);
-    store_frag(As + 16, fa1, a_kc, t);
-    store_frag(Bs, fb0, b_kc, t);
-    store_frag(Bs + 16, fb1, b_kc, t);
+    store_frag<BM>(As, fa0, a_kc, t);
+    store_frag<BM>(As + 16, fa1, a_kc, t);
+    store_frag<kGN>(Bs, fb0, b_kc, t);
+    store_frag<kGN>(Bs + 16, fb1, b_kc, t);
     __syncthreads();
     if (k0 + kGK < P.k) {
-      fa0 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, k0 + kGK, P.k, t);
-      fa1 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, k0 + kGK + 16, P.k, t);
-      fb0 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, k0 + kGK, P.k, t);
-      fb1 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, k0 + kGK + 16, P.k, t);
+      fa0 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, k0 + kGK, P.k, t, BM);
+      fa1 = load_frag(P.a, P.lda_m, P.lda_k, m0, P.m, k0 + kGK + 16, P.k, t, BM);
+      fb0 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, k0 + kGK, P.k, t, kGN);
+      fb1 = load_frag(P.b, P.ldb_n, P.ldb_k, n0, P.n, k0 + kGK + 16, P.k, t, kGN);
     }
     const int kmax = P.k - k0 < kGK ? ((P.k - k0 + 3) & ~3) : kGK;   // short last block: skip the all-zero tail
 #pragma unroll 8
     for (int kk = 0; kk < kmax; ++kk) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float av[TM];
+      if (TM == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        av[0] = a.x; av[1] = a.y; av[TM - 2] = a.z; av[TM - 1] = a.w;
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(&As[kk][ty * 2]);
+        av[0] = a.x; av[1] = a.y;
+      }
       const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
       if (want_rs) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rs[i] += av[i];
+        for (int i = 0; i < TM; ++i) rs[i] += av[i];
       }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= P.m) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -137,19 +161,27 @@ extern "C" int cvx_gemm_grouped(const cvx_gemm_problem* problems, int count, voi
   CVX_CHECK_ARG(problems && count > 0 && count <= CVX_MAX_GEMM_PROBLEMS, "gemm_grouped: 1..%d problems per launch (got %d)",
                 CVX_MAX_GEMM_PROBLEMS, count);
   GemmBatch batch;
-  int tiles = 0;
+  int tiles64 = 0;
   for (int i = 0; i < count; ++i) {
     const cvx_gemm_problem& p = problems[i];
     CVX_CHECK_ARG(p.a && p.b && p.c && p.m > 0 && p.n > 0 && p.k > 0, "gemm_grouped: problem %d has a null operand or an empty shape", i);
     CVX_CHECK_ARG((p.lda_k == 1 || p.lda_m == 1) && (p.ldb_k == 1 || p.ldb_n == 1) && p.ldc >= p.n,
                   "gemm_grouped: problem %d: each operand must be contiguous along rows or along k", i);
     batch.p[i] = p;
+    tiles64 += ((p.m + 63) / 64) * ((p.n + kGN - 1) / kGN);
+  }
+  // 64-row tiles when they already give every SM two CTAs, else 32-row tiles (twice as many, same arithmetic order)
+  static const int force_bm = [] { const char* e = getenv("CERVIX_GEMM_BM"); return e ? atoi(e) : 0; }();
+  const int bm = force_bm == 32 || force_bm == 64 ? force_bm : (tiles64 >= 2 * kNumSMs ? 64 : 32);
+  int tiles = 0;
+  for (int i = 0; i < count; ++i) {
     batch.tile_start[i] = tiles;
-    tiles += ((p.m + kGM - 1) / kGM) * ((p.n + kGN - 1) / kGN);
+    tiles += ((batch.p[i].m + bm - 1) / bm) * ((batch.p[i].n + kGN - 1) / kGN);
   }
   batch.tile_start[count] = tiles;
   batch.count = count;
-  launch_pdl(gemm_grouped_kernel, dim3(tiles), dim3(256), 0, as_stream(stream), batch);
+  if (bm == 64) launch_pdl(gemm_grouped_kernel<64>, dim3(tiles), dim3(256), 0, as_stream(stream), batch);
+  else launch_pdl(gemm_grouped_kernel<32>, dim3(tiles), dim3(256), 0, as_stream(stream), batch);
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

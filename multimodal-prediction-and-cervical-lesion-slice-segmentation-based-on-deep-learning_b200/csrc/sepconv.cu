@@ -319,7 +319,8 @@ int cvx_bn_bwd_sums(const void* dy, const void* y, const void* p, double* sums, 
   CVX_CHECK_ARG(dy && p && sums && (act == CVX_ACT_NONE || y) && rows > 0 && c > 0 && c % 8 == 0, "bn_bwd_sums: bad arguments");
   cudaStream_t st = as_stream(stream);
   CVX_WS_ZERO(sums, sizeof(double) * 2 * c, st);
-  return colreduce_launch<__nv_bfloat16, BnRawBwdF, 256, 3>(
+  // four resident 256-thread blocks per SM (61 registers): 42 -> 36 us on the middle-flow tensor against three
+  return colreduce_launch<__nv_bfloat16, BnRawBwdF, 256, 4>(
       BnRawBwdF{(const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)p, c, act}, rows, c, sums, st);
 }
 

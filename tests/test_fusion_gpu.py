@@ -264,6 +264,87 @@ def test_graph_captured_train_step_equals_eager(types):
     assert abs(a - b) > 1e-6
 
 
+def test_gemm_grouped_matches_spec():
+    """cvx_gemm_grouped against fp64 matmuls: the three operand layouts the head uses (forward = both k-contiguous, data
+    gradient = B row-contiguous, weight gradient = both row-contiguous + the row sums that are the bias gradient), ragged
+    sizes, several problems of different shapes in one launch, outputs written into row blocks of a stacked tensor."""
+    B = get_backend()
+    shapes = [(96, 512, 1024), (24, 128, 512), (7, 1, 128), (64, 1512, 512), (33, 4, 8), (130, 70, 50)]
+    xs = [rnd(m, k, seed=10 + i) for i, (m, n, k) in enumerate(shapes)]
+    ws = [rnd(n, k, seed=40 + i, scale=0.1) for i, (m, n, k) in enumerate(shapes)]
+    bs = [rnd(n, seed=70 + i) for i, (m, n, k) in enumerate(shapes)]
+    ys = [torch.empty(m, n, device="cuda") for (m, n, k) in shapes]
+    B.gemm_grouped([dict(a=x, b=w, c=y, bias=b, m=m, n=n, k=k, lda_m=k, lda_k=1, ldb_n=k, ldb_k=1, ldc=n)
+                    for x, w, b, y, (m, n, k) in zip(xs, ws, bs, ys, shapes)])
+    for x, w, b, y in zip(xs, ws, bs, ys):
+        close(y, (x.double() @ w.double().t() + b.double()).float(), 2e-6)
+    dys = [rnd(m, n, seed=100 + i) for i, (m, n, k) in enumerate(shapes)]
+    dxs = [torch.empty(m, k, device="cuda") for (m, n, k) in shapes]
+    B.gemm_grouped([dict(a=dy, b=w, c=dx, m=m, n=k, k=n, lda_m=n, lda_k=1, ldb_n=1, ldb_k=k, ldc=k)
+                    for dy, w, dx, (m, n, k) in zip(dys, ws, dxs, shapes)])
+    for dy, w, dx in zip(dys, ws, dxs):
+        close(dx, (dy.double() @ w.double()).float(), 2e-6)
+    dws = [torch.empty(n, k, device="cuda") for (m, n, k) in shapes]
+    dbs = [torch.empty(n, device="cuda") for (m, n, k) in shapes]
+    B.gemm_grouped([dict(a=dy, b=x, c=dw, rowsum=db, m=n, n=k, k=m, lda_m=1, lda_k=n, ldb_n=1, ldb_k=k, ldc=k)
+                    for dy, x, dw, db, (m, n, k) in zip(dys, xs, dws, dbs, shapes)])
+    for dy, x, dw, db in zip(dys, xs, dws, dbs):
+        close(dw, (dy.double().t() @ x.double()).float(), 2e-6)
+        close(db, dy.double().sum(0).float(), 2e-6)
+    # row blocks of one stacked output, each block with its own weight (the per-modality layer)
+    stack_in, out = rnd(3 * 40, 64, seed=5), torch.empty(3 * 40, 32, device="cuda")
+    w3 = [rnd(32, 64, seed=200 + i) for i in range(3)]
+    B.gemm_grouped([dict(a=stack_in[i * 40:(i + 1) * 40], b=w3[i], c=out[i * 40:(i + 1) * 40], m=40, n=32, k=64, lda_m=64,
+                         lda_k=1, ldb_n=64, ldb_k=1, ldc=32) for i in range(3)])
+    for i in range(3):
+        close(out[i * 40:(i + 1) * 40], (stack_in[i * 40:(i + 1) * 40].double() @ w3[i].double().t()).float(), 2e-6)
+
+
+@pytest.mark.parametrize("order", ["gm", "mg"])
+def test_segment_table_operators_match_spec(order):
+    """The all-modalities-at-once kernels (segment-table LayerNorm with per-modality affine, gated pooling, token
+    broadcast) against the per-segment plain-torch specification, for both segment orders, ragged node counts."""
+    B = get_backend()
+    G, nodes, C = 5, [16, 16, 4, 7], 256
+    tab = R.SegTable(G, nodes, order, torch.device("cuda"))
+    ctab = R.SegTable(G, nodes, order, torch.device("cpu"))
+    x, dy = rnd(tab.rows, C, seed=1), rnd(tab.rows, C, seed=2)
+    ws = [rnd(C, seed=10 + i) + 1 for i in range(4)]
+    bs = [rnd(C, seed=20 + i) for i in range(4)]
+    cpu = lambda t: [v.cpu() for v in t] if isinstance(t, list) else t.cpu()   # noqa: E731
+    for mode in (0, 1):
+        y, stats = B.segtab_layernorm_fwd(x, ws, bs, tab, 1e-5, mode)
+        yr, _ = EMU.segtab_layernorm_fwd(cpu(x), cpu(ws), cpu(bs), ctab, 1e-5, mode)
+        close(y.cpu(), yr)
+        dx, dws, dbs = B.segtab_layernorm_bwd(dy, x, ws, stats, tab, 1e-5, mode)
+        dxr, dwr, dbr = EMU.segtab_layernorm_bwd(cpu(dy), cpu(x), cpu(ws), None, ctab, 1e-5, mode)
+        close(dx.cpu(), dxr, 2e-5)
+        for a, b in zip(dws + dbs, dwr + dbr):
+            close(a.cpu(), b, 2e-5)
+    gate = rnd(tab.rows, seed=3)
+    pooled, att = B.segtab_gate_pool_fwd(x, gate, tab)
+    pr, ar = EMU.segtab_gate_pool_fwd(cpu(x), cpu(gate), ctab)
+    close(pooled.cpu(), pr); close(att.cpu(), ar)
+    dpool = rnd(tab.segments, C, seed=4)
+    gx, gg = B.segtab_gate_pool_bwd(dpool, x, att, tab)
+    gxr, ggr = EMU.segtab_gate_pool_bwd(cpu(dpool), cpu(x), ar, ctab)
+    close(gx.cpu(), gxr); close(gg.cpu(), ggr, 2e-5)
+    T = 3
+    tok = [-1] * tab.segments
+    seg_of_tok = [-1] * (G * T)
+    for g in range(G):
+        for j, m in enumerate((0, 2, 3)):                  # modality 1 takes no token
+            tok[tab.seg_id(m, g)] = g * T + j
+            seg_of_tok[g * T + j] = tab.seg_id(m, g)
+    t = rnd(G * T, C, seed=6)
+    tok_d = torch.tensor(tok, dtype=torch.int32, device="cuda")
+    sot_d = torch.tensor(seg_of_tok, dtype=torch.int32, device="cuda")
+    yb = B.segtab_bcast_add(x, t, tab, tok_d)
+    close(yb.cpu(), EMU.segtab_bcast_add(cpu(x), cpu(t), ctab, tok_d.cpu()))
+    dt = B.segtab_bcast_add_bwd(dy, tab, sot_d, G * T)
+    close(dt.cpu(), EMU.segtab_bcast_add_bwd(cpu(dy), ctab, sot_d.cpu(), G * T), 2e-5)
+
+
 def test_head_train_step_is_bit_reproducible():
     """Two trainers built from the same seed and fed the same batches end with IDENTICAL parameters: every reduction of
     the head (LayerNorm affine gradients, token scatter, objective, linear weight / bias gradients) sums in a fixed
