@@ -508,6 +508,87 @@ def kernel_rooflines(batch: int, peaks):
     return out, hbm
 
 
+def fit_one_epoch_throughput(model, imgs_h, pngs_h, labels_h, steps: int):
+    """Images/s of the drop-in ``fit_one_epoch`` on the same model: torch.optim.Adam handed in as the reference's train.py
+    does, pinned host batches, fp16=True (-> bf16 engine).  Two epochs: the first captures the graph, the second is timed."""
+    import contextlib
+    import io
+    import tempfile
+    import numpy as np
+    import torch
+    from cervix_b200.utils.utils_fit import fit_one_epoch
+
+    class _Hist:
+        val_loss: list = []
+
+        def append_loss(self, *a):
+            pass
+
+    class _Ev:
+        def on_epoch_end(self, *a):
+            pass
+
+    opt = torch.optim.Adam(model.parameters(), 1e-4, betas=(0.9, 0.999), weight_decay=0)
+    cls_w = np.array(CLS_WEIGHTS, np.float32)
+    batch = (imgs_h, pngs_h, labels_h)
+    val = [(imgs_h[:2], pngs_h[:2], labels_h[:2])]
+    stamps = {}
+    first = 6       # the graph is captured while the third batch is being stepped (~1 s of host time): start the clock at
+                    # the seventh pull, when that is safely over
+
+    def gen(n):
+        # fit_one_epoch pulls batch i one step ahead of issuing step i-1 (BatchPrefetcher) and pulls one element past
+        # epoch_step to see the end; a device sync at pull a and at pull b therefore brackets exactly b - a steps
+        for i in range(n + 1):
+            if i == first or i == n:
+                torch.cuda.synchronize()
+                stamps[i] = time.perf_counter()
+            yield batch
+
+    with tempfile.TemporaryDirectory() as save_dir, contextlib.redirect_stdout(io.StringIO()), \
+            contextlib.redirect_stderr(io.StringIO()):
+        n = steps + first
+        fit_one_epoch(model, model, _Hist(), _Ev(), opt, 0, n, 1, gen(n), val, 3, True, True, True, cls_w, 5, True, None, 1000,
+                      save_dir, 0)
+    sec = (stamps[n] - stamps[first]) / (n - first)
+    tr = getattr(model, "_cvx_trainer", None)
+    engine = "SegTrainer (CUDA graph)" if tr is not None and tr.graph is not None else "eager autograd + optimizer.step()"
+    if tr is not None:
+        tr.close()
+        model._cvx_trainer = None
+    return {"value": imgs_h.shape[0] / sec, "unit": UNIT, "steps": n - first, "ms_per_step": sec * 1e3,
+            "engine": engine,
+            "what": "utils.utils_fit.fit_one_epoch(model, torch.optim.Adam, ...) on pinned host batches (fp32 images, int64 "
+                    "class maps, fp32 one-hot labels as the reference's loader yields them), device-synchronised wall clock "
+                    "over the steady-state steps of the training phase"}
+
+
+def strong_scaling_leg(model, bsz: int, size: int, world: int, rank: int, steps: int, comm_in_graph: bool):
+    import torch
+    import torch.distributed as dist
+    from cervix_b200.engine import SegTrainer
+    trainer = SegTrainer(model, lr=1e-4, betas=(0.9, 0.999), cls_weights=CLS_WEIGHTS, num_classes=5, world_size=world)
+    imgs, pngs, _ = synthetic_batch(bsz, size, seed=100 + rank)
+    imgs, pngs = imgs.cuda(), pngs.cuda()
+    trainer.capture(imgs, pngs, None, comm_in_graph=comm_in_graph)
+    for _ in range(3):
+        trainer.step_graphed(imgs, pngs)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        trainer.step_graphed(imgs, pngs)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    trainer.close()
+    del trainer
+    return {"value": world * bsz / (ms * 1e-3), "unit": UNIT, "global_batch": world * bsz, "per_gpu_batch": bsz, "ms_per_step": ms,
+            "scaling": "strong (BASELINE configs[3]: global batch 256)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -627,9 +708,24 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e, ms_e2e_f32 = float(t[0]), float(t[1]), float(t[2])
+    # ---- the reference's own entry point: fit_one_epoch(model, torch.optim.Adam, pinned host batches in the loader's
+    # contract: fp32 images, int64 class maps, fp32 one-hot labels) - the drop-in routes it onto the same engine
+    # (utils_fit.py:31-198; single GPU only: under torchrun the scripts wrap the model in DDP first)
+    fit_ips = None
+    trainer.close()
+    del step_fn, trainer
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_fit:
+        fit_ips = fit_one_epoch_throughput(model, imgs_h, pngs_h, labels_h, max(args.steps, 12))
+    # ---- BASELINE configs[3] as written: GLOBAL batch 256 split over the ranks (train.py:499 `batch_size // ngpus`);
+    # the main line is weak scaling at 32 images per GPU (identical at N = 8).  N = 4 -> 64 images per GPU is timed here;
+    # N = 2 -> 128 per GPU needs ~140 GB of saved activations and is not attempted.
+    strong = None
+    if world > 1 and 256 % world == 0 and 32 < 256 // world <= 64 and not args.no_strong:
+        strong = strong_scaling_leg(model, 256 // world, size, world, rank, args.steps, comm_in_graph)
     classifier = None
     if not args.no_classifier:      # every rank takes part (patients are sharded, head gradients all-reduced)
-        del step_fn, trainer, model
+        del model
         torch.cuda.empty_cache()
         classifier = classifier_throughput(max(args.steps, 20), 3, patients=16 if world == 1 else 64,
                                            world=world, rank=rank,
@@ -694,6 +790,8 @@ def run_ours(args):
                 "fp32_contract": {"value": e2e_f32_value, "h2d_bytes_per_step": imgs_h.numel() * 4 + pngs_h.numel() * 8,
                                   "ms_per_step": ms_e2e_f32 / args.steps,
                                   "inputs": "pinned host fp32 NCHW images + int64 class maps (utils_fit.py:52-58)"}},
+        "fit_one_epoch": fit_ips,
+        "configs3_global_batch_256": strong,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "classifier": classifier,
@@ -716,6 +814,8 @@ def main():
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch run of the reference on this GPU")
     ap.add_argument("--no-classifier", action="store_true", help="skip the severity-classifier leg")
     ap.add_argument("--no-graph", action="store_true", help="run the single-GPU step eagerly instead of as a CUDA graph")
+    ap.add_argument("--no-fit", action="store_true", help="skip the fit_one_epoch (reference entry point) leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the configs[3] global-batch-256 leg at N = 4")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -154,6 +154,7 @@ class SegTrainer:
             for buf in model.buffers():
                 dist.broadcast(buf.data, 0)
         self._hooked = set()                            # hooks can only be put on parameters that require grad
+        self._hook_handles = []
         self._hooks_live = False
         self.refresh_trainable()
 
@@ -173,7 +174,7 @@ class SegTrainer:
                 self._t_start.setdefault(i, self.t)
                 if i not in self._hooked:
                     self._hooked.add(i)
-                    flat.params[i].register_post_accumulate_grad_hook(self._make_hook(i))
+                    self._hook_handles.append(flat.params[i].register_post_accumulate_grad_hook(self._make_hook(i)))
             else:
                 self._t_start.pop(i, None)
                 flat.params[i].grad = None
@@ -215,6 +216,17 @@ class SegTrainer:
         self.graph = None
         self._graph_key = None
         return True
+
+    def close(self):
+        """Detach from the model: remove the gradient hooks (they hold the trainer - and its captured graph's memory pool -
+        alive) and drop the graph.  The parameters keep living in the flat buffer."""
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles, self._hooked = [], set()
+        self.graph = None
+        self._graph_key = None
+        for bk in self.buckets:
+            bk.gather = bk.table_eager = bk.table_graph = None
 
     # ------------------------------------------------------------------ data parallel
     def _make_hook(self, i):

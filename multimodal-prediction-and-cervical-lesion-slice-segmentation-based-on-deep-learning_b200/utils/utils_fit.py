@@ -78,6 +78,20 @@ def _to_device(batch, cls_weights, cuda, local_rank):
     return imgs, pngs, labels, weights
 
 
+_FIT_STREAMS = {}
+
+
+def _fit_stream(device):
+    """The whole fast training phase runs on ONE dedicated non-default stream per device: autograd's AccumulateGrad nodes
+    remember the stream they were created on, and a node that lives on the legacy default stream cannot take part in a
+    later CUDA-graph capture (cudaErrorStreamCaptureImplicit: "would make the legacy stream depend on a capturing
+    blocking stream")."""
+    key = (device.type, device.index)
+    if key not in _FIT_STREAMS:
+        _FIT_STREAMS[key] = torch.cuda.Stream(device)
+    return _FIT_STREAMS[key]
+
+
 _TRAINER_STATE = "last_epoch_trainer_state.pth"
 _EAGER_STEPS_BEFORE_CAPTURE = 2     # lazy initialisation (kernel attributes, allocator, NCCL) happens in real steps
 
@@ -116,6 +130,8 @@ def _fast_trainer(model_train, optimizer, cuda, dice_loss, focal_loss, cls_weigh
     key = (id(optimizer), kind, bool(dice_loss), bool(focal_loss), world, tuple(float(w) for w in cls_weights))
     tr = getattr(net, "_cvx_trainer", None)
     if tr is None or getattr(tr, "_fit_key", None) != key:
+        if tr is not None:
+            tr.close()          # another optimizer / objective took over: release the old trainer's hooks and graph
         tr = SegTrainer(net, lr=g["lr"], weight_decay=g["weight_decay"], optimizer=kind, cls_weights=cls_weights,
                         num_classes=num_classes, dice=bool(dice_loss), focal=bool(focal_loss), world_size=world, **kw)
         tr._fit_key = key
@@ -191,11 +207,19 @@ def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, ep
     model_train.train()
     run_loss = run_fs = None
     steps = 0
-    trainer = _fast_trainer(model_train, optimizer, cuda, dice_loss, focal_loss, cls_weights, num_classes, save_dir, epoch)
-    if trainer is not None:
-        total_fast = _train_phase_fast(trainer, gen, epoch_step, cuda, local_rank, cls_weights, num_classes, dice_loss,
-                                       focal_loss, bar, main, optimizer)
-        gen = ()
+    trainer = None
+    if cuda and torch.cuda.is_available():
+        dev = torch.device("cuda", local_rank)
+        side, cur = _fit_stream(dev), torch.cuda.current_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            trainer = _fast_trainer(model_train, optimizer, cuda, dice_loss, focal_loss, cls_weights, num_classes, save_dir,
+                                    epoch)
+            if trainer is not None:
+                total_fast = _train_phase_fast(trainer, gen, epoch_step, cuda, local_rank, cls_weights, num_classes,
+                                               dice_loss, focal_loss, bar, main, optimizer)
+                gen = ()
+        cur.wait_stream(side)
     for iteration, batch in enumerate(gen):
         if iteration >= epoch_step:
             break
