@@ -85,6 +85,10 @@ class GradGather:
         ps = self.flat.params
         return [0 if ps[i].grad is None else ps[i].grad.data_ptr() for i in self.idx]
 
+    @staticmethod
+    def pointers_of(grads) -> List[int]:
+        return [0 if g is None else g.data_ptr() for g in grads]
+
     def launch(self, table: torch.Tensor):
         get_backend().multi_gather(table, self.chunk_tensor, self.chunk_start, self.dst_offsets, self.sizes, self.flat.grad)
 
@@ -215,6 +219,8 @@ class SegTrainer:
                 cur, idx = 0, []
         self.graph = None
         self._graph_key = None
+        self._split = False
+        self._graph_a = self._graph_b = self._split_keep = None
         return True
 
     def close(self):
@@ -225,6 +231,8 @@ class SegTrainer:
         self._hook_handles, self._hooked = [], set()
         self.graph = None
         self._graph_key = None
+        self._split = False
+        self._graph_a = self._graph_b = self._split_keep = None
         for bk in self.buckets:
             bk.gather = bk.table_eager = bk.table_graph = None
 
@@ -353,6 +361,128 @@ class SegTrainer:
             self.wd = wd
             self.hyper_dev[4:5].fill_(wd)
 
+    # ------------------------------------------------------------------ two-phase backward (data parallel, CUDA graphs)
+    _ENTRY_MODULES = ("conv1", "bn1", "conv2", "bn2", "block1", "block2", "block3")
+
+    def _split_plan(self):
+        """Parameter indices before / after the model's cut (``ops.cut_point`` at the end of Xception's entry flow), or None
+        when the model has no cut, a parameter is frozen, or the early parameters are not one leading run of the flat
+        buffer."""
+        names = [n for n, _ in self.model.named_parameters()]
+        if len(names) != len(self.flat.params) or not all(p.requires_grad for p in self.flat.params):
+            return None
+        early = [i for i, n in enumerate(names) if n.split(".")[0] == "backbone" and n.split(".")[1] in self._ENTRY_MODULES]
+        if not early or early != list(range(len(early))) or type(getattr(self.model, "backbone", None)).__name__ != "Xception":
+            return None
+        late = list(range(len(early), len(names)))
+        return early, late
+
+    def _phase_a(self, imgs, pngs, labels, late):
+        """Forward, objective, and the backward of everything AFTER the cut; gathers those gradients into the flat buffer."""
+        if pngs.dtype == torch.uint8:
+            pngs = get_backend().finish_batch_u8(None, pngs.contiguous(), self.num_classes, torch.float32)[1]
+        self.step_dev.add_(1)
+        self.step_devs.add_(1)
+        ops.set_step_counter(self.step_dev)
+        sink = {}
+        ops._CUT_SINK[0] = sink
+        try:
+            with ops.defer_batch_counters():
+                out = self.model(imgs)
+        finally:
+            ops._CUT_SINK[0] = None
+        if self.model.training and self._nbt:
+            torch._foreach_add_(self._nbt, 1)
+        ce, focal, dice, fs = seg_objective(out, pngs, labels, self.cls_weights, self.num_classes)
+        loss = (focal if self.focal else ce) + (dice if self.dice else 0.0)
+        tags = sorted(sink)
+        proxies = [sink[t][1] for t in tags]
+        grads = torch.autograd.grad(loss, proxies + [self.flat.params[i] for i in late], allow_unused=True)
+        self._split_cuts = ([sink[t][0] for t in tags], list(grads[:len(tags)]))
+        self._split_late_grads = grads[len(tags):]          # kept alive until the gather of the captured graph is recorded
+        self.last = torch.stack([ce.detach(), focal.detach(), dice.detach(), fs.detach()])
+        return self.last
+
+    def _phase_b(self, early):
+        """Backward of the part BEFORE the cut from the gradients phase A left at the cut tensors."""
+        outs, gouts = self._split_cuts
+        keep = [(o, g) for o, g in zip(outs, gouts) if g is not None]
+        grads = torch.autograd.grad([o for o, _ in keep], [self.flat.params[i] for i in early],
+                                    grad_outputs=[g for _, g in keep], allow_unused=True)
+        self._split_cuts = None
+        return grads
+
+    def capture_split(self, imgs: torch.Tensor, pngs: torch.Tensor, labels: Optional[torch.Tensor] = None, warmup: int = 3):
+        """Data-parallel CUDA-graph step with communication under backward, without recording NCCL in a graph: the step is
+        TWO graphs in one memory pool.  Graph A = forward + objective + backward down to the end of the entry flow + gather
+        of those gradients (97 % of the parameters: middle flow, exit flow, ASPP, decoder); graph B = backward of the entry
+        flow (3 % of the parameters, about a third of the backward time) + its gather.  Between the replays the host starts
+        the all-reduce of A's gradients, which then runs on NCCL's stream under graph B; what is left exposed is the
+        all-reduce of the entry flow's 6 MB.  Returns None (and captures nothing) when the model has no cut."""
+        self.refresh_trainable()
+        plan = self._split_plan()
+        if plan is None or not self._use_gather:
+            return None
+        early, late = plan
+        B = get_backend()
+        dev = self.flat.data.device
+        self.s_imgs, self.s_pngs = imgs.clone(), pngs.clone()
+        self.s_labels = None if labels is None else labels.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(self.s_imgs, self.s_pngs, self.s_labels)
+        torch.cuda.current_stream().wait_stream(side)
+        flat = self.flat
+        ga_late, ga_early = GradGather(flat, late), GradGather(flat, early)
+        t_late, t_early = ga_late.new_table(), ga_early.new_table()
+        self._split_ranges = ((flat.offsets[late[0]], flat.numel), (0, flat.offsets[late[0]]))
+        pool = torch.cuda.graph_pool_handle()
+        cap_stream = torch.cuda.Stream()
+        self._graph_a, self._graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        arena = getattr(B, "zero_arena_begin", None)
+        flat.detach_grads()
+        try:
+            with torch.cuda.graph(self._graph_a, pool=pool, stream=cap_stream):
+                if arena is not None:
+                    arena(dev)
+                self.s_out = self._phase_a(self.s_imgs, self.s_pngs, self.s_labels, late)
+                late_grads = self._split_late_grads
+                ga_late.launch(t_late)
+            with torch.cuda.graph(self._graph_b, pool=pool, stream=cap_stream):
+                early_grads = self._phase_b(early)
+                ga_early.launch(t_early)
+        finally:
+            if arena is not None:
+                B.zero_arena_end()
+        t_late.copy_(torch.tensor(GradGather.pointers_of(late_grads), dtype=torch.int64))
+        t_early.copy_(torch.tensor(GradGather.pointers_of(early_grads), dtype=torch.int64))
+        self._split_keep = (ga_late, ga_early, t_late, t_early, pool)
+        self._split_late_grads = None
+        self.graph = self._graph_a                       # "a captured step exists" for graph_matches / staleness checks
+        self._graph_key = (tuple(imgs.shape), imgs.dtype, tuple(pngs.shape), pngs.dtype,
+                           None if labels is None else tuple(labels.shape))
+        self._comm_in_graph = False
+        self._split = True
+        return self
+
+    def _step_split(self):
+        (lo_a, hi_a), (lo_b, hi_b) = self._split_ranges
+        g = self.flat.grad
+        self._graph_a.replay()
+        works = []
+        if self.world > 1:
+            works.append(dist.all_reduce(g[lo_a:hi_a], op=dist.ReduceOp.SUM, async_op=True))   # under graph B
+        self._graph_b.replay()
+        if self.world > 1:
+            works.append(dist.all_reduce(g[lo_b:hi_b], op=dist.ReduceOp.SUM, async_op=True))
+            works[0].wait()
+        self._update(lo_a, hi_a)
+        if self.world > 1:
+            works[1].wait()
+        self._update(lo_b, hi_b)
+
     # ------------------------------------------------------------------ checkpoint (optimizer + step state)
     def state_dict(self) -> dict:
         """Optimizer moments, step counts and hyper-parameters (the reference saves weights only, utils_fit.py:191-198; a
@@ -388,6 +518,7 @@ class SegTrainer:
         where each bucket completes, so that they overlap backward as in the eager step; with torch 2.11 / NCCL 2.28 on the
         2 x B200 box that capture hung at replay (profiles/r02_multigpu_notes.txt), so it is opt-in."""
         self.refresh_trainable()
+        self._split = False
         self._comm_in_graph = comm_in_graph or self.world == 1
         self.s_imgs, self.s_pngs = imgs.clone(), pngs.clone()
         self.s_labels = None if labels is None else labels.clone()
@@ -427,9 +558,12 @@ class SegTrainer:
         self.s_pngs.copy_(pngs, non_blocking=True)
         if self.s_labels is not None and labels is not None:
             self.s_labels.copy_(labels, non_blocking=True)
-        self.graph.replay()
-        if not self._comm_in_graph:
-            self._reduce_update_pipelined()
+        if getattr(self, "_split", False):
+            self._step_split()
+        else:
+            self.graph.replay()
+            if not self._comm_in_graph:
+                self._reduce_update_pipelined()
         self.t += 1
         return self.s_out
 

@@ -155,8 +155,11 @@ class Xception(nn.Module):
         x = ops.conv_bn_act(x, self.conv2.weight, 1, 1, 1, self.bn2, ops.ACT_RELU)
         x = self.block1(x)
         x = self.block2(x)
-        low_level = self.block2.hook_layer
+        low_level = ops.cut_point(self.block2.hook_layer, "low_level")
         x = self.block3(x, relu_out=True)            # block4 is an identity-skip block
+        # end of the entry flow: 3 % of the parameters are behind this point, ~35 % of the backward time (the 128^2 - 256^2
+        # tensors) - the data-parallel trainer all-reduces the other 97 % of the gradient under that part of backward
+        x = ops.cut_point(x, "entry_out")
         for i in range(4, 20):
             x = getattr(self, "block%d" % i)(x, inp_is_relu=True, relu_out=(i < 19))
         x = self.block20(x)

@@ -412,6 +412,23 @@ def to_nhwc(x, dtype):
     return ToNHWC.apply(x, dtype)
 
 
+# ---- cut points: tensors at which a trainer may split the backward pass into two phases (engine.SegTrainer, data
+# parallel: the all-reduce of the gradients produced by the first phase runs under the second phase).  When a sink is set,
+# the consumer side continues from a detached leaf copy (a view, no kernel), so the autograd graph falls apart into the
+# part after the cut (loss -> proxies, late parameters) and the part before it (original tensors -> early parameters);
+# the trainer feeds the proxies' gradients into the originals.  A no-op otherwise.
+_CUT_SINK = [None]
+
+
+def cut_point(x, tag: str):
+    sink = _CUT_SINK[0]
+    if sink is None or not torch.is_grad_enabled() or not x.requires_grad:
+        return x
+    proxy = x.detach().requires_grad_(True)
+    sink[tag] = (x, proxy)
+    return proxy
+
+
 def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1):
     return Conv2d.apply(x, weight, bias, stride, pad, dil)
 

@@ -250,3 +250,40 @@ def test_trainer_state_roundtrip_resumes_bit_exactly():
     assert torch.equal(la, lb)                        # same weights, fixed-order forward reductions: same losses
     # (the weight-gradient kernels accumulate split-K partials with fp32 atomics: equal to rounding, not to the bit)
     assert torch.allclose(a.flat.data, b.flat.data, rtol=0, atol=1e-5)
+
+
+def test_two_graph_split_backward_equals_the_single_backward():
+    """``capture_split`` (graph A: forward + backward down to the end of Xception's entry flow; graph B: the entry flow's
+    backward - the data-parallel step all-reduces A's gradients under B) against the ordinary one-graph step on one GPU.
+    The gradients are compared from IDENTICAL weights (lr = 0): on this 4 x 64 x 64 batch the train-mode network amplifies
+    a one-ulp weight difference into percent-level gradient changes within a step (two one-graph trainers differ as much,
+    tools/debug_split2.py), so trajectories cannot be compared.  The optimizer step of both ranges is then checked against
+    SGD written out by hand on the split trainer's own gradient."""
+    from cervix_b200.engine import SegTrainer
+    imgs, pngs, _ = _batches(1, bsz=4, size=64, seed=3)[0]
+    imgs, pngs = imgs.cuda(), pngs.cuda()
+    kw = dict(lr=0.0, optimizer="sgd", momentum=0.9, weight_decay=0.0, cls_weights=[1, 1, 5, 3, 4])
+    one = SegTrainer(_small_model(torch.float32, seed=2, bb="xception"), **kw).capture(imgs, pngs, None, warmup=1)
+    two = SegTrainer(_small_model(torch.float32, seed=2, bb="xception"), **kw).capture_split(imgs, pngs, None, warmup=1)
+    assert two is not None and two._split
+    (lo_a, hi_a), (lo_b, hi_b) = two._split_ranges
+    assert lo_b == 0 and hi_b == lo_a and hi_a == two.flat.numel and 0 < hi_b < 0.1 * hi_a      # the entry flow is small
+    assert torch.equal(one.flat.data, two.flat.data)
+    for step in range(2):
+        la, lb = one.step_graphed(imgs, pngs).clone(), two.step_graphed(imgs, pngs).clone()
+        assert torch.allclose(la, lb, rtol=1e-6, atol=1e-7), (step, la, lb)
+        ga, gb = one.flat.grad, two.flat.grad
+        assert float((ga - gb).abs().max()) <= 1e-5 * float(ga.abs().max()), step          # atomics order of the wgrads
+        assert float(gb[:hi_b].abs().max()) > 0 and float(gb[lo_a:].abs().max()) > 0
+    assert torch.equal(one.flat.data, two.flat.data)                                        # lr = 0 moved nothing
+    # one real step: both ranges are updated, with the gradient of this very replay
+    two.set_lr(1e-2)
+    w0, m0 = two.flat.data.clone(), two.m.clone()
+    two.step_graphed(imgs, pngs)
+    m1 = 0.9 * m0 + two.flat.grad
+    assert torch.allclose(two.m, m1, rtol=1e-6, atol=1e-8)
+    upd = two.flat.grad + 0.9 * m1 if two.nesterov else m1
+    assert torch.allclose(two.flat.data, w0 - 1e-2 * upd, rtol=1e-5, atol=1e-7)
+    assert float((two.flat.data[:hi_b] - w0[:hi_b]).abs().max()) > 0 and float((two.flat.data[lo_a:] - w0[lo_a:]).abs().max()) > 0
+    # a model without a cut (MobileNetV2) declines, and the caller falls back to the one-graph step
+    assert SegTrainer(_small_model(torch.float32, bb="mobilenet"), **kw).capture_split(imgs, pngs, None, warmup=1) is None
