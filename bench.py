@@ -707,12 +707,15 @@ def run_ours(args):
         sync_all()
         return max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
 
-    ms_e2e_f32 = e2e_run((imgs_h, pngs_h), args.steps)
+    # the e2e window is at least 24 steps: one ~10-20 ms host hiccup (pinned-copy start-up, the clock sampler's fork) in an
+    # 8-step window moved the number by 5 % between otherwise identical runs (profiles/r02_bench_b32_v3 / v4)
+    e2e_steps = max(args.steps, 24)
+    ms_e2e_f32 = e2e_run((imgs_h, pngs_h), e2e_steps)
     imgs_u8_h = (imgs_h.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
     pngs_u8_h = pngs_h.to(torch.uint8).pin_memory()
     if use_graph:
         capture_step(imgs_u8_h.cuda(), pngs_u8_h.cuda())      # same step over uint8 static input buffers
-    ms_e2e = e2e_run((imgs_u8_h, pngs_u8_h), args.steps)
+    ms_e2e = e2e_run((imgs_u8_h, pngs_u8_h), e2e_steps)
 
     t = torch.tensor([ms_total, ms_e2e, ms_e2e_f32], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -748,8 +751,8 @@ def run_ours(args):
 
     ms_step = ms_total / args.steps
     value = world * bsz * args.steps / (ms_total * 1e-3)
-    e2e_value = world * bsz * args.steps / (ms_e2e * 1e-3)
-    e2e_f32_value = world * bsz * args.steps / (ms_e2e_f32 * 1e-3)
+    e2e_value = world * bsz * e2e_steps / (ms_e2e * 1e-3)
+    e2e_f32_value = world * bsz * e2e_steps / (ms_e2e_f32 * 1e-3)
     kernels, roof_hbm = kernel_rooflines(bsz, peaks)
     step_tf = value / world * TRAIN_GFLOP_PER_IMAGE / 1e3
     # `roofline` describes the STEP (what the metric measures): convolution flops of one training step / step time against
@@ -797,10 +800,10 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
         "torch_gpu_baseline": torch_gpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": imgs_u8_h.numel() + pngs_u8_h.numel(),
-                "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps,
+                "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                 "inputs": "pinned host uint8 [B,H,W,3] pixels + uint8 class maps (what a loader decodes)",
                 "fp32_contract": {"value": e2e_f32_value, "h2d_bytes_per_step": imgs_h.numel() * 4 + pngs_h.numel() * 8,
-                                  "ms_per_step": ms_e2e_f32 / args.steps,
+                                  "ms_per_step": ms_e2e_f32 / e2e_steps,
                                   "inputs": "pinned host fp32 NCHW images + int64 class maps (utils_fit.py:52-58)"}},
         "fit_one_epoch": fit_ips,
         "configs3_global_batch_256": strong,

@@ -59,6 +59,10 @@ CVX_API int64_t     cvx_launch_count(void);
  * sets on = 1 for the duration of that step; the library then skips its own cudaMemsetAsync.  Process-wide, not
  * per-stream: one training step at a time per process (one process per GPU). */
 CVX_API int         cvx_set_ws_prezeroed(int on);
+/* Profiling aid (tools/tc_trace.py), not part of the operator surface: enable != 0 makes the following CTA-pair tcgen05
+ * forward / data-gradient launches leave clock64 phase marks of their first and last cluster; out64 (128 values, host
+ * memory, nullable) receives the marks left so far after a device synchronise (slot layout: csrc/conv_tc.cu). */
+CVX_API int         cvx_debug_tc_trace(int enable, unsigned long long* out64);
 /* 1 if the running device is sm_100 (tcgen05/TMA kernels usable), 0 otherwise */
 CVX_API int         cvx_device_is_sm100(void);
 
@@ -394,6 +398,44 @@ CVX_API int cvx_split_patches_u8(const unsigned char* images, void* patches, int
 CVX_API int cvx_finish_batch_u8(const unsigned char* images_u8, void* images_out, int64_t n_image_elems,
                                 const unsigned char* labels_u8, int64_t* labels_out, int64_t n_pixels, int num_classes,
                                 int dtype, void* stream);
+
+/* ---- training augmentation of the segmentation loader on the device ----------------------------
+ * Reference: DeeplabDataset.get_random_data, Segmentation/deeplabv3+/utils/dataloader.py:55-154 (PIL bicubic / nearest
+ * resize to a jittered size, flip, paste on a 128-grey canvas, cv2.GaussianBlur 5x5, cv2.warpAffine rotation, HSV gain
+ * jitter) - reproduced bit for bit on uint8 data.  The random decisions and the size-dependent coefficient tables come
+ * from the host (utils/dataloader.py); a batch is described by one cvx_aug_sample per image, in DEVICE memory. */
+typedef struct cvx_aug_sample {
+  int64_t src_off;        /* bytes into `src`: decoded image, uint8 RGB [ih][iw][3] */
+  int64_t lab_off;        /* bytes into `src`: class map, uint8 [ih][iw] */
+  int64_t tmp_off;        /* bytes into `tmp`: horizontal-pass result [ih][nw][3] (unused when iw == nw) */
+  int32_t xtab, ytab;     /* index into `tables` (int32): per axis first source index [n], tap count [n], weights [n][taps] */
+  int32_t xnn, ynn;       /* index into `tables`: nearest-neighbour source index per resized coordinate [nw], [nh] */
+  int32_t rot;            /* index into `tables`: adelta[W], bdelta[W], x0[H], y0[H] of cv2.warpAffine (rotate != 0 only) */
+  int32_t lut;            /* byte offset into `luts`: hue[256], sat[256], val[256]; -1 = no colour jitter (validation) */
+  int32_t ih, iw, nh, nw; /* source size, resized size */
+  int32_t xtaps, ytaps;   /* row length of the weight tables */
+  int32_t dx, dy;         /* paste position of the resized image on the canvas (may be negative) */
+  int32_t flip, blur, rotate;
+  int32_t reserved;
+} cvx_aug_sample;
+/* pass 1: horizontal resample of every sample whose width changes -> tmp; max_elems = max over samples of ih * nw
+ * (0: nothing to do).  Weights: Pillow's 22-bit fixed point. */
+CVX_API int cvx_aug_resize_rows(const cvx_aug_sample* samples, int batch, const unsigned char* src, const int* tables,
+                                unsigned char* tmp, int64_t max_elems, void* stream);
+/* pass 2: vertical resample + flip + paste -> canvas uint8 [batch][h][w][3] (fill 128) and labels uint8 [batch][h][w]
+ * (nearest resize, fill 0). */
+CVX_API int cvx_aug_compose(const cvx_aug_sample* samples, int batch, const unsigned char* src, const unsigned char* tmp,
+                            const int* tables, unsigned char* canvas, unsigned char* labels, int h, int w, void* stream);
+/* cv2.GaussianBlur(img, (5, 5), 0) of the samples with blur != 0 -> out (same layout as canvas; other samples untouched) */
+CVX_API int cvx_aug_blur5(const cvx_aug_sample* samples, int batch, const unsigned char* canvas, unsigned char* out, int h,
+                          int w, void* stream);
+/* rotation (samples with rotate != 0; bicubic for the image with border 128, nearest for the label with border 0) and the
+ * HSV gain jitter (samples with lut >= 0) -> out_img, out_lab.  A sample reads `blurred` if blur != 0, else `canvas`.
+ * cubic = OpenCV's 15-bit bicubic weights [32][32][16]; vec_cols = (w / 32) * 32: the columns OpenCV's vector loop covers. */
+CVX_API int cvx_aug_rotate_jitter(const cvx_aug_sample* samples, int batch, const unsigned char* canvas,
+                                  const unsigned char* blurred, const unsigned char* labels, const int* tables,
+                                  const short* cubic, const unsigned char* luts, unsigned char* out_img,
+                                  unsigned char* out_lab, int h, int w, int vec_cols, void* stream);
 
 #ifdef __cplusplus
 }

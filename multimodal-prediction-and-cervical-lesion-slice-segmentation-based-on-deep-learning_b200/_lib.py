@@ -29,6 +29,15 @@ class GemmProblem(C.Structure):
                 ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32), ("reserved", C.c_int32)]
 
 
+class AugSample(C.Structure):
+    """cvx_aug_sample of include/cervix_b200.h (the host packs these as numpy records: utils/dataloader.py AUG_SAMPLE)."""
+    _fields_ = [("src_off", C.c_int64), ("lab_off", C.c_int64), ("tmp_off", C.c_int64), ("xtab", C.c_int32), ("ytab", C.c_int32),
+                ("xnn", C.c_int32), ("ynn", C.c_int32), ("rot", C.c_int32), ("lut", C.c_int32), ("ih", C.c_int32),
+                ("iw", C.c_int32), ("nh", C.c_int32), ("nw", C.c_int32), ("xtaps", C.c_int32), ("ytaps", C.c_int32),
+                ("dx", C.c_int32), ("dy", C.c_int32), ("flip", C.c_int32), ("blur", C.c_int32), ("rotate", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 MAX_GEMM_PROBLEMS = 16
 MAX_PARAM_SETS = 8
 
@@ -128,6 +137,11 @@ PROTOTYPES = {
     "cvx_segtab_bcast_add_bwd": [_P, _P, _P, _P, _P, _I, _I, _P],
     "cvx_multi_gather_chunk": [],
     "cvx_set_ws_prezeroed": [_I],
+    "cvx_debug_tc_trace": [_I, _P],
+    "cvx_aug_resize_rows": [_P, _I, _P, _P, _P, _L, _P],
+    "cvx_aug_compose": [_P, _I, _P, _P, _P, _P, _P, _I, _I, _P],
+    "cvx_aug_blur5": [_P, _I, _P, _P, _I, _I, _P],
+    "cvx_aug_rotate_jitter": [_P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "cvx_multi_gather": [_P, _P, _P, _P, _P, _I, _P, _P],
     "cvx_seg_postprocess": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "cvx_confusion_matrix": [_P, _P, _L, _I, _P, _P],

@@ -140,6 +140,29 @@ class CudaBackend:
                                            self._stream()), "cvx_finish_batch_u8")
         return x, t
 
+    def augment_batch(self, samples, src, tables, luts, cubic, batch: int, h: int, w: int, max_elems: int, tmp_bytes: int,
+                      vec_cols: int, out=None):
+        """The training augmentation of dataloader.py:55-154 for a packed batch (utils/dataloader.py pack_batch):
+        descriptors uint8 [batch, 96], sources uint8, tables int32, colour tables uint8 [batch*768], OpenCV's bicubic
+        weights int16 [32,32,16] -> (uint8 [batch,h,w,3], uint8 [batch,h,w]).  Four launches (cvx_aug_*)."""
+        self._chk(samples, src, tables, luts, cubic)
+        if samples.dtype != torch.uint8 or samples.numel() != batch * C.sizeof(_lib.AugSample) or src.dtype != torch.uint8 \
+                or tables.dtype != torch.int32 or luts.dtype != torch.uint8 or luts.numel() != batch * 768 \
+                or cubic.dtype != torch.int16 or cubic.numel() != 32 * 32 * 16:
+            raise TypeError("augment_batch: packed blobs of utils.dataloader.pack_batch expected")
+        dev = src.device
+        u8 = lambda *shape: torch.empty(shape, dtype=torch.uint8, device=dev)   # noqa: E731
+        canvas, blurred, lab0 = u8(batch, h, w, 3), u8(batch, h, w, 3), u8(batch, h, w)
+        img, lab = out if out is not None else (u8(batch, h, w, 3), u8(batch, h, w))
+        tmp = u8(max(int(tmp_bytes), 16))
+        st = self._stream()
+        check(self.lib.cvx_aug_resize_rows(_p(samples), batch, _p(src), _p(tables), _p(tmp), int(max_elems), st), "cvx_aug_resize_rows")
+        check(self.lib.cvx_aug_compose(_p(samples), batch, _p(src), _p(tmp), _p(tables), _p(canvas), _p(lab0), h, w, st), "cvx_aug_compose")
+        check(self.lib.cvx_aug_blur5(_p(samples), batch, _p(canvas), _p(blurred), h, w, st), "cvx_aug_blur5")
+        check(self.lib.cvx_aug_rotate_jitter(_p(samples), batch, _p(canvas), _p(blurred), _p(lab0), _p(tables), _p(cubic), _p(luts),
+                                             _p(img), _p(lab), h, w, int(vec_cols), st), "cvx_aug_rotate_jitter")
+        return img, lab
+
     def to_nchw(self, x: torch.Tensor) -> torch.Tensor:
         self._chk(x)
         n, h, w, c = x.shape

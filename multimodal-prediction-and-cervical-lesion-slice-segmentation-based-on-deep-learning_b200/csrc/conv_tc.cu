@@ -98,7 +98,20 @@ struct TcFwdParams {
   int tiles_x, tiles_y;
   int stride;                // 1, or 2 (persistent forward kernel only: TMA element strides)
   int tile_n;                // output-channel tile (multiple of 16, <= 256), balanced over n_tiles
+  int trace;                 // tools only (cvx_debug_tc_trace): the first and the last cluster leave clock64 marks
 };
+
+// phase marks of the CTA-pair kernel for tools/tc_trace.py: [0] first cluster, [64] last cluster.  Slots: 0 globaltimer
+// at entry, 1 clock at entry, 2 set-up done, 3 dependency wait done, 4 first / 5 last TMA issue, 6 first operands landed,
+// 8+t MMAs of tile t committed, 24+t accumulator of tile t seen by the epilogue, 40+t epilogue of tile t done,
+// 56 statistics flushed, 57 clock at exit, 58 globaltimer at exit.
+__device__ unsigned long long g_tc_trace[128];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_MARK(slot) do { if (tr) tr[slot] = (unsigned long long)clock64(); } while (0)
 
 // Optional epilogue work of the forward / data-gradient kernels (persistent variants):
 //   y[row][c] = acc + bias[c] + side_scale[c] * side[row][c]          (bias, side nullable)
@@ -718,6 +731,9 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   const int pair = blockIdx.x / (2 * kPairs), npairs = gridDim.x / (2 * kPairs);   // cluster index / count
   const int kcb = (p.cin + 63) / 64;
   const int num_kb = p.kh * p.kw * kcb;
+  unsigned long long* tr = nullptr;
+  if (p.trace && crank == 0 && (pair == 0 || pair == npairs - 1)) tr = g_tc_trace + (pair == 0 ? 0 : 64);
+  if (tr && threadIdx.x == 0) { tr[0] = gtimer(); tr[1] = (unsigned long long)clock64(); }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_x);
@@ -745,7 +761,9 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_MARK(2);
   pdl_wait();      // barriers, TMEM and descriptors are set up: now wait for the producer of this kernel's inputs
+  if (threadIdx.x == 0) TC_MARK(3);
 
   // The producer and the issuer warps run their loops WARP-UNIFORMLY (all 32 lanes compute the same counters and
   // addresses and wait on the same barriers); only the TMA / tcgen05 instructions themselves sit under elect_one().
@@ -761,6 +779,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
     uint16_t bmask = 0;
 #pragma unroll
     for (int q = 0; q < kPairs; ++q) bmask |= (uint16_t)(1u << (2 * q + rank));
+    bool first_issue = true;
     for (int pt = pair; pt < total_pair_tiles; pt += npairs) {
       const int nt = pt % n_tiles;
       const int mtile = 2 * ((pt / n_tiles) * kPairs + (int)pidx) + (int)rank;
@@ -781,6 +800,8 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         mbar_wait(empty0 + 8 * s, ph ^ 1);
         const uint32_t sa = smem_base + s * k2StageBytes;
         const uint32_t lead_full = (full0 + 8 * s) & 0xFEFFFFFFu;  // the leader CTA's barrier (peer bit cleared)
+        if (tr && lane == 0) { if (first_issue) TC_MARK(4); TC_MARK(5); }
+        first_issue = false;
         if (elect_one()) {
           if (leader) mbar_expect_tx(full0 + 8 * s, tx_bytes);
           else mbar_arrive_cluster(lead_full0 + 8 * s);
@@ -817,6 +838,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full0 + 8 * s, ph);
           tc_fence_after();
+          if (tr && lane == 0 && tcount == 0 && kb == 0) TC_MARK(6);
           const uint32_t sa = smem_base + s * k2StageBytes;
           const uint64_t ad = desc_hi | (uint64_t)((sa >> 4) & 0x3FFF);
           const uint64_t bd = desc_hi | (uint64_t)(((sa + kABytes) >> 4) & 0x3FFF);
@@ -838,6 +860,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         if (elect_one()) umma_commit_2sm(tfull0 + 8 * acc, pair_mask);
         __syncwarp();
+        if (tr && lane == 0 && tcount < 16) TC_MARK(8 + tcount);
       }
     }
   } else {
@@ -929,6 +952,7 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
       const int acc = tcount & 1;
       mbar_wait(tfull0 + 8 * acc, (tcount >> 1) & 1);
       tc_fence_after();
+      if (tr && epi_tid == 0 && tcount < 16) TC_MARK(24 + tcount);
       const uint32_t t_addr = tmem_base + acc * kPBN + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
       for (int q = 0; q < nchunks; ++q) {
@@ -1001,14 +1025,17 @@ conv_tc_fwd_2cta_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid
         }
         ++chunk_count;
       }
+      if (tr && epi_tid == 0 && tcount < 16) TC_MARK(40 + tcount);
     }
     if (MODE & 1) stats_flush();
     if (epi_tid == 0) bulk_wait_read<0>();
     if (MODE & 1) tc_epilogue_flush_stats<256>(ep, stats_sm, n_tiles, p.tile_n, p.cout, epi_tid);
+    if (epi_tid == 0) TC_MARK(56);
   }
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_2sm(tmem_base, 2 * kPBN);
+  if (tr && threadIdx.x == 0) { tr[57] = (unsigned long long)clock64(); tr[58] = gtimer(); }
 }
 
 // ------------------------------------------------------------------------------ wgrad
@@ -1637,6 +1664,18 @@ static int launch_fwd_pairs(int kp, int mode, const CUtensorMap& mx, const CUten
   return launch_fwd_pairs_m<1>(mode, mx, mw, my, ms, ep, p, n_tiles, m_tiles, st);
 }
 
+static int g_tc_trace_on = 0;
+// tools/tc_trace.py: enable != 0 arms the phase marks of the next CTA-pair forward / data-gradient launches; out64
+// (128 values, host memory, nullable) receives the marks of the launches made so far (after a device synchronise)
+extern "C" CVX_API int cvx_debug_tc_trace(int enable, unsigned long long* out64) {
+  g_tc_trace_on = enable;
+  if (out64) {
+    CVX_CUDA_OK(cudaDeviceSynchronize());
+    CVX_CUDA_OK(cudaMemcpyFromSymbol(out64, g_tc_trace, sizeof(unsigned long long) * 128));
+  }
+  return CVX_OK;
+}
+
 // rows = output pixels [n,ho,wo] ; src = [n,hs,ws,cred] ; wp = [taps][ncol][cred]
 static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, int kh, int kw, int pad, int dil,
                      const void* src, const void* wp, const TcEpi& ep, void* dst, cudaStream_t st, int stride = 1) {
@@ -1644,6 +1683,7 @@ static int run_igemm(int n, int hs, int ws, int cred, int ho, int wo, int ncol, 
   TcFwdParams p;
   p.n = n; p.ho = ho; p.wo = wo; p.cout = ncol; p.cin = cred; p.kh = kh; p.kw = kw; p.pad = pad; p.dil = dil;
   p.stride = stride;
+  p.trace = g_tc_trace_on;
   {
     const int nt = (ncol + kPBN - 1) / kPBN;
     p.tile_n = ((ncol + nt - 1) / nt + 15) & ~15;   // balanced tiles: 304 -> 2 x 160 instead of 256 + 48

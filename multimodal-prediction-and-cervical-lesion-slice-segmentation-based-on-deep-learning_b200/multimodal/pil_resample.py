@@ -25,33 +25,50 @@ import numpy as np
 PRECISION_BITS = 32 - 8 - 2
 
 
-@functools.lru_cache(maxsize=64)
+def _triangle(x):
+    x = np.abs(x)
+    return np.where(x < 1.0, 1.0 - x, 0.0)
+
+
+def _keys_cubic(x):
+    """Pillow's bicubic kernel (a = -0.5), support 2."""
+    a = -0.5
+    x = np.abs(x)
+    return np.where(x < 1.0, ((a + 2.0) * x - (a + 3.0)) * x * x + 1.0,
+                    np.where(x < 2.0, (((x - 5.0) * x + 8.0) * x - 4.0) * a, 0.0))
+
+
+_KERNELS = {"bilinear": (_triangle, 1.0), "bicubic": (_keys_cubic, 2.0)}
+
+
 def bilinear_tables(in_size: int, out_size: int):
-    """Per output coordinate: first source index, number of taps, fixed-point weights (``[out_size, ksize]`` int32)."""
+    return resample_tables(in_size, out_size, "bilinear")
+
+
+@functools.lru_cache(maxsize=512)
+def resample_tables(in_size: int, out_size: int, kind: str = "bilinear"):
+    """Per output coordinate: first source index, number of taps, fixed-point weights (``[out_size, ksize]`` int32) of
+    ``Image.resize`` with the BILINEAR or BICUBIC filter."""
+    kernel, base_support = _KERNELS[kind]
     scale = float(in_size) / out_size
     filterscale = max(scale, 1.0)
-    support = 1.0 * filterscale                       # bilinear: support 1.0
+    support = base_support * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
-    xmin = np.zeros(out_size, dtype=np.int32)
-    cnt = np.zeros(out_size, dtype=np.int32)
-    kk = np.zeros((out_size, ksize), dtype=np.int32)
     ss = 1.0 / filterscale
-    for xx in range(out_size):
-        center = (xx + 0.5) * scale
-        lo = int(center - support + 0.5)
-        lo = max(lo, 0)
-        hi = int(center + support + 0.5)
-        hi = min(hi, in_size)
-        n = hi - lo
-        x = (np.arange(n, dtype=np.float64) + lo - center + 0.5) * ss
-        w = np.where(np.abs(x) < 1.0, 1.0 - np.abs(x), 0.0)
-        ww = float(w.sum())
-        if ww != 0.0:
-            w = w / ww
-        fixed = np.where(w < 0, (-0.5 + w * (1 << PRECISION_BITS)), (0.5 + w * (1 << PRECISION_BITS))).astype(np.int64)
-        xmin[xx], cnt[xx] = lo, n
-        kk[xx, :n] = fixed.astype(np.int32)
-    return xmin, cnt, kk
+    # all output coordinates at once; every floating-point operation keeps the order of the C loop
+    center = (np.arange(out_size, dtype=np.float64) + 0.5) * scale
+    lo = np.maximum(np.trunc(center - support + 0.5), 0.0).astype(np.int64)
+    hi = np.minimum(np.trunc(center + support + 0.5), float(in_size)).astype(np.int64)
+    n = hi - lo
+    idx = np.arange(ksize, dtype=np.int64)[None, :]
+    live = idx < n[:, None]
+    x = (((idx + lo[:, None]).astype(np.float64) - center[:, None]) + 0.5) * ss
+    w = np.where(live, kernel(x), 0.0)
+    ww = np.cumsum(w, axis=1)[:, -1]                  # Pillow accumulates the normaliser left to right (+0.0 is exact)
+    w = np.where((ww != 0.0)[:, None], w / np.where(ww != 0.0, ww, 1.0)[:, None], w)
+    fixed = np.where(w < 0, -0.5 + w * (1 << PRECISION_BITS), 0.5 + w * (1 << PRECISION_BITS)).astype(np.int64)
+    kk = np.where(live, fixed, 0).astype(np.int32)
+    return lo.astype(np.int32), n.astype(np.int32), kk
 
 
 def resize_u8_reference(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:

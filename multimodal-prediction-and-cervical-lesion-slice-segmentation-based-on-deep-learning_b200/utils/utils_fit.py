@@ -68,14 +68,29 @@ def _objective(outputs, pngs, labels, weights, num_classes, dice_loss, focal_los
     return loss, fs
 
 
-def _to_device(batch, cls_weights, cuda, local_rank):
+def _to_device(batch, cls_weights, cuda, local_rank, num_classes=None):
     imgs, pngs, labels = batch
     weights = torch.from_numpy(cls_weights) if not torch.is_tensor(cls_weights) else cls_weights
     if cuda:
         dev = torch.device("cuda", local_rank)
-        imgs, pngs, labels = (t.to(dev, non_blocking=True) for t in (imgs, pngs, labels))
+        imgs, pngs, labels = (None if t is None else t.to(dev, non_blocking=True) for t in (imgs, pngs, labels))
         weights = weights.to(dev)
+    if pngs.dtype == torch.uint8:       # batches of utils.dataloader.DeviceAugmentLoader: the loader tail of dataloader.py:40-47
+        pngs = pngs.long().clamp_(max=num_classes)
+    if labels is None:
+        labels = torch.nn.functional.one_hot(pngs, num_classes + 1).float()
     return imgs, pngs, labels, weights
+
+
+def _wrap_loader(gen, cuda, local_rank):
+    """A DataLoader built with the drop-in's ``deeplab_dataset_collate`` yields packed ``AugmentPlan`` batches (decoded
+    uint8 sources + drawn decisions): run them through the augmentation kernels on the training device."""
+    from .dataloader import DeviceAugmentLoader, deeplab_dataset_collate
+    if getattr(gen, "collate_fn", None) is not deeplab_dataset_collate:
+        return gen
+    if not (cuda and torch.cuda.is_available()):
+        raise RuntimeError("cervix_b200: the device augmentation of utils.dataloader needs a CUDA device (no CPU fallback)")
+    return DeviceAugmentLoader(gen, torch.device("cuda", local_rank))
 
 
 _FIT_STREAMS = {}
@@ -168,12 +183,15 @@ def _train_phase_fast(trainer, gen, epoch_step, cuda, local_rank, cls_weights, n
                 return
             imgs, pngs, labels = batch
             if state["implicit"] is None:       # checked once per epoch on the host, before anything is copied
-                state["implicit"] = (not labels.is_cuda) and _implicit_onehot(pngs, labels, num_classes)
+                state["implicit"] = labels is None or ((not labels.is_cuda) and _implicit_onehot(pngs, labels, num_classes))
             yield (imgs, pngs, None if state["implicit"] else labels)
 
+    # a loader that already delivers device tensors (utils.dataloader.DeviceAugmentLoader: uint8 pixels and class maps
+    # augmented on the GPU, uploaded one batch ahead on its own copy stream) needs no second staging step
+    batches = host_batches() if getattr(gen, "on_device", False) else BatchPrefetcher(host_batches(), dev)
     run = None
     steps = 0
-    for imgs, pngs, labels in BatchPrefetcher(host_batches(), dev):
+    for imgs, pngs, labels in batches:
         if trainer.graph_matches(imgs, pngs, labels):
             out = trainer.step_graphed(imgs, pngs, labels)
         elif trainer.t >= _EAGER_STEPS_BEFORE_CAPTURE and steps >= _EAGER_STEPS_BEFORE_CAPTURE:
@@ -200,6 +218,7 @@ def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, ep
                   gen_val, Epoch, cuda, dice_loss, focal_loss, cls_weights, num_classes, fp16, scaler, save_period,
                   save_dir, local_rank=0):
     _select_engine(model_train, fp16)
+    gen, gen_val = _wrap_loader(gen, cuda, local_rank), _wrap_loader(gen_val, cuda, local_rank)
     main = local_rank == 0
     if main:
         print("Start Train")
@@ -224,7 +243,7 @@ def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, ep
         if iteration >= epoch_step:
             break
         with torch.no_grad():
-            imgs, pngs, labels, weights = _to_device(batch, cls_weights, cuda, local_rank)
+            imgs, pngs, labels, weights = _to_device(batch, cls_weights, cuda, local_rank, num_classes)
         optimizer.zero_grad()
         outputs = model_train(imgs)
         loss, fs = _objective(outputs, pngs, labels, weights, num_classes, dice_loss, focal_loss)
@@ -254,7 +273,7 @@ def fit_one_epoch(model_train, model, loss_history, eval_callback, optimizer, ep
         if iteration >= epoch_step_val:
             break
         with torch.no_grad():
-            imgs, pngs, labels, weights = _to_device(batch, cls_weights, cuda, local_rank)
+            imgs, pngs, labels, weights = _to_device(batch, cls_weights, cuda, local_rank, num_classes)
             outputs = model_train(imgs)
             loss, fs = _objective(outputs, pngs, labels, weights, num_classes, dice_loss, focal_loss)
             run_loss = loss.detach().clone() if run_loss is None else run_loss + loss.detach()

@@ -44,6 +44,77 @@ class EmuBackend:
         t = None if labels_u8 is None else labels_u8.long().clamp(max=num_classes)
         return x, t
 
+    def augment_batch(self, samples, src, tables, luts, cubic, batch, h, w, max_elems, tmp_bytes, vec_cols, out=None):
+        """Interpreter of csrc/augment.cu on the PACKED blobs (descriptors, integer tables and colour tables exactly as
+        the host module built them), in numpy: checks the host side of utils/dataloader.py against the goldens on CPU."""
+        import numpy as np
+        from cervix_b200.utils.dataloader import AUG_SAMPLE
+        from oracle import augment_ref as A
+        rec = np.frombuffer(samples.cpu().numpy().tobytes(), dtype=AUG_SAMPLE)
+        srcb, tab = src.cpu().numpy(), tables.cpu().numpy().astype(np.int64)
+        lutb, cub = luts.cpu().numpy(), cubic.cpu().numpy().astype(np.int64).reshape(32, 32, 4, 4)
+        imgs = np.zeros((batch, h, w, 3), np.uint8)
+        labs = np.zeros((batch, h, w), np.uint8)
+
+        def resample(cur, off, n_out, taps, axis):
+            lo, cnt = tab[off:off + n_out], tab[off + n_out:off + 2 * n_out]
+            k = tab[off + 2 * n_out:off + 2 * n_out + n_out * taps].reshape(n_out, taps)
+            outs = []
+            for o in range(n_out):
+                seg = np.take(cur, np.arange(lo[o], lo[o] + cnt[o]), axis=axis)
+                wts = k[o, :cnt[o]].reshape([-1 if a == axis else 1 for a in range(3)])
+                outs.append(np.clip(((seg * wts).sum(axis) + (1 << 21)) >> 22, 0, 255))
+            return np.stack(outs, axis=axis)
+
+        for i, s in enumerate(rec):
+            ih, iw, nh, nw = int(s["ih"]), int(s["iw"]), int(s["nh"]), int(s["nw"])
+            img = srcb[s["src_off"]:s["src_off"] + ih * iw * 3].reshape(ih, iw, 3).astype(np.int64)
+            lab = srcb[s["lab_off"]:s["lab_off"] + ih * iw].reshape(ih, iw)
+            if iw != nw:
+                img = resample(img, int(s["xtab"]), nw, int(s["xtaps"]), 1)
+            if ih != nh:
+                img = resample(img, int(s["ytab"]), nh, int(s["ytaps"]), 0)
+            lab = lab[tab[s["ynn"]:s["ynn"] + nh]][:, tab[s["xnn"]:s["xnn"] + nw]]
+            img = img.astype(np.uint8)
+            if s["flip"]:
+                img, lab = img[:, ::-1], lab[:, ::-1]
+            img = A.paste((h, w), 128, img, int(s["dx"]), int(s["dy"]))
+            lab = A.paste((h, w), 0, lab, int(s["dx"]), int(s["dy"]))
+            if s["blur"]:
+                img = A.cv_gaussian5_u8(img)
+            if s["rotate"]:
+                r0 = int(s["rot"])
+                ad, bd = tab[r0:r0 + w], tab[r0 + w:r0 + 2 * w]
+                x0, y0 = tab[r0 + 2 * w:r0 + 2 * w + h], tab[r0 + 2 * w + h:r0 + 2 * w + 2 * h]
+                X, Y = (x0[:, None] + 16 + ad[None, :]) >> 5, (y0[:, None] + 16 + bd[None, :]) >> 5
+                wt = cub[Y & 31, X & 31]
+                acc = np.full((h, w, 3), 1 << 14, np.int64)
+                pix = img.astype(np.int64)
+                for k1 in range(4):
+                    sy = (Y >> 5) - 1 + k1
+                    for k2 in range(4):
+                        sx = (X >> 5) - 1 + k2
+                        ok = (sx >= 0) & (sx < w) & (sy >= 0) & (sy < h)
+                        px = np.where(ok[..., None], pix[np.clip(sy, 0, h - 1), np.clip(sx, 0, w - 1)], 128)
+                        acc += px * wt[:, :, k1, k2][..., None]
+                img = np.clip(acc >> 15, 0, 255).astype(np.uint8)
+                nx, ny = (x0[:, None] + 512 + ad[None, :]) >> 10, (y0[:, None] + 512 + bd[None, :]) >> 10
+                ok = (nx >= 0) & (nx < w) & (ny >= 0) & (ny < h)
+                lab = np.where(ok, lab[np.clip(ny, 0, h - 1), np.clip(nx, 0, w - 1)], 0).astype(np.uint8)
+            if s["lut"] >= 0:
+                lt = lutb[s["lut"]:s["lut"] + 768]
+                hsv = A.cv_rgb2hsv_u8(img)
+                hsv = np.stack([lt[hsv[..., 0]], lt[256 + hsv[..., 1].astype(np.int64)], lt[512 + hsv[..., 2].astype(np.int64)]], -1)
+                assert vec_cols == (w // A.CV_SIMD_PIXELS) * A.CV_SIMD_PIXELS
+                img = A.cv_hsv2rgb_u8(hsv)
+            imgs[i], labs[i] = img, lab
+        ti, tl = torch.from_numpy(imgs).to(src.device), torch.from_numpy(labs).to(src.device)
+        if out is not None:
+            out[0].copy_(ti)
+            out[1].copy_(tl)
+            return out
+        return ti, tl
+
     def to_nchw(self, x):
         return _nchw(x).contiguous()
 
