@@ -440,6 +440,68 @@ def classifier_cpu_baseline(size: int = 512, reps: int = 1):
 
 
 # ----------------------------------------------------------------------------- our arm
+def augment_leg(batch: int, size: int, peaks):
+    """the training augmentation (dataloader.py:55-154) for one batch of VOC-sized decoded images.
+    Host: drawing the decisions + building / packing the integer tables (one core; a DataLoader worker's share).
+    Device: the four cvx_aug_* launches, with and without the host->device copy of the packed batch.  Beside it the
+    unmodified reference's get_random_data + loader tail on one host core."""
+    import numpy as np
+    import torch
+    from cervix_b200.utils import dataloader as D
+    from oracle.ref_runner import augment_sources
+    srcs = augment_sources(batch)
+    np.random.seed(0)
+
+    def pack():
+        return D.pack_batch([(a, b, D.draw_params(b.shape[1], b.shape[0], (size, size))) for a, b in srcs], (size, size))
+
+    pack()
+    t0 = time.perf_counter()
+    reps = 5
+    plans = [pack().pin_memory() for _ in range(reps)]          # fresh random sizes every time: the table cache mostly misses
+    host_ms = (time.perf_counter() - t0) / reps * 1e3
+    aug = D.DeviceAugmenter("cuda")
+    for p in plans[:2]:
+        aug.run(p)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    for p in plans:
+        aug.run(p)
+    e[1].record()
+    blobs = [aug.upload(p) for p in plans]
+    torch.cuda.synchronize()
+    e[2].record()
+    for p, b in zip(plans, blobs):
+        aug.run(p, b)
+    e[3].record()
+    torch.cuda.synchronize()
+    ms_e2e, ms_dev = e[0].elapsed_time(e[1]) / reps, e[2].elapsed_time(e[3]) / reps
+    src_bytes = sum(int(p.src.numel()) for p in plans) / reps
+    out_bytes = batch * size * size * 4
+    res = {"what": "get_random_data for a batch of %d decoded images (375x500 / 500x375) onto %dx%d canvases: bicubic + "
+                   "nearest resize, flip, paste, blur (p=.25), rotation (p=.25), HSV jitter; uint8 in, uint8 out, bit-exact "
+                   "with Pillow / OpenCV (tests/test_augment.py)" % (batch, size, size),
+           "images_per_s_device": batch / (ms_dev * 1e-3), "ms_per_batch_device": ms_dev,
+           "images_per_s_with_h2d": batch / (ms_e2e * 1e-3), "ms_per_batch_with_h2d": ms_e2e,
+           "h2d_bytes_per_batch": int(src_bytes + sum(int(p.tables.numel()) * 4 + int(p.luts.numel()) + int(p.samples.numel()) for p in plans) / reps),
+           "host_pack_ms_per_batch_one_core": host_ms, "launches_per_batch": 4,
+           "roofline": {"bound": "hbm", "achieved": (src_bytes + out_bytes) / (ms_dev * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": (src_bytes + out_bytes) / (ms_dev * 1e-3) / 1e9 / peaks["hbm"],
+                        "bytes_per_batch": int(src_bytes + out_bytes),
+                        "note": "algorithmic bytes = decoded sources read once + augmented pixels and class maps written once; "
+                                "the four launches also write and re-read two uint8 canvases (L2-resident at this size)"}}
+    if reference_installed():
+        r = ref_subprocess(["--augment", 64, "--size", size], timeout_s=300)
+        if "error" not in r:
+            res["cpu_baseline"] = {"value": r["images_per_s"], "unit": "images/s", "cores": 1, "kind": "reference", "cpu": cpu_model_name(),
+                                   "sample": "unmodified reference get_random_data + loader tail (dataloader.py:36-154) on %d of the same "
+                                             "sources, one process (%.1f ms/image)" % (r["images"], r["ms_per_image"])}
+        else:
+            res["cpu_baseline"] = {"error": r["error"]}
+    return res
+
+
 def _time_launch(fn, flush, reps: int = 10):
     """Average duration of one launch: CUDA events on the launching (current) stream, L2 flushed between launches."""
     import torch
@@ -687,28 +749,40 @@ def run_ours(args):
         def host_batches(n):
             for _ in range(n):
                 yield host_batch
-        for bi, bp in BatchPrefetcher(host_batches(2)):
+        # ONE prefetcher for warm-up and timed steps: building it allocates its two device buffer sets (cudaMalloc behind
+        # two resident graph pools cost 60-150 ms, once per epoch in a real run), which is not a per-step cost.  Every
+        # timed step still has exactly one host->device copy enqueued inside the timed region (that of the NEXT batch).
+        warm = 6
+        pf = iter(BatchPrefetcher(host_batches(warm + k + 1)))
+        for _ in range(warm):
+            bi, bp = next(pf)
             step_fn(bi, bp, None).cpu()
         sync_all()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e2.record()
-        pf = BatchPrefetcher(host_batches(k))            # first copy is inside the timed region
         prev = None
-        for bi, bp in pf:
+        marks = []
+        for _ in range(k):
+            bi, bp = next(pf)
             r = step_fn(bi, bp, None)
             if use_graph:
                 r = r.clone()                             # the graph's output buffer is overwritten by the next replay
             if prev is not None:
                 prev.cpu()                                # result of the previous step (keeps 1 step in flight)
+                marks.append(time.perf_counter())
             prev = r
         prev.cpu()
+        marks.append(time.perf_counter())
         e3.record()
         sync_all()
+        gaps = sorted((b - a) * 1e3 for a, b in zip(marks, marks[1:]))
+        e2e_step_stats.append({"median_ms": gaps[len(gaps) // 2], "max_ms": gaps[-1], "first_result_ms": (marks[0] - t0) * 1e3})
         return max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
 
-    # the e2e window is at least 24 steps: one ~10-20 ms host hiccup (pinned-copy start-up, the clock sampler's fork) in an
-    # 8-step window moved the number by 5 % between otherwise identical runs (profiles/r02_bench_b32_v3 / v4)
+    e2e_step_stats = []
+
+    # the e2e window is at least 24 steps (per-step gaps are reported beside the mean: `step_gaps`)
     e2e_steps = max(args.steps, 24)
     ms_e2e_f32 = e2e_run((imgs_h, pngs_h), e2e_steps)
     imgs_u8_h = (imgs_h.permute(0, 2, 3, 1) * 255.0).round().to(torch.uint8).contiguous().pin_memory()
@@ -776,6 +850,12 @@ def run_ours(args):
             if isinstance(torch_gpu.get(k), dict) and "images_per_s" in torch_gpu[k]:
                 torch_gpu[k]["ours_over_this"] = value / torch_gpu[k]["images_per_s"]
                 torch_gpu[k]["ours_e2e_over_this"] = e2e_value / torch_gpu[k]["images_per_s"]
+    augment = None
+    if world == 1 and not args.no_augment:
+        try:
+            augment = augment_leg(bsz, size, peaks)
+        except Exception as e_aug:      # report, never fail the bench line
+            augment = {"error": repr(e_aug)}
     if classifier is not None and world == 1 and not args.no_cpu_baseline:
         try:
             classifier["cpu_baseline"] = classifier_cpu_baseline()
@@ -802,10 +882,12 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": imgs_u8_h.numel() + pngs_u8_h.numel(),
                 "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                 "inputs": "pinned host uint8 [B,H,W,3] pixels + uint8 class maps (what a loader decodes)",
+                "step_gaps": e2e_step_stats[1] if len(e2e_step_stats) > 1 else None,
                 "fp32_contract": {"value": e2e_f32_value, "h2d_bytes_per_step": imgs_h.numel() * 4 + pngs_h.numel() * 8,
-                                  "ms_per_step": ms_e2e_f32 / e2e_steps,
+                                  "ms_per_step": ms_e2e_f32 / e2e_steps, "step_gaps": e2e_step_stats[0] if e2e_step_stats else None,
                                   "inputs": "pinned host fp32 NCHW images + int64 class maps (utils_fit.py:52-58)"}},
         "fit_one_epoch": fit_ips,
+        "augment": augment,
         "configs3_global_batch_256": strong,
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -830,6 +912,7 @@ def main():
     ap.add_argument("--no-classifier", action="store_true", help="skip the severity-classifier leg")
     ap.add_argument("--no-graph", action="store_true", help="run the single-GPU step eagerly instead of as a CUDA graph")
     ap.add_argument("--no-fit", action="store_true", help="skip the fit_one_epoch (reference entry point) leg")
+    ap.add_argument("--no-augment", action="store_true", help="skip the device-augmentation leg")
     ap.add_argument("--no-strong", action="store_true", help="skip the configs[3] global-batch-256 leg at N = 4")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -124,8 +124,48 @@ def time_fit_one_epoch(device: str, batch: int, size: int, steps: int, warmup: i
             "torch_threads": torch.get_num_threads()}
 
 
+def augment_sources(count: int, seed: int = 0):
+    """VOC-sized synthetic decoded images (375 x 500 landscape / 500 x 375 portrait) with class maps - the same
+    sources bench.py's augmentation leg packs for the device."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.RandomState(seed)
+    out = []
+    for i in range(count):
+        ih, iw = (375, 500) if i % 2 == 0 else (500, 375)
+        low = rng.randint(0, 256, (ih // 6 + 2, iw // 6 + 2, 3)).astype(np.uint8)
+        img = np.asarray(Image.fromarray(low).resize((iw, ih), Image.BILINEAR))
+        out.append((img, rng.randint(0, 6, (ih, iw)).astype(np.uint8)))
+    return out
+
+
+def time_augment(count: int, size: int):
+    """The unmodified reference's DeeplabDataset.get_random_data + loader tail (dataloader.py:36-49) on one host core,
+    images per second (one DataLoader worker; train.py:281 starts four)."""
+    import time
+
+    import numpy as np
+    from PIL import Image
+    import_reference_seg()
+    from utils.dataloader import DeeplabDataset
+    from utils.utils import preprocess_input
+    ds = DeeplabDataset(["x"], (size, size), 5, True, "/nonexistent")
+    srcs = [(Image.fromarray(a), Image.fromarray(b)) for a, b in augment_sources(count)]
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    for jpg, png in srcs:
+        jpg, png = ds.get_random_data(jpg, png, (size, size), random=True)
+        jpg = np.transpose(preprocess_input(np.array(jpg, np.float64)), [2, 0, 1])
+        png = np.array(png)
+        png[png >= 5] = 5
+        np.eye(6)[png.reshape([-1])].reshape((size, size, 6))
+    sec = time.perf_counter() - t0
+    return {"images_per_s": count / sec, "ms_per_image": sec / count * 1e3, "images": count}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--augment", type=int, default=0, help="time get_random_data on this many images instead of training")
     ap.add_argument("--device", default="cpu")
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--size", type=int, default=512)
@@ -136,6 +176,9 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--budget-s", type=float, default=0.0)
     a = ap.parse_args()
+    if a.augment:
+        print(json.dumps(time_augment(a.augment, a.size)), flush=True)
+        return
     out = time_fit_one_epoch(a.device, a.batch, a.size, a.steps, a.warmup, a.fp16, a.channels_last, a.threads or None,
                              a.budget_s or None)
     print(json.dumps(out), flush=True)
