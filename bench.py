@@ -632,7 +632,8 @@ def strong_scaling_leg(model, bsz: int, size: int, world: int, rank: int, steps:
     trainer = SegTrainer(model, lr=1e-4, betas=(0.9, 0.999), cls_weights=CLS_WEIGHTS, num_classes=5, world_size=world)
     imgs, pngs, _ = synthetic_batch(bsz, size, seed=100 + rank)
     imgs, pngs = imgs.cuda(), pngs.cuda()
-    if comm_in_graph or trainer.capture_split(imgs, pngs, None) is None:
+    split = os.environ.get("CERVIX_SPLIT_BACKWARD", "1") != "0" and not comm_in_graph
+    if not (split and trainer.capture_split(imgs, pngs, None) is not None):
         trainer.capture(imgs, pngs, None, comm_in_graph=comm_in_graph)
     for _ in range(3):
         trainer.step_graphed(imgs, pngs)
@@ -808,8 +809,14 @@ def run_ours(args):
     # the main line is weak scaling at 32 images per GPU (identical at N = 8).  N = 4 -> 64 images per GPU is timed here;
     # N = 2 -> 128 per GPU needs ~140 GB of saved activations and is not attempted.
     strong = None
-    if world > 1 and 256 % world == 0 and 32 < 256 // world <= 64 and not args.no_strong:
-        strong = strong_scaling_leg(model, 256 // world, size, world, rank, args.steps, comm_in_graph)
+    strong_bsz = int(os.environ.get("CERVIX_BENCH_STRONG_BSZ", "0")) or (256 // world if 256 % world == 0 else 0)
+    if world > 1 and 32 < strong_bsz <= 64 and not args.no_strong:
+        free_gb = torch.tensor([torch.cuda.mem_get_info()[0] / 2 ** 30], device="cuda")
+        dist.all_reduce(free_gb, op=dist.ReduceOp.MIN)          # every rank takes the same decision
+        if float(free_gb) < 110.0:
+            strong = {"skipped": "%.0f GB free on the fullest GPU; a %d-image step keeps ~95 GB of activations" % (float(free_gb), strong_bsz)}
+        else:
+            strong = strong_scaling_leg(model, strong_bsz, size, world, rank, args.steps, comm_in_graph)
     classifier = None
     if not args.no_classifier:      # every rank takes part (patients are sharded, head gradients all-reduced)
         del model
