@@ -94,6 +94,24 @@ __global__ void spatial_broadcast_kernel(const T* __restrict__ x, T* __restrict_
   }
 }
 
+// vector form for C % VEC == 0 (ASPP's pooled branch, [B,2048] -> [B,32,32,2048] in backward): a thread keeps one
+// 16-byte channel vector of its image in registers and stores it to a strip of pixels - no per-element division
+template <typename T>
+__global__ void __launch_bounds__(256) spatial_broadcast_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int hw, int c,
+                                                                    float scale) {
+  constexpr int VEC = Elem<T>::kVec;
+  const int cvn = c / VEC;
+  const int nn = blockIdx.z;
+  T* out = y + (size_t)nn * hw * c;
+  for (int cv = blockIdx.x * blockDim.x + threadIdx.x; cv < cvn; cv += gridDim.x * blockDim.x) {
+    Vec<T> v;
+    v.load(x + (size_t)nn * c + cv * VEC);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v.v[i] *= scale;
+    for (int p = blockIdx.y; p < hw; p += gridDim.y) v.store(out + (size_t)p * c + cv * VEC);
+  }
+}
+
 // ---- bilinear, align_corners=True (same index arithmetic as ATen's upsample_bilinear2d) -----
 struct Lerp {
   int i0, i1;
@@ -126,42 +144,48 @@ __device__ __forceinline__ void lerp_range(int i, float scale, int out_size, int
   *hi = b > out_size - 1 ? out_size - 1 : b;
 }
 
+// One block row = one output row (blockIdx.x = image * ho + oy): the row's interpolation weights are block-uniform and
+// the element index inside the row is 32-bit (the flat 64-bit index with three 64-bit divisions per 16-byte store made
+// this kernel issue-bound at 1.5 TB/s).
 template <typename T>
-__global__ void upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int hi, int wi, int ho,
-                                    int wo, int c, float sh, float sw) {
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int hi, int wi, int ho,
+                                                           int wo, int c, float sh, float sw) {
   constexpr int VEC = Elem<T>::kVec;
   const int cvn = c / VEC;
-  const int64_t total = (int64_t)n * ho * wo * cvn;
-  CVX_GRID_STRIDE(e, total) {
-    const int c0 = (int)(e % cvn) * VEC;
-    int64_t p = e / cvn;
-    const int ox = (int)(p % wo), oy = (int)((p / wo) % ho), nn = (int)(p / ((int64_t)wo * ho));
-    const Lerp ly = lerp_of(oy, sh, hi), lx = lerp_of(ox, sw, wi);
-    const T* base = x + (size_t)nn * hi * wi * c + c0;
+  const int oy = blockIdx.x % ho, nn = blockIdx.x / ho;
+  const Lerp ly = lerp_of(oy, sh, hi);
+  const T* row0 = x + ((size_t)nn * hi + ly.i0) * wi * c;
+  const T* row1 = x + ((size_t)nn * hi + ly.i1) * wi * c;
+  T* out = y + ((size_t)nn * ho + oy) * wo * c;
+  const int per_row = wo * cvn;
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < per_row; e += gridDim.y * blockDim.x) {
+    const int ox = e / cvn, c0 = (e - ox * cvn) * VEC;
+    const Lerp lx = lerp_of(ox, sw, wi);
     Vec<T> a, b, cc, d, o;
-    a.load(base + ((size_t)ly.i0 * wi + lx.i0) * c);
-    b.load(base + ((size_t)ly.i0 * wi + lx.i1) * c);
-    cc.load(base + ((size_t)ly.i1 * wi + lx.i0) * c);
-    d.load(base + ((size_t)ly.i1 * wi + lx.i1) * c);
+    a.load(row0 + (size_t)lx.i0 * c + c0);
+    b.load(row0 + (size_t)lx.i1 * c + c0);
+    cc.load(row1 + (size_t)lx.i0 * c + c0);
+    d.load(row1 + (size_t)lx.i1 * c + c0);
 #pragma unroll
     for (int i = 0; i < VEC; ++i)
       o.v[i] = ly.w0 * (lx.w0 * a.v[i] + lx.w1 * b.v[i]) + ly.w1 * (lx.w0 * cc.v[i] + lx.w1 * d.v[i]);
-    o.store(y + e * VEC);
+    o.store(out + (size_t)e * VEC);
   }
 }
 
+// gradient (gather): one block row = one INPUT row (blockIdx.x = image * hi + iy), 32-bit indexing inside the row
 template <typename T>
-__global__ void upsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int hi, int wi, int ho,
-                                    int wo, int c, float sh, float sw) {
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int hi, int wi, int ho,
+                                                           int wo, int c, float sh, float sw) {
   constexpr int VEC = Elem<T>::kVec;
   const int cvn = c / VEC;
-  const int64_t total = (int64_t)n * hi * wi * cvn;
-  CVX_GRID_STRIDE(e, total) {
-    const int c0 = (int)(e % cvn) * VEC;
-    int64_t p = e / cvn;
-    const int ix = (int)(p % wi), iy = (int)((p / wi) % hi), nn = (int)(p / ((int64_t)wi * hi));
-    int ylo, yhi, xlo, xhi;
-    lerp_range(iy, sh, ho, &ylo, &yhi);
+  const int iy = blockIdx.x % hi, nn = blockIdx.x / hi;
+  int ylo, yhi;
+  lerp_range(iy, sh, ho, &ylo, &yhi);
+  const int per_row = wi * cvn;
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < per_row; e += gridDim.y * blockDim.x) {
+    const int ix = e / cvn, c0 = (e - ix * cvn) * VEC;
+    int xlo, xhi;
     lerp_range(ix, sw, wo, &xlo, &xhi);
     float acc[VEC];
 #pragma unroll
@@ -169,11 +193,12 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx
     for (int oy = ylo; oy <= yhi; ++oy) {
       const float wy = lerp_weight(iy, oy, sh, hi);
       if (wy == 0.f) continue;
+      const T* grow = dy + (((size_t)nn * ho + oy) * wo) * c + c0;
       for (int ox = xlo; ox <= xhi; ++ox) {
         const float wgt = wy * lerp_weight(ix, ox, sw, wi);
         if (wgt == 0.f) continue;
         Vec<T> g;
-        g.load(dy + (((size_t)nn * ho + oy) * wo + ox) * c + c0);
+        g.load(grow + (size_t)ox * c);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = fmaf(wgt, g.v[i], acc[i]);
       }
@@ -181,7 +206,7 @@ __global__ void upsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx
     Vec<T> o;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) o.v[i] = acc[i];
-    o.store(dx + e * VEC);
+    o.store(dx + (((size_t)nn * hi + iy) * wi) * c + (size_t)e * VEC);
   }
 }
 
@@ -444,6 +469,15 @@ int cvx_spatial_reduce(const void* x, void* y, int n, int hw, int c, float scale
 int cvx_spatial_broadcast(const void* x, void* y, int n, int hw, int c, float scale, int dtype, void* stream) {
   CVX_CHECK_ARG(x && y && n > 0 && hw > 0 && c > 0, "spatial_broadcast: bad arguments");
   const int64_t total = (int64_t)n * hw * c;
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  if (c % vec == 0 && n <= 65535 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    const int cvn = c / vec;
+    const int gy = hw < 64 ? hw : 64;              // 64 pixel strips per image: n * 64 * ceil(cvn / 256) blocks
+    const dim3 grid((unsigned)((cvn + 255) / 256), (unsigned)gy, (unsigned)n);
+    CVX_DISPATCH_DTYPE(dtype, T, (spatial_broadcast_vec_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, hw, c, scale)));
+    CVX_LAUNCH_OK();
+    return CVX_OK;
+  }
   CVX_DISPATCH_DTYPE(dtype, T, (spatial_broadcast_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, total, hw, c, scale)));
   CVX_LAUNCH_OK();
   return CVX_OK;
@@ -453,9 +487,11 @@ int cvx_upsample_fwd(const void* x, void* y, int n, int hi, int wi, int ho, int 
   CVX_CHECK_ARG(x && y && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_fwd: bad arguments");
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "upsample_fwd: C=%d not a multiple of %d", c, vec);
-  const int64_t total = (int64_t)n * ho * wo * (c / vec);
-  CVX_DISPATCH_DTYPE(dtype, T, (upsample_fwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
-                                   (const T*)x, (T*)y, n, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+  CVX_CHECK_ARG((int64_t)n * ho < (1ll << 31) && (int64_t)wo * (c / vec) < (1ll << 24), "upsample_fwd: tensor too large");
+  const int per_row = wo * (c / vec);
+  const dim3 grid((unsigned)(n * ho), (unsigned)((per_row + 1023) / 1024));   // 4 elements per thread
+  CVX_DISPATCH_DTYPE(dtype, T, (upsample_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (T*)y, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
@@ -464,9 +500,11 @@ int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, in
   CVX_CHECK_ARG(dy && dx && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_bwd: bad arguments");
   const int vec = dtype == CVX_F32 ? 4 : 8;
   CVX_CHECK_ARG(c % vec == 0, "upsample_bwd: C=%d not a multiple of %d", c, vec);
-  const int64_t total = (int64_t)n * hi * wi * (c / vec);
-  CVX_DISPATCH_DTYPE(dtype, T, (upsample_bwd_kernel<T><<<ew_grid(total), 256, 0, as_stream(stream)>>>(
-                                   (const T*)dy, (T*)dx, n, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+  CVX_CHECK_ARG((int64_t)n * hi < (1ll << 31) && (int64_t)wi * (c / vec) < (1ll << 24), "upsample_bwd: tensor too large");
+  const int per_row = wi * (c / vec);
+  const dim3 grid((unsigned)(n * hi), (unsigned)((per_row + 255) / 256));
+  CVX_DISPATCH_DTYPE(dtype, T, (upsample_bwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(
+                                   (const T*)dy, (T*)dx, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }

@@ -9,6 +9,8 @@ layer runs on the hand-written CUDA kernels behind ``ops.py``; there is no cuDNN
 """
 from functools import partial
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -55,10 +57,13 @@ class MobileNetV2(nn.Module):
         return low_level_features, x
 
 
-def _conv_bn_relu(x, seq, idx=0):
+_GRAD_CHAIN = os.environ.get("CERVIX_GRAD_CHAIN", "1") != "0"      # A/B switch for tools/profile_step.py
+
+
+def _conv_bn_relu(x, seq, idx=0, chain=None):
     conv, bn = seq[idx], seq[idx + 1]
     return ops.conv_bn_act(x, conv.weight, conv.stride[0], conv.padding[0], conv.dilation[0], bn, ops.ACT_RELU, None,
-                           conv.bias)
+                           conv.bias, chain)
 
 
 class ASPP(nn.Module):
@@ -81,8 +86,12 @@ class ASPP(nn.Module):
 
     def forward(self, x):
         n, row, col, c = x.shape  # NHWC
-        outs = [_conv_bn_relu(x, b) for b in (self.branch1, self.branch2, self.branch3, self.branch4)]
-        g = ops.global_avg_pool(x)
+        # five consumers of x: their gradients are summed inside the data-gradient GEMMs' epilogues (ops.GradChain)
+        # instead of by four add passes over the [B,row,col,2048] tensor
+        chain = ops.GradChain(5) if (torch.is_grad_enabled() and x.requires_grad and _GRAD_CHAIN) else None
+        xs = ops.fanout(x, 5) if chain is not None else (x,) * 5
+        outs = [_conv_bn_relu(xi, b, 0, chain) for xi, b in zip(xs, (self.branch1, self.branch2, self.branch3, self.branch4))]
+        g = ops.global_avg_pool(xs[4], chain)
         g = ops.conv2d(g, self.branch5_conv.weight, self.branch5_conv.bias, 1, 0, 1)
         g = ops.batchnorm_act(g, self.branch5_bn, ops.ACT_RELU)
         outs.append(ops.broadcast_hw(g, row, col))

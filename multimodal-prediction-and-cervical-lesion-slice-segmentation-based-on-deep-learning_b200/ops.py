@@ -68,16 +68,87 @@ class ToNCHW(Function):
         return get_backend().to_nhwc(dy.contiguous(), ctx.dtype)
 
 
+class GradChain:
+    """Gradient accumulation of a tensor with several consumers WITHOUT separate add passes (ASPP: five consumers of the
+    [B,32,32,2048] backbone output, deeplabv3_plus.py:89-114 - autograd would sum their gradients with four ATen adds of
+    134 MB tensors each).  The consumers share one chain: each backward adds its gradient to the running sum - the
+    tensor-core data gradient takes the sum as the epilogue's side input (cvx_conv_dgrad_tc_ex), so the add rides a pass
+    that exists anyway - and returns None to autograd until the last consumer hands over the total.  Used with ``fanout``,
+    which gives every consumer its own alias of the tensor."""
+
+    def __init__(self, consumers: int):
+        self.n = self.left = consumers
+        self.acc = None
+
+    def take(self, make):
+        """``make(side)`` -> this consumer's gradient with ``side`` (the running sum, or None) already added."""
+        self.acc = make(self.acc)
+        return self._emit()
+
+    def add(self, dx):
+        """A consumer that cannot add inside its own kernel."""
+        self.acc = dx if self.acc is None else self.acc + dx
+        return self._emit()
+
+    def _emit(self):
+        self.left -= 1
+        if self.left:
+            return None
+        out, self.acc, self.left = self.acc, None, self.n
+        return out
+
+
+class Fanout(Function):
+    """k aliases of one tensor; the backward expects at most one real gradient per chain (see GradChain) and falls back to
+    summing whatever arrives."""
+
+    @staticmethod
+    def forward(ctx, x, k):
+        return tuple(x.view_as(x) for _ in range(k))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        live = [g for g in grads if g is not None]
+        if not live:
+            return None, None
+        total = live[0]
+        for g in live[1:]:
+            total = total + g
+        return total, None
+
+
+_ONES = {}
+
+
+def _ones_f32(n, device):
+    key = (n, str(device))
+    if key not in _ONES:
+        _ONES[key] = torch.ones(n, dtype=torch.float32, device=device)
+    return _ONES[key]
+
+
+def _chained_dgrad(chain, B, dz, wpt, g, tc):
+    """Data gradient of a dense conv, added to the chain's running sum inside the GEMM epilogue when the layer runs on
+    the tensor-core path in bf16 (the side input is bf16); plain add otherwise."""
+    if chain is None:
+        return B.conv_dgrad(dz, wpt, g, tc)
+    if tc and dz.dtype == torch.bfloat16 and hasattr(B, "conv_dgrad_ex"):
+        return chain.take(lambda side: B.conv_dgrad(dz, wpt, g, tc) if side is None
+                          else B.conv_dgrad_ex(dz, wpt, g, None, side.contiguous(), _ones_f32(g.cin, dz.device)))
+    return chain.add(B.conv_dgrad(dz, wpt, g, tc))
+
+
 class Conv2d(Function):
     """Dense nn.Conv2d (groups=1) on NHWC.  weight: fp32 OIHW parameter; bias: fp32 or None."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, dil):
+    def forward(ctx, x, weight, bias, stride, pad, dil, chain=None):
         B = get_backend()
         x = x.contiguous()
         n, h, w, cin = x.shape
         cout, cin_w, kh, kw = weight.shape
         assert cin_w == cin, "conv: channel mismatch %d vs %d" % (cin_w, cin)
+        ctx.chain = chain
         tc = _tc_ok(x, cin, cout)
         sub = 1
         if tc and stride != 1 and kh == 1 and kw == 1 and pad == 0:
@@ -105,15 +176,18 @@ class Conv2d(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             wpt = B.pack_weight(weight.detach(), dy.dtype, True)
-            dx = B.conv_dgrad(dy, wpt, g, tc)
             if ctx.sub != 1:
-                dx = B.subsample_bwd(dx, ctx.in_hw[0], ctx.in_hw[1], ctx.sub)
+                dx = B.subsample_bwd(B.conv_dgrad(dy, wpt, g, tc), ctx.in_hw[0], ctx.in_hw[1], ctx.sub)
+                if ctx.chain is not None:
+                    dx = ctx.chain.add(dx)
+            else:
+                dx = _chained_dgrad(ctx.chain, B, dy, wpt, g, tc)
         if ctx.needs_input_grad[1]:
             dwp = B.conv_wgrad(x, dy, g, tc)
             dw = B.unpack_wgrad(dwp, g.cout, g.cin, g.kh, g.kw)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = B.bias_grad(dy)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class ConvBnAct(Function):
@@ -124,8 +198,9 @@ class ConvBnAct(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, running_mean, running_var, residual, stride, pad, dil, momentum, eps,
-                act):
+                act, chain=None):
         B = get_backend()
+        ctx.chain = chain
         x = x.contiguous()
         n, h, w, cin = x.shape
         cout, _, kh, kw = weight.shape
@@ -161,14 +236,17 @@ class ConvBnAct(Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             wpt = B.pack_weight(weight.detach(), dz.dtype, True)
-            dx = B.conv_dgrad(dz, wpt, g, tc)
             if ctx.sub != 1:
-                dx = B.subsample_bwd(dx, ctx.in_hw[0], ctx.in_hw[1], ctx.sub)
+                dx = B.subsample_bwd(B.conv_dgrad(dz, wpt, g, tc), ctx.in_hw[0], ctx.in_hw[1], ctx.sub)
+                if ctx.chain is not None:
+                    dx = ctx.chain.add(dx)
+            else:
+                dx = _chained_dgrad(ctx.chain, B, dz, wpt, g, tc)
         if ctx.needs_input_grad[1]:
             dw = B.unpack_wgrad(B.conv_wgrad(x, dz, g, tc), g.cout, g.cin, g.kh, g.kw)
         db = B.bias_grad(dz) if (ctx.has_bias and ctx.needs_input_grad[2]) else None   # (sums to ~0 behind a BatchNorm)
         return (dx, dw, db, dgamma if ctx.needs_input_grad[3] else None, dbeta if ctx.needs_input_grad[4] else None,
-                None, None, dres, None, None, None, None, None, None)
+                None, None, dres, None, None, None, None, None, None, None)
 
 
 class MaxPool3x3S2(Function):
@@ -314,15 +392,17 @@ class GlobalAvgPool(Function):
     """torch.mean over H then W with keepdim (ASPP branch 5)."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, chain=None):
         n, h, w, c = x.shape
         ctx.hw = (h, w)
+        ctx.chain = chain
         return get_backend().spatial_reduce(x.contiguous(), 1.0 / (h * w))
 
     @staticmethod
     def backward(ctx, dy):
         h, w = ctx.hw
-        return get_backend().spatial_broadcast(dy.contiguous(), h, w, 1.0 / (h * w))
+        dx = get_backend().spatial_broadcast(dy.contiguous(), h, w, 1.0 / (h * w))
+        return (dx if ctx.chain is None else ctx.chain.add(dx)), None
 
 
 class BroadcastHW(Function):
@@ -429,8 +509,13 @@ def cut_point(x, tag: str):
     return proxy
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1):
-    return Conv2d.apply(x, weight, bias, stride, pad, dil)
+def conv2d(x, weight, bias=None, stride=1, pad=0, dil=1, chain=None):
+    return Conv2d.apply(x, weight, bias, stride, pad, dil, chain)
+
+
+def fanout(x, k: int):
+    """k aliases of ``x`` for k consumers that share a ``GradChain``."""
+    return Fanout.apply(x, k)
 
 
 def dwconv3x3(x, weight, stride=1, pad=1, dil=1, relu_in=False):
@@ -477,7 +562,8 @@ def batchnorm_act(x, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None):
 _CONV_BN_MIN_K = int(os.environ.get("CERVIX_CONV_BN_MINK", str(1 << 30)))
 
 
-def conv_bn_act(x, conv_weight, stride, pad, dil, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None, bias=None):
+def conv_bn_act(x, conv_weight, stride, pad, dil, bn: torch.nn.BatchNorm2d, act=ACT_NONE, residual=None, bias=None,
+                chain=None):
     """``act(bn(conv(x)) + residual)``: one composite with the BatchNorm statistics from the GEMM
     epilogue when the layer trains on the tensor-core path, else ``conv2d`` followed by ``batchnorm_act``."""
     cout, cin, kh, kw = conv_weight.shape
@@ -487,12 +573,12 @@ def conv_bn_act(x, conv_weight, stride, pad, dil, bn: torch.nn.BatchNorm2d, act=
              and (stride == 1 or (kh == 1 and kw == 1 and pad == 0) or stride == 2)
              and x.shape[0] * x.shape[1] * x.shape[2] >= 1024)
     if not fused:
-        return batchnorm_act(conv2d(x, conv_weight, bias, stride, pad, dil), bn, act, residual)
+        return batchnorm_act(conv2d(x, conv_weight, bias, stride, pad, dil, chain), bn, act, residual)
     if bn.track_running_stats and bn.num_batches_tracked is not None and not _DEFER_NBT[0]:
         bn.num_batches_tracked.add_(1)
     momentum = _bn_momentum(bn)
     return ConvBnAct.apply(x, conv_weight, bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, stride,
-                           pad, dil, momentum, bn.eps, act)
+                           pad, dil, momentum, bn.eps, act, chain)
 
 
 def relu(x):
@@ -507,8 +593,8 @@ def cat_channels(xs):
     return CatChannels.apply(*xs)
 
 
-def global_avg_pool(x):
-    return GlobalAvgPool.apply(x)
+def global_avg_pool(x, chain=None):
+    return GlobalAvgPool.apply(x, chain)
 
 
 def broadcast_hw(x, h, w):
