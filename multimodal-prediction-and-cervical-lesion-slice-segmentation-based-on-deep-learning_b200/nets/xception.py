@@ -55,6 +55,9 @@ class SeparableConv2d(nn.Module):
         return ops.conv_bn_act(y, self.pointwise.weight, 1, 0, 1, self.bn2, out_act, residual)
 
 
+_GRAD_CHAIN = os.environ.get("CERVIX_GRAD_CHAIN", "1") != "0"      # A/B switch (tools/profile_step.py)
+
+
 class Block(nn.Module):
     def __init__(self, in_filters, out_filters, strides=1, atrous=None, grow_first=True, activate_first=True,
                  inplace=True):
@@ -92,16 +95,28 @@ class Block(nn.Module):
             return ops_fused.sep_chain(seps, inp, None, True, out_act)
         if self.skip is not None:
             s = self.skip
-            skip = ops.conv_bn_act(inp, s.weight, s.stride[0], 0, 1, self.skipbn, ops.ACT_NONE)
-            if fuse and ops_fused.chain_fusable(seps, inp):
-                self.hook_layer = None          # stride-1 block with a 1x1 skip (block20): all three fused
-                return ops_fused.sep_chain(seps, inp, skip, False, out_act)
-            if fuse and ops_fused.chain_fusable(seps[:2], inp):
+            fuse3 = fuse and ops_fused.chain_fusable(seps, inp)
+            fuse2 = fuse and not fuse3 and ops_fused.chain_fusable(seps[:2], inp)
+            # the block input has two consumers (skip conv, separable chain): one shared GradChain lets the later
+            # backward add the earlier one's gradient inside its own kernel instead of autograd adding two tensors
+            chain = ops.GradChain(2) if ((fuse3 or fuse2) and _GRAD_CHAIN and inp.requires_grad) else None
+            a, b = ops.fanout(inp, 2) if chain is not None else (inp, inp)
+            if fuse3:
+                # stride-1 block with a 1x1 skip (block20): all three fused.  Backward order is forced by the data flow
+                # (the chain hands the skip its gradient): the skip conv's data gradient takes the chain's as side input
+                skip = ops.conv_bn_act(a, s.weight, s.stride[0], 0, 1, self.skipbn, ops.ACT_NONE, chain=chain)
+                self.hook_layer = None
+                return ops_fused.sep_chain(seps, b, skip, False, out_act, chain)
+            if fuse2:
                 # entry-flow blocks: the first two (full-resolution) separable convs fused, their pre-ReLU output
-                # materialised once (it is block2's low-level feature), the strided third one on the operator path
-                x = ops_fused.sep_chain(seps[:2], inp, None, False, ops.ACT_NONE)
+                # materialised once (it is block2's low-level feature), the strided third one on the operator path.
+                # The skip conv is created AFTER the chain so that its backward runs first (autograd runs ready nodes
+                # latest-created first) and the chain's depthwise backward adds its gradient as the addend.
+                x = ops_fused.sep_chain(seps[:2], b, None, False, ops.ACT_NONE, chain)
+                skip = ops.conv_bn_act(a, s.weight, s.stride[0], 0, 1, self.skipbn, ops.ACT_NONE, chain=chain)
                 self.hook_layer = x
                 return self.sepconv3(x, residual=skip, out_act=out_act)
+            skip = ops.conv_bn_act(inp, s.weight, s.stride[0], 0, 1, self.skipbn, ops.ACT_NONE)
         else:
             if not inp_is_relu:
                 inp = ops.relu(inp)

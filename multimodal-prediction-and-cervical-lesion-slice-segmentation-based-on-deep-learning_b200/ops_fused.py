@@ -113,9 +113,10 @@ class SepChainFn(Function):
          strided third separable conv runs on the operator path)."""
 
     @staticmethod
-    def forward(ctx, inp, residual, res_is_inp: bool, act: int, buffers: Sequence[BnBuffers], *params):
+    def forward(ctx, inp, residual, res_is_inp: bool, act: int, buffers: Sequence[BnBuffers], chain, *params):
         B = get_backend()
         inp = inp.contiguous()
+        ctx.chain = chain          # ops.GradChain shared with the block's 1x1 skip conv (both consume the block input)
         K = len(params) // PARAMS_PER_SEP
         x, sc, sh = inp, None, None
         seps: List[_Sep] = []
@@ -160,7 +161,12 @@ class SepChainFn(Function):
                 x, sc, sh = prev.p, prev.scale2, prev.shift2
             else:
                 x, sc, sh = inp, None, None
-            addend = gres if (k == 0 and ctx.res_is_inp) else None
+            addend = None
+            if k == 0:
+                # what else flows into the block input is added by the depthwise backward kernel itself: the identity
+                # skip's gradient, or the running sum of the other consumers' gradients (the 1x1 skip conv's, if its
+                # backward has already run)
+                addend = gres if ctx.res_is_inp else (ctx.chain.acc if ctx.chain is not None else None)
             gx, sums, d_dw, d_g1, d_b1, d_pw = _sep_backward(B, s, dp, x, sc, sh, True, params[base + 3], addend, k > 0)
             grads[base + 0], grads[base + 1], grads[base + 2], grads[base + 3] = d_dw, d_g1, d_b1, d_pw
             if k > 0:
@@ -169,9 +175,9 @@ class SepChainFn(Function):
                 dp, _ = B.bn_bwd_affine(gx, None, prev.p, a, b, cc, ACT_NONE, False)
                 grads[pbase + 4], grads[pbase + 5] = dgam, dbet
             else:
-                dinp = gx
+                dinp = gx if ctx.chain is None else ctx.chain.take(lambda _sum_already_inside: gx)
         dres = gres if (ctx.has_res and not ctx.res_is_inp) else None
-        return (dinp, dres, None, None, None, *grads)
+        return (dinp, dres, None, None, None, None, *grads)
 
 
 def sep_params(sep) -> list:
@@ -199,7 +205,7 @@ def identity_block_fusable(block, inp: torch.Tensor) -> bool:
     return block.skip is None and chain_fusable((block.sepconv1, block.sepconv2, block.sepconv3), inp)
 
 
-def sep_chain(seps, inp: torch.Tensor, residual: Optional[torch.Tensor], res_is_inp: bool, act: int) -> torch.Tensor:
+def sep_chain(seps, inp: torch.Tensor, residual: Optional[torch.Tensor], res_is_inp: bool, act: int, chain=None) -> torch.Tensor:
     buffers, params = [], []
     for sep in seps:
         buffers += [BnBuffers(sep.bn1), BnBuffers(sep.bn2)]
@@ -207,7 +213,7 @@ def sep_chain(seps, inp: torch.Tensor, residual: Optional[torch.Tensor], res_is_
         for bn in (sep.bn1, sep.bn2):
             if bn.track_running_stats and bn.num_batches_tracked is not None and not ops._DEFER_NBT[0]:
                 bn.num_batches_tracked.add_(1)
-    return SepChainFn.apply(inp, residual, res_is_inp, act, buffers, *params)
+    return SepChainFn.apply(inp, residual, res_is_inp, act, buffers, chain, *params)
 
 
 def identity_block(block, inp: torch.Tensor, relu_out: bool) -> torch.Tensor:

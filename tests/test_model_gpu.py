@@ -179,3 +179,28 @@ def test_trainer_gradient_gather_matches_accumulate_path():
         check_flat(graphed)    # the captured gather reads the addresses the captured backward writes
         b = eager.step(imgs, pngs)
         assert torch.allclose(a[:3], b[:3], rtol=5e-2, atol=1e-4), (a, b)   # bf16 trajectories drift; exactness is check_flat
+
+
+@pytest.mark.parametrize("bb", ["xception", "mobilenet"])
+def test_gradient_chains_equal_autograd_accumulation(monkeypatch, bb):
+    """Tensors with several consumers (ASPP's input; the inputs of Xception's blocks with a 1x1 skip) have their gradient
+    summed inside the consuming kernels (ops.GradChain: the tcgen05 data gradient's side input, the depthwise backward's
+    addend) instead of by autograd's add passes.  Same forward bit for bit; the bf16 gradients differ only by where the sum
+    is rounded (once from the fp32 accumulator instead of twice)."""
+    import cervix_b200.nets.deeplabv3_plus as dl
+    import cervix_b200.nets.xception as xc
+    imgs, pngs, _ = O.synthetic_batch(4, 96, seed=5)
+    imgs, pngs = imgs.cuda(), pngs.cuda()
+    res = {}
+    for on in (True, False):
+        monkeypatch.setattr(dl, "_GRAD_CHAIN", on)
+        monkeypatch.setattr(xc, "_GRAD_CHAIN", on)
+        model = build(bb, 16, 3, torch.bfloat16, train=True)
+        out = model(imgs)
+        ce, focal, dice, _ = seg_objective(out, pngs, None, CLS_W.cuda(), 5)
+        (focal + dice).backward()
+        res[on] = (out.detach().clone(), torch.cat([p.grad.reshape(-1) for p in model.parameters()]))
+    assert torch.equal(res[True][0], res[False][0])
+    ga, gb = res[True][1].double(), res[False][1].double()
+    assert float((ga - gb).norm() / gb.norm()) < 2e-2
+    assert float(torch.nn.functional.cosine_similarity(ga, gb, dim=0)) > 0.9995

@@ -113,3 +113,39 @@ def test_misc_ops():
     c = ops.relu(ops.cat_channels([a, b])); gc = torch.randn_like(c); c.backward(gc)
     cr = F.relu(torch.cat([a.detach(), b.detach()], 3))
     assert close(c, cr) and close(a.grad, (gc * (cr > 0))[..., :8]) and close(b.grad, (gc * (cr > 0))[..., 8:])
+
+
+# ---- gradient chains: several consumers of one tensor, summed without separate add passes -----------------------------
+def test_grad_chain_hands_over_the_total_once_and_resets():
+    from cervix_b200 import ops
+    ch = ops.GradChain(3)
+    a, b, c = torch.ones(2), 2 * torch.ones(2), 4 * torch.ones(2)
+    assert ch.add(a) is None
+    assert ch.take(lambda side: side + b) is None            # a consumer that adds the running sum inside its own kernel
+    assert torch.equal(ch.add(c), 7 * torch.ones(2))
+    assert ch.acc is None and ch.left == 3                   # ready for a second backward over a retained graph
+    assert ch.take(lambda side: a if side is None else side + a) is None
+
+
+def test_aspp_with_and_without_the_gradient_chain(monkeypatch):
+    """ASPP's five consumers of the backbone output (deeplabv3_plus.py:89-114): with the chain every consumer but the
+    last returns None to autograd and the total arrives once; same input gradient and parameter gradients as autograd's own
+    accumulation."""
+    import cervix_b200.nets.deeplabv3_plus as dl
+    prev = backend.set_backend(EmuBackend())
+    try:
+        res = {}
+        for on in (True, False):
+            monkeypatch.setattr(dl, "_GRAD_CHAIN", on)
+            torch.manual_seed(0)
+            aspp = dl.ASPP(16, 8, rate=1).train()
+            x = torch.randn(2, 9, 9, 16).requires_grad_(True)
+            y = aspp(x)
+            y.mul(torch.linspace(-1, 1, y.numel()).view_as(y)).sum().backward()
+            res[on] = (y.detach(), x.grad.clone(), {k: p.grad.clone() for k, p in aspp.named_parameters()})
+        assert torch.equal(res[True][0], res[False][0])
+        assert torch.allclose(res[True][1], res[False][1], rtol=1e-5, atol=1e-6)
+        for k in res[True][2]:
+            assert torch.allclose(res[True][2][k], res[False][2][k], rtol=1e-5, atol=1e-6), k
+    finally:
+        backend.set_backend(prev)
