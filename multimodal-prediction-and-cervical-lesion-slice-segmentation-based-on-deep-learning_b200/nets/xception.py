@@ -55,7 +55,8 @@ class SeparableConv2d(nn.Module):
         return ops.conv_bn_act(y, self.pointwise.weight, 1, 0, 1, self.bn2, out_act, residual)
 
 
-_GRAD_CHAIN = os.environ.get("CERVIX_GRAD_CHAIN", "1") != "0"      # A/B switch (tools/profile_step.py)
+# gradient chains for the inputs of the blocks with a 1x1 skip: CERVIX_GRAD_CHAIN=2 (A/B switch)
+_GRAD_CHAIN = os.environ.get("CERVIX_GRAD_CHAIN", "1") == "2"
 
 
 class Block(nn.Module):

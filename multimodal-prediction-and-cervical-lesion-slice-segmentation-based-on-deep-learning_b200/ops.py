@@ -104,6 +104,7 @@ class Fanout(Function):
 
     @staticmethod
     def forward(ctx, x, k):
+        ctx.set_materialize_grads(False)      # consumers that handed their gradient to the chain return None: keep it None
         return tuple(x.view_as(x) for _ in range(k))
 
     @staticmethod
