@@ -181,6 +181,8 @@ class CudaBackend:
 
     def unpack_wgrad(self, g: torch.Tensor, cout, cin, kh, kw) -> torch.Tensor:
         self._chk(g)
+        if kh * kw == 1 and g.dtype == torch.float32:
+            return g.view(cout, cin, 1, 1)          # the packed [1][cout][cin] layout of a 1x1 filter IS its OIHW layout
         out = torch.empty((cout, cin, kh, kw), dtype=torch.float32, device=g.device)
         check(self.lib.cvx_unpack_wgrad(_p(g), _p(out), cout, cin, kh, kw, self._stream()), "cvx_unpack_wgrad")
         return out
