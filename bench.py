@@ -456,27 +456,30 @@ def augment_leg(batch: int, size: int, peaks):
         return D.pack_batch([(a, b, D.draw_params(b.shape[1], b.shape[0], (size, size))) for a, b in srcs], (size, size))
 
     pack()
-    t0 = time.perf_counter()
-    reps = 5
-    plans = [pack().pin_memory() for _ in range(reps)]          # fresh random sizes every time: the table cache mostly misses
-    host_ms = (time.perf_counter() - t0) / reps * 1e3
+    reps = 8
+    plans, host_t = [], []
+    for _ in range(reps):                     # fresh random sizes every time: the table cache mostly misses
+        t0 = time.perf_counter()
+        plans.append(pack().pin_memory())
+        host_t.append((time.perf_counter() - t0) * 1e3)
+    host_ms = sorted(host_t)[reps // 2]
     aug = D.DeviceAugmenter("cuda")
     for p in plans[:2]:
         aug.run(p)
     torch.cuda.synchronize()
-    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    e[0].record()
-    for p in plans:
-        aug.run(p)
-    e[1].record()
+
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # medians over the batches: the four launches of a batch are enqueued from Python, so a busy host core shows up as
+    # idle gaps between them in a mean
+    ms_e2e = sorted(timed(lambda: aug.run(p)) for p in plans)[reps // 2]
     blobs = [aug.upload(p) for p in plans]
     torch.cuda.synchronize()
-    e[2].record()
-    for p, b in zip(plans, blobs):
-        aug.run(p, b)
-    e[3].record()
-    torch.cuda.synchronize()
-    ms_e2e, ms_dev = e[0].elapsed_time(e[1]) / reps, e[2].elapsed_time(e[3]) / reps
+    ms_dev = sorted(timed(lambda: aug.run(p, b)) for p, b in zip(plans, blobs))[reps // 2]
     src_bytes = sum(int(p.src.numel()) for p in plans) / reps
     out_bytes = batch * size * size * 4
     res = {"what": "get_random_data for a batch of %d decoded images (375x500 / 500x375) onto %dx%d canvases: bicubic + "
