@@ -225,7 +225,8 @@ def test_freeze_then_unfreeze_keeps_optimizer_state_and_skips_frozen_parameters(
     assert len(tr.runs) >= 2 and sorted(int(c) for c in tr.step_devs.tolist()) == [1, 4]
     # the head's first moment moved on from where it was (b1 * m + (1 - b1) * g), it was not reset to (1 - b1) * g
     g_head = tr.flat.grad[~is_bb]
-    assert torch.allclose(tr.m[~is_bb], 0.9 * m_head + 0.1 * (g_head + 1e-2 * w1[~is_bb]), rtol=1e-4, atol=1e-7)
+    want_m = 0.9 * m_head + 0.1 * (g_head + 1e-2 * w1[~is_bb])
+    assert bool(((tr.m[~is_bb] - want_m).abs() <= 1e-5 * (m_head.abs() + g_head.abs() + 1e-2 * w1[~is_bb].abs()) + 1e-8).all())
 
 
 def test_trainer_state_roundtrip_resumes_bit_exactly():
@@ -280,10 +281,13 @@ def test_two_graph_split_backward_equals_the_single_backward():
     two.set_lr(1e-2)
     w0, m0 = two.flat.data.clone(), two.m.clone()
     two.step_graphed(imgs, pngs)
-    m1 = 0.9 * m0 + two.flat.grad
-    assert torch.allclose(two.m, m1, rtol=1e-6, atol=1e-8)
-    upd = two.flat.grad + 0.9 * m1 if two.nesterov else m1
-    assert torch.allclose(two.flat.data, w0 - 1e-2 * upd, rtol=1e-5, atol=1e-7)
+    g = two.flat.grad
+    m1 = 0.9 * m0 + g
+    # tolerances relative to the OPERANDS (the kernel fuses multiply-adds; where 0.9 m0 and g cancel, the result's own
+    # magnitude says nothing about the rounding)
+    assert bool(((two.m - m1).abs() <= 1e-6 * (m0.abs() + g.abs()) + 1e-9).all())
+    upd = g + 0.9 * m1 if two.nesterov else m1
+    assert bool(((two.flat.data - (w0 - 1e-2 * upd)).abs() <= 1e-6 * (w0.abs() + 1e-2 * (g.abs() + m1.abs())) + 1e-9).all())
     assert float((two.flat.data[:hi_b] - w0[:hi_b]).abs().max()) > 0 and float((two.flat.data[lo_a:] - w0[lo_a:]).abs().max()) > 0
     # a model without a cut (MobileNetV2) declines, and the caller falls back to the one-graph step
     assert SegTrainer(_small_model(torch.float32, bb="mobilenet"), **kw).capture_split(imgs, pngs, None, warmup=1) is None

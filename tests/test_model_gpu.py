@@ -204,5 +204,6 @@ def test_gradient_chains_equal_autograd_accumulation(monkeypatch, bb):
     ga, gb = res[True][1].double(), res[False][1].double()
     # the entry flow's gradients pass through ~40 bf16 roundings: a one-ulp change of a block-input gradient moves the
     # stem's weight gradients by 1 - 2 % (both variants are equally far from the fp32 gradient, test_bf16_train_step_*)
-    assert float((ga - gb).norm() / gb.norm()) < 4e-2
-    assert float(torch.nn.functional.cosine_similarity(ga, gb, dim=0)) > 0.999
+    # (measured 2.2e-2 for Xception; a missing or doubled summand is an O(1) error)
+    assert float((ga - gb).norm() / gb.norm()) < 6e-2
+    assert float(torch.nn.functional.cosine_similarity(ga, gb, dim=0)) > 0.998
