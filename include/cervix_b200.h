@@ -155,6 +155,13 @@ CVX_API int cvx_spatial_broadcast(const void* x, void* y, int n, int hw, int c, 
 /* F.interpolate(mode='bilinear', align_corners=True) on NHWC (deeplabv3_plus.py:184) */
 CVX_API int cvx_upsample_fwd(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
 CVX_API int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
+/* The decoder's x4 upsample written straight into the concat buffer (deeplabv3_plus.py:184-185: F.interpolate followed
+ * by torch.cat): channels [c_off, c_off + c) of y[n,ho,wo,c_total] = bilinear(x[n,hi,wi,c]); and its gradient read from
+ * the same channel slice of dy[n,ho,wo,c_total].  c, c_total, c_off multiples of the 16-byte vector (8 bf16 / 4 fp32). */
+CVX_API int cvx_upsample_into(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int c_total, int c_off,
+                              int dtype, void* stream);
+CVX_API int cvx_upsample_from_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int c_total,
+                                  int c_off, int dtype, void* stream);
 /* final upsample fused with the NHWC->NCHW fp32 conversion (deeplabv3_plus.py:187) */
 CVX_API int cvx_upsample_to_nchw_fwd(const void* x, float* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);
 CVX_API int cvx_upsample_to_nchw_bwd(const float* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream);

@@ -87,6 +87,8 @@ PROTOTYPES = {
     "cvx_spatial_broadcast": [_P, _P, _I, _I, _I, _F, _I, _P],
     "cvx_upsample_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cvx_upsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_upsample_into": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "cvx_upsample_from_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "cvx_upsample_to_nchw_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cvx_upsample_to_nchw_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "cvx_maxpool3x3s2_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],

@@ -395,6 +395,27 @@ class CudaBackend:
         check(self.lib.cvx_upsample_bwd(_p(dy), _p(dx), n, hi, wi, ho, wo, c, _dt(dy), self._stream()), "cvx_upsample_bwd")
         return dx
 
+    def upsample_concat(self, x, tail):
+        """cat([bilinear(x -> tail's size), tail], channels) without materialising the upsampled tensor: the upsample
+        kernel writes its channel slice of the concat buffer (deeplabv3_plus.py:184-185)."""
+        self._chk(x, tail)
+        n, hi, wi, c = x.shape
+        _, ho, wo, ct = tail.shape
+        y = torch.empty((n, ho, wo, c + ct), dtype=x.dtype, device=x.device)
+        st = self._stream()
+        check(self.lib.cvx_upsample_into(_p(x), _p(y), n, hi, wi, ho, wo, c, c + ct, 0, _dt(x), st), "cvx_upsample_into")
+        check(self.lib.cvx_copy_channels(_p(tail), ct, 0, _p(y), c + ct, c, n * ho * wo, ct, _dt(x), st), "cvx_copy_channels")
+        return y
+
+    def upsample_concat_bwd(self, dy, c: int, hi: int, wi: int):
+        """-> (gradient of the low-resolution input, gradient of the concatenated tail)."""
+        self._chk(dy)
+        n, ho, wo, ctot = dy.shape
+        dx = torch.empty((n, hi, wi, c), dtype=dy.dtype, device=dy.device)
+        check(self.lib.cvx_upsample_from_bwd(_p(dy), _p(dx), n, hi, wi, ho, wo, c, ctot, 0, _dt(dy), self._stream()),
+              "cvx_upsample_from_bwd")
+        return dx, self.slice_channels(dy, c, ctot - c)
+
     def upsample_to_nchw_fwd(self, x, ho: int, wo: int):
         self._chk(x)
         n, hi, wi, c = x.shape

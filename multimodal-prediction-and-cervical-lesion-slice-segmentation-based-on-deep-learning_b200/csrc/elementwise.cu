@@ -149,14 +149,14 @@ __device__ __forceinline__ void lerp_range(int i, float scale, int out_size, int
 // this kernel issue-bound at 1.5 TB/s).
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int hi, int wi, int ho,
-                                                           int wo, int c, float sh, float sw) {
+                                                           int wo, int c, float sh, float sw, int ldy, int yoff) {
   constexpr int VEC = Elem<T>::kVec;
   const int cvn = c / VEC;
   const int oy = blockIdx.x % ho, nn = blockIdx.x / ho;
   const Lerp ly = lerp_of(oy, sh, hi);
   const T* row0 = x + ((size_t)nn * hi + ly.i0) * wi * c;
   const T* row1 = x + ((size_t)nn * hi + ly.i1) * wi * c;
-  T* out = y + ((size_t)nn * ho + oy) * wo * c;
+  T* out = y + ((size_t)nn * ho + oy) * wo * ldy + yoff;   // ldy > c: a channel slice of a wider (concat) tensor
   const int per_row = wo * cvn;
   for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < per_row; e += gridDim.y * blockDim.x) {
     const int ox = e / cvn, c0 = (e - ox * cvn) * VEC;
@@ -169,14 +169,14 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const T* __restrict__
 #pragma unroll
     for (int i = 0; i < VEC; ++i)
       o.v[i] = ly.w0 * (lx.w0 * a.v[i] + lx.w1 * b.v[i]) + ly.w1 * (lx.w0 * cc.v[i] + lx.w1 * d.v[i]);
-    o.store(out + (size_t)e * VEC);
+    o.store(out + (size_t)ox * ldy + c0);
   }
 }
 
 // gradient (gather): one block row = one INPUT row (blockIdx.x = image * hi + iy), 32-bit indexing inside the row
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int hi, int wi, int ho,
-                                                           int wo, int c, float sh, float sw) {
+                                                           int wo, int c, float sh, float sw, int lddy, int dyoff) {
   constexpr int VEC = Elem<T>::kVec;
   const int cvn = c / VEC;
   const int iy = blockIdx.x % hi, nn = blockIdx.x / hi;
@@ -193,12 +193,12 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const T* __restrict__
     for (int oy = ylo; oy <= yhi; ++oy) {
       const float wy = lerp_weight(iy, oy, sh, hi);
       if (wy == 0.f) continue;
-      const T* grow = dy + (((size_t)nn * ho + oy) * wo) * c + c0;
+      const T* grow = dy + (((size_t)nn * ho + oy) * wo) * lddy + dyoff + c0;
       for (int ox = xlo; ox <= xhi; ++ox) {
         const float wgt = wy * lerp_weight(ix, ox, sw, wi);
         if (wgt == 0.f) continue;
         Vec<T> g;
-        g.load(grow + (size_t)ox * c);
+        g.load(grow + (size_t)ox * lddy);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = fmaf(wgt, g.v[i], acc[i]);
       }
@@ -483,30 +483,52 @@ int cvx_spatial_broadcast(const void* x, void* y, int n, int hw, int c, float sc
   return CVX_OK;
 }
 
-int cvx_upsample_fwd(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream) {
-  CVX_CHECK_ARG(x && y && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_fwd: bad arguments");
+static int upsample_fwd_launch(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int ldy, int yoff,
+                               int dtype, void* stream, const char* who) {
+  CVX_CHECK_ARG(x && y && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "%s: bad arguments", who);
   const int vec = dtype == CVX_F32 ? 4 : 8;
-  CVX_CHECK_ARG(c % vec == 0, "upsample_fwd: C=%d not a multiple of %d", c, vec);
-  CVX_CHECK_ARG((int64_t)n * ho < (1ll << 31) && (int64_t)wo * (c / vec) < (1ll << 24), "upsample_fwd: tensor too large");
+  CVX_CHECK_ARG(c % vec == 0 && ldy % vec == 0 && yoff % vec == 0 && yoff >= 0 && yoff + c <= ldy,
+                "%s: C=%d, row pitch %d and channel offset %d must be multiples of %d", who, c, ldy, yoff, vec);
+  CVX_CHECK_ARG((int64_t)n * ho < (1ll << 31) && (int64_t)wo * (c / vec) < (1ll << 24), "%s: tensor too large", who);
   const int per_row = wo * (c / vec);
   const dim3 grid((unsigned)(n * ho), (unsigned)((per_row + 1023) / 1024));   // 4 elements per thread
   CVX_DISPATCH_DTYPE(dtype, T, (upsample_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(
-                                   (const T*)x, (T*)y, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+                                   (const T*)x, (T*)y, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo), ldy, yoff)));
   CVX_LAUNCH_OK();
   return CVX_OK;
 }
 
-int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream) {
-  CVX_CHECK_ARG(dy && dx && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "upsample_bwd: bad arguments");
+static int upsample_bwd_launch(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int lddy, int dyoff,
+                               int dtype, void* stream, const char* who) {
+  CVX_CHECK_ARG(dy && dx && n > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && c > 0, "%s: bad arguments", who);
   const int vec = dtype == CVX_F32 ? 4 : 8;
-  CVX_CHECK_ARG(c % vec == 0, "upsample_bwd: C=%d not a multiple of %d", c, vec);
-  CVX_CHECK_ARG((int64_t)n * hi < (1ll << 31) && (int64_t)wi * (c / vec) < (1ll << 24), "upsample_bwd: tensor too large");
+  CVX_CHECK_ARG(c % vec == 0 && lddy % vec == 0 && dyoff % vec == 0 && dyoff >= 0 && dyoff + c <= lddy,
+                "%s: C=%d, row pitch %d and channel offset %d must be multiples of %d", who, c, lddy, dyoff, vec);
+  CVX_CHECK_ARG((int64_t)n * hi < (1ll << 31) && (int64_t)wi * (c / vec) < (1ll << 24), "%s: tensor too large", who);
   const int per_row = wi * (c / vec);
   const dim3 grid((unsigned)(n * hi), (unsigned)((per_row + 255) / 256));
   CVX_DISPATCH_DTYPE(dtype, T, (upsample_bwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>(
-                                   (const T*)dy, (T*)dx, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo))));
+                                   (const T*)dy, (T*)dx, hi, wi, ho, wo, c, lerp_scale(hi, ho), lerp_scale(wi, wo), lddy, dyoff)));
   CVX_LAUNCH_OK();
   return CVX_OK;
+}
+
+int cvx_upsample_fwd(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream) {
+  return upsample_fwd_launch(x, y, n, hi, wi, ho, wo, c, c, 0, dtype, stream, "upsample_fwd");
+}
+
+int cvx_upsample_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int dtype, void* stream) {
+  return upsample_bwd_launch(dy, dx, n, hi, wi, ho, wo, c, c, 0, dtype, stream, "upsample_bwd");
+}
+
+int cvx_upsample_into(const void* x, void* y, int n, int hi, int wi, int ho, int wo, int c, int c_total, int c_off, int dtype,
+                      void* stream) {
+  return upsample_fwd_launch(x, y, n, hi, wi, ho, wo, c, c_total, c_off, dtype, stream, "upsample_into");
+}
+
+int cvx_upsample_from_bwd(const void* dy, void* dx, int n, int hi, int wi, int ho, int wo, int c, int c_total, int c_off,
+                          int dtype, void* stream) {
+  return upsample_bwd_launch(dy, dx, n, hi, wi, ho, wo, c, c_total, c_off, dtype, stream, "upsample_from_bwd");
 }
 
 int cvx_upsample_to_nchw_fwd(const void* x, float* y, int n, int hi, int wi, int ho, int wo, int c, int dtype,

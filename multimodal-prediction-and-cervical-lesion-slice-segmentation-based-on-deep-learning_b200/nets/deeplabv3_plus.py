@@ -140,8 +140,7 @@ class DeepLab(nn.Module):
         low_level_features, x = self.backbone(x)
         x = self.aspp(x)
         low_level_features = _conv_bn_relu(low_level_features, self.shortcut_conv)
-        x = ops.upsample_bilinear(x, low_level_features.shape[1], low_level_features.shape[2])
-        x = ops.cat_channels([x, low_level_features])
+        x = ops.upsample_concat(x, low_level_features)       # x4 bilinear written straight into the concat buffer
         x = _conv_bn_relu(x, self.cat_conv, 0)
         x = ops.dropout(x, self.cat_conv[3].p, self.training)
         x = _conv_bn_relu(x, self.cat_conv, 4)

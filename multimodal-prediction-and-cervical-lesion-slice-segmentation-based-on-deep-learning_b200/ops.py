@@ -431,6 +431,21 @@ class UpsampleBilinear(Function):
         return get_backend().upsample_bwd(dy.contiguous(), *ctx.in_hw), None, None
 
 
+class UpsampleConcat(Function):
+    """cat([F.interpolate(x, size of tail, bilinear, align_corners=True), tail], channels) - the decoder's junction of the
+    ASPP output with the low-level feature (deeplabv3_plus.py:184-185) - with the upsample writing / its gradient reading
+    the concat buffer directly (no upsampled intermediate, no slice copy of the big half in backward)."""
+
+    @staticmethod
+    def forward(ctx, x, tail):
+        ctx.in_hw, ctx.c = (x.shape[1], x.shape[2]), x.shape[3]
+        return get_backend().upsample_concat(x.contiguous(), tail.contiguous())
+
+    @staticmethod
+    def backward(ctx, dy):
+        return get_backend().upsample_concat_bwd(dy.contiguous(), ctx.c, ctx.in_hw[0], ctx.in_hw[1])
+
+
 class UpsampleToNCHW(Function):
     """Final F.interpolate of the logits fused with the NHWC -> NCHW fp32 conversion."""
 
@@ -606,6 +621,17 @@ def upsample_bilinear(x, ho, wo):
     if x.shape[1] == ho and x.shape[2] == wo:
         return x
     return UpsampleBilinear.apply(x, ho, wo)
+
+
+_NO_UPCAT = os.environ.get("CERVIX_UPSAMPLE_CONCAT", "1") == "0"      # A/B switch
+
+
+def upsample_concat(x, tail):
+    B = get_backend()
+    vec = 4 if x.dtype == torch.float32 else 8
+    if not hasattr(B, "upsample_concat") or x.shape[3] % vec or tail.shape[3] % vec or _NO_UPCAT:
+        return cat_channels([upsample_bilinear(x, tail.shape[1], tail.shape[2]), tail])
+    return UpsampleConcat.apply(x, tail)
 
 
 def upsample_to_nchw(x, ho, wo):

@@ -115,6 +115,12 @@ class EmuBackend:
             return out
         return ti, tl
 
+    def upsample_concat(self, x, tail):
+        return torch.cat([self.upsample_fwd(x, tail.shape[1], tail.shape[2]), tail], dim=3).contiguous()
+
+    def upsample_concat_bwd(self, dy, c, hi, wi):
+        return self.upsample_bwd(dy[..., :c].contiguous(), hi, wi), dy[..., c:].contiguous()
+
     def to_nchw(self, x):
         return _nchw(x).contiguous()
 

@@ -195,6 +195,14 @@ def test_small_ops(B, dtype):
     check(B.upsample_bwd(dyu, 6, 10), EMU.upsample_bwd(dyu, 6, 10), tol(dtype), "up bwd")
     dyo = rnd((2, 21, 37, 48), dtype, 5)
     check(B.upsample_bwd(dyo, 6, 10), EMU.upsample_bwd(dyo, 6, 10), tol(dtype), "up bwd odd")
+    # the decoder junction: upsample written into / its gradient read from a channel slice of the concat buffer -
+    # bit-identical to upsample followed by cat (same arithmetic, different addresses)
+    tail = rnd((2, 24, 40, 24), dtype, 8)
+    cat = B.upsample_concat(x, tail)
+    assert torch.equal(cat, torch.cat([B.upsample_fwd(x, 24, 40), tail], dim=3))
+    dcat = rnd((2, 24, 40, 72), dtype, 9)
+    dxc, dtail = B.upsample_concat_bwd(dcat, 48, 6, 10)
+    assert torch.equal(dxc, B.upsample_bwd(dcat[..., :48].contiguous(), 6, 10)) and torch.equal(dtail, dcat[..., 48:])
     z = rnd((2, 6, 10, 5), dtype, 6)
     check(B.upsample_to_nchw_fwd(z, 24, 40), EMU.upsample_to_nchw_fwd(z, 24, 40), 1e-5 if dtype == torch.float32 else 1e-5, "to_nchw fwd")
     dz = rnd((2, 5, 24, 40), torch.float32, 7)
