@@ -170,11 +170,15 @@ CVX_API int cvx_upsample_to_nchw_bwd(const float* dy, void* dx, int n, int hi, i
 CVX_API int cvx_maxpool3x3s2_fwd(const void* x, void* y, int n, int h, int w, int c, int dtype, void* stream);
 CVX_API int cvx_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int c,
                          int dtype, void* stream);
-/* nn.Dropout: mask byte per element, y = x * mask / (1-p) (deeplabv3_plus.py:159,165) */
-/* step_dev (nullable device int): mixed into the seed so that a CUDA-graph replay draws a new mask every step */
+/* nn.Dropout (deeplabv3_plus.py:159,165): y = keep ? x / (1-p) : 0, where element i is kept iff a counter-based hash of
+ * (seed, *step_dev, i) clears the threshold p * 2^32.  mask (nullable): one byte per element, written when given.
+ * step_dev (nullable device int): mixed into the seed so that a CUDA-graph replay draws a new mask every step.
+ * cvx_dropout_bwd_seeded recomputes the decisions from the same (seed, step_dev) instead of reading a stored mask. */
 CVX_API int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, const int* step_dev,
                     int dtype, void* stream);
 CVX_API int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream);
+CVX_API int cvx_dropout_bwd_seeded(const void* dy, void* dx, int64_t n, float p, uint64_t seed, const int* step_dev, int dtype,
+                                   void* stream);
 
 /* ---- segmentation objective (nets/deeplabv3_training.py:9-56, utils/utils_metrics.py:13-35) */
 /* One pass over fp32 NCHW logits [n,c,h,w] and int64 targets [n,h,w] (value c = ignore).

@@ -95,6 +95,7 @@ PROTOTYPES = {
     "cvx_maxpool3x3s2_bwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "cvx_dropout_fwd": [_P, _P, _P, _L, _F, C.c_uint64, _P, _I, _P],
     "cvx_dropout_bwd": [_P, _P, _P, _L, _F, _I, _P],
+    "cvx_dropout_bwd_seeded": [_P, _P, _L, _F, C.c_uint64, _P, _I, _P],
     "cvx_seg_loss_stats": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
     "cvx_seg_loss_finalize": [_P, _P, _I, _F, _F, _P],
     "cvx_seg_loss_grad": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P],

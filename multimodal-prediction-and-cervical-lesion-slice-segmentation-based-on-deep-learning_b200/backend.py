@@ -432,13 +432,21 @@ class CudaBackend:
               "cvx_upsample_to_nchw_bwd")
         return dx
 
-    def dropout_fwd(self, x, p: float, seed: int, step_dev=None):
+    def dropout_fwd(self, x, p: float, seed: int, step_dev=None, want_mask: bool = True):
         self._chk(x, step_dev)
         y = torch.empty_like(x)
-        mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+        mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_mask else None
         check(self.lib.cvx_dropout_fwd(_p(x), _p(y), _p(mask), x.numel(), float(p), int(seed) & (2 ** 64 - 1),
                                        _p(step_dev), _dt(x), self._stream()), "cvx_dropout_fwd")
         return y, mask
+
+    def dropout_bwd_seeded(self, dy, p: float, seed: int, step_dev=None):
+        """Gradient of dropout_fwd(..., seed, step_dev) with the keep decisions recomputed (no stored mask)."""
+        self._chk(dy, step_dev)
+        dx = torch.empty_like(dy)
+        check(self.lib.cvx_dropout_bwd_seeded(_p(dy), _p(dx), dy.numel(), float(p), int(seed) & (2 ** 64 - 1), _p(step_dev),
+                                              _dt(dy), self._stream()), "cvx_dropout_bwd_seeded")
+        return dx
 
     def dropout_bwd(self, dy, mask, p: float):
         self._chk(dy, mask)

@@ -395,19 +395,48 @@ __device__ __forceinline__ uint32_t mix64(uint64_t z) {
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 
+__device__ __forceinline__ uint32_t dropout_thresh(float p) {
+  return (uint32_t)((double)p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)p * 4294967296.0);
+}
+// element i of the tensor is kept iff the counter-based hash of (seed, step, i) clears the threshold: the backward pass
+// recomputes the decision instead of reading a stored mask (mask == nullptr: none is written - 1 byte per element of
+// traffic saved in each direction)
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, int64_t i, uint32_t thresh) {
+  return mix64(seed * 0x100000001b3ull + (uint64_t)i) >= thresh;
+}
+
+// FWD: y = keep ? x / (1 - p) : 0  (writes the mask when one is given); !FWD: the same map applied to dy.
+// One 16-byte vector per thread and trip; the scalar tail (n % VEC) is handled by the first threads.
 template <typename T>
-__global__ void dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
-                                   float p, uint64_t seed, const int* __restrict__ step_dev) {
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ mask,
+                                                      int64_t n, float p, uint64_t seed, const int* __restrict__ step_dev) {
+  constexpr int VEC = Elem<T>::kVec;
   pdl_trigger();
   pdl_wait();
   if (step_dev) seed += 0x9e3779b97f4a7c15ull * (uint64_t)(*step_dev);  // per-step stream under CUDA-graph replay
   const float keep_scale = 1.f / (1.f - p);
-  const uint32_t thresh = (uint32_t)((double)p * 4294967296.0 > 4294967295.0 ? 4294967295.0 : (double)p * 4294967296.0);
-  CVX_GRID_STRIDE(i, n) {
-    const uint32_t r = mix64(seed * 0x100000001b3ull + (uint64_t)i);
-    const uint8_t keep = r >= thresh ? 1 : 0;
-    mask[i] = keep;
-    Elem<T>::st(y + i, keep ? Elem<T>::ld(x + i) * keep_scale : 0.f);
+  const uint32_t thresh = dropout_thresh(p);
+  const int64_t nvec = n / VEC;
+  CVX_GRID_STRIDE(v, nvec) {
+    Vec<T> a;
+    a.load(x + v * VEC);
+    uint8_t m[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      m[k] = dropout_keep(seed, v * VEC + k, thresh) ? 1 : 0;
+      a.v[k] = m[k] ? a.v[k] * keep_scale : 0.f;
+    }
+    a.store(y + v * VEC);
+    if (mask) {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) mask[v * VEC + k] = m[k];
+    }
+  }
+  const int64_t t0 = nvec * VEC + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t0 < n) {
+    const bool keep = dropout_keep(seed, t0, thresh);
+    if (mask) mask[t0] = keep ? 1 : 0;
+    Elem<T>::st(y + t0, keep ? Elem<T>::ld(x + t0) * keep_scale : 0.f);
   }
 }
 
@@ -587,12 +616,25 @@ int cvx_maxpool3x3s2_bwd(const void* x, const void* y, const void* dy, void* dx,
   return CVX_OK;
 }
 
-int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, const int* step_dev,
-                    int dtype, void* stream) {
-  CVX_CHECK_ARG(x && y && mask && n > 0 && p >= 0.f && p < 1.f, "dropout_fwd: bad arguments");
-  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(dropout_fwd_kernel<T>, dim3(ew_grid(n)), dim3(256), 0, as_stream(stream), (const T*)x, (T*)y, mask, n, p, seed, step_dev)));
+static int dropout_launch(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, const int* step_dev, int dtype,
+                          void* stream, const char* who) {
+  CVX_CHECK_ARG(x && y && n > 0 && p >= 0.f && p < 1.f, "%s: bad arguments", who);
+  CVX_CHECK_ARG((uintptr_t)x % 16 == 0 && (uintptr_t)y % 16 == 0, "%s: pointers must be 16-byte aligned", who);
+  const int vec = dtype == CVX_F32 ? 4 : 8;
+  const int64_t work = n / vec > 256 ? n / vec : 256;
+  CVX_DISPATCH_DTYPE(dtype, T, (launch_pdl(dropout_kernel<T>, dim3(ew_grid(work)), dim3(256), 0, as_stream(stream), (const T*)x, (T*)y, mask, n, p, seed, step_dev)));
   CVX_LAUNCH_OK();
   return CVX_OK;
+}
+
+int cvx_dropout_fwd(const void* x, void* y, uint8_t* mask, int64_t n, float p, uint64_t seed, const int* step_dev,
+                    int dtype, void* stream) {
+  return dropout_launch(x, y, mask, n, p, seed, step_dev, dtype, stream, "dropout_fwd");
+}
+
+int cvx_dropout_bwd_seeded(const void* dy, void* dx, int64_t n, float p, uint64_t seed, const int* step_dev, int dtype,
+                           void* stream) {
+  return dropout_launch(dy, dx, nullptr, n, p, seed, step_dev, dtype, stream, "dropout_bwd_seeded");
 }
 
 int cvx_dropout_bwd(const void* dy, const uint8_t* mask, void* dx, int64_t n, float p, int dtype, void* stream) {

@@ -459,18 +459,27 @@ class UpsampleToNCHW(Function):
         return get_backend().upsample_to_nchw_bwd(dy.contiguous().float(), ctx.in_hw[0], ctx.in_hw[1], ctx.dtype), None, None
 
 
+_MASKED_DROPOUT = os.environ.get("CERVIX_DROPOUT_MASK", "0") == "1"     # A/B switch: keep the stored byte mask
+
+
 class Dropout(Function):
     @staticmethod
     def forward(ctx, x, p, seed):
-        y, mask = get_backend().dropout_fwd(x.contiguous(), p, seed, _STEP_DEV[0])
+        B = get_backend()
+        ctx.p, ctx.seed, ctx.step_dev = p, seed, _STEP_DEV[0]
+        ctx.seeded = hasattr(B, "dropout_bwd_seeded") and not _MASKED_DROPOUT   # decisions = f(seed, step, index)
+        y, mask = B.dropout_fwd(x.contiguous(), p, seed, _STEP_DEV[0], want_mask=not ctx.seeded) if ctx.seeded \
+            else B.dropout_fwd(x.contiguous(), p, seed, _STEP_DEV[0])
         ctx.save_for_backward(mask)
-        ctx.p = p
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        B = get_backend()
+        if ctx.seeded:       # the step counter is read on the device: same value as in this step's forward
+            return B.dropout_bwd_seeded(dy.contiguous(), ctx.p, ctx.seed, ctx.step_dev), None, None
         (mask,) = ctx.saved_tensors
-        return get_backend().dropout_bwd(dy.contiguous(), mask, ctx.p), None, None
+        return B.dropout_bwd(dy.contiguous(), mask, ctx.p), None, None
 
 
 class SegLoss(Function):

@@ -240,6 +240,16 @@ def test_dropout(B, dtype):
     assert not torch.equal(mask, mask3)
     dy = rnd(x.shape, dtype, 2)
     check(B.dropout_bwd(dy, mask, 0.5), EMU.dropout_bwd(dy, mask, 0.5), 4e-3)
+    # the seeded backward recomputes the keep decisions: identical to the masked one; no mask is written on request
+    assert torch.equal(B.dropout_bwd_seeded(dy, 0.5, 1234), B.dropout_bwd(dy, mask, 0.5))
+    y_nomask, none = B.dropout_fwd(x, 0.5, 1234, None, want_mask=False)
+    assert none is None and torch.equal(y_nomask, y)
+    step = torch.tensor([3], dtype=torch.int32, device="cuda")
+    ys, ms = B.dropout_fwd(x, 0.5, 1234, step)
+    assert not torch.equal(ms, mask) and torch.equal(B.dropout_bwd_seeded(dy, 0.5, 1234, step), B.dropout_bwd(dy, ms, 0.5))
+    odd = x.reshape(-1)[:1003].contiguous()          # ragged length: vector body + scalar tail
+    yo, mo = B.dropout_fwd(odd, 0.5, 99)
+    assert torch.equal(yo, (odd.float() * mo / 0.5).to(odd.dtype)) and 0.4 < float(mo.float().mean()) < 0.6
     _, m1 = B.dropout_fwd(x, 0.1, 7)
     assert abs(float(m1.float().mean()) - 0.9) < 0.01
 
