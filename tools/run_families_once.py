@@ -84,7 +84,30 @@ timed("conv_fwd tc 3x3 304->256 @128 (cat_conv.0)", lambda: B.conv_fwd(x3, wp3, 
       2.0 * N * 128 * 128 * 256 * 304 * 9)
 del x3, wp3
 timed("upsample_fwd x4 (32^2 -> 128^2, 256 ch)", lambda: B.upsample_fwd(x[:, :32, :32].contiguous(), 128, 128), T + T / 16)
-del x, dy
+low48 = bf(N, 128, 128, 48)
+xs32 = x[:, :32, :32].contiguous()
+timed("upsample_concat (x4 into the 304-channel concat buffer)", lambda: B.upsample_concat(xs32, low48), T + T / 16 + 2 * low48.numel() * 2)
+step_dev = torch.ones(1, dtype=torch.int32, device=dev)
+timed("dropout_fwd, no stored mask (decoder, 256 ch @128^2)", lambda: B.dropout_fwd(x, 0.5, 1234, step_dev, want_mask=False), 2 * T)
+timed("dropout_bwd_seeded", lambda: B.dropout_bwd_seeded(dy, 0.5, 1234, step_dev), 2 * T)
+g2048 = bf(N, 1, 1, 2048)
+timed("spatial_broadcast (ASPP pooled branch backward, 2048 ch @32^2)", lambda: B.spatial_broadcast(g2048, 32, 32, 1.0 / 1024), N * 32 * 32 * 2048 * 2)
+del x, dy, low48, xs32
+# ---- training augmentation: one batch of 32 VOC-sized decoded images onto 512 x 512 canvases (four launches)
+import numpy as np  # noqa: E402
+from cervix_b200.utils import dataloader as D  # noqa: E402
+_rng = np.random.RandomState(0)
+_items = []
+np.random.seed(0)
+for _i in range(N):
+    _ih, _iw = (375, 500) if _i % 2 == 0 else (500, 375)
+    _items.append((_rng.randint(0, 256, (_ih, _iw, 3)).astype(np.uint8), _rng.randint(0, 6, (_ih, _iw)).astype(np.uint8),
+                   D.draw_params(_iw, _ih, (512, 512))))
+_plan = D.pack_batch(_items, (512, 512))
+_aug = D.DeviceAugmenter(dev)
+_blobs = _aug.upload(_plan, non_blocking=False)
+timed("augment batch (resize_rows + compose + blur5 + rotate_jitter)", lambda: _aug.run(_plan, _blobs),
+      int(_plan.src.numel()) + N * 512 * 512 * 4)
 # ---- strided / dilated depthwise (entry flow stride 2, exit flow dilation 2)
 g2 = ConvGeom(N, 256, 256, 128, 128, 3, 3, 2, 1, 1)
 x2, w2 = bf(N, 256, 256, 128), torch.randn(9, 128, device=dev)
