@@ -313,3 +313,25 @@ def test_gpu_fit_one_epoch_takes_the_drop_in_dataloader(tmp_path):
     lab = np.asarray(Image.open(tmp_path / "VOC2007" / "SegmentationClass" / "im00.png"))
     wi, wl = A.apply_params(src, lab, (64, 64), A.letterbox_params(src.shape[1], src.shape[0], (64, 64)))
     assert np.array_equal(imgs[0].cpu().numpy(), wi) and np.array_equal(labs[0].cpu().numpy(), wl)
+
+
+def test_fit_one_epoch_loader_hooks_without_a_device():
+    """Host logic of the drop-in loader inside utils_fit: a DataLoader built with the drop-in collate function is
+    recognised (and refused loudly when there is no CUDA device - the augmentation has no CPU fallback), any other loader
+    passes through; uint8 batches with implicit one-hot labels are finished on whatever device they live on."""
+    from torch.utils.data import DataLoader
+    from cervix_b200.utils import dataloader as D
+    from cervix_b200.utils import utils_fit as F
+    ds = D.DeeplabDataset(["a"], (32, 32), 5, True, "/nonexistent")
+    ours = DataLoader(ds, batch_size=1, collate_fn=D.deeplab_dataset_collate)
+    other = [(torch.zeros(1, 3, 8, 8), torch.zeros(1, 8, 8, dtype=torch.long), torch.zeros(1, 8, 8, 6))]
+    assert F._wrap_loader(other, False, 0) is other
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            F._wrap_loader(ours, True, 0)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            F._wrap_loader(ours, False, 0)
+    pngs = torch.tensor([[[0, 4, 5, 255]]], dtype=torch.uint8)
+    imgs, p, lab, w = F._to_device((torch.zeros(1, 1, 4, 3, dtype=torch.uint8), pngs, None), np.ones(5, np.float32), False, 0, 5)
+    assert p.dtype == torch.int64 and p.tolist() == [[[0, 4, 5, 5]]]
+    assert lab.shape == (1, 1, 4, 6) and lab.argmax(-1).tolist() == [[[0, 4, 5, 5]]]
