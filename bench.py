@@ -543,6 +543,11 @@ def kernel_rooflines(batch: int, peaks):
     out["mid_pw_fwd"] = {"kernel": "conv_tc_fwd_2cta_kernel<1, 2> (middle-flow pointwise 728->728 @32x32, batch %d, BN statistics "
                                    "epilogue; 51 launches/step)" % batch, "ms_per_launch": ms_f, "flops_per_launch": flops,
                          "achieved": flops / (ms_f * 1e-3) / 1e12, "peak": peaks["tf_burst"], "unit": "TFLOP/s"}
+    # DRAM traffic of one launch from the committed ncu --set full capture of this shape at batch 32
+    # (profiles/r02_ncu_summary_v2.txt: dram__bytes_read.sum 48.8 MB + dram__bytes_write.sum 7.8 MB; the 47.7 MB output is
+    # still in L2 when the kernel ends)
+    out["mid_pw_fwd"]["traffic"] = 56.6e6 if batch == 32 else None
+    out["mid_pw_fwd"]["traffic_source"] = "profiles/r02_ncu_summary_v2.txt (ncu --set full, batch 32): DRAM read 48.8 MB + write 7.8 MB per launch"
     out["mid_pw_wgrad"] = {"kernel": "conv_tc_wgrad_2cta_kernel (same shape; 51 launches/step)", "ms_per_launch": ms_w,
                            "flops_per_launch": flops, "achieved": flops / (ms_w * 1e-3) / 1e12, "peak": peaks["tf_burst"],
                            "unit": "TFLOP/s"}
@@ -568,7 +573,10 @@ def kernel_rooflines(batch: int, peaks):
                                       "data gradient + weight gradient + previous BatchNorm's backward sums; 37 launches/step)" % batch,
            "achieved": nbytes / (ms_d * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s", "bytes_per_launch": nbytes,
            "ms_per_launch": ms_d, "peak_source": peaks["source"] + " HBM copy bandwidth",
-           "traffic": None, "traffic_source": "see profiles/ (ncu --set full of this launch)"}
+           "traffic": 113.9e6 if batch == 32 else None,
+           "traffic_source": "profiles/r02_ncu_summary_v2.txt (ncu --set full of this launch at batch 32): DRAM read 95.5 MB + write "
+                             "18.4 MB - below the algorithmic 143 MB because the gradient it consumes and most of what it "
+                             "writes stay in L2"}
     hbm["frac"] = hbm["achieved"] / hbm["peak"]
     return out, hbm
 
