@@ -153,3 +153,45 @@ def test_fusion_two_rank_gloo_allreduce_matches_manual_sum(tmp_path):
         backend.set_backend(prev)
     assert float((r0["grad"] - total).abs().max()) <= 1e-5 * float(total.abs().max())
     assert float((r0["data"] - want).abs().max()) <= 2e-6
+
+
+def test_split_backward_plan_and_eager_phases_match_the_single_backward():
+    """Host logic of the two-graph data-parallel step (SegTrainer.capture_split) without a GPU: the plan puts Xception's
+    entry flow - and nothing else - before the cut, declines models without a cut or with frozen parameters, and the two
+    phases run eagerly (forward + late backward through the cut proxies, then the entry-flow backward from the gradients
+    left at the cuts) reproduce the gradients of one ordinary backward on the emulated ABI."""
+    prev = backend.set_backend(EmuBackend())
+    try:
+        torch.manual_seed(1)
+        model = DeepLab(5, "xception", False, 16).set_compute_dtype(torch.float32).train()
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        tr = SegTrainer(model, lr=0.0, optimizer="sgd", cls_weights=CLS_W)
+        names = [n for n, _ in model.named_parameters()]
+        early, late = tr._split_plan()
+        assert early == list(range(len(early))) and late == list(range(len(early), len(names)))
+        assert all(names[i].split(".")[1] in SegTrainer._ENTRY_MODULES for i in early)
+        assert names[late[0]].startswith("backbone.block4.") and not any(n.startswith("backbone.block3.") for n in names[late[0]:])
+        assert sum(tr.flat.params[i].numel() for i in early) < 0.1 * tr.flat.numel
+        g = torch.Generator().manual_seed(2)
+        imgs, pngs = torch.rand(2, 3, 32, 32, generator=g), torch.randint(0, 6, (2, 32, 32), generator=g)
+        tr._forward_backward(imgs, pngs, None)
+        want = tr.flat.grad.clone()
+        tr.flat.detach_grads()
+        tr._phase_a(imgs, pngs, None, late)
+        late_grads = tr._split_late_grads
+        early_grads = tr._phase_b(early)
+        got = torch.zeros_like(want)
+        for idx, grads in ((late, late_grads), (early, early_grads)):
+            for i, gr in zip(idx, grads):
+                if gr is not None:
+                    o = tr.flat.offsets[i]
+                    got[o:o + gr.numel()] = gr.reshape(-1)
+        assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+        # a frozen parameter or a backbone without a cut: no plan (the caller keeps the one-graph step)
+        next(model.backbone.parameters()).requires_grad_(False)
+        assert SegTrainer(model, lr=0.0, optimizer="sgd", cls_weights=CLS_W)._split_plan() is None
+        assert SegTrainer(_model(), lr=0.0, optimizer="sgd", cls_weights=CLS_W)._split_plan() is None
+    finally:
+        backend.set_backend(prev)
