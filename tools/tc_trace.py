@@ -24,15 +24,16 @@ def trace(cin, cout, stats, side, cold=True):
     wp = B.pack_weight(wt, torch.bfloat16, False)
     bias = torch.randn(cout, device="cuda")
     sd = torch.randn(N, 32, 32, cout, device="cuda").bfloat16() if side else None
+    ss = torch.ones(cout, device="cuda") if side else None      # the side input comes with a per-channel scale
     for _ in range(3):
-        B.conv_fwd_ex(x, wp, bias, g, sd, None, stats)
+        B.conv_fwd_ex(x, wp, bias, g, sd, ss, stats)
     if cold:
         flush.zero_()
     torch.cuda.synchronize()
     B.lib.cvx_debug_tc_trace(1, None)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    B.conv_fwd_ex(x, wp, bias, g, sd, None, stats)
+    B.conv_fwd_ex(x, wp, bias, g, sd, ss, stats)
     e1.record()
     buf = (C.c_ulonglong * 128)()
     B.lib.cvx_debug_tc_trace(0, buf)
